@@ -1,0 +1,180 @@
+/*
+ * csolve_b200.h -- C ABI of the B200-native csolve search hot path.
+ *
+ * Everything a host (the reference's C front end, or any FFI) binds is
+ * declared here: plain pointers and sizes, no C++/torch types.
+ *
+ * The seam this library replaces is
+ *     void solve(size_t size, struct env_t *env, struct constr_t *constr)
+ * (reference src/csolve.h:395, defined src/csolve.c:398, sole caller
+ * src/parser.y:86) together with everything solve() drives:
+ * propagate_clauses() (src/csolve.h:362, src/propagate.c:488-538), the
+ * per-type eval_*()/propagate_*() contractors (src/csolve.h:342-349), the
+ * objective_*() incumbent logic (src/csolve.h:380-392) and the branching
+ * strategy (src/csolve.h:425-435).
+ *
+ * The host hands over the root-normalised constraint network as a flat
+ * structure-of-arrays CSR (csolve_flat_model). integration/csolve_gpu_shim.c
+ * builds it from the reference's env_t/constr_t structures; the built-in front
+ * end (csolve_model_parse) builds it from csolve input text.
+ */
+#ifndef CSOLVE_B200_H
+#define CSOLVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSOLVE_B200_ABI_VERSION 1
+
+/* ---- error codes (all entry points return 0 on success) ------------------ */
+#define CSOLVE_OK                 0
+#define CSOLVE_ERR_INVALID       (-1)  /* bad argument / malformed model */
+#define CSOLVE_ERR_SYNTAX        (-2)  /* front end: lexer/parser error (src/csolve.h:513-516) */
+#define CSOLVE_ERR_INFEASIBLE    (-3)  /* front end: root phase failed ("INFEASIBLE PROBLEM", src/parser.y:71-73) */
+#define CSOLVE_ERR_UNBOUNDED     (-4)  /* front end: "unbounded variable: %s" (src/parser_support.c:249-251) */
+#define CSOLVE_ERR_UNSUPPORTED   (-5)  /* construct outside the device path (e.g. all_different nested in an operator) */
+#define CSOLVE_ERR_CUDA          (-6)  /* CUDA runtime error; csolve_last_error() has the text */
+#define CSOLVE_ERR_NO_DEVICE     (-7)  /* no CUDA device: there is NO CPU fallback */
+#define CSOLVE_ERR_CAPACITY      (-8)  /* a device pool (frontier, clause pool) overflowed */
+
+/* ---- node operators: the reference's enum operator_t (src/csolve.h:133-161),
+ *      TERM split into variable / constant leaves -------------------------- */
+#define CSOLVE_OP_VAR    0   /* TERM with env: l = variable index                       */
+#define CSOLVE_OP_CONST  1   /* TERM without env: l = lo, r = hi                        */
+#define CSOLVE_OP_EQ     2
+#define CSOLVE_OP_LT     3
+#define CSOLVE_OP_NEG    4
+#define CSOLVE_OP_ADD    5
+#define CSOLVE_OP_MUL    6
+#define CSOLVE_OP_NOT    7
+#define CSOLVE_OP_AND    8
+#define CSOLVE_OP_OR     9
+
+/* objective kinds, numbered like enum objective_t (src/csolve.h:241-247) */
+#define CSOLVE_OBJ_ANY 0
+#define CSOLVE_OBJ_ALL 1
+#define CSOLVE_OBJ_MIN 2
+#define CSOLVE_OBJ_MAX 3
+
+/* variable orders, numbered like enum order_t (src/csolve.h:249-256) */
+#define CSOLVE_ORDER_NONE            0  /* static: by initial priority, ties by index */
+#define CSOLVE_ORDER_SMALLEST_DOMAIN 1
+#define CSOLVE_ORDER_LARGEST_DOMAIN  2
+#define CSOLVE_ORDER_SMALLEST_VALUE  3
+#define CSOLVE_ORDER_LARGEST_VALUE   4
+
+/*
+ * Flat model: the root-normalised constraint network after the reference's
+ * root phase (src/parser.y:55-92), flattened.
+ *
+ * clause k   = one wand_expr_t that is not itself a WAND (a top-level element
+ *              of the root WAND or an element of a nested all_different WAND,
+ *              src/parser_support.c:350-361), in traversal order. Elements that
+ *              are exactly the constant TERM [1,1] are dropped.
+ * nodes      = the clause's expression tree in post-order (children before the
+ *              parent, left subtree before right subtree); the nodes of clause
+ *              k are clause_first[k] .. clause_first[k+1]-1 and the root is the
+ *              last one. node_l/node_r hold GLOBAL node indices for operators.
+ * watch list = for variable v, the clauses that mention v, in the order
+ *              clauses_init() appends them (src/parser_support.c:339-396);
+ *              variables fixed at root have an empty list (parser_support.c:341).
+ */
+typedef struct csolve_flat_model {
+  int32_t n_vars;
+  int32_t n_nodes;
+  int32_t n_clauses;
+  int32_t n_watch;
+  int32_t objective;           /* CSOLVE_OBJ_* */
+  int32_t obj_var;             /* index of "<obj>" (src/parser.y:120,126) or -1 */
+  const uint8_t *node_op;      /* [n_nodes] CSOLVE_OP_* */
+  const int32_t *node_l;       /* [n_nodes] */
+  const int32_t *node_r;       /* [n_nodes] (-1 for unary operators) */
+  const int32_t *clause_first; /* [n_clauses + 1] */
+  const int32_t *watch_ptr;    /* [n_vars + 1] */
+  const int32_t *watch_idx;    /* [n_watch] clause indices */
+  const int32_t *var_lo;       /* [n_vars] root domain (finite: src/parser_support.c:249) */
+  const int32_t *var_hi;       /* [n_vars] */
+  const int64_t *var_prio;     /* [n_vars] parse-time weights (env_t.prio, src/csolve.h:237) */
+  const char *const *var_name; /* [n_vars] env_t.key; may be NULL */
+} csolve_flat_model;
+
+/* ---- built-in front end --------------------------------------------------
+ * Parses csolve input text (grammar of src/parser.y, tokens of src/lexer.l),
+ * runs the root phase (propagate / normalize / propagate, src/parser.y:55-69)
+ * and flattens. CPU code; it is the host side of the boundary, not the hot path.
+ */
+typedef struct csolve_model csolve_model;
+
+typedef struct csolve_front_options {
+  int32_t compute_weights;     /* -w (src/main.c:127-130), default 1 */
+  int32_t objective_override;  /* -1 keep the file's objective; CSOLVE_OBJ_ANY/ALL replace an ANY/ALL header */
+} csolve_front_options;
+
+int csolve_model_parse(const char *text, size_t len, const csolve_front_options *opt,
+                       csolve_model **out);
+const csolve_flat_model *csolve_model_flat(const csolve_model *m);
+void csolve_model_free(csolve_model *m);
+
+/* ---- device ---------------------------------------------------------------*/
+typedef struct csolve_gpu_problem csolve_gpu_problem;
+
+typedef struct csolve_gpu_config {
+  int32_t device;              /* CUDA device ordinal */
+} csolve_gpu_config;
+
+typedef struct csolve_solve_options {
+  int32_t order;               /* CSOLVE_ORDER_* (-o, src/main.c:96-100) */
+  int32_t part_rank;           /* this process searches root-frontier items i with i % part_count == part_rank */
+  int32_t part_count;          /* number of partitions (GPUs); 1 = whole tree */
+  int32_t split_target;        /* expand the root until at least this many open sub-trees exist (0 = default) */
+  int32_t max_solutions;       /* capacity of the solution buffer (assignments kept for printing); 0 = none */
+  int32_t time_limit_ms;       /* -t; 0 = off */
+  int32_t slice_ms;            /* length of one persistent-kernel time slice; 0 = default */
+  int32_t reserved;
+} csolve_solve_options;
+
+typedef struct csolve_gpu_result {
+  uint64_t solutions;          /* ALL: solutions counted; ANY: 0/1; MIN/MAX: improving incumbents seen */
+  uint64_t nodes;              /* search nodes = the reference's CALLS (src/csolve.c:65-68) */
+  uint64_t cuts;               /* failed nodes = CUTS (src/csolve.c:256) */
+  uint64_t props;              /* domain narrowings = PROPS (src/propagate.c:78) */
+  uint64_t clause_visits;      /* clause contractions executed */
+  int32_t  best;               /* MIN/MAX: best objective value (objective_best(), src/objective.c:133) */
+  int32_t  has_solution;       /* 0 => "NO SOLUTION FOUND" (src/csolve.c:184-186) */
+  int32_t  timed_out;          /* "TIMEOUT" (src/csolve.c:181-183) */
+  int32_t  n_stored;           /* assignments stored in the solution buffer */
+  double   kernel_ms;          /* device time of the search kernels (CUDA events) */
+  double   expand_ms;          /* device time of root-frontier expansion */
+  uint64_t kernel_launches;    /* kernels launched by this call */
+} csolve_gpu_result;
+
+int  csolve_gpu_init(const csolve_gpu_config *cfg);
+void csolve_gpu_shutdown(void);
+int  csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **out);
+void csolve_gpu_unload(csolve_gpu_problem *p);
+
+/* Parity hook: B independent node transitions (src/csolve.c:448-457):
+ * for node b: domains dom_in[b] (n_vars pairs lo,hi), decision (var[b] := val[b]),
+ * incumbent best[b] (ignored for ANY/ALL) -> post-fixpoint domains dom_out[b] and failed[b].
+ * All pointers are HOST pointers; copies are part of the call. */
+int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes,
+                               const int32_t *dom_in, const int32_t *var, const int32_t *val,
+                               const int32_t *best, int32_t *dom_out, uint8_t *failed);
+
+/* Replacement for solve(): whole search on the device. */
+int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt, csolve_gpu_result *res);
+
+/* copy stored assignment i (n_vars values, variable order of the model) */
+int csolve_gpu_get_solution(csolve_gpu_problem *p, int32_t i, int32_t *values);
+
+const char *csolve_last_error(void);
+int csolve_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSOLVE_B200_H */
