@@ -1,0 +1,161 @@
+// compile.cpp -- host side: validate a csolve_flat_model and compile it into the
+// tables the kernels read (device_model.h): subtree ranges, per-clause records with
+// the specialised NOT(EQ) forms, the static branching order.
+#include "compile.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <numeric>
+
+namespace csolve_dev {
+
+namespace {
+
+// NOT(EQ(A, B)) operand of the form  var | const | ADD(var, const)
+struct Affine { bool ok; bool is_var; int var; int64_t k; };
+
+Affine affine_of(const csolve_flat_model &m, int n) {
+  Affine a{false, false, -1, 0};
+  int op = m.node_op[n];
+  if (op == CSOLVE_OP_VAR) { a.ok = true; a.is_var = true; a.var = m.node_l[n]; return a; }
+  if (op == CSOLVE_OP_CONST) {
+    if (m.node_l[n] != m.node_r[n]) return a;
+    a.ok = true; a.k = m.node_l[n]; return a;
+  }
+  if (op == CSOLVE_OP_ADD) {
+    int l = m.node_l[n], r = m.node_r[n];
+    if (m.node_op[l] == CSOLVE_OP_VAR && m.node_op[r] == CSOLVE_OP_CONST && m.node_l[r] == m.node_r[r]) {
+      a.ok = true; a.is_var = true; a.var = m.node_l[l]; a.k = m.node_l[r]; return a;
+    }
+  }
+  return a;
+}
+
+// every value involved stays far away from the +-infinity sentinels of src/arith.c
+const int64_t SAFE = (int64_t)1 << 29;
+bool small(int64_t v) { return v > -SAFE && v < SAFE; }
+
+}  // namespace
+
+int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &err) {
+  const int V = m.n_vars, C = m.n_clauses, N = m.n_nodes, W = m.n_watch;
+  if (V <= 0 || C < 0 || N < 0 || W < 0) { err = "invalid model sizes"; return CSOLVE_ERR_INVALID; }
+  if (m.objective < CSOLVE_OBJ_ANY || m.objective > CSOLVE_OBJ_MAX) { err = "invalid objective function type"; return CSOLVE_ERR_INVALID; }
+  const bool opt = m.objective == CSOLVE_OBJ_MIN || m.objective == CSOLVE_OBJ_MAX;
+  if (opt != (m.obj_var >= 0) || m.obj_var >= V) { err = "objective variable does not match objective kind"; return CSOLVE_ERR_INVALID; }
+  if (m.clause_first[0] != 0 || m.clause_first[C] != N) { err = "clause_first does not cover the nodes"; return CSOLVE_ERR_INVALID; }
+  if (m.watch_ptr[0] != 0 || m.watch_ptr[V] != W) { err = "watch_ptr does not cover the watch list"; return CSOLVE_ERR_INVALID; }
+  for (int v = 0; v < V; v++) {
+    if (m.watch_ptr[v + 1] < m.watch_ptr[v]) { err = "watch_ptr not monotone"; return CSOLVE_ERR_INVALID; }
+    if (m.var_lo[v] > m.var_hi[v] || m.var_lo[v] == INT32_MIN || m.var_hi[v] == INT32_MAX) {
+      err = "variable domain empty or unbounded"; return CSOLVE_ERR_INVALID;
+    }
+  }
+  for (int w = 0; w < W; w++) {
+    if (m.watch_idx[w] < 0 || m.watch_idx[w] >= C) { err = "watch_idx out of range"; return CSOLVE_ERR_INVALID; }
+  }
+
+  out.node_op.assign(m.node_op, m.node_op + N);
+  out.node_l.assign(m.node_l, m.node_l + N);
+  out.node_r.assign(m.node_r, m.node_r + N);
+  out.node_first.assign(N, 0);
+  out.watch_ptr.assign(m.watch_ptr, m.watch_ptr + V + 1);
+  out.watch_idx.assign(m.watch_idx, m.watch_idx + W);
+  out.clause.resize(C);
+  out.root_dom.resize(2 * (size_t)V);
+  for (int v = 0; v < V; v++) { out.root_dom[2 * v] = m.var_lo[v]; out.root_dom[2 * v + 1] = m.var_hi[v]; }
+
+  // subtree ranges + structure check (post-order, children inside the clause and before the parent)
+  std::vector<int> depth(N, 1);
+  int max_depth = 0, n_generic = 0;
+  for (int c = 0; c < C; c++) {
+    int b = m.clause_first[c], e = m.clause_first[c + 1];
+    if (e <= b) { err = "empty clause"; return CSOLVE_ERR_INVALID; }
+    for (int n = b; n < e; n++) {
+      int op = m.node_op[n];
+      if (op == CSOLVE_OP_VAR) {
+        if (m.node_l[n] < 0 || m.node_l[n] >= V) { err = "variable index out of range"; return CSOLVE_ERR_INVALID; }
+        out.node_first[n] = n;
+      } else if (op == CSOLVE_OP_CONST) {
+        if (m.node_l[n] != m.node_r[n]) { err = "anonymous terminal is not a single value"; return CSOLVE_ERR_UNSUPPORTED; }
+        out.node_first[n] = n;
+      } else if (op == CSOLVE_OP_NEG || op == CSOLVE_OP_NOT) {
+        int l = m.node_l[n];
+        if (l != n - 1 || l < b) { err = "malformed unary node"; return CSOLVE_ERR_INVALID; }
+        out.node_first[n] = out.node_first[l];
+        depth[n] = depth[l] + 1;
+      } else if (op >= CSOLVE_OP_EQ && op <= CSOLVE_OP_OR) {
+        int l = m.node_l[n], r = m.node_r[n];
+        if (r != n - 1 || r < b || l < b || l >= r || out.node_first[r] != l + 1) { err = "malformed binary node"; return CSOLVE_ERR_INVALID; }
+        out.node_first[n] = out.node_first[l];
+        depth[n] = std::max(depth[l], depth[r]) + 1;
+      } else {
+        err = "invalid operation"; return CSOLVE_ERR_INVALID;
+      }
+    }
+    if (out.node_first[e - 1] != b) { err = "clause is not a single tree"; return CSOLVE_ERR_INVALID; }
+    max_depth = std::max(max_depth, depth[e - 1]);
+
+    ClauseRec rec{CK_GENERIC, b, e - 1, 0};
+    // NOT(EQ(A, B)) with affine operands
+    int root = e - 1;
+    if (m.node_op[root] == CSOLVE_OP_NOT && m.node_op[m.node_l[root]] == CSOLVE_OP_EQ) {
+      int eq = m.node_l[root];
+      Affine A = affine_of(m, m.node_l[eq]), B = affine_of(m, m.node_r[eq]);
+      if (A.ok && B.ok && (A.is_var || B.is_var)) {
+        bool safe = small(A.k) && small(B.k);
+        if (A.is_var) safe = safe && small(m.var_lo[A.var]) && small(m.var_hi[A.var]);
+        if (B.is_var) safe = safe && small(m.var_lo[B.var]) && small(m.var_hi[B.var]);
+        if (safe) {
+          // a variable fixed at root never changes (src/parser_support.c:341): treat it as a constant
+          bool a_var = A.is_var && m.var_lo[A.var] != m.var_hi[A.var];
+          bool b_var = B.is_var && m.var_lo[B.var] != m.var_hi[B.var];
+          int64_t ak = A.k + ((A.is_var && !a_var) ? (int64_t)m.var_lo[A.var] : 0);
+          int64_t bk = B.k + ((B.is_var && !b_var) ? (int64_t)m.var_lo[B.var] : 0);
+          if (a_var && b_var) {
+            if (A.var != B.var) rec = ClauseRec{CK_NE_VV, A.var, B.var, (int32_t)(ak - bk)};
+          } else if (a_var) {
+            rec = ClauseRec{CK_NE_VC, A.var, 0, (int32_t)(bk - ak)};
+          } else if (b_var) {
+            rec = ClauseRec{CK_NE_VC, B.var, 0, (int32_t)(ak - bk)};
+          }
+        }
+      }
+    }
+    if (rec.kind == CK_GENERIC) n_generic++;
+    out.clause[c] = rec;
+  }
+  if (max_depth > MAX_DEPTH) { err = "clause expression too deep for the device interpreter"; return CSOLVE_ERR_UNSUPPORTED; }
+
+  // static branching order: priority descending, index ascending (the reference's heap with
+  // -o none -f true orders by env_t.prio only, src/strategy.c:79-121)
+  out.order.resize(V);
+  std::iota(out.order.begin(), out.order.end(), 0);
+  std::stable_sort(out.order.begin(), out.order.end(), [&](int a, int b) { return m.var_prio[a] > m.var_prio[b]; });
+  out.prio.resize(V);
+  for (int v = 0; v < V; v++) {
+    int64_t p = m.var_prio[v];
+    out.prio[v] = (int32_t)std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, p));
+  }
+
+  DevModel &h = out.host;
+  h.n_vars = V; h.n_clauses = C; h.n_nodes = N; h.n_watch = W;
+  h.objective = m.objective; h.obj_var = m.obj_var;
+  h.mask_words = (V + 31) / 32;
+  h.frame_words = frame_words(V, h.mask_words);
+  h.max_depth = max_depth;
+  h.n_generic = n_generic;
+  h.clause = out.clause.data();
+  h.watch_ptr = out.watch_ptr.data();
+  h.watch_idx = out.watch_idx.data();
+  h.node_op = out.node_op.data();
+  h.node_l = out.node_l.data();
+  h.node_r = out.node_r.data();
+  h.node_first = out.node_first.data();
+  h.order = out.order.data();
+  h.prio = out.prio.data();
+  h.root_dom = out.root_dom.data();
+  return CSOLVE_OK;
+}
+
+}  // namespace csolve_dev

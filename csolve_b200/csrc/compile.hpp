@@ -1,0 +1,20 @@
+// compile.hpp -- host-side compiled model (owner of the arrays DevModel points to).
+#pragma once
+#include <string>
+#include <vector>
+#include "csolve_b200.h"
+#include "device_model.h"
+
+namespace csolve_dev {
+
+struct CompiledModel {
+  DevModel host;                       // pointers into the vectors below (host addresses)
+  std::vector<ClauseRec> clause;
+  std::vector<int32_t> watch_ptr, watch_idx, node_l, node_r, node_first, order, prio, root_dom;
+  std::vector<uint8_t> node_op;
+};
+
+// returns CSOLVE_OK or an error code with a message in err
+int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &err);
+
+}  // namespace csolve_dev

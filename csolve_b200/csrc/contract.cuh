@@ -1,0 +1,378 @@
+// contract.cuh -- interval evaluation and clause contractors of the hot path.
+//
+// One lane contracts one clause. The functions are templated on a context
+// `Cx` that gives access to the search node's domain vector:
+//     Dom  cx.dom(v)                 current [lo,hi] of variable v
+//     void cx.raise_lo(v, lo)        lo := max(lo, .)   (device: shared-memory atomicMax)
+//     void cx.lower_hi(v, hi)        hi := min(hi, .)   (device: shared-memory atomicMin)
+// so the same code runs in the kernels (contexts over shared memory) and in
+// the host-side unit tests (contexts over a plain array).
+//
+// Semantics follow the reference exactly:
+//   arithmetic   src/arith.c:27-85
+//   evaluation   src/eval.c:27-277
+//   contraction  src/propagate.c:57-376   
+// with one structural difference: a narrowed variable is not propagated
+// recursively right away (src/propagate.c:44-54); it is put on the node's
+// worklist and its watchers run in a later round. The result is the same
+// greatest fixpoint.
+#pragma once
+#include <stdint.h>
+#include "csolve_b200.h"
+#include "device_model.h"
+
+#if defined(__CUDACC__)
+#define CSOLVE_HD __host__ __device__ __forceinline__
+#define CSOLVE_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CSOLVE_HD inline
+#define CSOLVE_HD_NOINLINE
+#endif
+
+namespace csolve_dev {
+
+static const int32_t DMIN = INT32_MIN;
+static const int32_t DMAX = INT32_MAX;
+
+struct Dom { int32_t lo, hi; };
+
+// ---- saturating arithmetic (src/arith.c) --------------------------------------
+CSOLVE_HD int32_t sneg(int32_t a) { return a == DMIN ? DMAX : (a == DMAX ? DMIN : -a); }
+CSOLVE_HD int32_t sadd(int32_t a, int32_t b) {
+  if (a == DMIN || b == DMIN) return DMIN;
+  if (a == DMAX || b == DMAX) return DMAX;
+  long long c = (long long)a + (long long)b;
+  return c < (long long)DMIN ? DMIN : (c > (long long)DMAX ? DMAX : (int32_t)c);
+}
+CSOLVE_HD int32_t smul(int32_t a, int32_t b) {
+  if (a == DMIN) return b < 0 ? DMAX : DMIN;
+  if (b == DMIN) return a < 0 ? DMAX : DMIN;
+  if (a == DMAX) return b < 0 ? DMIN : DMAX;
+  if (b == DMAX) return a < 0 ? DMIN : DMAX;
+  long long c = (long long)a * (long long)b;
+  return c < (long long)DMIN ? DMIN : (c > (long long)DMAX ? DMAX : (int32_t)c);
+}
+CSOLVE_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
+CSOLVE_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+
+// truthiness (src/csolve.h:57-67)
+CSOLVE_HD bool is_single(Dom v) { return v.lo == v.hi; }
+CSOLVE_HD bool is_true(Dom v) { return v.lo > 0 || v.hi < 0; }
+CSOLVE_HD bool is_false(Dom v) { return v.lo == 0 && v.hi == 0; }
+CSOLVE_HD Dom mk(int32_t lo, int32_t hi) { Dom d; d.lo = lo; d.hi = hi; return d; }
+
+// ---- evaluation: the subtree of a node is a contiguous post-order range, so
+//      bottom-up evaluation is one RPN pass (src/eval.c) ------------------------------
+CSOLVE_HD Dom eval_binary(int op, Dom a, Dom b) {
+  switch (op) {
+  case CSOLVE_OP_EQ:
+    if (a.lo == DMIN || a.hi == DMAX || b.lo == DMIN || b.hi == DMAX) return mk(0, 1);
+    if (a.hi == b.hi && a.lo == b.lo && a.hi == a.lo) return mk(1, 1);
+    if (a.hi < b.lo || a.lo > b.hi) return mk(0, 0);
+    return mk(0, 1);
+  case CSOLVE_OP_LT:
+    if (a.lo == DMIN || a.hi == DMAX || b.lo == DMIN || b.hi == DMAX) return mk(0, 1);
+    if (a.hi < b.lo) return mk(1, 1);
+    if (a.lo >= b.hi) return mk(0, 0);
+    return mk(0, 1);
+  case CSOLVE_OP_ADD:
+    return mk(sadd(a.lo, b.lo), sadd(a.hi, b.hi));
+  case CSOLVE_OP_MUL: {
+    int32_t ll = smul(a.lo, b.lo), lh = smul(a.lo, b.hi), hl = smul(a.hi, b.lo), hh = smul(a.hi, b.hi);
+    return mk(imin(imin(ll, lh), imin(hl, hh)), imax(imax(ll, lh), imax(hl, hh)));
+  }
+  case CSOLVE_OP_AND:
+    if (is_false(a) || is_false(b)) return mk(0, 0);
+    if (is_true(a) && is_true(b)) return mk(1, 1);
+    return mk(0, 1);
+  default: /* CSOLVE_OP_OR */
+    if (is_true(a) || is_true(b)) return mk(1, 1);
+    if (is_false(a) && is_false(b)) return mk(0, 0);
+    return mk(0, 1);
+  }
+}
+
+template <class Cx>
+CSOLVE_HD Dom eval_subtree(Cx &cx, const DevModel &m, int node) {
+  Dom st[MAX_DEPTH + 2];
+  int sp = 0;
+  for (int j = m.node_first[node]; j <= node; ++j) {
+    int op = m.node_op[j];
+    if (op == CSOLVE_OP_VAR) {
+      st[sp++] = cx.dom(m.node_l[j]);
+    } else if (op == CSOLVE_OP_CONST) {
+      st[sp++] = mk(m.node_l[j], m.node_r[j]);
+    } else if (op == CSOLVE_OP_NEG) {
+      Dom a = st[sp - 1];
+      st[sp - 1] = mk(sneg(a.hi), sneg(a.lo));
+    } else if (op == CSOLVE_OP_NOT) {
+      Dom a = st[sp - 1];
+      st[sp - 1] = is_true(a) ? mk(0, 0) : (is_false(a) ? mk(1, 1) : mk(0, 1));
+    } else {
+      Dom b = st[--sp];
+      Dom a = st[sp - 1];
+      st[sp - 1] = eval_binary(op, a, b);
+    }
+  }
+  return st[0];
+}
+
+// ---- TERM contractor on a variable (src/propagate.c:57-87) -----------------------
+// returns false on an empty intersection (PROP_ERROR)
+template <class Cx>
+CSOLVE_HD bool contract_var(Cx &cx, int v, int32_t lo, int32_t hi) {
+  Dom t = cx.dom(v);
+  if (t.lo > hi || t.hi < lo) return false;
+  bool ch = false;
+  if (lo > t.lo) { cx.raise_lo(v, lo); ch = true; }
+  if (hi < t.hi) { cx.lower_hi(v, hi); ch = true; }
+  if (ch) cx.count_prop();
+  return true;
+}
+
+// src/propagate.c:249-271; out: 0 nothing, 1 interval in [*lo,*hi], -1 error
+CSOLVE_HD int mul_target(Dom v, Dom cv, int32_t *lo, int32_t *hi) {
+  if (v.lo != DMIN && v.hi != DMIN && is_single(cv)) {
+    int32_t k = cv.lo;
+    if (((v.lo > 0 || v.hi < 0) && k == 0) ||
+        (is_single(v) && k != 0 && ((long long)v.lo % (long long)k) != 0)) {
+      return -1;
+    }
+    if (k != 0) {
+      int32_t a = (int32_t)((long long)v.lo / (long long)k);
+      int32_t b = (int32_t)((long long)v.hi / (long long)k);
+      *lo = imin(a, b);
+      *hi = imax(a, b);
+      return 1;
+    }
+  }
+  return 0;
+}
+
+struct PFrame { int32_t node, lo, hi, phase; };
+
+// ---- generic clause contractor: propagate VALUE(1) into the clause tree ------------
+// An explicit-stack rendering of the mutually recursive propagate_<op>() functions.
+// Frames on the stack are pending prop(node, [lo,hi]) calls; `phase` 1 means the right
+// child has already been handled and the left child is next (the reference always
+// contracts the right operand first, re-evaluates, then the left one).
+template <class Cx>
+CSOLVE_HD_NOINLINE bool contract_generic(Cx &cx, const DevModel &m, int root) {
+  PFrame st[MAX_DEPTH + 2];
+  int sp = 1;
+  st[0].node = root; st[0].lo = 1; st[0].hi = 1; st[0].phase = 0;
+  while (sp > 0) {
+    PFrame &f = st[sp - 1];
+    const int n = f.node;
+    const int op = m.node_op[n];
+    const Dom v = mk(f.lo, f.hi);
+    const int l = m.node_l[n], r = m.node_r[n];
+    switch (op) {
+    case CSOLVE_OP_VAR:
+      if (!contract_var(cx, l, v.lo, v.hi)) return false;
+      sp--;
+      break;
+    case CSOLVE_OP_CONST:
+      // anonymous terminal holding a single value: only the emptiness test matters
+      if (l > v.hi || r < v.lo) return false;
+      sp--;
+      break;
+    case CSOLVE_OP_NOT:  // src/propagate.c:289-301
+      if (is_true(v)) { f.node = l; f.lo = 0; f.hi = 0; f.phase = 0; }
+      else if (is_false(v)) { f.node = l; f.lo = 1; f.hi = 1; f.phase = 0; }
+      else sp--;
+      break;
+    case CSOLVE_OP_NEG:  // src/propagate.c:211-220
+      f.node = l; f.lo = sneg(v.hi); f.hi = sneg(v.lo); f.phase = 0;
+      break;
+    case CSOLVE_OP_EQ:   // src/propagate.c:90-152
+      if (is_true(v)) {
+        if (f.phase == 0) {
+          Dom lv = eval_subtree(cx, m, l);
+          f.phase = 1;
+          st[sp].node = r; st[sp].lo = lv.lo; st[sp].hi = lv.hi; st[sp].phase = 0; sp++;
+        } else {
+          Dom rv = eval_subtree(cx, m, r);
+          f.node = l; f.lo = rv.lo; f.hi = rv.hi; f.phase = 0;
+        }
+      } else if (is_false(v)) {
+        // both sides are evaluated up front; the left-side target only depends on those
+        Dom lv = eval_subtree(cx, m, l), rv = eval_subtree(cx, m, r);
+        bool has_l = false, has_r = false;
+        int32_t llo = 0, lhi = 0, rlo = 0, rhi = 0;
+        if (is_single(lv) && lv.lo != DMIN && lv.lo != DMAX) {
+          if (lv.lo == rv.lo) { has_r = true; rlo = lv.lo + 1; rhi = DMAX; }
+          else if (lv.lo == rv.hi) { has_r = true; rlo = DMIN; rhi = lv.lo - 1; }
+        }
+        if (is_single(rv) && rv.lo != DMIN && rv.lo != DMAX) {
+          if (rv.lo == lv.lo) { has_l = true; llo = rv.lo + 1; lhi = DMAX; }
+          else if (rv.lo == lv.hi) { has_l = true; llo = DMIN; lhi = rv.lo - 1; }
+        }
+        if (has_l) { f.node = l; f.lo = llo; f.hi = lhi; f.phase = 0; } else { sp--; }
+        if (has_r) { st[sp].node = r; st[sp].lo = rlo; st[sp].hi = rhi; st[sp].phase = 0; sp++; }
+      } else {
+        sp--;
+      }
+      break;
+    case CSOLVE_OP_LT:   // src/propagate.c:155-208
+      if (is_true(v)) {
+        if (f.phase == 0) {
+          Dom lv = eval_subtree(cx, m, l);
+          f.phase = 1;
+          if (lv.lo != DMIN && lv.lo != DMAX) {
+            st[sp].node = r; st[sp].lo = lv.lo + 1; st[sp].hi = DMAX; st[sp].phase = 0; sp++;
+          }
+        } else {
+          Dom rv = eval_subtree(cx, m, r);
+          if (rv.hi != DMIN && rv.hi != DMAX) { f.node = l; f.lo = DMIN; f.hi = rv.hi - 1; f.phase = 0; }
+          else sp--;
+        }
+      } else if (is_false(v)) {
+        if (f.phase == 0) {
+          Dom lv = eval_subtree(cx, m, l);
+          f.phase = 1;
+          st[sp].node = r; st[sp].lo = DMIN; st[sp].hi = lv.hi; st[sp].phase = 0; sp++;
+        } else {
+          Dom rv = eval_subtree(cx, m, r);
+          f.node = l; f.lo = rv.lo; f.hi = DMAX; f.phase = 0;
+        }
+      } else {
+        sp--;
+      }
+      break;
+    case CSOLVE_OP_ADD:  // src/propagate.c:222-246
+      if (f.phase == 0) {
+        Dom cv = eval_subtree(cx, m, l);
+        f.phase = 1;
+        st[sp].node = r; st[sp].lo = sadd(v.lo, sneg(cv.hi)); st[sp].hi = sadd(v.hi, sneg(cv.lo));
+        st[sp].phase = 0; sp++;
+      } else {
+        Dom cv = eval_subtree(cx, m, r);
+        f.node = l; f.lo = sadd(v.lo, sneg(cv.hi)); f.hi = sadd(v.hi, sneg(cv.lo)); f.phase = 0;
+      }
+      break;
+    case CSOLVE_OP_MUL: { // src/propagate.c:249-286
+      int32_t tlo = 0, thi = 0;
+      if (f.phase == 0) {
+        int k = mul_target(v, eval_subtree(cx, m, l), &tlo, &thi);
+        if (k < 0) return false;
+        f.phase = 1;
+        if (k > 0) { st[sp].node = r; st[sp].lo = tlo; st[sp].hi = thi; st[sp].phase = 0; sp++; }
+      } else {
+        int k = mul_target(v, eval_subtree(cx, m, r), &tlo, &thi);
+        if (k < 0) return false;
+        if (k > 0) { f.node = l; f.lo = tlo; f.hi = thi; f.phase = 0; } else sp--;
+      }
+      break;
+    }
+    case CSOLVE_OP_AND:  // src/propagate.c:346-361
+    case CSOLVE_OP_OR: { // src/propagate.c:364-376
+      const bool both = (op == CSOLVE_OP_AND) ? is_true(v) : is_false(v);
+      const bool either = (op == CSOLVE_OP_AND) ? is_false(v) : is_true(v);
+      if (both) {
+        if (f.phase == 0) {
+          f.phase = 1;
+          st[sp].node = r; st[sp].lo = v.lo; st[sp].hi = v.hi; st[sp].phase = 0; sp++;
+        } else {
+          f.node = l; f.phase = 0;
+        }
+      } else if (either) {
+        // push the value to the side whose sibling already is the neutral element
+        if (f.phase == 0) {
+          Dom lv = eval_subtree(cx, m, l);
+          f.phase = 1;
+          if ((op == CSOLVE_OP_AND) ? is_true(lv) : is_false(lv)) {
+            st[sp].node = r; st[sp].lo = v.lo; st[sp].hi = v.hi; st[sp].phase = 0; sp++;
+          }
+        } else {
+          Dom rv = eval_subtree(cx, m, r);
+          if ((op == CSOLVE_OP_AND) ? is_true(rv) : is_false(rv)) { f.node = l; f.phase = 0; }
+          else sp--;
+        }
+      } else {
+        sp--;
+      }
+      break;
+    }
+    default:
+      return false;
+    }
+  }
+  return true;
+}
+
+// ---- specialised contractors ----------------------------------------------------------
+// NOT(EQ(x + c, y)): the false branch of propagate_eq (src/propagate.c:104-134) reached
+// through propagate_not (src/propagate.c:289-301) and propagate_add (src/propagate.c:222-246);
+// only emitted when nothing can saturate.
+template <class Cx>
+CSOLVE_HD bool contract_ne_vv(Cx &cx, int x, int y, int32_t c) {
+  Dom X = cx.dom(x), Y = cx.dom(y);
+  const int32_t Ll = X.lo + c, Lh = X.hi + c;
+  bool ok = true;
+  if (X.lo == X.hi) {              // left side is a value: contract the right side first
+    if (Ll == Y.lo) ok = contract_var(cx, y, Y.lo + 1, DMAX);
+    else if (Ll == Y.hi) ok = contract_var(cx, y, DMIN, Y.hi - 1);
+    if (!ok) return false;
+  }
+  if (Y.lo == Y.hi) {              // right side (as evaluated up front) is a value
+    if (Y.lo == Ll) ok = contract_var(cx, x, X.lo + 1, DMAX);
+    else if (Y.lo == Lh) ok = contract_var(cx, x, DMIN, X.hi - 1);
+  }
+  return ok;
+}
+
+// NOT(EQ(x + k, const)) == (x != c)
+template <class Cx>
+CSOLVE_HD bool contract_ne_vc(Cx &cx, int x, int32_t c) {
+  Dom X = cx.dom(x);
+  if (X.lo == c) return contract_var(cx, x, c + 1, DMAX);
+  if (X.hi == c) return contract_var(cx, x, DMIN, c - 1);
+  return true;
+}
+
+// One clause contraction = propagate VALUE(1) into clause k (src/propagate.c:514-516).
+template <class Cx>
+CSOLVE_HD bool contract_clause(Cx &cx, const DevModel &m, const ClauseRec &rec) {
+  switch (rec.kind) {
+  case CK_NE_VV: return contract_ne_vv(cx, rec.a, rec.b, rec.c);
+  case CK_NE_VC: return contract_ne_vc(cx, rec.a, rec.c);
+  default:       return contract_generic(cx, m, rec.b);
+  }
+}
+
+// Leaf test for one clause: is_true(eval(clause)) (src/csolve.c:226, src/eval.c:221-245)
+template <class Cx>
+CSOLVE_HD bool clause_is_true(Cx &cx, const DevModel &m, const ClauseRec &rec) {
+  switch (rec.kind) {
+  case CK_NE_VV: {
+    Dom X = cx.dom(rec.a), Y = cx.dom(rec.b);
+    return X.hi + rec.c < Y.lo || X.lo + rec.c > Y.hi;
+  }
+  case CK_NE_VC: {
+    Dom X = cx.dom(rec.a);
+    return X.hi < rec.c || X.lo > rec.c;
+  }
+  default:
+    return is_true(eval_subtree(cx, m, rec.b));
+  }
+}
+
+// value tried at iteration i of a level (src/csolve.c:331-338, seed = 0: no restarts)
+CSOLVE_HD int32_t step_value(int32_t lo, int32_t hi, uint32_t i) {
+  return (i & 1u) ? (int32_t)((uint32_t)hi - (i >> 1)) : (int32_t)((uint32_t)lo + (i >> 1));
+}
+
+// objective_update_val (src/objective.c:101-126) applied to <obj>'s domain
+CSOLVE_HD Dom objective_tighten(int objective, Dom obj, int32_t best) {
+  if (objective == CSOLVE_OBJ_MIN) {
+    int32_t b = sadd(best, sneg(1));
+    if (obj.hi > b) obj.hi = b;
+  } else if (objective == CSOLVE_OBJ_MAX) {
+    int32_t b = sadd(best, 1);
+    if (obj.lo < b) obj.lo = b;
+  }
+  return obj;
+}
+
+}  // namespace csolve_dev

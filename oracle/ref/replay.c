@@ -43,8 +43,9 @@ static void ref_unload(void) {
   if (_loaded) {
     env_free();
     if (standin_root != NULL) expr_free(standin_root);
+    /* the variable order only exists when the root phase succeeded */
+    if (standin_env != NULL) strategy_var_order_free();
     bind_free(); patch_free(); alloc_free(); conflict_alloc_free();
-    strategy_var_order_free();
     _loaded = 0;
     standin_env = NULL; standin_norm = NULL; standin_root = NULL; standin_size = 0;
   }

@@ -1,0 +1,85 @@
+// host_contract.cpp -- TEST-ONLY harness: runs the product's contractors
+// (csolve_b200/csrc/contract.cuh, the code the kernels execute per lane) on the
+// host over a plain domain array, with a sequential worklist in place of the warp.
+// Not part of the library, not exported through the C ABI, never a fallback.
+#include <cstring>
+#include <string>
+#include <vector>
+#include "compile.hpp"
+#include "contract.cuh"
+
+using namespace csolve_dev;
+
+struct HostCx {
+  int32_t *d;                       // lo,hi pairs
+  std::vector<int> *queue;
+  std::vector<uint8_t> *queued;
+  uint64_t props = 0;
+  Dom dom(int v) const { return mk(d[2 * v], d[2 * v + 1]); }
+  void mark(int v) { if (!(*queued)[v]) { (*queued)[v] = 1; queue->push_back(v); } }
+  void raise_lo(int v, int32_t lo) { if (lo > d[2 * v]) { d[2 * v] = lo; mark(v); } }
+  void lower_hi(int v, int32_t hi) { if (hi < d[2 * v + 1]) { d[2 * v + 1] = hi; mark(v); } }
+  void count_prop() { props++; }
+};
+
+static CompiledModel g_cm;
+static std::string g_err;
+
+extern "C" int hc_load(const csolve_flat_model *m, int specialise) {
+  int rc = compile_model(*m, g_cm, g_err);
+  if (rc != 0) return rc;
+  if (!specialise) {
+    for (size_t c = 0; c < g_cm.clause.size(); c++) {
+      g_cm.clause[c] = ClauseRec{CK_GENERIC, m->clause_first[c], m->clause_first[c + 1] - 1, 0};
+    }
+  }
+  return 0;
+}
+extern "C" const char *hc_error() { return g_err.c_str(); }
+extern "C" int hc_n_specialised() {
+  int n = 0;
+  for (auto &c : g_cm.clause) n += c.kind != CK_GENERIC;
+  return n;
+}
+
+// one node transition (src/csolve.c:448-457); returns 1 if failed
+extern "C" int hc_node(const int32_t *dom_in, int var, int32_t val, int32_t best, int32_t *dom_out) {
+  const DevModel &m = g_cm.host;
+  int V = m.n_vars;
+  std::vector<int32_t> d(dom_in, dom_in + 2 * V);
+  std::vector<int> queue;
+  std::vector<uint8_t> queued(V, 0);
+  HostCx cx{d.data(), &queue, &queued};
+  if (d[2 * var] != d[2 * var + 1]) { d[2 * var] = val; d[2 * var + 1] = val; }
+  cx.mark(var);
+  if (m.obj_var >= 0) {
+    Dom o = objective_tighten(m.objective, cx.dom(m.obj_var), best);
+    d[2 * m.obj_var] = o.lo; d[2 * m.obj_var + 1] = o.hi;
+    cx.mark(m.obj_var);
+  }
+  bool failed = false;
+  for (size_t qi = 0; qi < queue.size() && !failed; qi++) {
+    int x = queue[qi];
+    queued[x] = 0;
+    if (d[2 * x] > d[2 * x + 1]) { failed = true; break; }
+    for (int w = m.watch_ptr[x]; w < m.watch_ptr[x + 1]; w++) {
+      if (!contract_clause(cx, m, m.clause[m.watch_idx[w]])) { failed = true; break; }
+    }
+  }
+  if (!failed) for (int v = 0; v < V; v++) if (d[2 * v] > d[2 * v + 1]) failed = true;
+  memcpy(dom_out, d.data(), sizeof(int32_t) * 2 * V);
+  return failed ? 1 : 0;
+}
+
+extern "C" int hc_leaf_true(const int32_t *dom_in) {
+  const DevModel &m = g_cm.host;
+  std::vector<int32_t> d(dom_in, dom_in + 2 * m.n_vars);
+  std::vector<int> queue; std::vector<uint8_t> queued(m.n_vars, 0);
+  HostCx cx{d.data(), &queue, &queued};
+  for (int c = 0; c < m.n_clauses; c++) if (!clause_is_true(cx, m, m.clause[c])) return 0;
+  return 1;
+}
+
+extern "C" int32_t hc_sneg(int32_t a) { return sneg(a); }
+extern "C" int32_t hc_sadd(int32_t a, int32_t b) { return sadd(a, b); }
+extern "C" int32_t hc_smul(int32_t a, int32_t b) { return smul(a, b); }
