@@ -1,0 +1,415 @@
+// capi.cu -- the C ABI of include/csolve_b200.h: device residency of the compiled
+// model and host orchestration of the search (frontier expansion, time-sliced
+// persistent search, rebalancing, result collection).
+//
+// There is no CPU implementation of the search behind these entry points: without a
+// CUDA device every device call fails with CSOLVE_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "csolve_b200.h"
+#include "compile.hpp"
+#include "front.hpp"
+#include "kernels.cuh"
+
+using namespace csolve_dev;
+
+namespace {
+
+int g_device = -1;
+int g_sm_count = 0;
+int g_clock_khz = 0;
+
+int fail(int code, const std::string &msg) {
+  csolve_front::set_last_error(msg);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver        \
+                      ? CSOLVE_ERR_NO_DEVICE : CSOLVE_ERR_CUDA,                         \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+    }                                                                                   \
+  } while (0)
+
+template <class T>
+int upload(const std::vector<T> &h, const T **d) {
+  T *p = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  if (!h.empty()) CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *d = p;
+  return CSOLVE_OK;
+}
+
+// host rendering of warp_select_var() for the root frame
+int select_root_var(const CompiledModel &cm, int order) {
+  const DevModel &m = cm.host;
+  if (order == CSOLVE_ORDER_NONE) return cm.order[0];
+  unsigned long long bestk = ~0ull;
+  int bestv = 0;
+  for (int v = 0; v < m.n_vars; v++) {
+    const int lo = cm.root_dom[2 * v], hi = cm.root_dom[2 * v + 1];
+    unsigned primary;
+    switch (order) {
+    case CSOLVE_ORDER_SMALLEST_DOMAIN: primary = (unsigned)hi - (unsigned)lo; break;
+    case CSOLVE_ORDER_LARGEST_DOMAIN:  primary = ~((unsigned)hi - (unsigned)lo); break;
+    case CSOLVE_ORDER_SMALLEST_VALUE:  primary = (unsigned)lo ^ 0x80000000u; break;
+    default:                           primary = ~((unsigned)hi ^ 0x80000000u); break;
+    }
+    const unsigned secondary = ~((unsigned)cm.prio[v] ^ 0x80000000u);
+    const unsigned long long k = ((unsigned long long)primary << 32) | secondary;
+    if (k < bestk) { bestk = k; bestv = v; }
+  }
+  return bestv;
+}
+
+}  // namespace
+
+struct csolve_gpu_problem {
+  CompiledModel cm;
+  DevModel dev{};                 // device pointers
+  std::vector<void *> allocs;     // model arrays on the device
+  // search workspace (allocated on first solve)
+  int grid = 0, n_warps = 0;
+  int32_t *stacks = nullptr;
+  WarpState *wstate = nullptr;
+  unsigned long long *wcount = nullptr;
+  unsigned long long *totals = nullptr;
+  SearchCtl *ctl = nullptr;
+  int32_t *pool_a = nullptr, *pool_b = nullptr;
+  int32_t pool_cap = 0;
+  int32_t *scratch = nullptr;
+  int32_t *solbuf = nullptr;
+  int32_t sol_cap = 0;
+  std::vector<int32_t> sol_host;
+  int32_t n_stored = 0;
+  cudaStream_t stream = nullptr;
+
+  ~csolve_gpu_problem() {
+    for (void *p : allocs) cudaFree(p);
+    cudaFree(stacks); cudaFree(wstate); cudaFree(wcount); cudaFree(totals); cudaFree(ctl);
+    cudaFree(pool_a); cudaFree(pool_b); cudaFree(scratch); cudaFree(solbuf);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+extern "C" const char *csolve_last_error(void) { return csolve_front::last_error(); }
+extern "C" int csolve_abi_version(void) { return CSOLVE_B200_ABI_VERSION; }
+
+extern "C" int csolve_gpu_init(const csolve_gpu_config *cfg) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    return fail(CSOLVE_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                          " (the search path has no CPU fallback)");
+  }
+  int dev = cfg ? cfg->device : 0;
+  if (dev < 0 || dev >= n) return fail(CSOLVE_ERR_INVALID, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&g_clock_khz, cudaDevAttrClockRate, dev));
+  g_device = dev;
+  return CSOLVE_OK;
+}
+
+extern "C" void csolve_gpu_shutdown(void) { g_device = -1; }
+
+extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **out) {
+  if (m == nullptr || out == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (g_device < 0) {
+    int rc = csolve_gpu_init(nullptr);
+    if (rc != CSOLVE_OK) return rc;
+  }
+  std::unique_ptr<csolve_gpu_problem> p(new csolve_gpu_problem);
+  std::string err;
+  int rc = compile_model(*m, p->cm, err);
+  if (rc != CSOLVE_OK) return fail(rc, err);
+
+  DevModel &d = p->dev;
+  d = p->cm.host;
+#define UP(field, vec)                                              \
+  do {                                                              \
+    rc = upload(p->cm.vec, &d.field);                               \
+    if (rc != CSOLVE_OK) return rc;                                 \
+    p->allocs.push_back((void *)d.field);                           \
+  } while (0)
+  UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx);
+  UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
+  UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
+#undef UP
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  *out = p.release();
+  return CSOLVE_OK;
+}
+
+extern "C" void csolve_gpu_unload(csolve_gpu_problem *p) { delete p; }
+
+extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes, const int32_t *dom_in,
+                                          const int32_t *var, const int32_t *val, const int32_t *best,
+                                          int32_t *dom_out, uint8_t *failed) {
+  if (p == nullptr || n_nodes < 0) return fail(CSOLVE_ERR_INVALID, "bad arguments");
+  if (n_nodes == 0) return CSOLVE_OK;
+  const int V = p->dev.n_vars;
+  for (int b = 0; b < n_nodes; b++) {
+    if (var[b] < 0 || var[b] >= V) return fail(CSOLVE_ERR_INVALID, "decision variable out of range");
+  }
+  const size_t dom_bytes = (size_t)n_nodes * 2 * V * sizeof(int32_t), vec_bytes = (size_t)n_nodes * sizeof(int32_t);
+  int32_t *d_in = nullptr, *d_var = nullptr, *d_val = nullptr, *d_best = nullptr, *d_out = nullptr;
+  uint8_t *d_failed = nullptr;
+  std::vector<int32_t> zero_best;
+  if (best == nullptr) { zero_best.assign(n_nodes, 0); best = zero_best.data(); }
+  int rc = CSOLVE_OK;
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_var); cudaFree(d_val); cudaFree(d_best); cudaFree(d_out); cudaFree(d_failed); };
+#define TRY2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(CSOLVE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+  TRY2(cudaMalloc(&d_in, dom_bytes)); TRY2(cudaMalloc(&d_out, dom_bytes));
+  TRY2(cudaMalloc(&d_var, vec_bytes)); TRY2(cudaMalloc(&d_val, vec_bytes)); TRY2(cudaMalloc(&d_best, vec_bytes));
+  TRY2(cudaMalloc(&d_failed, n_nodes));
+  TRY2(cudaMemcpyAsync(d_in, dom_in, dom_bytes, cudaMemcpyHostToDevice, p->stream));
+  TRY2(cudaMemcpyAsync(d_var, var, vec_bytes, cudaMemcpyHostToDevice, p->stream));
+  TRY2(cudaMemcpyAsync(d_val, val, vec_bytes, cudaMemcpyHostToDevice, p->stream));
+  TRY2(cudaMemcpyAsync(d_best, best, vec_bytes, cudaMemcpyHostToDevice, p->stream));
+  int grid = std::min((n_nodes + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, std::max(1, g_sm_count) * 8);
+  TRY2(launch_propagate_batch(p->dev, n_nodes, d_in, d_var, d_val, d_best, d_out, d_failed, grid, p->stream));
+  TRY2(cudaMemcpyAsync(dom_out, d_out, dom_bytes, cudaMemcpyDeviceToHost, p->stream));
+  TRY2(cudaMemcpyAsync(failed, d_failed, n_nodes, cudaMemcpyDeviceToHost, p->stream));
+  TRY2(cudaStreamSynchronize(p->stream));
+#undef TRY2
+  cleanup();
+  return rc;
+}
+
+// ---- search ------------------------------------------------------------------------------------
+namespace {
+
+int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
+  const DevModel &m = p->dev;
+  if (p->stacks == nullptr) {
+    int per_sm = search_blocks_per_sm(m, false);
+    if (per_sm <= 0) return fail(CSOLVE_ERR_CUDA, "search kernel does not fit on the device (shared memory per node too large)");
+    p->grid = per_sm * g_sm_count;
+    p->n_warps = p->grid * WARPS_PER_BLOCK;
+    const size_t stack_words = (size_t)p->n_warps * (m.n_vars + 1) * m.frame_words;
+    CUDA_TRY(cudaMalloc(&p->stacks, stack_words * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&p->wstate, (size_t)p->n_warps * sizeof(WarpState)));
+    CUDA_TRY(cudaMalloc(&p->wcount, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&p->totals, CNT_WIDTH * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&p->ctl, sizeof(SearchCtl)));
+    CUDA_TRY(cudaMalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
+  }
+  // frontier pools: room for the split target times the largest branching the expansion may apply
+  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 8;
+  int cap = std::max(target * 16, 1 << 16);
+  const size_t max_bytes = (size_t)2 << 30;   // per pool
+  while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
+  if (cap > p->pool_cap) {
+    cudaFree(p->pool_a); cudaFree(p->pool_b); p->pool_a = p->pool_b = nullptr;
+    CUDA_TRY(cudaMalloc(&p->pool_a, (size_t)cap * m.frame_words * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&p->pool_b, (size_t)cap * m.frame_words * sizeof(int32_t)));
+    p->pool_cap = cap;
+  }
+  int sol_cap = std::max(opt.max_solutions, m.obj_var >= 0 ? 4096 : (m.objective == CSOLVE_OBJ_ANY ? 1 : 0));
+  if (sol_cap > p->sol_cap) {
+    cudaFree(p->solbuf); p->solbuf = nullptr;
+    CUDA_TRY(cudaMalloc(&p->solbuf, (size_t)sol_cap * (m.n_vars + 1) * sizeof(int32_t)));
+    p->sol_cap = sol_cap;
+  }
+  return CSOLVE_OK;
+}
+
+}  // namespace
+
+extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve_gpu_result *res) {
+  if (p == nullptr || res == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  csolve_solve_options opt;
+  memset(&opt, 0, sizeof(opt));
+  if (opt_in) opt = *opt_in;
+  if (opt.part_count <= 0) opt.part_count = 1;
+  if (opt.part_rank < 0 || opt.part_rank >= opt.part_count) return fail(CSOLVE_ERR_INVALID, "part_rank out of range");
+  if (opt.order < CSOLVE_ORDER_NONE || opt.order > CSOLVE_ORDER_LARGEST_VALUE) return fail(CSOLVE_ERR_INVALID, "invalid ordering strategy");
+  memset(res, 0, sizeof(*res));
+  int rc = ensure_workspace(p, opt);
+  if (rc != CSOLVE_OK) return rc;
+
+  const DevModel &m = p->dev;
+  const CompiledModel &cm = p->cm;
+  const int V = m.n_vars, fw = m.frame_words;
+  cudaStream_t st = p->stream;
+  const auto wall0 = std::chrono::steady_clock::now();
+
+  // ---- initial state ----------------------------------------------------------------------------
+  SearchCtl ctl;
+  memset(&ctl, 0, sizeof(ctl));
+  ctl.best = m.objective == CSOLVE_OBJ_MIN ? INT32_MAX : (m.objective == CSOLVE_OBJ_MAX ? INT32_MIN : 0);   // src/objective.c:38-50
+  CUDA_TRY(cudaMemsetAsync(p->wcount, 0, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long), st));
+  std::vector<WarpState> ws(p->n_warps, WarpState{-1, 0});
+  CUDA_TRY(cudaMemcpyAsync(p->wstate, ws.data(), ws.size() * sizeof(WarpState), cudaMemcpyHostToDevice, st));
+
+  // root frame
+  std::vector<int32_t> root(fw, 0);
+  const int rv = select_root_var(cm, opt.order);
+  root[FR_VAR] = rv; root[FR_ITER] = 0;
+  root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
+  root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
+  root[FR_LEVEL] = 0; root[FR_BEST] = ctl.best; root[7] = 0x1234567;
+  memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
+  CUDA_TRY(cudaMemcpyAsync(p->pool_a, root.data(), fw * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  ctl.item_count = 1;
+  CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+
+  SearchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.m = m; a.ctl = p->ctl; a.stacks = p->stacks; a.wstate = p->wstate; a.wcount = p->wcount;
+  a.solbuf = p->solbuf; a.max_solutions = p->sol_cap; a.n_warps = p->n_warps; a.order = opt.order;
+  a.out_cap = p->pool_cap; a.expand_branch_max = 64;
+  const int slice_ms = opt.slice_ms > 0 ? opt.slice_ms : 20;
+  a.slice_cycles = (long long)g_clock_khz * slice_ms;
+
+  cudaEvent_t ev0, ev1, ev2;
+  CUDA_TRY(cudaEventCreate(&ev0)); CUDA_TRY(cudaEventCreate(&ev1)); CUDA_TRY(cudaEventCreate(&ev2));
+  CUDA_TRY(cudaEventRecord(ev0, st));
+  uint64_t launches = 0;
+
+  // ---- batched frontier expansion -------------------------------------------------------------------
+  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 8;
+  long long max_branch = 1;
+  for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
+  max_branch = std::min<long long>(max_branch, a.expand_branch_max);
+  int32_t *pin = p->pool_a, *pout = p->pool_b;
+  int n_items = 1;
+  bool stopped = false;
+  for (int lvl = 0; lvl < V && n_items > 0 && n_items < target; ++lvl) {
+    // would another level overflow the pool? domains only shrink, so a frame has at most as many
+    // children as the largest root domain (and never more than expand_branch_max)
+    if ((long long)n_items * max_branch > p->pool_cap) break;
+    a.items = pin; a.items_out = pout; a.frozen_best = ctl.best;
+    ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.idle = 0; ctl.passed = 0;
+    CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+    const int grid = std::min(p->grid, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    CUDA_TRY(launch_search(a, grid, true, st)); launches++;
+    CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ctl.out_dropped > 0) return fail(CSOLVE_ERR_CAPACITY, "frontier pool overflow during expansion");
+    n_items = ctl.out_count;
+    std::swap(pin, pout);
+    if (ctl.signal == SIG_STOP) { stopped = true; break; }
+    // frames with huge domains are passed through unsplit; when nothing else is left the
+    // breadth-first phase cannot make progress and the depth-first phase (which bisects) takes over
+    if (ctl.passed == n_items) break;
+  }
+  CUDA_TRY(cudaEventRecord(ev1, st));
+
+  // ---- partition: this rank keeps the frames whose path hash maps to it --------------------------------
+  if (opt.part_count > 1 && n_items > 0) {
+    std::vector<int32_t> all((size_t)n_items * fw);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), pin, all.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int32_t> mine;
+    mine.reserve(all.size() / opt.part_count + fw);
+    for (int i = 0; i < n_items; i++) {
+      const uint32_t h = (uint32_t)all[(size_t)i * fw + 7];
+      if ((int)(h % (uint32_t)opt.part_count) == opt.part_rank) mine.insert(mine.end(), all.begin() + (size_t)i * fw, all.begin() + (size_t)(i + 1) * fw);
+    }
+    n_items = (int)(mine.size() / fw);
+    if (n_items > 0) CUDA_TRY(cudaMemcpyAsync(pin, mine.data(), mine.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (opt.part_rank != 0) {
+      // the expansion was replicated on every rank: only rank 0 reports its counters and leaves
+      CUDA_TRY(cudaMemsetAsync(p->wcount, 0, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long), st));
+      if (m.objective == CSOLVE_OBJ_ALL) ctl.n_stored = 0;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+
+  // ---- time-sliced persistent search -----------------------------------------------------------------------
+  a.items = pin; a.items_out = nullptr;
+  ctl.item_next = 0; ctl.item_count = n_items; ctl.idle = 0; ctl.busy = 0;
+  ctl.signal = stopped ? SIG_STOP : SIG_RUN;
+  CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+  int idle_now = p->n_warps;          // every warp starts without a stack
+  int busy = 0;
+  bool timed_out = false;
+  uint64_t slices = 0;
+  while (!stopped && n_items > 0) {
+    // ask for the slice to end when an eighth of the warps that have work (or can fetch it) ran dry
+    const int can_work = std::min(p->n_warps, busy + std::max(0, ctl.item_count - ctl.item_next));
+    a.idle_exit = std::min(p->n_warps, (p->n_warps - can_work) + std::max(1, can_work / 8));
+    CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
+    CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
+    CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    slices++;
+    busy = ctl.busy - (ctl.item_next < ctl.item_count ? 1 : 0);
+    idle_now = p->n_warps - busy;
+    if (ctl.signal == SIG_STOP) break;
+    if (ctl.busy == 0) break;
+    if (opt.time_limit_ms > 0) {
+      const auto now = std::chrono::steady_clock::now();
+      if (std::chrono::duration_cast<std::chrono::milliseconds>(now - wall0).count() > opt.time_limit_ms) { timed_out = true; break; }
+    }
+  }
+  (void)idle_now;
+  CUDA_TRY(cudaEventRecord(ev2, st));
+
+  // ---- results ---------------------------------------------------------------------------------------------
+  CUDA_TRY(launch_reduce_counters(p->wcount, p->n_warps, p->totals, st)); launches++;
+  unsigned long long tot[CNT_WIDTH];
+  CUDA_TRY(cudaMemcpyAsync(tot, p->totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  p->n_stored = std::min(ctl.n_stored, p->sol_cap);
+  p->sol_host.resize((size_t)p->n_stored * (V + 1));
+  if (p->n_stored > 0) {
+    CUDA_TRY(cudaMemcpy(p->sol_host.data(), p->solbuf, p->sol_host.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  if (m.obj_var >= 0 && p->n_stored > 1) {
+    // order the stored incumbents as a chain of improvements; the optimum is last
+    std::vector<int> idx(p->n_stored);
+    for (int i = 0; i < p->n_stored; i++) idx[i] = i;
+    const bool is_min = m.objective == CSOLVE_OBJ_MIN;
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+      const int kx = p->sol_host[(size_t)x * (V + 1) + V], ky = p->sol_host[(size_t)y * (V + 1) + V];
+      return is_min ? kx > ky : kx < ky;
+    });
+    std::vector<int32_t> sorted(p->sol_host.size());
+    for (int i = 0; i < p->n_stored; i++)
+      memcpy(&sorted[(size_t)i * (V + 1)], &p->sol_host[(size_t)idx[i] * (V + 1)], sizeof(int32_t) * (V + 1));
+    p->sol_host.swap(sorted);
+  }
+
+  float ms_expand = 0, ms_search = 0;
+  cudaEventElapsedTime(&ms_expand, ev0, ev1);
+  cudaEventElapsedTime(&ms_search, ev1, ev2);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+
+  res->solutions = tot[CNT_SOLUTIONS];
+  res->nodes = tot[CNT_NODES];
+  res->cuts = tot[CNT_CUTS];
+  res->props = tot[CNT_PROPS];
+  res->clause_visits = tot[CNT_VISITS];
+  res->best = ctl.best;
+  res->has_solution = tot[CNT_SOLUTIONS] > 0;
+  res->timed_out = timed_out;
+  res->n_stored = p->n_stored;
+  res->kernel_ms = ms_search;
+  res->expand_ms = ms_expand;
+  res->kernel_launches = launches;
+  (void)slices;
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_get_solution(csolve_gpu_problem *p, int32_t i, int32_t *values) {
+  if (p == nullptr || values == nullptr || i < 0 || i >= p->n_stored) return fail(CSOLVE_ERR_INVALID, "solution index out of range");
+  memcpy(values, &p->sol_host[(size_t)i * (p->dev.n_vars + 1)], sizeof(int32_t) * p->dev.n_vars);
+  return CSOLVE_OK;
+}

@@ -4,6 +4,12 @@
 #pragma once
 #include <stdint.h>
 
+#if defined(__CUDACC__)
+#define CSOLVE_HOSTDEV __host__ __device__
+#else
+#define CSOLVE_HOSTDEV
+#endif
+
 namespace csolve_dev {
 
 // Compiled clause record: one 16-byte word per clause (a single LDG.128).
@@ -54,8 +60,8 @@ struct DevModel {
 static const int FR_VAR = 0, FR_ITER = 1, FR_LAST = 2, FR_LO = 3, FR_HI = 4, FR_LEVEL = 5, FR_BEST = 6;
 static const int FR_MASK = 8;
 
-static inline int frame_dom_offset(int mask_words) { return (FR_MASK + mask_words + 3) & ~3; }
-static inline int frame_words(int n_vars, int mask_words) {
+CSOLVE_HOSTDEV static inline int frame_dom_offset(int mask_words) { return (FR_MASK + mask_words + 3) & ~3; }
+CSOLVE_HOSTDEV static inline int frame_words(int n_vars, int mask_words) {
   return (frame_dom_offset(mask_words) + 2 * n_vars + 3) & ~3;
 }
 

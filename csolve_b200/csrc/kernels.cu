@@ -1,0 +1,625 @@
+// kernels.cu -- sm_100a kernels of the csolve search hot path.
+//
+//   k_search<false>   persistent depth-first search: one warp = one open search node at a
+//                     time; the node's domain vector is staged in shared memory, the warp's
+//                     DFS stack and the frontier pool live in HBM.     (src/csolve.c:398-476)
+//   k_search<true>    batched frontier expansion: every warp takes a frontier frame, tries
+//                     all of its values and appends the surviving children to the output
+//                     frontier.                                       (src/csolve.c:105-152, 432-457)
+//   k_rebalance       between time slices: idle warps receive the upper half of the
+//                     shallowest splittable frame of a busy warp (interval bisection, as
+//                     worker_spawn does in src/csolve.c:121-149).
+//   k_propagate_batch parity hook: B independent node transitions.      (src/csolve.c:448-457)
+//
+// Inside a node, propagation to fixpoint (src/propagate.c:488-538) is a warp-synchronous
+// worklist: the set of changed variables is a bitmask in shared memory; lanes stride over
+// the watch list of each changed variable and contract one clause each; narrowed bounds
+// are published with shared-memory atomicMax/atomicMin and recorded in the next round's
+// mask with atomicOr. No tensor cores: the work is irregular int32 compare/min/max.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kernels.cuh"
+#include "contract.cuh"
+
+namespace csolve_dev {
+
+#define FULL 0xffffffffu
+
+// ---- domain access of one warp: shared memory, lo/hi interleaved ---------------------------
+struct WarpCx {
+  int *d;            // shared: 2 * n_vars words
+  unsigned *nxt;     // shared: mask of variables narrowed in this round
+  unsigned props;    // per-lane PROPS partial
+  __device__ __forceinline__ Dom dom(int v) const {
+    const volatile int *p = d + 2 * v;
+    Dom r; r.lo = p[0]; r.hi = p[1];
+    return r;
+  }
+  __device__ __forceinline__ void mark(int v) { atomicOr(&nxt[v >> 5], 1u << (v & 31)); }
+  __device__ __forceinline__ void raise_lo(int v, int32_t lo) {
+    if (atomicMax(&d[2 * v], lo) < lo) mark(v);
+  }
+  __device__ __forceinline__ void lower_hi(int v, int32_t hi) {
+    if (atomicMin(&d[2 * v + 1], hi) > hi) mark(v);
+  }
+  __device__ __forceinline__ void count_prop() { props++; }
+};
+
+// per-warp shared memory carve-up
+struct WarpSmem {
+  int *d;          // 2V
+  unsigned *cur;   // mask_words: variables whose watchers run in this round
+  unsigned *nxt;   // mask_words
+  unsigned *amask; // mask_words: variables assigned on the path to the top frame
+};
+
+__device__ __forceinline__ int warp_smem_words(const DevModel &m) { return 2 * m.n_vars + 3 * m.mask_words; }
+
+__device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
+  WarpSmem s;
+  s.d = base;
+  s.cur = (unsigned *)(base + 2 * m.n_vars);
+  s.nxt = s.cur + m.mask_words;
+  s.amask = s.nxt + m.mask_words;
+  return s;
+}
+
+// ---- propagation to fixpoint for the node staged in s.d --------------------------------------
+// precondition: s.cur holds the initial worklist, s.nxt is zero, warp converged after __syncwarp.
+// returns false when the node failed (PROP_ERROR).
+__device__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, int lane, unsigned &props, unsigned &visits) {
+  WarpCx cx;
+  cx.d = s.d; cx.props = 0;
+  bool failed = false;
+  for (;;) {
+    cx.nxt = s.nxt;
+    bool any = false;
+    for (int w = 0; w < m.mask_words; ++w) {
+      unsigned bits = s.cur[w];
+      if (bits) any = true;
+      while (bits) {
+        const int x = (w << 5) + __ffs(bits) - 1;
+        bits &= bits - 1;
+        // bounds published by different lanes may cross: an empty domain is a failure
+        Dom dx = cx.dom(x);
+        if (dx.lo > dx.hi) failed = true;
+        const int b = __ldg(&m.watch_ptr[x]), e = __ldg(&m.watch_ptr[x + 1]);
+        for (int i = b + lane; i < e; i += 32) {
+          const int c = __ldg(&m.watch_idx[i]);
+          const int4 q = __ldg(reinterpret_cast<const int4 *>(&m.clause[c]));
+          ClauseRec rec; rec.kind = q.x; rec.a = q.y; rec.b = q.z; rec.c = q.w;
+          if (!contract_clause(cx, m, rec)) failed = true;
+          visits++;
+        }
+      }
+    }
+    __syncwarp();
+    if (__any_sync(FULL, failed)) { props += cx.props; return false; }
+    if (!any) break;
+    // next round: cur <- nxt, nxt <- 0
+    unsigned *t = s.cur; s.cur = s.nxt; s.nxt = t;
+    for (int w = lane; w < m.mask_words; w += 32) s.nxt[w] = 0;
+    __syncwarp();
+  }
+  props += cx.props;
+  return true;
+}
+
+// leaf test: every clause evaluates to true (src/csolve.c:226, src/eval.c:221-245)
+__device__ bool warp_all_true(const DevModel &m, WarpSmem &s, int lane) {
+  WarpCx cx; cx.d = s.d; cx.nxt = s.nxt; cx.props = 0;
+  bool ok = true;
+  for (int c = lane; c < m.n_clauses; c += 32) {
+    const int4 q = __ldg(reinterpret_cast<const int4 *>(&m.clause[c]));
+    ClauseRec rec; rec.kind = q.x; rec.a = q.y; rec.b = q.z; rec.c = q.w;
+    if (!clause_is_true(cx, m, rec)) ok = false;
+  }
+  return __all_sync(FULL, ok);
+}
+
+// ---- branching variable for the next level (src/strategy.c:79-121) -----------------------------
+// ORDER_NONE is static (priority order); the other orders look at the node's domains.
+// Ties: higher parse-time priority, then lower index.
+__device__ int warp_select_var(const DevModel &m, const WarpSmem &s, int lane, int order, int next_level, int cur_var) {
+  if (order == CSOLVE_ORDER_NONE) return __ldg(&m.order[next_level]);
+  unsigned long long bestk = ~0ull;
+  int bestv = 0x7fffffff;
+  for (int v = lane; v < m.n_vars; v += 32) {
+    if (v == cur_var || (s.amask[v >> 5] & (1u << (v & 31)))) continue;   // already has a level
+    const int lo = s.d[2 * v], hi = s.d[2 * v + 1];
+    unsigned primary;
+    switch (order) {
+    case CSOLVE_ORDER_SMALLEST_DOMAIN: primary = (unsigned)hi - (unsigned)lo; break;
+    case CSOLVE_ORDER_LARGEST_DOMAIN:  primary = ~((unsigned)hi - (unsigned)lo); break;
+    case CSOLVE_ORDER_SMALLEST_VALUE:  primary = (unsigned)lo ^ 0x80000000u; break;
+    default:                           primary = ~((unsigned)hi ^ 0x80000000u); break;
+    }
+    const unsigned secondary = ~((unsigned)__ldg(&m.prio[v]) ^ 0x80000000u);
+    const unsigned long long k = ((unsigned long long)primary << 32) | secondary;
+    if (k < bestk) { bestk = k; bestv = v; }   // ascending v per lane: first best wins
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ok = __shfl_xor_sync(FULL, bestk, o);
+    const int ov = __shfl_xor_sync(FULL, bestv, o);
+    if (ok < bestk || (ok == bestk && ov < bestv)) { bestk = ok; bestv = ov; }
+  }
+  return bestv;
+}
+
+// ---- frame <-> shared memory ----------------------------------------------------------------------
+__device__ __forceinline__ void load_domains(const DevModel &m, const int *frame, int *d, int lane) {
+  const int2 *src = reinterpret_cast<const int2 *>(frame + frame_dom_offset(m.mask_words));
+  int2 *dst = reinterpret_cast<int2 *>(d);
+  for (int v = lane; v < m.n_vars; v += 32) dst[v] = __ldcg(&src[v]);
+}
+__device__ __forceinline__ void store_domains(const DevModel &m, int *frame, const int *d, int lane) {
+  int2 *dst = reinterpret_cast<int2 *>(frame + frame_dom_offset(m.mask_words));
+  const int2 *src = reinterpret_cast<const int2 *>(d);
+  for (int v = lane; v < m.n_vars; v += 32) __stcg(&dst[v], src[v]);
+}
+
+__device__ __forceinline__ unsigned mix_hash(unsigned h, unsigned a, unsigned b) {
+  h ^= a * 0x9E3779B1u; h = (h << 13) | (h >> 19); h *= 0x85EBCA77u;
+  h ^= b * 0xC2B2AE3Du; h = (h << 15) | (h >> 17); h *= 0x27D4EB2Fu;
+  return h ^ (h >> 16);
+}
+
+// write the child frame for level `level + 1` (domains = the node's post-fixpoint state in s.d)
+__device__ __forceinline__ void write_child_frame(const DevModel &m, const WarpSmem &s, int *g, int lane,
+                                                  int nv, int level1, int best, unsigned hash, int parent_var) {
+  if (lane == 0) {
+    const int lo = s.d[2 * nv], hi = s.d[2 * nv + 1];
+    __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)((unsigned)hi - (unsigned)lo), lo));
+    __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(hi, level1, best, (int)hash));
+  }
+  for (int w = lane; w < m.mask_words; w += 32) {
+    unsigned mk = s.amask[w];
+    if ((parent_var >> 5) == w) mk |= 1u << (parent_var & 31);
+    __stcg(&g[FR_MASK + w], (int)mk);
+  }
+  store_domains(m, g, s.d, lane);
+}
+
+// record an accepted leaf (src/csolve.c:222-244): the assignment plus the objective key
+__device__ __forceinline__ void store_solution(const SearchArgs &a, const WarpSmem &s, int lane, int key) {
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(&a.ctl->n_stored, 1);
+  slot = __shfl_sync(FULL, slot, 0);
+  if (slot < a.max_solutions) {
+    int *dst = a.solbuf + (size_t)slot * (a.m.n_vars + 1);
+    for (int v = lane; v < a.m.n_vars; v += 32) dst[v] = s.d[2 * v];
+    if (lane == 0) dst[a.m.n_vars] = key;
+  }
+}
+
+// ---- the search kernel ----------------------------------------------------------------------------
+// Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
+template <bool EXPAND>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK)
+k_search(const SearchArgs a) {
+  extern __shared__ __align__(16) int smem[];
+  const DevModel &m = a.m;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+  if (gw >= a.n_warps) return;
+  // per-warp regions are padded to 16 bytes so the int2 staging copies stay aligned
+  const int wwords = (warp_smem_words(m) + 3) & ~3;
+  WarpSmem s = carve(m, smem + wib * wwords);
+
+  const int V = m.n_vars, fw = m.frame_words;
+  const bool optimise = m.obj_var >= 0;
+  int *stack = a.stacks + (size_t)gw * (V + 1) * fw;
+  SearchCtl *ctl = a.ctl;
+
+  int level = a.wstate[gw].level, base = a.wstate[gw].base;
+  unsigned long long nodes = 0, cuts = 0, sols = 0, refresh = 0;
+  unsigned props = 0, visits = 0;
+  const long long t0 = clock64();
+  bool parked = false;
+
+  // restore the assigned-variable mask of the top frame
+  if (level >= base) {
+    for (int w = lane; w < m.mask_words; w += 32) s.amask[w] = (unsigned)__ldcg(&stack[(size_t)level * fw + FR_MASK + w]);
+  }
+  __syncwarp();
+
+  for (;;) {
+    const int sig = *reinterpret_cast<volatile int *>(&ctl->signal);   // consumed at the end of the node
+
+    if (level < base) {
+      // out of work: take the next frontier frame, or go idle
+      int it = 0;
+      if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
+      it = __shfl_sync(FULL, it, 0);
+      if (it >= ctl->item_count) {
+        if (lane == 0) {
+          const int n = atomicAdd(&ctl->idle, 1) + 1;
+          if (!EXPAND && n >= a.idle_exit) atomicMax(&ctl->signal, SIG_SLICE_END);
+        }
+        break;
+      }
+      const int *src = a.items + (size_t)it * fw;
+      const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
+      int *dst = stack + (size_t)L * fw;
+      for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
+      for (int w = lane; w < m.mask_words; w += 32) s.amask[w] = (unsigned)__ldcg(&src[FR_MASK + w]);
+      level = base = L;
+      __syncwarp();
+    }
+
+    int *f = stack + (size_t)level * fw;
+    const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(f));
+    const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(f) + 1);
+    const int var = h0.x;
+    unsigned iter = (unsigned)h0.y;
+    const unsigned last = (unsigned)h0.z;
+    int lo = h0.w, hi = h1.x;
+    const int flevel = h1.y;      // variables assigned before this frame (== level for DFS frames)
+    const unsigned fhash = (unsigned)h1.w;
+
+    int best = 0;
+    if (optimise) best = EXPAND ? a.frozen_best : *reinterpret_cast<volatile int *>(&ctl->best);
+
+    if (EXPAND && last >= (unsigned)a.expand_branch_max) {
+      // too many values to enumerate breadth-first: pass the frame through unchanged
+      int slot = 0;
+      if (lane == 0) { slot = atomicAdd(&ctl->out_count, 1); atomicAdd(&ctl->passed, 1); }
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot < a.out_cap) {
+        int *g = a.items_out + (size_t)slot * fw;
+        for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&f[w]));
+      } else if (lane == 0) {
+        atomicAdd(&ctl->out_dropped, 1);
+      }
+      level = base - 1;
+      continue;
+    }
+
+    if (iter > last) {
+      // values exhausted (src/csolve.c:439-442): backtrack
+      level--;
+      if (level >= base) {
+        const int pv = __ldcg(&stack[(size_t)level * fw + FR_VAR]);
+        if (lane == 0) s.amask[pv >> 5] &= ~(1u << (pv & 31));
+        __syncwarp();
+      }
+      continue;
+    }
+
+    if (!EXPAND && optimise && best != h1.z) {
+      // The incumbent improved since this frame's domains were computed. The reference
+      // restarts from level 0 on every improvement (src/csolve.c:418-421); here the frame is
+      // re-propagated against the tighter <obj> bound and keeps only its untried values.
+      load_domains(m, f, s.d, lane);
+      for (int w = lane; w < m.mask_words; w += 32) { s.cur[w] = 0; s.nxt[w] = 0; }
+      __syncwarp();
+      bool ok = true;
+      if (lane == 0) {
+        Dom o; o.lo = s.d[2 * m.obj_var]; o.hi = s.d[2 * m.obj_var + 1];
+        o = objective_tighten(m.objective, o, best);
+        s.d[2 * m.obj_var] = o.lo; s.d[2 * m.obj_var + 1] = o.hi;
+        s.cur[m.obj_var >> 5] |= 1u << (m.obj_var & 31);
+        ok = o.lo <= o.hi;
+      }
+      ok = __shfl_sync(FULL, ok, 0);
+      __syncwarp();
+      if (ok) ok = warp_fixpoint(m, s, lane, props, visits);
+      refresh++;
+      // untried values of the old enumeration form the interval [lo + ceil(iter/2), hi - floor(iter/2)]
+      const long long ua = (long long)lo + ((iter + 1) >> 1), ub = (long long)hi - (iter >> 1);
+      long long na = ua, nb = ub;
+      if (ok) {
+        const long long dl = s.d[2 * var], dh = s.d[2 * var + 1];
+        na = ua > dl ? ua : dl; nb = ub < dh ? ub : dh;
+      }
+      if (!ok || na > nb) {
+        level--;
+        if (level >= base) {
+          const int pv = __ldcg(&stack[(size_t)level * fw + FR_VAR]);
+          if (lane == 0) s.amask[pv >> 5] &= ~(1u << (pv & 31));
+          __syncwarp();
+        }
+        continue;
+      }
+      // the frame keeps its (now tighter) parent domains, except that the branching variable
+      // still ranges over the values this frame owns
+      if (lane == 0) { s.d[2 * var] = (int)na; s.d[2 * var + 1] = (int)nb; }
+      __syncwarp();
+      store_domains(m, f, s.d, lane);
+      if (lane == 0) {
+        __stcg(reinterpret_cast<int4 *>(f), make_int4(var, 0, (int)(unsigned)(nb - na), (int)na));
+        __stcg(reinterpret_cast<int4 *>(f) + 1, make_int4((int)nb, flevel, best, (int)fhash));
+      }
+      __syncwarp();
+      continue;
+    }
+
+    // ---- one search node: assign var := val, propagate (src/csolve.c:444-457) ----------------
+    const int val = step_value(lo, hi, iter);
+    if (lane == 0) __stcg(&f[FR_ITER], (int)(iter + 1));
+    load_domains(m, f, s.d, lane);
+    for (int w = lane; w < m.mask_words; w += 32) { s.cur[w] = 0; s.nxt[w] = 0; }
+    __syncwarp();
+    bool ok = true;
+    if (lane == 0) {
+      s.d[2 * var] = val; s.d[2 * var + 1] = val;
+      s.cur[var >> 5] |= 1u << (var & 31);
+      if (optimise) {
+        Dom o; o.lo = s.d[2 * m.obj_var]; o.hi = s.d[2 * m.obj_var + 1];
+        o = objective_tighten(m.objective, o, best);
+        s.d[2 * m.obj_var] = o.lo; s.d[2 * m.obj_var + 1] = o.hi;
+        s.cur[m.obj_var >> 5] |= 1u << (m.obj_var & 31);
+        ok = o.lo <= o.hi;
+      }
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    __syncwarp();
+    if (ok) ok = warp_fixpoint(m, s, lane, props, visits);
+    nodes++;
+
+    if (!ok) {
+      cuts++;
+    } else if (flevel + 1 == V) {
+      // all variables assigned: leaf (src/csolve.c:416-424, 222-244)
+      if (warp_all_true(m, s, lane)) {
+        bool accepted = true;
+        int key = 0;
+        if (m.objective == CSOLVE_OBJ_MIN) {
+          key = s.d[2 * m.obj_var];
+          int old = 0;
+          if (lane == 0) old = atomicMin(&ctl->best, key);
+          old = __shfl_sync(FULL, old, 0);
+          accepted = key < old;
+        } else if (m.objective == CSOLVE_OBJ_MAX) {
+          key = s.d[2 * m.obj_var + 1];
+          int old = 0;
+          if (lane == 0) old = atomicMax(&ctl->best, key);
+          old = __shfl_sync(FULL, old, 0);
+          accepted = key > old;
+        } else if (m.objective == CSOLVE_OBJ_ANY) {
+          int old = 0;
+          if (lane == 0) old = atomicMax(&ctl->signal, SIG_STOP);
+          old = __shfl_sync(FULL, old, 0);
+          accepted = old != SIG_STOP;     // first finder wins (found_any(), src/csolve.c:207-209)
+        }
+        if (accepted) { sols++; store_solution(a, s, lane, key); }
+      }
+    } else {
+      const int nv = warp_select_var(m, s, lane, a.order, flevel + 1, var);
+      const unsigned chash = mix_hash(fhash, (unsigned)var, (unsigned)val);
+      if (EXPAND) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&ctl->out_count, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot < a.out_cap) {
+          write_child_frame(m, s, a.items_out + (size_t)slot * fw, lane, nv, flevel + 1, best, chash, var);
+        } else if (lane == 0) {
+          atomicAdd(&ctl->out_dropped, 1);
+        }
+      } else {
+        write_child_frame(m, s, stack + (size_t)(level + 1) * fw, lane, nv, flevel + 1, best, chash, var);
+        if (lane == 0) s.amask[var >> 5] |= 1u << (var & 31);
+        level++;
+      }
+      __syncwarp();
+    }
+
+    // ---- park? ----------------------------------------------------------------------------------
+    if (!EXPAND) {
+      if (sig != SIG_RUN) { parked = true; break; }
+      if (clock64() - t0 > a.slice_cycles) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
+        parked = true;
+        break;
+      }
+    }
+  }
+
+  (void)parked;
+  if (lane == 0) {
+    a.wstate[gw].level = level;
+    a.wstate[gw].base = base;
+  }
+  // flush counters (the slot belongs to this warp; values accumulate across slices)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    props += __shfl_xor_sync(FULL, props, o);
+    visits += __shfl_xor_sync(FULL, visits, o);
+  }
+  if (lane == 0) {
+    unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
+    c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
+    c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols; c[CNT_REFRESH] += refresh;
+  }
+}
+
+// ---- rebalance -----------------------------------------------------------------------------------
+// One block. Idle warps (level < base) are paired with busy warps that own a frame with at
+// least two untried values; the donor keeps the lower half of the untried interval, the idle
+// warp gets the upper half (both restart their value iteration over the new bounds).
+// scratch: [0] n_idle, [1] n_donor, then idle list [n_warps], donor list [2 * n_warps].
+__global__ void __launch_bounds__(1024)
+k_rebalance(const SearchArgs a, int32_t *scratch) {
+  const DevModel &m = a.m;
+  const int V = m.n_vars, fw = m.frame_words, nw = a.n_warps;
+  int *idle_list = scratch + 4;
+  int *donor_list = idle_list + nw;
+  __shared__ int n_idle, n_donor, idle_done, busy, moved;
+  if (threadIdx.x == 0) { n_idle = 0; n_donor = 0; idle_done = 0; busy = 0; moved = 0; }
+  __syncthreads();
+  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+    if (a.wstate[w].level < a.wstate[w].base) idle_list[atomicAdd(&n_idle, 1)] = w;
+    else atomicAdd(&busy, 1);
+  }
+  __syncthreads();
+  // frames still in the frontier pool are work too: nothing to move while they last
+  const bool pool_left = a.ctl->item_next < a.ctl->item_count;
+  for (int round = 0; round < 4 && !pool_left; ++round) {
+    if (idle_done >= n_idle) break;
+    if (threadIdx.x == 0) n_donor = 0;
+    __syncthreads();
+    for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+      const int lv = a.wstate[w].level, bs = a.wstate[w].base;
+      if (lv < bs) continue;
+      const int *stack = a.stacks + (size_t)w * (V + 1) * fw;
+      for (int L = bs; L <= lv; ++L) {
+        const int *f = stack + (size_t)L * fw;
+        const unsigned iter = (unsigned)f[FR_ITER], last = (unsigned)f[FR_LAST];
+        if (iter <= last && last - iter >= 1) {   // at least two untried values
+          const int k = atomicAdd(&n_donor, 1);
+          donor_list[2 * k] = w; donor_list[2 * k + 1] = L;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    const int pairs = min(n_idle - idle_done, n_donor);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int k = wid; k < pairs; k += nwarp) {
+      const int thief = idle_list[idle_done + k];
+      const int donor = donor_list[2 * k], L = donor_list[2 * k + 1];
+      int *df = a.stacks + (size_t)donor * (V + 1) * fw + (size_t)L * fw;
+      int *tf = a.stacks + (size_t)thief * (V + 1) * fw + (size_t)L * fw;
+      const unsigned iter = (unsigned)df[FR_ITER];
+      const long long lo = df[FR_LO], hi = df[FR_HI];
+      const long long ua = lo + ((iter + 1) >> 1), ub = hi - (iter >> 1);   // untried interval
+      const long long mid = ua + (ub - ua) / 2;
+      __syncwarp();
+      for (int w = lane; w < fw; w += 32) tf[w] = df[w];
+      __syncwarp();
+      if (lane == 0) {
+        const int var = df[FR_VAR];
+        const int dofs = frame_dom_offset(m.mask_words);
+        df[FR_ITER] = 0; df[FR_LO] = (int)ua; df[FR_HI] = (int)mid; df[FR_LAST] = (int)(unsigned)(mid - ua);
+        df[dofs + 2 * var] = (int)ua; df[dofs + 2 * var + 1] = (int)mid;
+        tf[FR_ITER] = 0; tf[FR_LO] = (int)(mid + 1); tf[FR_HI] = (int)ub; tf[FR_LAST] = (int)(unsigned)(ub - mid - 1);
+        tf[dofs + 2 * var] = (int)(mid + 1); tf[dofs + 2 * var + 1] = (int)ub;
+        a.wstate[thief].level = L; a.wstate[thief].base = L;
+        atomicAdd(&moved, 1); atomicAdd(&busy, 1);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) idle_done += pairs;
+    __syncthreads();
+    if (pairs == 0) break;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.ctl->busy = busy + (pool_left ? 1 : 0);
+    a.ctl->moved = moved;
+    a.ctl->idle = 0;
+    a.ctl->signal = a.ctl->signal == SIG_STOP ? SIG_STOP : SIG_RUN;
+  }
+}
+
+__global__ void k_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out) {
+  __shared__ unsigned long long acc[CNT_WIDTH];
+  if (threadIdx.x < CNT_WIDTH) acc[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long loc[CNT_WIDTH];
+  for (int k = 0; k < CNT_WIDTH; k++) loc[k] = 0;
+  for (int w = threadIdx.x; w < n_warps; w += blockDim.x)
+    for (int k = 0; k < CNT_WIDTH; k++) loc[k] += wcount[(size_t)w * CNT_WIDTH + k];
+  for (int k = 0; k < CNT_WIDTH; k++) atomicAdd(&acc[k], loc[k]);
+  __syncthreads();
+  if (threadIdx.x < CNT_WIDTH) out[threadIdx.x] = acc[threadIdx.x];
+}
+
+// ---- parity hook: independent node transitions ------------------------------------------------------
+__global__ void __launch_bounds__(THREADS_PER_BLOCK)
+k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const int32_t *var, const int32_t *val,
+                  const int32_t *best, int32_t *dom_out, uint8_t *failed) {
+  extern __shared__ __align__(16) int smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wwords = (warp_smem_words(m) + 3) & ~3;
+  WarpSmem s = carve(m, smem + wib * wwords);
+  const int V = m.n_vars;
+  const int n_warps = gridDim.x * WARPS_PER_BLOCK;
+  for (int b = blockIdx.x * WARPS_PER_BLOCK + wib; b < n_nodes; b += n_warps) {
+    const int2 *src = reinterpret_cast<const int2 *>(dom_in + (size_t)b * 2 * V);
+    for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.d)[v] = __ldg(&src[v]);
+    for (int w = lane; w < m.mask_words; w += 32) { s.cur[w] = 0; s.nxt[w] = 0; }
+    __syncwarp();
+    bool ok = true;
+    if (lane == 0) {
+      const int x = var[b];
+      // a variable that already is a value is not re-bound (src/csolve.c:301-303)
+      if (s.d[2 * x] != s.d[2 * x + 1]) { s.d[2 * x] = val[b]; s.d[2 * x + 1] = val[b]; }
+      s.cur[x >> 5] |= 1u << (x & 31);
+      if (m.obj_var >= 0) {
+        Dom o; o.lo = s.d[2 * m.obj_var]; o.hi = s.d[2 * m.obj_var + 1];
+        o = objective_tighten(m.objective, o, best[b]);
+        s.d[2 * m.obj_var] = o.lo; s.d[2 * m.obj_var + 1] = o.hi;
+        s.cur[m.obj_var >> 5] |= 1u << (m.obj_var & 31);
+        ok = o.lo <= o.hi;
+      }
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    __syncwarp();
+    unsigned props = 0, visits = 0;
+    if (ok) ok = warp_fixpoint(m, s, lane, props, visits);
+    int2 *dst = reinterpret_cast<int2 *>(dom_out + (size_t)b * 2 * V);
+    for (int v = lane; v < V; v += 32) dst[v] = reinterpret_cast<int2 *>(s.d)[v];
+    if (lane == 0) failed[b] = ok ? 0 : 1;
+    __syncwarp();
+  }
+}
+
+// ---- host-side launch wrappers -----------------------------------------------------------------------
+size_t search_smem_bytes(const DevModel &m) {
+  const int wwords = (2 * m.n_vars + 3 * m.mask_words + 3) & ~3;
+  return (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
+}
+
+static cudaError_t ensure_smem(const void *fn, size_t bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+int search_blocks_per_sm(const DevModel &m, bool expand) {
+  int n = 0;
+  const size_t smem = search_smem_bytes(m);
+  const void *fn = expand ? (const void *)k_search<true> : (const void *)k_search<false>;
+  if (ensure_smem(fn, smem) != cudaSuccess) return 0;
+  if (expand) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search<true>, THREADS_PER_BLOCK, smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search<false>, THREADS_PER_BLOCK, smem);
+  return n;
+}
+
+cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
+  const size_t smem = search_smem_bytes(a.m);
+  if (expand) {
+    cudaError_t e = ensure_smem((const void *)k_search<true>, smem);
+    if (e != cudaSuccess) return e;
+    k_search<true><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
+  } else {
+    cudaError_t e = ensure_smem((const void *)k_search<false>, smem);
+    if (e != cudaSuccess) return e;
+    k_search<false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t st) {
+  k_rebalance<<<1, 1024, 0, st>>>(a, scratch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out, cudaStream_t st) {
+  k_reduce_counters<<<1, 256, 0, st>>>(wcount, n_warps, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
+                                   const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
+                                   int grid, cudaStream_t st) {
+  const size_t smem = search_smem_bytes(m);
+  cudaError_t e = ensure_smem((const void *)k_propagate_batch, smem);
+  if (e != cudaSuccess) return e;
+  k_propagate_batch<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_nodes, dom_in, var, val, best, dom_out, failed);
+  return cudaGetLastError();
+}
+
+}  // namespace csolve_dev

@@ -1,0 +1,69 @@
+// kernels.cuh -- declarations shared by kernels.cu (device code) and capi.cu (host
+// orchestration): the control block, per-warp state and launch wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "device_model.h"
+
+namespace csolve_dev {
+
+static const int WARPS_PER_BLOCK = 8;
+static const int THREADS_PER_BLOCK = WARPS_PER_BLOCK * 32;
+
+// signal values polled by every warp once per search node
+static const int SIG_RUN = 0;          // keep going
+static const int SIG_SLICE_END = 1;    // park at the next node boundary (rebalance / incumbent exchange / time slice)
+static const int SIG_STOP = 2;         // ANY: a solution was found
+
+// per-warp counters (uint64 each), accumulated over all slices
+enum { CNT_NODES = 0, CNT_CUTS, CNT_PROPS, CNT_VISITS, CNT_SOLUTIONS, CNT_REFRESH, CNT_WIDTH };
+
+struct SearchCtl {
+  int32_t signal;
+  int32_t idle;         // warps that ran out of work during the current slice
+  int32_t item_next;    // next frontier item to hand out
+  int32_t item_count;   // frontier items available
+  int32_t best;         // incumbent objective value (objective_best(), src/objective.c:133)
+  int32_t n_stored;     // assignments written to the solution buffer
+  int32_t out_count;    // expand mode: frames appended to the output frontier
+  int32_t out_dropped;  // expand mode: children that did not fit (capacity error)
+  int32_t busy;         // written by the rebalance kernel: warps that still own work
+  int32_t moved;        // written by the rebalance kernel: frames handed to idle warps
+  int32_t passed;       // expand mode: frames passed through unsplit (domain too large to enumerate)
+  int32_t pad[5];
+};
+
+struct WarpState {
+  int32_t level;   // index of the top frame of the warp's stack; < base when the warp is idle
+  int32_t base;    // lowest level the warp owns
+};
+
+struct SearchArgs {
+  DevModel m;
+  SearchCtl *ctl;
+  int32_t *stacks;            // [n_warps][n_vars + 1][frame_words]
+  WarpState *wstate;          // [n_warps]
+  unsigned long long *wcount; // [n_warps][CNT_WIDTH]
+  const int32_t *items;       // frontier pool: [item_count][frame_words]
+  int32_t *items_out;         // expand mode: output pool
+  int32_t out_cap;            // expand mode: capacity of the output pool (frames)
+  int32_t *solbuf;            // [max_solutions][n_vars + 1]  (values..., objective key)
+  int32_t max_solutions;
+  int32_t n_warps;
+  int32_t order;              // CSOLVE_ORDER_*
+  int32_t idle_exit;          // request a slice end when this many warps are idle
+  int32_t frozen_best;        // expand mode: incumbent every node of this level is propagated against
+  long long slice_cycles;     // clock64() budget of one slice
+  int32_t expand_branch_max;  // expand mode: frames with more values than this are passed through unsplit
+};
+
+size_t search_smem_bytes(const DevModel &m);
+cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s);
+cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t s);
+cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out, cudaStream_t s);
+cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
+                                   const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
+                                   int grid, cudaStream_t s);
+int search_blocks_per_sm(const DevModel &m, bool expand);
+
+}  // namespace csolve_dev

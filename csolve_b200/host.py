@@ -1,0 +1,239 @@
+"""ctypes mirror of include/csolve_b200.h.
+
+Names follow the reference's interface for this path: a *model* is what the
+front end (src/parser.y:55-85) hands to ``solve()`` (src/csolve.h:395); a
+``GpuProblem`` is that model resident on the device; ``GpuProblem.solve()`` is the
+replacement for ``solve()``; ``GpuProblem.propagate_batch()`` replays node
+transitions (bind + propagate_clauses, src/csolve.c:448-457) in bulk.
+
+There is no CPU fallback: if the CUDA library is missing or no device is
+present the calls raise ``CsolveError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+OBJ_ANY, OBJ_ALL, OBJ_MIN, OBJ_MAX = 0, 1, 2, 3
+ORDER_NONE, ORDER_SMALLEST_DOMAIN, ORDER_LARGEST_DOMAIN, ORDER_SMALLEST_VALUE, ORDER_LARGEST_VALUE = range(5)
+ORDER_NAMES = {
+    "none": ORDER_NONE,
+    "smallest-domain": ORDER_SMALLEST_DOMAIN,
+    "largest-domain": ORDER_LARGEST_DOMAIN,
+    "smallest-value": ORDER_SMALLEST_VALUE,
+    "largest-value": ORDER_LARGEST_VALUE,
+}  # the -o values of src/main.c:187-209
+
+ERR_NAMES = {
+    -1: "invalid argument", -2: "syntax error", -3: "infeasible problem", -4: "unbounded variable",
+    -5: "unsupported construct", -6: "CUDA error", -7: "no CUDA device", -8: "capacity exceeded",
+}
+
+
+class CsolveError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s (%d): %s" % (ERR_NAMES.get(code, "error"), code, message))
+        self.code = code
+        self.message = message
+
+
+class FlatModel(C.Structure):
+    """struct csolve_flat_model"""
+    _fields_ = [
+        ("n_vars", C.c_int32), ("n_nodes", C.c_int32), ("n_clauses", C.c_int32), ("n_watch", C.c_int32),
+        ("objective", C.c_int32), ("obj_var", C.c_int32),
+        ("node_op", C.POINTER(C.c_uint8)), ("node_l", C.POINTER(C.c_int32)), ("node_r", C.POINTER(C.c_int32)),
+        ("clause_first", C.POINTER(C.c_int32)), ("watch_ptr", C.POINTER(C.c_int32)),
+        ("watch_idx", C.POINTER(C.c_int32)), ("var_lo", C.POINTER(C.c_int32)), ("var_hi", C.POINTER(C.c_int32)),
+        ("var_prio", C.POINTER(C.c_int64)), ("var_name", C.POINTER(C.c_char_p)),
+    ]
+
+    def to_dict(self):
+        def arr(p, n):
+            return [p[i] for i in range(n)]
+        return dict(
+            n_vars=self.n_vars, n_nodes=self.n_nodes, n_clauses=self.n_clauses, n_watch=self.n_watch,
+            objective=self.objective, obj_var=self.obj_var,
+            node_op=arr(self.node_op, self.n_nodes), node_l=arr(self.node_l, self.n_nodes),
+            node_r=arr(self.node_r, self.n_nodes), clause_first=arr(self.clause_first, self.n_clauses + 1),
+            watch_ptr=arr(self.watch_ptr, self.n_vars + 1), watch_idx=arr(self.watch_idx, self.n_watch),
+            var_lo=arr(self.var_lo, self.n_vars), var_hi=arr(self.var_hi, self.n_vars),
+            var_prio=arr(self.var_prio, self.n_vars),
+            var_name=[self.var_name[i].decode() for i in range(self.n_vars)] if self.var_name else None,
+        )
+
+
+class _FrontOptions(C.Structure):
+    _fields_ = [("compute_weights", C.c_int32), ("objective_override", C.c_int32)]
+
+
+class _GpuConfig(C.Structure):
+    _fields_ = [("device", C.c_int32)]
+
+
+class _SolveOptions(C.Structure):
+    _fields_ = [("order", C.c_int32), ("part_rank", C.c_int32), ("part_count", C.c_int32),
+                ("split_target", C.c_int32), ("max_solutions", C.c_int32), ("time_limit_ms", C.c_int32),
+                ("slice_ms", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _GpuResult(C.Structure):
+    _fields_ = [("solutions", C.c_uint64), ("nodes", C.c_uint64), ("cuts", C.c_uint64), ("props", C.c_uint64),
+                ("clause_visits", C.c_uint64), ("best", C.c_int32), ("has_solution", C.c_int32),
+                ("timed_out", C.c_int32), ("n_stored", C.c_int32), ("kernel_ms", C.c_double),
+                ("expand_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcsolve_b200.so")
+
+
+_lib = None
+
+
+def library():
+    """Load libcsolve_b200.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise CsolveError(-6, "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback for the search path)" % path)
+    lib = C.CDLL(path)
+    I32P, U8P = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    lib.csolve_model_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_FrontOptions), C.POINTER(C.c_void_p)]
+    lib.csolve_model_flat.argtypes = [C.c_void_p]
+    lib.csolve_model_flat.restype = C.POINTER(FlatModel)
+    lib.csolve_model_free.argtypes = [C.c_void_p]
+    lib.csolve_model_free.restype = None
+    lib.csolve_gpu_init.argtypes = [C.POINTER(_GpuConfig)]
+    lib.csolve_gpu_shutdown.restype = None
+    lib.csolve_gpu_load.argtypes = [C.POINTER(FlatModel), C.POINTER(C.c_void_p)]
+    lib.csolve_gpu_unload.argtypes = [C.c_void_p]
+    lib.csolve_gpu_unload.restype = None
+    lib.csolve_gpu_propagate_batch.argtypes = [C.c_void_p, C.c_int32, I32P, I32P, I32P, I32P, I32P, U8P]
+    lib.csolve_gpu_solve.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.POINTER(_GpuResult)]
+    lib.csolve_gpu_get_solution.argtypes = [C.c_void_p, C.c_int32, I32P]
+    lib.csolve_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise CsolveError(rc, library().csolve_last_error().decode(errors="replace"))
+
+
+class Model:
+    """A parsed, root-normalised and flattened csolve instance (host side)."""
+
+    def __init__(self, text, compute_weights=True, objective=None):
+        if isinstance(text, str):
+            text = text.encode()
+        lib = library()
+        opt = _FrontOptions(1 if compute_weights else 0, -1 if objective is None else int(objective))
+        h = C.c_void_p()
+        _check(lib.csolve_model_parse(text, len(text), C.byref(opt), C.byref(h)))
+        self._h = h
+        self.flat = lib.csolve_model_flat(h).contents
+
+    @classmethod
+    def from_file(cls, path, **kw):
+        with open(path, "rb") as f:
+            return cls(f.read(), **kw)
+
+    n_vars = property(lambda self: self.flat.n_vars)
+    objective = property(lambda self: self.flat.objective)
+    obj_var = property(lambda self: self.flat.obj_var)
+
+    @property
+    def var_names(self):
+        return [self.flat.var_name[i].decode() for i in range(self.flat.n_vars)]
+
+    @property
+    def root_domains(self):
+        v = self.flat.n_vars
+        out = np.empty(2 * v, np.int32)
+        out[0::2] = [self.flat.var_lo[i] for i in range(v)]
+        out[1::2] = [self.flat.var_hi[i] for i in range(v)]
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            library().csolve_model_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SolveResult:
+    def __init__(self, r, solutions):
+        for name, _ in _GpuResult._fields_:
+            setattr(self, name, getattr(r, name))
+        self.assignments = solutions
+
+    def __repr__(self):
+        return ("SolveResult(solutions=%d, nodes=%d, cuts=%d, props=%d, best=%d, has_solution=%d, kernel_ms=%.3f)"
+                % (self.solutions, self.nodes, self.cuts, self.props, self.best, self.has_solution, self.kernel_ms))
+
+
+class GpuProblem:
+    """A model resident on one GPU."""
+
+    def __init__(self, model, device=0):
+        lib = library()
+        _check(lib.csolve_gpu_init(C.byref(_GpuConfig(device))))
+        self.model = model
+        flat = model.flat if isinstance(model, Model) else model
+        self.n_vars = flat.n_vars
+        h = C.c_void_p()
+        _check(lib.csolve_gpu_load(C.byref(flat), C.byref(h)))
+        self._h = h
+
+    def propagate_batch(self, dom_in, var, val, best=None):
+        """dom_in: [B, 2*V] int32 (lo,hi pairs); var, val: [B]; returns (dom_out [B, 2*V], failed [B] uint8)."""
+        I32P, U8P = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        dom_in = np.ascontiguousarray(dom_in, np.int32).reshape(-1, 2 * self.n_vars)
+        n = dom_in.shape[0]
+        var = np.ascontiguousarray(var, np.int32).reshape(n)
+        val = np.ascontiguousarray(val, np.int32).reshape(n)
+        bestp = None
+        if best is not None:
+            best = np.ascontiguousarray(np.broadcast_to(np.asarray(best, np.int32), (n,)))
+            bestp = best.ctypes.data_as(I32P)
+        out = np.empty_like(dom_in)
+        failed = np.empty(n, np.uint8)
+        _check(library().csolve_gpu_propagate_batch(
+            self._h, n, dom_in.ctypes.data_as(I32P), var.ctypes.data_as(I32P), val.ctypes.data_as(I32P),
+            bestp, out.ctypes.data_as(I32P), failed.ctypes.data_as(U8P)))
+        return out, failed
+
+    def solve(self, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0,
+              time_limit_ms=0, slice_ms=0):
+        if isinstance(order, str):
+            order = ORDER_NAMES[order]
+        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms, 0)
+        res = _GpuResult()
+        _check(library().csolve_gpu_solve(self._h, C.byref(opt), C.byref(res)))
+        sols = []
+        buf = (C.c_int32 * self.n_vars)()
+        for i in range(res.n_stored):
+            _check(library().csolve_gpu_get_solution(self._h, i, buf))
+            sols.append(list(buf))
+        return SolveResult(res, sols)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            library().csolve_gpu_unload(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
