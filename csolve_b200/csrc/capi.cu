@@ -323,12 +323,14 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
     }
     n_items = (int)(mine.size() / fw);
     if (n_items > 0) CUDA_TRY(cudaMemcpyAsync(pin, mine.data(), mine.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (opt.part_rank != 0) {
-      // the expansion was replicated on every rank: only rank 0 reports its counters and leaves
-      CUDA_TRY(cudaMemsetAsync(p->wcount, 0, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long), st));
-      if (m.objective == CSOLVE_OBJ_ALL) ctl.n_stored = 0;
-    }
     CUDA_TRY(cudaStreamSynchronize(st));
+  }
+
+  if (opt.part_count > 1 && opt.part_rank != 0) {
+    // the expansion was replicated on every rank (also when it exhausted the whole tree):
+    // only rank 0 reports its counters and the leaves found in it
+    CUDA_TRY(cudaMemsetAsync(p->wcount, 0, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long), st));
+    if (m.objective == CSOLVE_OBJ_ALL) ctl.n_stored = 0;
   }
 
   // ---- time-sliced persistent search -----------------------------------------------------------------------

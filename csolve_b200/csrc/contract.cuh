@@ -157,10 +157,10 @@ struct PFrame { int32_t node, lo, hi, phase; };
 // child has already been handled and the left child is next (the reference always
 // contracts the right operand first, re-evaluates, then the left one).
 template <class Cx>
-CSOLVE_HD_NOINLINE bool contract_generic(Cx &cx, const DevModel &m, int root) {
+CSOLVE_HD_NOINLINE bool contract_generic(Cx &cx, const DevModel &m, int root, int32_t vlo = 1, int32_t vhi = 1) {
   PFrame st[MAX_DEPTH + 2];
   int sp = 1;
-  st[0].node = root; st[0].lo = 1; st[0].hi = 1; st[0].phase = 0;
+  st[0].node = root; st[0].lo = vlo; st[0].hi = vhi; st[0].phase = 0;
   while (sp > 0) {
     PFrame &f = st[sp - 1];
     const int n = f.node;

@@ -1,0 +1,56 @@
+"""One process per GPU: the search tree is partitioned across ranks, results are reduced.
+
+The reference's only parallel strategy is search-space splitting (worker_spawn, src/csolve.c:105-152)
+with a shared incumbent / solution counter (struct shared_t, src/csolve.h:259-266). Here every rank
+expands the root frontier identically, keeps the sub-trees whose path hash maps to it and searches them
+with no data-path collective; one reduction at the end combines
+    solutions, nodes, cuts, props, clause visits   -> SUM
+    incumbent (MIN / MAX objective)                -> MIN / MAX
+    time                                           -> MAX over ranks
+torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+from .host import OBJ_ANY, OBJ_MAX, OBJ_MIN
+
+
+def reduce_results(res, objective, device=None, group=None):
+    """res: SolveResult-like of this rank -> dict with the whole-job totals (same on every rank)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(solutions=int(res.solutions), nodes=int(res.nodes), cuts=int(res.cuts), props=int(res.props),
+                    clause_visits=int(res.clause_visits), best=int(res.best), has_solution=int(res.has_solution),
+                    timed_out=int(res.timed_out), kernel_ms=float(res.kernel_ms), expand_ms=float(res.expand_ms),
+                    kernel_launches=int(res.kernel_launches), kernel_ms_min=float(res.kernel_ms))
+    dev = device if device is not None else torch.device("cpu")
+    sums = torch.tensor([res.solutions, res.nodes, res.cuts, res.props, res.clause_visits, res.kernel_launches],
+                        dtype=torch.int64, device=dev)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    flags = torch.tensor([res.has_solution, res.timed_out], dtype=torch.int64, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    # a rank without a solution must not win the incumbent reduction
+    neutral = 2**31 - 1 if objective == OBJ_MIN else -2**31
+    mine = int(res.best) if res.has_solution else neutral
+    best = torch.tensor([mine], dtype=torch.int64, device=dev)
+    if objective == OBJ_MIN:
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    elif objective == OBJ_MAX:
+        dist.all_reduce(best, op=dist.ReduceOp.MAX, group=group)
+    times = torch.tensor([res.kernel_ms, res.expand_ms, -res.kernel_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(times, op=dist.ReduceOp.MAX, group=group)
+    s = sums.tolist()
+    solutions = s[0]
+    if objective == OBJ_ANY:
+        solutions = min(solutions, 1)   # found_any(): one solution is reported (src/csolve.c:207-209)
+    return dict(solutions=solutions, nodes=s[1], cuts=s[2], props=s[3], clause_visits=s[4], kernel_launches=s[5],
+                best=int(best.item()) if objective in (OBJ_MIN, OBJ_MAX) and flags[0].item() else int(res.best),
+                has_solution=int(flags[0].item()), timed_out=int(flags[1].item()),
+                kernel_ms=float(times[0].item()), expand_ms=float(times[1].item()), kernel_ms_min=float(-times[2].item()))
+
+
+def solve_partitioned(problem, objective, device=None, group=None, **solve_kw):
+    """Search this rank's share of the tree and reduce. `problem` is a GpuProblem (or anything with .solve)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    res = problem.solve(part_rank=rank, part_count=world, **solve_kw)
+    return reduce_results(res, objective, device=device, group=group), res

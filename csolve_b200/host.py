@@ -137,6 +137,7 @@ class Model:
         _check(lib.csolve_model_parse(text, len(text), C.byref(opt), C.byref(h)))
         self._h = h
         self.flat = lib.csolve_model_flat(h).contents
+        self.flat._owner = self   # the arrays belong to the C model: keep it alive as long as the view
 
     @classmethod
     def from_file(cls, path, **kw):

@@ -410,6 +410,20 @@ int orc_leaf_true(orc *o, const int32_t *dom_in) {
   return root_true(o);
 }
 
+/* unit-vector hooks: propagate [vlo,vhi] into the root of clause 0 / evaluate it */
+int orc_prop_root(orc *o, const int32_t *dom_in, int32_t vlo, int32_t vhi, int32_t *dom_out) {
+  reset(o, CSOLVE_ORDER_NONE, 1);
+  for (int v = 0; v < o->V; v++) o->dom[v] = mkv(dom_in[2 * v], dom_in[2 * v + 1]);
+  int r = prop(o, o->cfirst[1] - 1, mkv(vlo, vhi));
+  for (int v = 0; v < o->V; v++) { dom_out[2 * v] = o->dom[v].lo; dom_out[2 * v + 1] = o->dom[v].hi; }
+  return r;
+}
+void orc_eval_root(orc *o, const int32_t *dom_in, int32_t *out2) {
+  for (int v = 0; v < o->V; v++) o->dom[v] = mkv(dom_in[2 * v], dom_in[2 * v + 1]);
+  val_t r = ev(o, o->cfirst[1] - 1);
+  out2[0] = r.lo; out2[1] = r.hi;
+}
+
 typedef struct orc_result {
   uint64_t solutions, calls, cuts, props;
   int32_t best, has_solution, hit_limit, pad;

@@ -80,6 +80,25 @@ extern "C" int hc_leaf_true(const int32_t *dom_in) {
   return 1;
 }
 
+// propagate [vlo,vhi] into the root of clause 0 / evaluate it (unit-vector tests)
+extern "C" int hc_prop_root(const int32_t *dom_in, int32_t vlo, int32_t vhi, int32_t *dom_out) {
+  const DevModel &m = g_cm.host;
+  std::vector<int32_t> d(dom_in, dom_in + 2 * m.n_vars);
+  std::vector<int> queue; std::vector<uint8_t> queued(m.n_vars, 0);
+  HostCx cx{d.data(), &queue, &queued};
+  bool ok = contract_generic(cx, m, m.clause[0].b, vlo, vhi);
+  memcpy(dom_out, d.data(), sizeof(int32_t) * 2 * m.n_vars);
+  return ok ? (int)cx.props : -1;
+}
+extern "C" void hc_eval_root(const int32_t *dom_in, int32_t *out2) {
+  const DevModel &m = g_cm.host;
+  std::vector<int32_t> d(dom_in, dom_in + 2 * m.n_vars);
+  std::vector<int> queue; std::vector<uint8_t> queued(m.n_vars, 0);
+  HostCx cx{d.data(), &queue, &queued};
+  Dom v = eval_subtree(cx, m, m.clause[0].b);
+  out2[0] = v.lo; out2[1] = v.hi;
+}
+
 extern "C" int32_t hc_sneg(int32_t a) { return sneg(a); }
 extern "C" int32_t hc_sadd(int32_t a, int32_t b) { return sadd(a, b); }
 extern "C" int32_t hc_smul(int32_t a, int32_t b) { return smul(a, b); }

@@ -1,0 +1,84 @@
+"""The C-ABI library loads, exports every symbol include/csolve_b200.h declares, and the device
+entry points fail loudly (never fall back to a CPU path) when no GPU is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import csolve_b200 as cb
+import util
+from csolve_b200 import instances as I
+
+HEADER = os.path.join(util.ROOT, "include", "csolve_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(csolve_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    lib = cb.library()
+    names = declared_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    out = subprocess.run(["nm", "-D", "--defined-only", cb.library_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (csolve_\w+)", out))
+    assert set(names) <= exported
+
+
+def test_abi_version():
+    assert cb.library().csolve_abi_version() == 1
+
+
+def test_header_compiles_as_c():
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER])
+
+
+def test_library_contains_sm100a_code():
+    out = subprocess.run(["cuobjdump", "-lelf", cb.library_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_does_not_reference_oracle():
+    """nothing under csolve_b200/, include/ or integration/ may use oracle/"""
+    for base in ("csolve_b200", "include", "integration"):
+        for dp, _, files in os.walk(os.path.join(util.ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".c", ".cpp", ".cu", ".cuh", ".h", ".hpp")):
+                    text = open(os.path.join(dp, f), errors="replace").read()
+                    assert "csolve_oracle" not in text and "liboracle" not in text and "orc_" not in text, os.path.join(dp, f)
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_device_is_a_loud_error():
+    m = cb.Model(I.queens(4))
+    with pytest.raises(cb.CsolveError) as e:
+        cb.GpuProblem(m)
+    assert e.value.code == -7 and "no CPU fallback" in e.value.message
+
+
+def test_invalid_models_are_rejected_before_touching_the_device():
+    """compile_model() validation through the harness (same code csolve_gpu_load runs first)"""
+    hc = util.harness_lib()
+    m = cb.Model(I.queens(4))
+    d = m.flat
+    bad = cb.FlatModel.from_buffer_copy(d)
+    bad.obj_var = 2            # ALL with an objective variable
+    assert hc.hc_load(bad, 1) == -1
+    bad = cb.FlatModel.from_buffer_copy(d)
+    bad.n_clauses = d.n_clauses - 1
+    assert hc.hc_load(bad, 1) == -1
+    assert hc.hc_load(d, 1) == 0

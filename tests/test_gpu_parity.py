@@ -1,0 +1,270 @@
+"""Parity tests proper (run on the B200 with -m gpu): the CUDA path, called through the C ABI,
+against the oracle, the reference-generated golden fixtures and size-independent properties."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import csolve_b200 as cb
+import util
+from csolve_b200 import instances as I
+from make_instances import instance_table, random_table
+
+pytestmark = pytest.mark.gpu
+
+INST = instance_table()
+REPLAY = sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(util.GOLDEN, "replay_*.npz")) if "random" not in p)
+COUNTS = json.load(open(os.path.join(util.GOLDEN, "ref_counts.json")))
+
+
+def _load(name):
+    z = np.load(os.path.join(util.GOLDEN, "replay_%s.npz" % name))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("name", REPLAY)
+def test_node_transitions_match_reference_fixtures(name):
+    """bit-exact post-fixpoint domains and fail flags on nodes replayed through the reference"""
+    g = _load(name)
+    m = cb.Model(INST[name])
+    p = cb.GpuProblem(m)
+    out, failed = p.propagate_batch(g["dom_in"], g["var"], g["val"], g["best"])
+    assert np.array_equal(failed.astype(bool), g["failed"].astype(bool))
+    ok = ~g["failed"].astype(bool)
+    assert np.array_equal(out[ok], g["dom_out"][ok])
+
+
+def test_node_transitions_random_instances():
+    z = np.load(os.path.join(util.GOLDEN, "replay_random.npz"))
+    g = {k: z[k] for k in z.files}
+    rnd = random_table()
+    n = 0
+    for name in sorted({k.split("/")[0] for k in g}):
+        sub = {k.split("/")[1]: g[k] for k in g if k.startswith(name + "/")}
+        p = cb.GpuProblem(cb.Model(rnd[name]))
+        out, failed = p.propagate_batch(sub["dom_in"], sub["var"], sub["val"], sub["best"])
+        assert np.array_equal(failed.astype(bool), sub["failed"].astype(bool)), name
+        ok = ~sub["failed"].astype(bool)
+        assert np.array_equal(out[ok], sub["dom_out"][ok]), name
+        n += len(failed)
+    assert n > 500
+
+
+def test_node_transitions_against_oracle_on_seeded_walks():
+    """fresh seeded walks (not in the fixtures), oracle as checker, batch of ~20k nodes"""
+    import random
+    for name in ("queens10", "sudoku", "wcet", "sat100"):
+        m = cb.Model(INST[name])
+        orc = util.Oracle(m)
+        p = cb.GpuProblem(m)
+        rng = random.Random(99)
+        V = m.n_vars
+        root = m.root_domains
+        doms, vs, xs, bs, eo, ef = [], [], [], [], [], []
+        while len(doms) < 5000:
+            dom = root.copy()
+            un = list(range(V)); rng.shuffle(un)
+            best = 2**31 - 1 if m.objective == 2 else (-2**31 if m.objective == 3 else 0)
+            if m.obj_var >= 0 and rng.random() < 0.7:
+                best = rng.randint(int(root[2 * m.obj_var]), int(root[2 * m.obj_var + 1]))
+            while un:
+                x = un.pop()
+                v = rng.randint(int(dom[2 * x]), int(dom[2 * x + 1]))
+                o, f = orc.node(dom, x, v, best)
+                if not f and m.obj_var >= 0 and o[2 * m.obj_var] > o[2 * m.obj_var + 1]:
+                    f = 1
+                doms.append(dom.copy()); xs.append(x); vs.append(v); bs.append(best); eo.append(o); ef.append(f)
+                if f:
+                    break
+                dom = o
+        out, failed = p.propagate_batch(np.array(doms), xs, vs, bs)
+        ef = np.array(ef, bool)
+        assert np.array_equal(failed.astype(bool), ef), name
+        assert np.array_equal(out[~ef], np.array(eo)[~ef]), name
+
+
+ORDERS = [cb.ORDER_NONE, cb.ORDER_SMALLEST_DOMAIN, cb.ORDER_LARGEST_DOMAIN, cb.ORDER_SMALLEST_VALUE, cb.ORDER_LARGEST_VALUE]
+
+
+@pytest.mark.parametrize("name", ["queens4", "queens6", "queens8", "queens10", "sudoku", "sat20all", "sat50all", "sat50"])
+@pytest.mark.parametrize("order", ORDERS)
+def test_all_solutions_counters_equal_oracle(name, order):
+    """ALL mode: solutions, nodes and cuts are traversal-independent -> identical to the oracle's tree"""
+    text = INST[name] if name != "sat50" else I.random_3sat(50, seed=1, objective="ALL")
+    m = cb.Model(text)
+    r = cb.GpuProblem(m).solve(order=order)
+    o, _ = util.Oracle(m).solve_tree(order)
+    assert (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
+    if name in COUNTS and m.objective == cb.OBJ_ALL:
+        assert r.solutions == COUNTS[name]["nocf"]["solutions"]     # the reference CLI's count
+
+
+@pytest.mark.parametrize("split", [1, 64, 4096, 0])
+def test_counters_do_not_depend_on_the_split(split):
+    m = cb.Model(I.queens(9))
+    o, _ = util.Oracle(m).solve_tree(0)
+    r = cb.GpuProblem(m).solve(split_target=split, slice_ms=1)
+    assert (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts) == (352, o.calls, o.cuts)
+
+
+def test_stored_solutions_are_valid_and_distinct():
+    m = cb.Model(I.queens(8))
+    r = cb.GpuProblem(m).solve(max_solutions=200)
+    assert r.solutions == 92 and len(r.assignments) == 92
+    orc = util.Oracle(m)
+    seen = set()
+    for a in r.assignments:
+        dom = np.repeat(np.array(a, np.int32), 2)
+        assert orc.leaf_true(dom)
+        seen.add(tuple(a))
+    assert len(seen) == 92
+
+
+@pytest.mark.parametrize("name", ["queens8any", "sudoku_any", "sat100"])
+def test_any_returns_a_valid_assignment(name):
+    m = cb.Model(INST[name])
+    r = cb.GpuProblem(m).solve()
+    assert r.has_solution == 1 and r.solutions == 1 and len(r.assignments) == 1
+    assert util.Oracle(m).leaf_true(np.repeat(np.array(r.assignments[0], np.int32), 2))
+    if name == "sudoku_any":   # unique solution: must be the one the reference prints
+        printed = dict(kv.split(" = ") for kv in COUNTS[name]["nocf"]["last_solution"].split(", "))
+        assert [int(printed[n]) for n in m.var_names] == r.assignments[0]
+
+
+def test_unsat_reports_no_solution():
+    r = cb.GpuProblem(cb.Model(INST["sat50"])).solve()
+    assert r.has_solution == 0 and r.solutions == 0 and COUNTS["sat50"]["nocf"]["no_solution"]
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_schedule_optimum(order):
+    m = cb.Model(INST["schedule"])
+    r = cb.GpuProblem(m).solve(order=order)
+    assert r.best == COUNTS["schedule"]["nocf"]["best"] == 11 and r.has_solution
+    w = dict(zip(m.var_names, r.assignments[-1]))
+    assert w["end"] == 11 and w["<obj>"] == 11
+    assert util.Oracle(m).leaf_true(np.repeat(np.array(r.assignments[-1], np.int32), 2))
+
+
+@pytest.mark.parametrize("order", [cb.ORDER_NONE, cb.ORDER_SMALLEST_DOMAIN])
+def test_wcet_optimum(order):
+    m = cb.Model(INST["wcet"])
+    r = cb.GpuProblem(m).solve(order=order)
+    assert r.best == COUNTS["wcet"]["known_optimum"] == 1560
+    w = dict(zip(m.var_names, r.assignments[-1]))
+    assert w["<obj>"] == 1560
+    assert util.Oracle(m).leaf_true(np.repeat(np.array(r.assignments[-1], np.int32), 2))
+
+
+def test_random_optimisation_instances_match_oracle():
+    """MIN/MAX on random instances: optimum (or infeasibility) equals the oracle's reference-mode run"""
+    rnd = random_table()
+    n = 0
+    for name, text in sorted(rnd.items()):
+        if not (text.startswith("MIN") or text.startswith("MAX")):
+            continue
+        try:
+            m = cb.Model(text)
+        except cb.CsolveError:
+            continue
+        o, _ = util.Oracle(m).solve_reference(max_calls=200000)
+        if o.hit_limit:
+            continue
+        r = cb.GpuProblem(m).solve()
+        assert bool(r.has_solution) == bool(o.has_solution), name
+        if o.has_solution:
+            assert r.best == o.best, name
+        n += 1
+    assert n >= 10
+
+
+def test_random_all_instances_match_oracle():
+    rnd = random_table()
+    n = 0
+    for name, text in sorted(rnd.items()):
+        if not text.startswith("ALL"):
+            continue
+        try:
+            m = cb.Model(text)
+        except cb.CsolveError:
+            continue
+        o, _ = util.Oracle(m).solve_tree(0, max_calls=300000)
+        if o.hit_limit:
+            continue
+        r = cb.GpuProblem(m).solve()
+        assert (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts), name
+        n += 1
+    assert n >= 15
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+@pytest.mark.parametrize("split", [200, 1000000])
+def test_partitions_are_disjoint_and_complete(parts, split):
+    """multi-GPU partitioning, emulated on one GPU: the parts sum to the whole tree exactly.
+    split=200: the frontier is dealt to the ranks by path hash; split=1000000: the breadth-first
+    expansion exhausts the tree on every rank and only rank 0 may report it."""
+    m = cb.Model(I.queens(10))
+    p = cb.GpuProblem(m)
+    whole = p.solve(split_target=split)
+    tot = [0, 0, 0]
+    per = []
+    for r in range(parts):
+        x = p.solve(part_rank=r, part_count=parts, split_target=split)
+        tot[0] += x.solutions; tot[1] += x.nodes; tot[2] += x.cuts
+        per.append(x.solutions)
+    assert tuple(tot) == (whole.solutions, whole.nodes, whole.cuts) == (724, whole.nodes, whole.cuts)
+    if split == 200:
+        assert max(per) < 724 and min(per) > 0
+
+
+def test_edge_cases():
+    # one variable, domain of one value
+    r = cb.GpuProblem(cb.Model("ALL; x = 3;")).solve(max_solutions=4)
+    assert (r.solutions, r.nodes, r.assignments) == (1, 1, [[3]])
+    # fails at the first level
+    r = cb.GpuProblem(cb.Model("ALL; 0 <= x; x <= 2; 0 <= y; y <= 2; x != y; x + y = 4 | x + y = 0;")).solve()
+    assert (r.solutions, r.has_solution, r.nodes, r.cuts) == (0, 0, 3, 3)
+    # everything fixed at root: empty watch lists (the reference's fuzz/inputs/sat.txt shape)
+    t = "ANY; (!x1|!x2|!x3) & (!x2|!x3|!x4) & (!x2|!x2|x3) & (x2|x2|x2); 0<=x1;x1<=1; 0<=x2;x2<=1; 0<=x3;x3<=1; 0<=x4;x4<=1;"
+    r = cb.GpuProblem(cb.Model(t)).solve()
+    assert r.assignments == [[0, 1, 1, 0]] and r.nodes == 4
+    # a huge domain is bisected, never enumerated breadth-first
+    r = cb.GpuProblem(cb.Model("MIN x; 5 <= x; x <= 2000000000; y = x + 1;")).solve()
+    assert r.best == 5
+    # negative domains, multiplication, both objective directions
+    t = "-4 <= a; a <= 4; -4 <= b; b <= 4; a * b = 6; a < b;"
+    o, _ = util.Oracle(cb.Model("ALL;" + t)).solve_tree(0)
+    r = cb.GpuProblem(cb.Model("ALL;" + t)).solve()
+    assert r.solutions == o.solutions == 2
+    assert cb.GpuProblem(cb.Model("MAX a - b;" + t)).solve().best == -1
+    assert cb.GpuProblem(cb.Model("MIN a + b;" + t)).solve().best == -5
+
+
+def test_time_limit_reports_timeout():
+    r = cb.GpuProblem(cb.Model(I.queens(15))).solve(time_limit_ms=20, slice_ms=5)
+    assert r.timed_out == 1 and r.solutions < 2279184
+
+
+def test_batched_sudoku_instances():
+    """config 2 in miniature: generated unique-solution puzzles, one search root each"""
+    for g in I.sudoku_batch(12, seed=20261018):
+        m = cb.Model(I.sudoku(g))
+        r = cb.GpuProblem(m).solve(order=cb.ORDER_SMALLEST_DOMAIN, max_solutions=2)
+        assert r.solutions == 1
+        sol = dict(zip(m.var_names, r.assignments[0]))
+        for rr in range(9):
+            for cc in range(9):
+                if g[rr * 9 + cc] != ".":
+                    assert sol[I._cell(rr, cc)] == int(g[rr * 9 + cc])
+
+
+def test_queens_full_size_counts():
+    """BASELINE config 3 sizes; counts from OEIS A000170 (== the reference CLI's)"""
+    for n, cnt in ((12, 14200), (13, 73712), (14, 365596)):
+        r = cb.GpuProblem(cb.Model(I.queens(n))).solve()
+        assert r.solutions == cnt
+        # mirror symmetry X -> n+1-X: the tree differs, the count cannot
+    r = cb.GpuProblem(cb.Model(I.queens(14))).solve(order=cb.ORDER_SMALLEST_DOMAIN)
+    assert r.solutions == 365596

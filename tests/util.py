@@ -1,0 +1,215 @@
+"""Shared test helpers: build/load the oracle, the host contractor harness and (when present)
+the compiled reference; small flat-model builder for unit vectors."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_SO = os.path.join(ROOT, "oracle", "libcsolve_oracle.so")
+HARNESS_SO = os.path.join(ROOT, "tests", "harness", "libhost_contract.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libcsolve_ref.so")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "csolve_ref")
+
+I32P = C.POINTER(C.c_int32)
+DMIN, DMAX = -2**31, 2**31 - 1
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def build_oracle():
+    src = os.path.join(ROOT, "oracle", "csolve_oracle.c")
+    if not _newer(ORACLE_SO, [src, os.path.join(ROOT, "include", "csolve_b200.h")]):
+        subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                               src, "-o", ORACLE_SO])
+    return ORACLE_SO
+
+
+def build_harness():
+    csrc = os.path.join(ROOT, "csolve_b200", "csrc")
+    srcs = [os.path.join(ROOT, "tests", "harness", "host_contract.cpp"), os.path.join(csrc, "compile.cpp"),
+            os.path.join(csrc, "contract.cuh"), os.path.join(csrc, "device_model.h"), os.path.join(csrc, "compile.hpp")]
+    if not _newer(HARNESS_SO, srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                               "-I", csrc, srcs[0], srcs[1], "-o", HARNESS_SO])
+    return HARNESS_SO
+
+
+def ensure_built():
+    import csolve_b200
+    if not os.path.exists(csolve_b200.library_path()):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "csolve_b200", "csrc")])
+    build_oracle()
+    build_harness()
+
+
+class OrcResult(C.Structure):
+    _fields_ = [("solutions", C.c_uint64), ("calls", C.c_uint64), ("cuts", C.c_uint64), ("props", C.c_uint64),
+                ("best", C.c_int32), ("has_solution", C.c_int32), ("hit_limit", C.c_int32), ("pad", C.c_int32)]
+
+
+_orc = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        import csolve_b200 as cb
+        lib = C.CDLL(build_oracle())
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_create.argtypes = [C.POINTER(cb.FlatModel)]
+        lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_node.argtypes = [C.c_void_p, I32P, C.c_int, C.c_int32, C.c_int32, I32P]
+        lib.orc_leaf_true.argtypes = [C.c_void_p, I32P]
+        lib.orc_prop_root.argtypes = [C.c_void_p, I32P, C.c_int32, C.c_int32, I32P]
+        lib.orc_eval_root.argtypes = [C.c_void_p, I32P, I32P]
+        lib.orc_solve_reference.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.POINTER(OrcResult), I32P]
+        lib.orc_solve_tree.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(OrcResult), I32P]
+        for f in ("orc_neg", "orc_add", "orc_mul", "orc_min", "orc_max"):
+            getattr(lib, f).restype = C.c_int32
+        _orc = lib
+    return _orc
+
+
+def p32(a):
+    return a.ctypes.data_as(I32P)
+
+
+class Oracle:
+    """The CPU restatement (oracle/csolve_oracle.c) over a flat model."""
+
+    def __init__(self, model):
+        # accepts a csolve_b200.Model (kept alive: the flat arrays belong to it) or a bare FlatModel
+        self.lib = oracle_lib()
+        self._owner = model
+        flat = model.flat if hasattr(model, "flat") else model
+        self.flat = flat
+        self.V = flat.n_vars
+        self.h = self.lib.orc_create(C.byref(flat))
+
+    def node(self, dom_in, var, val, best=0):
+        dom_in = np.ascontiguousarray(dom_in, np.int32)
+        out = np.empty(2 * self.V, np.int32)
+        f = self.lib.orc_node(self.h, p32(dom_in), int(var), int(val), int(best), p32(out))
+        return out, int(f)
+
+    def leaf_true(self, dom):
+        dom = np.ascontiguousarray(dom, np.int32)
+        return bool(self.lib.orc_leaf_true(self.h, p32(dom)))
+
+    def prop_root(self, dom_in, vlo, vhi):
+        dom_in = np.ascontiguousarray(dom_in, np.int32)
+        out = np.empty(2 * self.V, np.int32)
+        r = self.lib.orc_prop_root(self.h, p32(dom_in), vlo, vhi, p32(out))
+        return out, r
+
+    def eval_root(self, dom_in):
+        dom_in = np.ascontiguousarray(dom_in, np.int32)
+        out = np.empty(2, np.int32)
+        self.lib.orc_eval_root(self.h, p32(dom_in), p32(out))
+        return [int(out[0]), int(out[1])]
+
+    def solve_reference(self, order=0, prefer_failing=1, max_calls=0):
+        r = OrcResult()
+        sol = np.zeros(max(self.V, 1), np.int32)
+        self.lib.orc_solve_reference(self.h, order, prefer_failing, max_calls, C.byref(r), p32(sol))
+        return r, sol[:self.V].copy()
+
+    def solve_tree(self, order=0, max_calls=0):
+        r = OrcResult()
+        sol = np.zeros(max(self.V, 1), np.int32)
+        self.lib.orc_solve_tree(self.h, order, max_calls, C.byref(r), p32(sol))
+        return r, sol[:self.V].copy()
+
+    def __del__(self):
+        try:
+            self.lib.orc_destroy(self.h)
+        except Exception:
+            pass
+
+
+_hc = None
+
+
+def harness_lib():
+    global _hc
+    if _hc is None:
+        import csolve_b200 as cb
+        lib = C.CDLL(build_harness())
+        lib.hc_load.argtypes = [C.POINTER(cb.FlatModel), C.c_int]
+        lib.hc_error.restype = C.c_char_p
+        lib.hc_node.argtypes = [I32P, C.c_int, C.c_int32, C.c_int32, I32P]
+        lib.hc_leaf_true.argtypes = [I32P]
+        lib.hc_prop_root.argtypes = [I32P, C.c_int32, C.c_int32, I32P]
+        lib.hc_eval_root.argtypes = [I32P, I32P]
+        for f in ("hc_sneg", "hc_sadd", "hc_smul"):
+            getattr(lib, f).restype = C.c_int32
+        _hc = lib
+    return _hc
+
+
+def reference_lib():
+    """The compiled reference (oracle/_ref), or None when it has not been built (no /root/reference)."""
+    if not os.path.exists(REF_SO):
+        return None
+    lib = C.CDLL(REF_SO)
+    import csolve_b200 as cb
+    lib.ref_flat.restype = C.POINTER(cb.FlatModel)
+    lib.ref_replay.argtypes = [I32P, C.c_int, C.c_int32, C.c_int32, I32P, C.c_void_p]
+    lib.ref_get_domains.argtypes = [I32P]
+    lib.ref_eval_root.argtypes = [I32P]
+    return lib
+
+
+# ---- hand-built flat models for unit vectors ------------------------------------------------------
+OPS = {"EQ": 2, "LT": 3, "NEG": 4, "ADD": 5, "MUL": 6, "NOT": 7, "AND": 8, "OR": 9}
+
+
+class HandModel:
+    """A flat model with one clause OP(v0[, v1]) over free variables (no watch lists)."""
+
+    def __init__(self, op, n_operands, domains):
+        import csolve_b200 as cb
+        V = len(domains)
+        ops, ls, rs = [], [], []
+        for i in range(n_operands):
+            ops.append(0); ls.append(i); rs.append(-1)
+        if n_operands == 1:
+            ops.append(OPS[op]); ls.append(0); rs.append(-1)
+        else:
+            ops.append(OPS[op]); ls.append(0); rs.append(1)
+        n = len(ops)
+        self._keep = dict(
+            op=(C.c_uint8 * n)(*ops), l=(C.c_int32 * n)(*ls), r=(C.c_int32 * n)(*rs),
+            cf=(C.c_int32 * 2)(0, n), wp=(C.c_int32 * (V + 1))(*([0] * (V + 1))), wi=(C.c_int32 * 1)(0),
+            # root domains are irrelevant for the unit hooks (they take explicit domains); keep them finite
+            lo=(C.c_int32 * V)(*([-(1 << 30)] * V)), hi=(C.c_int32 * V)(*([1 << 30] * V)),
+            prio=(C.c_int64 * V)(*([0] * V)))
+        k = self._keep
+        f = cb.FlatModel()
+        f.n_vars, f.n_nodes, f.n_clauses, f.n_watch, f.objective, f.obj_var = V, n, 1, 0, 1, -1
+        f.node_op = C.cast(k["op"], C.POINTER(C.c_uint8)); f.node_l = C.cast(k["l"], I32P); f.node_r = C.cast(k["r"], I32P)
+        f.clause_first = C.cast(k["cf"], I32P); f.watch_ptr = C.cast(k["wp"], I32P); f.watch_idx = C.cast(k["wi"], I32P)
+        f.var_lo = C.cast(k["lo"], I32P); f.var_hi = C.cast(k["hi"], I32P)
+        f.var_prio = C.cast(k["prio"], C.POINTER(C.c_int64)); f.var_name = None
+        self.flat = f
+
+
+def flat_digest(flat):
+    """canonical digest of a flat model (names included)"""
+    d = flat.to_dict()
+    return hashlib.sha256(json.dumps(d, sort_keys=True).encode()).hexdigest()
+
+
+def load_vectors():
+    with open(os.path.join(GOLDEN, "ref_unit_vectors.json")) as f:
+        return json.load(f)
