@@ -145,7 +145,7 @@ extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **
     if (rc != CSOLVE_OK) return rc;                                 \
     p->allocs.push_back((void *)d.field);                           \
   } while (0)
-  UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx);
+  UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
 #undef UP

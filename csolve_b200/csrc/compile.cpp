@@ -127,6 +127,48 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   }
   if (max_depth > MAX_DEPTH) { err = "clause expression too deep for the device interpreter"; return CSOLVE_ERR_UNSUPPORTED; }
 
+  // ---- watch records: per variable, the NOT(EQ) clauses grouped by partner, then the generic ones ----
+  out.wrec.clear();
+  out.wrec_ptr.assign(V + 1, 0);
+  if (V >= (1 << 28) || C >= (1 << 28)) { err = "model too large for the watch record encoding"; return CSOLVE_ERR_UNSUPPORTED; }
+  for (int v = 0; v < V; v++) {
+    out.wrec_ptr[v] = (int32_t)out.wrec.size();
+    struct Group { int partner; std::vector<int32_t> offs; };
+    std::vector<Group> vv;                 // NE_VV groups in first-seen order
+    std::vector<int32_t> consts;           // NE_VC constants
+    std::vector<int32_t> generic;
+    for (int w = m.watch_ptr[v]; w < m.watch_ptr[v + 1]; w++) {
+      const int c = m.watch_idx[w];
+      const ClauseRec &rec = out.clause[c];
+      if (rec.kind == CK_NE_VV && (rec.a == v || rec.b == v)) {
+        // clause: a + c != b. Seen from a: self + c != partner; seen from b: self + (-c) != partner
+        const int partner = rec.a == v ? rec.b : rec.a;
+        const int32_t off = rec.a == v ? rec.c : -rec.c;
+        Group *g = nullptr;
+        for (auto &x : vv) if (x.partner == partner) { g = &x; break; }
+        if (!g) { vv.push_back(Group{partner, {}}); g = &vv.back(); }
+        if (std::find(g->offs.begin(), g->offs.end(), off) == g->offs.end()) g->offs.push_back(off);
+      } else if (rec.kind == CK_NE_VC && rec.a == v) {
+        if (std::find(consts.begin(), consts.end(), rec.c) == consts.end()) consts.push_back(rec.c);
+      } else {
+        generic.push_back(c);
+      }
+    }
+    auto emit = [&](uint32_t kind, int arg, const std::vector<int32_t> &vals) {
+      for (size_t i = 0; i < vals.size(); i += 3) {
+        WatchRec r; r.c[0] = r.c[1] = r.c[2] = 0;
+        const int n = (int)std::min<size_t>(3, vals.size() - i);
+        for (int k = 0; k < n; k++) r.c[k] = vals[i + k];
+        r.w0 = (kind << 30) | ((uint32_t)n << 28) | (uint32_t)arg;
+        out.wrec.push_back(r);
+      }
+    };
+    for (auto &g : vv) emit(WK_NE_VV, g.partner, g.offs);
+    if (!consts.empty()) emit(WK_NE_VC, 0, consts);
+    for (int c : generic) { WatchRec r; r.w0 = (WK_GENERIC << 30) | (1u << 28) | (uint32_t)c; r.c[0] = r.c[1] = r.c[2] = 0; out.wrec.push_back(r); }
+  }
+  out.wrec_ptr[V] = (int32_t)out.wrec.size();
+
   // static branching order: priority descending, index ascending (the reference's heap with
   // -o none -f true orders by env_t.prio only, src/strategy.c:79-121)
   out.order.resize(V);
@@ -148,6 +190,13 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   h.clause = out.clause.data();
   h.watch_ptr = out.watch_ptr.data();
   h.watch_idx = out.watch_idx.data();
+  h.wrec = out.wrec.data();
+  h.wrec_ptr = out.wrec_ptr.data();
+  h.n_wrec = (int32_t)out.wrec.size();
+  {
+    const size_t bytes = out.wrec.size() * sizeof(WatchRec) + (size_t)(V + 1) * sizeof(int32_t);
+    h.table_smem_bytes = bytes <= 40 * 1024 ? (int32_t)((bytes + 15) & ~(size_t)15) : 0;
+  }
   h.node_op = out.node_op.data();
   h.node_l = out.node_l.data();
   h.node_r = out.node_r.data();

@@ -10,6 +10,8 @@ namespace csolve_dev {
 struct CompiledModel {
   DevModel host;                       // pointers into the vectors below (host addresses)
   std::vector<ClauseRec> clause;
+  std::vector<WatchRec> wrec;
+  std::vector<int32_t> wrec_ptr;
   std::vector<int32_t> watch_ptr, watch_idx, node_l, node_r, node_first, order, prio, root_dom;
   std::vector<uint8_t> node_op;
 };

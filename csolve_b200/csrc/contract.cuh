@@ -331,6 +331,56 @@ CSOLVE_HD bool contract_ne_vc(Cx &cx, int x, int32_t c) {
   return true;
 }
 
+// One watch record of variable `self` (device_model.h): X is the snapshot of self's domain the
+// caller took when it dequeued the variable. NE_VV: the NOT(EQ) clauses between self and one partner;
+// both directions of each clause are contracted from the snapshots, exactly like the false branch
+// of propagate_eq which evaluates both sides up front (src/propagate.c:122-134).
+template <class Cx>
+CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const WatchRec &rec) {
+  const uint32_t kind = wrec_kind(rec.w0);
+  const int n = wrec_n(rec.w0);
+  if (kind == WK_NE_VV) {
+    const int y = wrec_arg(rec.w0);
+    const Dom Y = cx.dom(y);
+    const bool xs = X.lo == X.hi, ys = Y.lo == Y.hi;
+    if (!xs && !ys) return true;           // neither side is a value: nothing to contract
+    // Predicated form of "if (other == my.lo) lo + 1 else if (other == my.hi) hi - 1" for every
+    // offset; the bounds asked for by the offsets of one record are combined and published once.
+    int32_t nyl = Y.lo, nyh = Y.hi, nxl = X.lo, nxh = X.hi;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; k++) {
+      if (k < n) {
+        const int32_t c = rec.c[k];
+        const int32_t Ll = X.lo + c, Lh = X.hi + c;     // self + c, never saturates (compile.cpp)
+        const bool yl = xs && Ll == Y.lo;               // self is the value Ll: partner loses it at a bound
+        const bool yh = xs && !yl && Ll == Y.hi;
+        nyl = yl ? Y.lo + 1 : nyl;
+        nyh = yh ? Y.hi - 1 : nyh;
+        const bool xl = ys && Y.lo == Ll;               // partner is the value Y.lo: self loses Y.lo - c
+        const bool xh = ys && !xl && Y.lo == Lh;
+        nxl = xl ? X.lo + 1 : nxl;
+        nxh = xh ? X.hi - 1 : nxh;
+      }
+    }
+    bool ok = true;
+    if (nyl != Y.lo || nyh != Y.hi) ok = contract_var(cx, y, nyl, nyh);
+    if (nxl != X.lo || nxh != X.hi) ok = contract_var(cx, self, nxl, nxh) && ok;
+    return ok;
+  }
+  if (kind == WK_NE_VC) {
+    bool ok = true;
+    for (int k = 0; k < n; k++) {
+      const int32_t c = rec.c[k];
+      if (X.lo == c) ok = contract_var(cx, self, c + 1, DMAX) && ok;
+      else if (X.hi == c) ok = contract_var(cx, self, DMIN, c - 1) && ok;
+    }
+    return ok;
+  }
+  return contract_generic(cx, m, m.clause[wrec_arg(rec.w0)].b);
+}
+
 // One clause contraction = propagate VALUE(1) into clause k (src/propagate.c:514-516).
 template <class Cx>
 CSOLVE_HD bool contract_clause(Cx &cx, const DevModel &m, const ClauseRec &rec) {

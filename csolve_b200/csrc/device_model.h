@@ -23,6 +23,20 @@ enum ClauseKind : int32_t { CK_GENERIC = 0, CK_NE_VV = 1, CK_NE_VC = 2 };
 
 struct ClauseRec { int32_t kind, a, b, c; };
 
+// Watch record: what a lane executes when variable `self` is on the node's worklist. One 16-byte
+// word; the records of a variable are contiguous (wrec_ptr[self] .. wrec_ptr[self + 1]).
+//   w0 = kind << 30 | n << 28 | arg        (n = number of offsets/constants used, 1..3)
+//   WK_GENERIC : arg = clause index; the whole clause is contracted by the interpreter
+//   WK_NE_VV   : arg = partner variable p; for k < n:  self + w[1 + k] != p
+//                (all NOT(EQ) clauses between the two variables, oriented from `self`, duplicates
+//                 merged: contracting the same clause twice cannot change the fixpoint)
+//   WK_NE_VC   : for k < n:  self != w[1 + k]
+enum WatchKind : uint32_t { WK_GENERIC = 0, WK_NE_VV = 1, WK_NE_VC = 2 };
+struct WatchRec { uint32_t w0; int32_t c[3]; };
+CSOLVE_HOSTDEV static inline uint32_t wrec_kind(uint32_t w0) { return w0 >> 30; }
+CSOLVE_HOSTDEV static inline int wrec_n(uint32_t w0) { return (int)((w0 >> 28) & 3u); }
+CSOLVE_HOSTDEV static inline int wrec_arg(uint32_t w0) { return (int)(w0 & 0x0fffffffu); }
+
 // Maximum expression depth the per-lane interpreter stacks are sized for.
 // csolve_gpu_load() rejects deeper models (CSOLVE_ERR_UNSUPPORTED).
 static const int MAX_DEPTH = 48;
@@ -37,6 +51,10 @@ struct DevModel {
   const ClauseRec *clause;   // [n_clauses]
   const int32_t *watch_ptr;  // [n_vars + 1]
   const int32_t *watch_idx;  // [n_watch]
+  const WatchRec *wrec;      // [n_wrec] compiled watch records
+  const int32_t *wrec_ptr;   // [n_vars + 1]
+  int32_t n_wrec;
+  int32_t table_smem_bytes;  // bytes needed to stage wrec + wrec_ptr in shared memory (0 = too large)
   const uint8_t *node_op;    // [n_nodes]
   const int32_t *node_l;     // [n_nodes]
   const int32_t *node_r;     // [n_nodes]

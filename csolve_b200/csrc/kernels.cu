@@ -25,6 +25,11 @@ namespace csolve_dev {
 
 #define FULL 0xffffffffu
 
+// resident blocks per SM the search kernel is compiled for (bounds the registers per thread)
+#ifndef CSOLVE_MIN_BLOCKS
+#define CSOLVE_MIN_BLOCKS 4
+#endif
+
 // ---- domain access of one warp: shared memory, lo/hi interleaved ---------------------------
 struct WarpCx {
   int *d;            // shared: 2 * n_vars words
@@ -47,18 +52,20 @@ struct WarpCx {
 
 // per-warp shared memory carve-up
 struct WarpSmem {
-  int *d;          // 2V
+  int *d;          // 2V: the node being propagated
+  int *p;          // 2V: domains of the top frame (state before this level's assignment)
   unsigned *cur;   // mask_words: variables whose watchers run in this round
   unsigned *nxt;   // mask_words
   unsigned *amask; // mask_words: variables assigned on the path to the top frame
 };
 
-__device__ __forceinline__ int warp_smem_words(const DevModel &m) { return 2 * m.n_vars + 3 * m.mask_words; }
+__device__ __forceinline__ int warp_smem_words(const DevModel &m) { return 4 * m.n_vars + 3 * m.mask_words; }
 
 __device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
   WarpSmem s;
   s.d = base;
-  s.cur = (unsigned *)(base + 2 * m.n_vars);
+  s.p = base + 2 * m.n_vars;
+  s.cur = (unsigned *)(base + 4 * m.n_vars);
   s.nxt = s.cur + m.mask_words;
   s.amask = s.nxt + m.mask_words;
   return s;
@@ -66,8 +73,10 @@ __device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
 
 // ---- propagation to fixpoint for the node staged in s.d --------------------------------------
 // precondition: s.cur holds the initial worklist, s.nxt is zero, warp converged after __syncwarp.
+// wrec / wptr: the compiled watch records (shared memory when the table was staged, else global).
 // returns false when the node failed (PROP_ERROR).
-__device__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, int lane, unsigned &props, unsigned &visits) {
+__device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, const int4 *wrec, const int *wptr,
+                                              int lane, unsigned &props, unsigned &visits) {
   WarpCx cx;
   cx.d = s.d; cx.props = 0;
   bool failed = false;
@@ -80,15 +89,15 @@ __device__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, int lane, unsigned
       while (bits) {
         const int x = (w << 5) + __ffs(bits) - 1;
         bits &= bits - 1;
-        // bounds published by different lanes may cross: an empty domain is a failure
-        Dom dx = cx.dom(x);
-        if (dx.lo > dx.hi) failed = true;
-        const int b = __ldg(&m.watch_ptr[x]), e = __ldg(&m.watch_ptr[x + 1]);
+        // snapshot of the dequeued variable; bounds published by different lanes may have
+        // crossed since it was queued: an empty domain is a failure
+        const Dom X = cx.dom(x);
+        if (X.lo > X.hi) failed = true;
+        const int b = wptr[x], e = wptr[x + 1];
         for (int i = b + lane; i < e; i += 32) {
-          const int c = __ldg(&m.watch_idx[i]);
-          const int4 q = __ldg(reinterpret_cast<const int4 *>(&m.clause[c]));
-          ClauseRec rec; rec.kind = q.x; rec.a = q.y; rec.b = q.z; rec.c = q.w;
-          if (!contract_clause(cx, m, rec)) failed = true;
+          const int4 q = wrec[i];
+          WatchRec rec; rec.w0 = (uint32_t)q.x; rec.c[0] = q.y; rec.c[1] = q.z; rec.c[2] = q.w;
+          if (!contract_watch(cx, m, x, X, rec)) failed = true;
           visits++;
         }
       }
@@ -103,6 +112,21 @@ __device__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, int lane, unsigned
   }
   props += cx.props;
   return true;
+}
+
+// stage the watch-record table into shared memory (whole block); returns the pointers to use
+__device__ __forceinline__ void stage_table(const DevModel &m, int *smem, const int4 *&wrec, const int *&wptr) {
+  if (m.table_smem_bytes > 0) {
+    int4 *dst = reinterpret_cast<int4 *>(smem);
+    const int4 *src = reinterpret_cast<const int4 *>(m.wrec);
+    for (int i = threadIdx.x; i < m.n_wrec; i += blockDim.x) dst[i] = __ldg(&src[i]);
+    int *pdst = smem + 4 * m.n_wrec;
+    for (int i = threadIdx.x; i <= m.n_vars; i += blockDim.x) pdst[i] = __ldg(&m.wrec_ptr[i]);
+    __syncthreads();
+    wrec = dst; wptr = pdst;
+  } else {
+    wrec = reinterpret_cast<const int4 *>(m.wrec); wptr = m.wrec_ptr;
+  }
 }
 
 // leaf test: every clause evaluates to true (src/csolve.c:226, src/eval.c:221-245)
@@ -196,17 +220,19 @@ __device__ __forceinline__ void store_solution(const SearchArgs &a, const WarpSm
 // ---- the search kernel ----------------------------------------------------------------------------
 // Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
 template <bool EXPAND>
-__global__ void __launch_bounds__(THREADS_PER_BLOCK)
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_MIN_BLOCKS)
 k_search(const SearchArgs a) {
   extern __shared__ __align__(16) int smem[];
   const DevModel &m = a.m;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+  const int4 *wrec; const int *wptr;
+  stage_table(m, smem, wrec, wptr);
   if (gw >= a.n_warps) return;
   // per-warp regions are padded to 16 bytes so the int2 staging copies stay aligned
   const int wwords = (warp_smem_words(m) + 3) & ~3;
-  WarpSmem s = carve(m, smem + wib * wwords);
+  WarpSmem s = carve(m, smem + (m.table_smem_bytes >> 2) + wib * wwords);
 
   const int V = m.n_vars, fw = m.frame_words;
   const bool optimise = m.obj_var >= 0;
@@ -217,13 +243,13 @@ k_search(const SearchArgs a) {
   unsigned long long nodes = 0, cuts = 0, sols = 0, refresh = 0;
   unsigned props = 0, visits = 0;
   const long long t0 = clock64();
-  bool parked = false;
 
-  // restore the assigned-variable mask of the top frame
-  if (level >= base) {
-    for (int w = lane; w < m.mask_words; w += 32) s.amask[w] = (unsigned)__ldcg(&stack[(size_t)level * fw + FR_MASK + w]);
-  }
-  __syncwarp();
+  // The header of the top frame lives in registers and its domains (the state BEFORE this level's
+  // assignment) in s.p while the warp iterates over the level's values; HBM is touched only when
+  // a frame is pushed, popped, refreshed, parked or fetched from the frontier.
+  bool have = false;
+  int var = 0, lo = 0, hi = 0, flevel = 0, fbest = 0;
+  unsigned iter = 0, last = 0, fhash = 0;
 
   for (;;) {
     const int sig = *reinterpret_cast<volatile int *>(&ctl->signal);   // consumed at the end of the node
@@ -244,20 +270,23 @@ k_search(const SearchArgs a) {
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       int *dst = stack + (size_t)L * fw;
       for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
-      for (int w = lane; w < m.mask_words; w += 32) s.amask[w] = (unsigned)__ldcg(&src[FR_MASK + w]);
       level = base = L;
+      have = false;
       __syncwarp();
     }
 
     int *f = stack + (size_t)level * fw;
-    const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(f));
-    const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(f) + 1);
-    const int var = h0.x;
-    unsigned iter = (unsigned)h0.y;
-    const unsigned last = (unsigned)h0.z;
-    int lo = h0.w, hi = h1.x;
-    const int flevel = h1.y;      // variables assigned before this frame (== level for DFS frames)
-    const unsigned fhash = (unsigned)h1.w;
+    if (!have) {
+      // (re)load the top frame: header, assigned-variable mask, domains
+      const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(f));
+      const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(f) + 1);
+      load_domains(m, f, s.p, lane);
+      for (int w = lane; w < m.mask_words; w += 32) s.amask[w] = (unsigned)__ldcg(&f[FR_MASK + w]);
+      var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; lo = h0.w;
+      hi = h1.x; flevel = h1.y; fbest = h1.z; fhash = (unsigned)h1.w;
+      have = true;
+      __syncwarp();
+    }
 
     int best = 0;
     if (optimise) best = EXPAND ? a.frozen_best : *reinterpret_cast<volatile int *>(&ctl->best);
@@ -274,25 +303,22 @@ k_search(const SearchArgs a) {
         atomicAdd(&ctl->out_dropped, 1);
       }
       level = base - 1;
+      have = false;
       continue;
     }
 
     if (iter > last) {
-      // values exhausted (src/csolve.c:439-442): backtrack
+      // values exhausted (src/csolve.c:439-442): backtrack; the parent frame is reloaded from HBM
       level--;
-      if (level >= base) {
-        const int pv = __ldcg(&stack[(size_t)level * fw + FR_VAR]);
-        if (lane == 0) s.amask[pv >> 5] &= ~(1u << (pv & 31));
-        __syncwarp();
-      }
+      have = false;
       continue;
     }
 
-    if (!EXPAND && optimise && best != h1.z) {
+    if (!EXPAND && optimise && best != fbest) {
       // The incumbent improved since this frame's domains were computed. The reference
       // restarts from level 0 on every improvement (src/csolve.c:418-421); here the frame is
       // re-propagated against the tighter <obj> bound and keeps only its untried values.
-      load_domains(m, f, s.d, lane);
+      for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.d)[v] = reinterpret_cast<const int2 *>(s.p)[v];
       for (int w = lane; w < m.mask_words; w += 32) { s.cur[w] = 0; s.nxt[w] = 0; }
       __syncwarp();
       bool ok = true;
@@ -305,7 +331,7 @@ k_search(const SearchArgs a) {
       }
       ok = __shfl_sync(FULL, ok, 0);
       __syncwarp();
-      if (ok) ok = warp_fixpoint(m, s, lane, props, visits);
+      if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
       refresh++;
       // untried values of the old enumeration form the interval [lo + ceil(iter/2), hi - floor(iter/2)]
       const long long ua = (long long)lo + ((iter + 1) >> 1), ub = (long long)hi - (iter >> 1);
@@ -316,21 +342,20 @@ k_search(const SearchArgs a) {
       }
       if (!ok || na > nb) {
         level--;
-        if (level >= base) {
-          const int pv = __ldcg(&stack[(size_t)level * fw + FR_VAR]);
-          if (lane == 0) s.amask[pv >> 5] &= ~(1u << (pv & 31));
-          __syncwarp();
-        }
+        have = false;
         continue;
       }
       // the frame keeps its (now tighter) parent domains, except that the branching variable
       // still ranges over the values this frame owns
+      __syncwarp();
       if (lane == 0) { s.d[2 * var] = (int)na; s.d[2 * var + 1] = (int)nb; }
       __syncwarp();
+      for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.p)[v] = reinterpret_cast<const int2 *>(s.d)[v];
       store_domains(m, f, s.d, lane);
+      lo = (int)na; hi = (int)nb; iter = 0; last = (unsigned)(nb - na); fbest = best;
       if (lane == 0) {
-        __stcg(reinterpret_cast<int4 *>(f), make_int4(var, 0, (int)(unsigned)(nb - na), (int)na));
-        __stcg(reinterpret_cast<int4 *>(f) + 1, make_int4((int)nb, flevel, best, (int)fhash));
+        __stcg(reinterpret_cast<int4 *>(f), make_int4(var, 0, (int)last, lo));
+        __stcg(reinterpret_cast<int4 *>(f) + 1, make_int4(hi, flevel, fbest, (int)fhash));
       }
       __syncwarp();
       continue;
@@ -338,8 +363,8 @@ k_search(const SearchArgs a) {
 
     // ---- one search node: assign var := val, propagate (src/csolve.c:444-457) ----------------
     const int val = step_value(lo, hi, iter);
-    if (lane == 0) __stcg(&f[FR_ITER], (int)(iter + 1));
-    load_domains(m, f, s.d, lane);
+    iter++;
+    for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.d)[v] = reinterpret_cast<const int2 *>(s.p)[v];
     for (int w = lane; w < m.mask_words; w += 32) { s.cur[w] = 0; s.nxt[w] = 0; }
     __syncwarp();
     bool ok = true;
@@ -356,7 +381,7 @@ k_search(const SearchArgs a) {
     }
     ok = __shfl_sync(FULL, ok, 0);
     __syncwarp();
-    if (ok) ok = warp_fixpoint(m, s, lane, props, visits);
+    if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
     nodes++;
 
     if (!ok) {
@@ -399,8 +424,16 @@ k_search(const SearchArgs a) {
           atomicAdd(&ctl->out_dropped, 1);
         }
       } else {
+        // push: the current frame's iteration state goes to HBM (it is reloaded on backtrack), the
+        // child frame is written for rebalancing/parking and becomes the register/shared-resident top
+        if (lane == 0) __stcg(&f[FR_ITER], (int)iter);
         write_child_frame(m, s, stack + (size_t)(level + 1) * fw, lane, nv, flevel + 1, best, chash, var);
         if (lane == 0) s.amask[var >> 5] |= 1u << (var & 31);
+        for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.p)[v] = reinterpret_cast<const int2 *>(s.d)[v];
+        __syncwarp();
+        lo = s.p[2 * nv]; hi = s.p[2 * nv + 1];
+        var = nv; iter = 0; last = (unsigned)hi - (unsigned)lo;
+        flevel = flevel + 1; fbest = best; fhash = chash;
         level++;
       }
       __syncwarp();
@@ -408,17 +441,16 @@ k_search(const SearchArgs a) {
 
     // ---- park? ----------------------------------------------------------------------------------
     if (!EXPAND) {
-      if (sig != SIG_RUN) { parked = true; break; }
+      if (sig != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
-        parked = true;
         break;
       }
     }
   }
 
-  (void)parked;
   if (lane == 0) {
+    if (have && level >= base) __stcg(&stack[(size_t)level * fw + FR_ITER], (int)iter);   // park the top frame
     a.wstate[gw].level = level;
     a.wstate[gw].base = base;
   }
@@ -533,8 +565,10 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
                   const int32_t *best, int32_t *dom_out, uint8_t *failed) {
   extern __shared__ __align__(16) int smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int4 *wrec; const int *wptr;
+  stage_table(m, smem, wrec, wptr);
   const int wwords = (warp_smem_words(m) + 3) & ~3;
-  WarpSmem s = carve(m, smem + wib * wwords);
+  WarpSmem s = carve(m, smem + (m.table_smem_bytes >> 2) + wib * wwords);
   const int V = m.n_vars;
   const int n_warps = gridDim.x * WARPS_PER_BLOCK;
   for (int b = blockIdx.x * WARPS_PER_BLOCK + wib; b < n_nodes; b += n_warps) {
@@ -559,7 +593,7 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
     ok = __shfl_sync(FULL, ok, 0);
     __syncwarp();
     unsigned props = 0, visits = 0;
-    if (ok) ok = warp_fixpoint(m, s, lane, props, visits);
+    if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
     int2 *dst = reinterpret_cast<int2 *>(dom_out + (size_t)b * 2 * V);
     for (int v = lane; v < V; v += 32) dst[v] = reinterpret_cast<int2 *>(s.d)[v];
     if (lane == 0) failed[b] = ok ? 0 : 1;
@@ -569,8 +603,8 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
 
 // ---- host-side launch wrappers -----------------------------------------------------------------------
 size_t search_smem_bytes(const DevModel &m) {
-  const int wwords = (2 * m.n_vars + 3 * m.mask_words + 3) & ~3;
-  return (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
+  const int wwords = (4 * m.n_vars + 3 * m.mask_words + 3) & ~3;
+  return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
 }
 
 static cudaError_t ensure_smem(const void *fn, size_t bytes) {

@@ -85,7 +85,8 @@ class _GpuResult(C.Structure):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcsolve_b200.so")
+    # CSOLVE_B200_LIB: development override to compare builds; the default is the in-tree library
+    return os.environ.get("CSOLVE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcsolve_b200.so")
 
 
 _lib = None

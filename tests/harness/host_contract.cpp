@@ -23,11 +23,15 @@ struct HostCx {
 };
 
 static CompiledModel g_cm;
+static int g_use_wrec = 1;
 static std::string g_err;
 
 extern "C" int hc_load(const csolve_flat_model *m, int specialise) {
   int rc = compile_model(*m, g_cm, g_err);
   if (rc != 0) return rc;
+  // specialise: 0 = every clause through the interpreter (per-clause watch lists),
+  //             1 = compiled watch records (what the kernels run), 2 = specialised per-clause records
+  g_use_wrec = specialise == 1;
   if (!specialise) {
     for (size_t c = 0; c < g_cm.clause.size(); c++) {
       g_cm.clause[c] = ClauseRec{CK_GENERIC, m->clause_first[c], m->clause_first[c + 1] - 1, 0};
@@ -62,8 +66,16 @@ extern "C" int hc_node(const int32_t *dom_in, int var, int32_t val, int32_t best
     int x = queue[qi];
     queued[x] = 0;
     if (d[2 * x] > d[2 * x + 1]) { failed = true; break; }
-    for (int w = m.watch_ptr[x]; w < m.watch_ptr[x + 1]; w++) {
-      if (!contract_clause(cx, m, m.clause[m.watch_idx[w]])) { failed = true; break; }
+    if (g_use_wrec) {
+      // the path the kernels take: compiled watch records, domain snapshot per dequeued variable
+      Dom X = cx.dom(x);
+      for (int w = m.wrec_ptr[x]; w < m.wrec_ptr[x + 1]; w++) {
+        if (!contract_watch(cx, m, x, X, m.wrec[w])) { failed = true; break; }
+      }
+    } else {
+      for (int w = m.watch_ptr[x]; w < m.watch_ptr[x + 1]; w++) {
+        if (!contract_clause(cx, m, m.clause[m.watch_idx[w]])) { failed = true; break; }
+      }
     }
   }
   if (!failed) for (int v = 0; v < V; v++) if (d[2 * v] > d[2 * v + 1]) failed = true;

@@ -39,9 +39,10 @@ def test_oracle_node_transitions(name):
 
 
 @pytest.mark.parametrize("name", REPLAY)
-@pytest.mark.parametrize("specialise", [0, 1])
+@pytest.mark.parametrize("specialise", [0, 1, 2])
 def test_product_contractors_on_host(name, specialise):
-    """contract.cuh (what each lane runs) with a sequential worklist, generic-only and specialised"""
+    """contract.cuh (what each lane runs) with a sequential worklist: interpreter only (0), the compiled
+    watch records the kernels use (1), specialised per-clause records (2)"""
     g = np.load(os.path.join(util.GOLDEN, "replay_%s.npz" % name))
     m = cb.Model(INST[name])
     hc = util.harness_lib()
