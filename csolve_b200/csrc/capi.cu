@@ -146,6 +146,7 @@ extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **
     p->allocs.push_back((void *)d.field);                           \
   } while (0)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
+  UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval);
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
 #undef UP
@@ -209,7 +210,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
     CUDA_TRY(cudaMalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
-  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 8;
+  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 48;
   int cap = std::max(target * 16, 1 << 16);
   const size_t max_bytes = (size_t)2 << 30;   // per pool
   while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
@@ -282,7 +283,7 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   uint64_t launches = 0;
 
   // ---- batched frontier expansion -------------------------------------------------------------------
-  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 8;
+  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 48;
   long long max_branch = 1;
   for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
   max_branch = std::min<long long>(max_branch, a.expand_branch_max);

@@ -169,6 +169,36 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   }
   out.wrec_ptr[V] = (int32_t)out.wrec.size();
 
+  // ---- "lane owns variable" tables: every clause is a NOT(EQ) between two variables or a variable
+  //      and a constant, at most 32 variables, offsets in [-32, 31], no objective variable ----
+  {
+    bool lov = V <= 32 && n_generic == 0 && m.obj_var < 0;
+    out.lov_pair.assign((size_t)V * 32, 0);
+    out.lov_cptr.assign(V + 1, 0);
+    out.lov_cval.clear();
+    for (int v = 0; v < V && lov; v++) {
+      out.lov_cptr[v] = (int32_t)out.lov_cval.size();
+      for (int w = out.wrec_ptr[v]; w < out.wrec_ptr[v + 1] && lov; w++) {
+        const WatchRec &r = out.wrec[w];
+        const int n = wrec_n(r.w0);
+        if (wrec_kind(r.w0) == WK_NE_VV) {
+          unsigned long long &e = out.lov_pair[(size_t)v * 32 + wrec_arg(r.w0)];
+          for (int k = 0; k < n; k++) {
+            if (r.c[k] < -32 || r.c[k] > 31) { lov = false; break; }
+            e |= 1ull << (r.c[k] + 32);
+          }
+        } else if (wrec_kind(r.w0) == WK_NE_VC) {
+          for (int k = 0; k < n; k++) out.lov_cval.push_back(r.c[k]);
+        } else {
+          lov = false;
+        }
+      }
+      if ((int)out.lov_cval.size() - out.lov_cptr[v] > 32) lov = false;   // one lane per constant
+    }
+    out.lov_cptr[V] = (int32_t)out.lov_cval.size();
+    out.host.lov = lov ? 1 : 0;
+  }
+
   // static branching order: priority descending, index ascending (the reference's heap with
   // -o none -f true orders by env_t.prio only, src/strategy.c:79-121)
   out.order.resize(V);
@@ -191,6 +221,9 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   h.watch_ptr = out.watch_ptr.data();
   h.watch_idx = out.watch_idx.data();
   h.wrec = out.wrec.data();
+  h.lov_pair = out.lov_pair.data(); h.lov_cptr = out.lov_cptr.data(); h.lov_cval = out.lov_cval.data();
+  h.n_lov_cval = (int32_t)out.lov_cval.size();
+  h.lov_smem_bytes = (int32_t)((((size_t)V * 32 * 2 + (V + 1) + out.lov_cval.size()) * 4 + 15) & ~(size_t)15);
   h.wrec_ptr = out.wrec_ptr.data();
   h.n_wrec = (int32_t)out.wrec.size();
   {

@@ -381,6 +381,38 @@ CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const 
   return contract_generic(cx, m, m.clause[wrec_arg(rec.w0)].b);
 }
 
+// ---- "lane owns variable" form ---------------------------------------------------------------------
+// Variable i (domain [Xlo,Xhi]) was dequeued; the calling lane owns variable j with domain [lo,hi] and
+// mask = lov_pair[i][j] is the set of offsets c of the clauses x_i + c != x_j (bit c + 32).
+// Same contraction as contract_watch(WK_NE_VV) seen from i with partner j:
+//   i is a value v      : every clause removes v + c from j if it sits on one of j's bounds;
+//   j is a value w      : every clause removes w - c from i if it sits on one of i's bounds -- returned as
+//                         proposals, combined across lanes by the caller with ballots.
+// When both are values and collide, j's domain becomes empty, which the caller detects when it
+// dequeues j (the reference fails in the same situation, src/propagate.c:57-66).
+struct LovStep { int32_t nlo, nhi; bool plo, phi; };
+CSOLVE_HD bool lov_has(unsigned long long mask, int32_t d) {
+  const uint32_t s = (uint32_t)(d + 32);
+  return s < 64u && ((mask >> s) & 1ull) != 0;
+}
+CSOLVE_HD LovStep lov_lane_step(unsigned long long mask, int32_t Xlo, int32_t Xhi, int32_t lo, int32_t hi) {
+  LovStep r; r.nlo = lo; r.nhi = hi; r.plo = false; r.phi = false;
+  if (Xlo == Xhi) {
+    if (lov_has(mask, lo - Xlo)) r.nlo = lo + 1;
+    if (lov_has(mask, hi - Xlo)) r.nhi = hi - 1;
+  } else if (lo == hi) {
+    r.plo = lov_has(mask, lo - Xlo);
+    r.phi = lov_has(mask, lo - Xhi);
+  }
+  return r;
+}
+// forbidden constant c of the dequeued variable (x_i != c): which bound of i it removes
+CSOLVE_HD void lov_const_step(int32_t c, int32_t Xlo, int32_t Xhi, bool &plo, bool &phi) {
+  const bool cl = c == Xlo;
+  plo = plo || cl;
+  phi = phi || (!cl && c == Xhi);
+}
+
 // One clause contraction = propagate VALUE(1) into clause k (src/propagate.c:514-516).
 template <class Cx>
 CSOLVE_HD bool contract_clause(Cx &cx, const DevModel &m, const ClauseRec &rec) {

@@ -55,6 +55,16 @@ struct DevModel {
   const int32_t *wrec_ptr;   // [n_vars + 1]
   int32_t n_wrec;
   int32_t table_smem_bytes;  // bytes needed to stage wrec + wrec_ptr in shared memory (0 = too large)
+  // "lane owns variable" form (pure NOT(EQ) networks with at most 32 variables, e.g. N-queens):
+  //   lov_pair[i * 32 + j] = 64-bit set of forbidden differences: bit (c + 32) is set iff the network
+  //                           holds the clause x_i + c != x_j  (-32 <= c < 32)
+  //   lov_cptr / lov_cval   = per variable CSR of forbidden constants (x_i != c)
+  int32_t lov;               // 1 when the model is eligible
+  int32_t lov_smem_bytes;
+  int32_t n_lov_cval;
+  const unsigned long long *lov_pair;  // [n_vars * 32]
+  const int32_t *lov_cptr;   // [n_vars + 1]
+  const int32_t *lov_cval;   // [n_lov_cval]
   const uint8_t *node_op;    // [n_nodes]
   const int32_t *node_l;     // [n_nodes]
   const int32_t *node_r;     // [n_nodes]

@@ -26,6 +26,9 @@ namespace csolve_dev {
 #define FULL 0xffffffffu
 
 // resident blocks per SM the search kernel is compiled for (bounds the registers per thread)
+#ifndef CSOLVE_LOV_MIN_BLOCKS
+#define CSOLVE_LOV_MIN_BLOCKS 4
+#endif
 #ifndef CSOLVE_MIN_BLOCKS
 #define CSOLVE_MIN_BLOCKS 4
 #endif
@@ -467,6 +470,290 @@ k_search(const SearchArgs a) {
   }
 }
 
+// =====================================================================================================
+// "Lane owns variable" search kernel for pure NOT(EQ) networks with at most 32 variables (N-queens).
+// Lane j keeps the bounds of variable j in registers: a node's domain vector never touches shared
+// memory, a dequeued variable is broadcast with two shuffles, every lane contracts its own clauses
+// with it (lov_lane_step), bounds requested of the dequeued variable are combined with ballots.
+// No atomics, no divergence; the worklist is a 32-bit register mask. Same frames, same frontier,
+// same rebalancing as k_search.
+struct LovTables { const unsigned long long *pair; const int *cptr; const int *cval; };
+
+__device__ __forceinline__ LovTables stage_lov(const DevModel &m, int *smem) {
+  unsigned long long *pair = reinterpret_cast<unsigned long long *>(smem);
+  int *cptr = smem + m.n_vars * 64;
+  int *cval = cptr + m.n_vars + 1;
+  for (int i = threadIdx.x; i < m.n_vars * 32; i += blockDim.x) pair[i] = __ldg(&m.lov_pair[i]);
+  for (int i = threadIdx.x; i <= m.n_vars; i += blockDim.x) cptr[i] = __ldg(&m.lov_cptr[i]);
+  for (int i = threadIdx.x; i < m.n_lov_cval; i += blockDim.x) cval[i] = __ldg(&m.lov_cval[i]);
+  __syncthreads();
+  LovTables t; t.pair = pair; t.cptr = cptr; t.cval = cval;
+  return t;
+}
+
+// propagate to fixpoint; lo/hi: this lane's variable. returns false when the node failed.
+// The dequeued variable's bounds are warp-uniform, so "is it a value?" is a uniform branch:
+//   value     -> every lane trims its own bounds (registers only), one ballot collects who changed;
+//   not value -> lanes whose variable is a value ask for the dequeued variable's bounds to move,
+//                two ballots combine the requests and the owning lane applies them.
+__device__ __forceinline__ bool lov_fixpoint(const LovTables &t, int V, bool has_consts, int lane, int &lo, int &hi,
+                                             unsigned changed, unsigned &props, unsigned &visits) {
+  const bool act = lane < V;
+  while (changed) {
+    const int i = __ffs(changed) - 1;
+    changed &= changed - 1;
+    const int Xlo = __shfl_sync(FULL, lo, i), Xhi = __shfl_sync(FULL, hi, i);
+    if (Xlo > Xhi) return false;                 // bounds requested by different lanes crossed
+    const unsigned long long mask = act ? t.pair[i * 32 + lane] : 0ull;
+    const LovStep r = lov_lane_step(mask, Xlo, Xhi, lo, hi);
+    unsigned chm = 0;
+    if (Xlo == Xhi) {
+      const bool mych = (r.nlo != lo) | (r.nhi != hi);
+      lo = r.nlo; hi = r.nhi;
+      chm = __ballot_sync(FULL, mych);
+    }
+    bool plo = r.plo, phi = r.phi;
+    if (has_consts) {
+      const int cb = t.cptr[i], ce = t.cptr[i + 1];
+      if (cb + lane < ce) lov_const_step(t.cval[cb + lane], Xlo, Xhi, plo, phi);
+    }
+    if (has_consts || Xlo != Xhi) {
+      const unsigned bl = __ballot_sync(FULL, plo), bh = __ballot_sync(FULL, phi);
+      if (lane == i) { if (bl) lo = Xlo + 1; if (bh) hi = Xhi - 1; }
+      if (bl | bh) chm |= 1u << i;
+    }
+    changed |= chm;
+    props += __popc(chm);
+    visits += (unsigned)V;
+  }
+  return true;
+}
+
+template <bool EXPAND>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_LOV_MIN_BLOCKS)
+k_search_lov(const SearchArgs a) {
+  extern __shared__ __align__(16) int smem[];
+  const DevModel &m = a.m;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+  const LovTables T = stage_lov(m, smem);
+  if (gw >= a.n_warps) return;
+
+  const int V = m.n_vars, fw = m.frame_words;
+  const int dofs = frame_dom_offset(1);
+  int *stack = a.stacks + (size_t)gw * (V + 1) * fw;
+  SearchCtl *ctl = a.ctl;
+  const bool act = lane < V;
+  const bool has_consts = m.n_lov_cval > 0;
+
+  int level = a.wstate[gw].level, base = a.wstate[gw].base;
+  unsigned long long nodes = 0, cuts = 0, sols = 0;
+  unsigned props = 0, visits = 0;
+  const long long t0 = clock64();
+
+  bool have = false;
+  int var = 0, flo = 0, fhi = 0, flevel = 0;
+  unsigned iter = 0, last = 0, fhash = 0, amask = 0;
+  int plo = 0, phi = 0;        // this lane's variable in the top frame (state before the assignment)
+
+  for (;;) {
+    const int sig = *reinterpret_cast<volatile int *>(&ctl->signal);
+
+    if (level < base) {
+      int it = 0;
+      if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
+      it = __shfl_sync(FULL, it, 0);
+      if (it >= ctl->item_count) {
+        if (lane == 0) {
+          const int n = atomicAdd(&ctl->idle, 1) + 1;
+          if (!EXPAND && n >= a.idle_exit) atomicMax(&ctl->signal, SIG_SLICE_END);
+        }
+        break;
+      }
+      const int *src = a.items + (size_t)it * fw;
+      const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
+      int *dst = stack + (size_t)L * fw;
+      for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
+      level = base = L;
+      have = false;
+      __syncwarp();
+    }
+
+    int *f = stack + (size_t)level * fw;
+    if (!have) {
+      const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(f));
+      const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(f) + 1);
+      amask = (unsigned)__ldcg(&f[FR_MASK]);
+      int2 dj = make_int2(0, 0);
+      if (act) dj = __ldcg(reinterpret_cast<const int2 *>(f + dofs) + lane);
+      plo = dj.x; phi = dj.y;
+      var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; flo = h0.w;
+      fhi = h1.x; flevel = h1.y; fhash = (unsigned)h1.w;
+      have = true;
+    }
+
+    if (EXPAND && last >= (unsigned)a.expand_branch_max) {
+      int slot = 0;
+      if (lane == 0) { slot = atomicAdd(&ctl->out_count, 1); atomicAdd(&ctl->passed, 1); }
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot < a.out_cap) {
+        int *g = a.items_out + (size_t)slot * fw;
+        for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&f[w]));
+      } else if (lane == 0) {
+        atomicAdd(&ctl->out_dropped, 1);
+      }
+      level = base - 1;
+      have = false;
+      continue;
+    }
+
+    if (iter > last) {
+      level--;
+      have = false;
+      continue;
+    }
+
+    // ---- one search node -------------------------------------------------------------------------
+    const int val = step_value(flo, fhi, iter);
+    iter++;
+    int lo = plo, hi = phi;
+    if (lane == var) { lo = val; hi = val; }
+    const bool ok = lov_fixpoint(T, V, has_consts, lane, lo, hi, 1u << var, props, visits);
+    nodes++;
+
+    if (!ok) {
+      cuts++;
+    } else if (flevel + 1 == V) {
+      // leaf: is_true(eval(root)) -- every clause x_i + c != x_j / x_i != c holds on the assignment
+      bool good = lo == hi;
+      for (int i = 0; i < V; i++) {
+        const int Xi = __shfl_sync(FULL, lo, i);
+        const unsigned long long mk = act ? T.pair[i * 32 + lane] : 0ull;
+        if (lov_has(mk, lo - Xi)) good = false;      // x_i + c == x_j for a clause of the pair
+        const int cb = T.cptr[i], ce = T.cptr[i + 1];
+        if (cb + lane < ce && T.cval[cb + lane] == Xi) good = false;
+      }
+      if (__all_sync(FULL, good || !act)) {
+        bool accepted = true;
+        if (m.objective == CSOLVE_OBJ_ANY) {
+          int old = 0;
+          if (lane == 0) old = atomicMax(&ctl->signal, SIG_STOP);
+          old = __shfl_sync(FULL, old, 0);
+          accepted = old != SIG_STOP;
+        }
+        if (accepted) {
+          sols++;
+          int slot = 0;
+          if (lane == 0) slot = atomicAdd(&ctl->n_stored, 1);
+          slot = __shfl_sync(FULL, slot, 0);
+          if (slot < a.max_solutions) {
+            int *dst = a.solbuf + (size_t)slot * (V + 1);
+            if (act) dst[lane] = lo;
+            if (lane == 0) dst[V] = 0;
+          }
+        }
+      }
+    } else {
+      // branching variable of the next level
+      int nv;
+      if (a.order == CSOLVE_ORDER_NONE) {
+        nv = __ldg(&m.order[flevel + 1]);
+      } else {
+        unsigned long long bestk = ~0ull;
+        int bestv = 0x7fffffff;
+        if (act && lane != var && !(amask & (1u << lane))) {
+          unsigned primary;
+          switch (a.order) {
+          case CSOLVE_ORDER_SMALLEST_DOMAIN: primary = (unsigned)hi - (unsigned)lo; break;
+          case CSOLVE_ORDER_LARGEST_DOMAIN:  primary = ~((unsigned)hi - (unsigned)lo); break;
+          case CSOLVE_ORDER_SMALLEST_VALUE:  primary = (unsigned)lo ^ 0x80000000u; break;
+          default:                           primary = ~((unsigned)hi ^ 0x80000000u); break;
+          }
+          const unsigned secondary = ~((unsigned)__ldg(&m.prio[lane]) ^ 0x80000000u);
+          bestk = ((unsigned long long)primary << 32) | secondary;
+          bestv = lane;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long ok2 = __shfl_xor_sync(FULL, bestk, o);
+          const int ov = __shfl_xor_sync(FULL, bestv, o);
+          if (ok2 < bestk || (ok2 == bestk && ov < bestv)) { bestk = ok2; bestv = ov; }
+        }
+        nv = bestv;
+      }
+      const unsigned chash = mix_hash(fhash, (unsigned)var, (unsigned)val);
+      const int nlo = __shfl_sync(FULL, lo, nv), nhi = __shfl_sync(FULL, hi, nv);
+      int *g;
+      if (EXPAND) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&ctl->out_count, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        g = slot < a.out_cap ? a.items_out + (size_t)slot * fw : nullptr;
+        if (g == nullptr && lane == 0) atomicAdd(&ctl->out_dropped, 1);
+      } else {
+        if (lane == 0) __stcg(&f[FR_ITER], (int)iter);
+        g = stack + (size_t)(level + 1) * fw;
+      }
+      if (g != nullptr) {
+        if (lane == 0) {
+          __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)((unsigned)nhi - (unsigned)nlo), nlo));
+          __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nhi, flevel + 1, 0, (int)chash));
+          __stcg(&g[FR_MASK], (int)(amask | (1u << var)));
+        }
+        if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, make_int2(lo, hi));
+      }
+      if (!EXPAND) {
+        amask |= 1u << var;
+        plo = lo; phi = hi;
+        var = nv; flo = nlo; fhi = nhi; iter = 0; last = (unsigned)nhi - (unsigned)nlo;
+        flevel = flevel + 1; fhash = chash;
+        level++;
+      }
+    }
+
+    if (!EXPAND) {
+      if (sig != SIG_RUN) break;
+      if (clock64() - t0 > a.slice_cycles) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
+        break;
+      }
+    }
+  }
+
+  if (lane == 0) {
+    if (have && level >= base) __stcg(&stack[(size_t)level * fw + FR_ITER], (int)iter);
+    a.wstate[gw].level = level;
+    a.wstate[gw].base = base;
+    unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
+    c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
+    c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS_PER_BLOCK)
+k_propagate_batch_lov(const DevModel m, int n_nodes, const int32_t *dom_in, const int32_t *var, const int32_t *val,
+                      int32_t *dom_out, uint8_t *failed) {
+  extern __shared__ __align__(16) int smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const LovTables T = stage_lov(m, smem);
+  const int V = m.n_vars;
+  const bool act = lane < V;
+  const int n_warps = gridDim.x * WARPS_PER_BLOCK;
+  for (int b = blockIdx.x * WARPS_PER_BLOCK + wib; b < n_nodes; b += n_warps) {
+    int2 dj = make_int2(0, 0);
+    if (act) dj = __ldg(reinterpret_cast<const int2 *>(dom_in + (size_t)b * 2 * V) + lane);
+    int lo = dj.x, hi = dj.y;
+    const int x = var[b];
+    if (lane == x && lo != hi) { lo = val[b]; hi = val[b]; }
+    unsigned props = 0, visits = 0;
+    bool ok = lov_fixpoint(T, V, m.n_lov_cval > 0, lane, lo, hi, 1u << x, props, visits);
+    ok = ok && !__any_sync(FULL, act && lo > hi);
+    if (act) reinterpret_cast<int2 *>(dom_out + (size_t)b * 2 * V)[lane] = make_int2(lo, hi);
+    if (lane == 0) failed[b] = ok ? 0 : 1;
+  }
+}
+
 // ---- rebalance -----------------------------------------------------------------------------------
 // One block. Idle warps (level < base) are paired with busy warps that own a frame with at
 // least two untried values; the donor keeps the lower half of the untried interval, the idle
@@ -603,6 +890,7 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
 
 // ---- host-side launch wrappers -----------------------------------------------------------------------
 size_t search_smem_bytes(const DevModel &m) {
+  if (m.lov) return (size_t)m.lov_smem_bytes;
   const int wwords = (4 * m.n_vars + 3 * m.mask_words + 3) & ~3;
   return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
 }
@@ -615,6 +903,11 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 int search_blocks_per_sm(const DevModel &m, bool expand) {
   int n = 0;
   const size_t smem = search_smem_bytes(m);
+  if (m.lov) {
+    if (expand) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search_lov<true>, THREADS_PER_BLOCK, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search_lov<false>, THREADS_PER_BLOCK, smem);
+    return n;
+  }
   const void *fn = expand ? (const void *)k_search<true> : (const void *)k_search<false>;
   if (ensure_smem(fn, smem) != cudaSuccess) return 0;
   if (expand) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search<true>, THREADS_PER_BLOCK, smem);
@@ -624,6 +917,11 @@ int search_blocks_per_sm(const DevModel &m, bool expand) {
 
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
   const size_t smem = search_smem_bytes(a.m);
+  if (a.m.lov) {
+    if (expand) k_search_lov<true><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
+    else k_search_lov<false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
+    return cudaGetLastError();
+  }
   if (expand) {
     cudaError_t e = ensure_smem((const void *)k_search<true>, smem);
     if (e != cudaSuccess) return e;
@@ -650,6 +948,10 @@ cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t st) {
   const size_t smem = search_smem_bytes(m);
+  if (m.lov) {
+    k_propagate_batch_lov<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_nodes, dom_in, var, val, dom_out, failed);
+    return cudaGetLastError();
+  }
   cudaError_t e = ensure_smem((const void *)k_propagate_batch, smem);
   if (e != cudaSuccess) return e;
   k_propagate_batch<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_nodes, dom_in, var, val, best, dom_out, failed);

@@ -83,6 +83,54 @@ extern "C" int hc_node(const int32_t *dom_in, int var, int32_t val, int32_t best
   return failed ? 1 : 0;
 }
 
+// the "lane owns variable" fixpoint with the warp emulated lane by lane (shuffles = array reads,
+// ballots = loops); returns -1 when the model is not eligible
+extern "C" int hc_node_lov(const int32_t *dom_in, int var, int32_t val, int32_t *dom_out) {
+  const DevModel &m = g_cm.host;
+  if (!m.lov) return -1;
+  const int V = m.n_vars;
+  int32_t lo[32], hi[32];
+  for (int j = 0; j < 32; j++) { lo[j] = j < V ? dom_in[2 * j] : 0; hi[j] = j < V ? dom_in[2 * j + 1] : 0; }
+  if (lo[var] != hi[var]) { lo[var] = val; hi[var] = val; }
+  uint32_t changed = 1u << var;
+  bool failed = false;
+  while (changed && !failed) {
+    const int i = __builtin_ctz(changed);
+    changed &= changed - 1;
+    const int32_t Xlo = lo[i], Xhi = hi[i];
+    if (Xlo > Xhi) { failed = true; break; }
+    uint32_t bl = 0, bh = 0, chm = 0;
+    int32_t nlo[32], nhi[32];
+    for (int j = 0; j < 32; j++) {
+      nlo[j] = lo[j]; nhi[j] = hi[j];
+      if (j >= V) continue;
+      LovStep r = lov_lane_step(m.lov_pair[i * 32 + j], Xlo, Xhi, lo[j], hi[j]);
+      bool plo = r.plo, phi = r.phi;
+      const int cb = m.lov_cptr[i], ce = m.lov_cptr[i + 1];
+      if (cb + j < ce) lov_const_step(m.lov_cval[cb + j], Xlo, Xhi, plo, phi);
+      if (r.nlo != lo[j] || r.nhi != hi[j]) chm |= 1u << j;
+      nlo[j] = r.nlo; nhi[j] = r.nhi;
+      if (plo) bl |= 1u << j;
+      if (phi) bh |= 1u << j;
+    }
+    // constants beyond lane V-1 (a variable may have up to 32 of them)
+    for (int j = V; j < 32; j++) {
+      bool plo = false, phi = false;
+      const int cb = m.lov_cptr[i], ce = m.lov_cptr[i + 1];
+      if (cb + j < ce) lov_const_step(m.lov_cval[cb + j], Xlo, Xhi, plo, phi);
+      if (plo) bl |= 1u << j;
+      if (phi) bh |= 1u << j;
+    }
+    for (int j = 0; j < 32; j++) { lo[j] = nlo[j]; hi[j] = nhi[j]; }
+    if (bl) lo[i] = Xlo + 1;
+    if (bh) hi[i] = Xhi - 1;
+    if (bl | bh) chm |= 1u << i;
+    changed |= chm;
+  }
+  for (int j = 0; j < V; j++) { dom_out[2 * j] = lo[j]; dom_out[2 * j + 1] = hi[j]; if (lo[j] > hi[j]) failed = true; }
+  return failed ? 1 : 0;
+}
+
 extern "C" int hc_leaf_true(const int32_t *dom_in) {
   const DevModel &m = g_cm.host;
   std::vector<int32_t> d(dom_in, dom_in + 2 * m.n_vars);

@@ -61,6 +61,24 @@ def test_product_contractors_on_host(name, specialise):
     assert _check_nodes(g, node, leaf) == 0
 
 
+@pytest.mark.parametrize("name", [n for n in REPLAY if n.startswith("queens")])
+def test_lane_owns_variable_form_on_host(name):
+    """the register-resident N-queens form (lov_lane_step) with the warp emulated on the host"""
+    g = np.load(os.path.join(util.GOLDEN, "replay_%s.npz" % name))
+    m = cb.Model(INST[name])
+    hc = util.harness_lib()
+    assert hc.hc_load(m.flat, 1) == 0, hc.hc_error()
+
+    def node(dom, var, val, best):
+        dom = np.ascontiguousarray(dom, np.int32)
+        out = np.empty_like(dom)
+        f = hc.hc_node_lov(util.p32(dom), var, val, util.p32(out))
+        assert f >= 0, "queens must be eligible"
+        return out, f
+
+    assert _check_nodes(g, node, lambda d: hc.hc_leaf_true(util.p32(np.ascontiguousarray(d, np.int32)))) == 0
+
+
 def test_random_instances_node_transitions():
     z = np.load(os.path.join(util.GOLDEN, "replay_random.npz"))
     g = {k: z[k] for k in z.files}
