@@ -529,6 +529,12 @@ __device__ __forceinline__ bool lov_fixpoint(const LovTables &t, int V, bool has
   return true;
 }
 
+// shared-memory frame of the LOV kernel: 8 header words (var, iter, last, lo | hi, level, amask, hash)
+// followed by the 2 * V domain words. The warp's whole DFS stack lives in shared memory during a
+// slice; it is loaded from / parked to the HBM frames (device_model.h layout) at the slice boundaries,
+// where k_rebalance and the host see it.
+__device__ __forceinline__ int lov_sframe_words(int V) { return (8 + 2 * V + 3) & ~3; }   // 16-byte aligned
+
 template <bool EXPAND>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_LOV_MIN_BLOCKS)
 k_search_lov(const SearchArgs a) {
@@ -542,6 +548,8 @@ k_search_lov(const SearchArgs a) {
 
   const int V = m.n_vars, fw = m.frame_words;
   const int dofs = frame_dom_offset(1);
+  const int sfw = lov_sframe_words(V);
+  int *sst = smem + (m.lov_smem_bytes >> 2) + wib * (EXPAND ? sfw : V * sfw);   // this warp's stack
   int *stack = a.stacks + (size_t)gw * (V + 1) * fw;
   SearchCtl *ctl = a.ctl;
   const bool act = lane < V;
@@ -551,6 +559,26 @@ k_search_lov(const SearchArgs a) {
   unsigned long long nodes = 0, cuts = 0, sols = 0;
   unsigned props = 0, visits = 0;
   const long long t0 = clock64();
+
+  // HBM frame -> shared frame
+  auto frame_in = [&](const int *g, int *sf) {
+    if (lane < 8) sf[lane] = lane == 6 ? __ldcg(&g[FR_MASK]) : __ldcg(&g[lane]);
+    if (act) reinterpret_cast<int2 *>(sf + 8)[lane] = __ldcg(reinterpret_cast<const int2 *>(g + dofs) + lane);
+  };
+  // shared frame -> HBM frame (best_seen is unused by pure NOT(EQ) networks)
+  auto frame_out = [&](const int *sf, int *g) {
+    if (lane < 8) {
+      int w = sf[lane];
+      if (lane == 6) { __stcg(&g[FR_MASK], w); w = 0; }
+      __stcg(&g[lane], w);
+    }
+    if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, reinterpret_cast<const int2 *>(sf + 8)[lane]);
+  };
+
+  if (!EXPAND && level >= base) {
+    for (int L = base; L <= level; ++L) frame_in(stack + (size_t)L * fw, sst + L * sfw);
+    __syncwarp();
+  }
 
   bool have = false;
   int var = 0, flo = 0, fhi = 0, flevel = 0;
@@ -573,23 +601,21 @@ k_search_lov(const SearchArgs a) {
       }
       const int *src = a.items + (size_t)it * fw;
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
-      int *dst = stack + (size_t)L * fw;
-      for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
+      frame_in(src, sst + L * sfw);
       level = base = L;
       have = false;
       __syncwarp();
     }
 
-    int *f = stack + (size_t)level * fw;
+    int *sf = sst + level * sfw;
     if (!have) {
-      const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(f));
-      const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(f) + 1);
-      amask = (unsigned)__ldcg(&f[FR_MASK]);
+      const int4 h0 = reinterpret_cast<const int4 *>(sf)[0];
+      const int4 h1 = reinterpret_cast<const int4 *>(sf)[1];
       int2 dj = make_int2(0, 0);
-      if (act) dj = __ldcg(reinterpret_cast<const int2 *>(f + dofs) + lane);
+      if (act) dj = reinterpret_cast<const int2 *>(sf + 8)[lane];
       plo = dj.x; phi = dj.y;
       var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; flo = h0.w;
-      fhi = h1.x; flevel = h1.y; fhash = (unsigned)h1.w;
+      fhi = h1.x; flevel = h1.y; amask = (unsigned)h1.z; fhash = (unsigned)h1.w;
       have = true;
     }
 
@@ -597,12 +623,8 @@ k_search_lov(const SearchArgs a) {
       int slot = 0;
       if (lane == 0) { slot = atomicAdd(&ctl->out_count, 1); atomicAdd(&ctl->passed, 1); }
       slot = __shfl_sync(FULL, slot, 0);
-      if (slot < a.out_cap) {
-        int *g = a.items_out + (size_t)slot * fw;
-        for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&f[w]));
-      } else if (lane == 0) {
-        atomicAdd(&ctl->out_dropped, 1);
-      }
+      if (slot < a.out_cap) frame_out(sf, a.items_out + (size_t)slot * fw);
+      else if (lane == 0) atomicAdd(&ctl->out_dropped, 1);
       level = base - 1;
       have = false;
       continue;
@@ -684,31 +706,38 @@ k_search_lov(const SearchArgs a) {
       }
       const unsigned chash = mix_hash(fhash, (unsigned)var, (unsigned)val);
       const int nlo = __shfl_sync(FULL, lo, nv), nhi = __shfl_sync(FULL, hi, nv);
-      int *g;
+      const unsigned nlast = (unsigned)nhi - (unsigned)nlo;
+      const unsigned nmask = amask | (1u << var);
       if (EXPAND) {
         int slot = 0;
         if (lane == 0) slot = atomicAdd(&ctl->out_count, 1);
         slot = __shfl_sync(FULL, slot, 0);
-        g = slot < a.out_cap ? a.items_out + (size_t)slot * fw : nullptr;
-        if (g == nullptr && lane == 0) atomicAdd(&ctl->out_dropped, 1);
-      } else {
-        if (lane == 0) __stcg(&f[FR_ITER], (int)iter);
-        g = stack + (size_t)(level + 1) * fw;
-      }
-      if (g != nullptr) {
-        if (lane == 0) {
-          __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)((unsigned)nhi - (unsigned)nlo), nlo));
-          __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nhi, flevel + 1, 0, (int)chash));
-          __stcg(&g[FR_MASK], (int)(amask | (1u << var)));
+        if (slot < a.out_cap) {
+          int *g = a.items_out + (size_t)slot * fw;
+          if (lane == 0) {
+            __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)nlast, nlo));
+            __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nhi, flevel + 1, 0, (int)chash));
+            __stcg(&g[FR_MASK], (int)nmask);
+          }
+          if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, make_int2(lo, hi));
+        } else if (lane == 0) {
+          atomicAdd(&ctl->out_dropped, 1);
         }
-        if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, make_int2(lo, hi));
-      }
-      if (!EXPAND) {
-        amask |= 1u << var;
+      } else {
+        // push: everything stays in shared memory / registers
+        int *nf = sf + sfw;
+        if (lane == 0) {
+          sf[FR_ITER] = (int)iter;
+          reinterpret_cast<int4 *>(nf)[0] = make_int4(nv, 0, (int)nlast, nlo);
+          reinterpret_cast<int4 *>(nf)[1] = make_int4(nhi, flevel + 1, (int)nmask, (int)chash);
+        }
+        if (act) reinterpret_cast<int2 *>(nf + 8)[lane] = make_int2(lo, hi);
+        amask = nmask;
         plo = lo; phi = hi;
-        var = nv; flo = nlo; fhi = nhi; iter = 0; last = (unsigned)nhi - (unsigned)nlo;
+        var = nv; flo = nlo; fhi = nhi; iter = 0; last = nlast;
         flevel = flevel + 1; fhash = chash;
         level++;
+        __syncwarp();
       }
     }
 
@@ -721,8 +750,13 @@ k_search_lov(const SearchArgs a) {
     }
   }
 
+  if (!EXPAND && level >= base) {
+    // park: the stack goes back to HBM for k_rebalance / the next slice
+    if (have && lane == 0) sst[level * sfw + FR_ITER] = (int)iter;
+    __syncwarp();
+    for (int L = base; L <= level; ++L) frame_out(sst + L * sfw, stack + (size_t)L * fw);
+  }
   if (lane == 0) {
-    if (have && level >= base) __stcg(&stack[(size_t)level * fw + FR_ITER], (int)iter);
     a.wstate[gw].level = level;
     a.wstate[gw].base = base;
     unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
@@ -890,7 +924,7 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
 
 // ---- host-side launch wrappers -----------------------------------------------------------------------
 size_t search_smem_bytes(const DevModel &m) {
-  if (m.lov) return (size_t)m.lov_smem_bytes;
+  if (m.lov) return (size_t)m.lov_smem_bytes + (size_t)WARPS_PER_BLOCK * m.n_vars * ((8 + 2 * m.n_vars + 3) & ~3) * sizeof(int);
   const int wwords = (4 * m.n_vars + 3 * m.mask_words + 3) & ~3;
   return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
 }
@@ -904,6 +938,8 @@ int search_blocks_per_sm(const DevModel &m, bool expand) {
   int n = 0;
   const size_t smem = search_smem_bytes(m);
   if (m.lov) {
+    const void *lf = expand ? (const void *)k_search_lov<true> : (const void *)k_search_lov<false>;
+    if (ensure_smem(lf, smem) != cudaSuccess) return 0;
     if (expand) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search_lov<true>, THREADS_PER_BLOCK, smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search_lov<false>, THREADS_PER_BLOCK, smem);
     return n;
@@ -918,6 +954,8 @@ int search_blocks_per_sm(const DevModel &m, bool expand) {
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
   const size_t smem = search_smem_bytes(a.m);
   if (a.m.lov) {
+    cudaError_t e = ensure_smem(expand ? (const void *)k_search_lov<true> : (const void *)k_search_lov<false>, smem);
+    if (e != cudaSuccess) return e;
     if (expand) k_search_lov<true><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
     else k_search_lov<false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
     return cudaGetLastError();
@@ -949,6 +987,8 @@ cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t
                                    int grid, cudaStream_t st) {
   const size_t smem = search_smem_bytes(m);
   if (m.lov) {
+    cudaError_t e = ensure_smem((const void *)k_propagate_batch_lov, smem);
+    if (e != cudaSuccess) return e;
     k_propagate_batch_lov<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_nodes, dom_in, var, val, dom_out, failed);
     return cudaGetLastError();
   }
