@@ -197,6 +197,20 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     }
     out.lov_cptr[V] = (int32_t)out.lov_cval.size();
     out.host.lov = lov ? 1 : 0;
+    int32_t vmin = INT32_MAX, vmax = INT32_MIN;
+    for (int v = 0; v < V; v++) { vmin = std::min(vmin, m.var_lo[v]); vmax = std::max(vmax, m.var_hi[v]); }
+    bool bits = lov && (int64_t)vmax - (int64_t)vmin < 32;
+    // constants outside the window can never sit on a bound: they are simply not representable (and not needed)
+    out.host.lov_bits = bits ? 1 : 0;
+    out.host.lov_vbase = vmin;
+    out.lov_fconst.assign(V, 0u);
+    if (bits) {
+      for (int v = 0; v < V; v++)
+        for (int k = out.lov_cptr[v]; k < out.lov_cptr[v + 1]; k++) {
+          const int64_t b = (int64_t)out.lov_cval[k] - vmin;
+          if (b >= 0 && b < 32) out.lov_fconst[v] |= 1u << b;
+        }
+    }
   }
 
   // static branching order: priority descending, index ascending (the reference's heap with
@@ -223,7 +237,8 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   h.wrec = out.wrec.data();
   h.lov_pair = out.lov_pair.data(); h.lov_cptr = out.lov_cptr.data(); h.lov_cval = out.lov_cval.data();
   h.n_lov_cval = (int32_t)out.lov_cval.size();
-  h.lov_smem_bytes = (int32_t)((((size_t)V * 32 * 2 + (V + 1) + out.lov_cval.size()) * 4 + 15) & ~(size_t)15);
+  h.lov_fconst = out.lov_fconst.data();
+  h.lov_smem_bytes = (int32_t)((((size_t)V * 32 * 2 + (V + 1) + out.lov_cval.size() + V) * 4 + 15) & ~(size_t)15);
   h.wrec_ptr = out.wrec_ptr.data();
   h.n_wrec = (int32_t)out.wrec.size();
   {

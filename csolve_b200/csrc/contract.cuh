@@ -406,6 +406,34 @@ CSOLVE_HD LovStep lov_lane_step(unsigned long long mask, int32_t Xlo, int32_t Xh
   }
   return r;
 }
+// ---- forbidden-value sets ---------------------------------------------------------------------------
+// When all root domains fit a window of 32 values (bit b = value vbase + b) the same fixpoint is
+// reached without re-queuing a variable for every single bound move: F_j collects the values the
+// variables that ARE a value (and the constants) forbid for x_j; the contractors of
+// src/propagate.c:104-119 remove a forbidden value only while it sits on a bound, i.e. lo moves up
+// to the first value >= lo that is not in F_j and hi down to the last value <= hi not in F_j.
+// Values strictly inside the interval stay (intervals have no holes), exactly as in the reference.
+//
+// lov_forbid: variable i became the value w; mask = lov_pair[i][j] (bit c + 32: x_i + c != x_j).
+// Forbidden for j: w + c, i.e. bit (w - vbase) + c  ->  mask shifted right by 32 - (w - vbase).
+CSOLVE_HD uint32_t lov_forbid(unsigned long long mask, int32_t w, int32_t vbase) {
+  return (uint32_t)(mask >> (32 - (w - vbase)));
+}
+// lov_trim: returns false when no value of [lo,hi] survives (PROP_ERROR)
+CSOLVE_HD bool lov_trim(uint32_t F, int32_t vbase, int32_t &lo, int32_t &hi) {
+  const int bl = lo - vbase, bh = hi - vbase;                 // 0..31
+  uint32_t free_ = ~F & (0xffffffffu << bl) & (0xffffffffu >> (31 - bh));
+  if (free_ == 0u) return false;
+#if defined(__CUDA_ARCH__)
+  lo = vbase + (__ffs((int)free_) - 1);
+  hi = vbase + (31 - __clz((int)free_));
+#else
+  lo = vbase + __builtin_ctz(free_);
+  hi = vbase + (31 - __builtin_clz(free_));
+#endif
+  return true;
+}
+
 // forbidden constant c of the dequeued variable (x_i != c): which bound of i it removes
 CSOLVE_HD void lov_const_step(int32_t c, int32_t Xlo, int32_t Xhi, bool &plo, bool &phi) {
   const bool cl = c == Xlo;

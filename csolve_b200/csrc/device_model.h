@@ -60,11 +60,14 @@ struct DevModel {
   //                           holds the clause x_i + c != x_j  (-32 <= c < 32)
   //   lov_cptr / lov_cval   = per variable CSR of forbidden constants (x_i != c)
   int32_t lov;               // 1 when the model is eligible
+  int32_t lov_bits;          // 1 when additionally all root domains fit a 32-value window (forbidden-value sets)
+  int32_t lov_vbase;         // smallest root lower bound (bit 0 of the value sets)
   int32_t lov_smem_bytes;
   int32_t n_lov_cval;
   const unsigned long long *lov_pair;  // [n_vars * 32]
   const int32_t *lov_cptr;   // [n_vars + 1]
   const int32_t *lov_cval;   // [n_lov_cval]
+  const uint32_t *lov_fconst; // [n_vars] forbidden-value set of the constants (lov_bits)
   const uint8_t *node_op;    // [n_nodes]
   const int32_t *node_l;     // [n_nodes]
   const int32_t *node_r;     // [n_nodes]

@@ -477,17 +477,19 @@ k_search(const SearchArgs a) {
 // with it (lov_lane_step), bounds requested of the dequeued variable are combined with ballots.
 // No atomics, no divergence; the worklist is a 32-bit register mask. Same frames, same frontier,
 // same rebalancing as k_search.
-struct LovTables { const unsigned long long *pair; const int *cptr; const int *cval; };
+struct LovTables { const unsigned long long *pair; const int *cptr; const int *cval; const uint32_t *fconst; };
 
 __device__ __forceinline__ LovTables stage_lov(const DevModel &m, int *smem) {
   unsigned long long *pair = reinterpret_cast<unsigned long long *>(smem);
   int *cptr = smem + m.n_vars * 64;
   int *cval = cptr + m.n_vars + 1;
+  uint32_t *fconst = reinterpret_cast<uint32_t *>(cval + m.n_lov_cval);
+  for (int i = threadIdx.x; i < m.n_vars; i += blockDim.x) fconst[i] = __ldg(&m.lov_fconst[i]);
   for (int i = threadIdx.x; i < m.n_vars * 32; i += blockDim.x) pair[i] = __ldg(&m.lov_pair[i]);
   for (int i = threadIdx.x; i <= m.n_vars; i += blockDim.x) cptr[i] = __ldg(&m.lov_cptr[i]);
   for (int i = threadIdx.x; i < m.n_lov_cval; i += blockDim.x) cval[i] = __ldg(&m.lov_cval[i]);
   __syncthreads();
-  LovTables t; t.pair = pair; t.cptr = cptr; t.cval = cval;
+  LovTables t; t.pair = pair; t.cptr = cptr; t.cval = cval; t.fconst = fconst;
   return t;
 }
 
@@ -529,13 +531,43 @@ __device__ __forceinline__ bool lov_fixpoint(const LovTables &t, int V, bool has
   return true;
 }
 
+// Forbidden-value-set form of the same fixpoint (contract.cuh: lov_forbid / lov_trim). `pend` holds the
+// variables that became a value and whose forbidden values have not been distributed yet.
+__device__ __forceinline__ bool lov_fixpoint_bits(const LovTables &t, int V, int vbase, int lane, int &lo, int &hi,
+                                                  uint32_t &F, unsigned pend, unsigned &props, unsigned &visits) {
+  const bool act = lane < V;
+  while (pend) {
+    const int i = __ffs(pend) - 1;
+    pend &= pend - 1;
+    const int w = __shfl_sync(FULL, lo, i);
+    if (act) F |= lov_forbid(t.pair[i * 32 + lane], w, vbase);
+    const bool was = lo == hi;
+    const int olo = lo, ohi = hi;
+    const bool alive = lov_trim(F, vbase, lo, hi);
+    if (__any_sync(FULL, !alive)) return false;
+    pend |= __ballot_sync(FULL, !was && lo == hi);
+    props += __popc(__ballot_sync(FULL, lo != olo || hi != ohi));
+    visits += (unsigned)V;
+  }
+  return true;
+}
+// forbidden-value set of this lane's variable for a frame whose domains are in sdom (lo,hi pairs)
+__device__ __forceinline__ uint32_t lov_rebuild_F(const LovTables &t, int V, int vbase, int lane, const int *sdom) {
+  uint32_t F = lane < V ? t.fconst[lane] : 0u;
+  for (int i = 0; i < V; i++) {
+    const int2 di = reinterpret_cast<const int2 *>(sdom)[i];
+    if (di.x == di.y && lane < V) F |= lov_forbid(t.pair[i * 32 + lane], di.x, vbase);
+  }
+  return F;
+}
+
 // shared-memory frame of the LOV kernel: 8 header words (var, iter, last, lo | hi, level, amask, hash)
 // followed by the 2 * V domain words. The warp's whole DFS stack lives in shared memory during a
 // slice; it is loaded from / parked to the HBM frames (device_model.h layout) at the slice boundaries,
 // where k_rebalance and the host see it.
-__device__ __forceinline__ int lov_sframe_words(int V) { return (8 + 2 * V + 3) & ~3; }   // 16-byte aligned
+__device__ __forceinline__ int lov_sframe_words(int V) { return (8 + 3 * V + 3) & ~3; }   // header, domains, value sets; 16-byte aligned
 
-template <bool EXPAND>
+template <bool EXPAND, bool BITS>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_LOV_MIN_BLOCKS)
 k_search_lov(const SearchArgs a) {
   extern __shared__ __align__(16) int smem[];
@@ -554,6 +586,7 @@ k_search_lov(const SearchArgs a) {
   SearchCtl *ctl = a.ctl;
   const bool act = lane < V;
   const bool has_consts = m.n_lov_cval > 0;
+  const int vbase = m.lov_vbase;
 
   int level = a.wstate[gw].level, base = a.wstate[gw].base;
   unsigned long long nodes = 0, cuts = 0, sols = 0;
@@ -564,6 +597,11 @@ k_search_lov(const SearchArgs a) {
   auto frame_in = [&](const int *g, int *sf) {
     if (lane < 8) sf[lane] = lane == 6 ? __ldcg(&g[FR_MASK]) : __ldcg(&g[lane]);
     if (act) reinterpret_cast<int2 *>(sf + 8)[lane] = __ldcg(reinterpret_cast<const int2 *>(g + dofs) + lane);
+    if (BITS) {
+      __syncwarp();
+      const uint32_t F = lov_rebuild_F(T, V, vbase, lane, sf + 8);
+      if (act) sf[8 + 2 * V + lane] = (int)F;
+    }
   };
   // shared frame -> HBM frame (best_seen is unused by pure NOT(EQ) networks)
   auto frame_out = [&](const int *sf, int *g) {
@@ -584,6 +622,7 @@ k_search_lov(const SearchArgs a) {
   int var = 0, flo = 0, fhi = 0, flevel = 0;
   unsigned iter = 0, last = 0, fhash = 0, amask = 0;
   int plo = 0, phi = 0;        // this lane's variable in the top frame (state before the assignment)
+  uint32_t pF = 0;             // ... and its forbidden-value set (BITS)
 
   for (;;) {
     const int sig = *reinterpret_cast<volatile int *>(&ctl->signal);
@@ -611,9 +650,10 @@ k_search_lov(const SearchArgs a) {
     if (!have) {
       const int4 h0 = reinterpret_cast<const int4 *>(sf)[0];
       const int4 h1 = reinterpret_cast<const int4 *>(sf)[1];
-      int2 dj = make_int2(0, 0);
+      int2 dj = make_int2(vbase, vbase);       // idle lanes hold a harmless one-value domain
       if (act) dj = reinterpret_cast<const int2 *>(sf + 8)[lane];
       plo = dj.x; phi = dj.y;
+      if (BITS) pF = act ? (uint32_t)sf[8 + 2 * V + lane] : 0u;
       var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; flo = h0.w;
       fhi = h1.x; flevel = h1.y; amask = (unsigned)h1.z; fhash = (unsigned)h1.w;
       have = true;
@@ -641,7 +681,9 @@ k_search_lov(const SearchArgs a) {
     iter++;
     int lo = plo, hi = phi;
     if (lane == var) { lo = val; hi = val; }
-    const bool ok = lov_fixpoint(T, V, has_consts, lane, lo, hi, 1u << var, props, visits);
+    uint32_t F = pF;
+    const bool ok = BITS ? lov_fixpoint_bits(T, V, vbase, lane, lo, hi, F, 1u << var, props, visits)
+                         : lov_fixpoint(T, V, has_consts, lane, lo, hi, 1u << var, props, visits);
     nodes++;
 
     if (!ok) {
@@ -649,7 +691,8 @@ k_search_lov(const SearchArgs a) {
     } else if (flevel + 1 == V) {
       // leaf: is_true(eval(root)) -- every clause x_i + c != x_j / x_i != c holds on the assignment
       bool good = lo == hi;
-      for (int i = 0; i < V; i++) {
+      if (BITS) good = good && !((F >> (lo - vbase)) & 1u);     // F holds every value the other variables forbid
+      for (int i = 0; !BITS && i < V; i++) {
         const int Xi = __shfl_sync(FULL, lo, i);
         const unsigned long long mk = act ? T.pair[i * 32 + lane] : 0ull;
         if (lov_has(mk, lo - Xi)) good = false;      // x_i + c == x_j for a clause of the pair
@@ -732,8 +775,9 @@ k_search_lov(const SearchArgs a) {
           reinterpret_cast<int4 *>(nf)[1] = make_int4(nhi, flevel + 1, (int)nmask, (int)chash);
         }
         if (act) reinterpret_cast<int2 *>(nf + 8)[lane] = make_int2(lo, hi);
+        if (BITS && act) nf[8 + 2 * V + lane] = (int)F;
         amask = nmask;
-        plo = lo; phi = hi;
+        plo = lo; phi = hi; pF = F;
         var = nv; flo = nlo; fhi = nhi; iter = 0; last = nlast;
         flevel = flevel + 1; fhash = chash;
         level++;
@@ -781,7 +825,19 @@ k_propagate_batch_lov(const DevModel m, int n_nodes, const int32_t *dom_in, cons
     const int x = var[b];
     if (lane == x && lo != hi) { lo = val[b]; hi = val[b]; }
     unsigned props = 0, visits = 0;
-    bool ok = lov_fixpoint(T, V, m.n_lov_cval > 0, lane, lo, hi, 1u << x, props, visits);
+    bool ok;
+    if (m.lov_bits) {
+      // forbidden-value sets of the incoming state, then the transition
+      if (!act) { lo = m.lov_vbase; hi = m.lov_vbase; }
+      uint32_t F = act ? T.fconst[lane] : 0u;
+      for (int i = 0; i < V; i++) {
+        const int li = __shfl_sync(FULL, dj.x, i), hi_i = __shfl_sync(FULL, dj.y, i);
+        if (li == hi_i && act) F |= lov_forbid(T.pair[i * 32 + lane], li, m.lov_vbase);
+      }
+      ok = lov_fixpoint_bits(T, V, m.lov_vbase, lane, lo, hi, F, 1u << x, props, visits);
+    } else {
+      ok = lov_fixpoint(T, V, m.n_lov_cval > 0, lane, lo, hi, 1u << x, props, visits);
+    }
     ok = ok && !__any_sync(FULL, act && lo > hi);
     if (act) reinterpret_cast<int2 *>(dom_out + (size_t)b * 2 * V)[lane] = make_int2(lo, hi);
     if (lane == 0) failed[b] = ok ? 0 : 1;
@@ -924,9 +980,14 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
 
 // ---- host-side launch wrappers -----------------------------------------------------------------------
 size_t search_smem_bytes(const DevModel &m) {
-  if (m.lov) return (size_t)m.lov_smem_bytes + (size_t)WARPS_PER_BLOCK * m.n_vars * ((8 + 2 * m.n_vars + 3) & ~3) * sizeof(int);
+  if (m.lov) return (size_t)m.lov_smem_bytes + (size_t)WARPS_PER_BLOCK * m.n_vars * ((8 + 3 * m.n_vars + 3) & ~3) * sizeof(int);
   const int wwords = (4 * m.n_vars + 3 * m.mask_words + 3) & ~3;
   return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
+}
+
+static const void *lov_kernel(bool expand, bool bits) {
+  if (expand) return bits ? (const void *)k_search_lov<true, true> : (const void *)k_search_lov<true, false>;
+  return bits ? (const void *)k_search_lov<false, true> : (const void *)k_search_lov<false, false>;
 }
 
 static cudaError_t ensure_smem(const void *fn, size_t bytes) {
@@ -938,10 +999,9 @@ int search_blocks_per_sm(const DevModel &m, bool expand) {
   int n = 0;
   const size_t smem = search_smem_bytes(m);
   if (m.lov) {
-    const void *lf = expand ? (const void *)k_search_lov<true> : (const void *)k_search_lov<false>;
+    const void *lf = lov_kernel(expand, m.lov_bits != 0);
     if (ensure_smem(lf, smem) != cudaSuccess) return 0;
-    if (expand) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search_lov<true>, THREADS_PER_BLOCK, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search_lov<false>, THREADS_PER_BLOCK, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lf, THREADS_PER_BLOCK, smem);
     return n;
   }
   const void *fn = expand ? (const void *)k_search<true> : (const void *)k_search<false>;
@@ -954,11 +1014,11 @@ int search_blocks_per_sm(const DevModel &m, bool expand) {
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
   const size_t smem = search_smem_bytes(a.m);
   if (a.m.lov) {
-    cudaError_t e = ensure_smem(expand ? (const void *)k_search_lov<true> : (const void *)k_search_lov<false>, smem);
+    const void *lf = lov_kernel(expand, a.m.lov_bits != 0);
+    cudaError_t e = ensure_smem(lf, smem);
     if (e != cudaSuccess) return e;
-    if (expand) k_search_lov<true><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
-    else k_search_lov<false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
-    return cudaGetLastError();
+    void *args[] = {(void *)&a};
+    return cudaLaunchKernel(lf, dim3(grid), dim3(THREADS_PER_BLOCK), args, smem, st);
   }
   if (expand) {
     cudaError_t e = ensure_smem((const void *)k_search<true>, smem);

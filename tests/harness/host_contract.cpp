@@ -94,6 +94,30 @@ extern "C" int hc_node_lov(const int32_t *dom_in, int var, int32_t val, int32_t 
   if (lo[var] != hi[var]) { lo[var] = val; hi[var] = val; }
   uint32_t changed = 1u << var;
   bool failed = false;
+  if (m.lov_bits) {
+    // forbidden-value-set form (lov_forbid / lov_trim), lanes emulated one after the other
+    const int vb = m.lov_vbase;
+    uint32_t F[32];
+    for (int j = 0; j < V; j++) {
+      F[j] = m.lov_fconst[j];
+      for (int i = 0; i < V; i++)
+        if (dom_in[2 * i] == dom_in[2 * i + 1]) F[j] |= lov_forbid(m.lov_pair[i * 32 + j], dom_in[2 * i], vb);
+    }
+    uint32_t pend = 1u << var;
+    while (pend && !failed) {
+      const int i = __builtin_ctz(pend);
+      pend &= pend - 1;
+      const int32_t w = lo[i];
+      for (int j = 0; j < V; j++) {
+        F[j] |= lov_forbid(m.lov_pair[i * 32 + j], w, vb);
+        const bool was = lo[j] == hi[j];
+        if (!lov_trim(F[j], vb, lo[j], hi[j])) { failed = true; }
+        else if (!was && lo[j] == hi[j]) pend |= 1u << j;
+      }
+    }
+    for (int j = 0; j < V; j++) { dom_out[2 * j] = lo[j]; dom_out[2 * j + 1] = hi[j]; }
+    return failed ? 1 : 0;
+  }
   while (changed && !failed) {
     const int i = __builtin_ctz(changed);
     changed &= changed - 1;
