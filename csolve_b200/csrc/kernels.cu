@@ -26,6 +26,9 @@ namespace csolve_dev {
 #define FULL 0xffffffffu
 
 // resident blocks per SM the search kernel is compiled for (bounds the registers per thread)
+// nodes between two polls of the control block (signal, time slice)
+#define POLL_NODES 32
+
 #ifndef CSOLVE_LOV_MIN_BLOCKS
 #define CSOLVE_LOV_MIN_BLOCKS 4
 #endif
@@ -252,10 +255,9 @@ k_search(const SearchArgs a) {
   // a frame is pushed, popped, refreshed, parked or fetched from the frontier.
   bool have = false;
   int var = 0, lo = 0, hi = 0, flevel = 0, fbest = 0;
-  unsigned iter = 0, last = 0, fhash = 0;
+  unsigned iter = 0, last = 0, fhash = 0, poll = 0;
 
   for (;;) {
-    const int sig = *reinterpret_cast<volatile int *>(&ctl->signal);   // consumed at the end of the node
 
     if (level < base) {
       // out of work: take the next frontier frame, or go idle
@@ -443,8 +445,10 @@ k_search(const SearchArgs a) {
     }
 
     // ---- park? ----------------------------------------------------------------------------------
-    if (!EXPAND) {
-      if (sig != SIG_RUN) break;
+    // every POLL_NODES nodes: has a slice end / stop been requested, is the time slice over?
+    // (an L2 round trip per node would dominate short nodes)
+    if (!EXPAND && (++poll & (POLL_NODES - 1)) == 0) {
+      if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
@@ -623,10 +627,9 @@ k_search_lov(const SearchArgs a) {
   unsigned iter = 0, last = 0, fhash = 0, amask = 0;
   int plo = 0, phi = 0;        // this lane's variable in the top frame (state before the assignment)
   uint32_t pF = 0;             // ... and its forbidden-value set (BITS)
+  unsigned poll = 0;
 
   for (;;) {
-    const int sig = *reinterpret_cast<volatile int *>(&ctl->signal);
-
     if (level < base) {
       int it = 0;
       if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
@@ -785,8 +788,8 @@ k_search_lov(const SearchArgs a) {
       }
     }
 
-    if (!EXPAND) {
-      if (sig != SIG_RUN) break;
+    if (!EXPAND && (++poll & (POLL_NODES - 1)) == 0) {
+      if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
