@@ -248,9 +248,9 @@ def run_ours(args):
                     "path": "Model(text) -> GpuProblem -> solve() through libcsolve_b200.so, host buffers"},
             "gpu_launches": tot_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "k_search<false>",
+                         "frac": achieved / peak, "traffic": None, "kernel": "k_search_lov<false,true>" if args.queens <= 32 else "k_search<false>",
                          "bytes_per_node": bytes_per_node, "peak_source": peak_src,
-                         "note": "rank 0; algorithmic bytes = nodes x 2 x (8V+16); the kernel is issue/latency bound, see DESIGN.md"},
+                         "note": "rank 0; algorithmic bytes = nodes x 2 x (8V+16); the DFS stacks live in shared memory during a slice, so real DRAM traffic is far below this nominal figure (DESIGN.md)"},
         }
         if not args.no_cpu_baseline and world == 1:
             c, dt, kind, sols = cpu_reference_run(args.cpu_queens)

@@ -211,7 +211,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
   int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 48;
-  int cap = std::max(target * 16, 1 << 16);
+  int cap = std::max(target * 4, 1 << 16);
   const size_t max_bytes = (size_t)2 << 30;   // per pool
   while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
   if (cap > p->pool_cap) {
