@@ -219,6 +219,8 @@ def run_ours(args):
         tot_nodes += red["nodes"]; tot_sols = red["solutions"]; tot_launch += red["kernel_launches"]
         dev_ms += red["kernel_ms"] + red["expand_ms"]   # max over ranks, device clock (CUDA events on the library's stream)
         search_ms += res.kernel_ms
+        print("[bench rank %d] nodes=%d search_ms=%.2f expand_ms=%.2f launches=%d wall_ms=%.2f" % (
+            rank, res.nodes, res.kernel_ms, res.expand_ms, res.kernel_launches, wall * 1e3), file=sys.stderr, flush=True)
         my_nodes += res.nodes
         wall_s += float(w.item())
     barrier()

@@ -210,8 +210,8 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
     CUDA_TRY(cudaMalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
-  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 48;
-  int cap = std::max(target * 4, 1 << 16);
+  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 64;
+  int cap = std::max(target * 16, 1 << 16);
   const size_t max_bytes = (size_t)2 << 30;   // per pool
   while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
   if (cap > p->pool_cap) {
@@ -283,7 +283,7 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   uint64_t launches = 0;
 
   // ---- batched frontier expansion -------------------------------------------------------------------
-  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 48;
+  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 64;
   long long max_branch = 1;
   for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
   max_branch = std::min<long long>(max_branch, a.expand_branch_max);
@@ -311,21 +311,9 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   }
   CUDA_TRY(cudaEventRecord(ev1, st));
 
-  // ---- partition: this rank keeps the frames whose path hash maps to it --------------------------------
-  if (opt.part_count > 1 && n_items > 0) {
-    std::vector<int32_t> all((size_t)n_items * fw);
-    CUDA_TRY(cudaMemcpyAsync(all.data(), pin, all.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    std::vector<int32_t> mine;
-    mine.reserve(all.size() / opt.part_count + fw);
-    for (int i = 0; i < n_items; i++) {
-      const uint32_t h = (uint32_t)all[(size_t)i * fw + 7];
-      if ((int)(h % (uint32_t)opt.part_count) == opt.part_rank) mine.insert(mine.end(), all.begin() + (size_t)i * fw, all.begin() + (size_t)(i + 1) * fw);
-    }
-    n_items = (int)(mine.size() / fw);
-    if (n_items > 0) CUDA_TRY(cudaMemcpyAsync(pin, mine.data(), mine.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-  }
+  // ---- partition: every rank holds the whole frontier; the search kernel skips the frames whose path
+  //      hash maps to another rank (no copy, no compaction)
+  a.part_rank = opt.part_rank; a.part_count = opt.part_count;
 
   if (opt.part_count > 1 && opt.part_rank != 0) {
     // the expansion was replicated on every rank (also when it exhausted the whole tree):

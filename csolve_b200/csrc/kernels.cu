@@ -261,9 +261,16 @@ k_search(const SearchArgs a) {
 
     if (level < base) {
       // out of work: take the next frontier frame, or go idle
+      // next frontier frame of this rank's partition (frames of other ranks are skipped, not copied)
       int it = 0;
-      if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
-      it = __shfl_sync(FULL, it, 0);
+      const int *src = nullptr;
+      for (;;) {
+        if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= ctl->item_count) break;
+        src = a.items + (size_t)it * fw;
+        if (EXPAND || a.part_count <= 1 || (unsigned)__ldcg(&src[7]) % (unsigned)a.part_count == (unsigned)a.part_rank) break;
+      }
       if (it >= ctl->item_count) {
         if (lane == 0) {
           const int n = atomicAdd(&ctl->idle, 1) + 1;
@@ -271,7 +278,6 @@ k_search(const SearchArgs a) {
         }
         break;
       }
-      const int *src = a.items + (size_t)it * fw;
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       int *dst = stack + (size_t)L * fw;
       for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
@@ -631,9 +637,16 @@ k_search_lov(const SearchArgs a) {
 
   for (;;) {
     if (level < base) {
+      // next frontier frame of this rank's partition (frames of other ranks are skipped, not copied)
       int it = 0;
-      if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
-      it = __shfl_sync(FULL, it, 0);
+      const int *src = nullptr;
+      for (;;) {
+        if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= ctl->item_count) break;
+        src = a.items + (size_t)it * fw;
+        if (EXPAND || a.part_count <= 1 || (unsigned)__ldcg(&src[7]) % (unsigned)a.part_count == (unsigned)a.part_rank) break;
+      }
       if (it >= ctl->item_count) {
         if (lane == 0) {
           const int n = atomicAdd(&ctl->idle, 1) + 1;
@@ -641,7 +654,6 @@ k_search_lov(const SearchArgs a) {
         }
         break;
       }
-      const int *src = a.items + (size_t)it * fw;
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       frame_in(src, sst + L * sfw);
       level = base = L;

@@ -1,7 +1,7 @@
 #!/bin/bash
 N=${1:-16}
-for lib in build/lib_lov3.so build/lib_lov4.so build/lib_lov5.so; do
-  for split in 0 200000 1000000; do
-    SPLIT=$split CSOLVE_B200_LIB=$PWD/$lib python scripts/profile_target.py $N 2>&1 | sed "s|^|$lib split=$split |" | cut -c1-60,150-
+for split in 0 1000000 3000000 8000000; do
+  for rep in 1 2; do
+    SPLIT=$split python scripts/profile_target.py $N 2>&1 | sed "s|^|split=$split |" | cut -c1-40,120-
   done
 done
