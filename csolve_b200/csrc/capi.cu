@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -41,6 +42,31 @@ int fail(int code, const std::string &msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
     }                                                                                   \
   } while (0)
+
+// Workspace blocks (stacks, frontier pools) are recycled across problems of one process: a fresh
+// cudaMalloc/cudaFree of hundreds of MB per solve would dominate the end-to-end time of short searches.
+struct WsBlock { void *p; size_t bytes; };
+std::vector<WsBlock> g_ws_free;
+
+cudaError_t ws_alloc(void **out, size_t bytes) {
+  for (size_t i = 0; i < g_ws_free.size(); i++) {
+    if (g_ws_free[i].bytes >= bytes && g_ws_free[i].bytes <= bytes + bytes / 4 + 4096) {
+      *out = g_ws_free[i].p;
+      g_ws_free.erase(g_ws_free.begin() + i);
+      return cudaSuccess;
+    }
+  }
+  return cudaMalloc(out, bytes);
+}
+void ws_free(void *p, size_t bytes) {
+  if (p == nullptr) return;
+  if (g_ws_free.size() >= 16) { cudaFree(g_ws_free.front().p); g_ws_free.erase(g_ws_free.begin()); }
+  g_ws_free.push_back(WsBlock{p, bytes});
+}
+void ws_release_all() {
+  for (auto &b : g_ws_free) cudaFree(b.p);
+  g_ws_free.clear();
+}
 
 template <class T>
 int upload(const std::vector<T> &h, const T **d) {
@@ -83,6 +109,7 @@ struct csolve_gpu_problem {
   // search workspace (allocated on first solve)
   int grid = 0, n_warps = 0;
   int32_t *stacks = nullptr;
+  size_t stacks_bytes = 0, pool_bytes = 0;
   WarpState *wstate = nullptr;
   unsigned long long *wcount = nullptr;
   unsigned long long *totals = nullptr;
@@ -98,8 +125,8 @@ struct csolve_gpu_problem {
 
   ~csolve_gpu_problem() {
     for (void *p : allocs) cudaFree(p);
-    cudaFree(stacks); cudaFree(wstate); cudaFree(wcount); cudaFree(totals); cudaFree(ctl);
-    cudaFree(pool_a); cudaFree(pool_b); cudaFree(scratch); cudaFree(solbuf);
+    ws_free(stacks, stacks_bytes); cudaFree(wstate); cudaFree(wcount); cudaFree(totals); cudaFree(ctl);
+    ws_free(pool_a, pool_bytes); ws_free(pool_b, pool_bytes); cudaFree(scratch); cudaFree(solbuf);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -123,7 +150,10 @@ extern "C" int csolve_gpu_init(const csolve_gpu_config *cfg) {
   return CSOLVE_OK;
 }
 
-extern "C" void csolve_gpu_shutdown(void) { g_device = -1; }
+extern "C" void csolve_gpu_shutdown(void) {
+  ws_release_all();
+  g_device = -1;
+}
 
 extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **out) {
   if (m == nullptr || out == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
@@ -202,7 +232,8 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
     p->grid = per_sm * g_sm_count;
     p->n_warps = p->grid * WARPS_PER_BLOCK;
     const size_t stack_words = (size_t)p->n_warps * (m.n_vars + 1) * m.frame_words;
-    CUDA_TRY(cudaMalloc(&p->stacks, stack_words * sizeof(int32_t)));
+    p->stacks_bytes = stack_words * sizeof(int32_t);
+    CUDA_TRY(ws_alloc((void **)&p->stacks, p->stacks_bytes));
     CUDA_TRY(cudaMalloc(&p->wstate, (size_t)p->n_warps * sizeof(WarpState)));
     CUDA_TRY(cudaMalloc(&p->wcount, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&p->totals, CNT_WIDTH * sizeof(unsigned long long)));
@@ -210,14 +241,15 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
     CUDA_TRY(cudaMalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
-  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 64;
-  int cap = std::max(target * 16, 1 << 16);
+  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 128;
+  int cap = std::max(target * 4, 1 << 16);
   const size_t max_bytes = (size_t)2 << 30;   // per pool
   while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
   if (cap > p->pool_cap) {
-    cudaFree(p->pool_a); cudaFree(p->pool_b); p->pool_a = p->pool_b = nullptr;
-    CUDA_TRY(cudaMalloc(&p->pool_a, (size_t)cap * m.frame_words * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&p->pool_b, (size_t)cap * m.frame_words * sizeof(int32_t)));
+    ws_free(p->pool_a, p->pool_bytes); ws_free(p->pool_b, p->pool_bytes); p->pool_a = p->pool_b = nullptr;
+    p->pool_bytes = (size_t)cap * m.frame_words * sizeof(int32_t);
+    CUDA_TRY(ws_alloc((void **)&p->pool_a, p->pool_bytes));
+    CUDA_TRY(ws_alloc((void **)&p->pool_b, p->pool_bytes));
     p->pool_cap = cap;
   }
   int sol_cap = std::max(opt.max_solutions, m.obj_var >= 0 ? 4096 : (m.objective == CSOLVE_OBJ_ANY ? 1 : 0));
@@ -283,7 +315,7 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   uint64_t launches = 0;
 
   // ---- batched frontier expansion -------------------------------------------------------------------
-  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 64;
+  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 128;
   long long max_branch = 1;
   for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
   max_branch = std::min<long long>(max_branch, a.expand_branch_max);
@@ -303,6 +335,7 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
     CUDA_TRY(cudaStreamSynchronize(st));
     if (ctl.out_dropped > 0) return fail(CSOLVE_ERR_CAPACITY, "frontier pool overflow during expansion");
     n_items = ctl.out_count;
+    if (getenv("CSOLVE_DEBUG")) fprintf(stderr, "[csolve] expand level %d -> %d frames (target %d, pool %d, branch %lld)\n", lvl, n_items, target, p->pool_cap, max_branch);
     std::swap(pin, pout);
     if (ctl.signal == SIG_STOP) { stopped = true; break; }
     // frames with huge domains are passed through unsplit; when nothing else is left the
