@@ -110,6 +110,7 @@ struct csolve_gpu_problem {
   int grid = 0, n_warps = 0;
   int32_t *stacks = nullptr;
   size_t stacks_bytes = 0, pool_bytes = 0;
+  int ws_lov = -1;
   WarpState *wstate = nullptr;
   unsigned long long *wcount = nullptr;
   unsigned long long *totals = nullptr;
@@ -224,9 +225,16 @@ extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes
 // ---- search ------------------------------------------------------------------------------------
 namespace {
 
-int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
-  const DevModel &m = p->dev;
+int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots) {
+  DevModel m = p->dev;
+  if (batch) m.lov = 0;
+  if (p->stacks != nullptr && p->ws_lov != m.lov) {
+    // the lane-owns-variable and the general kernels have different occupancies: rebuild the per-warp state
+    ws_free(p->stacks, p->stacks_bytes); cudaFree(p->wstate); cudaFree(p->wcount); cudaFree(p->totals); cudaFree(p->ctl); cudaFree(p->scratch);
+    p->stacks = nullptr; p->wstate = nullptr; p->wcount = nullptr; p->totals = nullptr; p->ctl = nullptr; p->scratch = nullptr;
+  }
   if (p->stacks == nullptr) {
+    p->ws_lov = m.lov;
     int per_sm = search_blocks_per_sm(m, false);
     if (per_sm <= 0) return fail(CSOLVE_ERR_CUDA, "search kernel does not fit on the device (shared memory per node too large)");
     p->grid = per_sm * g_sm_count;
@@ -242,6 +250,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
   int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 128;
+  target = std::max(target, n_roots);
   int cap = std::max(target * 4, 1 << 16);
   const size_t max_bytes = (size_t)2 << 30;   // per pool
   while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
@@ -263,7 +272,10 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt) {
 
 }  // namespace
 
-extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve_gpu_result *res) {
+namespace {
+// n_roots == 0: the model's own root. n_roots > 0: batched roots over the shared network (ALL models).
+int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve_gpu_result *res, int n_roots,
+               const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed) {
   if (p == nullptr || res == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
   csolve_solve_options opt;
   memset(&opt, 0, sizeof(opt));
@@ -272,10 +284,13 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   if (opt.part_rank < 0 || opt.part_rank >= opt.part_count) return fail(CSOLVE_ERR_INVALID, "part_rank out of range");
   if (opt.order < CSOLVE_ORDER_NONE || opt.order > CSOLVE_ORDER_LARGEST_VALUE) return fail(CSOLVE_ERR_INVALID, "invalid ordering strategy");
   memset(res, 0, sizeof(*res));
-  int rc = ensure_workspace(p, opt);
+  const bool batch = n_roots > 0;
+  if (batch && p->dev.objective != CSOLVE_OBJ_ALL) return fail(CSOLVE_ERR_UNSUPPORTED, "batched roots need an ALL model");
+  int rc = ensure_workspace(p, opt, batch, n_roots);
   if (rc != CSOLVE_OK) return rc;
 
-  const DevModel &m = p->dev;
+  DevModel m = p->dev;
+  if (batch) m.lov = 0;            // batched roots run on the general kernels
   const CompiledModel &cm = p->cm;
   const int V = m.n_vars, fw = m.frame_words;
   cudaStream_t st = p->stream;
@@ -289,16 +304,34 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   std::vector<WarpState> ws(p->n_warps, WarpState{-1, 0});
   CUDA_TRY(cudaMemcpyAsync(p->wstate, ws.data(), ws.size() * sizeof(WarpState), cudaMemcpyHostToDevice, st));
 
-  // root frame
-  std::vector<int32_t> root(fw, 0);
-  const int rv = select_root_var(cm, opt.order);
-  root[FR_VAR] = rv; root[FR_ITER] = 0;
-  root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
-  root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
-  root[FR_LEVEL] = 0; root[FR_BEST] = ctl.best; root[7] = 0x1234567;
-  memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
-  CUDA_TRY(cudaMemcpyAsync(p->pool_a, root.data(), fw * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  ctl.item_count = 1;
+  int32_t *d_roots = nullptr; unsigned char *d_rfail = nullptr; unsigned int *d_rsol = nullptr; int32_t *d_nout = nullptr;
+  auto free_batch = [&]() { cudaFree(d_roots); cudaFree(d_rfail); cudaFree(d_rsol); cudaFree(d_nout); };
+  if (!batch) {
+    // root frame
+    std::vector<int32_t> root(fw, 0);
+    const int rv = select_root_var(cm, opt.order);
+    root[FR_VAR] = rv; root[FR_ITER] = 0;
+    root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
+    root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
+    root[FR_LEVEL] = 0; root[FR_BEST] = ctl.best; root[7] = 0x1234567;
+    memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
+    CUDA_TRY(cudaMemcpyAsync(p->pool_a, root.data(), fw * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    ctl.item_count = 1;
+  } else {
+    // root phase on the device: propagate every root to fixpoint, emit one tagged frame per consistent root
+    const size_t rb = (size_t)n_roots * 2 * V * sizeof(int32_t);
+    CUDA_TRY(cudaMalloc(&d_roots, rb)); CUDA_TRY(cudaMalloc(&d_rfail, n_roots));
+    CUDA_TRY(cudaMalloc(&d_rsol, (size_t)n_roots * sizeof(unsigned int))); CUDA_TRY(cudaMalloc(&d_nout, sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(d_roots, root_dom, rb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_rsol, 0, (size_t)n_roots * sizeof(unsigned int), st));
+    CUDA_TRY(cudaMemsetAsync(d_nout, 0, sizeof(int32_t), st));
+    const int grid = std::min(p->grid, (n_roots + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    CUDA_TRY(launch_root_frames(m, n_roots, d_roots, opt.order, p->pool_a, d_nout, d_rfail, grid, st));
+    int32_t n_ok = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_ok, d_nout, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ctl.item_count = n_ok;
+  }
   CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
 
   SearchArgs a;
@@ -306,13 +339,13 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   a.m = m; a.ctl = p->ctl; a.stacks = p->stacks; a.wstate = p->wstate; a.wcount = p->wcount;
   a.solbuf = p->solbuf; a.max_solutions = p->sol_cap; a.n_warps = p->n_warps; a.order = opt.order;
   a.out_cap = p->pool_cap; a.expand_branch_max = 64;
+  a.inst_solutions = d_rsol;
   const int slice_ms = opt.slice_ms > 0 ? opt.slice_ms : 20;
   a.slice_cycles = (long long)g_clock_khz * slice_ms;
 
   cudaEvent_t ev0, ev1, ev2;
   CUDA_TRY(cudaEventCreate(&ev0)); CUDA_TRY(cudaEventCreate(&ev1)); CUDA_TRY(cudaEventCreate(&ev2));
   CUDA_TRY(cudaEventRecord(ev0, st));
-  uint64_t launches = 0;
 
   // ---- batched frontier expansion -------------------------------------------------------------------
   const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 128;
@@ -320,7 +353,8 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
   max_branch = std::min<long long>(max_branch, a.expand_branch_max);
   int32_t *pin = p->pool_a, *pout = p->pool_b;
-  int n_items = 1;
+  int n_items = ctl.item_count;
+  uint64_t launches = batch ? 1 : 0;
   bool stopped = false;
   for (int lvl = 0; lvl < V && n_items > 0 && n_items < target; ++lvl) {
     // would another level overflow the pool? domains only shrink, so a frame has at most as many
@@ -416,6 +450,11 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   cudaEventElapsedTime(&ms_search, ev1, ev2);
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
 
+  if (batch) {
+    if (root_solutions) CUDA_TRY(cudaMemcpy(root_solutions, d_rsol, (size_t)n_roots * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (root_failed) CUDA_TRY(cudaMemcpy(root_failed, d_rfail, n_roots, cudaMemcpyDeviceToHost));
+    free_batch();
+  }
   res->solutions = tot[CNT_SOLUTIONS];
   res->nodes = tot[CNT_NODES];
   res->cuts = tot[CNT_CUTS];
@@ -429,6 +468,25 @@ extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_option
   res->expand_ms = ms_expand;
   res->kernel_launches = launches;
   (void)slices;
+  return CSOLVE_OK;
+}
+
+}  // namespace
+
+extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt, csolve_gpu_result *res) {
+  return solve_impl(p, opt, res, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_options *opt, int32_t n_roots,
+                                      const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed,
+                                      csolve_gpu_result *res) {
+  if (n_roots <= 0 || root_dom == nullptr) return fail(CSOLVE_ERR_INVALID, "bad arguments");
+  return solve_impl(p, opt, res, n_roots, root_dom, root_solutions, root_failed);
+}
+
+extern "C" int csolve_gpu_get_solution_key(csolve_gpu_problem *p, int32_t i, int32_t *key) {
+  if (p == nullptr || key == nullptr || i < 0 || i >= p->n_stored) return fail(CSOLVE_ERR_INVALID, "solution index out of range");
+  *key = p->sol_host[(size_t)i * (p->dev.n_vars + 1) + p->dev.n_vars];
   return CSOLVE_OK;
 }
 

@@ -205,7 +205,7 @@ __device__ __forceinline__ void write_child_frame(const DevModel &m, const WarpS
   }
   for (int w = lane; w < m.mask_words; w += 32) {
     unsigned mk = s.amask[w];
-    if ((parent_var >> 5) == w) mk |= 1u << (parent_var & 31);
+    if (parent_var >= 0 && (parent_var >> 5) == w) mk |= 1u << (parent_var & 31);
     __stcg(&g[FR_MASK + w], (int)mk);
   }
   store_domains(m, g, s.d, lane);
@@ -420,7 +420,14 @@ k_search(const SearchArgs a) {
           old = __shfl_sync(FULL, old, 0);
           accepted = old != SIG_STOP;     // first finder wins (found_any(), src/csolve.c:207-209)
         }
-        if (accepted) { sols++; store_solution(a, s, lane, key); }
+        if (accepted) {
+          sols++;
+          if (a.inst_solutions != nullptr) {       // batched roots: header word 6 carries the root id
+            key = fbest;
+            if (lane == 0) atomicAdd(&a.inst_solutions[fbest], 1u);
+          }
+          store_solution(a, s, lane, key);
+        }
       }
     } else {
       const int nv = warp_select_var(m, s, lane, a.order, flevel + 1, var);
@@ -430,7 +437,7 @@ k_search(const SearchArgs a) {
         if (lane == 0) slot = atomicAdd(&ctl->out_count, 1);
         slot = __shfl_sync(FULL, slot, 0);
         if (slot < a.out_cap) {
-          write_child_frame(m, s, a.items_out + (size_t)slot * fw, lane, nv, flevel + 1, best, chash, var);
+          write_child_frame(m, s, a.items_out + (size_t)slot * fw, lane, nv, flevel + 1, optimise ? best : fbest, chash, var);
         } else if (lane == 0) {
           atomicAdd(&ctl->out_dropped, 1);
         }
@@ -438,13 +445,13 @@ k_search(const SearchArgs a) {
         // push: the current frame's iteration state goes to HBM (it is reloaded on backtrack), the
         // child frame is written for rebalancing/parking and becomes the register/shared-resident top
         if (lane == 0) __stcg(&f[FR_ITER], (int)iter);
-        write_child_frame(m, s, stack + (size_t)(level + 1) * fw, lane, nv, flevel + 1, best, chash, var);
+        write_child_frame(m, s, stack + (size_t)(level + 1) * fw, lane, nv, flevel + 1, optimise ? best : fbest, chash, var);
         if (lane == 0) s.amask[var >> 5] |= 1u << (var & 31);
         for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.p)[v] = reinterpret_cast<const int2 *>(s.d)[v];
         __syncwarp();
         lo = s.p[2 * nv]; hi = s.p[2 * nv + 1];
         var = nv; iter = 0; last = (unsigned)hi - (unsigned)lo;
-        flevel = flevel + 1; fbest = best; fhash = chash;
+        flevel = flevel + 1; fbest = optimise ? best : fbest; fhash = chash;
         level++;
       }
       __syncwarp();
@@ -993,6 +1000,45 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
   }
 }
 
+// ---- batched roots: root phase on the device -----------------------------------------------------------
+// Root r = a full domain vector over the shared network (e.g. one sudoku: the clue cells are single values).
+// The warp propagates EVERY variable's watchers to fixpoint (what the reference's root sweeps do,
+// src/propagate.c:474-485) and, if the root is consistent, emits its level-0 frame tagged with r.
+__global__ void __launch_bounds__(THREADS_PER_BLOCK)
+k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out, int32_t *n_out,
+              unsigned char *root_failed) {
+  extern __shared__ __align__(16) int smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int4 *wrec; const int *wptr;
+  stage_table(m, smem, wrec, wptr);
+  const int wwords = (warp_smem_words(m) + 3) & ~3;
+  WarpSmem s = carve(m, smem + (m.table_smem_bytes >> 2) + wib * wwords);
+  const int V = m.n_vars, fw = m.frame_words;
+  const int n_warps = gridDim.x * WARPS_PER_BLOCK;
+  for (int r = blockIdx.x * WARPS_PER_BLOCK + wib; r < n_roots; r += n_warps) {
+    const int2 *src = reinterpret_cast<const int2 *>(root_dom + (size_t)r * 2 * V);
+    for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.d)[v] = __ldg(&src[v]);
+    for (int w = lane; w < m.mask_words; w += 32) {
+      const int rem = V - (w << 5);
+      s.cur[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+      s.nxt[w] = 0; s.amask[w] = 0;
+    }
+    __syncwarp();
+    unsigned props = 0, visits = 0;
+    const bool ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
+    if (lane == 0) root_failed[r] = ok ? 0 : 1;
+    if (ok) {
+      int nv = warp_select_var(m, s, lane, order, 0, -1);
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(n_out, 1);
+      slot = __shfl_sync(FULL, slot, 0);
+      // header word 6 = root id; the path hash starts from the root id so partitions spread the roots
+      write_child_frame(m, s, frames_out + (size_t)slot * fw, lane, nv, 0, r, mix_hash(0x1234567u, (unsigned)r, 0u), -1);
+    }
+    __syncwarp();
+  }
+}
+
 // ---- host-side launch wrappers -----------------------------------------------------------------------
 size_t search_smem_bytes(const DevModel &m) {
   if (m.lov) return (size_t)m.lov_smem_bytes + (size_t)WARPS_PER_BLOCK * m.n_vars * ((8 + 3 * m.n_vars + 3) & ~3) * sizeof(int);
@@ -1044,6 +1090,17 @@ cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream
     if (e != cudaSuccess) return e;
     k_search<false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
+                               int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t st) {
+  DevModel m = m_in;
+  m.lov = 0;                                  // the batched path runs on the general kernels
+  const size_t smem = search_smem_bytes(m);
+  cudaError_t e = ensure_smem((const void *)k_root_frames, smem);
+  if (e != cudaSuccess) return e;
+  k_root_frames<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_roots, root_dom, order, frames_out, n_out, root_failed);
   return cudaGetLastError();
 }
 

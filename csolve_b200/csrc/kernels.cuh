@@ -55,6 +55,7 @@ struct SearchArgs {
   int32_t frozen_best;        // expand mode: incumbent every node of this level is propagated against
   long long slice_cycles;     // clock64() budget of one slice
   int32_t expand_branch_max;  // expand mode: frames with more values than this are passed through unsplit
+  unsigned int *inst_solutions; // batched roots: per-root solution counters (else nullptr); the root id travels in header word 6
   int32_t part_rank;          // this process searches the frontier frames whose path hash % part_count == part_rank
   int32_t part_count;
 };
@@ -67,5 +68,7 @@ cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t s);
 int search_blocks_per_sm(const DevModel &m, bool expand);
+cudaError_t launch_root_frames(const DevModel &m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
+                               int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t s);
 
 }  // namespace csolve_dev

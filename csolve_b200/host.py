@@ -116,6 +116,9 @@ def library():
     lib.csolve_gpu_propagate_batch.argtypes = [C.c_void_p, C.c_int32, I32P, I32P, I32P, I32P, I32P, U8P]
     lib.csolve_gpu_solve.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.POINTER(_GpuResult)]
     lib.csolve_gpu_get_solution.argtypes = [C.c_void_p, C.c_int32, I32P]
+    lib.csolve_gpu_get_solution_key.argtypes = [C.c_void_p, C.c_int32, I32P]
+    lib.csolve_gpu_solve_batch.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.c_int32, I32P,
+                                           C.POINTER(C.c_uint32), U8P, C.POINTER(_GpuResult)]
     lib.csolve_last_error.restype = C.c_char_p
     _lib = lib
     return lib
@@ -228,6 +231,32 @@ class GpuProblem:
             _check(library().csolve_gpu_get_solution(self._h, i, buf))
             sols.append(list(buf))
         return SolveResult(res, sols)
+
+    def solve_batch(self, root_domains, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0,
+                    max_solutions=0, time_limit_ms=0, slice_ms=0):
+        """Search many roots that share this model's network. root_domains: [R, 2*V] int32.
+        Returns (SolveResult, per-root solution counts [R], per-root infeasible-at-root flags [R]);
+        SolveResult.assignments are (root id, values) pairs."""
+        I32P, U8P = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        if isinstance(order, str):
+            order = ORDER_NAMES[order]
+        roots = np.ascontiguousarray(root_domains, np.int32).reshape(-1, 2 * self.n_vars)
+        n = roots.shape[0]
+        counts = np.zeros(n, np.uint32)
+        failed = np.zeros(n, np.uint8)
+        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms, 0)
+        res = _GpuResult()
+        _check(library().csolve_gpu_solve_batch(self._h, C.byref(opt), n, roots.ctypes.data_as(I32P),
+                                                counts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                failed.ctypes.data_as(U8P), C.byref(res)))
+        sols = []
+        buf = (C.c_int32 * self.n_vars)()
+        key = C.c_int32()
+        for i in range(res.n_stored):
+            _check(library().csolve_gpu_get_solution(self._h, i, buf))
+            _check(library().csolve_gpu_get_solution_key(self._h, i, C.byref(key)))
+            sols.append((key.value, list(buf)))
+        return SolveResult(res, sols), counts, failed
 
     def close(self):
         if getattr(self, "_h", None):

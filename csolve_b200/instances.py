@@ -72,6 +72,24 @@ def sudoku(grid, objective="ALL"):
     return "\n".join(lines) + "\n"
 
 
+def sudoku_roots(model_var_names, grids):
+    """Root domain vectors [len(grids), 2 * 81] for the clue-free model sudoku('.' * 81): clue cells are
+    single values, the others [1, 9]."""
+    import numpy as np
+    index = {n: k for k, n in enumerate(model_var_names)}
+    out = np.empty((len(grids), 2 * len(model_var_names)), np.int32)
+    out[:, 0::2] = 1
+    out[:, 1::2] = 9
+    for g, grid in enumerate(grids):
+        for r in range(9):
+            for c in range(9):
+                ch = grid[r * 9 + c]
+                if ch not in ".0":
+                    k = index[_cell(r, c)]
+                    out[g, 2 * k] = out[g, 2 * k + 1] = int(ch)
+    return out
+
+
 def _count_solutions(grid, limit=2):
     """tiny bitmask backtracker used only to keep generated puzzles unique (generator, not solver path)"""
     rows, cols, boxes = [0] * 9, [0] * 9, [0] * 9

@@ -168,6 +168,20 @@ int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes,
 /* Replacement for solve(): whole search on the device. */
 int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt, csolve_gpu_result *res);
 
+/* Batched roots (BASELINE config 2: many instances that share one constraint network and differ only in
+ * their root domains, e.g. 10 000 sudokus = the 27 all_different groups + per-instance clue domains).
+ * root_dom: n_roots x (2 * n_vars) lo,hi pairs (HOST). The root phase (propagation of every variable's
+ * clauses to fixpoint, what src/propagate.c:474-485 does once per process) runs on the device for all
+ * roots at once, then all roots are searched together. Requires an ALL model.
+ * root_solutions[r] = number of solutions of root r; root_failed[r] = 1 if root r is infeasible at root
+ * ("INFEASIBLE PROBLEM"). Stored assignments carry the root id as their key. */
+int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_options *opt, int32_t n_roots,
+                           const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed,
+                           csolve_gpu_result *res);
+
+/* key of stored assignment i: MIN/MAX objective value, or the root id for batched roots */
+int csolve_gpu_get_solution_key(csolve_gpu_problem *p, int32_t i, int32_t *key);
+
 /* copy stored assignment i (n_vars values, variable order of the model) */
 int csolve_gpu_get_solution(csolve_gpu_problem *p, int32_t i, int32_t *values);
 

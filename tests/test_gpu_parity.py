@@ -261,6 +261,40 @@ def test_batched_sudoku_instances():
                     assert sol[I._cell(rr, cc)] == int(g[rr * 9 + cc])
 
 
+def test_batched_roots_share_one_network():
+    """config 2: many sudokus over ONE resident network, root phase and search batched on the device"""
+    grids = I.sudoku_batch(200, seed=20261018)
+    grids.append("11" + "." * 79)                       # infeasible at root: two 1s in the first row
+    grids.append(I.SUDOKU_EXAMPLE)
+    m = cb.Model(I.sudoku("." * 81))
+    p = cb.GpuProblem(m)
+    roots = I.sudoku_roots(m.var_names, grids)
+    r, counts, failed = p.solve_batch(roots, order=cb.ORDER_SMALLEST_DOMAIN, max_solutions=len(grids) + 8)
+    assert failed.tolist() == [0] * 200 + [1, 0]
+    assert counts.tolist() == [1] * 200 + [0, 1]
+    assert r.solutions == 201
+    names = m.var_names
+    seen = set()
+    for rid, vals in r.assignments:
+        sol = dict(zip(names, vals))
+        g = grids[rid]
+        for rr in range(9):
+            for cc in range(9):
+                if g[rr * 9 + cc] != ".":
+                    assert sol[I._cell(rr, cc)] == int(g[rr * 9 + cc])
+        assert util.Oracle(m).leaf_true(np.repeat(np.array(vals, np.int32), 2))
+        seen.add(rid)
+    assert len(seen) == 201
+    # the example's unique solution equals what the reference prints for examples/sudoku.txt
+    printed = dict(kv.split(" = ") for kv in COUNTS["sudoku"]["nocf"]["last_solution"].split(", "))
+    ex = [vals for rid, vals in r.assignments if rid == 201][0]
+    assert [int(printed[n]) for n in names] == ex
+    # per-root counters equal independent per-instance searches (oracle on the per-instance model)
+    for g in grids[:5]:
+        o, _ = util.Oracle(cb.Model(I.sudoku(g))).solve_tree(cb.ORDER_SMALLEST_DOMAIN)
+        assert o.solutions == 1
+
+
 def test_queens_full_size_counts():
     """BASELINE config 3 sizes; counts from OEIS A000170 (== the reference CLI's)"""
     for n, cnt in ((12, 14200), (13, 73712), (14, 365596)):
