@@ -340,6 +340,12 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   a.solbuf = p->solbuf; a.max_solutions = p->sol_cap; a.n_warps = p->n_warps; a.order = opt.order;
   a.out_cap = p->pool_cap; a.expand_branch_max = 64;
   a.inst_solutions = d_rsol;
+  int32_t *d_gprio = nullptr;
+  if (opt.prefer_failing && !m.lov) {
+    // device-wide dynamic priorities, seeded with the parse-time weights (env_t.prio)
+    CUDA_TRY(cudaMalloc(&d_gprio, (size_t)V * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(d_gprio, cm.prio.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
   const int slice_ms = opt.slice_ms > 0 ? opt.slice_ms : 20;
   a.slice_cycles = (long long)g_clock_khz * slice_ms;
 
@@ -391,6 +397,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
 
   // ---- time-sliced persistent search -----------------------------------------------------------------------
   a.items = pin; a.items_out = nullptr;
+  a.gprio = d_gprio;     // the breadth-first expansion above stays deterministic (identical on every rank)
   ctl.item_next = 0; ctl.item_count = n_items; ctl.idle = 0; ctl.busy = 0;
   ctl.signal = stopped ? SIG_STOP : SIG_RUN;
   CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
@@ -450,6 +457,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   cudaEventElapsedTime(&ms_search, ev1, ev2);
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
 
+  cudaFree(d_gprio);
   if (batch) {
     if (root_solutions) CUDA_TRY(cudaMemcpy(root_solutions, d_rsol, (size_t)n_roots * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     if (root_failed) CUDA_TRY(cudaMemcpy(root_failed, d_rfail, n_roots, cudaMemcpyDeviceToHost));

@@ -82,10 +82,11 @@ __device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
 // wrec / wptr: the compiled watch records (shared memory when the table was staged, else global).
 // returns false when the node failed (PROP_ERROR).
 __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, const int4 *wrec, const int *wptr,
-                                              int lane, unsigned &props, unsigned &visits) {
+                                              int lane, unsigned &props, unsigned &visits, int *gprio = nullptr) {
   WarpCx cx;
   cx.d = s.d; cx.props = 0;
   bool failed = false;
+  int fail_var = -1;
   for (;;) {
     cx.nxt = s.nxt;
     bool any = false;
@@ -103,13 +104,18 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
         for (int i = b + lane; i < e; i += 32) {
           const int4 q = wrec[i];
           WatchRec rec; rec.w0 = (uint32_t)q.x; rec.c[0] = q.y; rec.c[1] = q.z; rec.c[2] = q.w;
-          if (!contract_watch(cx, m, x, X, rec)) failed = true;
+          if (!contract_watch(cx, m, x, X, rec)) { failed = true; fail_var = x; }
           visits++;
         }
       }
     }
     __syncwarp();
-    if (__any_sync(FULL, failed)) { props += cx.props; return false; }
+    if (__any_sync(FULL, failed)) {
+      // prefer-failing: the variable whose clauses failed gains priority (propagate_term_recurse, src/propagate.c:44-54)
+      if (gprio != nullptr && fail_var >= 0) atomicAdd(&gprio[fail_var], 1);
+      props += cx.props;
+      return false;
+    }
     if (!any) break;
     // next round: cur <- nxt, nxt <- 0
     unsigned *t = s.cur; s.cur = s.nxt; s.nxt = t;
@@ -150,8 +156,9 @@ __device__ bool warp_all_true(const DevModel &m, WarpSmem &s, int lane) {
 // ---- branching variable for the next level (src/strategy.c:79-121) -----------------------------
 // ORDER_NONE is static (priority order); the other orders look at the node's domains.
 // Ties: higher parse-time priority, then lower index.
-__device__ int warp_select_var(const DevModel &m, const WarpSmem &s, int lane, int order, int next_level, int cur_var) {
-  if (order == CSOLVE_ORDER_NONE) return __ldg(&m.order[next_level]);
+__device__ int warp_select_var(const DevModel &m, const WarpSmem &s, int lane, int order, int next_level, int cur_var,
+                               const int *gprio = nullptr) {
+  if (order == CSOLVE_ORDER_NONE && gprio == nullptr) return __ldg(&m.order[next_level]);
   unsigned long long bestk = ~0ull;
   int bestv = 0x7fffffff;
   for (int v = lane; v < m.n_vars; v += 32) {
@@ -162,9 +169,11 @@ __device__ int warp_select_var(const DevModel &m, const WarpSmem &s, int lane, i
     case CSOLVE_ORDER_SMALLEST_DOMAIN: primary = (unsigned)hi - (unsigned)lo; break;
     case CSOLVE_ORDER_LARGEST_DOMAIN:  primary = ~((unsigned)hi - (unsigned)lo); break;
     case CSOLVE_ORDER_SMALLEST_VALUE:  primary = (unsigned)lo ^ 0x80000000u; break;
-    default:                           primary = ~((unsigned)hi ^ 0x80000000u); break;
+    case CSOLVE_ORDER_LARGEST_VALUE:   primary = ~((unsigned)hi ^ 0x80000000u); break;
+    default:                           primary = 0; break;      // ORDER_NONE: priority only
     }
-    const unsigned secondary = ~((unsigned)__ldg(&m.prio[v]) ^ 0x80000000u);
+    const int pr = gprio != nullptr ? __ldcg(&gprio[v]) : __ldg(&m.prio[v]);
+    const unsigned secondary = ~((unsigned)pr ^ 0x80000000u);
     const unsigned long long k = ((unsigned long long)primary << 32) | secondary;
     if (k < bestk) { bestk = k; bestv = v; }   // ascending v per lane: first best wins
   }
@@ -392,8 +401,10 @@ k_search(const SearchArgs a) {
     }
     ok = __shfl_sync(FULL, ok, 0);
     __syncwarp();
-    if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
+    if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits, a.gprio);
     nodes++;
+    // prio-- on success, prio++ on failure (src/csolve.c:459-462)
+    if (a.gprio != nullptr && lane == 0) atomicAdd(&a.gprio[var], ok ? -1 : 1);
 
     if (!ok) {
       cuts++;
@@ -430,7 +441,7 @@ k_search(const SearchArgs a) {
         }
       }
     } else {
-      const int nv = warp_select_var(m, s, lane, a.order, flevel + 1, var);
+      const int nv = warp_select_var(m, s, lane, a.order, flevel + 1, var, a.gprio);
       const unsigned chash = mix_hash(fhash, (unsigned)var, (unsigned)val);
       if (EXPAND) {
         int slot = 0;

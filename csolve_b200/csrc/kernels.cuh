@@ -55,6 +55,7 @@ struct SearchArgs {
   int32_t frozen_best;        // expand mode: incumbent every node of this level is propagated against
   long long slice_cycles;     // clock64() budget of one slice
   int32_t expand_branch_max;  // expand mode: frames with more values than this are passed through unsplit
+  int32_t *gprio;             // prefer-failing: device-wide dynamic priorities [n_vars] (else nullptr)
   unsigned int *inst_solutions; // batched roots: per-root solution counters (else nullptr); the root id travels in header word 6
   int32_t part_rank;          // this process searches the frontier frames whose path hash % part_count == part_rank
   int32_t part_count;

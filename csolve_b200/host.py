@@ -74,7 +74,7 @@ class _GpuConfig(C.Structure):
 class _SolveOptions(C.Structure):
     _fields_ = [("order", C.c_int32), ("part_rank", C.c_int32), ("part_count", C.c_int32),
                 ("split_target", C.c_int32), ("max_solutions", C.c_int32), ("time_limit_ms", C.c_int32),
-                ("slice_ms", C.c_int32), ("reserved", C.c_int32)]
+                ("slice_ms", C.c_int32), ("prefer_failing", C.c_int32)]
 
 
 class _GpuResult(C.Structure):
@@ -219,10 +219,11 @@ class GpuProblem:
         return out, failed
 
     def solve(self, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0,
-              time_limit_ms=0, slice_ms=0):
+              time_limit_ms=0, slice_ms=0, prefer_failing=False):
         if isinstance(order, str):
             order = ORDER_NAMES[order]
-        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms, 0)
+        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
+                            1 if prefer_failing else 0)
         res = _GpuResult()
         _check(library().csolve_gpu_solve(self._h, C.byref(opt), C.byref(res)))
         sols = []

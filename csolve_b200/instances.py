@@ -173,10 +173,40 @@ def sudoku_puzzle(rng, min_clues=26):
     return "".join(flat)
 
 
-def sudoku_batch(count, seed=20261018, min_clues=26):
-    """`count` unique-solution puzzles as 81-character strings (deterministic in seed)."""
+def _transform(grid, rng):
+    """validity- and uniqueness-preserving symmetry: digit relabelling, band/stack/row/column permutations, transpose"""
+    digits = list("123456789")
+    rng.shuffle(digits)
+
+    def lines():
+        bands = [0, 1, 2]
+        rng.shuffle(bands)
+        out = []
+        for b in bands:
+            rows = [0, 1, 2]
+            rng.shuffle(rows)
+            out += [b * 3 + r for r in rows]
+        return out
+    rp, cp = lines(), lines()
+    g = [[grid[rp[r] * 9 + cp[c]] for c in range(9)] for r in range(9)]
+    if rng.random() < 0.5:
+        g = [list(x) for x in zip(*g)]
+    return "".join(ch if ch == "." else digits[int(ch) - 1] for row in g for ch in row)
+
+
+def sudoku_batch(count, seed=20261018, min_clues=26, base=0):
+    """`count` unique-solution puzzles as 81-character strings (deterministic in seed).
+    base == 0: every puzzle is dug independently (slow: a uniqueness check per removed clue).
+    base > 0 : `base` puzzles are dug, the rest are random symmetry transforms of them (distinct
+               instances, uniqueness preserved) -- how the 10 000-instance batch of config 2 is made."""
     rng = random.Random(seed)
-    return [sudoku_puzzle(rng, min_clues) for _ in range(count)]
+    if base <= 0 or base >= count:
+        return [sudoku_puzzle(rng, min_clues) for _ in range(count)]
+    dug = [sudoku_puzzle(rng, min_clues) for _ in range(base)]
+    out = list(dug)
+    while len(out) < count:
+        out.append(_transform(dug[len(out) % base], rng))
+    return out
 
 
 def schedule():

@@ -134,7 +134,10 @@ typedef struct csolve_solve_options {
   int32_t max_solutions;       /* capacity of the solution buffer (assignments kept for printing); 0 = none */
   int32_t time_limit_ms;       /* -t; 0 = off */
   int32_t slice_ms;            /* length of one persistent-kernel time slice; 0 = default */
-  int32_t reserved;
+  int32_t prefer_failing;      /* -f (src/main.c:63-67): break ordering ties by a failure-driven priority that is
+                                * shared by all warps and updated during the search (src/csolve.c:459-462,
+                                * src/propagate.c:33-54). The tree then depends on timing: ALL counts and optima are
+                                * unchanged, node counters are not reproducible. 0 = static parse-time priorities */
 } csolve_solve_options;
 
 typedef struct csolve_gpu_result {
