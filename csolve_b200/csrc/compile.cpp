@@ -31,6 +31,18 @@ Affine affine_of(const csolve_flat_model &m, int n) {
   return a;
 }
 
+// Is the tree below n a disjunction of literals?  want_true: the subtree must be true.
+//   true:  VAR v -> v ; NOT x -> lits(x, false) ; OR(l, r) -> both
+//   false: VAR v -> !v ; NOT x -> lits(x, true) ; AND(l, r) -> both     (De Morgan form of normal_or, src/normalize.c:257-266)
+bool collect_lits(const csolve_flat_model &m, int n, bool want_true, std::vector<int> &lits) {
+  const int op = m.node_op[n];
+  if (op == CSOLVE_OP_VAR) { lits.push_back((m.node_l[n] << 1) | (want_true ? 0 : 1)); return true; }
+  if (op == CSOLVE_OP_NOT) return collect_lits(m, m.node_l[n], !want_true, lits);
+  if ((op == CSOLVE_OP_OR && want_true) || (op == CSOLVE_OP_AND && !want_true))
+    return collect_lits(m, m.node_l[n], want_true, lits) && collect_lits(m, m.node_r[n], want_true, lits);
+  return false;
+}
+
 // every value involved stays far away from the +-infinity sentinels of src/arith.c
 const int64_t SAFE = (int64_t)1 << 29;
 bool small(int64_t v) { return v > -SAFE && v < SAFE; }
@@ -122,6 +134,20 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
         }
       }
     }
+    if (rec.kind == CK_GENERIC) {
+      // a SAT clause: 2..3 literals over distinct variables whose root domains lie in [0,1]. On such a tree
+      // the reference's OR / AND / NOT contractors (src/propagate.c:289-376) are exactly unit propagation.
+      std::vector<int> lits;
+      if (collect_lits(m, root, true, lits) && lits.size() >= 2 && lits.size() <= 3) {
+        bool good = true;
+        for (size_t i = 0; i < lits.size() && good; i++) {
+          const int v = lits[i] >> 1;
+          if (m.var_lo[v] < 0 || m.var_hi[v] > 1) good = false;
+          for (size_t j = 0; j < i; j++) if ((lits[j] >> 1) == v) good = false;
+        }
+        if (good) rec = ClauseRec{CK_LITS | ((int32_t)lits.size() << 8), lits[0], lits[1], lits.size() > 2 ? lits[2] : 0};
+      }
+    }
     if (rec.kind == CK_GENERIC) n_generic++;
     out.clause[c] = rec;
   }
@@ -136,7 +162,7 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     struct Group { int partner; std::vector<int32_t> offs; };
     std::vector<Group> vv;                 // NE_VV groups in first-seen order
     std::vector<int32_t> consts;           // NE_VC constants
-    std::vector<int32_t> generic;
+    std::vector<int32_t> generic, lit_clauses;
     for (int w = m.watch_ptr[v]; w < m.watch_ptr[v + 1]; w++) {
       const int c = m.watch_idx[w];
       const ClauseRec &rec = out.clause[c];
@@ -150,6 +176,8 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
         if (std::find(g->offs.begin(), g->offs.end(), off) == g->offs.end()) g->offs.push_back(off);
       } else if (rec.kind == CK_NE_VC && rec.a == v) {
         if (std::find(consts.begin(), consts.end(), rec.c) == consts.end()) consts.push_back(rec.c);
+      } else if ((rec.kind & 0xff) == CK_LITS) {
+        lit_clauses.push_back(c);
       } else {
         generic.push_back(c);
       }
@@ -165,6 +193,12 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     };
     for (auto &g : vv) emit(WK_NE_VV, g.partner, g.offs);
     if (!consts.empty()) emit(WK_NE_VC, 0, consts);
+    for (int c : lit_clauses) {
+      const ClauseRec &rec = out.clause[c];
+      WatchRec r; r.c[0] = rec.a; r.c[1] = rec.b; r.c[2] = rec.c;
+      r.w0 = ((uint32_t)WK_LITS << 30) | ((uint32_t)(rec.kind >> 8) << 28) | (uint32_t)c;
+      out.wrec.push_back(r);
+    }
     for (int c : generic) { WatchRec r; r.w0 = (WK_GENERIC << 30) | (1u << 28) | (uint32_t)c; r.c[0] = r.c[1] = r.c[2] = 0; out.wrec.push_back(r); }
   }
   out.wrec_ptr[V] = (int32_t)out.wrec.size();

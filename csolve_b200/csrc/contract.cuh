@@ -331,6 +331,36 @@ CSOLVE_HD bool contract_ne_vc(Cx &cx, int x, int32_t c) {
   return true;
 }
 
+// A disjunction of n <= 3 literals (code = var << 1 | negated) over distinct 0/1 variables. On such a tree
+// the reference's OR-true / AND-false "push to the side whose sibling is neutral" rule
+// (propagate_logic_either, src/propagate.c:320-343) is unit propagation: nothing happens while a literal is
+// true or two are undecided; one undecided literal with all others false is made true; all false fails.
+template <class Cx>
+CSOLVE_HD bool contract_lits(Cx &cx, int n, int32_t l0, int32_t l1, int32_t l2) {
+  int n_false = 0, unk = -1;
+  const int32_t lit[3] = {l0, l1, l2};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 3; k++) {
+    if (k < n) {
+      const Dom D = cx.dom(lit[k] >> 1);
+      if (D.lo == D.hi) {
+        if ((D.lo != 0) != ((lit[k] & 1) != 0)) return true;      // a true literal: the clause holds
+        n_false++;
+      } else {
+        unk = unk < 0 ? lit[k] : -2;                                // -2: more than one undecided
+      }
+    }
+  }
+  if (n_false == n) return false;
+  if (unk >= 0 && n_false == n - 1) {
+    const int32_t val = (unk & 1) ? 0 : 1;
+    return contract_var(cx, unk >> 1, val, val);
+  }
+  return true;
+}
+
 // One watch record of variable `self` (device_model.h): X is the snapshot of self's domain the
 // caller took when it dequeued the variable. NE_VV: the NOT(EQ) clauses between self and one partner;
 // both directions of each clause are contracted from the snapshots, exactly like the false branch
@@ -378,6 +408,7 @@ CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const 
     }
     return ok;
   }
+  if (kind == WK_LITS) return contract_lits(cx, n, rec.c[0], rec.c[1], rec.c[2]);
   return contract_generic(cx, m, m.clause[wrec_arg(rec.w0)].b);
 }
 
@@ -444,6 +475,7 @@ CSOLVE_HD void lov_const_step(int32_t c, int32_t Xlo, int32_t Xhi, bool &plo, bo
 // One clause contraction = propagate VALUE(1) into clause k (src/propagate.c:514-516).
 template <class Cx>
 CSOLVE_HD bool contract_clause(Cx &cx, const DevModel &m, const ClauseRec &rec) {
+  if ((rec.kind & 0xff) == CK_LITS) return contract_lits(cx, rec.kind >> 8, rec.a, rec.b, rec.c);
   switch (rec.kind) {
   case CK_NE_VV: return contract_ne_vv(cx, rec.a, rec.b, rec.c);
   case CK_NE_VC: return contract_ne_vc(cx, rec.a, rec.c);
@@ -454,6 +486,16 @@ CSOLVE_HD bool contract_clause(Cx &cx, const DevModel &m, const ClauseRec &rec) 
 // Leaf test for one clause: is_true(eval(clause)) (src/csolve.c:226, src/eval.c:221-245)
 template <class Cx>
 CSOLVE_HD bool clause_is_true(Cx &cx, const DevModel &m, const ClauseRec &rec) {
+  if ((rec.kind & 0xff) == CK_LITS) {
+    // eval of the OR / NOT(AND) tree is true iff some literal is a true value (src/eval.c:167-219)
+    const int32_t lit[3] = {rec.a, rec.b, rec.c};
+    for (int k = 0; k < (rec.kind >> 8); k++) {
+      const Dom D = cx.dom(lit[k] >> 1);
+      if (D.lo == D.hi && ((D.lo != 0) != ((lit[k] & 1) != 0))) return true;
+      if (D.lo != D.hi && (D.lo > 0 || D.hi < 0) && !(lit[k] & 1)) return true;   // positive literal, 0 excluded
+    }
+    return false;
+  }
   switch (rec.kind) {
   case CK_NE_VV: {
     Dom X = cx.dom(rec.a), Y = cx.dom(rec.b);

@@ -16,10 +16,12 @@ namespace csolve_dev {
 //   kind == CK_GENERIC : a = first node, b = root node (= last node), interpreted
 //   kind == CK_NE_VV   : NOT(EQ(x + ka, y + kb))  ->  a = x, b = y, c = ka - kb   (x + c != y)
 //   kind == CK_NE_VC   : NOT(EQ(x + ka, const))   ->  a = x, c = const - ka       (x != c)
+//   kind == CK_LITS | n << 8 : a disjunction of n <= 3 literals over distinct 0/1 variables (a SAT clause in
+//                        any OR / NOT(AND) nesting); a, b, c = literal codes var << 1 | negated
 // The NE kinds are only emitted when no intermediate value can reach the
 // saturation sentinels (see compile.cpp), so plain int32 arithmetic is bit-exact
 // with the reference's saturating operators (src/arith.c).
-enum ClauseKind : int32_t { CK_GENERIC = 0, CK_NE_VV = 1, CK_NE_VC = 2 };
+enum ClauseKind : int32_t { CK_GENERIC = 0, CK_NE_VV = 1, CK_NE_VC = 2, CK_LITS = 3 };
 
 struct ClauseRec { int32_t kind, a, b, c; };
 
@@ -31,7 +33,8 @@ struct ClauseRec { int32_t kind, a, b, c; };
 //                (all NOT(EQ) clauses between the two variables, oriented from `self`, duplicates
 //                 merged: contracting the same clause twice cannot change the fixpoint)
 //   WK_NE_VC   : for k < n:  self != w[1 + k]
-enum WatchKind : uint32_t { WK_GENERIC = 0, WK_NE_VV = 1, WK_NE_VC = 2 };
+//   WK_LITS    : w[1 + k] = literal codes (var << 1 | negated) of a disjunction of n literals; unit propagation
+enum WatchKind : uint32_t { WK_GENERIC = 0, WK_NE_VV = 1, WK_NE_VC = 2, WK_LITS = 3 };
 struct WatchRec { uint32_t w0; int32_t c[3]; };
 CSOLVE_HOSTDEV static inline uint32_t wrec_kind(uint32_t w0) { return w0 >> 30; }
 CSOLVE_HOSTDEV static inline int wrec_n(uint32_t w0) { return (int)((w0 >> 28) & 3u); }
