@@ -123,6 +123,8 @@ struct csolve_gpu_problem {
   std::vector<int32_t> sol_host;
   int32_t n_stored = 0;
   cudaStream_t stream = nullptr;
+  csolve_exchange_fn exchange = nullptr;
+  void *exchange_user = nullptr;
 
   ~csolve_gpu_problem() {
     for (void *p : allocs) cudaFree(p);
@@ -405,23 +407,43 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   int busy = 0;
   bool timed_out = false;
   uint64_t slices = 0;
-  while (!stopped && n_items > 0) {
-    // ask for the slice to end when an eighth of the warps that have work (or can fetch it) ran dry
-    const int can_work = std::min(p->n_warps, busy + std::max(0, ctl.item_count - ctl.item_next));
-    a.idle_exit = std::min(p->n_warps, (p->n_warps - can_work) + std::max(1, can_work / 8));
-    CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
-    CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
-    CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    slices++;
-    busy = ctl.busy - (ctl.item_next < ctl.item_count ? 1 : 0);
-    idle_now = p->n_warps - busy;
-    if (ctl.signal == SIG_STOP) break;
-    if (ctl.busy == 0) break;
-    if (opt.time_limit_ms > 0) {
-      const auto now = std::chrono::steady_clock::now();
-      if (std::chrono::duration_cast<std::chrono::milliseconds>(now - wall0).count() > opt.time_limit_ms) { timed_out = true; break; }
+  // With an exchange callback (one process per GPU) every rank keeps calling it once per slice until ALL ranks
+  // are done, so the collectives inside it stay matched; a rank that ran dry simply waits there.
+  bool local_done = stopped || n_items == 0;
+  const bool is_min = m.objective == CSOLVE_OBJ_MIN;
+  for (;;) {
+    if (!local_done) {
+      // ask for the slice to end when an eighth of the warps that have work (or can fetch it) ran dry
+      const int can_work = std::min(p->n_warps, busy + std::max(0, ctl.item_count - ctl.item_next));
+      a.idle_exit = std::min(p->n_warps, (p->n_warps - can_work) + std::max(1, can_work / 8));
+      CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
+      CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
+      CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      slices++;
+      busy = ctl.busy - (ctl.item_next < ctl.item_count ? 1 : 0);
+      idle_now = p->n_warps - busy;
+      if (ctl.signal == SIG_STOP || ctl.busy == 0) local_done = true;
+      if (!local_done && opt.time_limit_ms > 0) {
+        const auto now = std::chrono::steady_clock::now();
+        if (std::chrono::duration_cast<std::chrono::milliseconds>(now - wall0).count() > opt.time_limit_ms) { timed_out = true; local_done = true; }
+      }
     }
+    if (p->exchange == nullptr) {
+      if (local_done) break;
+      continue;
+    }
+    // periodic incumbent / first-solution exchange between the ranks (NCCL all-reduce in the callback)
+    int32_t best = ctl.best, found = (m.objective == CSOLVE_OBJ_ANY && ctl.signal == SIG_STOP) ? 1 : 0;
+    const int all_done = p->exchange(p->exchange_user, &best, &found, local_done ? 1 : 0);
+    if (m.obj_var >= 0 && (is_min ? best < ctl.best : best > ctl.best)) {
+      ctl.best = best;     // another rank found a better incumbent: prune with it from the next slice on
+      CUDA_TRY(cudaMemcpyAsync(&p->ctl->best, &ctl.best, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    if (found && m.objective == CSOLVE_OBJ_ANY && !local_done) {
+      local_done = true;   // found_any() on another rank (src/csolve.c:207-209)
+    }
+    if (all_done) break;
   }
   (void)idle_now;
   CUDA_TRY(cudaEventRecord(ev2, st));
@@ -483,6 +505,13 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
 
 extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt, csolve_gpu_result *res) {
   return solve_impl(p, opt, res, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int csolve_gpu_set_exchange(csolve_gpu_problem *p, csolve_exchange_fn fn, void *user) {
+  if (p == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  p->exchange = fn;
+  p->exchange_user = user;
+  return CSOLVE_OK;
 }
 
 extern "C" int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_options *opt, int32_t n_roots,

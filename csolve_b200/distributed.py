@@ -48,9 +48,38 @@ def reduce_results(res, objective, device=None, group=None):
                 kernel_ms=float(times[0].item()), expand_ms=float(times[1].item()), kernel_ms_min=float(-times[2].item()))
 
 
-def solve_partitioned(problem, objective, device=None, group=None, **solve_kw):
-    """Search this rank's share of the tree and reduce. `problem` is a GpuProblem (or anything with .solve)."""
+def make_exchange(objective, device=None, group=None):
+    """The per-slice exchange between ranks: ONE all-reduce of three integers.
+    MIN models reduce with MIN over [best, -found, done]; everything else with MAX over [best, found, -done]
+    (so that `done` is always an AND over the ranks and `found` an OR)."""
+    dev = device if device is not None else torch.device("cpu")
+    is_min = objective == OBJ_MIN
+
+    def exchange(best, found, local_done):
+        if is_min:
+            t = torch.tensor([best, -found, local_done], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            b, f, d = t.tolist()
+            return b, -f, d
+        t = torch.tensor([best, found, -local_done], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        b, f, d = t.tolist()
+        return b, f, -d
+    return exchange
+
+
+def solve_partitioned(problem, objective, device=None, group=None, exchange=None, **solve_kw):
+    """Search this rank's share of the tree and reduce. `problem` is a GpuProblem (or anything with .solve).
+    exchange=True installs the per-slice incumbent / first-solution exchange (MIN, MAX and ANY models)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    res = problem.solve(part_rank=rank, part_count=world, **solve_kw)
+    if exchange is None:
+        exchange = world > 1 and objective in (OBJ_MIN, OBJ_MAX, OBJ_ANY)
+    if exchange and world > 1 and hasattr(problem, "set_exchange"):
+        problem.set_exchange(make_exchange(objective, device=device, group=group))
+    try:
+        res = problem.solve(part_rank=rank, part_count=world, **solve_kw)
+    finally:
+        if exchange and world > 1 and hasattr(problem, "set_exchange"):
+            problem.set_exchange(None)
     return reduce_results(res, objective, device=device, group=group), res

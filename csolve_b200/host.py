@@ -84,6 +84,10 @@ class _GpuResult(C.Structure):
                 ("expand_ms", C.c_double), ("kernel_launches", C.c_uint64)]
 
 
+# int (*csolve_exchange_fn)(void *user, int32_t *best, int32_t *found, int32_t local_done)
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32)
+
+
 def library_path():
     # CSOLVE_B200_LIB: development override to compare builds; the default is the in-tree library
     return os.environ.get("CSOLVE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcsolve_b200.so")
@@ -119,6 +123,7 @@ def library():
     lib.csolve_gpu_get_solution_key.argtypes = [C.c_void_p, C.c_int32, I32P]
     lib.csolve_gpu_solve_batch.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.c_int32, I32P,
                                            C.POINTER(C.c_uint32), U8P, C.POINTER(_GpuResult)]
+    lib.csolve_gpu_set_exchange.argtypes = [C.c_void_p, EXCHANGE_FN, C.c_void_p]
     lib.csolve_last_error.restype = C.c_char_p
     _lib = lib
     return lib
@@ -232,6 +237,22 @@ class GpuProblem:
             _check(library().csolve_gpu_get_solution(self._h, i, buf))
             sols.append(list(buf))
         return SolveResult(res, sols)
+
+    def set_exchange(self, fn):
+        """fn(best, found, local_done) -> (best, found, all_done): called once per time slice (see
+        csolve_gpu_set_exchange in include/csolve_b200.h). Pass None to remove it."""
+        if fn is None:
+            self._exchange_cb = None
+            _check(library().csolve_gpu_set_exchange(self._h, C.cast(None, EXCHANGE_FN), None))
+            return
+
+        def tramp(user, best_p, found_p, local_done):
+            b, f, done = fn(int(best_p[0]), int(found_p[0]), int(local_done))
+            best_p[0] = int(b)
+            found_p[0] = int(f)
+            return 1 if done else 0
+        self._exchange_cb = EXCHANGE_FN(tramp)          # keep the trampoline alive
+        _check(library().csolve_gpu_set_exchange(self._h, self._exchange_cb, None))
 
     def solve_batch(self, root_domains, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0,
                     max_solutions=0, time_limit_ms=0, slice_ms=0):

@@ -171,6 +171,16 @@ int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes,
 /* Replacement for solve(): whole search on the device. */
 int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt, csolve_gpu_result *res);
 
+/* One process per GPU: exchange between the ranks, called on the host once per time slice of
+ * csolve_gpu_solve() until it returns non-zero ("every rank is done"). It replaces the reference's shared page
+ * (struct shared_t: objective_best / solutions, src/csolve.h:259-266):
+ *   *best   in: this rank's incumbent        out: the best incumbent of all ranks (MIN/MAX models)
+ *   *found  in: 1 if this rank has a solution (ANY models)   out: 1 if any rank has one -> this rank stops
+ *   local_done: this rank has no work left (it keeps calling so that the collectives stay matched)
+ * The callback typically wraps one NCCL all-reduce (csolve_b200/distributed.py). */
+typedef int (*csolve_exchange_fn)(void *user, int32_t *best, int32_t *found, int32_t local_done);
+int csolve_gpu_set_exchange(csolve_gpu_problem *p, csolve_exchange_fn fn, void *user);
+
 /* Batched roots (BASELINE config 2: many instances that share one constraint network and differ only in
  * their root domains, e.g. 10 000 sudokus = the 27 all_different groups + per-instance clue domains).
  * root_dom: n_roots x (2 * n_vars) lo,hi pairs (HOST). The root phase (propagation of every variable's

@@ -303,3 +303,29 @@ def test_queens_full_size_counts():
         # mirror symmetry X -> n+1-X: the tree differs, the count cannot
     r = cb.GpuProblem(cb.Model(I.queens(14))).solve(order=cb.ORDER_SMALLEST_DOMAIN)
     assert r.solutions == 365596
+
+
+def test_exchange_callback_injects_incumbent_and_stops_any():
+    """the per-slice exchange hook (multi-GPU incumbent all-reduce), emulated in one process"""
+    m = cb.Model(INST["wcet"])
+    p = cb.GpuProblem(m)
+    base = p.solve(slice_ms=2)
+    calls = []
+
+    def other_rank_has_1559(best, found, local_done):
+        calls.append((best, local_done))
+        return max(best, 1559), found, local_done      # MAX model: another rank already holds 1559
+
+    p.set_exchange(other_rank_has_1559)
+    r = p.solve(slice_ms=2)
+    p.set_exchange(None)
+    assert r.best == 1560 and len(calls) >= 1 and calls[-1][1] == 1
+    # with 1559 known from the first slice on, only 1560 itself can still be accepted as an improvement
+    assert 1 <= r.solutions < base.solutions
+    # ANY: another rank reports a solution -> this rank stops without one
+    m2 = cb.Model(I.random_3sat(200, seed=1))
+    p2 = cb.GpuProblem(m2)
+    p2.set_exchange(lambda best, found, done: (best, 1, 1))
+    r2 = p2.solve(slice_ms=1)
+    p2.set_exchange(None)
+    assert r2.has_solution == 0 and r2.nodes < 21000000
