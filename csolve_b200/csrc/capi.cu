@@ -116,6 +116,7 @@ struct csolve_gpu_problem {
   unsigned long long *totals = nullptr;
   SearchCtl *ctl = nullptr;
   int32_t *pool_a = nullptr, *pool_b = nullptr;
+  int32_t *ready = nullptr;
   int32_t pool_cap = 0;
   int32_t *scratch = nullptr;
   int32_t *solbuf = nullptr;
@@ -129,7 +130,7 @@ struct csolve_gpu_problem {
   ~csolve_gpu_problem() {
     for (void *p : allocs) cudaFree(p);
     ws_free(stacks, stacks_bytes); cudaFree(wstate); cudaFree(wcount); cudaFree(totals); cudaFree(ctl);
-    ws_free(pool_a, pool_bytes); ws_free(pool_b, pool_bytes); cudaFree(scratch); cudaFree(solbuf);
+    ws_free(pool_a, pool_bytes); ws_free(pool_b, pool_bytes); cudaFree(scratch); cudaFree(solbuf); cudaFree(ready);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -261,6 +262,8 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
     p->pool_bytes = (size_t)cap * m.frame_words * sizeof(int32_t);
     CUDA_TRY(ws_alloc((void **)&p->pool_a, p->pool_bytes));
     CUDA_TRY(ws_alloc((void **)&p->pool_b, p->pool_bytes));
+    cudaFree(p->ready); p->ready = nullptr;
+    CUDA_TRY(cudaMalloc(&p->ready, (size_t)cap * sizeof(int32_t)));
     p->pool_cap = cap;
   }
   int sol_cap = std::max(opt.max_solutions, m.obj_var >= 0 ? 4096 : (m.objective == CSOLVE_OBJ_ANY ? 1 : 0));
@@ -363,8 +366,13 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   int32_t *pin = p->pool_a, *pout = p->pool_b;
   int n_items = ctl.item_count;
   uint64_t launches = batch ? 1 : 0;
+  if (batch && n_items >= p->n_warps / 2) n_items = -n_items;   // enough roots: no breadth-first phase at all
   bool stopped = false;
-  for (int lvl = 0; lvl < V && n_items > 0 && n_items < target; ++lvl) {
+  // Breadth-first levels pay off while the frontier multiplies; once there is about one frame per two warps
+  // and a level no longer doubles it (unit-propagation-heavy models, batched roots), or after 24 levels,
+  // the depth-first phase with rebalancing takes over.
+  for (int lvl = 0; lvl < V && lvl < 24 && n_items > 0 && n_items < target; ++lvl) {
+    const int before = n_items;
     // would another level overflow the pool? domains only shrink, so a frame has at most as many
     // children as the largest root domain (and never more than expand_branch_max)
     if ((long long)n_items * max_branch > p->pool_cap) break;
@@ -383,7 +391,9 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     // frames with huge domains are passed through unsplit; when nothing else is left the
     // breadth-first phase cannot make progress and the depth-first phase (which bisects) takes over
     if (ctl.passed == n_items) break;
+    if (n_items >= p->n_warps / 2 && n_items < 2 * (long long)before) break;
   }
+  if (n_items < 0) n_items = -n_items;
   CUDA_TRY(cudaEventRecord(ev1, st));
 
   // ---- partition: every rank holds the whole frontier; the search kernel skips the frames whose path
@@ -399,8 +409,12 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
 
   // ---- time-sliced persistent search -----------------------------------------------------------------------
   a.items = pin; a.items_out = nullptr;
+  // shared pool ring of the depth-first phase: the expanded frontier occupies the first n_items slots
+  a.pool = pin; a.pool_cap = p->pool_cap; a.ready = p->ready; a.n_initial = n_items;
+  CUDA_TRY(cudaMemsetAsync(p->ready, 0, (size_t)p->pool_cap * sizeof(int32_t), st));
+  if (p->pool_cap - n_items < 1024) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
   a.gprio = d_gprio;     // the breadth-first expansion above stays deterministic (identical on every rank)
-  ctl.item_next = 0; ctl.item_count = n_items; ctl.idle = 0; ctl.busy = 0;
+  ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.idle = 0; ctl.busy = 0; ctl.hungry = 0;
   ctl.signal = stopped ? SIG_STOP : SIG_RUN;
   CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
   int idle_now = p->n_warps;          // every warp starts without a stack
@@ -414,14 +428,12 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   for (;;) {
     if (!local_done) {
       // ask for the slice to end when an eighth of the warps that have work (or can fetch it) ran dry
-      const int can_work = std::min(p->n_warps, busy + std::max(0, ctl.item_count - ctl.item_next));
-      a.idle_exit = std::min(p->n_warps, (p->n_warps - can_work) + std::max(1, can_work / 8));
       CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
       CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
       CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       slices++;
-      busy = ctl.busy - (ctl.item_next < ctl.item_count ? 1 : 0);
+      busy = ctl.busy;
       idle_now = p->n_warps - busy;
       if (ctl.signal == SIG_STOP || ctl.busy == 0) local_done = true;
       if (!local_done && opt.time_limit_ms > 0) {

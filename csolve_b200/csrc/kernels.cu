@@ -232,6 +232,80 @@ __device__ __forceinline__ void store_solution(const SearchArgs &a, const WarpSm
   }
 }
 
+
+// ---- shared frame pool (depth-first phase) ---------------------------------------------------------------
+// The frontier pool is a ring: head = ctl->item_next, tail = ctl->item_count, ready[slot] = 1 once a frame is
+// completely written. Idle warps wait here for frames; busy warps donate half of the untried interval of their
+// shallowest splittable frame whenever somebody is waiting (the bisection worker_spawn does with fork(),
+// src/csolve.c:121-149) -- so load balancing does not need the kernel to end.
+// Returns the claimed slot, or -1 when the warp has to leave the kernel (slice end / stop / nothing left anywhere).
+__device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &hungry) {
+  SearchCtl *ctl = a.ctl;
+  const int fw = a.m.frame_words;
+  const int ring = a.pool_cap - a.n_initial;       // donated frames live in the slots behind the root frontier
+  int slot = -1;
+  if (lane == 0) {
+    for (;;) {
+      if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) { slot = -1; break; }
+      // 1. the expanded root frontier: static, claimed with a plain atomicAdd (no contention retries)
+      if (*reinterpret_cast<volatile int *>(&ctl->init_next) < a.n_initial) {
+        const int it = atomicAdd(&ctl->init_next, 1);
+        if (it < a.n_initial) {
+          if (a.part_count > 1 &&
+              (unsigned)__ldcg(&a.pool[(size_t)it * fw + 7]) % (unsigned)a.part_count != (unsigned)a.part_rank) continue;
+          slot = it;
+          break;
+        }
+        continue;
+      }
+      // 2. the ring of donated frames
+      const int h = *reinterpret_cast<volatile int *>(&ctl->item_next);
+      const int t = *reinterpret_cast<volatile int *>(&ctl->item_count);
+      if (t - h > 0) {
+        const int s = a.n_initial + (int)((unsigned)h % (unsigned)ring);
+        if (*reinterpret_cast<volatile int *>(&a.ready[s]) == 1 && atomicCAS(&ctl->item_next, h, h + 1) == h) {
+          slot = s;
+          break;
+        }
+        continue;
+      }
+      if (!hungry) { hungry = true; atomicAdd(&ctl->hungry, 1); }
+      if (*reinterpret_cast<volatile int *>(&ctl->hungry) >= a.n_warps) {
+        atomicMax(&ctl->signal, SIG_SLICE_END);    // every warp is waiting and the pool is empty: nothing left
+        slot = -1;
+        break;
+      }
+      __nanosleep(500);
+    }
+    if (slot >= 0 && hungry) { hungry = false; atomicSub(&ctl->hungry, 1); }
+  }
+  return __shfl_sync(FULL, slot, 0);
+}
+
+// should this warp donate now?  (lane 0 reads the control block; every lane gets the answer)
+__device__ __forceinline__ bool donation_wanted(const SearchArgs &a, int lane) {
+  int want = 0;
+  if (lane == 0) {
+    const int hungry = *reinterpret_cast<volatile int *>(&a.ctl->hungry);
+    if (hungry > 0) {
+      const int backlog = *reinterpret_cast<volatile int *>(&a.ctl->item_count) - *reinterpret_cast<volatile int *>(&a.ctl->item_next);
+      want = backlog < hungry && backlog < (a.pool_cap - a.n_initial) / 2;
+    }
+  }
+  return __shfl_sync(FULL, want, 0) != 0;
+}
+
+// reserve a pool slot for a donated frame (lane 0), wait until its previous tenant has been copied out
+__device__ __forceinline__ int reserve_slot(const SearchArgs &a, int lane) {
+  int s = 0;
+  if (lane == 0) {
+    const int t = atomicAdd(&a.ctl->item_count, 1);
+    s = a.n_initial + (int)((unsigned)t % (unsigned)(a.pool_cap - a.n_initial));
+    while (*reinterpret_cast<volatile int *>(&a.ready[s]) != 0) __nanosleep(100);
+  }
+  return __shfl_sync(FULL, s, 0);
+}
+
 // ---- the search kernel ----------------------------------------------------------------------------
 // Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
 template <bool EXPAND>
@@ -265,31 +339,31 @@ k_search(const SearchArgs a) {
   bool have = false;
   int var = 0, lo = 0, hi = 0, flevel = 0, fbest = 0;
   unsigned iter = 0, last = 0, fhash = 0, poll = 0;
+  bool hungry = false;
 
   for (;;) {
 
     if (level < base) {
-      // out of work: take the next frontier frame, or go idle
-      // next frontier frame of this rank's partition (frames of other ranks are skipped, not copied)
-      int it = 0;
-      const int *src = nullptr;
-      for (;;) {
+      // out of work: take a frame of the frontier / shared pool
+      const int *src;
+      if (EXPAND) {
+        int it = 0;
         if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
         it = __shfl_sync(FULL, it, 0);
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
-        if (EXPAND || a.part_count <= 1 || (unsigned)__ldcg(&src[7]) % (unsigned)a.part_count == (unsigned)a.part_rank) break;
-      }
-      if (it >= ctl->item_count) {
-        if (lane == 0) {
-          const int n = atomicAdd(&ctl->idle, 1) + 1;
-          if (!EXPAND && n >= a.idle_exit) atomicMax(&ctl->signal, SIG_SLICE_END);
-        }
-        break;
+      } else {
+        const int slot = claim_frame(a, lane, hungry);
+        if (slot < 0) break;
+        src = a.pool + (size_t)slot * fw;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       int *dst = stack + (size_t)L * fw;
       for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
+      if (!EXPAND) {
+        __syncwarp();
+        if (lane == 0) { __threadfence(); __stcg(&a.ready[(src - a.pool) / fw], 0); }   // slot may be reused
+      }
       level = base = L;
       have = false;
       __syncwarp();
@@ -469,13 +543,52 @@ k_search(const SearchArgs a) {
     }
 
     // ---- park? ----------------------------------------------------------------------------------
-    // every POLL_NODES nodes: has a slice end / stop been requested, is the time slice over?
-    // (an L2 round trip per node would dominate short nodes)
-    if (!EXPAND && (++poll & (POLL_NODES - 1)) == 0) {
+    // every few nodes: has a slice end / stop been requested, is the time slice over, is somebody waiting for work?
+    // (general-kernel nodes are long, so the control block is polled often; an L2 round trip per node would
+    // dominate the short nodes of the lane-owns-variable kernel, which polls every POLL_NODES nodes)
+    if (!EXPAND && (++poll & 3u) == 0) {
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
+      }
+      if (level >= base && donation_wanted(a, lane)) {
+        // shallowest frame with at least two untried values; the top frame's header is in registers
+        int L = -1;
+        unsigned d_iter = 0; int d_lo = 0, d_hi = 0;
+        if (lane == 0) {
+          for (int q = base; q <= level; ++q) {
+            unsigned it2, la2; int lo2, hi2;
+            if (q == level) { it2 = iter; la2 = last; lo2 = lo; hi2 = hi; }
+            else {
+              const int4 g0 = __ldcg(reinterpret_cast<const int4 *>(stack + (size_t)q * fw));
+              it2 = (unsigned)g0.y; la2 = (unsigned)g0.z; lo2 = g0.w; hi2 = __ldcg(&stack[(size_t)q * fw + FR_HI]);
+            }
+            if (it2 <= la2 && la2 - it2 >= 1) { L = q; d_iter = it2; d_lo = lo2; d_hi = hi2; break; }
+          }
+        }
+        L = __shfl_sync(FULL, L, 0);
+        if (L >= 0) {
+          d_iter = __shfl_sync(FULL, d_iter, 0); d_lo = __shfl_sync(FULL, d_lo, 0); d_hi = __shfl_sync(FULL, d_hi, 0);
+          const long long ua = (long long)d_lo + ((d_iter + 1) >> 1), ub = (long long)d_hi - (d_iter >> 1);
+          const long long mid = ua + (ub - ua) / 2;
+          const int slot = reserve_slot(a, lane);
+          int *own = stack + (size_t)L * fw;
+          int *g = a.pool + (size_t)slot * fw;
+          for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
+          __syncwarp();
+          if (lane == 0) {
+            // the donated frame owns [mid + 1, ub]; this warp keeps [ua, mid]; both restart their value iteration
+            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
+            __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
+            __stcg(&own[FR_ITER], 0); __stcg(&own[FR_LO], (int)ua); __stcg(&own[FR_HI], (int)mid);
+            __stcg(&own[FR_LAST], (int)(unsigned)(mid - ua));
+            __threadfence();
+            __stcg(&a.ready[slot], 1);
+          }
+          if (L == level) { iter = 0; lo = (int)ua; hi = (int)mid; last = (unsigned)(mid - ua); }
+          __syncwarp();
+        }
       }
     }
   }
@@ -653,27 +766,28 @@ k_search_lov(const SearchArgs a) {
   uint32_t pF = 0;             // ... and its forbidden-value set (BITS)
   unsigned poll = 0;
 
+  bool hungry = false;
   for (;;) {
     if (level < base) {
-      // next frontier frame of this rank's partition (frames of other ranks are skipped, not copied)
-      int it = 0;
-      const int *src = nullptr;
-      for (;;) {
+      // out of work: take a frame of the frontier / shared pool
+      const int *src;
+      if (EXPAND) {
+        int it = 0;
         if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
         it = __shfl_sync(FULL, it, 0);
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
-        if (EXPAND || a.part_count <= 1 || (unsigned)__ldcg(&src[7]) % (unsigned)a.part_count == (unsigned)a.part_rank) break;
-      }
-      if (it >= ctl->item_count) {
-        if (lane == 0) {
-          const int n = atomicAdd(&ctl->idle, 1) + 1;
-          if (!EXPAND && n >= a.idle_exit) atomicMax(&ctl->signal, SIG_SLICE_END);
-        }
-        break;
+      } else {
+        const int slot = claim_frame(a, lane, hungry);
+        if (slot < 0) break;
+        src = a.pool + (size_t)slot * fw;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       frame_in(src, sst + L * sfw);
+      if (!EXPAND) {
+        __syncwarp();
+        if (lane == 0) { __threadfence(); __stcg(&a.ready[(src - a.pool) / fw], 0); }   // slot may be reused
+      }
       level = base = L;
       have = false;
       __syncwarp();
@@ -824,6 +938,39 @@ k_search_lov(const SearchArgs a) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
       }
+      if (level >= base && donation_wanted(a, lane)) {
+        // shallowest frame with at least two untried values (the top frame's iteration state is in registers)
+        int L = -1;
+        unsigned d_iter = 0; int d_lo = 0, d_hi = 0;
+        if (lane == 0) {
+          for (int q = base; q <= level; ++q) {
+            const int *qf = sst + q * sfw;
+            const unsigned it2 = q == level ? iter : (unsigned)qf[FR_ITER];
+            const unsigned la2 = (unsigned)qf[FR_LAST];
+            if (it2 <= la2 && la2 - it2 >= 1) { L = q; d_iter = it2; d_lo = qf[FR_LO]; d_hi = qf[FR_HI]; break; }
+          }
+        }
+        L = __shfl_sync(FULL, L, 0);
+        if (L >= 0) {
+          d_iter = __shfl_sync(FULL, d_iter, 0); d_lo = __shfl_sync(FULL, d_lo, 0); d_hi = __shfl_sync(FULL, d_hi, 0);
+          const long long ua = (long long)d_lo + ((d_iter + 1) >> 1), ub = (long long)d_hi - (d_iter >> 1);
+          const long long mid = ua + (ub - ua) / 2;
+          const int slot = reserve_slot(a, lane);
+          int *own = sst + L * sfw;
+          int *g = a.pool + (size_t)slot * fw;
+          frame_out(own, g);
+          __syncwarp();
+          if (lane == 0) {
+            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
+            __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
+            own[FR_ITER] = 0; own[FR_LO] = (int)ua; own[FR_HI] = (int)mid; own[FR_LAST] = (int)(unsigned)(mid - ua);
+            __threadfence();
+            __stcg(&a.ready[slot], 1);
+          }
+          if (L == level) { iter = 0; flo = (int)ua; fhi = (int)mid; last = (unsigned)(mid - ua); }
+          __syncwarp();
+        }
+      }
     }
   }
 
@@ -897,7 +1044,7 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
   }
   __syncthreads();
   // frames still in the frontier pool are work too: nothing to move while they last
-  const bool pool_left = a.ctl->item_next < a.ctl->item_count;
+  const bool pool_left = a.ctl->item_count - a.ctl->item_next > 0 || a.ctl->init_next < a.n_initial;
   for (int round = 0; round < 4 && !pool_left; ++round) {
     if (idle_done >= n_idle) break;
     if (threadIdx.x == 0) n_donor = 0;
@@ -952,6 +1099,7 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
     a.ctl->busy = busy + (pool_left ? 1 : 0);
     a.ctl->moved = moved;
     a.ctl->idle = 0;
+    a.ctl->hungry = 0;
     a.ctl->signal = a.ctl->signal == SIG_STOP ? SIG_STOP : SIG_RUN;
   }
 }

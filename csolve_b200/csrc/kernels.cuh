@@ -30,7 +30,9 @@ struct SearchCtl {
   int32_t busy;         // written by the rebalance kernel: warps that still own work
   int32_t moved;        // written by the rebalance kernel: frames handed to idle warps
   int32_t passed;       // expand mode: frames passed through unsplit (domain too large to enumerate)
-  int32_t pad[5];
+  int32_t hungry;       // warps waiting for a frame of the shared pool
+  int32_t init_next;    // next frame of the expanded root frontier (static part of the pool, claimed with atomicAdd)
+  int32_t pad[3];
 };
 
 struct WarpState {
@@ -57,6 +59,10 @@ struct SearchArgs {
   int32_t expand_branch_max;  // expand mode: frames with more values than this are passed through unsplit
   int32_t *gprio;             // prefer-failing: device-wide dynamic priorities [n_vars] (else nullptr)
   unsigned int *inst_solutions; // batched roots: per-root solution counters (else nullptr); the root id travels in header word 6
+  int32_t *ready;             // [pool_cap] 1 = the pool slot holds a complete frame (shared pool ring)
+  int32_t *pool;              // the shared pool (same memory as `items` in the depth-first phase), writable
+  int32_t pool_cap;           // frames in the pool ring
+  int32_t n_initial;          // the first n_initial pool entries are the expanded root frontier (rank partition applies)
   int32_t part_rank;          // this process searches the frontier frames whose path hash % part_count == part_rank
   int32_t part_count;
 };
