@@ -181,6 +181,7 @@ extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **
   } while (0)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
   UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst);
+  if (getenv("CSOLVE_NO_LOV")) { d.lov = 0; d.lovk = 0; d.frame_words = frame_words(d.n_vars, d.mask_words); }   // development switch: general kernels only
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
 #undef UP
@@ -231,13 +232,14 @@ namespace {
 int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots) {
   DevModel m = p->dev;
   if (batch) m.lov = 0;
-  if (p->stacks != nullptr && p->ws_lov != m.lov) {
+  const int ws_key = m.lov * 16 + m.lovk;
+  if (p->stacks != nullptr && p->ws_lov != ws_key) {
     // the lane-owns-variable and the general kernels have different occupancies: rebuild the per-warp state
     ws_free(p->stacks, p->stacks_bytes); cudaFree(p->wstate); cudaFree(p->wcount); cudaFree(p->totals); cudaFree(p->ctl); cudaFree(p->scratch);
     p->stacks = nullptr; p->wstate = nullptr; p->wcount = nullptr; p->totals = nullptr; p->ctl = nullptr; p->scratch = nullptr;
   }
   if (p->stacks == nullptr) {
-    p->ws_lov = m.lov;
+    p->ws_lov = ws_key;
     int per_sm = search_blocks_per_sm(m, false);
     if (per_sm <= 0) return fail(CSOLVE_ERR_CUDA, "search kernel does not fit on the device (shared memory per node too large)");
     p->grid = per_sm * g_sm_count;
@@ -320,6 +322,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
     root[FR_LEVEL] = 0; root[FR_BEST] = ctl.best; root[7] = 0x1234567;
     memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
+    if (m.lovk) memcpy(&root[frame_dom_offset(m.mask_words) + 2 * V], cm.lov_fconst.data(), sizeof(int32_t) * V);   // value sets
     CUDA_TRY(cudaMemcpyAsync(p->pool_a, root.data(), fw * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     ctl.item_count = 1;
   } else {

@@ -206,8 +206,10 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   // ---- "lane owns variable" tables: every clause is a NOT(EQ) between two variables or a variable
   //      and a constant, at most 32 variables, offsets in [-32, 31], no objective variable ----
   {
-    bool lov = V <= 32 && n_generic == 0 && m.obj_var < 0;
-    out.lov_pair.assign((size_t)V * 32, 0);
+    const int K = (V + 31) / 32;                 // variables per lane
+    bool lov = V <= 128 && n_generic == 0 && m.obj_var < 0;
+    const int stride = 32 * K;
+    out.lov_pair.assign((size_t)V * stride, 0);
     out.lov_cptr.assign(V + 1, 0);
     out.lov_cval.clear();
     for (int v = 0; v < V && lov; v++) {
@@ -216,7 +218,7 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
         const WatchRec &r = out.wrec[w];
         const int n = wrec_n(r.w0);
         if (wrec_kind(r.w0) == WK_NE_VV) {
-          unsigned long long &e = out.lov_pair[(size_t)v * 32 + wrec_arg(r.w0)];
+          unsigned long long &e = out.lov_pair[(size_t)v * stride + wrec_arg(r.w0)];
           for (int k = 0; k < n; k++) {
             if (r.c[k] < -32 || r.c[k] > 31) { lov = false; break; }
             e |= 1ull << (r.c[k] + 32);
@@ -227,15 +229,16 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
           lov = false;
         }
       }
-      if ((int)out.lov_cval.size() - out.lov_cptr[v] > 32) lov = false;   // one lane per constant
+      if (K == 1 && (int)out.lov_cval.size() - out.lov_cptr[v] > 32) lov = false;   // one lane per constant
     }
     out.lov_cptr[V] = (int32_t)out.lov_cval.size();
-    out.host.lov = lov ? 1 : 0;
     int32_t vmin = INT32_MAX, vmax = INT32_MIN;
     for (int v = 0; v < V; v++) { vmin = std::min(vmin, m.var_lo[v]); vmax = std::max(vmax, m.var_hi[v]); }
     bool bits = lov && (int64_t)vmax - (int64_t)vmin < 32;
+    out.host.lov = (lov && K == 1) ? 1 : 0;
+    out.host.lovk = (bits && K >= 2) ? K : 0;
     // constants outside the window can never sit on a bound: they are simply not representable (and not needed)
-    out.host.lov_bits = bits ? 1 : 0;
+    out.host.lov_bits = (bits && K == 1) ? 1 : 0;
     out.host.lov_vbase = vmin;
     out.lov_fconst.assign(V, 0u);
     if (bits) {
@@ -263,6 +266,7 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   h.objective = m.objective; h.obj_var = m.obj_var;
   h.mask_words = (V + 31) / 32;
   h.frame_words = frame_words(V, h.mask_words);
+  if (h.lovk) h.frame_words = (h.frame_words + V + 3) & ~3;      // + forbidden-value sets
   h.max_depth = max_depth;
   h.n_generic = n_generic;
   h.clause = out.clause.data();
@@ -272,7 +276,7 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   h.lov_pair = out.lov_pair.data(); h.lov_cptr = out.lov_cptr.data(); h.lov_cval = out.lov_cval.data();
   h.n_lov_cval = (int32_t)out.lov_cval.size();
   h.lov_fconst = out.lov_fconst.data();
-  h.lov_smem_bytes = (int32_t)((((size_t)V * 32 * 2 + (V + 1) + out.lov_cval.size() + V) * 4 + 15) & ~(size_t)15);
+  h.lov_smem_bytes = (int32_t)((((size_t)V * 32 * 2 + (V + 1) + out.lov_cval.size() + V) * 4 + 15) & ~(size_t)15);   // K == 1 only
   h.wrec_ptr = out.wrec_ptr.data();
   h.n_wrec = (int32_t)out.wrec.size();
   {

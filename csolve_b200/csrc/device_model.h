@@ -65,6 +65,8 @@ struct DevModel {
   int32_t lov;               // 1 when the model is eligible
   int32_t lov_bits;          // 1 when additionally all root domains fit a 32-value window (forbidden-value sets)
   int32_t lov_vbase;         // smallest root lower bound (bit 0 of the value sets)
+  int32_t lovk;              // K = 2..4 when the model (33..128 variables, value window <= 32) runs on the K-variables-per-lane
+                             // kernel; its frames carry n_vars extra words (the forbidden-value sets) after the domains
   int32_t lov_smem_bytes;
   int32_t n_lov_cval;
   const unsigned long long *lov_pair;  // [n_vars * 32]

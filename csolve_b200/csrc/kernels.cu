@@ -1024,6 +1024,451 @@ k_propagate_batch_lov(const DevModel m, int n_nodes, const int32_t *dom_in, cons
   }
 }
 
+// =====================================================================================================
+// K variables per lane: pure NOT(EQ) networks with 33..128 variables whose values fit a 32-value window
+// (sudoku: 81 cells, values 1..9). Lane j owns variables j, j + 32, ... in registers together with their
+// forbidden-value sets; same fixpoint as k_search_lov<.,true>. The DFS stack stays in HBM (frames carry the
+// value sets behind the domains); levels whose variable already is a value are counted and skipped: in this
+// form their propagation provably changes nothing (the variable's forbidden values were distributed when it
+// became a value).
+template <int K>
+struct LovK {
+  int lo[K], hi[K];
+  uint32_t F[K];
+};
+
+template <int K>
+__device__ __forceinline__ bool lovk_fixpoint(const DevModel &m, int lane, LovK<K> &x, uint32_t (&pend)[K],
+                                              unsigned &props, unsigned &visits) {
+  const int V = m.n_vars, vbase = m.lov_vbase;
+  for (;;) {
+    int kk = -1;
+#pragma unroll
+    for (int q = K - 1; q >= 0; q--) if (pend[q]) kk = q;
+    if (kk < 0) break;
+    const int bit = __ffs(pend[kk]) - 1;
+    const int i = kk * 32 + bit;
+    int wsrc = x.lo[0];
+#pragma unroll
+    for (int q = 1; q < K; q++) if (kk == q) wsrc = x.lo[q];
+    const int w = __shfl_sync(FULL, wsrc, bit);
+#pragma unroll
+    for (int q = 0; q < K; q++) if (kk == q) pend[q] &= pend[q] - 1;
+    bool dead = false;
+    unsigned changed = 0;
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      const int v = lane + 32 * q;
+      const bool act = v < V;
+      if (act) x.F[q] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + v]), w, vbase);
+      const bool was = x.lo[q] == x.hi[q];
+      const int olo = x.lo[q], ohi = x.hi[q];
+      if (!lov_trim(x.F[q], vbase, x.lo[q], x.hi[q])) dead = true;
+      pend[q] |= __ballot_sync(FULL, act && !was && x.lo[q] == x.hi[q]);
+      changed += __popc(__ballot_sync(FULL, x.lo[q] != olo || x.hi[q] != ohi));
+    }
+    if (__any_sync(FULL, dead)) return false;
+    props += changed;
+    visits += (unsigned)V;
+  }
+  return true;
+}
+
+template <int K>
+__device__ __forceinline__ void lovk_load(const DevModel &m, const int *frame, int lane, LovK<K> &x) {
+  const int dofs = frame_dom_offset(m.mask_words);
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const int v = lane + 32 * q;
+    int2 d = make_int2(m.lov_vbase, m.lov_vbase);
+    uint32_t F = 0;
+    if (v < m.n_vars) {
+      d = __ldcg(reinterpret_cast<const int2 *>(frame + dofs) + v);
+      F = (uint32_t)__ldcg(&frame[dofs + 2 * m.n_vars + v]);
+    }
+    x.lo[q] = d.x; x.hi[q] = d.y; x.F[q] = F;
+  }
+}
+template <int K>
+__device__ __forceinline__ void lovk_store(const DevModel &m, int *frame, int lane, const LovK<K> &x) {
+  const int dofs = frame_dom_offset(m.mask_words);
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const int v = lane + 32 * q;
+    if (v < m.n_vars) {
+      __stcg(reinterpret_cast<int2 *>(frame + dofs) + v, make_int2(x.lo[q], x.hi[q]));
+      __stcg(&frame[dofs + 2 * m.n_vars + v], (int)x.F[q]);
+    }
+  }
+}
+
+// next branching variable among those without a level; -1 if none. amask: uniform words.
+template <int K>
+__device__ __forceinline__ int lovk_select(const DevModel &m, int lane, const LovK<K> &x, const uint32_t (&amask)[K],
+                                           int order, int level1) {
+  if (order == CSOLVE_ORDER_NONE) return level1 < m.n_vars ? __ldg(&m.order[level1]) : -1;
+  unsigned long long bestk = ~0ull;
+  int bestv = 0x7fffffff;
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const int v = lane + 32 * q;
+    if (v >= m.n_vars || (amask[q] >> lane) & 1u) continue;
+    unsigned primary;
+    switch (order) {
+    case CSOLVE_ORDER_SMALLEST_DOMAIN: primary = (unsigned)x.hi[q] - (unsigned)x.lo[q]; break;
+    case CSOLVE_ORDER_LARGEST_DOMAIN:  primary = ~((unsigned)x.hi[q] - (unsigned)x.lo[q]); break;
+    case CSOLVE_ORDER_SMALLEST_VALUE:  primary = (unsigned)x.lo[q] ^ 0x80000000u; break;
+    default:                           primary = ~((unsigned)x.hi[q] ^ 0x80000000u); break;
+    }
+    const unsigned secondary = ~((unsigned)__ldg(&m.prio[v]) ^ 0x80000000u);
+    const unsigned long long key = ((unsigned long long)primary << 32) | secondary;
+    if (key < bestk) { bestk = key; bestv = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ok2 = __shfl_xor_sync(FULL, bestk, o);
+    const int ov = __shfl_xor_sync(FULL, bestv, o);
+    if (ok2 < bestk || (ok2 == bestk && ov < bestv)) { bestk = ok2; bestv = ov; }
+  }
+  return bestv == 0x7fffffff ? -1 : bestv;
+}
+
+// bounds of variable v (warp-uniform) from the register file of its owner lane
+template <int K>
+__device__ __forceinline__ int2 lovk_bounds(const LovK<K> &x, int v) {
+  int l = x.lo[0], h = x.hi[0];
+#pragma unroll
+  for (int q = 1; q < K; q++) if ((v >> 5) == q) { l = x.lo[q]; h = x.hi[q]; }
+  return make_int2(__shfl_sync(FULL, l, v & 31), __shfl_sync(FULL, h, v & 31));
+}
+
+template <bool EXPAND, int K>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, 3)
+k_search_lovk(const SearchArgs a) {
+  const DevModel &m = a.m;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+  if (gw >= a.n_warps) return;
+  const int V = m.n_vars, fw = m.frame_words;
+  int *stack = a.stacks + (size_t)gw * (V + 1) * fw;
+  SearchCtl *ctl = a.ctl;
+
+  int level = a.wstate[gw].level, base = a.wstate[gw].base;
+  unsigned long long nodes = 0, cuts = 0, sols = 0;
+  unsigned props = 0, visits = 0, poll = 0;
+  const long long t0 = clock64();
+  bool have = false, hungry = false;
+  int var = 0, flo = 0, fhi = 0, flevel = 0, ftag = 0;
+  unsigned iter = 0, last = 0, fhash = 0;
+  uint32_t amask[K];
+  LovK<K> P;                       // top frame: state before this level's assignment
+#pragma unroll
+  for (int q = 0; q < K; q++) { amask[q] = 0; P.lo[q] = P.hi[q] = m.lov_vbase; P.F[q] = 0; }
+
+  for (;;) {
+    if (level < base) {
+      const int *src;
+      if (EXPAND) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= ctl->item_count) break;
+        src = a.items + (size_t)it * fw;
+      } else {
+        const int slot = claim_frame(a, lane, hungry);
+        if (slot < 0) break;
+        src = a.pool + (size_t)slot * fw;
+      }
+      const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
+      int *dst = stack + (size_t)L * fw;
+      for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
+      if (!EXPAND) {
+        __syncwarp();
+        if (lane == 0) { __threadfence(); __stcg(&a.ready[(src - a.pool) / fw], 0); }
+      }
+      level = base = L;
+      have = false;
+      __syncwarp();
+    }
+
+    int *f = stack + (size_t)level * fw;
+    if (!have) {
+      const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(f));
+      const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(f) + 1);
+#pragma unroll
+      for (int q = 0; q < K; q++) amask[q] = (uint32_t)__ldcg(&f[FR_MASK + q]);
+      lovk_load<K>(m, f, lane, P);
+      var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; flo = h0.w;
+      fhi = h1.x; flevel = h1.y; ftag = h1.z; fhash = (unsigned)h1.w;
+      have = true;
+    }
+
+    if (EXPAND && last >= (unsigned)a.expand_branch_max) {
+      int slot = 0;
+      if (lane == 0) { slot = atomicAdd(&ctl->out_count, 1); atomicAdd(&ctl->passed, 1); }
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot < a.out_cap) {
+        int *g = a.items_out + (size_t)slot * fw;
+        for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&f[w]));
+      } else if (lane == 0) {
+        atomicAdd(&ctl->out_dropped, 1);
+      }
+      level = base - 1; have = false;
+      continue;
+    }
+    if (iter > last) { level--; have = false; continue; }
+
+    // ---- one search node -------------------------------------------------------------------------
+    const int val = step_value(flo, fhi, iter);
+    iter++;
+    LovK<K> x = P;
+    uint32_t pend[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      pend[q] = 0;
+      if ((var >> 5) == q) {
+        pend[q] = 1u << (var & 31);
+        if (lane == (var & 31)) { x.lo[q] = val; x.hi[q] = val; }
+      }
+    }
+    const bool ok = lovk_fixpoint<K>(m, lane, x, pend, props, visits);
+    nodes++;
+
+    if (!ok) {
+      cuts++;
+    } else {
+      // levels of variables that already are a value: one node each, nothing to propagate (see above)
+      uint32_t am[K];
+#pragma unroll
+      for (int q = 0; q < K; q++) am[q] = amask[q] | (((var >> 5) == q) ? (1u << (var & 31)) : 0u);
+      int lev = flevel + 1;
+      int nv = -1;
+      int2 nb = make_int2(0, 0);
+      unsigned hsh = mix_hash(fhash, (unsigned)var, (unsigned)val);
+      while (lev < V) {
+        nv = lovk_select<K>(m, lane, x, am, a.order, lev);
+        nb = lovk_bounds<K>(x, nv);
+        if (nb.x != nb.y) break;
+        nodes++;                                   // the level of a fixed variable
+        hsh = mix_hash(hsh, (unsigned)nv, (unsigned)nb.x);
+#pragma unroll
+        for (int q = 0; q < K; q++) if ((nv >> 5) == q) am[q] |= 1u << (nv & 31);
+        lev++;
+      }
+      if (lev >= V) {
+        // leaf: every variable is a value and none of them is forbidden by the others
+        bool good = true;
+#pragma unroll
+        for (int q = 0; q < K; q++)
+          if (lane + 32 * q < V && (x.lo[q] != x.hi[q] || ((x.F[q] >> (x.lo[q] - m.lov_vbase)) & 1u))) good = false;
+        if (__all_sync(FULL, good)) {
+          bool accepted = true;
+          if (m.objective == CSOLVE_OBJ_ANY) {
+            int old = 0;
+            if (lane == 0) old = atomicMax(&ctl->signal, SIG_STOP);
+            old = __shfl_sync(FULL, old, 0);
+            accepted = old != SIG_STOP;
+          }
+          if (accepted) {
+            sols++;
+            if (a.inst_solutions != nullptr && lane == 0) atomicAdd(&a.inst_solutions[ftag], 1u);
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&ctl->n_stored, 1);
+            slot = __shfl_sync(FULL, slot, 0);
+            if (slot < a.max_solutions) {
+              int *dst = a.solbuf + (size_t)slot * (V + 1);
+#pragma unroll
+              for (int q = 0; q < K; q++) if (lane + 32 * q < V) dst[lane + 32 * q] = x.lo[q];
+              if (lane == 0) dst[V] = ftag;
+            }
+          }
+        }
+      } else {
+        int *g;
+        if (EXPAND) {
+          int slot = 0;
+          if (lane == 0) slot = atomicAdd(&ctl->out_count, 1);
+          slot = __shfl_sync(FULL, slot, 0);
+          g = slot < a.out_cap ? a.items_out + (size_t)slot * fw : nullptr;
+          if (g == nullptr && lane == 0) atomicAdd(&ctl->out_dropped, 1);
+        } else {
+          if (lane == 0) __stcg(&f[FR_ITER], (int)iter);
+          g = stack + (size_t)(level + 1) * fw;
+        }
+        const unsigned nlast = (unsigned)nb.y - (unsigned)nb.x;
+        if (g != nullptr) {
+          if (lane == 0) {
+            __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)nlast, nb.x));
+            __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nb.y, lev, ftag, (int)hsh));
+          }
+          if (lane < K) {
+            uint32_t mv = am[0];
+#pragma unroll
+            for (int q = 1; q < K; q++) if (lane == q) mv = am[q];
+            __stcg(&g[FR_MASK + lane], (int)mv);
+          }
+          lovk_store<K>(m, g, lane, x);
+        }
+        if (!EXPAND) {
+#pragma unroll
+          for (int q = 0; q < K; q++) amask[q] = am[q];
+          P = x;
+          var = nv; flo = nb.x; fhi = nb.y; iter = 0; last = nlast;
+          flevel = lev; fhash = hsh;
+          level++;
+          __syncwarp();
+        }
+      }
+    }
+
+    if (!EXPAND && (++poll & 7u) == 0) {
+      if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
+      if (clock64() - t0 > a.slice_cycles) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
+        break;
+      }
+      if (level >= base && donation_wanted(a, lane)) {
+        int L = -1;
+        unsigned d_iter = 0; int d_lo = 0, d_hi = 0;
+        if (lane == 0) {
+          for (int q = base; q <= level; ++q) {
+            unsigned it2, la2; int lo2, hi2;
+            if (q == level) { it2 = iter; la2 = last; lo2 = flo; hi2 = fhi; }
+            else {
+              const int4 g0 = __ldcg(reinterpret_cast<const int4 *>(stack + (size_t)q * fw));
+              it2 = (unsigned)g0.y; la2 = (unsigned)g0.z; lo2 = g0.w; hi2 = __ldcg(&stack[(size_t)q * fw + FR_HI]);
+            }
+            if (it2 <= la2 && la2 - it2 >= 1) { L = q; d_iter = it2; d_lo = lo2; d_hi = hi2; break; }
+          }
+        }
+        L = __shfl_sync(FULL, L, 0);
+        if (L >= 0) {
+          d_iter = __shfl_sync(FULL, d_iter, 0); d_lo = __shfl_sync(FULL, d_lo, 0); d_hi = __shfl_sync(FULL, d_hi, 0);
+          const long long ua = (long long)d_lo + ((d_iter + 1) >> 1), ub = (long long)d_hi - (d_iter >> 1);
+          const long long mid = ua + (ub - ua) / 2;
+          const int slot = reserve_slot(a, lane);
+          int *own = stack + (size_t)L * fw;
+          int *g = a.pool + (size_t)slot * fw;
+          for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
+          __syncwarp();
+          if (lane == 0) {
+            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
+            __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
+            __stcg(&own[FR_ITER], 0); __stcg(&own[FR_LO], (int)ua); __stcg(&own[FR_HI], (int)mid);
+            __stcg(&own[FR_LAST], (int)(unsigned)(mid - ua));
+            __threadfence();
+            __stcg(&a.ready[slot], 1);
+          }
+          if (L == level) { iter = 0; flo = (int)ua; fhi = (int)mid; last = (unsigned)(mid - ua); }
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  if (lane == 0) {
+    if (have && level >= base) __stcg(&stack[(size_t)level * fw + FR_ITER], (int)iter);
+    a.wstate[gw].level = level;
+    a.wstate[gw].base = base;
+    unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
+    c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
+    c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols;
+  }
+}
+
+// node transitions (parity hook) and batched root frames for the K-variables-per-lane form
+template <int K>
+__device__ __forceinline__ void lovk_from_domains(const DevModel &m, const int32_t *dom, int lane, LovK<K> &x, uint32_t (&singles)[K]) {
+  const int V = m.n_vars;
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const int v = lane + 32 * q;
+    int2 d = make_int2(m.lov_vbase, m.lov_vbase);
+    if (v < V) d = __ldg(reinterpret_cast<const int2 *>(dom) + v);
+    x.lo[q] = d.x; x.hi[q] = d.y;
+    x.F[q] = v < V ? __ldg(&m.lov_fconst[v]) : 0u;
+    singles[q] = __ballot_sync(FULL, v < V && d.x == d.y);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK)
+k_propagate_batch_lovk(const DevModel m, int n_nodes, const int32_t *dom_in, const int32_t *var, const int32_t *val,
+                       int32_t *dom_out, uint8_t *failed) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int V = m.n_vars;
+  const int n_warps = gridDim.x * WARPS_PER_BLOCK;
+  for (int b = blockIdx.x * WARPS_PER_BLOCK + wib; b < n_nodes; b += n_warps) {
+    LovK<K> x; uint32_t pend[K];
+    lovk_from_domains<K>(m, dom_in + (size_t)b * 2 * V, lane, x, pend);
+    unsigned props = 0, visits = 0;
+    // value sets of the incoming state (which the search always leaves at a fixpoint): the values of the
+    // variables that are a value are distributed WITHOUT trimming; then the decision is propagated
+    for (int i = 0; i < V; i++) {
+      bool single_i = false;
+#pragma unroll
+      for (int q = 0; q < K; q++) if ((i >> 5) == q) single_i = (pend[q] >> (i & 31)) & 1u;
+      if (!single_i) continue;
+      const int2 bi = lovk_bounds<K>(x, i);
+#pragma unroll
+      for (int q = 0; q < K; q++) {
+        const int v = lane + 32 * q;
+        if (v < V) x.F[q] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + v]), bi.x, m.lov_vbase);
+      }
+    }
+    bool ok = true;
+    const int xv = var[b];
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      pend[q] = 0;
+      if ((xv >> 5) == q) {
+        pend[q] = 1u << (xv & 31);
+        if (lane == (xv & 31) && x.lo[q] != x.hi[q]) { x.lo[q] = val[b]; x.hi[q] = val[b]; }
+      }
+    }
+    if (ok) ok = lovk_fixpoint<K>(m, lane, x, pend, props, visits);
+#pragma unroll
+    for (int q = 0; q < K; q++)
+      if (lane + 32 * q < V) reinterpret_cast<int2 *>(dom_out + (size_t)b * 2 * V)[lane + 32 * q] = make_int2(x.lo[q], x.hi[q]);
+    if (lane == 0) failed[b] = ok ? 0 : 1;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK)
+k_root_frames_lovk(const DevModel m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out, int32_t *n_out,
+                   unsigned char *root_failed) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int V = m.n_vars, fw = m.frame_words;
+  const int n_warps = gridDim.x * WARPS_PER_BLOCK;
+  for (int r = blockIdx.x * WARPS_PER_BLOCK + wib; r < n_roots; r += n_warps) {
+    LovK<K> x; uint32_t pend[K];
+    lovk_from_domains<K>(m, root_dom + (size_t)r * 2 * V, lane, x, pend);
+    unsigned props = 0, visits = 0;
+    const bool ok = lovk_fixpoint<K>(m, lane, x, pend, props, visits);   // root phase: every value is distributed
+    if (lane == 0) root_failed[r] = ok ? 0 : 1;
+    if (!ok) continue;
+    uint32_t am[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) am[q] = 0;
+    // the first level (levels of variables that already are a value are skipped by the search kernel, not here:
+    // the root frame must exist even when everything is fixed)
+    const int nv = lovk_select<K>(m, lane, x, am, order, 0);
+    const int2 nb = lovk_bounds<K>(x, nv);
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(n_out, 1);
+    slot = __shfl_sync(FULL, slot, 0);
+    int *g = frames_out + (size_t)slot * fw;
+    if (lane == 0) {
+      __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)((unsigned)nb.y - (unsigned)nb.x), nb.x));
+      __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nb.y, 0, r, (int)mix_hash(0x1234567u, (unsigned)r, 0u)));
+    }
+    if (lane < K) __stcg(&g[FR_MASK + lane], 0);
+    lovk_store<K>(m, g, lane, x);
+  }
+}
+
 // ---- rebalance -----------------------------------------------------------------------------------
 // One block. Idle warps (level < base) are paired with busy warps that own a frame with at
 // least two untried values; the donor keeps the lower half of the untried interval, the idle
@@ -1200,9 +1645,18 @@ k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order,
 
 // ---- host-side launch wrappers -----------------------------------------------------------------------
 size_t search_smem_bytes(const DevModel &m) {
+  if (m.lovk) return 0;
   if (m.lov) return (size_t)m.lov_smem_bytes + (size_t)WARPS_PER_BLOCK * m.n_vars * ((8 + 3 * m.n_vars + 3) & ~3) * sizeof(int);
   const int wwords = (4 * m.n_vars + 3 * m.mask_words + 3) & ~3;
   return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
+}
+
+static const void *lovk_kernel(bool expand, int K) {
+  switch (K) {
+  case 2: return expand ? (const void *)k_search_lovk<true, 2> : (const void *)k_search_lovk<false, 2>;
+  case 3: return expand ? (const void *)k_search_lovk<true, 3> : (const void *)k_search_lovk<false, 3>;
+  default: return expand ? (const void *)k_search_lovk<true, 4> : (const void *)k_search_lovk<false, 4>;
+  }
 }
 
 static const void *lov_kernel(bool expand, bool bits) {
@@ -1218,6 +1672,10 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 int search_blocks_per_sm(const DevModel &m, bool expand) {
   int n = 0;
   const size_t smem = search_smem_bytes(m);
+  if (m.lovk) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lovk_kernel(expand, m.lovk), THREADS_PER_BLOCK, 0);
+    return n;
+  }
   if (m.lov) {
     const void *lf = lov_kernel(expand, m.lov_bits != 0);
     if (ensure_smem(lf, smem) != cudaSuccess) return 0;
@@ -1233,6 +1691,10 @@ int search_blocks_per_sm(const DevModel &m, bool expand) {
 
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
   const size_t smem = search_smem_bytes(a.m);
+  if (a.m.lovk) {
+    void *args[] = {(void *)&a};
+    return cudaLaunchKernel(lovk_kernel(expand, a.m.lovk), dim3(grid), dim3(THREADS_PER_BLOCK), args, 0, st);
+  }
   if (a.m.lov) {
     const void *lf = lov_kernel(expand, a.m.lov_bits != 0);
     cudaError_t e = ensure_smem(lf, smem);
@@ -1254,8 +1716,16 @@ cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream
 
 cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
                                int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t st) {
+  if (m_in.lovk) {
+    switch (m_in.lovk) {
+    case 2: k_root_frames_lovk<2><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, n_out, root_failed); break;
+    case 3: k_root_frames_lovk<3><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, n_out, root_failed); break;
+    default: k_root_frames_lovk<4><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, n_out, root_failed); break;
+    }
+    return cudaGetLastError();
+  }
   DevModel m = m_in;
-  m.lov = 0;                                  // the batched path runs on the general kernels
+  m.lov = 0;                                  // otherwise the batched path runs on the general kernels
   const size_t smem = search_smem_bytes(m);
   cudaError_t e = ensure_smem((const void *)k_root_frames, smem);
   if (e != cudaSuccess) return e;
@@ -1277,6 +1747,14 @@ cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t st) {
   const size_t smem = search_smem_bytes(m);
+  if (m.lovk) {
+    switch (m.lovk) {
+    case 2: k_propagate_batch_lovk<2><<<grid, THREADS_PER_BLOCK, 0, st>>>(m, n_nodes, dom_in, var, val, dom_out, failed); break;
+    case 3: k_propagate_batch_lovk<3><<<grid, THREADS_PER_BLOCK, 0, st>>>(m, n_nodes, dom_in, var, val, dom_out, failed); break;
+    default: k_propagate_batch_lovk<4><<<grid, THREADS_PER_BLOCK, 0, st>>>(m, n_nodes, dom_in, var, val, dom_out, failed); break;
+    }
+    return cudaGetLastError();
+  }
   if (m.lov) {
     cudaError_t e = ensure_smem((const void *)k_propagate_batch_lov, smem);
     if (e != cudaSuccess) return e;

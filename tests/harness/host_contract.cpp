@@ -87,32 +87,33 @@ extern "C" int hc_node(const int32_t *dom_in, int var, int32_t val, int32_t best
 // ballots = loops); returns -1 when the model is not eligible
 extern "C" int hc_node_lov(const int32_t *dom_in, int var, int32_t val, int32_t *dom_out) {
   const DevModel &m = g_cm.host;
-  if (!m.lov) return -1;
+  if (!m.lov && !m.lovk) return -1;
   const int V = m.n_vars;
-  int32_t lo[32], hi[32];
-  for (int j = 0; j < 32; j++) { lo[j] = j < V ? dom_in[2 * j] : 0; hi[j] = j < V ? dom_in[2 * j + 1] : 0; }
+  const int stride = 32 * ((V + 31) / 32);       // row length of lov_pair
+  int32_t lo[128], hi[128];
+  for (int j = 0; j < 128; j++) { lo[j] = j < V ? dom_in[2 * j] : 0; hi[j] = j < V ? dom_in[2 * j + 1] : 0; }
   if (lo[var] != hi[var]) { lo[var] = val; hi[var] = val; }
-  uint32_t changed = 1u << var;
+  uint32_t changed = var < 32 ? 1u << var : 0u;
   bool failed = false;
-  if (m.lov_bits) {
+  if (m.lov_bits || m.lovk) {
     // forbidden-value-set form (lov_forbid / lov_trim), lanes emulated one after the other
     const int vb = m.lov_vbase;
-    uint32_t F[32];
+    uint32_t F[128];
     for (int j = 0; j < V; j++) {
       F[j] = m.lov_fconst[j];
       for (int i = 0; i < V; i++)
-        if (dom_in[2 * i] == dom_in[2 * i + 1]) F[j] |= lov_forbid(m.lov_pair[i * 32 + j], dom_in[2 * i], vb);
+        if (dom_in[2 * i] == dom_in[2 * i + 1]) F[j] |= lov_forbid(m.lov_pair[(size_t)i * stride + j], dom_in[2 * i], vb);
     }
-    uint32_t pend = 1u << var;
-    while (pend && !failed) {
-      const int i = __builtin_ctz(pend);
-      pend &= pend - 1;
+    std::vector<int> pend(1, var);
+    std::vector<uint8_t> in_pend(V, 0);
+    for (size_t qi = 0; qi < pend.size() && !failed; qi++) {
+      const int i = pend[qi];
       const int32_t w = lo[i];
       for (int j = 0; j < V; j++) {
-        F[j] |= lov_forbid(m.lov_pair[i * 32 + j], w, vb);
+        F[j] |= lov_forbid(m.lov_pair[(size_t)i * stride + j], w, vb);
         const bool was = lo[j] == hi[j];
         if (!lov_trim(F[j], vb, lo[j], hi[j])) { failed = true; }
-        else if (!was && lo[j] == hi[j]) pend |= 1u << j;
+        else if (!was && lo[j] == hi[j] && !in_pend[j]) { in_pend[j] = 1; pend.push_back(j); }
       }
     }
     for (int j = 0; j < V; j++) { dom_out[2 * j] = lo[j]; dom_out[2 * j + 1] = hi[j]; }
@@ -128,7 +129,7 @@ extern "C" int hc_node_lov(const int32_t *dom_in, int var, int32_t val, int32_t 
     for (int j = 0; j < 32; j++) {
       nlo[j] = lo[j]; nhi[j] = hi[j];
       if (j >= V) continue;
-      LovStep r = lov_lane_step(m.lov_pair[i * 32 + j], Xlo, Xhi, lo[j], hi[j]);
+      LovStep r = lov_lane_step(m.lov_pair[(size_t)i * stride + j], Xlo, Xhi, lo[j], hi[j]);
       bool plo = r.plo, phi = r.phi;
       const int cb = m.lov_cptr[i], ce = m.lov_cptr[i + 1];
       if (cb + j < ce) lov_const_step(m.lov_cval[cb + j], Xlo, Xhi, plo, phi);

@@ -61,9 +61,10 @@ def test_product_contractors_on_host(name, specialise):
     assert _check_nodes(g, node, leaf) == 0
 
 
-@pytest.mark.parametrize("name", [n for n in REPLAY if n.startswith("queens")])
+@pytest.mark.parametrize("name", [n for n in REPLAY if n.startswith("queens") or n.startswith("sudoku")])
 def test_lane_owns_variable_form_on_host(name):
-    """the register-resident N-queens form (lov_lane_step) with the warp emulated on the host"""
+    """the register-resident forms (N-queens: one variable per lane; sudoku: three per lane, forbidden-value sets)
+    with the warp emulated on the host"""
     g = np.load(os.path.join(util.GOLDEN, "replay_%s.npz" % name))
     m = cb.Model(INST[name])
     hc = util.harness_lib()
@@ -73,7 +74,7 @@ def test_lane_owns_variable_form_on_host(name):
         dom = np.ascontiguousarray(dom, np.int32)
         out = np.empty_like(dom)
         f = hc.hc_node_lov(util.p32(dom), var, val, util.p32(out))
-        assert f >= 0, "queens must be eligible"
+        assert f >= 0, "pure NOT(EQ) networks must be eligible"
         return out, f
 
     assert _check_nodes(g, node, lambda d: hc.hc_leaf_true(util.p32(np.ascontiguousarray(d, np.int32)))) == 0
