@@ -124,6 +124,7 @@ struct csolve_gpu_problem {
   std::vector<int32_t> sol_host;
   int32_t n_stored = 0;
   cudaStream_t stream = nullptr;
+  NogoodPool ng{};                 // device clause pool of learned nogoods (allocated on demand)
   csolve_exchange_fn exchange = nullptr;
   void *exchange_user = nullptr;
 
@@ -131,6 +132,7 @@ struct csolve_gpu_problem {
     for (void *p : allocs) cudaFree(p);
     ws_free(stacks, stacks_bytes); cudaFree(wstate); cudaFree(wcount); cudaFree(totals); cudaFree(ctl);
     ws_free(pool_a, pool_bytes); ws_free(pool_b, pool_bytes); cudaFree(scratch); cudaFree(solbuf); cudaFree(ready);
+    cudaFree(ng.lits); cudaFree(ng.start); cudaFree(ng.len); cudaFree(ng.watch); cudaFree(ng.watch_n); cudaFree(ng.counters);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -229,10 +231,10 @@ extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes
 // ---- search ------------------------------------------------------------------------------------
 namespace {
 
-int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots) {
+int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots, bool learn) {
   DevModel m = p->dev;
   if (batch) m.lov = 0;
-  const int ws_key = m.lov * 16 + m.lovk;
+  const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0);
   if (p->stacks != nullptr && p->ws_lov != ws_key) {
     // the lane-owns-variable and the general kernels have different occupancies: rebuild the per-warp state
     ws_free(p->stacks, p->stacks_bytes); cudaFree(p->wstate); cudaFree(p->wcount); cudaFree(p->totals); cudaFree(p->ctl); cudaFree(p->scratch);
@@ -240,7 +242,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
   }
   if (p->stacks == nullptr) {
     p->ws_lov = ws_key;
-    int per_sm = search_blocks_per_sm(m, false);
+    int per_sm = search_blocks_per_sm(m, false, learn);
     if (per_sm <= 0) return fail(CSOLVE_ERR_CUDA, "search kernel does not fit on the device (shared memory per node too large)");
     p->grid = per_sm * g_sm_count;
     p->n_warps = p->grid * WARPS_PER_BLOCK;
@@ -293,8 +295,22 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   memset(res, 0, sizeof(*res));
   const bool batch = n_roots > 0;
   if (batch && p->dev.objective != CSOLVE_OBJ_ALL) return fail(CSOLVE_ERR_UNSUPPORTED, "batched roots need an ALL model");
-  int rc = ensure_workspace(p, opt, batch, n_roots);
+  // learning needs the general kernel; the specialised NOT(EQ) kernels never meet a 0/1-only conflict
+  const bool learn = opt.create_conflicts != 0 && !batch && !p->dev.lov && !p->dev.lovk;
+  int rc = ensure_workspace(p, opt, batch, n_roots, learn);
   if (rc != CSOLVE_OK) return rc;
+  if (learn) {
+    NogoodPool &g = p->ng;
+    if (g.lits == nullptr) {
+      g.cap_ng = 1 << 18; g.cap_lits = 1 << 23; g.cap_w = 4096;
+      CUDA_TRY(cudaMalloc(&g.lits, (size_t)g.cap_lits * 4)); CUDA_TRY(cudaMalloc(&g.start, (size_t)g.cap_ng * 4));
+      CUDA_TRY(cudaMalloc(&g.len, (size_t)g.cap_ng * 4)); CUDA_TRY(cudaMalloc(&g.watch, (size_t)p->dev.n_vars * g.cap_w * 4));
+      CUDA_TRY(cudaMalloc(&g.watch_n, (size_t)p->dev.n_vars * 4)); CUDA_TRY(cudaMalloc(&g.counters, 8 * 4));
+    }
+    CUDA_TRY(cudaMemsetAsync(g.watch, 0xff, (size_t)p->dev.n_vars * g.cap_w * 4, p->stream));
+    CUDA_TRY(cudaMemsetAsync(g.watch_n, 0, (size_t)p->dev.n_vars * 4, p->stream));
+    CUDA_TRY(cudaMemsetAsync(g.counters, 0, 8 * 4, p->stream));
+  }
 
   DevModel m = p->dev;
   if (batch) m.lov = 0;            // batched roots run on the general kernels
@@ -417,6 +433,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   CUDA_TRY(cudaMemsetAsync(p->ready, 0, (size_t)p->pool_cap * sizeof(int32_t), st));
   if (p->pool_cap - n_items < 1024) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
   a.gprio = d_gprio;     // the breadth-first expansion above stays deterministic (identical on every rank)
+  if (learn) a.ng = p->ng;
   ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.idle = 0; ctl.busy = 0; ctl.hungry = 0;
   ctl.signal = stopped ? SIG_STOP : SIG_RUN;
   CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
@@ -512,6 +529,12 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   res->kernel_ms = ms_search;
   res->expand_ms = ms_expand;
   res->kernel_launches = launches;
+  if (learn) {
+    int32_t cnt[8];
+    CUDA_TRY(cudaMemcpy(cnt, p->ng.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    res->conflicts = std::min(cnt[0], p->ng.cap_ng);
+    res->conflicts_abandoned = (uint64_t)cnt[3] + (uint64_t)cnt[4];
+  }
   (void)slices;
   return CSOLVE_OK;
 }
@@ -534,6 +557,31 @@ extern "C" int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_
                                       csolve_gpu_result *res) {
   if (n_roots <= 0 || root_dom == nullptr) return fail(CSOLVE_ERR_INVALID, "bad arguments");
   return solve_impl(p, opt, res, n_roots, root_dom, root_solutions, root_failed);
+}
+
+extern "C" int csolve_gpu_get_nogoods(csolve_gpu_problem *p, int32_t *lits, int32_t cap_lits, int32_t *starts, int32_t cap_ng,
+                                      int32_t *n_out) {
+  if (p == nullptr || lits == nullptr || starts == nullptr || n_out == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  *n_out = 0;
+  starts[0] = 0;
+  if (p->ng.lits == nullptr) return CSOLVE_OK;
+  int32_t cnt[8];
+  CUDA_TRY(cudaMemcpy(cnt, p->ng.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+  const int n = std::min(std::min(cnt[0], p->ng.cap_ng), cap_ng);
+  std::vector<int32_t> st(n), ln(n);
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpy(st.data(), p->ng.start, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ln.data(), p->ng.len, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  int total = 0, kept = 0;
+  for (int k = 0; k < n; k++) {
+    if (total + ln[k] > cap_lits) break;
+    CUDA_TRY(cudaMemcpy(lits + total, p->ng.lits + st[k], (size_t)ln[k] * 4, cudaMemcpyDeviceToHost));
+    total += ln[k];
+    starts[++kept] = total;
+  }
+  *n_out = kept;
+  return CSOLVE_OK;
 }
 
 extern "C" int csolve_gpu_get_solution_key(csolve_gpu_problem *p, int32_t i, int32_t *key) {

@@ -361,6 +361,32 @@ CSOLVE_HD bool contract_lits(Cx &cx, int n, int32_t l0, int32_t l1, int32_t l2) 
   return true;
 }
 
+// A learned nogood (src/conflict.c: a CONFL node): literals code = var << 1 | value with value in {0,1}.
+// propagate_confl (src/propagate.c:395-471): if some literal's variable is a value different from the
+// recorded one the nogood does not apply; if every literal but one matches and one variable is not a value,
+// the recorded value is removed from that variable's bound; all literals matching is NOT an error.
+template <class Cx>
+CSOLVE_HD bool contract_nogood(Cx &cx, const int32_t *lits, int n) {
+  int32_t unk = -1;
+  for (int k = 0; k < n; k++) {
+    const int32_t lit = lits[k];
+    const Dom D = cx.dom(lit >> 1);
+    if (D.lo == D.hi) {
+      if (D.lo != (lit & 1)) return true;      // a variable left the recorded value: nothing to infer
+    } else {
+      if (unk >= 0) return true;               // two variables still open
+      unk = lit;
+    }
+  }
+  if (unk < 0) return true;
+  const int v = unk >> 1;
+  const int32_t val = unk & 1;
+  const Dom D = cx.dom(v);
+  if (D.lo == val) return contract_var(cx, v, D.lo + 1, DMAX);      // propagate_confl_infer, src/propagate.c:441-456
+  if (D.hi == val) return contract_var(cx, v, DMIN, D.hi - 1);
+  return true;
+}
+
 // One watch record of variable `self` (device_model.h): X is the snapshot of self's domain the
 // caller took when it dequeued the variable. NE_VV: the NOT(EQ) clauses between self and one partner;
 // both directions of each clause are contracted from the snapshots, exactly like the false branch

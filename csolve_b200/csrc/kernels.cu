@@ -41,6 +41,8 @@ struct WarpCx {
   int *d;            // shared: 2 * n_vars words
   unsigned *nxt;     // shared: mask of variables narrowed in this round
   unsigned props;    // per-lane PROPS partial
+  int *rlo = nullptr, *rhi = nullptr;   // learning: which record last raised lo / lowered hi of a variable in this node
+  int cur = -1;                         // ... code of the record being contracted (>= 0 watch record, <= -2 nogood -2 - id)
   __device__ __forceinline__ Dom dom(int v) const {
     const volatile int *p = d + 2 * v;
     Dom r; r.lo = p[0]; r.hi = p[1];
@@ -48,10 +50,10 @@ struct WarpCx {
   }
   __device__ __forceinline__ void mark(int v) { atomicOr(&nxt[v >> 5], 1u << (v & 31)); }
   __device__ __forceinline__ void raise_lo(int v, int32_t lo) {
-    if (atomicMax(&d[2 * v], lo) < lo) mark(v);
+    if (atomicMax(&d[2 * v], lo) < lo) { mark(v); if (rlo) rlo[v] = cur; }
   }
   __device__ __forceinline__ void lower_hi(int v, int32_t hi) {
-    if (atomicMin(&d[2 * v + 1], hi) > hi) mark(v);
+    if (atomicMin(&d[2 * v + 1], hi) > hi) { mark(v); if (rhi) rhi[v] = cur; }
   }
   __device__ __forceinline__ void count_prop() { props++; }
 };
@@ -63,9 +65,16 @@ struct WarpSmem {
   unsigned *cur;   // mask_words: variables whose watchers run in this round
   unsigned *nxt;   // mask_words
   unsigned *amask; // mask_words: variables assigned on the path to the top frame
+  // learning only (src/conflict.c): per-variable reason records of this node, analysis scratch
+  int *rlo, *rhi;  // V each
+  unsigned *seen;  // mask_words
+  int *work;       // 2V: stack of record codes still to expand
+  int *nlits;      // NG_MAX_LITS
 };
 
-__device__ __forceinline__ int warp_smem_words(const DevModel &m) { return 4 * m.n_vars + 3 * m.mask_words; }
+__device__ __host__ __forceinline__ int warp_smem_words(const DevModel &m, bool learn = false) {
+  return 4 * m.n_vars + 3 * m.mask_words + (learn ? 4 * m.n_vars + m.mask_words + NG_MAX_LITS : 0);
+}
 
 __device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
   WarpSmem s;
@@ -74,6 +83,11 @@ __device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
   s.cur = (unsigned *)(base + 4 * m.n_vars);
   s.nxt = s.cur + m.mask_words;
   s.amask = s.nxt + m.mask_words;
+  s.rlo = (int *)(s.amask + m.mask_words);       // only valid when the region was sized with learn = true
+  s.rhi = s.rlo + m.n_vars;
+  s.seen = (unsigned *)(s.rhi + m.n_vars);
+  s.work = (int *)(s.seen + m.mask_words);
+  s.nlits = s.work + 2 * m.n_vars;
   return s;
 }
 
@@ -81,12 +95,17 @@ __device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
 // precondition: s.cur holds the initial worklist, s.nxt is zero, warp converged after __syncwarp.
 // wrec / wptr: the compiled watch records (shared memory when the table was staged, else global).
 // returns false when the node failed (PROP_ERROR).
+struct FailInfo { int rec; int var; };   // learning: record being contracted when the node failed / variable found empty
+
+template <bool LEARN = false>
 __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, const int4 *wrec, const int *wptr,
-                                              int lane, unsigned &props, unsigned &visits, int *gprio = nullptr) {
+                                              int lane, unsigned &props, unsigned &visits, int *gprio = nullptr,
+                                              const NogoodPool *ng = nullptr, FailInfo *fi = nullptr) {
   WarpCx cx;
   cx.d = s.d; cx.props = 0;
+  if (LEARN) { cx.rlo = s.rlo; cx.rhi = s.rhi; }
   bool failed = false;
-  int fail_var = -1;
+  int fail_var = -1, fail_rec = -1, empty_var = -1;
   for (;;) {
     cx.nxt = s.nxt;
     bool any = false;
@@ -99,20 +118,40 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
         // snapshot of the dequeued variable; bounds published by different lanes may have
         // crossed since it was queued: an empty domain is a failure
         const Dom X = cx.dom(x);
-        if (X.lo > X.hi) failed = true;
+        if (X.lo > X.hi) { failed = true; empty_var = x; }
         const int b = wptr[x], e = wptr[x + 1];
         for (int i = b + lane; i < e; i += 32) {
           const int4 q = wrec[i];
           WatchRec rec; rec.w0 = (uint32_t)q.x; rec.c[0] = q.y; rec.c[1] = q.z; rec.c[2] = q.w;
-          if (!contract_watch(cx, m, x, X, rec)) { failed = true; fail_var = x; }
+          if (LEARN) cx.cur = i;
+          if (!contract_watch(cx, m, x, X, rec)) { failed = true; fail_var = x; fail_rec = i; }
           visits++;
+        }
+        if (LEARN) {
+          // learned nogoods that mention x (propagate_confl, src/propagate.c:459-471)
+          const int cnt = min(*reinterpret_cast<volatile int *>(&ng->watch_n[x]), ng->cap_w);
+          for (int i = lane; i < cnt; i += 32) {
+            const int id = __ldcg(&ng->watch[(size_t)x * ng->cap_w + i]);
+            if (id < 0) continue;
+            cx.cur = -2 - id;
+            if (!contract_nogood(cx, ng->lits + __ldcg(&ng->start[id]), __ldcg(&ng->len[id]))) {
+              failed = true; fail_var = x; fail_rec = -2 - id;
+            }
+            visits++;
+          }
         }
       }
     }
     __syncwarp();
-    if (__any_sync(FULL, failed)) {
+    const unsigned fmask = __ballot_sync(FULL, failed);
+    if (fmask) {
       // prefer-failing: the variable whose clauses failed gains priority (propagate_term_recurse, src/propagate.c:44-54)
       if (gprio != nullptr && fail_var >= 0) atomicAdd(&gprio[fail_var], 1);
+      if (LEARN && fi != nullptr) {
+        const int src = __ffs(fmask) - 1;
+        fi->rec = __shfl_sync(FULL, fail_rec, src);
+        fi->var = __shfl_sync(FULL, empty_var, src);
+      }
       props += cx.props;
       return false;
     }
@@ -124,6 +163,101 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
   }
   props += cx.props;
   return true;
+}
+
+// ---- conflict analysis (src/conflict.c:327-362), executed by lane 0 after a failed node ---------------------
+// The nogood is the set of (variable = value) facts the failure rests on: the decision of this node and the
+// values of variables that were already a value before this node (src/conflict.c:188-197: "bound at a lower
+// level" terminals are taken as they are); variables narrowed inside this node are replaced by the variables of
+// the record that narrowed them (src/conflict.c:289-307). Only 0/1 values can be recorded
+// (src/conflict.c:173-179): anything else abandons the analysis, as in the reference.
+// Differences to the reference, none of which affects results: no back-jump (the search stays chronological,
+// the nogood prunes later nodes), a variable that became a value at an earlier level is always taken as a
+// literal (the reference expands the reasons of the failing variable itself one level further).
+struct Analysis {
+  const DevModel &m; const WarpSmem &s; const int4 *wrec; const int *wptr; const NogoodPool &ng;
+  int decision_var, n_lits, n_work; bool ok;
+
+  __device__ void visit(int y) {
+    if (!ok) return;
+    if (s.seen[y >> 5] & (1u << (y & 31))) return;
+    s.seen[y >> 5] |= 1u << (y & 31);
+    const int dl = s.d[2 * y], dh = s.d[2 * y + 1], pl = s.p[2 * y], ph = s.p[2 * y + 1];
+    if (y == decision_var || (dl == pl && dh == ph)) {
+      // the decision, or a value fixed before this node
+      const int lo = y == decision_var ? dl : pl, hi = y == decision_var ? dh : ph;
+      if (lo != hi || lo < 0 || lo > 1 || n_lits >= NG_MAX_LITS) { ok = false; return; }
+      s.nlits[n_lits++] = (y << 1) | lo;
+      return;
+    }
+    // narrowed in this node: its bounds must be explainable by records alone
+    if (__ldg(&m.root_dom[2 * y]) < 0 || __ldg(&m.root_dom[2 * y + 1]) > 1 || pl != __ldg(&m.root_dom[2 * y]) || ph != __ldg(&m.root_dom[2 * y + 1])) { ok = false; return; }
+    if (dl != pl) push(s.rlo[y]);
+    if (dh != ph) push(s.rhi[y]);
+  }
+  __device__ void push(int code) {
+    if (code == -1 || n_work >= 2 * m.n_vars) { ok = false; return; }    // narrowed without a record (objective tightening)
+    s.work[n_work++] = code;
+  }
+  __device__ int owner_of(int r) const {      // variable whose watch list holds record r
+    int a = 0, b = m.n_vars;
+    while (b - a > 1) { const int c = (a + b) >> 1; if (wptr[c] <= r) a = c; else b = c; }
+    return a;
+  }
+  __device__ void expand(int code) {
+    if (code <= -2) {
+      const int id = -2 - code;
+      const int st = __ldcg(&ng.start[id]), n = __ldcg(&ng.len[id]);
+      for (int k = 0; k < n && ok; k++) visit(__ldcg(&ng.lits[st + k]) >> 1);
+      return;
+    }
+    const int4 q = wrec[code];
+    const uint32_t kind = wrec_kind((uint32_t)q.x);
+    if (kind == WK_NE_VV) { visit(owner_of(code)); visit(wrec_arg((uint32_t)q.x)); }
+    else if (kind == WK_NE_VC) { visit(owner_of(code)); }
+    else if (kind == WK_LITS) {
+      const int n = wrec_n((uint32_t)q.x);
+      visit(q.y >> 1); if (n > 1) visit(q.z >> 1); if (n > 2) visit(q.w >> 1);
+    } else {
+      const ClauseRec c = m.clause[wrec_arg((uint32_t)q.x)];
+      for (int j = c.a; j <= c.b && ok; j++) if (m.node_op[j] == CSOLVE_OP_VAR) visit(m.node_l[j]);
+    }
+  }
+};
+
+__device__ __noinline__ void learn_nogood(const DevModel &m, const WarpSmem &s, const int4 *wrec, const int *wptr,
+                                          const NogoodPool &ng, int decision_var, FailInfo fi) {
+  atomicAdd(&ng.counters[2], 1);
+  for (int w = 0; w < m.mask_words; w++) s.seen[w] = 0;
+  Analysis an{m, s, wrec, wptr, ng, decision_var, 0, 0, true};
+  if (fi.var >= 0) {
+    // a variable whose bounds crossed: explained by the records that moved its two bounds
+    const int y = fi.var;
+    s.seen[y >> 5] |= 1u << (y & 31);
+    if (__ldg(&m.root_dom[2 * y]) < 0 || __ldg(&m.root_dom[2 * y + 1]) > 1) an.ok = false;
+    if (y == decision_var) an.ok = false;     // rare (needs two lanes racing on the decision variable): not analysed
+    if (an.ok) { if (s.d[2 * y] != s.p[2 * y]) an.push(s.rlo[y]); if (s.d[2 * y + 1] != s.p[2 * y + 1]) an.push(s.rhi[y]); }
+  } else if (fi.rec != -1) {
+    an.push(fi.rec);
+  } else {
+    an.ok = false;
+  }
+  while (an.ok && an.n_work > 0) an.expand(s.work[--an.n_work]);
+  if (!an.ok || an.n_lits == 0) { atomicAdd(&ng.counters[3], 1); return; }
+  const int n = an.n_lits;
+  const int st = atomicAdd(&ng.counters[1], n);
+  if (st + n > ng.cap_lits) { atomicAdd(&ng.counters[4], 1); return; }
+  const int id = atomicAdd(&ng.counters[0], 1);
+  if (id >= ng.cap_ng) { atomicAdd(&ng.counters[4], 1); return; }
+  for (int k = 0; k < n; k++) ng.lits[st + k] = s.nlits[k];
+  ng.start[id] = st; ng.len[id] = n;
+  __threadfence();
+  // the nogood is watched by every variable it mentions (src/conflict.c:354-358)
+  for (int k = 0; k < n; k++) {
+    const int v = s.nlits[k] >> 1;
+    const int slot = atomicAdd(&ng.watch_n[v], 1);
+    if (slot < ng.cap_w) __stcg(&ng.watch[(size_t)v * ng.cap_w + slot], id);
+  }
 }
 
 // stage the watch-record table into shared memory (whole block); returns the pointers to use
@@ -308,7 +442,7 @@ __device__ __forceinline__ int reserve_slot(const SearchArgs &a, int lane) {
 
 // ---- the search kernel ----------------------------------------------------------------------------
 // Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
-template <bool EXPAND>
+template <bool EXPAND, bool LEARN>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_MIN_BLOCKS)
 k_search(const SearchArgs a) {
   extern __shared__ __align__(16) int smem[];
@@ -320,7 +454,7 @@ k_search(const SearchArgs a) {
   stage_table(m, smem, wrec, wptr);
   if (gw >= a.n_warps) return;
   // per-warp regions are padded to 16 bytes so the int2 staging copies stay aligned
-  const int wwords = (warp_smem_words(m) + 3) & ~3;
+  const int wwords = (warp_smem_words(m, LEARN) + 3) & ~3;
   WarpSmem s = carve(m, smem + (m.table_smem_bytes >> 2) + wib * wwords);
 
   const int V = m.n_vars, fw = m.frame_words;
@@ -425,7 +559,8 @@ k_search(const SearchArgs a) {
       }
       ok = __shfl_sync(FULL, ok, 0);
       __syncwarp();
-      if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
+      if (LEARN) { for (int v = lane; v < V; v += 32) { s.rlo[v] = -1; s.rhi[v] = -1; } __syncwarp(); }
+      if (ok) ok = warp_fixpoint<LEARN>(m, s, wrec, wptr, lane, props, visits, nullptr, &a.ng, nullptr);
       refresh++;
       // untried values of the old enumeration form the interval [lo + ceil(iter/2), hi - floor(iter/2)]
       const long long ua = (long long)lo + ((iter + 1) >> 1), ub = (long long)hi - (iter >> 1);
@@ -474,9 +609,17 @@ k_search(const SearchArgs a) {
       }
     }
     ok = __shfl_sync(FULL, ok, 0);
+    if (LEARN) { for (int v = lane; v < V; v += 32) { s.rlo[v] = -1; s.rhi[v] = -1; } }
     __syncwarp();
-    if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits, a.gprio);
+    FailInfo fi; fi.rec = -1; fi.var = -1;
+    if (ok) ok = warp_fixpoint<LEARN>(m, s, wrec, wptr, lane, props, visits, a.gprio, &a.ng, &fi);
     nodes++;
+    if (LEARN && !ok) {
+      // conflict_create (src/conflict.c:327-362): record why this node failed
+      __syncwarp();
+      if (lane == 0) learn_nogood(m, s, wrec, wptr, a.ng, var, fi);
+      __syncwarp();
+    }
     // prio-- on success, prio++ on failure (src/csolve.c:459-462)
     if (a.gprio != nullptr && lane == 0) atomicAdd(&a.gprio[var], ok ? -1 : 1);
 
@@ -1644,7 +1787,11 @@ k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order,
 }
 
 // ---- host-side launch wrappers -----------------------------------------------------------------------
-size_t search_smem_bytes(const DevModel &m) {
+size_t search_smem_bytes(const DevModel &m, bool learn) {
+  if (learn) {
+    const int wwords = (warp_smem_words(m, true) + 3) & ~3;
+    return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
+  }
   if (m.lovk) return 0;
   if (m.lov) return (size_t)m.lov_smem_bytes + (size_t)WARPS_PER_BLOCK * m.n_vars * ((8 + 3 * m.n_vars + 3) & ~3) * sizeof(int);
   const int wwords = (4 * m.n_vars + 3 * m.mask_words + 3) & ~3;
@@ -1669,9 +1816,17 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
   return cudaSuccess;
 }
 
-int search_blocks_per_sm(const DevModel &m, bool expand) {
+bool search_learns(const SearchArgs &a) { return a.ng.lits != nullptr; }
+
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn) {
   int n = 0;
-  const size_t smem = search_smem_bytes(m);
+  const size_t smem = search_smem_bytes(m, learn);
+  if (learn) {
+    const void *fn = expand ? (const void *)k_search<true, true> : (const void *)k_search<false, true>;
+    if (ensure_smem(fn, smem) != cudaSuccess) return 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem);
+    return n;
+  }
   if (m.lovk) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lovk_kernel(expand, m.lovk), THREADS_PER_BLOCK, 0);
     return n;
@@ -1682,15 +1837,23 @@ int search_blocks_per_sm(const DevModel &m, bool expand) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lf, THREADS_PER_BLOCK, smem);
     return n;
   }
-  const void *fn = expand ? (const void *)k_search<true> : (const void *)k_search<false>;
+  const void *fn = expand ? (const void *)k_search<true, false> : (const void *)k_search<false, false>;
   if (ensure_smem(fn, smem) != cudaSuccess) return 0;
-  if (expand) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search<true>, THREADS_PER_BLOCK, smem);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_search<false>, THREADS_PER_BLOCK, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem);
   return n;
 }
 
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
-  const size_t smem = search_smem_bytes(a.m);
+  const bool learn = search_learns(a);
+  const size_t smem = search_smem_bytes(a.m, learn);
+  if (learn) {
+    // conflict-clause learning runs on the general kernel
+    const void *fn = expand ? (const void *)k_search<true, true> : (const void *)k_search<false, true>;
+    cudaError_t e = ensure_smem(fn, smem);
+    if (e != cudaSuccess) return e;
+    void *args[] = {(void *)&a};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(THREADS_PER_BLOCK), args, smem, st);
+  }
   if (a.m.lovk) {
     void *args[] = {(void *)&a};
     return cudaLaunchKernel(lovk_kernel(expand, a.m.lovk), dim3(grid), dim3(THREADS_PER_BLOCK), args, 0, st);
@@ -1703,13 +1866,13 @@ cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream
     return cudaLaunchKernel(lf, dim3(grid), dim3(THREADS_PER_BLOCK), args, smem, st);
   }
   if (expand) {
-    cudaError_t e = ensure_smem((const void *)k_search<true>, smem);
+    cudaError_t e = ensure_smem((const void *)k_search<true, false>, smem);
     if (e != cudaSuccess) return e;
-    k_search<true><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
+    k_search<true, false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
   } else {
-    cudaError_t e = ensure_smem((const void *)k_search<false>, smem);
+    cudaError_t e = ensure_smem((const void *)k_search<false, false>, smem);
     if (e != cudaSuccess) return e;
-    k_search<false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
+    k_search<false, false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
   }
   return cudaGetLastError();
 }
@@ -1726,7 +1889,7 @@ cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t 
   }
   DevModel m = m_in;
   m.lov = 0;                                  // otherwise the batched path runs on the general kernels
-  const size_t smem = search_smem_bytes(m);
+  const size_t smem = search_smem_bytes(m, false);
   cudaError_t e = ensure_smem((const void *)k_root_frames, smem);
   if (e != cudaSuccess) return e;
   k_root_frames<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_roots, root_dom, order, frames_out, n_out, root_failed);
@@ -1746,7 +1909,7 @@ cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps
 cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t st) {
-  const size_t smem = search_smem_bytes(m);
+  const size_t smem = search_smem_bytes(m, false);
   if (m.lovk) {
     switch (m.lovk) {
     case 2: k_propagate_batch_lovk<2><<<grid, THREADS_PER_BLOCK, 0, st>>>(m, n_nodes, dom_in, var, val, dom_out, failed); break;

@@ -40,6 +40,17 @@ struct WarpState {
   int32_t base;    // lowest level the warp owns
 };
 
+// Learned nogoods (src/conflict.c): an append-only pool shared by all warps of one GPU.
+//   nogood k = lits[start[k] .. start[k] + len[k]), literal code = var << 1 | value (value in {0,1})
+//   watch[v * cap_w + i] = nogoods that mention variable v (-1 = slot reserved, not written yet)
+//   counters: [0] nogoods, [1] literals, [2] conflicts analysed, [3] analyses abandoned (a non-0/1 value was involved,
+//   src/conflict.c:173-179, or the nogood was too long), [4] pool full
+struct NogoodPool {
+  int32_t *lits, *start, *len, *watch, *watch_n, *counters;
+  int32_t cap_ng, cap_lits, cap_w;
+};
+static const int NG_MAX_LITS = 96;   // longest nogood kept
+
 struct SearchArgs {
   DevModel m;
   SearchCtl *ctl;
@@ -57,6 +68,7 @@ struct SearchArgs {
   int32_t frozen_best;        // expand mode: incumbent every node of this level is propagated against
   long long slice_cycles;     // clock64() budget of one slice
   int32_t expand_branch_max;  // expand mode: frames with more values than this are passed through unsplit
+  NogoodPool ng;              // ng.lits == nullptr: conflict-clause learning off
   int32_t *gprio;             // prefer-failing: device-wide dynamic priorities [n_vars] (else nullptr)
   unsigned int *inst_solutions; // batched roots: per-root solution counters (else nullptr); the root id travels in header word 6
   int32_t *ready;             // [pool_cap] 1 = the pool slot holds a complete frame (shared pool ring)
@@ -67,14 +79,15 @@ struct SearchArgs {
   int32_t part_count;
 };
 
-size_t search_smem_bytes(const DevModel &m);
+size_t search_smem_bytes(const DevModel &m, bool learn = false);
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s);
+bool search_learns(const SearchArgs &a);
 cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t s);
 cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out, cudaStream_t s);
 cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t s);
-int search_blocks_per_sm(const DevModel &m, bool expand);
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn = false);
 cudaError_t launch_root_frames(const DevModel &m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
                                int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t s);
 

@@ -74,14 +74,16 @@ class _GpuConfig(C.Structure):
 class _SolveOptions(C.Structure):
     _fields_ = [("order", C.c_int32), ("part_rank", C.c_int32), ("part_count", C.c_int32),
                 ("split_target", C.c_int32), ("max_solutions", C.c_int32), ("time_limit_ms", C.c_int32),
-                ("slice_ms", C.c_int32), ("prefer_failing", C.c_int32)]
+                ("slice_ms", C.c_int32), ("create_conflicts", C.c_int32), ("reserved", C.c_int32),
+                ("prefer_failing", C.c_int32)]
 
 
 class _GpuResult(C.Structure):
     _fields_ = [("solutions", C.c_uint64), ("nodes", C.c_uint64), ("cuts", C.c_uint64), ("props", C.c_uint64),
                 ("clause_visits", C.c_uint64), ("best", C.c_int32), ("has_solution", C.c_int32),
                 ("timed_out", C.c_int32), ("n_stored", C.c_int32), ("kernel_ms", C.c_double),
-                ("expand_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+                ("expand_ms", C.c_double), ("kernel_launches", C.c_uint64), ("conflicts", C.c_uint64),
+                ("conflicts_abandoned", C.c_uint64)]
 
 
 # int (*csolve_exchange_fn)(void *user, int32_t *best, int32_t *found, int32_t local_done)
@@ -120,6 +122,7 @@ def library():
     lib.csolve_gpu_propagate_batch.argtypes = [C.c_void_p, C.c_int32, I32P, I32P, I32P, I32P, I32P, U8P]
     lib.csolve_gpu_solve.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.POINTER(_GpuResult)]
     lib.csolve_gpu_get_solution.argtypes = [C.c_void_p, C.c_int32, I32P]
+    lib.csolve_gpu_get_nogoods.argtypes = [C.c_void_p, I32P, C.c_int32, I32P, C.c_int32, I32P]
     lib.csolve_gpu_get_solution_key.argtypes = [C.c_void_p, C.c_int32, I32P]
     lib.csolve_gpu_solve_batch.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.c_int32, I32P,
                                            C.POINTER(C.c_uint32), U8P, C.POINTER(_GpuResult)]
@@ -224,11 +227,11 @@ class GpuProblem:
         return out, failed
 
     def solve(self, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0,
-              time_limit_ms=0, slice_ms=0, prefer_failing=False):
+              time_limit_ms=0, slice_ms=0, prefer_failing=False, create_conflicts=False):
         if isinstance(order, str):
             order = ORDER_NAMES[order]
         opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
-                            1 if prefer_failing else 0)
+                            1 if create_conflicts else 0, 0, 1 if prefer_failing else 0)
         res = _GpuResult()
         _check(library().csolve_gpu_solve(self._h, C.byref(opt), C.byref(res)))
         sols = []
@@ -237,6 +240,16 @@ class GpuProblem:
             _check(library().csolve_gpu_get_solution(self._h, i, buf))
             sols.append(list(buf))
         return SolveResult(res, sols)
+
+    def nogoods(self, cap_lits=1 << 22, cap_ng=1 << 18):
+        """nogoods learned by the last solve(create_conflicts=True): list of [(var, value), ...]"""
+        lits = np.zeros(cap_lits, np.int32)
+        starts = np.zeros(cap_ng + 1, np.int32)
+        n = C.c_int32()
+        I32P = C.POINTER(C.c_int32)
+        _check(library().csolve_gpu_get_nogoods(self._h, lits.ctypes.data_as(I32P), cap_lits, starts.ctypes.data_as(I32P),
+                                                cap_ng, C.byref(n)))
+        return [[(int(c) >> 1, int(c) & 1) for c in lits[starts[k]:starts[k + 1]]] for k in range(n.value)]
 
     def set_exchange(self, fn):
         """fn(best, found, local_done) -> (best, found, all_done): called once per time slice (see
@@ -266,7 +279,7 @@ class GpuProblem:
         n = roots.shape[0]
         counts = np.zeros(n, np.uint32)
         failed = np.zeros(n, np.uint8)
-        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms, 0)
+        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms, 0, 0, 0)
         res = _GpuResult()
         _check(library().csolve_gpu_solve_batch(self._h, C.byref(opt), n, roots.ctypes.data_as(I32P),
                                                 counts.ctypes.data_as(C.POINTER(C.c_uint32)),

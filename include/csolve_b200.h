@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSOLVE_B200_ABI_VERSION 1
+#define CSOLVE_B200_ABI_VERSION 2
 
 /* ---- error codes (all entry points return 0 on success) ------------------ */
 #define CSOLVE_OK                 0
@@ -134,6 +134,12 @@ typedef struct csolve_solve_options {
   int32_t max_solutions;       /* capacity of the solution buffer (assignments kept for printing); 0 = none */
   int32_t time_limit_ms;       /* -t; 0 = off */
   int32_t slice_ms;            /* length of one persistent-kernel time slice; 0 = default */
+  int32_t create_conflicts;    /* -c (src/main.c:57-61): learn decision nogoods from failed nodes (src/conflict.c) into a
+                                * device clause pool that is propagated on later nodes. Only 0/1-valued facts can be
+                                * recorded, so it matters for SAT-like models; models that run on the specialised
+                                * NOT(EQ) kernels never produce a nogood (neither does the reference) and ignore it.
+                                * No back-jump, no restarts: results are identical with and without. 0 = off */
+  int32_t reserved;
   int32_t prefer_failing;      /* -f (src/main.c:63-67): break ordering ties by a failure-driven priority that is
                                 * shared by all warps and updated during the search (src/csolve.c:459-462,
                                 * src/propagate.c:33-54). The tree then depends on timing: ALL counts and optima are
@@ -153,6 +159,8 @@ typedef struct csolve_gpu_result {
   double   kernel_ms;          /* device time of the search kernels (CUDA events) */
   double   expand_ms;          /* device time of root-frontier expansion */
   uint64_t kernel_launches;    /* kernels launched by this call */
+  uint64_t conflicts;          /* nogoods learned = CONFL (src/conflict.c:361) */
+  uint64_t conflicts_abandoned;/* analyses given up (non-0/1 value involved, too long, pool full) */
 } csolve_gpu_result;
 
 int  csolve_gpu_init(const csolve_gpu_config *cfg);
@@ -191,6 +199,12 @@ int csolve_gpu_set_exchange(csolve_gpu_problem *p, csolve_exchange_fn fn, void *
 int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_options *opt, int32_t n_roots,
                            const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed,
                            csolve_gpu_result *res);
+
+/* Learned nogoods of the last csolve_gpu_solve() with create_conflicts: copies up to cap_lits literal codes
+ * (var << 1 | value) into lits and the start offset of every nogood into starts[0..n] (starts[n] = total);
+ * returns the number of nogoods n in *n_out. For inspection and tests. */
+int csolve_gpu_get_nogoods(csolve_gpu_problem *p, int32_t *lits, int32_t cap_lits, int32_t *starts, int32_t cap_ng,
+                           int32_t *n_out);
 
 /* key of stored assignment i: MIN/MAX objective value, or the root id for batched roots */
 int csolve_gpu_get_solution_key(csolve_gpu_problem *p, int32_t i, int32_t *key);

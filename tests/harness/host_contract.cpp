@@ -184,6 +184,16 @@ extern "C" void hc_eval_root(const int32_t *dom_in, int32_t *out2) {
   out2[0] = v.lo; out2[1] = v.hi;
 }
 
+// unit hook for learned nogoods: returns -1 on failure, else the number of narrowed variables
+extern "C" int hc_prop_nogood(const int32_t *dom_in, int n_vars, const int32_t *lits, int n, int32_t *dom_out) {
+  std::vector<int32_t> d(dom_in, dom_in + 2 * n_vars);
+  std::vector<int> queue; std::vector<uint8_t> queued(n_vars, 0);
+  HostCx cx{d.data(), &queue, &queued};
+  bool ok = contract_nogood(cx, lits, n);
+  memcpy(dom_out, d.data(), sizeof(int32_t) * 2 * n_vars);
+  return ok ? (int)cx.props : -1;
+}
+
 extern "C" int32_t hc_sneg(int32_t a) { return sneg(a); }
 extern "C" int32_t hc_sadd(int32_t a, int32_t b) { return sadd(a, b); }
 extern "C" int32_t hc_smul(int32_t a, int32_t b) { return smul(a, b); }

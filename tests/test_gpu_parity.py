@@ -329,3 +329,42 @@ def test_exchange_callback_injects_incumbent_and_stops_any():
     r2 = p2.solve(slice_ms=1)
     p2.set_exchange(None)
     assert r2.has_solution == 0 and r2.nodes < 21000000
+
+
+def test_conflict_learning_keeps_results_and_learns_sound_nogoods():
+    """-c true on the device (src/conflict.c): identical counts / status, and every learned nogood is implied
+    by the model (adding its literals as constraints leaves no solution)."""
+    import re
+    for name, nsol in (("sat20all", 9), ("sat50all", 23)):
+        m = cb.Model(INST[name])
+        p = cb.GpuProblem(m)
+        r = p.solve(create_conflicts=True, split_target=1)   # no breadth-first phase: nogoods are learned depth-first
+        assert r.solutions == nsol                       # the reference over-counts here with -c true (SURVEY.md 8c.4)
+        assert r.conflicts > 0
+        ngs = p.nogoods()
+        assert len(ngs) == r.conflicts
+        names = m.var_names
+        checked = 0
+        for ng in ngs[:: max(1, len(ngs) // 40)]:
+            assert all(val in (0, 1) for _, val in ng) and len({v for v, _ in ng}) == len(ng)
+            text = INST[name] + "".join("%s = %d;\n" % (names[v], val) for v, val in ng)
+            try:
+                o, _ = util.Oracle(cb.Model(text)).solve_tree(0)
+                assert o.solutions == 0, (name, ng)
+            except cb.CsolveError as e:
+                assert e.code == -3                      # already infeasible at root
+            checked += 1
+        assert checked >= 5
+    # status on the decision versions, with and without the failure-driven order
+    for name, sat in (("sat50", 0), ("sat100", 1)):
+        for pf in (False, True):
+            r = cb.GpuProblem(cb.Model(INST[name])).solve(create_conflicts=True, prefer_failing=pf, split_target=1)
+            assert r.has_solution == sat
+    r = cb.GpuProblem(cb.Model(I.random_3sat(200, seed=1))).solve(create_conflicts=True, prefer_failing=True)
+    assert r.has_solution == 0 and r.conflicts > 0
+    # models on the NOT(EQ) kernels never produce a nogood (neither does the reference: CONFL 0 in BASELINE.md)
+    r = cb.GpuProblem(cb.Model(I.queens(8))).solve(create_conflicts=True)
+    assert (r.solutions, r.conflicts) == (92, 0)
+    # general kernel, non-binary values: every analysis is abandoned, results unchanged
+    r = cb.GpuProblem(cb.Model(INST["wcet"])).solve(create_conflicts=True, split_target=1)
+    assert r.best == 1560 and r.conflicts == 0 and r.conflicts_abandoned > 0

@@ -83,3 +83,24 @@ def test_propagate(case):
     # change count: every terminal is a variable here, so the count can only be >= the reference's
     if all(n in case["vars"] or case["terms"][n][0] == case["terms"][n][1] for n in names):
         assert res == case["result"]
+
+
+def test_nogood_propagation_vectors():
+    """PropagateConfl.* of the reference (test/test_propagate.c:1011-1155), value = true: the nogood
+    {A = 0, B = 1} against (A, B) domains -> expected change of B / no change"""
+    hc = util.harness_lib()
+    lits = np.array([(0 << 1) | 0, (1 << 1) | 1], np.int32)
+    cases = [
+        ([0, 0, 0, 1], [0, 0, 0, 0], 1),      # Basic: A matches, B open -> B loses 1
+        ([0, 0, 0, 0], [0, 0, 0, 0], 0),      # NonConfl: B is 0 != 1 -> nothing
+        ([0, 1, 0, 1], [0, 1, 0, 1], 0),      # TwoVars: two open variables -> nothing
+        ([1, 1, 0, 1], [1, 1, 0, 1], 0),      # A is 1 != 0 -> nothing
+        ([0, 0, 1, 1], [0, 0, 1, 1], 0),      # everything matches: NOT an error (src/propagate.c:459-471)
+        ([0, 0, 0, 5], [0, 0, 0, 5], 0),      # the recorded value sits on neither bound of B
+        ([0, 0, 1, 5], [0, 0, 2, 5], 1),      # ... on the lower bound
+    ]
+    for dom, exp, changed in cases:
+        d = np.array(dom, np.int32)
+        out = np.zeros_like(d)
+        r = hc.hc_prop_nogood(util.p32(d), 2, util.p32(lits), 2, util.p32(out))
+        assert r == changed and out.tolist() == exp, (dom, out.tolist(), r)

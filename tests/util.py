@@ -150,6 +150,7 @@ def harness_lib():
         lib.hc_node.argtypes = [I32P, C.c_int, C.c_int32, C.c_int32, I32P]
         lib.hc_leaf_true.argtypes = [I32P]
         lib.hc_node_lov.argtypes = [I32P, C.c_int, C.c_int32, I32P]
+        lib.hc_prop_nogood.argtypes = [I32P, C.c_int, I32P, C.c_int, I32P]
         lib.hc_prop_root.argtypes = [I32P, C.c_int32, C.c_int32, I32P]
         lib.hc_eval_root.argtypes = [I32P, I32P]
         for f in ("hc_sneg", "hc_sadd", "hc_smul"):
