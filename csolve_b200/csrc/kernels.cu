@@ -907,6 +907,7 @@ k_search_lov(const SearchArgs a) {
   unsigned iter = 0, last = 0, fhash = 0, amask = 0;
   int plo = 0, phi = 0;        // this lane's variable in the top frame (state before the assignment)
   uint32_t pF = 0;             // ... and its forbidden-value set (BITS)
+  uint32_t fvarF = 0;          // forbidden-value set of the top frame's branching variable (warp-uniform)
   unsigned poll = 0;
 
   bool hungry = false;
@@ -944,6 +945,7 @@ k_search_lov(const SearchArgs a) {
       if (act) dj = reinterpret_cast<const int2 *>(sf + 8)[lane];
       plo = dj.x; phi = dj.y;
       if (BITS) pF = act ? (uint32_t)sf[8 + 2 * V + lane] : 0u;
+      if (BITS) fvarF = __shfl_sync(FULL, pF, h0.x);
       var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; flo = h0.w;
       fhi = h1.x; flevel = h1.y; amask = (unsigned)h1.z; fhash = (unsigned)h1.w;
       have = true;
@@ -969,6 +971,12 @@ k_search_lov(const SearchArgs a) {
     // ---- one search node -------------------------------------------------------------------------
     const int val = step_value(flo, fhi, iter);
     iter++;
+    if (BITS && ((fvarF >> (val - vbase)) & 1u)) {
+      // the value is already forbidden by a variable that is a value (or by a constant): the node's first
+      // trim of its own variable fails (lov_trim on [val,val]); counted as a failed node without the detour
+      nodes++; cuts++;
+      continue;
+    }
     int lo = plo, hi = phi;
     if (lane == var) { lo = val; hi = val; }
     uint32_t F = pF;
@@ -1068,6 +1076,7 @@ k_search_lov(const SearchArgs a) {
         if (BITS && act) nf[8 + 2 * V + lane] = (int)F;
         amask = nmask;
         plo = lo; phi = hi; pF = F;
+        if (BITS) fvarF = __shfl_sync(FULL, F, nv);
         var = nv; flo = nlo; fhi = nhi; iter = 0; last = nlast;
         flevel = flevel + 1; fhash = chash;
         level++;
@@ -1285,6 +1294,15 @@ __device__ __forceinline__ int2 lovk_bounds(const LovK<K> &x, int v) {
   return make_int2(__shfl_sync(FULL, l, v & 31), __shfl_sync(FULL, h, v & 31));
 }
 
+// forbidden-value set of variable v (warp-uniform) from its owner lane
+template <int K>
+__device__ __forceinline__ uint32_t lovk_F(const LovK<K> &x, int v) {
+  uint32_t f = x.F[0];
+#pragma unroll
+  for (int q = 1; q < K; q++) if ((v >> 5) == q) f = x.F[q];
+  return __shfl_sync(FULL, f, v & 31);
+}
+
 template <bool EXPAND, int K>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, 3)
 k_search_lovk(const SearchArgs a) {
@@ -1305,6 +1323,7 @@ k_search_lovk(const SearchArgs a) {
   int var = 0, flo = 0, fhi = 0, flevel = 0, ftag = 0;
   unsigned iter = 0, last = 0, fhash = 0;
   uint32_t amask[K];
+  uint32_t fvarF = 0;              // forbidden-value set of the top frame's branching variable (warp-uniform)
   LovK<K> P;                       // top frame: state before this level's assignment
 #pragma unroll
   for (int q = 0; q < K; q++) { amask[q] = 0; P.lo[q] = P.hi[q] = m.lov_vbase; P.F[q] = 0; }
@@ -1342,6 +1361,7 @@ k_search_lovk(const SearchArgs a) {
 #pragma unroll
       for (int q = 0; q < K; q++) amask[q] = (uint32_t)__ldcg(&f[FR_MASK + q]);
       lovk_load<K>(m, f, lane, P);
+      fvarF = lovk_F<K>(P, h0.x);
       var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; flo = h0.w;
       fhi = h1.x; flevel = h1.y; ftag = h1.z; fhash = (unsigned)h1.w;
       have = true;
@@ -1365,6 +1385,10 @@ k_search_lovk(const SearchArgs a) {
     // ---- one search node -------------------------------------------------------------------------
     const int val = step_value(flo, fhi, iter);
     iter++;
+    if ((fvarF >> (val - m.lov_vbase)) & 1u) {      // already forbidden: a failed node (see k_search_lov)
+      nodes++; cuts++;
+      continue;
+    }
     LovK<K> x = P;
     uint32_t pend[K];
 #pragma unroll
@@ -1457,6 +1481,7 @@ k_search_lovk(const SearchArgs a) {
 #pragma unroll
           for (int q = 0; q < K; q++) amask[q] = am[q];
           P = x;
+          fvarF = lovk_F<K>(x, nv);
           var = nv; flo = nb.x; fhi = nb.y; iter = 0; last = nlast;
           flevel = lev; fhash = hsh;
           level++;
