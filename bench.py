@@ -156,6 +156,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, workload):
+    """real DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum), None when there is no capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("kernel") == kernel and t.get("workload") == workload:
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -239,6 +252,7 @@ def run_ours(args):
         bytes_per_node = 2 * (8 * V + 16)                       # parent domains + header in, child out
         peak, peak_src = measured_peak_gbs()
         achieved = (my_nodes * bytes_per_node) / (search_ms / 1000.0) / 1e9 if search_ms > 0 else 0.0
+        kernel = "k_search_lov<false,true>" if args.queens <= 32 else "k_search<false>"
         line = {
             "metric": METRIC, "value": tot_nodes / (dev_ms / 1000.0), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -253,7 +267,7 @@ def run_ours(args):
                     "path": "Model(text) -> GpuProblem -> solve() through libcsolve_b200.so, host buffers"},
             "gpu_launches": tot_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "k_search_lov<false,true>" if args.queens <= 32 else "k_search<false>",
+                         "frac": achieved / peak, "traffic": measured_traffic(kernel, "queens%d-all" % V), "kernel": kernel,
                          "bytes_per_node": bytes_per_node, "peak_source": peak_src,
                          "note": "rank 0; algorithmic bytes = nodes x 2 x (8V+16); the DFS stacks live in shared memory during a slice, so real DRAM traffic is far below this nominal figure (DESIGN.md)"},
         }
