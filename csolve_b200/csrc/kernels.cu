@@ -809,7 +809,7 @@ __device__ __forceinline__ bool lov_fixpoint(const LovTables &t, int V, bool has
       if (bl | bh) chm |= 1u << i;
     }
     changed |= chm;
-    props += __popc(chm);
+    props += (chm >> lane) & 1u;                       // per lane; summed over the warp when the counters are flushed
     visits += (unsigned)V;
   }
   return true;
@@ -830,7 +830,7 @@ __device__ __forceinline__ bool lov_fixpoint_bits(const LovTables &t, int V, int
     const bool alive = lov_trim(F, vbase, lo, hi);
     if (__any_sync(FULL, !alive)) return false;
     pend |= __ballot_sync(FULL, !was && lo == hi);
-    props += __popc(__ballot_sync(FULL, lo != olo || hi != ohi));
+    props += (lo != olo || hi != ohi) ? 1u : 0u;      // per lane; summed over the warp when the counters are flushed
     visits += (unsigned)V;
   }
   return true;
@@ -845,10 +845,18 @@ __device__ __forceinline__ uint32_t lov_rebuild_F(const LovTables &t, int V, int
   return F;
 }
 
-// shared-memory frame of the LOV kernel: 8 header words (var, iter, last, lo | hi, level, amask, hash)
-// followed by the 2 * V domain words. The warp's whole DFS stack lives in shared memory during a
-// slice; it is loaded from / parked to the HBM frames (device_model.h layout) at the slice boundaries,
-// where k_rebalance and the host see it.
+// Shared-memory frame of the LOV kernel (private to it; converted at the HBM boundary by frame_in / frame_out):
+//   word 0  cursor   next value of the branching variable to try        word 4  amask  variables that have a level
+//   word 1  rem      values left: the frame owns [cursor, cursor+rem)   word 5  hash   path hash (rank partition)
+//   word 2  var      branching variable                                 word 6,7 unused
+//   word 3  level
+// followed by the 2 * V domain words and the V forbidden-value sets. Values are tried in ASCENDING order here
+// (the reference alternates lo, hi, lo+1, ... -- src/csolve.c:331-338 -- which matters only for which solution ANY
+// meets first; counts are order-free), so the untried values of a level always form one interval and whole runs
+// of values that are already forbidden are counted as failed nodes in one step (one bit scan instead of one loop
+// iteration each). The warp's whole DFS stack lives in shared memory during a slice; it is loaded from / parked
+// to the HBM frames (device_model.h layout, iter = 0 over the remaining interval) at the slice boundaries, where
+// k_rebalance and the host see it.
 __device__ __forceinline__ int lov_sframe_words(int V) { return (8 + 3 * V + 3) & ~3; }   // header, domains, value sets; 16-byte aligned
 
 template <bool EXPAND, bool BITS>
@@ -874,12 +882,22 @@ k_search_lov(const SearchArgs a) {
 
   int level = a.wstate[gw].level, base = a.wstate[gw].base;
   unsigned long long nodes = 0, cuts = 0, sols = 0;
+  unsigned n32 = 0, c32 = 0;   // nodes / cuts since the last flush into the 64-bit counters
   unsigned props = 0, visits = 0;
   const long long t0 = clock64();
 
-  // HBM frame -> shared frame
+  // HBM frame -> shared frame. The untried values of an alternating enumeration at iteration `it` are the
+  // interval [lo + ceil(it / 2), hi - floor(it / 2)]: la - it + 1 values.
   auto frame_in = [&](const int *g, int *sf) {
-    if (lane < 8) sf[lane] = lane == 6 ? __ldcg(&g[FR_MASK]) : __ldcg(&g[lane]);
+    if (lane == 0) {
+      const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(g));
+      const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(g) + 1);
+      const int mk = __ldcg(&g[FR_MASK]);
+      const unsigned it = (unsigned)h0.y, la = (unsigned)h0.z;
+      const bool left = it <= la;
+      reinterpret_cast<int4 *>(sf)[0] = make_int4(left ? (int)((unsigned)h0.w + ((it + 1) >> 1)) : h0.w, left ? (int)(la - it + 1u) : 0, h0.x, h1.y);
+      reinterpret_cast<int2 *>(sf)[2] = make_int2(mk, h1.w);
+    }
     if (act) reinterpret_cast<int2 *>(sf + 8)[lane] = __ldcg(reinterpret_cast<const int2 *>(g + dofs) + lane);
     if (BITS) {
       __syncwarp();
@@ -887,12 +905,15 @@ k_search_lov(const SearchArgs a) {
       if (act) sf[8 + 2 * V + lane] = (int)F;
     }
   };
-  // shared frame -> HBM frame (best_seen is unused by pure NOT(EQ) networks)
+  // shared frame -> HBM frame (best_seen is unused by pure NOT(EQ) networks); an exhausted frame is iter 1 > last 0
   auto frame_out = [&](const int *sf, int *g) {
-    if (lane < 8) {
-      int w = sf[lane];
-      if (lane == 6) { __stcg(&g[FR_MASK], w); w = 0; }
-      __stcg(&g[lane], w);
+    if (lane == 0) {
+      const int4 s0 = reinterpret_cast<const int4 *>(sf)[0];
+      const int2 s1 = reinterpret_cast<const int2 *>(sf)[2];
+      const unsigned rm = (unsigned)s0.y;
+      __stcg(reinterpret_cast<int4 *>(g), make_int4(s0.z, rm ? 0 : 1, rm ? (int)(rm - 1u) : 0, s0.x));
+      __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(rm ? (int)((unsigned)s0.x + rm - 1u) : s0.x, s0.w, 0, s1.y));
+      __stcg(&g[FR_MASK], s1.x);
     }
     if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, reinterpret_cast<const int2 *>(sf + 8)[lane]);
   };
@@ -903,8 +924,9 @@ k_search_lov(const SearchArgs a) {
   }
 
   bool have = false;
-  int var = 0, flo = 0, fhi = 0, flevel = 0;
-  unsigned iter = 0, last = 0, fhash = 0, amask = 0;
+  int var = 0, cur = 0, flevel = 0;   // top frame: branching variable, cursor, level
+  unsigned rem = 0;                   // ... values left: [cur, cur + rem)
+  unsigned fhash = 0, amask = 0;
   int plo = 0, phi = 0;        // this lane's variable in the top frame (state before the assignment)
   uint32_t pF = 0;             // ... and its forbidden-value set (BITS)
   uint32_t fvarF = 0;          // forbidden-value set of the top frame's branching variable (warp-uniform)
@@ -940,52 +962,66 @@ k_search_lov(const SearchArgs a) {
     int *sf = sst + level * sfw;
     if (!have) {
       const int4 h0 = reinterpret_cast<const int4 *>(sf)[0];
-      const int4 h1 = reinterpret_cast<const int4 *>(sf)[1];
+      const int2 h1 = reinterpret_cast<const int2 *>(sf)[2];
       int2 dj = make_int2(vbase, vbase);       // idle lanes hold a harmless one-value domain
       if (act) dj = reinterpret_cast<const int2 *>(sf + 8)[lane];
       plo = dj.x; phi = dj.y;
       if (BITS) pF = act ? (uint32_t)sf[8 + 2 * V + lane] : 0u;
-      if (BITS) fvarF = __shfl_sync(FULL, pF, h0.x);
-      var = h0.x; iter = (unsigned)h0.y; last = (unsigned)h0.z; flo = h0.w;
-      fhi = h1.x; flevel = h1.y; amask = (unsigned)h1.z; fhash = (unsigned)h1.w;
+      if (BITS) fvarF = __shfl_sync(FULL, pF, h0.z);
+      cur = h0.x; rem = (unsigned)h0.y; var = h0.z; flevel = h0.w;
+      amask = (unsigned)h1.x; fhash = (unsigned)h1.y;
       have = true;
+      if (EXPAND && rem > (unsigned)a.expand_branch_max) {
+        // too many values to enumerate breadth-first: pass the frame through unchanged
+        int slot = 0;
+        if (lane == 0) { slot = atomicAdd(&ctl->out_count, 1); atomicAdd(&ctl->passed, 1); }
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot < a.out_cap) frame_out(sf, a.items_out + (size_t)slot * fw);
+        else if (lane == 0) atomicAdd(&ctl->out_dropped, 1);
+        level = base - 1;
+        have = false;
+        continue;
+      }
     }
 
-    if (EXPAND && last >= (unsigned)a.expand_branch_max) {
-      int slot = 0;
-      if (lane == 0) { slot = atomicAdd(&ctl->out_count, 1); atomicAdd(&ctl->passed, 1); }
-      slot = __shfl_sync(FULL, slot, 0);
-      if (slot < a.out_cap) frame_out(sf, a.items_out + (size_t)slot * fw);
-      else if (lane == 0) atomicAdd(&ctl->out_dropped, 1);
-      level = base - 1;
-      have = false;
-      continue;
+    // ---- next value of the level -------------------------------------------------------------------
+    int val = cur;
+    if (BITS) {
+      // values of [cur, cur + rem) the fixed variables (and constants) do not forbid yet; a forbidden value's node
+      // fails at the first trim of its own variable (lov_trim on [val, val]): counted, not executed
+      const unsigned span = rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u);
+      const uint32_t avail = rem ? (~fvarF & (span << (cur - vbase))) : 0u;
+      if (avail == 0u) {
+        n32 += rem; c32 += rem;
+        level--;
+        have = false;
+        continue;
+      }
+      const int b = __ffs((int)avail) - 1;
+      const unsigned skipped = (unsigned)(b - (cur - vbase));
+      n32 += skipped; c32 += skipped;
+      val = vbase + b;
+      rem -= skipped + 1u;
+    } else {
+      if (rem == 0u) {
+        level--;
+        have = false;
+        continue;
+      }
+      rem--;
     }
-
-    if (iter > last) {
-      level--;
-      have = false;
-      continue;
-    }
+    cur = val + 1;
 
     // ---- one search node -------------------------------------------------------------------------
-    const int val = step_value(flo, fhi, iter);
-    iter++;
-    if (BITS && ((fvarF >> (val - vbase)) & 1u)) {
-      // the value is already forbidden by a variable that is a value (or by a constant): the node's first
-      // trim of its own variable fails (lov_trim on [val,val]); counted as a failed node without the detour
-      nodes++; cuts++;
-      continue;
-    }
     int lo = plo, hi = phi;
     if (lane == var) { lo = val; hi = val; }
     uint32_t F = pF;
     const bool ok = BITS ? lov_fixpoint_bits(T, V, vbase, lane, lo, hi, F, 1u << var, props, visits)
                          : lov_fixpoint(T, V, has_consts, lane, lo, hi, 1u << var, props, visits);
-    nodes++;
+    n32++;
 
     if (!ok) {
-      cuts++;
+      c32++;
     } else if (flevel + 1 == V) {
       // leaf: is_true(eval(root)) -- every clause x_i + c != x_j / x_i != c holds on the assignment
       bool good = lo == hi;
@@ -1045,18 +1081,19 @@ k_search_lov(const SearchArgs a) {
         }
         nv = bestv;
       }
-      const unsigned chash = mix_hash(fhash, (unsigned)var, (unsigned)val);
       const int nlo = __shfl_sync(FULL, lo, nv), nhi = __shfl_sync(FULL, hi, nv);
-      const unsigned nlast = (unsigned)nhi - (unsigned)nlo;
+      const unsigned nrem = (unsigned)nhi - (unsigned)nlo + 1u;
       const unsigned nmask = amask | (1u << var);
       if (EXPAND) {
+        // the path hash decides which rank searches the frame (only frames of the expanded frontier are partitioned)
+        const unsigned chash = mix_hash(fhash, (unsigned)var, (unsigned)val);
         int slot = 0;
         if (lane == 0) slot = atomicAdd(&ctl->out_count, 1);
         slot = __shfl_sync(FULL, slot, 0);
         if (slot < a.out_cap) {
           int *g = a.items_out + (size_t)slot * fw;
           if (lane == 0) {
-            __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)nlast, nlo));
+            __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)(nrem - 1u), nlo));
             __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nhi, flevel + 1, 0, (int)chash));
             __stcg(&g[FR_MASK], (int)nmask);
           }
@@ -1068,70 +1105,74 @@ k_search_lov(const SearchArgs a) {
         // push: everything stays in shared memory / registers
         int *nf = sf + sfw;
         if (lane == 0) {
-          sf[FR_ITER] = (int)iter;
-          reinterpret_cast<int4 *>(nf)[0] = make_int4(nv, 0, (int)nlast, nlo);
-          reinterpret_cast<int4 *>(nf)[1] = make_int4(nhi, flevel + 1, (int)nmask, (int)chash);
+          reinterpret_cast<int2 *>(sf)[0] = make_int2(cur, (int)rem);
+          reinterpret_cast<int4 *>(nf)[0] = make_int4(nlo, (int)nrem, nv, flevel + 1);
+          reinterpret_cast<int2 *>(nf)[2] = make_int2((int)nmask, (int)fhash);
         }
         if (act) reinterpret_cast<int2 *>(nf + 8)[lane] = make_int2(lo, hi);
         if (BITS && act) nf[8 + 2 * V + lane] = (int)F;
         amask = nmask;
         plo = lo; phi = hi; pF = F;
         if (BITS) fvarF = __shfl_sync(FULL, F, nv);
-        var = nv; flo = nlo; fhi = nhi; iter = 0; last = nlast;
-        flevel = flevel + 1; fhash = chash;
+        var = nv; cur = nlo; rem = nrem;
+        flevel = flevel + 1;
         level++;
         __syncwarp();
       }
     }
 
     if (!EXPAND && (++poll & (POLL_NODES - 1)) == 0) {
+      nodes += n32; cuts += c32; n32 = 0; c32 = 0;
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
       }
       if (level >= base && donation_wanted(a, lane)) {
-        // shallowest frame with at least two untried values (the top frame's iteration state is in registers)
-        int L = -1;
-        unsigned d_iter = 0; int d_lo = 0, d_hi = 0;
+        // shallowest frame with at least two untried values (the top frame's cursor is in registers)
+        int L = -1, d_cur = 0;
+        unsigned d_rem = 0;
         if (lane == 0) {
           for (int q = base; q <= level; ++q) {
             const int *qf = sst + q * sfw;
-            const unsigned it2 = q == level ? iter : (unsigned)qf[FR_ITER];
-            const unsigned la2 = (unsigned)qf[FR_LAST];
-            if (it2 <= la2 && la2 - it2 >= 1) { L = q; d_iter = it2; d_lo = qf[FR_LO]; d_hi = qf[FR_HI]; break; }
+            const unsigned rm = q == level ? rem : (unsigned)qf[1];
+            if (rm >= 2u) { L = q; d_rem = rm; d_cur = q == level ? cur : qf[0]; break; }
           }
         }
         L = __shfl_sync(FULL, L, 0);
         if (L >= 0) {
-          d_iter = __shfl_sync(FULL, d_iter, 0); d_lo = __shfl_sync(FULL, d_lo, 0); d_hi = __shfl_sync(FULL, d_hi, 0);
-          const long long ua = (long long)d_lo + ((d_iter + 1) >> 1), ub = (long long)d_hi - (d_iter >> 1);
-          const long long mid = ua + (ub - ua) / 2;
+          d_cur = __shfl_sync(FULL, d_cur, 0); d_rem = __shfl_sync(FULL, d_rem, 0);
+          // this warp keeps the lower half [d_cur, d_cur + keep), the donated frame owns the rest
+          const unsigned keep = (d_rem - 1u) / 2u + 1u, give = d_rem - keep;
+          const int glo = (int)((unsigned)d_cur + keep);
           const int slot = reserve_slot(a, lane);
           int *own = sst + L * sfw;
           int *g = a.pool + (size_t)slot * fw;
           frame_out(own, g);
           __syncwarp();
           if (lane == 0) {
-            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
-            __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
-            own[FR_ITER] = 0; own[FR_LO] = (int)ua; own[FR_HI] = (int)mid; own[FR_LAST] = (int)(unsigned)(mid - ua);
+            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], glo); __stcg(&g[FR_HI], (int)((unsigned)glo + give - 1u));
+            __stcg(&g[FR_LAST], (int)(give - 1u));
+            own[0] = d_cur; own[1] = (int)keep;
             __threadfence();
             __stcg(&a.ready[slot], 1);
           }
-          if (L == level) { iter = 0; flo = (int)ua; fhi = (int)mid; last = (unsigned)(mid - ua); }
+          if (L == level) rem = keep;
           __syncwarp();
         }
       }
     }
   }
+  nodes += n32; cuts += c32;
 
   if (!EXPAND && level >= base) {
     // park: the stack goes back to HBM for k_rebalance / the next slice
-    if (have && lane == 0) sst[level * sfw + FR_ITER] = (int)iter;
+    if (have && lane == 0) { sst[level * sfw] = cur; sst[level * sfw + 1] = (int)rem; }
     __syncwarp();
     for (int L = base; L <= level; ++L) frame_out(sst + L * sfw, stack + (size_t)L * fw);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) props += __shfl_xor_sync(FULL, props, o);
   if (lane == 0) {
     a.wstate[gw].level = level;
     a.wstate[gw].base = base;
