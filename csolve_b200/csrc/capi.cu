@@ -231,6 +231,10 @@ extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes
 // ---- search ------------------------------------------------------------------------------------
 namespace {
 
+// slots behind the expanded root frontier that stay free for donated frames (a ticket queue: one slot per waiting
+// warp plus the frames delivered ahead of their tickets)
+int ring_min_frames(int n_warps) { return 2 * n_warps + 1024; }
+
 int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots, bool learn) {
   DevModel m = p->dev;
   if (batch) m.lov = 0;
@@ -258,7 +262,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
   // frontier pools: room for the split target times the largest branching the expansion may apply
   int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 128;
   target = std::max(target, n_roots);
-  int cap = std::max(target * 4, 1 << 16);
+  int cap = std::max(target * 4, 1 << 16) + ring_min_frames(p->n_warps);
   const size_t max_bytes = (size_t)2 << 30;   // per pool
   while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
   if (cap > p->pool_cap) {
@@ -324,7 +328,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   memset(&ctl, 0, sizeof(ctl));
   ctl.best = m.objective == CSOLVE_OBJ_MIN ? INT32_MAX : (m.objective == CSOLVE_OBJ_MAX ? INT32_MIN : 0);   // src/objective.c:38-50
   CUDA_TRY(cudaMemsetAsync(p->wcount, 0, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long), st));
-  std::vector<WarpState> ws(p->n_warps, WarpState{-1, 0});
+  std::vector<WarpState> ws(p->n_warps, WarpState{-1, 0, 0, 0u});
   CUDA_TRY(cudaMemcpyAsync(p->wstate, ws.data(), ws.size() * sizeof(WarpState), cudaMemcpyHostToDevice, st));
 
   int32_t *d_roots = nullptr; unsigned char *d_rfail = nullptr; unsigned int *d_rsol = nullptr; int32_t *d_nout = nullptr;
@@ -394,7 +398,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     const int before = n_items;
     // would another level overflow the pool? domains only shrink, so a frame has at most as many
     // children as the largest root domain (and never more than expand_branch_max)
-    if ((long long)n_items * max_branch > p->pool_cap) break;
+    if ((long long)n_items * max_branch > p->pool_cap - ring_min_frames(p->n_warps)) break;
     a.items = pin; a.items_out = pout; a.frozen_best = ctl.best;
     ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.idle = 0; ctl.passed = 0;
     CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
@@ -431,7 +435,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   // shared pool ring of the depth-first phase: the expanded frontier occupies the first n_items slots
   a.pool = pin; a.pool_cap = p->pool_cap; a.ready = p->ready; a.n_initial = n_items;
   CUDA_TRY(cudaMemsetAsync(p->ready, 0, (size_t)p->pool_cap * sizeof(int32_t), st));
-  if (p->pool_cap - n_items < 1024) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
+  if (p->pool_cap - n_items < ring_min_frames(p->n_warps)) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
   a.gprio = d_gprio;     // the breadth-first expansion above stays deterministic (identical on every rank)
   if (learn) a.ng = p->ng;
   ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.idle = 0; ctl.busy = 0; ctl.hungry = 0;
@@ -486,6 +490,34 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   CUDA_TRY(cudaMemcpyAsync(tot, p->totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (getenv("CSOLVE_DEBUG")) {
+    // load-balance diagnostics of the depth-first phase
+    std::vector<unsigned long long> wc((size_t)p->n_warps * CNT_WIDTH);
+    CUDA_TRY(cudaMemcpy(wc.data(), p->wcount, wc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    double wait = 0, claims = 0, lw = 0, lw_max = 0, lw_min = 1e30, nmax = 0;
+    for (int w = 0; w < p->n_warps; w++) {
+      const unsigned long long *c = &wc[(size_t)w * CNT_WIDTH];
+      wait += (double)c[CNT_WAIT]; claims += (double)c[CNT_CLAIMS];
+      const double l = (double)c[CNT_LASTWORK];
+      lw += l; lw_max = std::max(lw_max, l); lw_min = std::min(lw_min, l); nmax = std::max(nmax, (double)c[CNT_NODES]);
+    }
+    const double khz = (double)g_clock_khz;
+    fprintf(stderr, "[csolve] depth-first phase: %llu slices, %d warps, per warp: waited %.3f ms, %.1f claims, last node at %.3f ms "
+                    "(min %.3f, max %.3f), most nodes on one warp %.0f (avg %.0f), %d frames donated\n", (unsigned long long)slices, p->n_warps,
+            wait / p->n_warps / khz, claims / p->n_warps, lw / p->n_warps / khz, lw_min / khz, lw_max / khz, nmax,
+            (double)tot[CNT_NODES] / p->n_warps, ctl.item_count);
+    fprintf(stderr, "[csolve]   polls %llu, donation wanted %llu, donated %llu\n", tot[CNT_POLLS], tot[CNT_WANTED], tot[CNT_DONATED]);
+    {
+      std::vector<double> lws, wts;
+      for (int w = 0; w < p->n_warps; w++) { lws.push_back((double)wc[(size_t)w * CNT_WIDTH + CNT_LASTWORK] / khz); wts.push_back((double)wc[(size_t)w * CNT_WIDTH + CNT_WAIT] / khz); }
+      std::sort(lws.begin(), lws.end()); std::sort(wts.begin(), wts.end());
+      fprintf(stderr, "[csolve]   last-node deciles:");
+      for (int d = 0; d <= 10; d++) fprintf(stderr, " %.3f", lws[std::min<size_t>(lws.size() - 1, lws.size() * d / 10)]);
+      fprintf(stderr, "  p99 %.3f p99.9 %.3f\n[csolve]   waited deciles:", lws[lws.size() * 99 / 100], lws[lws.size() * 999 / 1000]);
+      for (int d = 0; d <= 10; d++) fprintf(stderr, " %.3f", wts[std::min<size_t>(wts.size() - 1, wts.size() * d / 10)]);
+      fprintf(stderr, "\n");
+    }
+  }
   p->n_stored = std::min(ctl.n_stored, p->sol_cap);
   p->sol_host.resize((size_t)p->n_stored * (V + 1));
   if (p->n_stored > 0) {

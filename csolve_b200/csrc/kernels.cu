@@ -368,76 +368,141 @@ __device__ __forceinline__ void store_solution(const SearchArgs &a, const WarpSm
 
 
 // ---- shared frame pool (depth-first phase) ---------------------------------------------------------------
-// The frontier pool is a ring: head = ctl->item_next, tail = ctl->item_count, ready[slot] = 1 once a frame is
-// completely written. Idle warps wait here for frames; busy warps donate half of the untried interval of their
-// shallowest splittable frame whenever somebody is waiting (the bisection worker_spawn does with fork(),
-// src/csolve.c:121-149) -- so load balancing does not need the kernel to end.
+// Work comes from two places.
+// (1) The expanded root frontier (the first n_initial pool entries): static, claimed in CHUNKS with one atomicAdd --
+//     guided self-scheduling: a chunk is 1/4 of an even share of what is left, at most 32 frames, so the atomics are
+//     few while the frontier is long and single frames are handed out when it runs out; with a rank partition every
+//     lane looks at one frame of the chunk and a ballot keeps the ones whose path hash maps to this rank.
+// (2) Behind it the pool is a ring of DONATED frames run as a ticket queue: a warp that ran dry takes a ticket
+//     (fetch-and-add on ctl->item_next) and waits for ITS slot's ready flag -- a private address, so thousands of
+//     waiters do not contend; a busy warp that sees unserved tickets (item_next > item_count) takes the next one to
+//     serve (fetch-and-add on ctl->item_count), writes the frame into that slot and publishes it. Frames are the
+//     shallowest untried work of the donor's stack (the bisection worker_spawn does with fork(),
+//     src/csolve.c:121-149). Neither side retries on a shared line: a head claimed with atomicCAS serialised the
+//     hand-off at about one frame per microsecond (measured), which was the whole tail of a search.
+//     ready[slot]: 0 free, 1 frame present, -1 the ticket's holder left at a slice end (the donor that draws this
+//     ticket takes another one; k_rebalance clears what is left between slices).
 // Returns the claimed slot, or -1 when the warp has to leave the kernel (slice end / stop / nothing left anywhere).
-__device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &hungry) {
+struct Claim {
+  int base; unsigned mask;     // claimed, not yet searched frames of the root frontier (bit b = frame base + b)
+  bool drained;                // the root frontier has been handed out completely
+};
+
+__device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &hungry, Claim &cl, int *blk_hungry) {
+  if (cl.mask) {
+    const int b = __ffs((int)cl.mask) - 1;
+    cl.mask &= cl.mask - 1;
+    return cl.base + b;
+  }
   SearchCtl *ctl = a.ctl;
   const int fw = a.m.frame_words;
   const int ring = a.pool_cap - a.n_initial;       // donated frames live in the slots behind the root frontier
   int slot = -1;
-  if (lane == 0) {
-    for (;;) {
-      if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) { slot = -1; break; }
-      // 1. the expanded root frontier: static, claimed with a plain atomicAdd (no contention retries)
-      if (*reinterpret_cast<volatile int *>(&ctl->init_next) < a.n_initial) {
-        const int it = atomicAdd(&ctl->init_next, 1);
-        if (it < a.n_initial) {
-          if (a.part_count > 1 &&
-              (unsigned)__ldcg(&a.pool[(size_t)it * fw + 7]) % (unsigned)a.part_count != (unsigned)a.part_rank) continue;
-          slot = it;
-          break;
+  int tslot = -1;                                  // lane 0: slot of the ticket this warp holds
+  unsigned spins = 0, nap = 200;
+  for (;;) {
+    // code: >= 0 ring slot claimed, -1 leave the kernel, -2 nothing yet (retry), -3 the root frontier is drained
+    int code = -2, it = 0, n = 0;
+    if (lane == 0) {
+      if (tslot < 0 && (spins & 7u) == 0u && *reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) {
+        code = -1;
+      } else if (!cl.drained) {
+        const int nx = *reinterpret_cast<volatile int *>(&ctl->init_next);
+        if (nx < a.n_initial) {
+          n = min(32, max(min(a.part_count, 32), (a.n_initial - nx) / (a.n_warps * 4)));
+          it = atomicAdd(&ctl->init_next, n);
+          if (it >= a.n_initial) n = 0;
         }
-        continue;
-      }
-      // 2. the ring of donated frames
-      const int h = *reinterpret_cast<volatile int *>(&ctl->item_next);
-      const int t = *reinterpret_cast<volatile int *>(&ctl->item_count);
-      if (t - h > 0) {
-        const int s = a.n_initial + (int)((unsigned)h % (unsigned)ring);
-        if (*reinterpret_cast<volatile int *>(&a.ready[s]) == 1 && atomicCAS(&ctl->item_next, h, h + 1) == h) {
-          slot = s;
-          break;
+        if (n == 0) code = -3;
+      } else {
+        if (tslot < 0) {
+          const int ticket = atomicAdd(&ctl->item_next, 1);
+          tslot = a.n_initial + (int)((unsigned)ticket % (unsigned)ring);
+          if (!hungry) { hungry = true; atomicAdd(&ctl->hungry, 1); atomicAdd(blk_hungry, 1); }
         }
-        continue;
+        if (*reinterpret_cast<volatile int *>(&a.ready[tslot]) == 1) {
+          code = tslot;
+        } else {
+          bool leave = false;
+          if ((spins & 3u) == 3u) {
+            if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) leave = true;
+            else if (*reinterpret_cast<volatile int *>(&ctl->hungry) >= a.n_warps) {
+              atomicMax(&ctl->signal, SIG_SLICE_END);    // every warp is waiting: nothing left anywhere
+              leave = true;
+            }
+          }
+          if (leave) {
+            // give the ticket back -- unless its frame arrived in the meantime
+            code = atomicCAS(&a.ready[tslot], 0, -1) == 1 ? tslot : -1;
+          } else {
+            __nanosleep(nap);
+            nap = min(nap * 2u, 3200u);
+          }
+        }
       }
-      if (!hungry) { hungry = true; atomicAdd(&ctl->hungry, 1); }
-      if (*reinterpret_cast<volatile int *>(&ctl->hungry) >= a.n_warps) {
-        atomicMax(&ctl->signal, SIG_SLICE_END);    // every warp is waiting and the pool is empty: nothing left
-        slot = -1;
+      spins++;
+    }
+    code = __shfl_sync(FULL, code, 0);
+    if (code == -1) break;
+    if (code >= 0) { slot = code; break; }
+    if (code == -3) { cl.drained = true; continue; }
+    n = __shfl_sync(FULL, n, 0);
+    if (n > 0) {
+      it = __shfl_sync(FULL, it, 0);
+      const int idx = it + lane;
+      bool mine = lane < n && idx < a.n_initial;
+      if (mine && a.part_count > 1)
+        mine = (unsigned)__ldcg(&a.pool[(size_t)idx * fw + 7]) % (unsigned)a.part_count == (unsigned)a.part_rank;
+      const unsigned mk = __ballot_sync(FULL, mine);
+      if (mk) {
+        cl.base = it;
+        cl.mask = mk & (mk - 1);
+        slot = it + __ffs((int)mk) - 1;
         break;
       }
-      __nanosleep(500);
     }
-    if (slot >= 0 && hungry) { hungry = false; atomicSub(&ctl->hungry, 1); }
   }
-  return __shfl_sync(FULL, slot, 0);
+  if (lane == 0 && slot >= 0 && hungry) { hungry = false; atomicSub(&ctl->hungry, 1); atomicSub(blk_hungry, 1); }
+  return slot;
 }
 
 // should this warp donate now?  (lane 0 reads the control block; every lane gets the answer)
 __device__ __forceinline__ bool donation_wanted(const SearchArgs &a, int lane) {
   int want = 0;
   if (lane == 0) {
-    const int hungry = *reinterpret_cast<volatile int *>(&a.ctl->hungry);
-    if (hungry > 0) {
-      const int backlog = *reinterpret_cast<volatile int *>(&a.ctl->item_count) - *reinterpret_cast<volatile int *>(&a.ctl->item_next);
-      want = backlog < hungry && backlog < (a.pool_cap - a.n_initial) / 2;
-    }
+    // tickets taken by waiting warps that no donor has picked up yet
+    want = *reinterpret_cast<volatile int *>(&a.ctl->item_next) - *reinterpret_cast<volatile int *>(&a.ctl->item_count) > 0;
   }
   return __shfl_sync(FULL, want, 0) != 0;
 }
 
-// reserve a pool slot for a donated frame (lane 0), wait until its previous tenant has been copied out
+// take the next ticket to serve (lane 0); its slot must be free: wait while the previous lap's frame is still being
+// copied out, skip tickets whose holder left
 __device__ __forceinline__ int reserve_slot(const SearchArgs &a, int lane) {
   int s = 0;
   if (lane == 0) {
-    const int t = atomicAdd(&a.ctl->item_count, 1);
-    s = a.n_initial + (int)((unsigned)t % (unsigned)(a.pool_cap - a.n_initial));
-    while (*reinterpret_cast<volatile int *>(&a.ready[s]) != 0) __nanosleep(100);
+    for (;;) {
+      const int t = atomicAdd(&a.ctl->item_count, 1);
+      s = a.n_initial + (int)((unsigned)t % (unsigned)(a.pool_cap - a.n_initial));
+      int r;
+      while ((r = *reinterpret_cast<volatile int *>(&a.ready[s])) == 1) __nanosleep(100);
+      if (r == 0) break;
+      __stcg(&a.ready[s], 0);       // abandoned ticket: nobody waits here any more
+    }
   }
   return __shfl_sync(FULL, s, 0);
+}
+
+// make the frame written to `slot` visible to the ticket's holder (lane 0; every lane gets the answer).
+// false: the holder left while the frame was being written -- the caller donates again to another ticket.
+__device__ __forceinline__ bool publish_slot(const SearchArgs &a, int lane, int slot) {
+  int ok = 1;
+  if (lane == 0) {
+    __threadfence();
+    ok = atomicCAS(&a.ready[slot], 0, 1) == 0;
+    if (!ok) __stcg(&a.ready[slot], 0);
+  }
+  return __shfl_sync(FULL, ok, 0) != 0;
 }
 
 // ---- the search kernel ----------------------------------------------------------------------------
@@ -451,6 +516,9 @@ k_search(const SearchArgs a) {
   const int wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
   const int4 *wrec; const int *wptr;
+  __shared__ int s_blk_hungry;       // warps of this block waiting for a frame: their neighbours poll for donations faster
+  if (threadIdx.x == 0) s_blk_hungry = 0;
+  __syncthreads();
   stage_table(m, smem, wrec, wptr);
   if (gw >= a.n_warps) return;
   // per-warp regions are padded to 16 bytes so the int2 staging copies stay aligned
@@ -463,6 +531,7 @@ k_search(const SearchArgs a) {
   SearchCtl *ctl = a.ctl;
 
   int level = a.wstate[gw].level, base = a.wstate[gw].base;
+  Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
   unsigned long long nodes = 0, cuts = 0, sols = 0, refresh = 0;
   unsigned props = 0, visits = 0;
   const long long t0 = clock64();
@@ -487,7 +556,7 @@ k_search(const SearchArgs a) {
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
       } else {
-        const int slot = claim_frame(a, lane, hungry);
+        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry);
         if (slot < 0) break;
         src = a.pool + (size_t)slot * fw;
       }
@@ -689,7 +758,7 @@ k_search(const SearchArgs a) {
     // every few nodes: has a slice end / stop been requested, is the time slice over, is somebody waiting for work?
     // (general-kernel nodes are long, so the control block is polled often; an L2 round trip per node would
     // dominate the short nodes of the lane-owns-variable kernel, which polls every POLL_NODES nodes)
-    if (!EXPAND && (++poll & 3u) == 0) {
+    if (!EXPAND && ((++poll & 3u) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -707,27 +776,34 @@ k_search(const SearchArgs a) {
               const int4 g0 = __ldcg(reinterpret_cast<const int4 *>(stack + (size_t)q * fw));
               it2 = (unsigned)g0.y; la2 = (unsigned)g0.z; lo2 = g0.w; hi2 = __ldcg(&stack[(size_t)q * fw + FR_HI]);
             }
-            if (it2 <= la2 && la2 - it2 >= 1) { L = q; d_iter = it2; d_lo = lo2; d_hi = hi2; break; }
+            // a frame below the top is given away whole (the warp still has the deeper levels); the top frame is halved
+            if (it2 <= la2 && (q < level || la2 - it2 >= 1)) { L = q; d_iter = it2; d_lo = lo2; d_hi = hi2; break; }
           }
         }
         L = __shfl_sync(FULL, L, 0);
         if (L >= 0) {
           d_iter = __shfl_sync(FULL, d_iter, 0); d_lo = __shfl_sync(FULL, d_lo, 0); d_hi = __shfl_sync(FULL, d_hi, 0);
           const long long ua = (long long)d_lo + ((d_iter + 1) >> 1), ub = (long long)d_hi - (d_iter >> 1);
-          const long long mid = ua + (ub - ua) / 2;
-          const int slot = reserve_slot(a, lane);
+          const long long mid = L < level ? ua - 1 : ua + (ub - ua) / 2;
           int *own = stack + (size_t)L * fw;
-          int *g = a.pool + (size_t)slot * fw;
-          for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
-          __syncwarp();
+          for (;;) {
+            const int slot = reserve_slot(a, lane);
+            int *g = a.pool + (size_t)slot * fw;
+            for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
+            __syncwarp();
+            if (lane == 0) {
+              // the donated frame owns [mid + 1, ub]; this warp keeps [ua, mid]; both restart their value iteration
+              __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
+              __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
+            }
+            if (publish_slot(a, lane, slot)) break;
+          }
           if (lane == 0) {
-            // the donated frame owns [mid + 1, ub]; this warp keeps [ua, mid]; both restart their value iteration
-            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
-            __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
-            __stcg(&own[FR_ITER], 0); __stcg(&own[FR_LO], (int)ua); __stcg(&own[FR_HI], (int)mid);
-            __stcg(&own[FR_LAST], (int)(unsigned)(mid - ua));
-            __threadfence();
-            __stcg(&a.ready[slot], 1);
+            if (L < level) { __stcg(&own[FR_ITER], 1); __stcg(&own[FR_LAST], 0); }     // exhausted: iter > last
+            else {
+              __stcg(&own[FR_ITER], 0); __stcg(&own[FR_LO], (int)ua); __stcg(&own[FR_HI], (int)mid);
+              __stcg(&own[FR_LAST], (int)(unsigned)(mid - ua));
+            }
           }
           if (L == level) { iter = 0; lo = (int)ua; hi = (int)mid; last = (unsigned)(mid - ua); }
           __syncwarp();
@@ -740,6 +816,7 @@ k_search(const SearchArgs a) {
     if (have && level >= base) __stcg(&stack[(size_t)level * fw + FR_ITER], (int)iter);   // park the top frame
     a.wstate[gw].level = level;
     a.wstate[gw].base = base;
+    a.wstate[gw].claim_base = cl.base; a.wstate[gw].claim_mask = cl.mask;
   }
   // flush counters (the slot belongs to this warp; values accumulate across slices)
 #pragma unroll
@@ -867,6 +944,8 @@ k_search_lov(const SearchArgs a) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+  __shared__ int s_blk_hungry;       // warps of this block waiting for a frame: their neighbours poll for donations faster
+  if (threadIdx.x == 0) s_blk_hungry = 0;
   const LovTables T = stage_lov(m, smem);
   if (gw >= a.n_warps) return;
 
@@ -881,10 +960,13 @@ k_search_lov(const SearchArgs a) {
   const int vbase = m.lov_vbase;
 
   int level = a.wstate[gw].level, base = a.wstate[gw].base;
+  Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
   unsigned long long nodes = 0, cuts = 0, sols = 0;
   unsigned n32 = 0, c32 = 0;   // nodes / cuts since the last flush into the 64-bit counters
   unsigned props = 0, visits = 0;
   const long long t0 = clock64();
+  long long waited = 0, lastwork = -1;
+  unsigned claims = 0, dbg_polls = 0, dbg_wanted = 0, dbg_donated = 0;
 
   // HBM frame -> shared frame. The untried values of an alternating enumeration at iteration `it` are the
   // interval [lo + ceil(it / 2), hi - floor(it / 2)]: la - it + 1 values.
@@ -944,8 +1026,12 @@ k_search_lov(const SearchArgs a) {
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
       } else {
-        const int slot = claim_frame(a, lane, hungry);
+        const long long w0 = clock64();
+        lastwork = w0 - t0;
+        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry);
+        waited += clock64() - w0;
         if (slot < 0) break;
+        claims++;
         src = a.pool + (size_t)slot * fw;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
@@ -1121,8 +1207,10 @@ k_search_lov(const SearchArgs a) {
       }
     }
 
-    if (!EXPAND && (++poll & (POLL_NODES - 1)) == 0) {
+    // every POLL_NODES nodes -- every 4 while a warp of this block is waiting for work (shared-memory flag: no L2 trip)
+    if (!EXPAND && (++poll & (*reinterpret_cast<volatile int *>(&s_blk_hungry) > 0 ? 3u : (unsigned)(POLL_NODES - 1))) == 0) {
       nodes += n32; cuts += c32; n32 = 0; c32 = 0;
+      dbg_polls++;
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -1130,34 +1218,51 @@ k_search_lov(const SearchArgs a) {
       }
       if (level >= base && donation_wanted(a, lane)) {
         // shallowest frame with at least two untried values (the top frame's cursor is in registers)
+        // BITS: only values that are not forbidden yet count -- both halves get real work
+        dbg_wanted++;
         int L = -1, d_cur = 0;
-        unsigned d_rem = 0;
+        unsigned d_rem = 0, keep = 0;
         if (lane == 0) {
+          // a frame below the top is given away whole (the warp still has the deeper levels); the top frame is halved
           for (int q = base; q <= level; ++q) {
             const int *qf = sst + q * sfw;
-            const unsigned rm = q == level ? rem : (unsigned)qf[1];
-            if (rm >= 2u) { L = q; d_rem = rm; d_cur = q == level ? cur : qf[0]; break; }
+            const bool top = q == level;
+            const unsigned rm = top ? rem : (unsigned)qf[1];
+            if (rm < (top ? 2u : 1u)) continue;
+            const int cq = top ? cur : qf[0];
+            unsigned kp = top ? (rm - 1u) / 2u + 1u : 0u;
+            if (BITS) {
+              const uint32_t Fq = top ? fvarF : (uint32_t)qf[8 + 2 * V + qf[2]];
+              const uint32_t av = ~Fq & ((rm >= 32u ? 0xffffffffu : ((1u << rm) - 1u)) << (cq - vbase));
+              const int cnt = __popc(av);
+              if (cnt < (top ? 2 : 1)) continue;
+              if (top) kp = (unsigned)((int)__fns(av, 0, cnt / 2) - (cq - vbase)) + 1u;    // up to the (cnt / 2)-th allowed value
+            }
+            L = q; d_rem = rm; d_cur = cq; keep = kp;
+            break;
           }
         }
         L = __shfl_sync(FULL, L, 0);
         if (L >= 0) {
-          d_cur = __shfl_sync(FULL, d_cur, 0); d_rem = __shfl_sync(FULL, d_rem, 0);
-          // this warp keeps the lower half [d_cur, d_cur + keep), the donated frame owns the rest
-          const unsigned keep = (d_rem - 1u) / 2u + 1u, give = d_rem - keep;
+          d_cur = __shfl_sync(FULL, d_cur, 0); d_rem = __shfl_sync(FULL, d_rem, 0); keep = __shfl_sync(FULL, keep, 0);
+          // this warp keeps the lower part [d_cur, d_cur + keep), the donated frame owns the rest
+          const unsigned give = d_rem - keep;
           const int glo = (int)((unsigned)d_cur + keep);
-          const int slot = reserve_slot(a, lane);
           int *own = sst + L * sfw;
-          int *g = a.pool + (size_t)slot * fw;
-          frame_out(own, g);
-          __syncwarp();
-          if (lane == 0) {
-            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], glo); __stcg(&g[FR_HI], (int)((unsigned)glo + give - 1u));
-            __stcg(&g[FR_LAST], (int)(give - 1u));
-            own[0] = d_cur; own[1] = (int)keep;
-            __threadfence();
-            __stcg(&a.ready[slot], 1);
+          for (;;) {
+            const int slot = reserve_slot(a, lane);
+            int *g = a.pool + (size_t)slot * fw;
+            frame_out(own, g);
+            __syncwarp();
+            if (lane == 0) {
+              __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], glo); __stcg(&g[FR_HI], (int)((unsigned)glo + give - 1u));
+              __stcg(&g[FR_LAST], (int)(give - 1u));
+            }
+            if (publish_slot(a, lane, slot)) break;
           }
+          if (lane == 0) { own[0] = d_cur; own[1] = (int)keep; }
           if (L == level) rem = keep;
+          dbg_donated++;
           __syncwarp();
         }
       }
@@ -1176,9 +1281,13 @@ k_search_lov(const SearchArgs a) {
   if (lane == 0) {
     a.wstate[gw].level = level;
     a.wstate[gw].base = base;
+    a.wstate[gw].claim_base = cl.base; a.wstate[gw].claim_mask = cl.mask;
     unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
     c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
     c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols;
+    c[CNT_WAIT] += (unsigned long long)waited; c[CNT_CLAIMS] += claims;
+    c[CNT_POLLS] += dbg_polls; c[CNT_WANTED] += dbg_wanted; c[CNT_DONATED] += dbg_donated;
+    c[CNT_LASTWORK] = (unsigned long long)(lastwork >= 0 ? lastwork : clock64() - t0);
   }
 }
 
@@ -1351,12 +1460,16 @@ k_search_lovk(const SearchArgs a) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+  __shared__ int s_blk_hungry;       // warps of this block waiting for a frame: their neighbours poll for donations faster
+  if (threadIdx.x == 0) s_blk_hungry = 0;
+  __syncthreads();
   if (gw >= a.n_warps) return;
   const int V = m.n_vars, fw = m.frame_words;
   int *stack = a.stacks + (size_t)gw * (V + 1) * fw;
   SearchCtl *ctl = a.ctl;
 
   int level = a.wstate[gw].level, base = a.wstate[gw].base;
+  Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
   unsigned long long nodes = 0, cuts = 0, sols = 0;
   unsigned props = 0, visits = 0, poll = 0;
   const long long t0 = clock64();
@@ -1379,7 +1492,7 @@ k_search_lovk(const SearchArgs a) {
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
       } else {
-        const int slot = claim_frame(a, lane, hungry);
+        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry);
         if (slot < 0) break;
         src = a.pool + (size_t)slot * fw;
       }
@@ -1531,7 +1644,7 @@ k_search_lovk(const SearchArgs a) {
       }
     }
 
-    if (!EXPAND && (++poll & 7u) == 0) {
+    if (!EXPAND && (++poll & (*reinterpret_cast<volatile int *>(&s_blk_hungry) > 0 ? 1u : 7u)) == 0) {
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -1548,26 +1661,33 @@ k_search_lovk(const SearchArgs a) {
               const int4 g0 = __ldcg(reinterpret_cast<const int4 *>(stack + (size_t)q * fw));
               it2 = (unsigned)g0.y; la2 = (unsigned)g0.z; lo2 = g0.w; hi2 = __ldcg(&stack[(size_t)q * fw + FR_HI]);
             }
-            if (it2 <= la2 && la2 - it2 >= 1) { L = q; d_iter = it2; d_lo = lo2; d_hi = hi2; break; }
+            // a frame below the top is given away whole (the warp still has the deeper levels); the top frame is halved
+            if (it2 <= la2 && (q < level || la2 - it2 >= 1)) { L = q; d_iter = it2; d_lo = lo2; d_hi = hi2; break; }
           }
         }
         L = __shfl_sync(FULL, L, 0);
         if (L >= 0) {
           d_iter = __shfl_sync(FULL, d_iter, 0); d_lo = __shfl_sync(FULL, d_lo, 0); d_hi = __shfl_sync(FULL, d_hi, 0);
           const long long ua = (long long)d_lo + ((d_iter + 1) >> 1), ub = (long long)d_hi - (d_iter >> 1);
-          const long long mid = ua + (ub - ua) / 2;
-          const int slot = reserve_slot(a, lane);
+          const long long mid = L < level ? ua - 1 : ua + (ub - ua) / 2;
           int *own = stack + (size_t)L * fw;
-          int *g = a.pool + (size_t)slot * fw;
-          for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
-          __syncwarp();
+          for (;;) {
+            const int slot = reserve_slot(a, lane);
+            int *g = a.pool + (size_t)slot * fw;
+            for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
+            __syncwarp();
+            if (lane == 0) {
+              __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
+              __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
+            }
+            if (publish_slot(a, lane, slot)) break;
+          }
           if (lane == 0) {
-            __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
-            __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
-            __stcg(&own[FR_ITER], 0); __stcg(&own[FR_LO], (int)ua); __stcg(&own[FR_HI], (int)mid);
-            __stcg(&own[FR_LAST], (int)(unsigned)(mid - ua));
-            __threadfence();
-            __stcg(&a.ready[slot], 1);
+            if (L < level) { __stcg(&own[FR_ITER], 1); __stcg(&own[FR_LAST], 0); }     // exhausted: iter > last
+            else {
+              __stcg(&own[FR_ITER], 0); __stcg(&own[FR_LO], (int)ua); __stcg(&own[FR_HI], (int)mid);
+              __stcg(&own[FR_LAST], (int)(unsigned)(mid - ua));
+            }
           }
           if (L == level) { iter = 0; flo = (int)ua; fhi = (int)mid; last = (unsigned)(mid - ua); }
           __syncwarp();
@@ -1580,6 +1700,7 @@ k_search_lovk(const SearchArgs a) {
     if (have && level >= base) __stcg(&stack[(size_t)level * fw + FR_ITER], (int)iter);
     a.wstate[gw].level = level;
     a.wstate[gw].base = base;
+    a.wstate[gw].claim_base = cl.base; a.wstate[gw].claim_mask = cl.mask;
     unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
     c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
     c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols;
@@ -1693,10 +1814,19 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
   if (threadIdx.x == 0) { n_idle = 0; n_donor = 0; idle_done = 0; busy = 0; moved = 0; }
   __syncthreads();
   for (int w = threadIdx.x; w < nw; w += blockDim.x) {
-    if (a.wstate[w].level < a.wstate[w].base) idle_list[atomicAdd(&n_idle, 1)] = w;
-    else atomicAdd(&busy, 1);
+    if (a.wstate[w].level >= a.wstate[w].base || a.wstate[w].claim_mask != 0u) atomicAdd(&busy, 1);   // claimed root-frontier frames are work too
+    else idle_list[atomicAdd(&n_idle, 1)] = w;
   }
   __syncthreads();
+  // every waiting warp has left the search kernel: tickets no donor served are void (their slots carry the -1 marker)
+  {
+    const int served = a.ctl->item_count, taken = a.ctl->item_next;
+    const unsigned ring = (unsigned)(a.pool_cap - a.n_initial);
+    for (int i = served + (int)threadIdx.x; i - taken < 0; i += blockDim.x) a.ready[a.n_initial + (int)((unsigned)i % ring)] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0 && taken - served > 0) a.ctl->item_count = taken;
+    __syncthreads();
+  }
   // frames still in the frontier pool are work too: nothing to move while they last
   const bool pool_left = a.ctl->item_count - a.ctl->item_next > 0 || a.ctl->init_next < a.n_initial;
   for (int round = 0; round < 4 && !pool_left; ++round) {

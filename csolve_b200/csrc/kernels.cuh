@@ -16,28 +16,45 @@ static const int SIG_SLICE_END = 1;    // park at the next node boundary (rebala
 static const int SIG_STOP = 2;         // ANY: a solution was found
 
 // per-warp counters (uint64 each), accumulated over all slices
-enum { CNT_NODES = 0, CNT_CUTS, CNT_PROPS, CNT_VISITS, CNT_SOLUTIONS, CNT_REFRESH, CNT_WIDTH };
+// CNT_WAIT / CNT_CLAIMS / CNT_LASTWORK: load-balance diagnostics (cycles spent waiting for a frame, frames claimed,
+// cycle offset of the warp's last node inside its last slice), printed under CSOLVE_DEBUG
+enum { CNT_NODES = 0, CNT_CUTS, CNT_PROPS, CNT_VISITS, CNT_SOLUTIONS, CNT_REFRESH, CNT_WAIT, CNT_CLAIMS, CNT_LASTWORK, CNT_POLLS, CNT_WANTED, CNT_DONATED, CNT_WIDTH };
 
+// The fields every warp hammers with atomics sit on cache lines of their own (an L2 atomic locks its line: with
+// everything on one line the claims of the root frontier, the ring head/tail and the hungry counter serialised each
+// other and the signal polls -- 8..16 us per claim were measured on a busy B200).
 struct SearchCtl {
+  // line 0: read-mostly (polled)
   int32_t signal;
   int32_t idle;         // warps that ran out of work during the current slice
-  int32_t item_next;    // next frontier item to hand out
-  int32_t item_count;   // frontier items available
   int32_t best;         // incumbent objective value (objective_best(), src/objective.c:133)
+  int32_t busy;         // written by the rebalance kernel: warps that still own work
+  int32_t moved;        // written by the rebalance kernel: frames handed to idle warps
+  int32_t pad0[27];
+  // line 1: claims of the expanded root frontier
+  int32_t init_next;    // next frame of the expanded root frontier (static part of the pool, claimed with atomicAdd)
+  int32_t pad1[31];
+  // line 2: ring of donated frames (depth-first phase) / input cursor (expansion)
+  int32_t item_next;    // expansion: next frontier item to hand out; depth-first phase: tickets taken by waiting warps
+  int32_t pad2[31];
+  int32_t item_count;   // expansion: frontier items available; depth-first phase: tickets served by donating warps
+  int32_t pad2b[31];
+  // line 3
+  int32_t hungry;       // warps waiting for a frame of the shared pool
+  int32_t pad3[31];
+  // line 4: output side
   int32_t n_stored;     // assignments written to the solution buffer
   int32_t out_count;    // expand mode: frames appended to the output frontier
   int32_t out_dropped;  // expand mode: children that did not fit (capacity error)
-  int32_t busy;         // written by the rebalance kernel: warps that still own work
-  int32_t moved;        // written by the rebalance kernel: frames handed to idle warps
   int32_t passed;       // expand mode: frames passed through unsplit (domain too large to enumerate)
-  int32_t hungry;       // warps waiting for a frame of the shared pool
-  int32_t init_next;    // next frame of the expanded root frontier (static part of the pool, claimed with atomicAdd)
-  int32_t pad[3];
+  int32_t pad4[28];
 };
 
 struct WarpState {
   int32_t level;   // index of the top frame of the warp's stack; < base when the warp is idle
   int32_t base;    // lowest level the warp owns
+  int32_t claim_base;   // frames of the expanded root frontier this warp has claimed and not searched yet:
+  uint32_t claim_mask;  // bit b = frame claim_base + b (kept across time slices)
 };
 
 // Learned nogoods (src/conflict.c): an append-only pool shared by all warps of one GPU.

@@ -57,3 +57,10 @@ if "sudoku" in args:
         w = (time.perf_counter() - t0) * 1e3
         print("sudoku x10000 nodes=%d search_ms=%.2f expand_ms=%.2f wall_ms=%.2f ok=%s" % (
             r.nodes, r.kernel_ms, r.expand_ms, w, counts.tolist() == [1] * len(grids)), flush=True)
+if "split" in args:
+    P = int(args[args.index("split") + 1])
+    for mult in (8, 16, 32, 64, 128, 256):
+        st = 4736 * mult
+        run("queens%d split %dx" % (n, mult), I.queens(n), split_target=st)
+        if P > 1:
+            run("queens%d split %dx part 0/%d" % (n, mult, P), I.queens(n), split_target=st, part_rank=0, part_count=P)
