@@ -235,6 +235,11 @@ namespace {
 // warp plus the frames delivered ahead of their tickets)
 int ring_min_frames(int n_warps) { return 2 * n_warps + 1024; }
 
+// Breadth-first expansion target. The ticket queue keeps every warp busy to the end whatever the size of the root
+// frontier (measured: 16-queens search time is the same from 16 to 256 frames per warp), so the frontier only has to
+// be long enough for an even rank partition; every further level is expansion time that all ranks replicate.
+const int DEFAULT_FRAMES_PER_WARP = 16;
+
 int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots, bool learn) {
   DevModel m = p->dev;
   if (batch) m.lov = 0;
@@ -260,7 +265,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
     CUDA_TRY(cudaMalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
-  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 128;
+  int target = opt.split_target > 0 ? opt.split_target : p->n_warps * DEFAULT_FRAMES_PER_WARP;
   target = std::max(target, n_roots);
   int cap = std::max(target * 4, 1 << 16) + ring_min_frames(p->n_warps);
   const size_t max_bytes = (size_t)2 << 30;   // per pool
@@ -374,7 +379,13 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     CUDA_TRY(cudaMalloc(&d_gprio, (size_t)V * sizeof(int32_t)));
     CUDA_TRY(cudaMemcpyAsync(d_gprio, cm.prio.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   }
-  const int slice_ms = opt.slice_ms > 0 ? opt.slice_ms : 20;
+  // a slice ends so that the host can check the time limit / run the rank exchange; without either the kernel only
+  // has to come back when it is done. Branch-and-bound profits from short slices: between two slices k_rebalance
+  // hands EVERY idle warp half of a busy warp's shallowest frame at once, which finds good incumbents sooner
+  // (wcet: 56 ms with 5 ms slices, 71 ms with 20 ms, 380 ms with one long slice).
+  const int slice_ms = opt.slice_ms > 0 ? opt.slice_ms
+                       : p->dev.obj_var >= 0 ? 5
+                       : (p->exchange != nullptr || opt.time_limit_ms > 0) ? 20 : 1000;
   a.slice_cycles = (long long)g_clock_khz * slice_ms;
 
   cudaEvent_t ev0, ev1, ev2;
@@ -382,7 +393,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   CUDA_TRY(cudaEventRecord(ev0, st));
 
   // ---- batched frontier expansion -------------------------------------------------------------------
-  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * 128;
+  const int target = opt.split_target > 0 ? opt.split_target : p->n_warps * DEFAULT_FRAMES_PER_WARP;
   long long max_branch = 1;
   for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
   max_branch = std::min<long long>(max_branch, a.expand_branch_max);

@@ -34,9 +34,11 @@ n = int(args[args.index("queens") + 1]) if "queens" in args else 16
 run("queens%d" % n, I.queens(n))
 if "parts" in args:
     P = int(args[args.index("parts") + 1])
-    tot = 0
-    for rk in (0, P // 2, P - 1):
+    worst = 0.0
+    for rk in range(P):
         r = run("queens%d part %d/%d" % (n, rk, P), I.queens(n), part_rank=rk, part_count=P)
+        worst = max(worst, r.kernel_ms + r.expand_ms)
+    print("slowest rank of %d: %.2f ms" % (P, worst))
 if "orders" in args:
     for o in ("smallest-domain", "largest-domain"):
         run("queens%d -o %s" % (n - 2, o), I.queens(n - 2), order=o)
@@ -64,3 +66,7 @@ if "split" in args:
         run("queens%d split %dx" % (n, mult), I.queens(n), split_target=st)
         if P > 1:
             run("queens%d split %dx part 0/%d" % (n, mult, P), I.queens(n), split_target=st, part_rank=0, part_count=P)
+if "wcetvar" in args:
+    for kw in ({}, {"slice_ms": 20}, {"split_target": 4736 * 128}, {"split_target": 4736 * 128, "slice_ms": 20}, {"slice_ms": 5}, {"slice_ms": 100}):
+        for _ in range(2):
+            run("wcet %s" % kw, I.wcet(), reps=2, **kw)
