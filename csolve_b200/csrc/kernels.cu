@@ -896,12 +896,11 @@ __device__ __forceinline__ bool lov_fixpoint(const LovTables &t, int V, bool has
 // variables that became a value and whose forbidden values have not been distributed yet.
 __device__ __forceinline__ bool lov_fixpoint_bits(const LovTables &t, int V, int vbase, int lane, int &lo, int &hi,
                                                   uint32_t &F, unsigned pend, unsigned &props, unsigned &visits) {
-  const bool act = lane < V;
   while (pend) {
     const int i = __ffs(pend) - 1;
     pend &= pend - 1;
     const int w = __shfl_sync(FULL, lo, i);
-    if (act) F |= lov_forbid(t.pair[i * 32 + lane], w, vbase);
+    F |= lov_forbid(t.pair[i * 32 + lane], w, vbase);    // lanes >= V read the zero entries of the table: no branch
     const bool was = lo == hi;
     const int olo = lo, ohi = hi;
     const bool alive = lov_trim(F, vbase, lo, hi);
@@ -1012,7 +1011,14 @@ k_search_lov(const SearchArgs a) {
   int plo = 0, phi = 0;        // this lane's variable in the top frame (state before the assignment)
   uint32_t pF = 0;             // ... and its forbidden-value set (BITS)
   uint32_t fvarF = 0;          // forbidden-value set of the top frame's branching variable (warp-uniform)
+  uint32_t avail = 0;          // values of [cur, cur + rem) that are not in fvarF (BITS)
   unsigned poll = 0;
+  // the last level is not searched: with every other variable a value, each value its forbidden set leaves is a solution
+#ifdef CSOLVE_NO_COUNT_LAST
+  const bool count_last = false;
+#else
+  const bool count_last = BITS && !EXPAND && m.objective == CSOLVE_OBJ_ALL && a.max_solutions == 0 && V >= 2;
+#endif
 
   bool hungry = false;
   for (;;) {
@@ -1053,9 +1059,12 @@ k_search_lov(const SearchArgs a) {
       if (act) dj = reinterpret_cast<const int2 *>(sf + 8)[lane];
       plo = dj.x; phi = dj.y;
       if (BITS) pF = act ? (uint32_t)sf[8 + 2 * V + lane] : 0u;
-      if (BITS) fvarF = __shfl_sync(FULL, pF, h0.z);
       cur = h0.x; rem = (unsigned)h0.y; var = h0.z; flevel = h0.w;
       amask = (unsigned)h1.x; fhash = (unsigned)h1.y;
+      if (BITS) {
+        fvarF = __shfl_sync(FULL, pF, var);
+        avail = rem ? (~fvarF & ((rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u)) << (cur - vbase))) : 0u;
+      }
       have = true;
       if (EXPAND && rem > (unsigned)a.expand_branch_max) {
         // too many values to enumerate breadth-first: pass the frame through unchanged
@@ -1075,8 +1084,7 @@ k_search_lov(const SearchArgs a) {
     if (BITS) {
       // values of [cur, cur + rem) the fixed variables (and constants) do not forbid yet; a forbidden value's node
       // fails at the first trim of its own variable (lov_trim on [val, val]): counted, not executed
-      const unsigned span = rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u);
-      const uint32_t avail = rem ? (~fvarF & (span << (cur - vbase))) : 0u;
+      // (`avail` is kept in a register while the frame is the top one)
       if (avail == 0u) {
         n32 += rem; c32 += rem;
         level--;
@@ -1084,6 +1092,7 @@ k_search_lov(const SearchArgs a) {
         continue;
       }
       const int b = __ffs((int)avail) - 1;
+      avail &= avail - 1u;
       const unsigned skipped = (unsigned)(b - (cur - vbase));
       n32 += skipped; c32 += skipped;
       val = vbase + b;
@@ -1187,6 +1196,14 @@ k_search_lov(const SearchArgs a) {
         } else if (lane == 0) {
           atomicAdd(&ctl->out_dropped, 1);
         }
+      } else if (count_last && flevel + 2 == V) {
+        // nv is the last variable: F_nv holds everything the V - 1 values forbid (the clause tables are symmetric),
+        // so each remaining value is an accepted leaf and each forbidden one a failed node -- counted, not searched
+        const uint32_t Fn = __shfl_sync(FULL, F, nv);
+        const int good = __popc(~Fn & ((nrem >= 32u ? 0xffffffffu : ((1u << nrem) - 1u)) << (nlo - vbase)));
+        n32 += nrem; c32 += nrem - (unsigned)good; sols += (unsigned)good;
+        props += (lane == nv && nrem > 1u) ? (unsigned)good : 0u;  // each of those nodes narrows nv to its value (branch-free:
+                                                                   // a divergent branch here kept the warp split far into the loop)
       } else {
         // push: everything stays in shared memory / registers
         int *nf = sf + sfw;
@@ -1199,7 +1216,10 @@ k_search_lov(const SearchArgs a) {
         if (BITS && act) nf[8 + 2 * V + lane] = (int)F;
         amask = nmask;
         plo = lo; phi = hi; pF = F;
-        if (BITS) fvarF = __shfl_sync(FULL, F, nv);
+        if (BITS) {
+          fvarF = __shfl_sync(FULL, F, nv);
+          avail = ~fvarF & ((nrem >= 32u ? 0xffffffffu : ((1u << nrem) - 1u)) << (nlo - vbase));
+        }
         var = nv; cur = nlo; rem = nrem;
         flevel = flevel + 1;
         level++;
@@ -1208,7 +1228,12 @@ k_search_lov(const SearchArgs a) {
     }
 
     // every POLL_NODES nodes -- every 4 while a warp of this block is waiting for work (shared-memory flag: no L2 trip)
+#ifdef CSOLVE_OLD_POLL
     if (!EXPAND && (++poll & (*reinterpret_cast<volatile int *>(&s_blk_hungry) > 0 ? 3u : (unsigned)(POLL_NODES - 1))) == 0) {
+#else
+    if (!EXPAND && (++poll & 3u) == 0 &&
+        ((poll & (unsigned)(POLL_NODES - 1)) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
+#endif
       nodes += n32; cuts += c32; n32 = 0; c32 = 0;
       dbg_polls++;
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
@@ -1232,8 +1257,7 @@ k_search_lov(const SearchArgs a) {
             const int cq = top ? cur : qf[0];
             unsigned kp = top ? (rm - 1u) / 2u + 1u : 0u;
             if (BITS) {
-              const uint32_t Fq = top ? fvarF : (uint32_t)qf[8 + 2 * V + qf[2]];
-              const uint32_t av = ~Fq & ((rm >= 32u ? 0xffffffffu : ((1u << rm) - 1u)) << (cq - vbase));
+              const uint32_t av = top ? avail : (~(uint32_t)qf[8 + 2 * V + qf[2]] & ((rm >= 32u ? 0xffffffffu : ((1u << rm) - 1u)) << (cq - vbase)));
               const int cnt = __popc(av);
               if (cnt < (top ? 2 : 1)) continue;
               if (top) kp = (unsigned)((int)__fns(av, 0, cnt / 2) - (cq - vbase)) + 1u;    // up to the (cnt / 2)-th allowed value
@@ -1261,7 +1285,11 @@ k_search_lov(const SearchArgs a) {
             if (publish_slot(a, lane, slot)) break;
           }
           if (lane == 0) { own[0] = d_cur; own[1] = (int)keep; }
-          if (L == level) rem = keep;
+          if (L == level) {
+            rem = keep;
+            const unsigned e = (unsigned)(cur - vbase) + keep;          // first bit that no longer belongs to the frame
+            if (BITS && e < 32u) avail &= (1u << e) - 1u;
+          }
           dbg_donated++;
           __syncwarp();
         }
@@ -1362,7 +1390,7 @@ __device__ __forceinline__ bool lovk_fixpoint(const DevModel &m, int lane, LovK<
     for (int q = 0; q < K; q++) {
       const int v = lane + 32 * q;
       const bool act = v < V;
-      if (act) x.F[q] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + v]), w, vbase);
+      x.F[q] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + v]), w, vbase);   // v >= V: zero entries of the table
       const bool was = x.lo[q] == x.hi[q];
       const int olo = x.lo[q], ohi = x.hi[q];
       if (!lov_trim(x.F[q], vbase, x.lo[q], x.hi[q])) dead = true;
