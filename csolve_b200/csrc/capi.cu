@@ -127,6 +127,9 @@ struct csolve_gpu_problem {
   NogoodPool ng{};                 // device clause pool of learned nogoods (allocated on demand)
   csolve_exchange_fn exchange = nullptr;
   void *exchange_user = nullptr;
+  csolve_rebalance_fn rebalance = nullptr;
+  void *rebalance_user = nullptr;
+  const SearchArgs *parked = nullptr;   // search arguments while the rebalance callback runs (export / import are valid)
 
   ~csolve_gpu_problem() {
     for (void *p : allocs) cudaFree(p);
@@ -491,6 +494,17 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
       local_done = true;   // found_any() on another rank (src/csolve.c:207-209)
     }
     if (all_done) break;
+    if (p->rebalance != nullptr && !batch && !(found && m.objective == CSOLVE_OBJ_ANY)) {
+      // frontier rebalancing: ranks that ran dry receive frames split off the busy warps of the others. Every rank
+      // makes the call (the collectives inside must stay matched); one that hit its time limit poses as a rank with
+      // a single busy warp: it neither receives nor has anything to spare.
+      p->parked = &a;
+      const int got = timed_out ? p->rebalance(p->rebalance_user, p, 0, 1, fw)
+                                : p->rebalance(p->rebalance_user, p, local_done ? p->n_warps : idle_now, local_done ? 0 : busy, fw);
+      p->parked = nullptr;
+      if (got < 0) return fail(CSOLVE_ERR_INVALID, "rebalance callback failed");
+      if (got > 0) local_done = false;
+    }
   }
   (void)idle_now;
   CUDA_TRY(cudaEventRecord(ev2, st));
@@ -592,6 +606,51 @@ extern "C" int csolve_gpu_set_exchange(csolve_gpu_problem *p, csolve_exchange_fn
   if (p == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
   p->exchange = fn;
   p->exchange_user = user;
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_set_rebalance(csolve_gpu_problem *p, csolve_rebalance_fn fn, void *user) {
+  if (p == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  p->rebalance = fn;
+  p->rebalance_user = user;
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_export_frames(csolve_gpu_problem *p, int32_t max_frames, int32_t *frames, int32_t *n_out) {
+  if (p == nullptr || frames == nullptr || n_out == nullptr || max_frames < 0) return fail(CSOLVE_ERR_INVALID, "bad arguments");
+  *n_out = 0;
+  if (p->parked == nullptr) return fail(CSOLVE_ERR_INVALID, "csolve_gpu_export_frames is only valid inside the rebalance callback");
+  if (max_frames == 0) return CSOLVE_OK;
+  const SearchArgs &a = *p->parked;
+  const size_t bytes = (size_t)max_frames * a.m.frame_words * sizeof(int32_t);
+  int32_t *d_buf = nullptr, *d_n = nullptr;
+  CUDA_TRY(cudaMalloc(&d_buf, bytes));
+  CUDA_TRY(cudaMalloc(&d_n, sizeof(int32_t)));
+  cudaError_t e = launch_export_frames(a, d_buf, max_frames, d_n, p->stream);
+  int32_t n = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  if (e == cudaSuccess && n > 0) e = cudaMemcpy(frames, d_buf, (size_t)n * a.m.frame_words * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_buf); cudaFree(d_n);
+  if (e != cudaSuccess) return fail(CSOLVE_ERR_CUDA, std::string("export frames: ") + cudaGetErrorString(e));
+  *n_out = n;
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_import_frames(csolve_gpu_problem *p, const int32_t *frames, int32_t n_frames) {
+  if (p == nullptr || frames == nullptr || n_frames < 0) return fail(CSOLVE_ERR_INVALID, "bad arguments");
+  if (p->parked == nullptr) return fail(CSOLVE_ERR_INVALID, "csolve_gpu_import_frames is only valid inside the rebalance callback");
+  if (n_frames == 0) return CSOLVE_OK;
+  const SearchArgs &a = *p->parked;
+  if (n_frames > a.n_warps) return fail(CSOLVE_ERR_CAPACITY, "more frames than the donation ring holds");
+  const size_t bytes = (size_t)n_frames * a.m.frame_words * sizeof(int32_t);
+  int32_t *d_buf = nullptr;
+  CUDA_TRY(cudaMalloc(&d_buf, bytes));
+  cudaError_t e = cudaMemcpyAsync(d_buf, frames, bytes, cudaMemcpyHostToDevice, p->stream);
+  if (e == cudaSuccess) e = launch_import_frames(a, d_buf, n_frames, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  cudaFree(d_buf);
+  if (e != cudaSuccess) return fail(CSOLVE_ERR_CUDA, std::string("import frames: ") + cudaGetErrorString(e));
   return CSOLVE_OK;
 }
 

@@ -1916,6 +1916,77 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
   }
 }
 
+// ---- frontier rebalancing between ranks ---------------------------------------------------------------
+// Between two time slices (every warp parked): split up to max_frames frames off the parked stacks into `out`
+// (frames of frame_words words) so that the host can ship them to a rank that ran dry. Same rule as the in-kernel
+// donation: the shallowest frame of a busy warp that still has untried values -- whole if it lies below the warp's
+// top frame, its upper half otherwise. One block.
+__global__ void __launch_bounds__(1024)
+k_export_frames(const SearchArgs a, int32_t *out, int max_frames, int32_t *n_out) {
+  const DevModel &m = a.m;
+  const int V = m.n_vars, fw = m.frame_words, nw = a.n_warps;
+  __shared__ int n_taken;
+  if (threadIdx.x == 0) n_taken = 0;
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int w = wid; w < nw; w += nwarp) {
+    const int lv = a.wstate[w].level, bs = a.wstate[w].base;
+    if (lv < bs) continue;
+    int *stack = a.stacks + (size_t)w * (V + 1) * fw;
+    int L = -1;
+    for (int q = bs; q <= lv && L < 0; ++q) {
+      const unsigned iter = (unsigned)stack[(size_t)q * fw + FR_ITER], last = (unsigned)stack[(size_t)q * fw + FR_LAST];
+      if (iter <= last && (q < lv || last - iter >= 1)) L = q;
+    }
+    if (L < 0) continue;                         // warp-uniform
+    int k = 0;
+    if (lane == 0) k = atomicAdd(&n_taken, 1);
+    k = __shfl_sync(FULL, k, 0);
+    if (k >= max_frames) break;
+    int *df = stack + (size_t)L * fw;
+    int *tf = out + (size_t)k * fw;
+    const unsigned iter = (unsigned)df[FR_ITER];
+    const long long lo = df[FR_LO], hi = df[FR_HI];
+    const long long ua = lo + ((iter + 1) >> 1), ub = hi - (iter >> 1);   // untried interval
+    const long long mid = L < lv ? ua - 1 : ua + (ub - ua) / 2;
+    __syncwarp();
+    for (int x = lane; x < fw; x += 32) tf[x] = df[x];
+    __syncwarp();
+    if (lane == 0) {
+      const int var = df[FR_VAR];
+      const int dofs = frame_dom_offset(m.mask_words);
+      tf[FR_ITER] = 0; tf[FR_LO] = (int)(mid + 1); tf[FR_HI] = (int)ub; tf[FR_LAST] = (int)(unsigned)(ub - mid - 1);
+      tf[dofs + 2 * var] = (int)(mid + 1); tf[dofs + 2 * var + 1] = (int)ub;
+      if (L < lv) { df[FR_ITER] = 1; df[FR_LAST] = 0; }      // exhausted: iter > last
+      else {
+        df[FR_ITER] = 0; df[FR_LO] = (int)ua; df[FR_HI] = (int)mid; df[FR_LAST] = (int)(unsigned)(mid - ua);
+        df[dofs + 2 * var] = (int)ua; df[dofs + 2 * var + 1] = (int)mid;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *n_out = min(n_taken, max_frames);
+}
+
+// frames received from another rank go into the ring as tickets served ahead of their holders: the first warps that
+// run dry in the next slice find them ready. One block.
+__global__ void __launch_bounds__(1024)
+k_import_frames(const SearchArgs a, const int32_t *in, int n_frames) {
+  const int fw = a.m.frame_words;
+  const unsigned ring = (unsigned)(a.pool_cap - a.n_initial);
+  __shared__ int first;
+  if (threadIdx.x == 0) first = atomicAdd(&a.ctl->item_count, n_frames);
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int k = wid; k < n_frames; k += nwarp) {
+    const int slot = a.n_initial + (int)((unsigned)(first + k) % ring);
+    int *g = a.pool + (size_t)slot * fw;
+    for (int x = lane; x < fw; x += 32) g[x] = in[(size_t)k * fw + x];
+    __syncwarp();
+    if (lane == 0) a.ready[slot] = 1;
+  }
+}
+
 __global__ void k_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out) {
   __shared__ unsigned long long acc[CNT_WIDTH];
   if (threadIdx.x < CNT_WIDTH) acc[threadIdx.x] = 0;
@@ -2122,6 +2193,16 @@ cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t 
 
 cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t st) {
   k_rebalance<<<1, 1024, 0, st>>>(a, scratch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_export_frames(const SearchArgs &a, int32_t *out, int max_frames, int32_t *n_out, cudaStream_t st) {
+  k_export_frames<<<1, 1024, 0, st>>>(a, out, max_frames, n_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_import_frames(const SearchArgs &a, const int32_t *in, int n_frames, cudaStream_t st) {
+  k_import_frames<<<1, 1024, 0, st>>>(a, in, n_frames);
   return cudaGetLastError();
 }
 

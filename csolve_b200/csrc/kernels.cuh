@@ -100,6 +100,8 @@ size_t search_smem_bytes(const DevModel &m, bool learn = false);
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s);
 bool search_learns(const SearchArgs &a);
 cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t s);
+cudaError_t launch_export_frames(const SearchArgs &a, int32_t *out, int max_frames, int32_t *n_out, cudaStream_t s);
+cudaError_t launch_import_frames(const SearchArgs &a, const int32_t *in, int n_frames, cudaStream_t s);
 cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out, cudaStream_t s);
 cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,

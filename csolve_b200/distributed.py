@@ -68,18 +68,88 @@ def make_exchange(objective, device=None, group=None):
     return exchange
 
 
-def solve_partitioned(problem, objective, device=None, group=None, exchange=None, **solve_kw):
+def plan_transfers(busy, max_frames):
+    """Who ships how many frames to whom. busy[r] = warps of rank r that still own work (0: the rank ran dry).
+    Ranks that ran dry receive an even share of what the busy ranks can spare: a donor keeps at least half of its busy
+    warps' worth of frames and never exports more than max_frames. Deterministic: every rank computes the same plan.
+    Returns give[d][r] (frames from donor d to receiver r)."""
+    world = len(busy)
+    give = [[0] * world for _ in range(world)]
+    receivers = [r for r in range(world) if busy[r] == 0]
+    donors = [d for d in range(world) if busy[d] > 0]
+    if not receivers or not donors:
+        return give
+    fair = sum(busy) // world                      # frames per rank if one busy warp is worth one frame
+    for d in donors:
+        spare = min(max_frames, busy[d] // 2, max(busy[d] - fair, 0))
+        share = spare // len(receivers)
+        if share == 0:
+            continue
+        for r in receivers:
+            give[d][r] = share
+    return give
+
+
+def make_rebalance(device=None, group=None, max_frames=1024):
+    """The per-slice frontier rebalancing between ranks: one all-gather of the busy counts; only when
+    some rank ran dry while another still works, one all-gather of the exported frames (padded to max_frames)."""
+    dev = device if device is not None else torch.device("cpu")
+
+    def rebalance(problem, n_idle, n_busy, frame_words):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        mine = torch.tensor([n_busy], dtype=torch.int64, device=dev)
+        allb = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine, group=group)
+        busy = [int(t.item()) for t in allb]
+        give = plan_transfers(busy, max_frames)
+        if not any(any(row) for row in give):
+            return 0
+        want = sum(give[rank])
+        frames = problem.export_frames(want) if want > 0 else None
+        n_out = 0 if frames is None else int(frames.shape[0])
+        buf = torch.zeros((max_frames * frame_words + 1,), dtype=torch.int32, device=dev)
+        buf[0] = n_out
+        if n_out:
+            buf[1:1 + n_out * frame_words] = torch.from_numpy(frames.reshape(-1)).to(dev)
+        allf = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(allf, buf, group=group)
+        got = 0
+        for d in range(world):
+            if give[d][rank] == 0:
+                continue
+            n_d = int(allf[d][0].item())
+            # donor d dealt its exported frames to its receivers in rank order, give[d][r] each (fewer if it ran short)
+            start = 0
+            for r in range(rank):
+                start += give[d][r]
+            cnt = max(0, min(give[d][rank], n_d - start))
+            if cnt:
+                fr = allf[d][1 + start * frame_words:1 + (start + cnt) * frame_words].cpu().numpy()
+                got += problem.import_frames(fr.reshape(cnt, frame_words))
+        return got
+    return rebalance
+
+
+def solve_partitioned(problem, objective, device=None, group=None, exchange=None, rebalance=False, **solve_kw):
     """Search this rank's share of the tree and reduce. `problem` is a GpuProblem (or anything with .solve).
-    exchange=True installs the per-slice incumbent / first-solution exchange (MIN, MAX and ANY models)."""
+    exchange=True installs the per-slice incumbent / first-solution exchange (MIN, MAX and ANY models);
+    rebalance=True additionally ships frames from busy ranks to ranks that ran dry (it needs the exchange: that is
+    where the ranks agree that everybody is done)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if exchange is None:
-        exchange = world > 1 and objective in (OBJ_MIN, OBJ_MAX, OBJ_ANY)
+        exchange = world > 1 and (rebalance or objective in (OBJ_MIN, OBJ_MAX, OBJ_ANY))
+    exchange = exchange or rebalance
     if exchange and world > 1 and hasattr(problem, "set_exchange"):
         problem.set_exchange(make_exchange(objective, device=device, group=group))
+    if rebalance and world > 1 and hasattr(problem, "set_rebalance"):
+        problem.set_rebalance(make_rebalance(device=device, group=group))
     try:
         res = problem.solve(part_rank=rank, part_count=world, **solve_kw)
     finally:
         if exchange and world > 1 and hasattr(problem, "set_exchange"):
             problem.set_exchange(None)
+        if rebalance and world > 1 and hasattr(problem, "set_rebalance"):
+            problem.set_rebalance(None)
     return reduce_results(res, objective, device=device, group=group), res

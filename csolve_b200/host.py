@@ -90,6 +90,10 @@ class _GpuResult(C.Structure):
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32)
 
 
+# int (*csolve_rebalance_fn)(void *user, csolve_gpu_problem *p, int32_t n_idle, int32_t n_busy, int32_t frame_words)
+REBALANCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)
+
+
 def library_path():
     # CSOLVE_B200_LIB: development override to compare builds; the default is the in-tree library
     return os.environ.get("CSOLVE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcsolve_b200.so")
@@ -127,6 +131,9 @@ def library():
     lib.csolve_gpu_solve_batch.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.c_int32, I32P,
                                            C.POINTER(C.c_uint32), U8P, C.POINTER(_GpuResult)]
     lib.csolve_gpu_set_exchange.argtypes = [C.c_void_p, EXCHANGE_FN, C.c_void_p]
+    lib.csolve_gpu_set_rebalance.argtypes = [C.c_void_p, REBALANCE_FN, C.c_void_p]
+    lib.csolve_gpu_export_frames.argtypes = [C.c_void_p, C.c_int32, I32P, I32P]
+    lib.csolve_gpu_import_frames.argtypes = [C.c_void_p, I32P, C.c_int32]
     lib.csolve_last_error.restype = C.c_char_p
     _lib = lib
     return lib
@@ -266,6 +273,40 @@ class GpuProblem:
             return 1 if done else 0
         self._exchange_cb = EXCHANGE_FN(tramp)          # keep the trampoline alive
         _check(library().csolve_gpu_set_exchange(self._h, self._exchange_cb, None))
+
+    def set_rebalance(self, fn):
+        """fn(problem, n_idle, n_busy, frame_words) -> number of frames imported: called once per time slice after the
+        exchange callback while some rank still has work (csolve_gpu_set_rebalance in include/csolve_b200.h). Inside
+        it export_frames() / import_frames() move frames between the ranks. Pass None to remove it."""
+        if fn is None:
+            self._rebalance_cb = None
+            _check(library().csolve_gpu_set_rebalance(self._h, C.cast(None, REBALANCE_FN), None))
+            return
+
+        def tramp(user, handle, n_idle, n_busy, frame_words):
+            self._frame_words = int(frame_words)
+            try:
+                return int(fn(self, int(n_idle), int(n_busy), int(frame_words)))
+            except Exception:            # an exception cannot cross the C frames: abort the search instead
+                import traceback
+                traceback.print_exc()
+                return -1
+        self._rebalance_cb = REBALANCE_FN(tramp)        # keep the trampoline alive
+        _check(library().csolve_gpu_set_rebalance(self._h, self._rebalance_cb, None))
+
+    def export_frames(self, max_frames):
+        """inside the rebalance callback: split up to max_frames frames off this rank's busy warps -> [n, frame_words] int32"""
+        buf = np.zeros((max(int(max_frames), 1), self._frame_words), np.int32)
+        n = C.c_int32()
+        _check(library().csolve_gpu_export_frames(self._h, int(max_frames), buf.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)))
+        return buf[:n.value]
+
+    def import_frames(self, frames):
+        """inside the rebalance callback: add frames ([n, frame_words] int32) to this rank's pool"""
+        frames = np.ascontiguousarray(frames, np.int32).reshape(-1, self._frame_words)
+        if frames.shape[0]:
+            _check(library().csolve_gpu_import_frames(self._h, frames.ctypes.data_as(C.POINTER(C.c_int32)), frames.shape[0]))
+        return frames.shape[0]
 
     def solve_batch(self, root_domains, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0,
                     max_solutions=0, time_limit_ms=0, slice_ms=0):

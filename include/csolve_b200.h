@@ -189,6 +189,22 @@ int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt, cso
 typedef int (*csolve_exchange_fn)(void *user, int32_t *best, int32_t *found, int32_t local_done);
 int csolve_gpu_set_exchange(csolve_gpu_problem *p, csolve_exchange_fn fn, void *user);
 
+/* Frontier rebalancing between the ranks (the reference's worker_spawn hands half of a worker's open values to a new
+ * process whenever a slot is free, src/csolve.c:121-149; across GPUs the same bisection travels as frames).
+ * The callback runs on the host once per time slice, right after the exchange callback and only while some rank still
+ * has work, with every search warp parked:
+ *   n_idle / n_busy  warps of this rank without / with work        frame_words  32-bit words of one frame
+ * Inside it the two calls below move frames (HOST buffers, n * frame_words words):
+ *   csolve_gpu_export_frames  splits up to max_frames frames off this rank's busy warps (shallowest untried work
+ *                             first: whole frames below a warp's top frame, the upper half of a top frame)
+ *   csolve_gpu_import_frames  adds frames to this rank's pool; its idle warps pick them up in the next slice
+ * It returns the number of frames it imported (>= 0) or a negative value to abort the search. Typically it wraps one
+ * all-gather of the ranks' (idle, busy) counts and one of the exported frames (csolve_b200/distributed.py). */
+typedef int (*csolve_rebalance_fn)(void *user, csolve_gpu_problem *p, int32_t n_idle, int32_t n_busy, int32_t frame_words);
+int csolve_gpu_set_rebalance(csolve_gpu_problem *p, csolve_rebalance_fn fn, void *user);
+int csolve_gpu_export_frames(csolve_gpu_problem *p, int32_t max_frames, int32_t *frames, int32_t *n_out);
+int csolve_gpu_import_frames(csolve_gpu_problem *p, const int32_t *frames, int32_t n_frames);
+
 /* Batched roots (BASELINE config 2: many instances that share one constraint network and differ only in
  * their root domains, e.g. 10 000 sudokus = the 27 all_different groups + per-instance clue domains).
  * root_dom: n_roots x (2 * n_vars) lo,hi pairs (HOST). The root phase (propagation of every variable's

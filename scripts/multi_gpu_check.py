@@ -25,7 +25,15 @@ cases = [("queens10 ALL", I.queens(10), dict(split_target=300), ("solutions", 72
          ("wcet MAX", I.wcet(), dict(slice_ms=2), ("best", 1560)),
          ("sat200 s1 ANY", I.random_3sat(200, seed=1), dict(prefer_failing=True), ("has_solution", 0)),
          ("sat200 s2 ANY", I.random_3sat(200, seed=2), dict(prefer_failing=True), ("has_solution", 1))]
+# the same again with frontier rebalancing between the ranks (frames shipped from busy ranks to ranks that ran dry);
+# the lopsided cases give rank 0 almost nothing to begin with (split_target=1: one root frame, owned by one rank)
+cases += [(n + " +rebal", t, dict(kw, rebalance=True), w) for n, t, kw, w in cases[:]]
+cases += [("queens13 lopsided +rebal", I.queens(13), dict(split_target=1, slice_ms=1, rebalance=True), ("solutions", 73712)),
+          ("queens13 lopsided", I.queens(13), dict(split_target=1, slice_ms=1, exchange=True), ("solutions", 73712)),
+          ("sat200 s1 lopsided +rebal", I.random_3sat(200, seed=1), dict(prefer_failing=True, split_target=1, slice_ms=2, rebalance=True), ("has_solution", 0)),
+          ("sat200 s1 lopsided", I.random_3sat(200, seed=1), dict(prefer_failing=True, split_target=1, slice_ms=2), ("has_solution", 0))]
 ok = True
+counts = {}
 for name, text, kw, (key, want) in cases:
     m = cb.Model(text)
     p = cb.GpuProblem(m, device=local)
@@ -38,6 +46,13 @@ for name, text, kw, (key, want) in cases:
     if rank == 0:
         print("%-14s world=%d %s=%s (want %s) %s nodes=%d rank0_nodes=%d wall=%.1f ms" % (
             name, dist.get_world_size(), key, out[key], want, "OK" if good else "WRONG", out["nodes"], mine.nodes, dt * 1e3), flush=True)
+    if "ALL" in name or "lopsided" in name and "queens" in name:
+        # all-solutions counters are traversal-independent: rebalancing must not change them
+        ref = counts.setdefault(name.replace(" +rebal", ""), (out["solutions"], out["nodes"], out["cuts"]))
+        if ref != (out["solutions"], out["nodes"], out["cuts"]):
+            ok = False
+            if rank == 0:
+                print("   counters differ from the run without rebalancing: %s vs %s" % ((out["solutions"], out["nodes"], out["cuts"]), ref))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

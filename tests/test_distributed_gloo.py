@@ -98,3 +98,99 @@ def test_partitioned_incumbent_min():
     assert a["has_solution"] == 1
     # 6-queens solutions: (2,4,6,1,3,5) (3,6,2,5,1,4) (4,1,5,2,6,3) (5,3,1,6,4,2): min X1+X2 = 5
     assert a["best"] == 5
+
+
+# ---- frontier rebalancing between ranks (csolve_b200/distributed.py: plan_transfers / make_rebalance) -----------
+def test_plan_transfers():
+    sys.path.insert(0, ROOT)
+    from csolve_b200.distributed import plan_transfers
+    assert plan_transfers([10, 12], 64) == [[0, 0], [0, 0]]                 # nobody ran dry
+    assert plan_transfers([0, 0], 64) == [[0, 0], [0, 0]]                   # nobody has anything
+    g = plan_transfers([0, 1000], 64)                                       # capped by max_frames
+    assert g == [[0, 0], [64, 0]]
+    g = plan_transfers([0, 40, 0, 8], 1024)                                 # fair = 12: rank 1 spares min(20, 28), rank 3 nothing
+    assert g[1] == [10, 0, 10, 0] and g[3] == [0, 0, 0, 0] and g[0] == [0] * 4
+    for busy in ([0, 3], [5, 0, 0, 0, 0, 0, 0, 0], [0, 4736, 4736, 0]):
+        g = plan_transfers(busy, 1024)
+        for d, row in enumerate(g):
+            assert sum(row) <= busy[d] // 2 and (busy[d] > 0 or sum(row) == 0)
+            assert all(x == 0 for r, x in enumerate(row) if busy[r] > 0)     # only ranks that ran dry receive
+
+
+def _rebalance_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    import csolve_b200 as cb
+    from csolve_b200 import distributed as D
+
+    FW = 12
+
+    class SlicedFake:
+        """stands in for GpuProblem: a bag of unit-work frames, 10 of them searched per slice; the per-slice
+        protocol (exchange, then rebalance while somebody still works) is the one of csolve_gpu_solve()"""
+
+        def __init__(self, n):
+            self.frames = [np.full(FW, 1000 * rank + i, np.int32) for i in range(n)]
+            self.done_ids = []
+            self.exchange = self.rebalance = None
+
+        def set_exchange(self, fn):
+            self.exchange = fn
+
+        def set_rebalance(self, fn):
+            self.rebalance = fn
+
+        def export_frames(self, n):
+            n = min(n, len(self.frames) // 2)
+            out, self.frames = self.frames[:n], self.frames[n:]
+            return np.stack(out) if out else np.zeros((0, FW), np.int32)
+
+        def import_frames(self, fr):
+            self.frames += [np.array(f) for f in fr]
+            return len(fr)
+
+        def solve(self, part_rank=0, part_count=1, **kw):
+            slices = 0
+            while True:
+                for f in self.frames[:10]:
+                    self.done_ids.append(int(f[0]))
+                self.frames = self.frames[10:]
+                slices += 1
+                local_done = 0 if self.frames else 1
+                _, _, all_done = self.exchange(0, 0, local_done)
+                if all_done:
+                    break
+                self.rebalance(self, 0 if self.frames else 8, len(self.frames), FW)
+            r = _Res()
+            r.solutions = len(self.done_ids); r.nodes = r.cuts = r.props = r.clause_visits = 0
+            r.kernel_launches = slices
+            r.best = 0; r.has_solution = 1; r.timed_out = 0; r.kernel_ms = float(slices); r.expand_ms = 0.0
+            return r
+
+    prob = SlicedFake(200 if rank == 0 else 0)
+    out, mine = D.solve_partitioned(prob, cb.OBJ_ALL, rebalance=True)
+    q.put((rank, out, sorted(prob.done_ids)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rebalance_moves_frames_to_the_rank_that_ran_dry():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rebalance_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=120) for _ in procs], key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids0, ids1 = outs[0][2], outs[1][2]
+    assert sorted(ids0 + ids1) == list(range(200))          # every frame searched exactly once
+    assert len(ids1) > 40                                   # the idle rank took a real share
+    assert outs[0][1]["solutions"] == 200 and outs[0][1] == outs[1][1]
+    assert outs[0][1]["kernel_ms"] < 20                     # 200 frames at 10 per slice on one rank would be 20 slices

@@ -331,6 +331,53 @@ def test_exchange_callback_injects_incumbent_and_stops_any():
     assert r2.has_solution == 0 and r2.nodes < 21000000
 
 
+@pytest.mark.parametrize("name,order,general", [("queens15", cb.ORDER_NONE, False), ("queens13", cb.ORDER_NONE, True),
+                                                ("queens9", cb.ORDER_SMALLEST_DOMAIN, True), ("sat50", cb.ORDER_NONE, True)])
+def test_rebalance_export_import_keeps_the_counts(name, order, general, monkeypatch):
+    """the frontier-rebalancing hook (csolve_gpu_export_frames / import_frames), emulated in one process: after every
+    slice frames are split off the busy warps and shipped -- back to the same rank, or held for one slice as if they
+    came from another rank. Every node must still be searched exactly once: the counters equal those of the plain
+    search (which test_all_solutions_counters_equal_oracle ties to the oracle's tree)."""
+    text = I.random_3sat(50, seed=1, objective="ALL") if name == "sat50" else I.queens(int(name[6:]))
+    if general:
+        monkeypatch.setenv("CSOLVE_NO_LOV", "1")       # general kernel: slow enough for several 1 ms slices
+    m = cb.Model(text)
+    p = cb.GpuProblem(m)
+    base = p.solve(order=order)
+    moved = []
+    held = []
+
+    def exchange(best, found, local_done):
+        return best, found, 1 if (local_done and not held) else 0      # not done while frames are in transit
+
+    def rebalance(prob, n_idle, n_busy, fw):
+        got = 0
+        if held:                                    # frames "received from another rank"
+            got += prob.import_frames(held.pop())
+        if n_busy > 0:
+            fr = prob.export_frames(48)
+            assert fr.shape[1] == fw
+            moved.append(fr.shape[0])
+            if fr.shape[0]:
+                if len(moved) % 2:
+                    held.append(fr.copy())
+                else:
+                    got += prob.import_frames(fr)
+        return got
+
+    p.set_exchange(exchange)
+    p.set_rebalance(rebalance)
+    r = p.solve(order=order, slice_ms=1, split_target=64)
+    p.set_rebalance(None)
+    p.set_exchange(None)
+    assert (r.solutions, r.nodes, r.cuts) == (base.solutions, base.nodes, base.cuts)
+    assert not held
+    if name == "queens15":
+        assert r.solutions == 2279184
+    if name in ("queens15", "queens13"):
+        assert sum(moved) > 0                       # the search was long enough to be rebalanced at least once
+
+
 def test_conflict_learning_keeps_results_and_learns_sound_nogoods():
     """-c true on the device (src/conflict.c): identical counts / status, and every learned nogood is implied
     by the model (adding its literals as constraints leaves no solution)."""
