@@ -897,17 +897,21 @@ __device__ __forceinline__ bool lov_fixpoint(const LovTables &t, int V, bool has
 __device__ __forceinline__ bool lov_fixpoint_bits(const LovTables &t, int V, int vbase, int lane, int &lo, int &hi,
                                                   uint32_t &F, unsigned pend, unsigned &props, unsigned &visits) {
   while (pend) {
-    const int i = __ffs(pend) - 1;
-    pend &= pend - 1;
-    const int w = __shfl_sync(FULL, lo, i);
-    F |= lov_forbid(t.pair[i * 32 + lane], w, vbase);    // lanes >= V read the zero entries of the table: no branch
+    // the forbidden values of ALL variables that just became a value are distributed, then every lane trims once
+    // (the greatest fixpoint does not depend on the order)
+    do {
+      const int i = __ffs(pend) - 1;
+      pend &= pend - 1;
+      const int w = __shfl_sync(FULL, lo, i);
+      F |= lov_forbid(t.pair[i * 32 + lane], w, vbase);    // lanes >= V read the zero entries of the table: no branch
+      visits++;                                            // counted in variables here, scaled by V when flushed
+    } while (pend);
     const bool was = lo == hi;
     const int olo = lo, ohi = hi;
     const bool alive = lov_trim(F, vbase, lo, hi);
     if (__any_sync(FULL, !alive)) return false;
-    pend |= __ballot_sync(FULL, !was && lo == hi);
+    pend = __ballot_sync(FULL, !was && lo == hi);
     props += (lo != olo || hi != ohi) ? 1u : 0u;      // per lane; summed over the warp when the counters are flushed
-    visits += (unsigned)V;
   }
   return true;
 }
@@ -956,7 +960,10 @@ k_search_lov(const SearchArgs a) {
   SearchCtl *ctl = a.ctl;
   const bool act = lane < V;
   const bool has_consts = m.n_lov_cval > 0;
-  const int vbase = m.lov_vbase;
+  // BITS: inside the kernel a value is its bit index in the value sets (value - lov_vbase, 0..31); zb is added back
+  // wherever a value leaves the kernel (HBM frames, stored solutions). Saves the +- vbase of every trim and shift.
+  const int zb = BITS ? m.lov_vbase : 0;
+  const int vbase = BITS ? 0 : m.lov_vbase;
 
   int level = a.wstate[gw].level, base = a.wstate[gw].base;
   Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
@@ -976,10 +983,14 @@ k_search_lov(const SearchArgs a) {
       const int mk = __ldcg(&g[FR_MASK]);
       const unsigned it = (unsigned)h0.y, la = (unsigned)h0.z;
       const bool left = it <= la;
-      reinterpret_cast<int4 *>(sf)[0] = make_int4(left ? (int)((unsigned)h0.w + ((it + 1) >> 1)) : h0.w, left ? (int)(la - it + 1u) : 0, h0.x, h1.y);
+      reinterpret_cast<int4 *>(sf)[0] = make_int4((left ? (int)((unsigned)h0.w + ((it + 1) >> 1)) : h0.w) - zb, left ? (int)(la - it + 1u) : 0, h0.x, h1.y);
       reinterpret_cast<int2 *>(sf)[2] = make_int2(mk, h1.w);
     }
-    if (act) reinterpret_cast<int2 *>(sf + 8)[lane] = __ldcg(reinterpret_cast<const int2 *>(g + dofs) + lane);
+    if (act) {
+      int2 d = __ldcg(reinterpret_cast<const int2 *>(g + dofs) + lane);
+      d.x -= zb; d.y -= zb;
+      reinterpret_cast<int2 *>(sf + 8)[lane] = d;
+    }
     if (BITS) {
       __syncwarp();
       const uint32_t F = lov_rebuild_F(T, V, vbase, lane, sf + 8);
@@ -992,11 +1003,15 @@ k_search_lov(const SearchArgs a) {
       const int4 s0 = reinterpret_cast<const int4 *>(sf)[0];
       const int2 s1 = reinterpret_cast<const int2 *>(sf)[2];
       const unsigned rm = (unsigned)s0.y;
-      __stcg(reinterpret_cast<int4 *>(g), make_int4(s0.z, rm ? 0 : 1, rm ? (int)(rm - 1u) : 0, s0.x));
-      __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(rm ? (int)((unsigned)s0.x + rm - 1u) : s0.x, s0.w, 0, s1.y));
+      __stcg(reinterpret_cast<int4 *>(g), make_int4(s0.z, rm ? 0 : 1, rm ? (int)(rm - 1u) : 0, s0.x + zb));
+      __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4((rm ? (int)((unsigned)s0.x + rm - 1u) : s0.x) + zb, s0.w, 0, s1.y));
       __stcg(&g[FR_MASK], s1.x);
     }
-    if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, reinterpret_cast<const int2 *>(sf + 8)[lane]);
+    if (act) {
+      int2 d = reinterpret_cast<const int2 *>(sf + 8)[lane];
+      d.x += zb; d.y += zb;
+      __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, d);
+    }
   };
 
   if (!EXPAND && level >= base) {
@@ -1143,7 +1158,7 @@ k_search_lov(const SearchArgs a) {
           slot = __shfl_sync(FULL, slot, 0);
           if (slot < a.max_solutions) {
             int *dst = a.solbuf + (size_t)slot * (V + 1);
-            if (act) dst[lane] = lo;
+            if (act) dst[lane] = lo + zb;
             if (lane == 0) dst[V] = 0;
           }
         }
@@ -1188,11 +1203,11 @@ k_search_lov(const SearchArgs a) {
         if (slot < a.out_cap) {
           int *g = a.items_out + (size_t)slot * fw;
           if (lane == 0) {
-            __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)(nrem - 1u), nlo));
-            __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nhi, flevel + 1, 0, (int)chash));
+            __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)(nrem - 1u), nlo + zb));
+            __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nhi + zb, flevel + 1, 0, (int)chash));
             __stcg(&g[FR_MASK], (int)nmask);
           }
-          if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, make_int2(lo, hi));
+          if (act) __stcg(reinterpret_cast<int2 *>(g + dofs) + lane, make_int2(lo + zb, hi + zb));
         } else if (lane == 0) {
           atomicAdd(&ctl->out_dropped, 1);
         }
@@ -1279,7 +1294,7 @@ k_search_lov(const SearchArgs a) {
             frame_out(own, g);
             __syncwarp();
             if (lane == 0) {
-              __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], glo); __stcg(&g[FR_HI], (int)((unsigned)glo + give - 1u));
+              __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], glo + zb); __stcg(&g[FR_HI], (int)((unsigned)glo + give - 1u) + zb);
               __stcg(&g[FR_LAST], (int)(give - 1u));
             }
             if (publish_slot(a, lane, slot)) break;
@@ -1312,7 +1327,7 @@ k_search_lov(const SearchArgs a) {
     a.wstate[gw].claim_base = cl.base; a.wstate[gw].claim_mask = cl.mask;
     unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
     c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
-    c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols;
+    c[CNT_VISITS] += BITS ? (unsigned long long)visits * (unsigned)V : visits; c[CNT_SOLUTIONS] += sols;
     c[CNT_WAIT] += (unsigned long long)waited; c[CNT_CLAIMS] += claims;
     c[CNT_POLLS] += dbg_polls; c[CNT_WANTED] += dbg_wanted; c[CNT_DONATED] += dbg_donated;
     c[CNT_LASTWORK] = (unsigned long long)(lastwork >= 0 ? lastwork : clock64() - t0);
