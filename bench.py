@@ -28,12 +28,14 @@ UNIT = "nodes/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queens", type=int, default=16, help="board size of the workload (BASELINE config 3: 14..16)")
     ap.add_argument("--order", default="none")
-    ap.add_argument("--cpu-queens", type=int, default=12, help="board size of the bounded CPU sample")
+    ap.add_argument("--cpu-queens", type=int, default=0,
+                    help="board size of the bounded CPU sample (default: 13-queens, ~10 s, for cpu_baseline; 12-queens, "
+                         "~2 s per step, for the steps of --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -74,7 +76,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_queens
+    n = args.cpu_queens or 12
     for _ in range(max(args.warmup, 0) and 1):   # one untimed run is enough to page the binary in
         cpu_reference_run(min(n, 10))
     nodes = 0
@@ -272,10 +274,11 @@ def run_ours(args):
                          "note": "rank 0; algorithmic bytes = nodes x 2 x (8V+16); the DFS stacks live in shared memory during a slice, so real DRAM traffic is far below this nominal figure (DESIGN.md)"},
         }
         if not args.no_cpu_baseline and world == 1:
-            c, dt, kind, sols = cpu_reference_run(args.cpu_queens)
+            nq = args.cpu_queens or 13
+            c, dt, kind, sols = cpu_reference_run(nq)
             line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": "%d-queens all-solutions, %d nodes in %.2f s, single thread, default flags"
-                                              % (args.cpu_queens, c, dt)}
+                                              % (nq, c, dt)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

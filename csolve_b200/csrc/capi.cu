@@ -48,19 +48,21 @@ int fail(int code, const std::string &msg) {
 struct WsBlock { void *p; size_t bytes; };
 std::vector<WsBlock> g_ws_free;
 
-cudaError_t ws_alloc(void **out, size_t bytes) {
+cudaError_t ws_alloc(void **out, size_t bytes, size_t *got = nullptr) {
   for (size_t i = 0; i < g_ws_free.size(); i++) {
     if (g_ws_free[i].bytes >= bytes && g_ws_free[i].bytes <= bytes + bytes / 4 + 4096) {
       *out = g_ws_free[i].p;
+      if (got) *got = g_ws_free[i].bytes;
       g_ws_free.erase(g_ws_free.begin() + i);
       return cudaSuccess;
     }
   }
+  if (got) *got = bytes;
   return cudaMalloc(out, bytes);
 }
 void ws_free(void *p, size_t bytes) {
   if (p == nullptr) return;
-  if (g_ws_free.size() >= 16) { cudaFree(g_ws_free.front().p); g_ws_free.erase(g_ws_free.begin()); }
+  if (g_ws_free.size() >= 96) { cudaFree(g_ws_free.front().p); g_ws_free.erase(g_ws_free.begin()); }
   g_ws_free.push_back(WsBlock{p, bytes});
 }
 void ws_release_all() {
@@ -68,11 +70,35 @@ void ws_release_all() {
   g_ws_free.clear();
 }
 
+// the same cache for the small per-problem buffers: cudaMalloc / cudaFree take milliseconds each once the process
+// has peer mappings (one process per GPU under NCCL), which showed up as 20-40 ms of end-to-end time per search
+std::vector<WsBlock> g_live;
+cudaError_t cmalloc(void **out, size_t bytes) {
+  bytes = std::max<size_t>(bytes, 256);
+  size_t got = bytes;
+  cudaError_t e = ws_alloc(out, bytes, &got);
+  if (e == cudaSuccess) g_live.push_back(WsBlock{*out, got});
+  return e;
+}
+template <class T> cudaError_t cmalloc(T **out, size_t bytes) { return cmalloc(reinterpret_cast<void **>(out), bytes); }
+void cfree(void *p) {
+  if (p == nullptr) return;
+  for (size_t i = 0; i < g_live.size(); i++) {
+    if (g_live[i].p == p) {
+      // a recycled block may be larger than what was asked for: keep its true size
+      ws_free(p, g_live[i].bytes);
+      g_live.erase(g_live.begin() + i);
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
 template <class T>
 int upload(const std::vector<T> &h, const T **d) {
   T *p = nullptr;
   size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
-  CUDA_TRY(cudaMalloc(&p, bytes));
+  CUDA_TRY(cmalloc(&p, bytes));
   if (!h.empty()) CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   *d = p;
   return CSOLVE_OK;
@@ -132,10 +158,10 @@ struct csolve_gpu_problem {
   const SearchArgs *parked = nullptr;   // search arguments while the rebalance callback runs (export / import are valid)
 
   ~csolve_gpu_problem() {
-    for (void *p : allocs) cudaFree(p);
-    ws_free(stacks, stacks_bytes); cudaFree(wstate); cudaFree(wcount); cudaFree(totals); cudaFree(ctl);
-    ws_free(pool_a, pool_bytes); ws_free(pool_b, pool_bytes); cudaFree(scratch); cudaFree(solbuf); cudaFree(ready);
-    cudaFree(ng.lits); cudaFree(ng.start); cudaFree(ng.len); cudaFree(ng.watch); cudaFree(ng.watch_n); cudaFree(ng.counters);
+    for (void *p : allocs) cfree(p);
+    ws_free(stacks, stacks_bytes); cfree(wstate); cfree(wcount); cfree(totals); cfree(ctl);
+    ws_free(pool_a, pool_bytes); ws_free(pool_b, pool_bytes); cfree(scratch); cfree(solbuf); cfree(ready);
+    cfree(ng.lits); cfree(ng.start); cfree(ng.len); cfree(ng.watch); cfree(ng.watch_n); cfree(ng.counters);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -144,6 +170,9 @@ extern "C" const char *csolve_last_error(void) { return csolve_front::last_error
 extern "C" int csolve_abi_version(void) { return CSOLVE_B200_ABI_VERSION; }
 
 extern "C" int csolve_gpu_init(const csolve_gpu_config *cfg) {
+  // already on this device: nothing to ask the driver again (cudaDevAttrClockRate is a live query that takes tens
+  // of milliseconds every now and then -- it showed up as 20..100 ms of "load" time in the end-to-end numbers)
+  if (g_device >= 0 && g_device == (cfg ? cfg->device : 0)) return cudaSetDevice(g_device) == cudaSuccess ? CSOLVE_OK : fail(CSOLVE_ERR_CUDA, "cudaSetDevice failed");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -249,7 +278,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
   const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0);
   if (p->stacks != nullptr && p->ws_lov != ws_key) {
     // the lane-owns-variable and the general kernels have different occupancies: rebuild the per-warp state
-    ws_free(p->stacks, p->stacks_bytes); cudaFree(p->wstate); cudaFree(p->wcount); cudaFree(p->totals); cudaFree(p->ctl); cudaFree(p->scratch);
+    ws_free(p->stacks, p->stacks_bytes); cfree(p->wstate); cfree(p->wcount); cfree(p->totals); cfree(p->ctl); cfree(p->scratch);
     p->stacks = nullptr; p->wstate = nullptr; p->wcount = nullptr; p->totals = nullptr; p->ctl = nullptr; p->scratch = nullptr;
   }
   if (p->stacks == nullptr) {
@@ -261,11 +290,11 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
     const size_t stack_words = (size_t)p->n_warps * (m.n_vars + 1) * m.frame_words;
     p->stacks_bytes = stack_words * sizeof(int32_t);
     CUDA_TRY(ws_alloc((void **)&p->stacks, p->stacks_bytes));
-    CUDA_TRY(cudaMalloc(&p->wstate, (size_t)p->n_warps * sizeof(WarpState)));
-    CUDA_TRY(cudaMalloc(&p->wcount, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&p->totals, CNT_WIDTH * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&p->ctl, sizeof(SearchCtl)));
-    CUDA_TRY(cudaMalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
+    CUDA_TRY(cmalloc(&p->wstate, (size_t)p->n_warps * sizeof(WarpState)));
+    CUDA_TRY(cmalloc(&p->wcount, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long)));
+    CUDA_TRY(cmalloc(&p->totals, CNT_WIDTH * sizeof(unsigned long long)));
+    CUDA_TRY(cmalloc(&p->ctl, sizeof(SearchCtl)));
+    CUDA_TRY(cmalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
   int target = opt.split_target > 0 ? opt.split_target : p->n_warps * DEFAULT_FRAMES_PER_WARP;
@@ -278,14 +307,14 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
     p->pool_bytes = (size_t)cap * m.frame_words * sizeof(int32_t);
     CUDA_TRY(ws_alloc((void **)&p->pool_a, p->pool_bytes));
     CUDA_TRY(ws_alloc((void **)&p->pool_b, p->pool_bytes));
-    cudaFree(p->ready); p->ready = nullptr;
-    CUDA_TRY(cudaMalloc(&p->ready, (size_t)cap * sizeof(int32_t)));
+    cfree(p->ready); p->ready = nullptr;
+    CUDA_TRY(cmalloc(&p->ready, (size_t)cap * sizeof(int32_t)));
     p->pool_cap = cap;
   }
   int sol_cap = std::max(opt.max_solutions, m.obj_var >= 0 ? 4096 : (m.objective == CSOLVE_OBJ_ANY ? 1 : 0));
   if (sol_cap > p->sol_cap) {
-    cudaFree(p->solbuf); p->solbuf = nullptr;
-    CUDA_TRY(cudaMalloc(&p->solbuf, (size_t)sol_cap * (m.n_vars + 1) * sizeof(int32_t)));
+    cfree(p->solbuf); p->solbuf = nullptr;
+    CUDA_TRY(cmalloc(&p->solbuf, (size_t)sol_cap * (m.n_vars + 1) * sizeof(int32_t)));
     p->sol_cap = sol_cap;
   }
   return CSOLVE_OK;
@@ -315,9 +344,9 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     NogoodPool &g = p->ng;
     if (g.lits == nullptr) {
       g.cap_ng = 1 << 18; g.cap_lits = 1 << 23; g.cap_w = 4096;
-      CUDA_TRY(cudaMalloc(&g.lits, (size_t)g.cap_lits * 4)); CUDA_TRY(cudaMalloc(&g.start, (size_t)g.cap_ng * 4));
-      CUDA_TRY(cudaMalloc(&g.len, (size_t)g.cap_ng * 4)); CUDA_TRY(cudaMalloc(&g.watch, (size_t)p->dev.n_vars * g.cap_w * 4));
-      CUDA_TRY(cudaMalloc(&g.watch_n, (size_t)p->dev.n_vars * 4)); CUDA_TRY(cudaMalloc(&g.counters, 8 * 4));
+      CUDA_TRY(cmalloc(&g.lits, (size_t)g.cap_lits * 4)); CUDA_TRY(cmalloc(&g.start, (size_t)g.cap_ng * 4));
+      CUDA_TRY(cmalloc(&g.len, (size_t)g.cap_ng * 4)); CUDA_TRY(cmalloc(&g.watch, (size_t)p->dev.n_vars * g.cap_w * 4));
+      CUDA_TRY(cmalloc(&g.watch_n, (size_t)p->dev.n_vars * 4)); CUDA_TRY(cmalloc(&g.counters, 8 * 4));
     }
     CUDA_TRY(cudaMemsetAsync(g.watch, 0xff, (size_t)p->dev.n_vars * g.cap_w * 4, p->stream));
     CUDA_TRY(cudaMemsetAsync(g.watch_n, 0, (size_t)p->dev.n_vars * 4, p->stream));
@@ -379,7 +408,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   int32_t *d_gprio = nullptr;
   if (opt.prefer_failing && !m.lov) {
     // device-wide dynamic priorities, seeded with the parse-time weights (env_t.prio)
-    CUDA_TRY(cudaMalloc(&d_gprio, (size_t)V * sizeof(int32_t)));
+    CUDA_TRY(cmalloc(&d_gprio, (size_t)V * sizeof(int32_t)));
     CUDA_TRY(cudaMemcpyAsync(d_gprio, cm.prio.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   }
   // a slice ends so that the host can check the time limit / run the rank exchange; without either the kernel only
@@ -568,7 +597,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   cudaEventElapsedTime(&ms_search, ev1, ev2);
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
 
-  cudaFree(d_gprio);
+  cfree(d_gprio);
   if (batch) {
     if (root_solutions) CUDA_TRY(cudaMemcpy(root_solutions, d_rsol, (size_t)n_roots * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     if (root_failed) CUDA_TRY(cudaMemcpy(root_failed, d_rfail, n_roots, cudaMemcpyDeviceToHost));

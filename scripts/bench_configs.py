@@ -83,10 +83,14 @@ if __name__ == "__main__":
     m = cb.Model(I.sudoku("." * 81))
     p = cb.GpuProblem(m)
     roots = I.sudoku_roots(m.var_names, grids)
-    p.solve_batch(roots[:64], order="smallest-domain")
-    t0 = time.perf_counter()
-    r, counts, failed = p.solve_batch(roots, order="smallest-domain")
-    wall = time.perf_counter() - t0
+    p.solve_batch(roots, order="smallest-domain")          # warm-up (workspace allocation, lazy kernel loading)
+    wall = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r_, counts, failed = p.solve_batch(roots, order="smallest-domain")
+        w_ = time.perf_counter() - t0
+        if wall is None or w_ < wall:
+            r, wall = r_, w_
     assert counts.tolist() == [1] * n_inst and not failed.any()
     sample = 20
     cpu_secs = 0.0
