@@ -264,8 +264,9 @@ extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes
 namespace {
 
 // slots behind the expanded root frontier that stay free for donated frames (a ticket queue: one slot per waiting
-// warp plus the frames delivered ahead of their tickets)
-int ring_min_frames(int n_warps) { return 2 * n_warps + 1024; }
+// warp, plus frames delivered ahead of their tickets by racing donors -- at most one per warp -- plus one import of at
+// most n_warps frames from another rank)
+int ring_min_frames(int n_warps) { return 4 * n_warps + 1024; }
 
 // Breadth-first expansion target. The ticket queue keeps every warp busy to the end whatever the size of the root
 // frontier (measured: 16-queens search time is the same from 16 to 256 frames per warp), so the frontier only has to

@@ -109,6 +109,23 @@ def test_counters_do_not_depend_on_the_split(split):
     assert (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts) == (352, o.calls, o.cuts)
 
 
+@pytest.mark.parametrize("general", [False, True])
+@pytest.mark.parametrize("n,split,slice_ms", [(11, 1, 1), (12, 1, 1), (12, 40, 1), (13, 1, 2)])
+def test_ticket_queue_hands_out_the_whole_tree(n, split, slice_ms, general, monkeypatch):
+    """split_target=1: the expansion stops at the first level with a frame or more, so almost every warp gets its
+    work through the donation ring (tickets, served slots, tickets given back at the many slice ends); the counters
+    must not notice"""
+    if general:
+        monkeypatch.setenv("CSOLVE_NO_LOV", "1")
+    m = cb.Model(I.queens(n))
+    p = cb.GpuProblem(m)
+    base = p.solve()
+    for _ in range(3):
+        r = p.solve(split_target=split, slice_ms=slice_ms)
+        assert (r.solutions, r.nodes, r.cuts) == (base.solutions, base.nodes, base.cuts)
+    assert base.solutions == {11: 2680, 12: 14200, 13: 73712}[n]
+
+
 def test_stored_solutions_are_valid_and_distinct():
     m = cb.Model(I.queens(8))
     r = cb.GpuProblem(m).solve(max_solutions=200)
