@@ -550,6 +550,8 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     std::vector<unsigned long long> wc((size_t)p->n_warps * CNT_WIDTH);
     CUDA_TRY(cudaMemcpy(wc.data(), p->wcount, wc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     double wait = 0, claims = 0, lw = 0, lw_max = 0, lw_min = 1e30, nmax = 0;
+    float dbg_ms = 0;
+    cudaEventElapsedTime(&dbg_ms, ev1, ev2);
     for (int w = 0; w < p->n_warps; w++) {
       const unsigned long long *c = &wc[(size_t)w * CNT_WIDTH];
       wait += (double)c[CNT_WAIT]; claims += (double)c[CNT_CLAIMS];
@@ -557,8 +559,8 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
       lw += l; lw_max = std::max(lw_max, l); lw_min = std::min(lw_min, l); nmax = std::max(nmax, (double)c[CNT_NODES]);
     }
     const double khz = (double)g_clock_khz;
-    fprintf(stderr, "[csolve] depth-first phase: %llu slices, %d warps, per warp: waited %.3f ms, %.1f claims, last node at %.3f ms "
-                    "(min %.3f, max %.3f), most nodes on one warp %.0f (avg %.0f), %d frames donated\n", (unsigned long long)slices, p->n_warps,
+    fprintf(stderr, "[csolve] depth-first phase: %.2f ms, %llu slices, %d warps, per warp: waited %.3f ms, %.1f claims, last node at %.3f ms "
+                    "(min %.3f, max %.3f), most nodes on one warp %.0f (avg %.0f), %d frames donated\n", dbg_ms, (unsigned long long)slices, p->n_warps,
             wait / p->n_warps / khz, claims / p->n_warps, lw / p->n_warps / khz, lw_min / khz, lw_max / khz, nmax,
             (double)tot[CNT_NODES] / p->n_warps, ctl.item_count);
     fprintf(stderr, "[csolve]   polls %llu, donation wanted %llu, donated %llu\n", tot[CNT_POLLS], tot[CNT_WANTED], tot[CNT_DONATED]);

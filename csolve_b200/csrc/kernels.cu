@@ -44,8 +44,9 @@ struct WarpCx {
   int *rlo = nullptr, *rhi = nullptr;   // learning: which record last raised lo / lowered hi of a variable in this node
   int cur = -1;                         // ... code of the record being contracted (>= 0 watch record, <= -2 nogood -2 - id)
   __device__ __forceinline__ Dom dom(int v) const {
-    const volatile int *p = d + 2 * v;
-    Dom r; r.lo = p[0]; r.hi = p[1];
+    // one 8-byte load (the pair is 8-byte aligned): bounds published by other lanes are seen, never torn per word
+    const unsigned long long q = *reinterpret_cast<const volatile unsigned long long *>(d + 2 * v);
+    Dom r; r.lo = (int)(unsigned)q; r.hi = (int)(unsigned)(q >> 32);
     return r;
   }
   __device__ __forceinline__ void mark(int v) { atomicOr(&nxt[v >> 5], 1u << (v & 31)); }
@@ -109,18 +110,35 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
   for (;;) {
     cx.nxt = s.nxt;
     bool any = false;
-    for (int w = 0; w < m.mask_words; ++w) {
-      unsigned bits = s.cur[w];
-      if (bits) any = true;
-      while (bits) {
-        const int x = (w << 5) + __ffs(bits) - 1;
+    // The changed variables of this round, 1024 at a time: every lane loads one word of the mask, a ballot finds the
+    // non-empty words, and the variables are handed out TWO at a time -- lanes 0..15 contract the watch records of one,
+    // lanes 16..31 those of the other (watch lists are short: 13 records on average for 3-SAT, 3(N-1) for N-queens);
+    // a single variable gets the whole warp. The fixpoint does not depend on the order.
+    for (int wb = 0; wb < m.mask_words; wb += 32) {
+      const unsigned myw = wb + lane < m.mask_words ? s.cur[wb + lane] : 0u;
+      unsigned nz = __ballot_sync(FULL, myw != 0u);
+      if (nz) any = true;
+      unsigned bits = 0;
+      int wcur = 0;
+      for (;;) {
+        int xA = -1, xB = -1;
+        if (bits == 0u && nz != 0u) { wcur = __ffs((int)nz) - 1; nz &= nz - 1; bits = __shfl_sync(FULL, myw, wcur); }
+        if (bits == 0u) break;
+        xA = ((wb + wcur) << 5) + __ffs((int)bits) - 1;
         bits &= bits - 1;
+        if (!LEARN) {
+          if (bits == 0u && nz != 0u) { wcur = __ffs((int)nz) - 1; nz &= nz - 1; bits = __shfl_sync(FULL, myw, wcur); }
+          if (bits != 0u) { xB = ((wb + wcur) << 5) + __ffs((int)bits) - 1; bits &= bits - 1; }
+        }
+        const bool two = xB >= 0;
+        const int x = (two && lane >= 16) ? xB : xA;
+        const int first = two ? (lane & 15) : lane, stride = two ? 16 : 32;
         // snapshot of the dequeued variable; bounds published by different lanes may have
         // crossed since it was queued: an empty domain is a failure
         const Dom X = cx.dom(x);
         if (X.lo > X.hi) { failed = true; empty_var = x; }
         const int b = wptr[x], e = wptr[x + 1];
-        for (int i = b + lane; i < e; i += 32) {
+        for (int i = b + first; i < e; i += stride) {
           const int4 q = wrec[i];
           WatchRec rec; rec.w0 = (uint32_t)q.x; rec.c[0] = q.y; rec.c[1] = q.z; rec.c[2] = q.w;
           if (LEARN) cx.cur = i;
@@ -140,6 +158,7 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
             visits++;
           }
         }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -535,6 +554,8 @@ k_search(const SearchArgs a) {
   unsigned long long nodes = 0, cuts = 0, sols = 0, refresh = 0;
   unsigned props = 0, visits = 0;
   const long long t0 = clock64();
+  long long waited = 0, lastwork = -1;     // load-balance diagnostics (CSOLVE_DEBUG)
+  unsigned claims = 0;
 
   // The header of the top frame lives in registers and its domains (the state BEFORE this level's
   // assignment) in s.p while the warp iterates over the level's values; HBM is touched only when
@@ -556,8 +577,12 @@ k_search(const SearchArgs a) {
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
       } else {
+        const long long w0 = clock64();
+        lastwork = w0 - t0;
         const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry);
+        waited += clock64() - w0;
         if (slot < 0) break;
+        claims++;
         src = a.pool + (size_t)slot * fw;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
@@ -828,6 +853,8 @@ k_search(const SearchArgs a) {
     unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
     c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
     c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols; c[CNT_REFRESH] += refresh;
+    c[CNT_WAIT] += (unsigned long long)waited; c[CNT_CLAIMS] += claims;
+    c[CNT_LASTWORK] = (unsigned long long)(lastwork >= 0 ? lastwork : clock64() - t0);
   }
 }
 
