@@ -301,6 +301,199 @@ CSOLVE_HD_NOINLINE bool contract_generic(Cx &cx, const DevModel &m, int root, in
   return true;
 }
 
+// ---- the same contractor with the operand values of one call memoised ---------------------------------
+// propagate_<op>() re-evaluates the sibling subtree at every level (eval_*() from scratch, src/eval.c): on wcet's
+// 57-node objective clause, a left-deep sum 16 levels deep, one contraction costs about n^2 / 4 node evaluations.
+// Here the value of EVERY node of the clause is computed once, bottom-up over the contiguous post-order range, and
+//   * the operand evaluated BEFORE anything is narrowed at a level (the left one) is taken from that table
+//     (a variable leaf is re-read: free),
+//   * the operand evaluated AFTER the other side was narrowed (the right one) has its own range re-evaluated, which
+//     also refreshes the table for the levels below.
+// Without repeated variables this is value for value the reference's sequence; when a variable occurs in both
+// operands the left value may be the one from the start of the call, i.e. wider, so a single call can narrow less
+// than the reference's. The FIXPOINT is the same: at a state where a call changes nothing its table is exact, so it
+// acts exactly like the reference's call there, and a weaker sound contractor cannot stop above the greatest common
+// fixpoint (tests/test_gpu_parity.py compares post-fixpoint domains with the compiled reference).
+static const int MEMO_NODES = 96;    // longest clause the memo table holds; longer ones take contract_generic
+
+template <class Cx>
+CSOLVE_HD void eval_range(Cx &cx, const DevModel &m, int from, int to, int first, Dom *val) {
+  for (int j = from; j <= to; ++j) {
+    const int op = m.node_op[j];
+    const int l = m.node_l[j];
+    Dom out;
+    if (op == CSOLVE_OP_VAR) out = cx.dom(l);
+    else if (op == CSOLVE_OP_CONST) out = mk(l, m.node_r[j]);
+    else if (op == CSOLVE_OP_NEG) { const Dom a = val[l - first]; out = mk(sneg(a.hi), sneg(a.lo)); }
+    else if (op == CSOLVE_OP_NOT) { const Dom a = val[l - first]; out = is_true(a) ? mk(0, 0) : (is_false(a) ? mk(1, 1) : mk(0, 1)); }
+    else out = eval_binary(op, val[l - first], val[m.node_r[j] - first]);
+    val[j - first] = out;
+  }
+}
+
+template <class Cx>
+CSOLVE_HD_NOINLINE bool contract_generic_memo(Cx &cx, const DevModel &m, int root) {
+  const int first = m.node_first[root];
+  Dom val[MEMO_NODES];
+  eval_range(cx, m, first, root, first, val);
+  // value of the operand that is looked at before this level narrows anything
+  auto before = [&](int node) -> Dom {
+    return m.node_op[node] == CSOLVE_OP_VAR ? cx.dom(m.node_l[node]) : val[node - first];
+  };
+  // value of the operand that is looked at after its sibling was narrowed
+  auto after = [&](int node) -> Dom {
+    eval_range(cx, m, m.node_first[node], node, first, val);
+    return val[node - first];
+  };
+  PFrame st[MAX_DEPTH + 2];
+  int sp = 1;
+  st[0].node = root; st[0].lo = 1; st[0].hi = 1; st[0].phase = 0;
+  while (sp > 0) {
+    PFrame &f = st[sp - 1];
+    const int n = f.node;
+    const int op = m.node_op[n];
+    const Dom v = mk(f.lo, f.hi);
+    const int l = m.node_l[n], r = m.node_r[n];
+    switch (op) {
+    case CSOLVE_OP_VAR:
+      if (!contract_var(cx, l, v.lo, v.hi)) return false;
+      sp--;
+      break;
+    case CSOLVE_OP_CONST:
+      if (l > v.hi || r < v.lo) return false;
+      sp--;
+      break;
+    case CSOLVE_OP_NOT:
+      if (is_true(v)) { f.node = l; f.lo = 0; f.hi = 0; f.phase = 0; }
+      else if (is_false(v)) { f.node = l; f.lo = 1; f.hi = 1; f.phase = 0; }
+      else sp--;
+      break;
+    case CSOLVE_OP_NEG:
+      f.node = l; f.lo = sneg(v.hi); f.hi = sneg(v.lo); f.phase = 0;
+      break;
+    case CSOLVE_OP_EQ:
+      if (is_true(v)) {
+        if (f.phase == 0) {
+          const Dom lv = before(l);
+          f.phase = 1;
+          st[sp].node = r; st[sp].lo = lv.lo; st[sp].hi = lv.hi; st[sp].phase = 0; sp++;
+        } else {
+          const Dom rv = after(r);
+          f.node = l; f.lo = rv.lo; f.hi = rv.hi; f.phase = 0;
+        }
+      } else if (is_false(v)) {
+        const Dom lv = before(l), rv = before(r);
+        bool has_l = false, has_r = false;
+        int32_t llo = 0, lhi = 0, rlo = 0, rhi = 0;
+        if (is_single(lv) && lv.lo != DMIN && lv.lo != DMAX) {
+          if (lv.lo == rv.lo) { has_r = true; rlo = lv.lo + 1; rhi = DMAX; }
+          else if (lv.lo == rv.hi) { has_r = true; rlo = DMIN; rhi = lv.lo - 1; }
+        }
+        if (is_single(rv) && rv.lo != DMIN && rv.lo != DMAX) {
+          if (rv.lo == lv.lo) { has_l = true; llo = rv.lo + 1; lhi = DMAX; }
+          else if (rv.lo == lv.hi) { has_l = true; llo = DMIN; lhi = rv.lo - 1; }
+        }
+        if (has_l) { f.node = l; f.lo = llo; f.hi = lhi; f.phase = 0; } else { sp--; }
+        if (has_r) { st[sp].node = r; st[sp].lo = rlo; st[sp].hi = rhi; st[sp].phase = 0; sp++; }
+      } else {
+        sp--;
+      }
+      break;
+    case CSOLVE_OP_LT:
+      if (is_true(v)) {
+        if (f.phase == 0) {
+          const Dom lv = before(l);
+          f.phase = 1;
+          if (lv.lo != DMIN && lv.lo != DMAX) {
+            st[sp].node = r; st[sp].lo = lv.lo + 1; st[sp].hi = DMAX; st[sp].phase = 0; sp++;
+          }
+        } else {
+          const Dom rv = after(r);
+          if (rv.hi != DMIN && rv.hi != DMAX) { f.node = l; f.lo = DMIN; f.hi = rv.hi - 1; f.phase = 0; }
+          else sp--;
+        }
+      } else if (is_false(v)) {
+        if (f.phase == 0) {
+          const Dom lv = before(l);
+          f.phase = 1;
+          st[sp].node = r; st[sp].lo = DMIN; st[sp].hi = lv.hi; st[sp].phase = 0; sp++;
+        } else {
+          const Dom rv = after(r);
+          f.node = l; f.lo = rv.lo; f.hi = DMAX; f.phase = 0;
+        }
+      } else {
+        sp--;
+      }
+      break;
+    case CSOLVE_OP_ADD:
+      if (f.phase == 0) {
+        const Dom cv = before(l);
+        f.phase = 1;
+        st[sp].node = r; st[sp].lo = sadd(v.lo, sneg(cv.hi)); st[sp].hi = sadd(v.hi, sneg(cv.lo));
+        st[sp].phase = 0; sp++;
+      } else {
+        const Dom cv = after(r);
+        f.node = l; f.lo = sadd(v.lo, sneg(cv.hi)); f.hi = sadd(v.hi, sneg(cv.lo)); f.phase = 0;
+      }
+      break;
+    case CSOLVE_OP_MUL: {
+      int32_t tlo = 0, thi = 0;
+      if (f.phase == 0) {
+        const int k = mul_target(v, before(l), &tlo, &thi);
+        if (k < 0) return false;
+        f.phase = 1;
+        if (k > 0) { st[sp].node = r; st[sp].lo = tlo; st[sp].hi = thi; st[sp].phase = 0; sp++; }
+      } else {
+        const int k = mul_target(v, after(r), &tlo, &thi);
+        if (k < 0) return false;
+        if (k > 0) { f.node = l; f.lo = tlo; f.hi = thi; f.phase = 0; } else sp--;
+      }
+      break;
+    }
+    case CSOLVE_OP_AND:
+    case CSOLVE_OP_OR: {
+      const bool both = (op == CSOLVE_OP_AND) ? is_true(v) : is_false(v);
+      const bool either = (op == CSOLVE_OP_AND) ? is_false(v) : is_true(v);
+      if (both) {
+        if (f.phase == 0) {
+          f.phase = 1;
+          st[sp].node = r; st[sp].lo = v.lo; st[sp].hi = v.hi; st[sp].phase = 0; sp++;
+        } else {
+          f.node = l; f.phase = 0;
+        }
+      } else if (either) {
+        if (f.phase == 0) {
+          const Dom lv = before(l);
+          f.phase = 1;
+          if ((op == CSOLVE_OP_AND) ? is_true(lv) : is_false(lv)) {
+            st[sp].node = r; st[sp].lo = v.lo; st[sp].hi = v.hi; st[sp].phase = 0; sp++;
+          }
+        } else {
+          const Dom rv = after(r);
+          if ((op == CSOLVE_OP_AND) ? is_true(rv) : is_false(rv)) { f.node = l; f.phase = 0; }
+          else sp--;
+        }
+      } else {
+        sp--;
+      }
+      break;
+    }
+    default:
+      return false;
+    }
+  }
+  return true;
+}
+
+// clauses the memo table cannot hold (and host-side uses) take the plain rendering
+template <class Cx>
+CSOLVE_HD bool contract_tree(Cx &cx, const DevModel &m, int root) {
+#if defined(__CUDA_ARCH__)
+  if (root - m.node_first[root] < MEMO_NODES) return contract_generic_memo(cx, m, root);
+#endif
+  return contract_generic(cx, m, root);
+}
+
 // ---- specialised contractors ----------------------------------------------------------
 // NOT(EQ(x + c, y)): the false branch of propagate_eq (src/propagate.c:104-134) reached
 // through propagate_not (src/propagate.c:289-301) and propagate_add (src/propagate.c:222-246);
@@ -435,7 +628,7 @@ CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const 
     return ok;
   }
   if (kind == WK_LITS) return contract_lits(cx, n, rec.c[0], rec.c[1], rec.c[2]);
-  return contract_generic(cx, m, m.clause[wrec_arg(rec.w0)].b);
+  return contract_tree(cx, m, m.clause[wrec_arg(rec.w0)].b);
 }
 
 // ---- "lane owns variable" form ---------------------------------------------------------------------
@@ -505,7 +698,7 @@ CSOLVE_HD bool contract_clause(Cx &cx, const DevModel &m, const ClauseRec &rec) 
   switch (rec.kind) {
   case CK_NE_VV: return contract_ne_vv(cx, rec.a, rec.b, rec.c);
   case CK_NE_VC: return contract_ne_vc(cx, rec.a, rec.c);
-  default:       return contract_generic(cx, m, rec.b);
+  default:       return contract_tree(cx, m, rec.b);
   }
 }
 
