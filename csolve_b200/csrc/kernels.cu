@@ -1247,10 +1247,14 @@ k_search_lov(const SearchArgs a) {
         props += (lane == nv && nrem > 1u) ? (unsigned)good : 0u;  // each of those nodes narrows nv to its value (branch-free:
                                                                    // a divergent branch here kept the warp split far into the loop)
       } else {
-        // push: everything stays in shared memory / registers
-        int *nf = sf + sfw;
+        // push: everything stays in shared memory / registers. When the frame has no value left to try after this one
+        // (BITS: what is left of its interval is forbidden -- failed nodes, counted here) the child takes its place
+        // instead of going on top of it: no pop back into an exhausted frame, no reload of it.
+        const bool last_value = BITS ? avail == 0u : rem == 0u;
+        if (BITS && last_value) { n32 += rem; c32 += rem; }
+        int *nf = last_value ? sf : sf + sfw;
         if (lane == 0) {
-          reinterpret_cast<int2 *>(sf)[0] = make_int2(cur, (int)rem);
+          if (!last_value) reinterpret_cast<int2 *>(sf)[0] = make_int2(cur, (int)rem);
           reinterpret_cast<int4 *>(nf)[0] = make_int4(nlo, (int)nrem, nv, flevel + 1);
           reinterpret_cast<int2 *>(nf)[2] = make_int2((int)nmask, (int)fhash);
         }
@@ -1264,7 +1268,7 @@ k_search_lov(const SearchArgs a) {
         }
         var = nv; cur = nlo; rem = nrem;
         flevel = flevel + 1;
-        level++;
+        level += last_value ? 0 : 1;
         __syncwarp();
       }
     }
