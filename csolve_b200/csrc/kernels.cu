@@ -942,6 +942,29 @@ __device__ __forceinline__ bool lov_fixpoint_bits(const LovTables &t, int V, int
   }
   return true;
 }
+// the same fixpoint entered from a search node: the first round has exactly one variable, the decision var := val, and
+// both are warp-uniform -- no bit scan, no shuffle for it
+__device__ __forceinline__ bool lov_fixpoint_bits_node(const LovTables &t, int vbase, int lane, int &lo, int &hi,
+                                                       uint32_t &F, int var, int val, unsigned &props, unsigned &visits) {
+  F |= lov_forbid(t.pair[var * 32 + lane], val, vbase);
+  visits++;
+  for (;;) {
+    const bool was = lo == hi;
+    const int olo = lo, ohi = hi;
+    const bool alive = lov_trim(F, vbase, lo, hi);
+    if (__any_sync(FULL, !alive)) return false;
+    unsigned pend = __ballot_sync(FULL, !was && lo == hi);
+    props += (lo != olo || hi != ohi) ? 1u : 0u;
+    if (pend == 0u) return true;
+    do {
+      const int i = __ffs(pend) - 1;
+      pend &= pend - 1;
+      const int w = __shfl_sync(FULL, lo, i);
+      F |= lov_forbid(t.pair[i * 32 + lane], w, vbase);
+      visits++;
+    } while (pend);
+  }
+}
 // forbidden-value set of this lane's variable for a frame whose domains are in sdom (lo,hi pairs)
 __device__ __forceinline__ uint32_t lov_rebuild_F(const LovTables &t, int V, int vbase, int lane, const int *sdom) {
   uint32_t F = lane < V ? t.fconst[lane] : 0u;
@@ -1153,7 +1176,7 @@ k_search_lov(const SearchArgs a) {
     int lo = plo, hi = phi;
     if (lane == var) { lo = val; hi = val; }
     uint32_t F = pF;
-    const bool ok = BITS ? lov_fixpoint_bits(T, V, vbase, lane, lo, hi, F, 1u << var, props, visits)
+    const bool ok = BITS ? lov_fixpoint_bits_node(T, vbase, lane, lo, hi, F, var, val, props, visits)
                          : lov_fixpoint(T, V, has_consts, lane, lo, hi, 1u << var, props, visits);
     n32++;
 
