@@ -1070,6 +1070,7 @@ k_search_lov(const SearchArgs a) {
   }
 
   bool have = false;
+  int *sf = sst + level * sfw;        // the top frame; moved with the stack (recomputing it cost 8 instructions per node)
   int var = 0, cur = 0, flevel = 0;   // top frame: branching variable, cursor, level
   unsigned rem = 0;                   // ... values left: [cur, cur + rem)
   unsigned fhash = 0, amask = 0;
@@ -1112,11 +1113,11 @@ k_search_lov(const SearchArgs a) {
         if (lane == 0) { __threadfence(); __stcg(&a.ready[(src - a.pool) / fw], 0); }   // slot may be reused
       }
       level = base = L;
+      sf = sst + L * sfw;
       have = false;
       __syncwarp();
     }
 
-    int *sf = sst + level * sfw;
     if (!have) {
       const int4 h0 = reinterpret_cast<const int4 *>(sf)[0];
       const int2 h1 = reinterpret_cast<const int2 *>(sf)[2];
@@ -1152,7 +1153,7 @@ k_search_lov(const SearchArgs a) {
       // (`avail` is kept in a register while the frame is the top one)
       if (avail == 0u) {
         n32 += rem; c32 += rem;
-        level--;
+        level--; sf -= sfw;
         have = false;
         continue;
       }
@@ -1164,7 +1165,7 @@ k_search_lov(const SearchArgs a) {
       rem -= skipped + 1u;
     } else {
       if (rem == 0u) {
-        level--;
+        level--; sf -= sfw;
         have = false;
         continue;
       }
@@ -1292,6 +1293,7 @@ k_search_lov(const SearchArgs a) {
         var = nv; cur = nlo; rem = nrem;
         flevel = flevel + 1;
         level += last_value ? 0 : 1;
+        sf = nf;
         __syncwarp();
       }
     }
