@@ -370,7 +370,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   CUDA_TRY(cudaMemcpyAsync(p->wstate, ws.data(), ws.size() * sizeof(WarpState), cudaMemcpyHostToDevice, st));
 
   int32_t *d_roots = nullptr; unsigned char *d_rfail = nullptr; unsigned int *d_rsol = nullptr; int32_t *d_nout = nullptr;
-  auto free_batch = [&]() { cudaFree(d_roots); cudaFree(d_rfail); cudaFree(d_rsol); cudaFree(d_nout); };
+  auto free_batch = [&]() { cfree(d_roots); cfree(d_rfail); cfree(d_rsol); cfree(d_nout); };
   if (!batch) {
     // root frame
     std::vector<int32_t> root(fw, 0);
@@ -386,8 +386,8 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   } else {
     // root phase on the device: propagate every root to fixpoint, emit one tagged frame per consistent root
     const size_t rb = (size_t)n_roots * 2 * V * sizeof(int32_t);
-    CUDA_TRY(cudaMalloc(&d_roots, rb)); CUDA_TRY(cudaMalloc(&d_rfail, n_roots));
-    CUDA_TRY(cudaMalloc(&d_rsol, (size_t)n_roots * sizeof(unsigned int))); CUDA_TRY(cudaMalloc(&d_nout, sizeof(int32_t)));
+    CUDA_TRY(cmalloc(&d_roots, rb)); CUDA_TRY(cmalloc(&d_rfail, n_roots));
+    CUDA_TRY(cmalloc(&d_rsol, (size_t)n_roots * sizeof(unsigned int))); CUDA_TRY(cmalloc(&d_nout, sizeof(int32_t)));
     CUDA_TRY(cudaMemcpyAsync(d_roots, root_dom, rb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(d_rsol, 0, (size_t)n_roots * sizeof(unsigned int), st));
     CUDA_TRY(cudaMemsetAsync(d_nout, 0, sizeof(int32_t), st));
@@ -656,14 +656,14 @@ extern "C" int csolve_gpu_export_frames(csolve_gpu_problem *p, int32_t max_frame
   const SearchArgs &a = *p->parked;
   const size_t bytes = (size_t)max_frames * a.m.frame_words * sizeof(int32_t);
   int32_t *d_buf = nullptr, *d_n = nullptr;
-  CUDA_TRY(cudaMalloc(&d_buf, bytes));
-  CUDA_TRY(cudaMalloc(&d_n, sizeof(int32_t)));
+  CUDA_TRY(cmalloc(&d_buf, bytes));
+  CUDA_TRY(cmalloc(&d_n, sizeof(int32_t)));
   cudaError_t e = launch_export_frames(a, d_buf, max_frames, d_n, p->stream);
   int32_t n = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
   if (e == cudaSuccess && n > 0) e = cudaMemcpy(frames, d_buf, (size_t)n * a.m.frame_words * sizeof(int32_t), cudaMemcpyDeviceToHost);
-  cudaFree(d_buf); cudaFree(d_n);
+  cfree(d_buf); cfree(d_n);
   if (e != cudaSuccess) return fail(CSOLVE_ERR_CUDA, std::string("export frames: ") + cudaGetErrorString(e));
   *n_out = n;
   return CSOLVE_OK;
@@ -677,11 +677,11 @@ extern "C" int csolve_gpu_import_frames(csolve_gpu_problem *p, const int32_t *fr
   if (n_frames > a.n_warps) return fail(CSOLVE_ERR_CAPACITY, "more frames than the donation ring holds");
   const size_t bytes = (size_t)n_frames * a.m.frame_words * sizeof(int32_t);
   int32_t *d_buf = nullptr;
-  CUDA_TRY(cudaMalloc(&d_buf, bytes));
+  CUDA_TRY(cmalloc(&d_buf, bytes));
   cudaError_t e = cudaMemcpyAsync(d_buf, frames, bytes, cudaMemcpyHostToDevice, p->stream);
   if (e == cudaSuccess) e = launch_import_frames(a, d_buf, n_frames, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-  cudaFree(d_buf);
+  cfree(d_buf);
   if (e != cudaSuccess) return fail(CSOLVE_ERR_CUDA, std::string("import frames: ") + cudaGetErrorString(e));
   return CSOLVE_OK;
 }
