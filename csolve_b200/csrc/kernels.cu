@@ -1666,6 +1666,26 @@ k_search_lovk(const SearchArgs a) {
       int nv = -1;
       int2 nb = make_int2(0, 0);
       unsigned hsh = mix_hash(fhash, (unsigned)var, (unsigned)val);
+      if (a.order == CSOLVE_ORDER_SMALLEST_DOMAIN) {
+        // in this order every variable that is a value and has no level yet is selected before any other one: all
+        // their levels are counted at once (a sudoku node fixes 5..20 cells; selecting them one by one cost a 64-bit
+        // warp reduction each). The path hash folds them in order-independently.
+        unsigned cnt = 0, fold = 0;
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+          const int v = lane + 32 * q;
+          const bool fixed = v < V && !((am[q] >> lane) & 1u) && x.lo[q] == x.hi[q];
+          const unsigned mk = __ballot_sync(FULL, fixed);
+          cnt += (unsigned)__popc(mk);
+          am[q] |= mk;
+          fold ^= fixed ? mix_hash(0x9E3779B9u, (unsigned)v, (unsigned)x.lo[q]) : 0u;
+        }
+        if (cnt) {
+          nodes += cnt;
+          lev += (int)cnt;
+          hsh = mix_hash(hsh, __reduce_xor_sync(FULL, fold), cnt);
+        }
+      }
       while (lev < V) {
         nv = lovk_select<K>(m, lane, x, am, a.order, lev);
         nb = lovk_bounds<K>(x, nv);
