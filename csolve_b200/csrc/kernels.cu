@@ -1443,34 +1443,39 @@ __device__ __forceinline__ bool lovk_fixpoint(const DevModel &m, int lane, LovK<
                                               unsigned &props, unsigned &visits) {
   const int V = m.n_vars, vbase = m.lov_vbase;
   for (;;) {
-    int kk = -1;
+    uint32_t any = 0;
 #pragma unroll
-    for (int q = K - 1; q >= 0; q--) if (pend[q]) kk = q;
-    if (kk < 0) break;
-    const int bit = __ffs(pend[kk]) - 1;
-    const int i = kk * 32 + bit;
-    int wsrc = x.lo[0];
+    for (int q = 0; q < K; q++) any |= pend[q];
+    if (any == 0u) break;
+    // the forbidden values of ALL variables that just became a value are distributed (one shuffle and K table words
+    // each), then every lane trims its K variables once -- a sudoku node fixes many cells per round
 #pragma unroll
-    for (int q = 1; q < K; q++) if (kk == q) wsrc = x.lo[q];
-    const int w = __shfl_sync(FULL, wsrc, bit);
+    for (int q = 0; q < K; q++) {
+      uint32_t pq = pend[q];
+      while (pq) {
+        const int bit = __ffs((int)pq) - 1;
+        pq &= pq - 1;
+        const int i = q * 32 + bit;
+        const int w = __shfl_sync(FULL, x.lo[q], bit);
 #pragma unroll
-    for (int q = 0; q < K; q++) if (kk == q) pend[q] &= pend[q] - 1;
+        for (int q2 = 0; q2 < K; q2++)     // v >= V: zero entries of the table
+          x.F[q2] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + lane + 32 * q2]), w, vbase);
+        visits += (unsigned)V;
+      }
+    }
     bool dead = false;
     unsigned changed = 0;
 #pragma unroll
     for (int q = 0; q < K; q++) {
-      const int v = lane + 32 * q;
-      const bool act = v < V;
-      x.F[q] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + v]), w, vbase);   // v >= V: zero entries of the table
+      const bool act = lane + 32 * q < V;
       const bool was = x.lo[q] == x.hi[q];
       const int olo = x.lo[q], ohi = x.hi[q];
       if (!lov_trim(x.F[q], vbase, x.lo[q], x.hi[q])) dead = true;
-      pend[q] |= __ballot_sync(FULL, act && !was && x.lo[q] == x.hi[q]);
-      changed += __popc(__ballot_sync(FULL, x.lo[q] != olo || x.hi[q] != ohi));
+      pend[q] = __ballot_sync(FULL, act && !was && x.lo[q] == x.hi[q]);
+      changed += (x.lo[q] != olo || x.hi[q] != ohi) ? 1u : 0u;
     }
     if (__any_sync(FULL, dead)) return false;
-    props += changed;
-    visits += (unsigned)V;
+    props += changed;       // per lane; the callers that report it sum over the warp
   }
   return true;
 }
@@ -1815,6 +1820,8 @@ k_search_lovk(const SearchArgs a) {
     }
   }
 
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) props += __shfl_xor_sync(FULL, props, o);      // counted per lane in lovk_fixpoint
   if (lane == 0) {
     if (have && level >= base) __stcg(&stack[(size_t)level * fw + FR_ITER], (int)iter);
     a.wstate[gw].level = level;
