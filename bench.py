@@ -185,10 +185,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the search path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: while the job runs, file descriptor 1 points at stderr, so whatever a
+    # library prints there (NCCL prints its version banner at any NCCL_DEBUG level >= VERSION) cannot get in front of it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO print there)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     text = I.queens(args.queens)
@@ -279,10 +281,16 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": "%d-queens all-solutions, %d nodes in %.2f s, single thread, default flags"
                                               % (nq, c, dt)}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
 
 
 if __name__ == "__main__":
