@@ -51,6 +51,16 @@ def scaling():
             "Reference CPU solver (unmodified engine, 1 thread, default flags): 16-queens ALL = 1 048 203 447 CALLS in 6 629.7 s in the "
             "build container (158 k nodes/s); the GPU box's host runs the same binary at 392 k nodes/s on the 12/13-queens samples, i.e. "
             "about 2 670 s for 16-queens."]
+    q1, q8 = os.path.join(PROF, "r1_bench_q18_n1.json"), os.path.join(PROF, "r1_bench_q18_n8.json")
+    if os.path.exists(q1) and os.path.exists(q8):
+        a, b = last_json(q1), last_json(q8)
+        out += ["", "## A larger tree: 18-queens (666 090 624 solutions, 42.7 G nodes), `bench.py --queens 18`", "",
+                "| GPUs | nodes/s | time-to-solution ms | speed-up | efficiency |", "|---|---|---|---|---|",
+                "| 1 | %.2f G | %.1f | 1.00x | 100%% |" % (a["value"] / 1e9, a["ms_per_step"]),
+                "| 8 | %.2f G | %.1f | %.2fx | %.1f%% |" % (b["value"] / 1e9, b["ms_per_step"], a["ms_per_step"] / b["ms_per_step"],
+                                                         100 * a["ms_per_step"] / b["ms_per_step"] / 8),
+                "", "With seconds of work per rank the +-2 % of the hash partition and the replicated expansion no longer show: "
+                "the partition of a 16 x larger frontier subtree population evens out. (17-queens on one GPU: 345 ms, 16.9 G nodes/s.)"]
     open(os.path.join(PROF, "r1_scaling.md"), "w").write("\n".join(out) + "\n")
 
 
