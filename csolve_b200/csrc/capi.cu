@@ -104,6 +104,15 @@ int upload(const std::vector<T> &h, const T **d) {
   return CSOLVE_OK;
 }
 
+// runs a cleanup on every way out of a function (the CUDA_TRY returns included)
+template <class F>
+struct ScopeExit {
+  F f;
+  explicit ScopeExit(F fn) : f(fn) {}
+  ScopeExit(const ScopeExit &) = delete;
+  ~ScopeExit() { f(); }
+};
+
 // host rendering of warp_select_var() for the root frame
 int select_root_var(const CompiledModel &cm, int order) {
   const DevModel &m = cm.host;
@@ -241,11 +250,11 @@ extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes
   std::vector<int32_t> zero_best;
   if (best == nullptr) { zero_best.assign(n_nodes, 0); best = zero_best.data(); }
   int rc = CSOLVE_OK;
-  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_var); cudaFree(d_val); cudaFree(d_best); cudaFree(d_out); cudaFree(d_failed); };
+  auto cleanup = [&]() { cfree(d_in); cfree(d_var); cfree(d_val); cfree(d_best); cfree(d_out); cfree(d_failed); };
 #define TRY2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(CSOLVE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
-  TRY2(cudaMalloc(&d_in, dom_bytes)); TRY2(cudaMalloc(&d_out, dom_bytes));
-  TRY2(cudaMalloc(&d_var, vec_bytes)); TRY2(cudaMalloc(&d_val, vec_bytes)); TRY2(cudaMalloc(&d_best, vec_bytes));
-  TRY2(cudaMalloc(&d_failed, n_nodes));
+  TRY2(cmalloc(&d_in, dom_bytes)); TRY2(cmalloc(&d_out, dom_bytes));
+  TRY2(cmalloc(&d_var, vec_bytes)); TRY2(cmalloc(&d_val, vec_bytes)); TRY2(cmalloc(&d_best, vec_bytes));
+  TRY2(cmalloc(&d_failed, n_nodes));
   TRY2(cudaMemcpyAsync(d_in, dom_in, dom_bytes, cudaMemcpyHostToDevice, p->stream));
   TRY2(cudaMemcpyAsync(d_var, var, vec_bytes, cudaMemcpyHostToDevice, p->stream));
   TRY2(cudaMemcpyAsync(d_val, val, vec_bytes, cudaMemcpyHostToDevice, p->stream));
@@ -370,7 +379,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   CUDA_TRY(cudaMemcpyAsync(p->wstate, ws.data(), ws.size() * sizeof(WarpState), cudaMemcpyHostToDevice, st));
 
   int32_t *d_roots = nullptr; unsigned char *d_rfail = nullptr; unsigned int *d_rsol = nullptr; int32_t *d_nout = nullptr;
-  auto free_batch = [&]() { cfree(d_roots); cfree(d_rfail); cfree(d_rsol); cfree(d_nout); };
+  ScopeExit batch_guard([&]() { cfree(d_roots); cfree(d_rfail); cfree(d_rsol); cfree(d_nout); });
   if (!batch) {
     // root frame
     std::vector<int32_t> root(fw, 0);
@@ -407,6 +416,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   a.out_cap = p->pool_cap; a.expand_branch_max = 64;
   a.inst_solutions = d_rsol;
   int32_t *d_gprio = nullptr;
+  ScopeExit gprio_guard([&]() { cfree(d_gprio); });
   if (opt.prefer_failing && !m.lov) {
     // device-wide dynamic priorities, seeded with the parse-time weights (env_t.prio)
     CUDA_TRY(cmalloc(&d_gprio, (size_t)V * sizeof(int32_t)));
@@ -421,7 +431,8 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
                        : (p->exchange != nullptr || opt.time_limit_ms > 0) ? 20 : 1000;
   a.slice_cycles = (long long)g_clock_khz * slice_ms;
 
-  cudaEvent_t ev0, ev1, ev2;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  ScopeExit event_guard([&]() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (ev2) cudaEventDestroy(ev2); });
   CUDA_TRY(cudaEventCreate(&ev0)); CUDA_TRY(cudaEventCreate(&ev1)); CUDA_TRY(cudaEventCreate(&ev2));
   CUDA_TRY(cudaEventRecord(ev0, st));
 
@@ -444,7 +455,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     // children as the largest root domain (and never more than expand_branch_max)
     if ((long long)n_items * max_branch > p->pool_cap - ring_min_frames(p->n_warps)) break;
     a.items = pin; a.items_out = pout; a.frozen_best = ctl.best;
-    ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.idle = 0; ctl.passed = 0;
+    ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.passed = 0;
     CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
     const int grid = std::min(p->grid, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     CUDA_TRY(launch_search(a, grid, true, st)); launches++;
@@ -482,7 +493,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   if (p->pool_cap - n_items < ring_min_frames(p->n_warps)) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
   a.gprio = d_gprio;     // the breadth-first expansion above stays deterministic (identical on every rank)
   if (learn) a.ng = p->ng;
-  ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.idle = 0; ctl.busy = 0; ctl.hungry = 0;
+  ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0;
   ctl.signal = stopped ? SIG_STOP : SIG_RUN;
   CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
   int idle_now = p->n_warps;          // every warp starts without a stack
@@ -495,7 +506,6 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   const bool is_min = m.objective == CSOLVE_OBJ_MIN;
   for (;;) {
     if (!local_done) {
-      // ask for the slice to end when an eighth of the warps that have work (or can fetch it) ran dry
       CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
       CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
       CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
@@ -536,7 +546,6 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
       if (got > 0) local_done = false;
     }
   }
-  (void)idle_now;
   CUDA_TRY(cudaEventRecord(ev2, st));
 
   // ---- results ---------------------------------------------------------------------------------------------
@@ -598,13 +607,10 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   float ms_expand = 0, ms_search = 0;
   cudaEventElapsedTime(&ms_expand, ev0, ev1);
   cudaEventElapsedTime(&ms_search, ev1, ev2);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
 
-  cfree(d_gprio);
   if (batch) {
     if (root_solutions) CUDA_TRY(cudaMemcpy(root_solutions, d_rsol, (size_t)n_roots * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     if (root_failed) CUDA_TRY(cudaMemcpy(root_failed, d_rfail, n_roots, cudaMemcpyDeviceToHost));
-    free_batch();
   }
   res->solutions = tot[CNT_SOLUTIONS];
   res->nodes = tot[CNT_NODES];

@@ -2008,7 +2008,6 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
   if (threadIdx.x == 0) {
     a.ctl->busy = busy + (pool_left ? 1 : 0);
     a.ctl->moved = moved;
-    a.ctl->idle = 0;
     a.ctl->hungry = 0;
     a.ctl->signal = a.ctl->signal == SIG_STOP ? SIG_STOP : SIG_RUN;
   }

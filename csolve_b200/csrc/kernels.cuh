@@ -26,11 +26,10 @@ enum { CNT_NODES = 0, CNT_CUTS, CNT_PROPS, CNT_VISITS, CNT_SOLUTIONS, CNT_REFRES
 struct SearchCtl {
   // line 0: read-mostly (polled)
   int32_t signal;
-  int32_t idle;         // warps that ran out of work during the current slice
   int32_t best;         // incumbent objective value (objective_best(), src/objective.c:133)
   int32_t busy;         // written by the rebalance kernel: warps that still own work
   int32_t moved;        // written by the rebalance kernel: frames handed to idle warps
-  int32_t pad0[27];
+  int32_t pad0[28];
   // line 1: claims of the expanded root frontier
   int32_t init_next;    // next frame of the expanded root frontier (static part of the pool, claimed with atomicAdd)
   int32_t pad1[31];
@@ -81,7 +80,6 @@ struct SearchArgs {
   int32_t max_solutions;
   int32_t n_warps;
   int32_t order;              // CSOLVE_ORDER_*
-  int32_t idle_exit;          // request a slice end when this many warps are idle
   int32_t frozen_best;        // expand mode: incumbent every node of this level is propagated against
   long long slice_cycles;     // clock64() budget of one slice
   int32_t expand_branch_max;  // expand mode: frames with more values than this are passed through unsplit

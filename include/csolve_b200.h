@@ -133,7 +133,10 @@ typedef struct csolve_solve_options {
   int32_t split_target;        /* expand the root until at least this many open sub-trees exist (0 = default) */
   int32_t max_solutions;       /* capacity of the solution buffer (assignments kept for printing); 0 = none */
   int32_t time_limit_ms;       /* -t; 0 = off */
-  int32_t slice_ms;            /* length of one persistent-kernel time slice; 0 = default */
+  int32_t slice_ms;            /* length of one persistent-kernel time slice; 0 = default: the whole search in one
+                                * slice for ANY / ALL models when there is neither a time limit nor an exchange
+                                * callback, 20 ms with either, 2 ms for MIN / MAX (a slice end redistributes the open
+                                * frames over all warps, which finds good incumbents sooner) */
   int32_t create_conflicts;    /* -c (src/main.c:57-61): learn decision nogoods from failed nodes (src/conflict.c) into a
                                 * device clause pool that is propagated on later nodes. Only 0/1-valued facts can be
                                 * recorded, so it matters for SAT-like models; models that run on the specialised
