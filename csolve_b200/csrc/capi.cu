@@ -224,6 +224,7 @@ extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **
   } while (0)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
   UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst);
+  UP(lin, lin); UP(lin_term, lin_term);
   if (getenv("CSOLVE_NO_LOV")) { d.lov = 0; d.lovk = 0; d.frame_words = frame_words(d.n_vars, d.mask_words); }   // development switch: general kernels only
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);

@@ -43,6 +43,34 @@ bool collect_lits(const csolve_flat_model &m, int n, bool want_true, std::vector
   return false;
 }
 
+// A sum of terms below n:  ADD(a, b) | var | const | MUL(var, const) | MUL(const, var) | NEG(term).
+// sign: -1 below an odd number of NEG nodes (only directly above a term: NEG(ADD(..)) is not flattened).
+bool collect_terms(const csolve_flat_model &m, int n, std::vector<LinTerm> &terms, int64_t &konst, bool top = true) {
+  const int op = m.node_op[n];
+  if (op == CSOLVE_OP_ADD) return collect_terms(m, m.node_l[n], terms, konst, false) && collect_terms(m, m.node_r[n], terms, konst, false);
+  int t = n;
+  int32_t flags = 0;
+  if (op == CSOLVE_OP_NEG) { t = m.node_l[n]; flags |= LIN_NEG; }
+  const int top_op = m.node_op[t];
+  if (top_op == CSOLVE_OP_VAR) { terms.push_back(LinTerm{m.node_l[t] | flags, 1}); return true; }
+  if (top_op == CSOLVE_OP_CONST) {
+    if (m.node_l[t] != m.node_r[t]) return false;
+    konst += (flags & LIN_NEG) ? -(int64_t)m.node_l[t] : (int64_t)m.node_l[t];
+    return true;
+  }
+  if (top_op == CSOLVE_OP_MUL) {
+    const int l = m.node_l[t], r = m.node_r[t];
+    int v = -1, c = -1;
+    if (m.node_op[l] == CSOLVE_OP_VAR && m.node_op[r] == CSOLVE_OP_CONST) { v = l; c = r; }
+    else if (m.node_op[l] == CSOLVE_OP_CONST && m.node_op[r] == CSOLVE_OP_VAR) { v = r; c = l; }
+    if (v < 0 || m.node_l[c] != m.node_r[c]) return false;
+    terms.push_back(LinTerm{m.node_l[v] | flags | LIN_MUL, m.node_l[c]});
+    return true;
+  }
+  (void)top;
+  return false;
+}
+
 // every value involved stays far away from the +-infinity sentinels of src/arith.c
 const int64_t SAFE = (int64_t)1 << 29;
 bool small(int64_t v) { return v > -SAFE && v < SAFE; }
@@ -74,6 +102,7 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   out.watch_ptr.assign(m.watch_ptr, m.watch_ptr + V + 1);
   out.watch_idx.assign(m.watch_idx, m.watch_idx + W);
   out.clause.resize(C);
+  out.lin.clear(); out.lin_term.clear();
   out.root_dom.resize(2 * (size_t)V);
   for (int v = 0; v < V; v++) { out.root_dom[2 * v] = m.var_lo[v]; out.root_dom[2 * v + 1] = m.var_hi[v]; }
 
@@ -150,7 +179,35 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     }
     if (rec.kind == CK_GENERIC) n_generic++;
     out.clause[c] = rec;
+    // EQ(x, sum) / EQ(sum, x) with a linear sum: contracted by the whole warp (the ClauseRec stays generic: the leaf
+    // test evaluates the tree). Nothing may be able to saturate (src/arith.c) and x must not occur in the sum.
+    if (rec.kind == CK_GENERIC && m.node_op[root] == CSOLVE_OP_EQ && (int)out.lin.size() < MAX_LIN && V <= LIN_VAR) {
+      const int l = m.node_l[root], r = m.node_r[root];
+      int ov = -1, sum = -1;
+      if (m.node_op[l] == CSOLVE_OP_VAR && m.node_op[r] == CSOLVE_OP_ADD) { ov = m.node_l[l]; sum = r; }
+      else if (m.node_op[r] == CSOLVE_OP_VAR && m.node_op[l] == CSOLVE_OP_ADD) { ov = m.node_l[r]; sum = l; }
+      std::vector<LinTerm> terms;
+      int64_t konst = 0;
+      if (sum >= 0 && collect_terms(m, sum, terms, konst) && terms.size() >= 2 && terms.size() <= (size_t)MAX_LIN) {
+        int64_t span = std::max(std::llabs((int64_t)m.var_lo[ov]), std::llabs((int64_t)m.var_hi[ov])) + std::llabs(konst);
+        bool good = true;
+        for (const LinTerm &t : terms) {
+          const int v = t.var & LIN_VAR;
+          if (v == ov) good = false;
+          const int64_t bound = std::max(std::llabs((int64_t)m.var_lo[v]), std::llabs((int64_t)m.var_hi[v]));
+          if (!small(bound) || !small(t.k)) { good = false; break; }
+          span += bound * std::max<int64_t>(1, std::llabs((int64_t)t.k)) + bound;
+          if (!small(span)) { good = false; break; }
+        }
+        if (good) {
+          out.lin.push_back(LinClause{ov, (int32_t)terms.size(), (int32_t)out.lin_term.size(), (int32_t)konst, c, 0, 0, 0});
+          out.lin_term.insert(out.lin_term.end(), terms.begin(), terms.end());
+        }
+      }
+    }
   }
+  std::vector<int> lin_of_clause(C, -1);
+  for (size_t i = 0; i < out.lin.size(); i++) lin_of_clause[out.lin[i].clause] = (int)i;
   if (max_depth > MAX_DEPTH) { err = "clause expression too deep for the device interpreter"; return CSOLVE_ERR_UNSUPPORTED; }
 
   // ---- watch records: per variable, the NOT(EQ) clauses grouped by partner, then the generic ones ----
@@ -199,7 +256,12 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
       r.w0 = ((uint32_t)WK_LITS << 30) | ((uint32_t)(rec.kind >> 8) << 28) | (uint32_t)c;
       out.wrec.push_back(r);
     }
-    for (int c : generic) { WatchRec r; r.w0 = (WK_GENERIC << 30) | (1u << 28) | (uint32_t)c; r.c[0] = r.c[1] = r.c[2] = 0; out.wrec.push_back(r); }
+    for (int c : generic) {
+      WatchRec r; r.c[0] = r.c[1] = r.c[2] = 0;
+      r.w0 = lin_of_clause[c] >= 0 ? (WK_GENERIC << 30) | (2u << 28) | (uint32_t)lin_of_clause[c]
+                                   : (WK_GENERIC << 30) | (1u << 28) | (uint32_t)c;
+      out.wrec.push_back(r);
+    }
   }
   out.wrec_ptr[V] = (int32_t)out.wrec.size();
 
@@ -283,6 +345,9 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     const size_t bytes = out.wrec.size() * sizeof(WatchRec) + (size_t)(V + 1) * sizeof(int32_t);
     h.table_smem_bytes = bytes <= 40 * 1024 ? (int32_t)((bytes + 15) & ~(size_t)15) : 0;
   }
+  h.n_lin = (int32_t)out.lin.size();
+  h.lin = out.lin.data();
+  h.lin_term = out.lin_term.data();
   h.node_op = out.node_op.data();
   h.node_l = out.node_l.data();
   h.node_r = out.node_r.data();

@@ -17,6 +17,8 @@ struct CompiledModel {
   std::vector<uint32_t> lov_fconst;
   std::vector<int32_t> watch_ptr, watch_idx, node_l, node_r, node_first, order, prio, root_dom;
   std::vector<uint8_t> node_op;
+  std::vector<LinClause> lin;
+  std::vector<LinTerm> lin_term;
 };
 
 // returns CSOLVE_OK or an error code with a message in err

@@ -494,6 +494,51 @@ CSOLVE_HD bool contract_tree(Cx &cx, const DevModel &m, int root) {
   return contract_generic(cx, m, root);
 }
 
+// ---- linear clause  x_obj == konst + SUM (+-) k_i * x_i, one term per lane ------------------------------
+// What the nested propagate_eq / propagate_add / propagate_neg / propagate_mul calls do to such a tree
+// (src/propagate.c:90-286), flattened: the sum's bounds go to x_obj; term i must lie in x_obj - (sum of the others),
+// and is then contracted by its own node's rule (a bare variable: intersect; a MUL node: propagate_mul's division and
+// divisibility rules against BOTH operands, whichever order they are written in). A call of the nested version
+// narrows the right operand first and re-evaluates; this one works from a snapshot, so a single call may narrow
+// less, but at a state that a call leaves unchanged both do the same: same fixpoint, same failures.
+// Nothing here can saturate: compile.cpp only emits a LinClause when the magnitudes stay far below 2^30.
+struct LinLane { int32_t var, k, flags; Dom X; int32_t tlo, thi; };
+
+template <class Cx>
+CSOLVE_HD LinLane lin_lane_load(Cx &cx, const DevModel &m, const LinClause &L, int lane) {
+  LinLane t; t.var = -1; t.k = 0; t.flags = 0; t.X = mk(0, 0); t.tlo = 0; t.thi = 0;
+  if (lane < L.n_terms) {
+    const LinTerm q = m.lin_term[L.first + lane];
+    t.var = q.var & LIN_VAR; t.flags = q.var & (LIN_NEG | LIN_MUL); t.k = q.k;
+    t.X = cx.dom(t.var);
+    const long long a = (long long)t.k * t.X.lo, b = (long long)t.k * t.X.hi;
+    int32_t lo = (int32_t)(a < b ? a : b), hi = (int32_t)(a < b ? b : a);
+    if (t.flags & LIN_NEG) { const int32_t x = -lo; lo = -hi; hi = x; }
+    t.tlo = lo; t.thi = hi;
+  }
+  return t;
+}
+
+// SL / SH: konst + sum of the terms' lower / upper bounds over all lanes; O: x_obj's domain when the call started
+template <class Cx>
+CSOLVE_HD bool lin_lane_apply(Cx &cx, const LinClause &L, const LinLane &t, int lane, int32_t SL, int32_t SH, Dom O) {
+  bool ok = true;
+  if (lane == 0) ok = contract_var(cx, L.obj, SL, SH);          // x_obj ∩= eval(sum)
+  if (t.var < 0) return ok;
+  Dom v = mk(O.lo - (SH - t.thi), O.hi - (SL - t.tlo));         // what this term may be
+  if (t.flags & LIN_NEG) v = mk(-v.hi, -v.lo);                  // propagate_neg
+  if (!(t.flags & LIN_MUL)) return contract_var(cx, t.var, v.lo, v.hi) && ok;
+  int32_t lo = 0, hi = 0;
+  // against the variable operand (matters once it is a value): the constant operand must fit
+  int r = mul_target(v, t.X, &lo, &hi);
+  if (r < 0 || (r > 0 && (t.k > hi || t.k < lo))) return false;
+  // against the constant operand: the variable's share
+  r = mul_target(v, mk(t.k, t.k), &lo, &hi);
+  if (r < 0) return false;
+  if (r > 0 && !contract_var(cx, t.var, lo, hi)) return false;
+  return ok;
+}
+
 // ---- specialised contractors ----------------------------------------------------------
 // NOT(EQ(x + c, y)): the false branch of propagate_eq (src/propagate.c:104-134) reached
 // through propagate_not (src/propagate.c:289-301) and propagate_add (src/propagate.c:222-246);
@@ -584,10 +629,17 @@ CSOLVE_HD bool contract_nogood(Cx &cx, const int32_t *lits, int n) {
 // caller took when it dequeued the variable. NE_VV: the NOT(EQ) clauses between self and one partner;
 // both directions of each clause are contracted from the snapshots, exactly like the false branch
 // of propagate_eq which evaluates both sides up front (src/propagate.c:122-134).
+// lin_hit: a linear clause is not contracted here but reported (bit = its index): the caller contracts it once, with
+// the whole warp, after the records of the round step. While nogoods are learned it goes through the interpreter like
+// any generic clause (the reason records name single watch records).
 template <class Cx>
-CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const WatchRec &rec) {
+CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const WatchRec &rec, unsigned &lin_hit) {
   const uint32_t kind = wrec_kind(rec.w0);
   const int n = wrec_n(rec.w0);
+  if (kind == WK_GENERIC && n == 2) {
+    if (!cx.interprets_linear()) { lin_hit |= 1u << wrec_arg(rec.w0); return true; }
+    return contract_tree(cx, m, m.clause[m.lin[wrec_arg(rec.w0)].clause].b);
+  }
   if (kind == WK_NE_VV) {
     const int y = wrec_arg(rec.w0);
     const Dom Y = cx.dom(y);

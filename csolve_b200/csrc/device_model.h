@@ -28,7 +28,8 @@ struct ClauseRec { int32_t kind, a, b, c; };
 // Watch record: what a lane executes when variable `self` is on the node's worklist. One 16-byte
 // word; the records of a variable are contiguous (wrec_ptr[self] .. wrec_ptr[self + 1]).
 //   w0 = kind << 30 | n << 28 | arg        (n = number of offsets/constants used, 1..3)
-//   WK_GENERIC : arg = clause index; the whole clause is contracted by the interpreter
+//   WK_GENERIC : n == 1: arg = clause index; the whole clause is contracted by the interpreter
+//                n == 2: arg = index of a linear clause (LinClause below), contracted by the whole warp
 //   WK_NE_VV   : arg = partner variable p; for k < n:  self + w[1 + k] != p
 //                (all NOT(EQ) clauses between the two variables, oriented from `self`, duplicates
 //                 merged: contracting the same clause twice cannot change the fixpoint)
@@ -39,6 +40,16 @@ struct WatchRec { uint32_t w0; int32_t c[3]; };
 CSOLVE_HOSTDEV static inline uint32_t wrec_kind(uint32_t w0) { return w0 >> 30; }
 CSOLVE_HOSTDEV static inline int wrec_n(uint32_t w0) { return (int)((w0 >> 28) & 3u); }
 CSOLVE_HOSTDEV static inline int wrec_arg(uint32_t w0) { return (int)(w0 & 0x0fffffffu); }
+
+// Linear clause  x_obj == konst + SUM_i (+-) k_i * x_i  (the objective clause of a MIN / MAX model with a linear
+// objective; EQ(<obj>, expr) or EQ(expr, <obj>), src/parser.y): contracted by the whole warp, one term per lane,
+// instead of one lane interpreting the whole tree. term.var: variable index | LIN_NEG (the term sits under a NEG
+// node) | LIN_MUL (the term is a MUL(var, const) / MUL(const, var) node: propagate_mul's rules apply; without it the
+// term is the bare variable, k == 1).
+struct LinClause { int32_t obj, n_terms, first, konst, clause, pad0, pad1, pad2; };
+struct LinTerm { int32_t var, k; };
+static const int32_t LIN_NEG = 1 << 30, LIN_MUL = 1 << 29, LIN_VAR = (1 << 28) - 1;
+static const int MAX_LIN = 32;          // linear clauses per model (a dirty bit each), terms per clause (a lane each)
 
 // Maximum expression depth the per-lane interpreter stacks are sized for.
 // csolve_gpu_load() rejects deeper models (CSOLVE_ERR_UNSUPPORTED).
@@ -73,6 +84,9 @@ struct DevModel {
   const int32_t *lov_cptr;   // [n_vars + 1]
   const int32_t *lov_cval;   // [n_lov_cval]
   const uint32_t *lov_fconst; // [n_vars] forbidden-value set of the constants (lov_bits)
+  int32_t n_lin;             // linear clauses (watch records WK_GENERIC with n == 2, arg = index into lin[])
+  const LinClause *lin;      // [n_lin]
+  const LinTerm *lin_term;   // terms of all linear clauses
   const uint8_t *node_op;    // [n_nodes]
   const int32_t *node_l;     // [n_nodes]
   const int32_t *node_r;     // [n_nodes]

@@ -57,7 +57,19 @@ struct WarpCx {
     if (atomicMin(&d[2 * v + 1], hi) > hi) { mark(v); if (rhi) rhi[v] = cur; }
   }
   __device__ __forceinline__ void count_prop() { props++; }
+  __device__ __forceinline__ bool interprets_linear() const { return rlo != nullptr; }   // learning: see contract_watch
 };
+
+// one linear clause contracted by the whole warp (contract.cuh: lin_lane_load / lin_lane_apply)
+__device__ __forceinline__ bool warp_contract_linear(WarpCx &cx, const DevModel &m, int c, int lane) {
+  const int4 q0 = __ldg(reinterpret_cast<const int4 *>(&m.lin[c]));
+  const int4 q1 = __ldg(reinterpret_cast<const int4 *>(&m.lin[c]) + 1);
+  LinClause L; L.obj = q0.x; L.n_terms = q0.y; L.first = q0.z; L.konst = q0.w; L.clause = q1.x; L.pad0 = L.pad1 = L.pad2 = 0;
+  const Dom O = cx.dom(L.obj);
+  const LinLane t = lin_lane_load(cx, m, L, lane);
+  const int32_t SL = __reduce_add_sync(FULL, t.tlo) + L.konst, SH = __reduce_add_sync(FULL, t.thi) + L.konst;
+  return lin_lane_apply(cx, L, t, lane, SL, SH, O);
+}
 
 // per-warp shared memory carve-up
 struct WarpSmem {
@@ -120,6 +132,7 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
       if (nz) any = true;
       unsigned bits = 0;
       int wcur = 0;
+      unsigned lin_hit = 0;               // linear clauses that watch a variable of this chunk (per lane)
       for (;;) {
         int xA = -1, xB = -1;
         if (bits == 0u && nz != 0u) { wcur = __ffs((int)nz) - 1; nz &= nz - 1; bits = __shfl_sync(FULL, myw, wcur); }
@@ -142,7 +155,7 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
           const int4 q = wrec[i];
           WatchRec rec; rec.w0 = (uint32_t)q.x; rec.c[0] = q.y; rec.c[1] = q.z; rec.c[2] = q.w;
           if (LEARN) cx.cur = i;
-          if (!contract_watch(cx, m, x, X, rec)) { failed = true; fail_var = x; fail_rec = i; }
+          if (!contract_watch(cx, m, x, X, rec, lin_hit)) { failed = true; fail_var = x; fail_rec = i; }
           visits++;
         }
         if (LEARN) {
@@ -159,6 +172,16 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
           }
         }
         __syncwarp();
+      }
+      if (m.n_lin > 0) {
+        // each linear clause that watches one of the round's variables: once, by the whole warp
+        unsigned dirty = __reduce_or_sync(FULL, lin_hit);
+        while (dirty) {
+          const int c = __ffs((int)dirty) - 1;
+          dirty &= dirty - 1;
+          if (!warp_contract_linear(cx, m, c, lane)) { failed = true; fail_var = m.lin[c].obj; }
+          visits++;
+        }
       }
     }
     __syncwarp();
@@ -238,7 +261,8 @@ struct Analysis {
       const int n = wrec_n((uint32_t)q.x);
       visit(q.y >> 1); if (n > 1) visit(q.z >> 1); if (n > 2) visit(q.w >> 1);
     } else {
-      const ClauseRec c = m.clause[wrec_arg((uint32_t)q.x)];
+      const int ci = wrec_n((uint32_t)q.x) == 2 ? m.lin[wrec_arg((uint32_t)q.x)].clause : wrec_arg((uint32_t)q.x);
+      const ClauseRec c = m.clause[ci];
       for (int j = c.a; j <= c.b && ok; j++) if (m.node_op[j] == CSOLVE_OP_VAR) visit(m.node_l[j]);
     }
   }

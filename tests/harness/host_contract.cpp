@@ -20,7 +20,20 @@ struct HostCx {
   void raise_lo(int v, int32_t lo) { if (lo > d[2 * v]) { d[2 * v] = lo; mark(v); } }
   void lower_hi(int v, int32_t hi) { if (hi < d[2 * v + 1]) { d[2 * v + 1] = hi; mark(v); } }
   void count_prop() { props++; }
+  bool interprets_linear() const { return false; }
 };
+
+// the warp-cooperative linear contractor with the lanes emulated one after the other (reductions = loops)
+static bool host_contract_linear(HostCx &cx, const DevModel &m, int c) {
+  const LinClause &L = m.lin[c];
+  const Dom O = cx.dom(L.obj);
+  LinLane t[32];
+  long long SL = L.konst, SH = L.konst;
+  for (int lane = 0; lane < 32; lane++) { t[lane] = lin_lane_load(cx, m, L, lane); SL += t[lane].tlo; SH += t[lane].thi; }
+  bool ok = true;
+  for (int lane = 0; lane < 32; lane++) if (!lin_lane_apply(cx, L, t[lane], lane, (int32_t)SL, (int32_t)SH, O)) ok = false;
+  return ok;
+}
 
 static CompiledModel g_cm;
 static int g_use_wrec = 1;
@@ -40,6 +53,7 @@ extern "C" int hc_load(const csolve_flat_model *m, int specialise) {
   return 0;
 }
 extern "C" const char *hc_error() { return g_err.c_str(); }
+extern "C" int hc_n_linear() { return g_cm.host.n_lin; }
 extern "C" int hc_n_specialised() {
   int n = 0;
   for (auto &c : g_cm.clause) n += c.kind != CK_GENERIC;
@@ -69,9 +83,12 @@ extern "C" int hc_node(const int32_t *dom_in, int var, int32_t val, int32_t best
     if (g_use_wrec) {
       // the path the kernels take: compiled watch records, domain snapshot per dequeued variable
       Dom X = cx.dom(x);
+      unsigned lin_hit = 0;
       for (int w = m.wrec_ptr[x]; w < m.wrec_ptr[x + 1]; w++) {
-        if (!contract_watch(cx, m, x, X, m.wrec[w])) { failed = true; break; }
+        if (!contract_watch(cx, m, x, X, m.wrec[w], lin_hit)) { failed = true; break; }
       }
+      for (int c = 0; c < m.n_lin && !failed; c++)
+        if (((lin_hit >> c) & 1u) && !host_contract_linear(cx, m, c)) failed = true;
     } else {
       for (int w = m.watch_ptr[x]; w < m.watch_ptr[x + 1]; w++) {
         if (!contract_clause(cx, m, m.clause[m.watch_idx[w]])) { failed = true; break; }
