@@ -426,7 +426,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   // a slice ends so that the host can check the time limit / run the rank exchange; without either the kernel only
   // has to come back when it is done. Branch-and-bound profits from short slices: between two slices k_rebalance
   // hands EVERY idle warp half of a busy warp's shallowest frame at once, which finds good incumbents sooner
-  // (wcet: 33 ms with 2 ms slices, 35 ms with 5 ms, 40 ms with 10 ms, several times that with one long slice).
+  // (wcet: 11 ms with 1-2 ms slices, 15 ms with 5 ms, 23-33 ms with 10 ms, several times that with one long slice).
   const int slice_ms = opt.slice_ms > 0 ? opt.slice_ms
                        : p->dev.obj_var >= 0 ? 2
                        : (p->exchange != nullptr || opt.time_limit_ms > 0) ? 20 : 1000;

@@ -67,6 +67,6 @@ if "split" in args:
         if P > 1:
             run("queens%d split %dx part 0/%d" % (n, mult, P), I.queens(n), split_target=st, part_rank=0, part_count=P)
 if "wcetvar" in args:
-    for kw in ({"slice_ms": 1}, {"slice_ms": 2}, {"slice_ms": 3}, {"slice_ms": 5}, {"slice_ms": 10}, {"slice_ms": 2, "order": "smallest-domain"}, {"slice_ms": 2, "order": "largest-value"}):
+    for kw in ({"slice_ms": 1}, {"slice_ms": 2}, {"slice_ms": 3}, {"slice_ms": 5}, {"slice_ms": 10}):
         for _ in range(2):
             run("wcet %s" % kw, I.wcet(), reps=2, **kw)
