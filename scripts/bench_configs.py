@@ -18,7 +18,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "csolve_ref")
 
 
 def ref_run(text, flags=(), timeout=600):
-    if not os.path.exists(REF):
+    if not os.path.exists(REF) or "--no-cpu" in sys.argv:      # --no-cpu: GPU columns only (a quick refresh)
         return None
     with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
         f.write(text)
