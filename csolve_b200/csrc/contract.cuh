@@ -629,17 +629,16 @@ CSOLVE_HD bool contract_nogood(Cx &cx, const int32_t *lits, int n) {
 // caller took when it dequeued the variable. NE_VV: the NOT(EQ) clauses between self and one partner;
 // both directions of each clause are contracted from the snapshots, exactly like the false branch
 // of propagate_eq which evaluates both sides up front (src/propagate.c:122-134).
-// lin_hit: a linear clause is not contracted here but reported (bit = its index): the caller contracts it once, with
-// the whole warp, after the records of the round step. While nogoods are learned it goes through the interpreter like
-// any generic clause (the reason records name single watch records).
+// A record of a linear clause (WK_GENERIC, n == 2) that reaches this function is interpreted like any generic clause
+// (while nogoods are learned: the reason records name single watch records). Otherwise the caller intercepts it with
+// wrec_is_linear() and contracts the clause once per round step with the whole warp.
+CSOLVE_HD bool wrec_is_linear(uint32_t w0) { return (w0 >> 28) == ((WK_GENERIC << 2) | 2u); }
+
 template <class Cx>
-CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const WatchRec &rec, unsigned &lin_hit) {
+CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const WatchRec &rec) {
   const uint32_t kind = wrec_kind(rec.w0);
   const int n = wrec_n(rec.w0);
-  if (kind == WK_GENERIC && n == 2) {
-    if (!cx.interprets_linear()) { lin_hit |= 1u << wrec_arg(rec.w0); return true; }
-    return contract_tree(cx, m, m.clause[m.lin[wrec_arg(rec.w0)].clause].b);
-  }
+  if (kind == WK_GENERIC && n == 2) return contract_tree(cx, m, m.clause[m.lin[wrec_arg(rec.w0)].clause].b);
   if (kind == WK_NE_VV) {
     const int y = wrec_arg(rec.w0);
     const Dom Y = cx.dom(y);

@@ -57,7 +57,6 @@ struct WarpCx {
     if (atomicMin(&d[2 * v + 1], hi) > hi) { mark(v); if (rhi) rhi[v] = cur; }
   }
   __device__ __forceinline__ void count_prop() { props++; }
-  __device__ __forceinline__ bool interprets_linear() const { return rlo != nullptr; }   // learning: see contract_watch
 };
 
 // one linear clause contracted by the whole warp (contract.cuh: lin_lane_load / lin_lane_apply)
@@ -110,7 +109,9 @@ __device__ __forceinline__ WarpSmem carve(const DevModel &m, int *base) {
 // returns false when the node failed (PROP_ERROR).
 struct FailInfo { int rec; int var; };   // learning: record being contracted when the node failed / variable found empty
 
-template <bool LEARN = false>
+// LIN: the model has linear clauses that the whole warp contracts (a template parameter, not a run-time test: the
+// test and the extra live register cost the 3-SAT kernel 5..10 % when they sat in the common code)
+template <bool LEARN = false, bool LIN = false>
 __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, const int4 *wrec, const int *wptr,
                                               int lane, unsigned &props, unsigned &visits, int *gprio = nullptr,
                                               const NogoodPool *ng = nullptr, FailInfo *fi = nullptr) {
@@ -155,7 +156,8 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
           const int4 q = wrec[i];
           WatchRec rec; rec.w0 = (uint32_t)q.x; rec.c[0] = q.y; rec.c[1] = q.z; rec.c[2] = q.w;
           if (LEARN) cx.cur = i;
-          if (!contract_watch(cx, m, x, X, rec, lin_hit)) { failed = true; fail_var = x; fail_rec = i; }
+          if (LIN && wrec_is_linear(rec.w0)) lin_hit |= 1u << wrec_arg(rec.w0);   // contracted below, by the warp
+          else if (!contract_watch(cx, m, x, X, rec)) { failed = true; fail_var = x; fail_rec = i; }
           visits++;
         }
         if (LEARN) {
@@ -173,7 +175,7 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
         }
         __syncwarp();
       }
-      if (m.n_lin > 0) {
+      if (LIN) {
         // each linear clause that watches one of the round's variables: once, by the whole warp
         unsigned dirty = __reduce_or_sync(FULL, lin_hit);
         while (dirty) {
@@ -550,7 +552,7 @@ __device__ __forceinline__ bool publish_slot(const SearchArgs &a, int lane, int 
 
 // ---- the search kernel ----------------------------------------------------------------------------
 // Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
-template <bool EXPAND, bool LEARN>
+template <bool EXPAND, bool LEARN, bool LIN = false>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_MIN_BLOCKS)
 k_search(const SearchArgs a) {
   extern __shared__ __align__(16) int smem[];
@@ -678,7 +680,7 @@ k_search(const SearchArgs a) {
       ok = __shfl_sync(FULL, ok, 0);
       __syncwarp();
       if (LEARN) { for (int v = lane; v < V; v += 32) { s.rlo[v] = -1; s.rhi[v] = -1; } __syncwarp(); }
-      if (ok) ok = warp_fixpoint<LEARN>(m, s, wrec, wptr, lane, props, visits, nullptr, &a.ng, nullptr);
+      if (ok) ok = warp_fixpoint<LEARN, LIN>(m, s, wrec, wptr, lane, props, visits, nullptr, &a.ng, nullptr);
       refresh++;
       // untried values of the old enumeration form the interval [lo + ceil(iter/2), hi - floor(iter/2)]
       const long long ua = (long long)lo + ((iter + 1) >> 1), ub = (long long)hi - (iter >> 1);
@@ -730,7 +732,7 @@ k_search(const SearchArgs a) {
     if (LEARN) { for (int v = lane; v < V; v += 32) { s.rlo[v] = -1; s.rhi[v] = -1; } }
     __syncwarp();
     FailInfo fi; fi.rec = -1; fi.var = -1;
-    if (ok) ok = warp_fixpoint<LEARN>(m, s, wrec, wptr, lane, props, visits, a.gprio, &a.ng, &fi);
+    if (ok) ok = warp_fixpoint<LEARN, LIN>(m, s, wrec, wptr, lane, props, visits, a.gprio, &a.ng, &fi);
     nodes++;
     if (LEARN && !ok) {
       // conflict_create (src/conflict.c:327-362): record why this node failed
@@ -2155,7 +2157,8 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
     ok = __shfl_sync(FULL, ok, 0);
     __syncwarp();
     unsigned props = 0, visits = 0;
-    if (ok) ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
+    if (ok) ok = m.n_lin > 0 ? warp_fixpoint<false, true>(m, s, wrec, wptr, lane, props, visits)
+                             : warp_fixpoint<false, false>(m, s, wrec, wptr, lane, props, visits);
     int2 *dst = reinterpret_cast<int2 *>(dom_out + (size_t)b * 2 * V);
     for (int v = lane; v < V; v += 32) dst[v] = reinterpret_cast<int2 *>(s.d)[v];
     if (lane == 0) failed[b] = ok ? 0 : 1;
@@ -2188,7 +2191,8 @@ k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order,
     }
     __syncwarp();
     unsigned props = 0, visits = 0;
-    const bool ok = warp_fixpoint(m, s, wrec, wptr, lane, props, visits);
+    const bool ok = m.n_lin > 0 ? warp_fixpoint<false, true>(m, s, wrec, wptr, lane, props, visits)
+                                : warp_fixpoint<false, false>(m, s, wrec, wptr, lane, props, visits);
     if (lane == 0) root_failed[r] = ok ? 0 : 1;
     if (ok) {
       int nv = warp_select_var(m, s, lane, order, 0, -1);
@@ -2253,7 +2257,8 @@ int search_blocks_per_sm(const DevModel &m, bool expand, bool learn) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lf, THREADS_PER_BLOCK, smem);
     return n;
   }
-  const void *fn = expand ? (const void *)k_search<true, false> : (const void *)k_search<false, false>;
+  const void *fn = m.n_lin > 0 ? (expand ? (const void *)k_search<true, false, true> : (const void *)k_search<false, false, true>)
+                               : (expand ? (const void *)k_search<true, false, false> : (const void *)k_search<false, false, false>);
   if (ensure_smem(fn, smem) != cudaSuccess) return 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem);
   return n;
@@ -2281,16 +2286,12 @@ cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream
     void *args[] = {(void *)&a};
     return cudaLaunchKernel(lf, dim3(grid), dim3(THREADS_PER_BLOCK), args, smem, st);
   }
-  if (expand) {
-    cudaError_t e = ensure_smem((const void *)k_search<true, false>, smem);
-    if (e != cudaSuccess) return e;
-    k_search<true, false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
-  } else {
-    cudaError_t e = ensure_smem((const void *)k_search<false, false>, smem);
-    if (e != cudaSuccess) return e;
-    k_search<false, false><<<grid, THREADS_PER_BLOCK, smem, st>>>(a);
-  }
-  return cudaGetLastError();
+  const void *fn = a.m.n_lin > 0 ? (expand ? (const void *)k_search<true, false, true> : (const void *)k_search<false, false, true>)
+                                 : (expand ? (const void *)k_search<true, false, false> : (const void *)k_search<false, false, false>);
+  cudaError_t e = ensure_smem(fn, smem);
+  if (e != cudaSuccess) return e;
+  void *args[] = {(void *)&a};
+  return cudaLaunchKernel(fn, dim3(grid), dim3(THREADS_PER_BLOCK), args, smem, st);
 }
 
 cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,

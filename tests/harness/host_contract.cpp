@@ -20,7 +20,6 @@ struct HostCx {
   void raise_lo(int v, int32_t lo) { if (lo > d[2 * v]) { d[2 * v] = lo; mark(v); } }
   void lower_hi(int v, int32_t hi) { if (hi < d[2 * v + 1]) { d[2 * v + 1] = hi; mark(v); } }
   void count_prop() { props++; }
-  bool interprets_linear() const { return false; }
 };
 
 // the warp-cooperative linear contractor with the lanes emulated one after the other (reductions = loops)
@@ -85,7 +84,8 @@ extern "C" int hc_node(const int32_t *dom_in, int var, int32_t val, int32_t best
       Dom X = cx.dom(x);
       unsigned lin_hit = 0;
       for (int w = m.wrec_ptr[x]; w < m.wrec_ptr[x + 1]; w++) {
-        if (!contract_watch(cx, m, x, X, m.wrec[w], lin_hit)) { failed = true; break; }
+        if (m.n_lin > 0 && wrec_is_linear(m.wrec[w].w0)) { lin_hit |= 1u << wrec_arg(m.wrec[w].w0); continue; }
+        if (!contract_watch(cx, m, x, X, m.wrec[w])) { failed = true; break; }
       }
       for (int c = 0; c < m.n_lin && !failed; c++)
         if (((lin_hit >> c) & 1u) && !host_contract_linear(cx, m, c)) failed = true;
