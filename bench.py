@@ -205,9 +205,11 @@ def run_ours(args):
         res = prob.solve(order=order, part_rank=rank, part_count=world)   # D2H: counters, incumbent, status
         wall = time.perf_counter() - t0
         f = model.flat
+        # model arrays + root frame + the 640-byte control block once per expansion level and once for the search
+        levels = max(int(res.kernel_launches) - 3, 0)
         h2d = (f.n_clauses * 16 + (f.n_vars + 1) * 4 + f.n_watch * 4 + f.n_nodes * 13 + f.n_vars * 16
-               + 64 + (8 + f.n_vars * 2 + 4) * 4)       # model arrays + control block + root frame
-        d2h = 64 * (res.kernel_launches // 2 + 2) + 48  # control block per slice + counters
+               + (8 + f.n_vars * 2 + 4) * 4 + 640 * (levels + 1))
+        d2h = 640 * (levels + 2) + 96                   # control block per expansion level / slice / at the end + counters
         prob.close(); model.close()
         return res, wall, h2d, d2h
 
