@@ -1,5 +1,5 @@
 import sys, time
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import csolve_b200 as cb
 from csolve_b200 import instances as I
 text=I.queens(16)
