@@ -7,12 +7,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "csolve_b200.h"
@@ -23,10 +26,6 @@
 using namespace csolve_dev;
 
 namespace {
-
-int g_device = -1;
-int g_sm_count = 0;
-int g_clock_khz = 0;
 
 int fail(int code, const std::string &msg) {
   csolve_front::set_last_error(msg);
@@ -43,66 +42,140 @@ int fail(int code, const std::string &msg) {
     }                                                                                   \
   } while (0)
 
-// Workspace blocks (stacks, frontier pools) are recycled across problems of one process: a fresh
-// cudaMalloc/cudaFree of hundreds of MB per solve would dominate the end-to-end time of short searches.
+// ---- per-device state ---------------------------------------------------------------------------------------
+// One context per CUDA device, created on first use and kept for the life of the process. A problem belongs to
+// the device it was loaded on; every entry point makes that device current for the calling thread, so problems on
+// different devices can be driven from different host threads (csolve_gpu_group does exactly that).
+//
+// Device memory blocks (stacks, frontier pools, the small per-problem buffers) are recycled across the problems of
+// one device: cudaMalloc / cudaFree cost milliseconds each once the process has peer mappings (measured: 20-40 ms of
+// end-to-end time per search), a search takes about as long. The cache is bounded in BYTES; when an allocation fails
+// the cache is released and the allocation retried once.
 struct WsBlock { void *p; size_t bytes; };
-std::vector<WsBlock> g_ws_free;
 
-cudaError_t ws_alloc(void **out, size_t bytes, size_t *got = nullptr) {
-  for (size_t i = 0; i < g_ws_free.size(); i++) {
-    if (g_ws_free[i].bytes >= bytes && g_ws_free[i].bytes <= bytes + bytes / 4 + 4096) {
-      *out = g_ws_free[i].p;
-      if (got) *got = g_ws_free[i].bytes;
-      g_ws_free.erase(g_ws_free.begin() + i);
-      return cudaSuccess;
+struct DeviceCtx {
+  int device = -1;
+  int sm_count = 0;
+  int clock_khz = 0;
+  std::mutex mu;                       // guards the two lists below
+  std::vector<WsBlock> free_blocks;    // cached, not in use
+  std::vector<WsBlock> live;           // handed out by cmalloc (true size of a recycled block)
+  size_t free_bytes = 0;
+  static constexpr size_t kMaxCachedBytes = (size_t)6 << 30;
+
+  cudaError_t alloc(void **out, size_t bytes, size_t *got) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < free_blocks.size(); i++) {
+        if (free_blocks[i].bytes >= bytes && free_blocks[i].bytes <= bytes + bytes / 4 + 4096) {
+          *out = free_blocks[i].p;
+          if (got) *got = free_blocks[i].bytes;
+          free_bytes -= free_blocks[i].bytes;
+          free_blocks.erase(free_blocks.begin() + i);
+          return cudaSuccess;
+        }
+      }
     }
+    if (got) *got = bytes;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();              // clear the sticky error, drop the cache, try once more
+      release_all();
+      e = cudaMalloc(out, bytes);
+    }
+    return e;
   }
-  if (got) *got = bytes;
-  return cudaMalloc(out, bytes);
-}
-void ws_free(void *p, size_t bytes) {
-  if (p == nullptr) return;
-  if (g_ws_free.size() >= 96) { cudaFree(g_ws_free.front().p); g_ws_free.erase(g_ws_free.begin()); }
-  g_ws_free.push_back(WsBlock{p, bytes});
-}
-void ws_release_all() {
-  for (auto &b : g_ws_free) cudaFree(b.p);
-  g_ws_free.clear();
+  void release(void *p, size_t bytes) {
+    if (p == nullptr) return;
+    std::vector<void *> evict;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      free_blocks.push_back(WsBlock{p, bytes});
+      free_bytes += bytes;
+      while (!free_blocks.empty() && (free_bytes > kMaxCachedBytes || free_blocks.size() > 256)) {
+        evict.push_back(free_blocks.front().p);
+        free_bytes -= free_blocks.front().bytes;
+        free_blocks.erase(free_blocks.begin());
+      }
+    }
+    for (void *q : evict) cudaFree(q);
+  }
+  void release_all() {
+    std::vector<WsBlock> blocks;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      blocks.swap(free_blocks);
+      free_bytes = 0;
+    }
+    for (auto &b : blocks) cudaFree(b.p);
+  }
+  cudaError_t cmalloc(void **out, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    size_t got = bytes;
+    cudaError_t e = alloc(out, bytes, &got);
+    if (e == cudaSuccess) {
+      std::lock_guard<std::mutex> lk(mu);
+      live.push_back(WsBlock{*out, got});
+    }
+    return e;
+  }
+  void cfree(void *p) {
+    if (p == nullptr) return;
+    size_t bytes = 0;
+    bool found = false;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < live.size(); i++) {
+        if (live[i].p == p) { bytes = live[i].bytes; live.erase(live.begin() + i); found = true; break; }
+      }
+    }
+    if (found) release(p, bytes);     // a recycled block may be larger than what was asked for: keep its true size
+    else cudaFree(p);
+  }
+};
+
+std::mutex g_ctx_mu;
+std::vector<std::unique_ptr<DeviceCtx>> g_ctx;      // indexed by device ordinal
+std::atomic<int> g_default_device{-1};              // set by csolve_gpu_init(): the device csolve_gpu_load() uses
+
+// context of `device` (created on first use); makes the device current for the calling thread
+int device_ctx(int device, DeviceCtx **out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    return fail(CSOLVE_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                          " (the search path has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return fail(CSOLVE_ERR_INVALID, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if ((int)g_ctx.size() < n) g_ctx.resize(n);
+  if (!g_ctx[device]) {
+    std::unique_ptr<DeviceCtx> c(new DeviceCtx);
+    c->device = device;
+    // queried once: cudaDevAttrClockRate is a live query that takes tens of milliseconds every now and then
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device));
+    g_ctx[device] = std::move(c);
+  }
+  *out = g_ctx[device].get();
+  return CSOLVE_OK;
 }
 
-// the same cache for the small per-problem buffers: cudaMalloc / cudaFree take milliseconds each once the process
-// has peer mappings (one process per GPU under NCCL), which showed up as 20-40 ms of end-to-end time per search
-std::vector<WsBlock> g_live;
-cudaError_t cmalloc(void **out, size_t bytes) {
-  bytes = std::max<size_t>(bytes, 256);
-  size_t got = bytes;
-  cudaError_t e = ws_alloc(out, bytes, &got);
-  if (e == cudaSuccess) g_live.push_back(WsBlock{*out, got});
-  return e;
-}
-template <class T> cudaError_t cmalloc(T **out, size_t bytes) { return cmalloc(reinterpret_cast<void **>(out), bytes); }
-void cfree(void *p) {
-  if (p == nullptr) return;
-  for (size_t i = 0; i < g_live.size(); i++) {
-    if (g_live[i].p == p) {
-      // a recycled block may be larger than what was asked for: keep its true size
-      ws_free(p, g_live[i].bytes);
-      g_live.erase(g_live.begin() + i);
-      return;
-    }
-  }
-  cudaFree(p);
-}
+template <class T> cudaError_t cmalloc(DeviceCtx *c, T **out, size_t bytes) { return c->cmalloc(reinterpret_cast<void **>(out), bytes); }
 
 template <class T>
-int upload(const std::vector<T> &h, const T **d) {
+int upload(DeviceCtx *C, const std::vector<T> &h, const T **d) {
   T *p = nullptr;
   size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
-  CUDA_TRY(cmalloc(&p, bytes));
+  CUDA_TRY(cmalloc(C, &p, bytes));
   if (!h.empty()) CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   *d = p;
   return CSOLVE_OK;
 }
+
+// first statement of every entry point that touches the device: the problem's device becomes current for this thread
+#define ENTER(p) DeviceCtx *C = (p)->ctx; CUDA_TRY(cudaSetDevice(C->device))
 
 // runs a cleanup on every way out of a function (the CUDA_TRY returns included)
 template <class F>
@@ -138,9 +211,11 @@ int select_root_var(const CompiledModel &cm, int order) {
 }  // namespace
 
 struct csolve_gpu_problem {
+  DeviceCtx *ctx = nullptr;       // the device this problem lives on
   CompiledModel cm;
   DevModel dev{};                 // device pointers
-  std::vector<void *> allocs;     // model arrays on the device
+  std::vector<void *> allocs;     // model arrays on the device (one packed block)
+  size_t model_bytes = 0;         // size of that block: the host-to-device bytes of a load
   // search workspace (allocated on first solve)
   int grid = 0, n_warps = 0;
   int32_t *stacks = nullptr;
@@ -160,6 +235,9 @@ struct csolve_gpu_problem {
   int32_t n_stored = 0;
   cudaStream_t stream = nullptr;
   NogoodPool ng{};                 // device clause pool of learned nogoods (allocated on demand)
+  int32_t *sample_rec = nullptr, *sample_n = nullptr;   // parity instrumentation (csolve_solve_options.sample_mod)
+  int32_t sample_cap = 0;
+  int32_t sample_seen = 0;
   csolve_exchange_fn exchange = nullptr;
   void *exchange_user = nullptr;
   csolve_rebalance_fn rebalance = nullptr;
@@ -167,10 +245,14 @@ struct csolve_gpu_problem {
   const SearchArgs *parked = nullptr;   // search arguments while the rebalance callback runs (export / import are valid)
 
   ~csolve_gpu_problem() {
-    for (void *p : allocs) cfree(p);
-    ws_free(stacks, stacks_bytes); cfree(wstate); cfree(wcount); cfree(totals); cfree(ctl);
-    ws_free(pool_a, pool_bytes); ws_free(pool_b, pool_bytes); cfree(scratch); cfree(solbuf); cfree(ready);
-    cfree(ng.lits); cfree(ng.start); cfree(ng.len); cfree(ng.watch); cfree(ng.watch_n); cfree(ng.counters);
+    DeviceCtx *C = ctx;
+    if (C == nullptr) return;
+    cudaSetDevice(C->device);
+    for (void *p : allocs) C->cfree(p);
+    C->release(stacks, stacks_bytes); C->cfree(wstate); C->cfree(wcount); C->cfree(totals); C->cfree(ctl);
+    C->release(pool_a, pool_bytes); C->release(pool_b, pool_bytes); C->cfree(scratch); C->cfree(solbuf); C->cfree(ready);
+    C->cfree(sample_rec); C->cfree(sample_n);
+    C->cfree(ng.lits); C->cfree(ng.start); C->cfree(ng.len); C->cfree(ng.watch); C->cfree(ng.watch_n); C->cfree(ng.counters);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -179,71 +261,110 @@ extern "C" const char *csolve_last_error(void) { return csolve_front::last_error
 extern "C" int csolve_abi_version(void) { return CSOLVE_B200_ABI_VERSION; }
 
 extern "C" int csolve_gpu_init(const csolve_gpu_config *cfg) {
-  // already on this device: nothing to ask the driver again (cudaDevAttrClockRate is a live query that takes tens
-  // of milliseconds every now and then -- it showed up as 20..100 ms of "load" time in the end-to-end numbers)
-  if (g_device >= 0 && g_device == (cfg ? cfg->device : 0)) return cudaSetDevice(g_device) == cudaSuccess ? CSOLVE_OK : fail(CSOLVE_ERR_CUDA, "cudaSetDevice failed");
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0) {
-    return fail(CSOLVE_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
-                                          " (the search path has no CPU fallback)");
-  }
-  int dev = cfg ? cfg->device : 0;
-  if (dev < 0 || dev >= n) return fail(CSOLVE_ERR_INVALID, "device ordinal out of range");
-  CUDA_TRY(cudaSetDevice(dev));
-  CUDA_TRY(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  CUDA_TRY(cudaDeviceGetAttribute(&g_clock_khz, cudaDevAttrClockRate, dev));
-  g_device = dev;
+  DeviceCtx *C = nullptr;
+  const int rc = device_ctx(cfg ? cfg->device : 0, &C);
+  if (rc != CSOLVE_OK) return rc;
+  g_default_device.store(C->device);
   return CSOLVE_OK;
 }
 
 extern "C" void csolve_gpu_shutdown(void) {
-  ws_release_all();
-  g_device = -1;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  for (auto &c : g_ctx) {
+    if (c && cudaSetDevice(c->device) == cudaSuccess) c->release_all();
+  }
+  g_default_device.store(-1);
 }
 
-extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **out) {
+extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device, csolve_gpu_problem **out) {
   if (m == nullptr || out == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (g_device < 0) {
-    int rc = csolve_gpu_init(nullptr);
-    if (rc != CSOLVE_OK) return rc;
-  }
+  DeviceCtx *C = nullptr;
+  int rc = device_ctx(device, &C);
+  if (rc != CSOLVE_OK) return rc;
   std::unique_ptr<csolve_gpu_problem> p(new csolve_gpu_problem);
+  p->ctx = C;
   std::string err;
-  int rc = compile_model(*m, p->cm, err);
+  rc = compile_model(*m, p->cm, err);
   if (rc != CSOLVE_OK) return fail(rc, err);
 
+  // ONE upload for the whole compiled model: the arrays are packed into a single pinned-size host image (each
+  // 256-byte aligned) and copied with one cudaMemcpy; 18 separate synchronous copies cost ~0.2 ms of a 50 ms search.
   DevModel &d = p->dev;
   d = p->cm.host;
-#define UP(field, vec)                                              \
-  do {                                                              \
-    rc = upload(p->cm.vec, &d.field);                               \
-    if (rc != CSOLVE_OK) return rc;                                 \
-    p->allocs.push_back((void *)d.field);                           \
-  } while (0)
+  if (getenv("CSOLVE_NO_LOV")) { d.lov = 0; d.lovk = 0; d.frame_words = frame_words(d.n_vars, d.mask_words); }   // development switch: general kernels only
+  std::vector<unsigned char> image;
+  struct Part { size_t off; const void *src; size_t bytes; const void **field; };
+  std::vector<Part> parts;
+  auto add = [&](const void *src, size_t bytes, const void **field) {
+    const size_t off = (image.size() + 255) & ~(size_t)255;
+    image.resize(off + std::max<size_t>(bytes, 16));
+    if (bytes) memcpy(image.data() + off, src, bytes);
+    parts.push_back(Part{off, src, bytes, field});
+  };
+#define UP(field, vec) add(p->cm.vec.data(), p->cm.vec.size() * sizeof(p->cm.vec[0]), (const void **)&d.field)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
   UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst);
   UP(lin, lin); UP(lin_term, lin_term);
-  if (getenv("CSOLVE_NO_LOV")) { d.lov = 0; d.lovk = 0; d.frame_words = frame_words(d.n_vars, d.mask_words); }   // development switch: general kernels only
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
 #undef UP
+  unsigned char *base = nullptr;
+  CUDA_TRY(cmalloc(C, &base, image.size()));
+  p->allocs.push_back(base);
+  CUDA_TRY(cudaMemcpy(base, image.data(), image.size(), cudaMemcpyHostToDevice));
+  for (const Part &q : parts) *q.field = base + q.off;
+  p->model_bytes = image.size();
   CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   *out = p.release();
   return CSOLVE_OK;
 }
 
+extern "C" int csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **out) {
+  int dev = g_default_device.load();
+  if (dev < 0) {
+    int rc = csolve_gpu_init(nullptr);
+    if (rc != CSOLVE_OK) return rc;
+    dev = g_default_device.load();
+  }
+  return csolve_gpu_load_device(m, dev, out);
+}
+
 extern "C" void csolve_gpu_unload(csolve_gpu_problem *p) { delete p; }
+
+namespace {
+// caller-supplied domains must be sub-intervals of the model's root domains (see include/csolve_b200.h)
+int check_domains(const csolve_gpu_problem *p, int32_t n, const int32_t *dom, const char *what) {
+  const int V = p->dev.n_vars;
+  const int32_t *root = p->cm.root_dom.data();
+  for (int32_t b = 0; b < n; b++) {
+    const int32_t *d = dom + (size_t)b * 2 * V;
+    for (int v = 0; v < V; v++) {
+      if (d[2 * v] > d[2 * v + 1] || d[2 * v] < root[2 * v] || d[2 * v + 1] > root[2 * v + 1]) {
+        return fail(CSOLVE_ERR_INVALID, std::string(what) + " " + std::to_string(b) + ": the domain of variable " + std::to_string(v) +
+                                            " is empty or not inside the model's root domain");
+      }
+    }
+  }
+  return CSOLVE_OK;
+}
+}  // namespace
 
 extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes, const int32_t *dom_in,
                                           const int32_t *var, const int32_t *val, const int32_t *best,
                                           int32_t *dom_out, uint8_t *failed) {
   if (p == nullptr || n_nodes < 0) return fail(CSOLVE_ERR_INVALID, "bad arguments");
   if (n_nodes == 0) return CSOLVE_OK;
+  ENTER(p);
   const int V = p->dev.n_vars;
+  if (dom_in == nullptr || var == nullptr || val == nullptr || dom_out == nullptr || failed == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
   for (int b = 0; b < n_nodes; b++) {
     if (var[b] < 0 || var[b] >= V) return fail(CSOLVE_ERR_INVALID, "decision variable out of range");
+    if (val[b] < p->cm.root_dom[2 * var[b]] || val[b] > p->cm.root_dom[2 * var[b] + 1]) return fail(CSOLVE_ERR_INVALID, "decision value outside the variable's root domain");
+  }
+  {
+    const int rc0 = check_domains(p, n_nodes, dom_in, "node");
+    if (rc0 != CSOLVE_OK) return rc0;
   }
   const size_t dom_bytes = (size_t)n_nodes * 2 * V * sizeof(int32_t), vec_bytes = (size_t)n_nodes * sizeof(int32_t);
   int32_t *d_in = nullptr, *d_var = nullptr, *d_val = nullptr, *d_best = nullptr, *d_out = nullptr;
@@ -251,16 +372,16 @@ extern "C" int csolve_gpu_propagate_batch(csolve_gpu_problem *p, int32_t n_nodes
   std::vector<int32_t> zero_best;
   if (best == nullptr) { zero_best.assign(n_nodes, 0); best = zero_best.data(); }
   int rc = CSOLVE_OK;
-  auto cleanup = [&]() { cfree(d_in); cfree(d_var); cfree(d_val); cfree(d_best); cfree(d_out); cfree(d_failed); };
+  auto cleanup = [&]() { C->cfree(d_in); C->cfree(d_var); C->cfree(d_val); C->cfree(d_best); C->cfree(d_out); C->cfree(d_failed); };
 #define TRY2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(CSOLVE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
-  TRY2(cmalloc(&d_in, dom_bytes)); TRY2(cmalloc(&d_out, dom_bytes));
-  TRY2(cmalloc(&d_var, vec_bytes)); TRY2(cmalloc(&d_val, vec_bytes)); TRY2(cmalloc(&d_best, vec_bytes));
-  TRY2(cmalloc(&d_failed, n_nodes));
+  TRY2(cmalloc(C, &d_in, dom_bytes)); TRY2(cmalloc(C, &d_out, dom_bytes));
+  TRY2(cmalloc(C, &d_var, vec_bytes)); TRY2(cmalloc(C, &d_val, vec_bytes)); TRY2(cmalloc(C, &d_best, vec_bytes));
+  TRY2(cmalloc(C, &d_failed, n_nodes));
   TRY2(cudaMemcpyAsync(d_in, dom_in, dom_bytes, cudaMemcpyHostToDevice, p->stream));
   TRY2(cudaMemcpyAsync(d_var, var, vec_bytes, cudaMemcpyHostToDevice, p->stream));
   TRY2(cudaMemcpyAsync(d_val, val, vec_bytes, cudaMemcpyHostToDevice, p->stream));
   TRY2(cudaMemcpyAsync(d_best, best, vec_bytes, cudaMemcpyHostToDevice, p->stream));
-  int grid = std::min((n_nodes + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, std::max(1, g_sm_count) * 8);
+  int grid = std::min((n_nodes + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, std::max(1, C->sm_count) * 8);
   TRY2(launch_propagate_batch(p->dev, n_nodes, d_in, d_var, d_val, d_best, d_out, d_failed, grid, p->stream));
   TRY2(cudaMemcpyAsync(dom_out, d_out, dom_bytes, cudaMemcpyDeviceToHost, p->stream));
   TRY2(cudaMemcpyAsync(failed, d_failed, n_nodes, cudaMemcpyDeviceToHost, p->stream));
@@ -284,28 +405,30 @@ int ring_min_frames(int n_warps) { return 4 * n_warps + 1024; }
 const int DEFAULT_FRAMES_PER_WARP = 16;
 
 int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots, bool learn) {
+  DeviceCtx *C = p->ctx;
   DevModel m = p->dev;
   if (batch) m.lov = 0;
-  const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0);
+  const bool sample = opt.sample_mod != 0u;
+  const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0) + (sample ? 128 : 0);
   if (p->stacks != nullptr && p->ws_lov != ws_key) {
     // the lane-owns-variable and the general kernels have different occupancies: rebuild the per-warp state
-    ws_free(p->stacks, p->stacks_bytes); cfree(p->wstate); cfree(p->wcount); cfree(p->totals); cfree(p->ctl); cfree(p->scratch);
+    C->release(p->stacks, p->stacks_bytes); C->cfree(p->wstate); C->cfree(p->wcount); C->cfree(p->totals); C->cfree(p->ctl); C->cfree(p->scratch);
     p->stacks = nullptr; p->wstate = nullptr; p->wcount = nullptr; p->totals = nullptr; p->ctl = nullptr; p->scratch = nullptr;
   }
   if (p->stacks == nullptr) {
     p->ws_lov = ws_key;
-    int per_sm = search_blocks_per_sm(m, false, learn);
+    int per_sm = search_blocks_per_sm(m, false, learn, sample);
     if (per_sm <= 0) return fail(CSOLVE_ERR_CUDA, "search kernel does not fit on the device (shared memory per node too large)");
-    p->grid = per_sm * g_sm_count;
+    p->grid = per_sm * C->sm_count;
     p->n_warps = p->grid * WARPS_PER_BLOCK;
     const size_t stack_words = (size_t)p->n_warps * (m.n_vars + 1) * m.frame_words;
     p->stacks_bytes = stack_words * sizeof(int32_t);
-    CUDA_TRY(ws_alloc((void **)&p->stacks, p->stacks_bytes));
-    CUDA_TRY(cmalloc(&p->wstate, (size_t)p->n_warps * sizeof(WarpState)));
-    CUDA_TRY(cmalloc(&p->wcount, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long)));
-    CUDA_TRY(cmalloc(&p->totals, CNT_WIDTH * sizeof(unsigned long long)));
-    CUDA_TRY(cmalloc(&p->ctl, sizeof(SearchCtl)));
-    CUDA_TRY(cmalloc(&p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
+    CUDA_TRY(C->alloc((void **)&p->stacks, p->stacks_bytes, nullptr));
+    CUDA_TRY(cmalloc(C, &p->wstate, (size_t)p->n_warps * sizeof(WarpState)));
+    CUDA_TRY(cmalloc(C, &p->wcount, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long)));
+    CUDA_TRY(cmalloc(C, &p->totals, CNT_WIDTH * sizeof(unsigned long long)));
+    CUDA_TRY(cmalloc(C, &p->ctl, sizeof(SearchCtl)));
+    CUDA_TRY(cmalloc(C, &p->scratch, (size_t)(4 + 3 * p->n_warps) * sizeof(int32_t)));
   }
   // frontier pools: room for the split target times the largest branching the expansion may apply
   int target = opt.split_target > 0 ? opt.split_target : p->n_warps * DEFAULT_FRAMES_PER_WARP;
@@ -314,18 +437,27 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
   const size_t max_bytes = (size_t)2 << 30;   // per pool
   while ((size_t)cap * m.frame_words * sizeof(int32_t) > max_bytes && cap > 1024) cap /= 2;
   if (cap > p->pool_cap) {
-    ws_free(p->pool_a, p->pool_bytes); ws_free(p->pool_b, p->pool_bytes); p->pool_a = p->pool_b = nullptr;
+    C->release(p->pool_a, p->pool_bytes); C->release(p->pool_b, p->pool_bytes); p->pool_a = p->pool_b = nullptr;
     p->pool_bytes = (size_t)cap * m.frame_words * sizeof(int32_t);
-    CUDA_TRY(ws_alloc((void **)&p->pool_a, p->pool_bytes));
-    CUDA_TRY(ws_alloc((void **)&p->pool_b, p->pool_bytes));
-    cfree(p->ready); p->ready = nullptr;
-    CUDA_TRY(cmalloc(&p->ready, (size_t)cap * sizeof(int32_t)));
+    CUDA_TRY(C->alloc((void **)&p->pool_a, p->pool_bytes, nullptr));
+    CUDA_TRY(C->alloc((void **)&p->pool_b, p->pool_bytes, nullptr));
+    C->cfree(p->ready); p->ready = nullptr;
+    CUDA_TRY(cmalloc(C, &p->ready, (size_t)cap * sizeof(int32_t)));
     p->pool_cap = cap;
+  }
+  if (sample) {
+    const int want = opt.sample_cap > 0 ? opt.sample_cap : 65536;
+    if (want > p->sample_cap) {
+      C->cfree(p->sample_rec); p->sample_rec = nullptr;
+      CUDA_TRY(cmalloc(C, &p->sample_rec, (size_t)want * sample_words(m.n_vars) * sizeof(int32_t)));
+      p->sample_cap = want;
+    }
+    if (p->sample_n == nullptr) CUDA_TRY(cmalloc(C, &p->sample_n, sizeof(int32_t)));
   }
   int sol_cap = std::max(opt.max_solutions, m.obj_var >= 0 ? 4096 : (m.objective == CSOLVE_OBJ_ANY ? 1 : 0));
   if (sol_cap > p->sol_cap) {
-    cfree(p->solbuf); p->solbuf = nullptr;
-    CUDA_TRY(cmalloc(&p->solbuf, (size_t)sol_cap * (m.n_vars + 1) * sizeof(int32_t)));
+    C->cfree(p->solbuf); p->solbuf = nullptr;
+    CUDA_TRY(cmalloc(C, &p->solbuf, (size_t)sol_cap * (m.n_vars + 1) * sizeof(int32_t)));
     p->sol_cap = sol_cap;
   }
   return CSOLVE_OK;
@@ -338,6 +470,7 @@ namespace {
 int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve_gpu_result *res, int n_roots,
                const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed) {
   if (p == nullptr || res == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  ENTER(p);
   csolve_solve_options opt;
   memset(&opt, 0, sizeof(opt));
   if (opt_in) opt = *opt_in;
@@ -349,15 +482,20 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   if (batch && p->dev.objective != CSOLVE_OBJ_ALL) return fail(CSOLVE_ERR_UNSUPPORTED, "batched roots need an ALL model");
   // learning needs the general kernel; the specialised NOT(EQ) kernels never meet a 0/1-only conflict
   const bool learn = opt.create_conflicts != 0 && !batch && !p->dev.lov && !p->dev.lovk;
+  if (learn && opt.sample_mod != 0u) return fail(CSOLVE_ERR_UNSUPPORTED, "sample_mod is not available together with create_conflicts");
+  if (batch) {
+    const int rc0 = check_domains(p, n_roots, root_dom, "root");
+    if (rc0 != CSOLVE_OK) return rc0;
+  }
   int rc = ensure_workspace(p, opt, batch, n_roots, learn);
   if (rc != CSOLVE_OK) return rc;
   if (learn) {
     NogoodPool &g = p->ng;
     if (g.lits == nullptr) {
       g.cap_ng = 1 << 18; g.cap_lits = 1 << 23; g.cap_w = 4096;
-      CUDA_TRY(cmalloc(&g.lits, (size_t)g.cap_lits * 4)); CUDA_TRY(cmalloc(&g.start, (size_t)g.cap_ng * 4));
-      CUDA_TRY(cmalloc(&g.len, (size_t)g.cap_ng * 4)); CUDA_TRY(cmalloc(&g.watch, (size_t)p->dev.n_vars * g.cap_w * 4));
-      CUDA_TRY(cmalloc(&g.watch_n, (size_t)p->dev.n_vars * 4)); CUDA_TRY(cmalloc(&g.counters, 8 * 4));
+      CUDA_TRY(cmalloc(C, &g.lits, (size_t)g.cap_lits * 4)); CUDA_TRY(cmalloc(C, &g.start, (size_t)g.cap_ng * 4));
+      CUDA_TRY(cmalloc(C, &g.len, (size_t)g.cap_ng * 4)); CUDA_TRY(cmalloc(C, &g.watch, (size_t)p->dev.n_vars * g.cap_w * 4));
+      CUDA_TRY(cmalloc(C, &g.watch_n, (size_t)p->dev.n_vars * 4)); CUDA_TRY(cmalloc(C, &g.counters, 8 * 4));
     }
     CUDA_TRY(cudaMemsetAsync(g.watch, 0xff, (size_t)p->dev.n_vars * g.cap_w * 4, p->stream));
     CUDA_TRY(cudaMemsetAsync(g.watch_n, 0, (size_t)p->dev.n_vars * 4, p->stream));
@@ -380,7 +518,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   CUDA_TRY(cudaMemcpyAsync(p->wstate, ws.data(), ws.size() * sizeof(WarpState), cudaMemcpyHostToDevice, st));
 
   int32_t *d_roots = nullptr; unsigned char *d_rfail = nullptr; unsigned int *d_rsol = nullptr; int32_t *d_nout = nullptr;
-  ScopeExit batch_guard([&]() { cfree(d_roots); cfree(d_rfail); cfree(d_rsol); cfree(d_nout); });
+  ScopeExit batch_guard([&]() { C->cfree(d_roots); C->cfree(d_rfail); C->cfree(d_rsol); C->cfree(d_nout); });
   if (!batch) {
     // root frame
     std::vector<int32_t> root(fw, 0);
@@ -396,13 +534,18 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   } else {
     // root phase on the device: propagate every root to fixpoint, emit one tagged frame per consistent root
     const size_t rb = (size_t)n_roots * 2 * V * sizeof(int32_t);
-    CUDA_TRY(cmalloc(&d_roots, rb)); CUDA_TRY(cmalloc(&d_rfail, n_roots));
-    CUDA_TRY(cmalloc(&d_rsol, (size_t)n_roots * sizeof(unsigned int))); CUDA_TRY(cmalloc(&d_nout, sizeof(int32_t)));
+    CUDA_TRY(cmalloc(C, &d_roots, rb)); CUDA_TRY(cmalloc(C, &d_rfail, n_roots));
+    CUDA_TRY(cmalloc(C, &d_rsol, (size_t)n_roots * sizeof(unsigned int))); CUDA_TRY(cmalloc(C, &d_nout, sizeof(int32_t)));
     CUDA_TRY(cudaMemcpyAsync(d_roots, root_dom, rb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(d_rsol, 0, (size_t)n_roots * sizeof(unsigned int), st));
     CUDA_TRY(cudaMemsetAsync(d_nout, 0, sizeof(int32_t), st));
+    // one frame per consistent root goes into pool_a, the donation ring needs its slots behind them
+    if ((long long)n_roots + ring_min_frames(p->n_warps) > p->pool_cap) {
+      return fail(CSOLVE_ERR_CAPACITY, "too many roots for one call: " + std::to_string(n_roots) + " roots, the frontier pool holds " +
+                                           std::to_string(p->pool_cap - ring_min_frames(p->n_warps)) + " (split the batch)");
+    }
     const int grid = std::min(p->grid, (n_roots + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    CUDA_TRY(launch_root_frames(m, n_roots, d_roots, opt.order, p->pool_a, d_nout, d_rfail, grid, st));
+    CUDA_TRY(launch_root_frames(m, n_roots, d_roots, opt.order, p->pool_a, p->pool_cap, d_nout, d_rfail, grid, st));
     int32_t n_ok = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_ok, d_nout, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -416,11 +559,17 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   a.solbuf = p->solbuf; a.max_solutions = p->sol_cap; a.n_warps = p->n_warps; a.order = opt.order;
   a.out_cap = p->pool_cap; a.expand_branch_max = 64;
   a.inst_solutions = d_rsol;
+  p->sample_seen = 0;
+  if (opt.sample_mod != 0u) {
+    a.sample_rec = p->sample_rec; a.sample_n = p->sample_n; a.sample_cap = p->sample_cap; a.sample_mod = opt.sample_mod;
+    a.sample_fkeep = std::max(opt.sample_failed_keep, 1u);
+    CUDA_TRY(cudaMemsetAsync(p->sample_n, 0, sizeof(int32_t), st));
+  }
   int32_t *d_gprio = nullptr;
-  ScopeExit gprio_guard([&]() { cfree(d_gprio); });
+  ScopeExit gprio_guard([&]() { C->cfree(d_gprio); });
   if (opt.prefer_failing && !m.lov) {
     // device-wide dynamic priorities, seeded with the parse-time weights (env_t.prio)
-    CUDA_TRY(cmalloc(&d_gprio, (size_t)V * sizeof(int32_t)));
+    CUDA_TRY(cmalloc(C, &d_gprio, (size_t)V * sizeof(int32_t)));
     CUDA_TRY(cudaMemcpyAsync(d_gprio, cm.prio.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   }
   // a slice ends so that the host can check the time limit / run the rank exchange; without either the kernel only
@@ -430,7 +579,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   const int slice_ms = opt.slice_ms > 0 ? opt.slice_ms
                        : p->dev.obj_var >= 0 ? 2
                        : (p->exchange != nullptr || opt.time_limit_ms > 0) ? 20 : 1000;
-  a.slice_cycles = (long long)g_clock_khz * slice_ms;
+  a.slice_cycles = (long long)C->clock_khz * slice_ms;
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   ScopeExit event_guard([&]() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (ev2) cudaEventDestroy(ev2); });
@@ -568,7 +717,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
       const double l = (double)c[CNT_LASTWORK];
       lw += l; lw_max = std::max(lw_max, l); lw_min = std::min(lw_min, l); nmax = std::max(nmax, (double)c[CNT_NODES]);
     }
-    const double khz = (double)g_clock_khz;
+    const double khz = (double)C->clock_khz;
     fprintf(stderr, "[csolve] depth-first phase: %.2f ms, %llu slices, %d warps, per warp: waited %.3f ms, %.1f claims, last node at %.3f ms "
                     "(min %.3f, max %.3f), most nodes on one warp %.0f (avg %.0f), %d frames donated\n", dbg_ms, (unsigned long long)slices, p->n_warps,
             wait / p->n_warps / khz, claims / p->n_warps, lw / p->n_warps / khz, lw_min / khz, lw_max / khz, nmax,
@@ -603,6 +752,15 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     for (int i = 0; i < p->n_stored; i++)
       memcpy(&sorted[(size_t)i * (V + 1)], &p->sol_host[(size_t)idx[i] * (V + 1)], sizeof(int32_t) * (V + 1));
     p->sol_host.swap(sorted);
+  }
+
+  if (m.obj_var >= 0 && tot[CNT_SOLUTIONS] > 0 &&
+      (p->n_stored == 0 || p->sol_host[(size_t)(p->n_stored - 1) * (V + 1) + V] != ctl.best)) {
+    return fail(CSOLVE_ERR_CAPACITY, "the witness of the optimum was overwritten in the solution ring (more than " +
+                                         std::to_string(p->sol_cap) + " concurrent incumbents); raise max_solutions");
+  }
+  if (opt.sample_mod != 0u) {
+    CUDA_TRY(cudaMemcpy(&p->sample_seen, p->sample_n, sizeof(int32_t), cudaMemcpyDeviceToHost));
   }
 
   float ms_expand = 0, ms_search = 0;
@@ -660,17 +818,18 @@ extern "C" int csolve_gpu_export_frames(csolve_gpu_problem *p, int32_t max_frame
   *n_out = 0;
   if (p->parked == nullptr) return fail(CSOLVE_ERR_INVALID, "csolve_gpu_export_frames is only valid inside the rebalance callback");
   if (max_frames == 0) return CSOLVE_OK;
+  ENTER(p);
   const SearchArgs &a = *p->parked;
   const size_t bytes = (size_t)max_frames * a.m.frame_words * sizeof(int32_t);
   int32_t *d_buf = nullptr, *d_n = nullptr;
-  CUDA_TRY(cmalloc(&d_buf, bytes));
-  CUDA_TRY(cmalloc(&d_n, sizeof(int32_t)));
+  CUDA_TRY(cmalloc(C, &d_buf, bytes));
+  CUDA_TRY(cmalloc(C, &d_n, sizeof(int32_t)));
   cudaError_t e = launch_export_frames(a, d_buf, max_frames, d_n, p->stream);
   int32_t n = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
   if (e == cudaSuccess && n > 0) e = cudaMemcpy(frames, d_buf, (size_t)n * a.m.frame_words * sizeof(int32_t), cudaMemcpyDeviceToHost);
-  cfree(d_buf); cfree(d_n);
+  C->cfree(d_buf); C->cfree(d_n);
   if (e != cudaSuccess) return fail(CSOLVE_ERR_CUDA, std::string("export frames: ") + cudaGetErrorString(e));
   *n_out = n;
   return CSOLVE_OK;
@@ -680,15 +839,16 @@ extern "C" int csolve_gpu_import_frames(csolve_gpu_problem *p, const int32_t *fr
   if (p == nullptr || frames == nullptr || n_frames < 0) return fail(CSOLVE_ERR_INVALID, "bad arguments");
   if (p->parked == nullptr) return fail(CSOLVE_ERR_INVALID, "csolve_gpu_import_frames is only valid inside the rebalance callback");
   if (n_frames == 0) return CSOLVE_OK;
+  ENTER(p);
   const SearchArgs &a = *p->parked;
   if (n_frames > a.n_warps) return fail(CSOLVE_ERR_CAPACITY, "more frames than the donation ring holds");
   const size_t bytes = (size_t)n_frames * a.m.frame_words * sizeof(int32_t);
   int32_t *d_buf = nullptr;
-  CUDA_TRY(cmalloc(&d_buf, bytes));
+  CUDA_TRY(cmalloc(C, &d_buf, bytes));
   cudaError_t e = cudaMemcpyAsync(d_buf, frames, bytes, cudaMemcpyHostToDevice, p->stream);
   if (e == cudaSuccess) e = launch_import_frames(a, d_buf, n_frames, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-  cfree(d_buf);
+  C->cfree(d_buf);
   if (e != cudaSuccess) return fail(CSOLVE_ERR_CUDA, std::string("import frames: ") + cudaGetErrorString(e));
   return CSOLVE_OK;
 }
@@ -706,6 +866,7 @@ extern "C" int csolve_gpu_get_nogoods(csolve_gpu_problem *p, int32_t *lits, int3
   *n_out = 0;
   starts[0] = 0;
   if (p->ng.lits == nullptr) return CSOLVE_OK;
+  ENTER(p);
   int32_t cnt[8];
   CUDA_TRY(cudaMemcpy(cnt, p->ng.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
   const int n = std::min(std::min(cnt[0], p->ng.cap_ng), cap_ng);
@@ -722,6 +883,18 @@ extern "C" int csolve_gpu_get_nogoods(csolve_gpu_problem *p, int32_t *lits, int3
     starts[++kept] = total;
   }
   *n_out = kept;
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_get_samples(csolve_gpu_problem *p, int32_t *records, int32_t cap_records, int32_t *n_out, int32_t *n_seen) {
+  if (p == nullptr || n_out == nullptr || cap_records < 0 || (records == nullptr && cap_records > 0)) return fail(CSOLVE_ERR_INVALID, "bad arguments");
+  ENTER(p);
+  const int n = std::min(std::min(p->sample_seen, p->sample_cap), cap_records);
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpy(records, p->sample_rec, (size_t)n * sample_words(p->dev.n_vars) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  *n_out = n;
+  if (n_seen) *n_seen = p->sample_seen;
   return CSOLVE_OK;
 }
 

@@ -383,6 +383,31 @@ __device__ __forceinline__ unsigned mix_hash(unsigned h, unsigned a, unsigned b)
   return h ^ (h >> 16);
 }
 
+// ---- parity instrumentation (SAMPLE instances of the search kernels only) -------------------------------
+// A node is identified by (parent domains, variable, value); whether it is recorded depends only on that identity,
+// so the recorded set of a deterministic tree does not depend on how the warps happened to traverse it.
+__device__ __forceinline__ unsigned sample_dom_hash(const int *p, int V, int lane) {
+  unsigned h = 0;
+  for (int v = lane; v < V; v += 32) h ^= mix_hash(0x9E3779B9u + (unsigned)v, (unsigned)p[2 * v], (unsigned)p[2 * v + 1]);
+  return __reduce_xor_sync(FULL, h);
+}
+// failed nodes are thinned further (1 in sample_fkeep of the hits): most nodes of a search fail
+__device__ __forceinline__ bool sample_hit(const SearchArgs &a, unsigned hpar, int var, int val, bool failed) {
+  const unsigned key = mix_hash(hpar, (unsigned)var, (unsigned)val);
+  if (key % a.sample_mod != 0u) return false;
+  return !failed || (key / a.sample_mod) % a.sample_fkeep == 0u;
+}
+// reserves a record and writes its header; returns the record (nullptr: buffer full), same on every lane
+__device__ __forceinline__ int *sample_begin(const SearchArgs &a, int lane, int flags, int var, int val, int best) {
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(a.sample_n, 1);
+  slot = __shfl_sync(FULL, slot, 0);
+  if (slot >= a.sample_cap) return nullptr;
+  int *r = a.sample_rec + (size_t)slot * sample_words(a.m.n_vars);
+  if (lane == 0) { r[0] = flags; r[1] = var; r[2] = val; r[3] = best; }
+  return r;
+}
+
 // write the child frame for level `level + 1` (domains = the node's post-fixpoint state in s.d)
 __device__ __forceinline__ void write_child_frame(const DevModel &m, const WarpSmem &s, int *g, int lane,
                                                   int nv, int level1, int best, unsigned hash, int parent_var) {
@@ -404,6 +429,9 @@ __device__ __forceinline__ void store_solution(const SearchArgs &a, const WarpSm
   int slot = 0;
   if (lane == 0) slot = atomicAdd(&a.ctl->n_stored, 1);
   slot = __shfl_sync(FULL, slot, 0);
+  // MIN / MAX: the buffer is a ring -- every accepted leaf improves on all earlier ones, so the optimum's witness is
+  // among the most recent entries however many incumbents there were
+  if (a.m.obj_var >= 0 && a.max_solutions > 0) slot = (int)((unsigned)slot % (unsigned)a.max_solutions);
   if (slot < a.max_solutions) {
     int *dst = a.solbuf + (size_t)slot * (a.m.n_vars + 1);
     for (int v = lane; v < a.m.n_vars; v += 32) dst[v] = s.d[2 * v];
@@ -433,7 +461,7 @@ struct Claim {
   bool drained;                // the root frontier has been handed out completely
 };
 
-__device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &hungry, Claim &cl, int *blk_hungry) {
+__device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &hungry, Claim &cl, int *blk_hungry, long long t0) {
   if (cl.mask) {
     const int b = __ffs((int)cl.mask) - 1;
     cl.mask &= cl.mask - 1;
@@ -471,8 +499,11 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
           bool leave = false;
           if ((spins & 3u) == 3u) {
             if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) leave = true;
-            else if (*reinterpret_cast<volatile int *>(&ctl->hungry) >= a.n_warps) {
-              atomicMax(&ctl->signal, SIG_SLICE_END);    // every warp is waiting: nothing left anywhere
+            else if (*reinterpret_cast<volatile int *>(&ctl->hungry) >= a.n_warps || clock64() - t0 > a.slice_cycles) {
+              // every warp is waiting: nothing left anywhere -- or the time slice is over. Waiters watch the clock too:
+              // if fewer blocks are resident than the launch assumed (another context on the device, a profiler),
+              // `hungry` can never reach n_warps and the resident warps would wait for ever.
+              atomicMax(&ctl->signal, SIG_SLICE_END);
               leave = true;
             }
           }
@@ -552,7 +583,7 @@ __device__ __forceinline__ bool publish_slot(const SearchArgs &a, int lane, int 
 
 // ---- the search kernel ----------------------------------------------------------------------------
 // Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
-template <bool EXPAND, bool LEARN, bool LIN = false>
+template <bool EXPAND, bool LEARN, bool LIN = false, bool SAMPLE = false>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_MIN_BLOCKS)
 k_search(const SearchArgs a) {
   extern __shared__ __align__(16) int smem[];
@@ -605,7 +636,7 @@ k_search(const SearchArgs a) {
       } else {
         const long long w0 = clock64();
         lastwork = w0 - t0;
-        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry);
+        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
         waited += clock64() - w0;
         if (slot < 0) break;
         claims++;
@@ -742,12 +773,26 @@ k_search(const SearchArgs a) {
     }
     // prio-- on success, prio++ on failure (src/csolve.c:459-462)
     if (a.gprio != nullptr && lane == 0) atomicAdd(&a.gprio[var], ok ? -1 : 1);
+    bool s_hit = false;
+    if (SAMPLE) {
+      __syncwarp();
+      s_hit = sample_hit(a, sample_dom_hash(s.p, V, lane), var, val, !ok);
+      if (s_hit && !(ok && flevel + 1 == V)) {
+        int *r = sample_begin(a, lane, ok ? 0 : SAMPLE_FAILED, var, val, best);
+        if (r != nullptr) for (int w = lane; w < 2 * V; w += 32) { r[4 + w] = s.p[w]; r[4 + 2 * V + w] = s.d[w]; }
+      }
+    }
 
     if (!ok) {
       cuts++;
     } else if (flevel + 1 == V) {
       // all variables assigned: leaf (src/csolve.c:416-424, 222-244)
-      if (warp_all_true(m, s, lane)) {
+      const bool leaf_ok = warp_all_true(m, s, lane);
+      if (SAMPLE && s_hit) {
+        int *r = sample_begin(a, lane, leaf_ok ? SAMPLE_LEAF : 0, var, val, best);
+        if (r != nullptr) for (int w = lane; w < 2 * V; w += 32) { r[4 + w] = s.p[w]; r[4 + 2 * V + w] = s.d[w]; }
+      }
+      if (leaf_ok) {
         bool accepted = true;
         int key = 0;
         if (m.objective == CSOLVE_OBJ_MIN) {
@@ -1015,7 +1060,7 @@ __device__ __forceinline__ uint32_t lov_rebuild_F(const LovTables &t, int V, int
 // k_rebalance and the host see it.
 __device__ __forceinline__ int lov_sframe_words(int V) { return (8 + 3 * V + 3) & ~3; }   // header, domains, value sets; 16-byte aligned
 
-template <bool EXPAND, bool BITS>
+template <bool EXPAND, bool BITS, bool SAMPLE = false>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_LOV_MIN_BLOCKS)
 k_search_lov(const SearchArgs a) {
   extern __shared__ __align__(16) int smem[];
@@ -1095,6 +1140,24 @@ k_search_lov(const SearchArgs a) {
     __syncwarp();
   }
 
+  // parity instrumentation (SAMPLE instances only): identity hash of a parent state, one record
+  auto s_hash = [&](int l, int h) {
+    return __reduce_xor_sync(FULL, act ? mix_hash(0x9E3779B9u + (unsigned)lane, (unsigned)(l + zb), (unsigned)(h + zb)) : 0u);
+  };
+  auto s_record = [&](int flags, int svar, int sval, int l0, int h0, int l1, int h1) {
+    int *r = sample_begin(a, lane, flags, svar, sval + zb, 0);
+    if (r != nullptr && act) {
+      reinterpret_cast<int2 *>(r + 4)[lane] = make_int2(l0 + zb, h0 + zb);
+      reinterpret_cast<int2 *>(r + 4 + 2 * V)[lane] = make_int2(l1 + zb, h1 + zb);
+    }
+  };
+  // values [b0, b1) (bit indices) of the top frame's variable that are already forbidden: failed nodes, counted in bulk
+  auto s_skipped = [&](int b0, int b1, int svar, int l0, int h0) {
+    const unsigned hp = s_hash(l0, h0);
+    for (int b = b0; b < b1; b++)
+      if (sample_hit(a, hp, svar, vbase + b + zb, true)) s_record(SAMPLE_FAILED | SAMPLE_COUNTED, svar, vbase + b, l0, h0, l0, h0);
+  };
+
   bool have = false;
   int *sf = sst + level * sfw;        // the top frame; moved with the stack (recomputing it cost 8 instructions per node)
   int var = 0, cur = 0, flevel = 0;   // top frame: branching variable, cursor, level
@@ -1126,7 +1189,7 @@ k_search_lov(const SearchArgs a) {
       } else {
         const long long w0 = clock64();
         lastwork = w0 - t0;
-        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry);
+        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
         waited += clock64() - w0;
         if (slot < 0) break;
         claims++;
@@ -1178,6 +1241,7 @@ k_search_lov(const SearchArgs a) {
       // fails at the first trim of its own variable (lov_trim on [val, val]): counted, not executed
       // (`avail` is kept in a register while the frame is the top one)
       if (avail == 0u) {
+        if (SAMPLE) s_skipped(cur - vbase, cur - vbase + (int)rem, var, plo, phi);
         n32 += rem; c32 += rem;
         level--; sf -= sfw;
         have = false;
@@ -1186,6 +1250,7 @@ k_search_lov(const SearchArgs a) {
       const int b = __ffs((int)avail) - 1;
       avail &= avail - 1u;
       const unsigned skipped = (unsigned)(b - (cur - vbase));
+      if (SAMPLE) s_skipped(cur - vbase, b, var, plo, phi);
       n32 += skipped; c32 += skipped;
       val = vbase + b;
       rem -= skipped + 1u;
@@ -1206,6 +1271,11 @@ k_search_lov(const SearchArgs a) {
     const bool ok = BITS ? lov_fixpoint_bits_node(T, vbase, lane, lo, hi, F, var, val, props, visits)
                          : lov_fixpoint(T, V, has_consts, lane, lo, hi, 1u << var, props, visits);
     n32++;
+    bool s_hit = false;
+    if (SAMPLE) {
+      s_hit = sample_hit(a, s_hash(plo, phi), var, val + zb, !ok);
+      if (s_hit && !(ok && flevel + 1 == V)) s_record(ok ? 0 : SAMPLE_FAILED, var, val, plo, phi, lo, hi);
+    }
 
     if (!ok) {
       c32++;
@@ -1220,7 +1290,9 @@ k_search_lov(const SearchArgs a) {
         const int cb = T.cptr[i], ce = T.cptr[i + 1];
         if (cb + lane < ce && T.cval[cb + lane] == Xi) good = false;
       }
-      if (__all_sync(FULL, good || !act)) {
+      const bool leaf_ok = __all_sync(FULL, good || !act);
+      if (SAMPLE && s_hit) s_record(leaf_ok ? SAMPLE_LEAF : 0, var, val, plo, phi, lo, hi);
+      if (leaf_ok) {
         bool accepted = true;
         if (m.objective == CSOLVE_OBJ_ANY) {
           int old = 0;
@@ -1293,6 +1365,16 @@ k_search_lov(const SearchArgs a) {
         // so each remaining value is an accepted leaf and each forbidden one a failed node -- counted, not searched
         const uint32_t Fn = __shfl_sync(FULL, F, nv);
         const int good = __popc(~Fn & ((nrem >= 32u ? 0xffffffffu : ((1u << nrem) - 1u)) << (nlo - vbase)));
+        if (SAMPLE) {
+          // the nodes of the last level: forbidden values fail, every other value is an accepted leaf
+          const unsigned hp = s_hash(lo, hi);
+          for (int b = nlo - vbase; b < nlo - vbase + (int)nrem; b++) {
+            const bool bad = (Fn >> b) & 1u;
+            if (!sample_hit(a, hp, nv, vbase + b + zb, bad)) continue;
+            s_record(SAMPLE_COUNTED | (bad ? SAMPLE_FAILED : SAMPLE_LEAF), nv, vbase + b, lo, hi,
+                     lane == nv ? vbase + b : lo, lane == nv ? vbase + b : hi);
+          }
+        }
         n32 += nrem; c32 += nrem - (unsigned)good; sols += (unsigned)good;
         props += (lane == nv && nrem > 1u) ? (unsigned)good : 0u;  // each of those nodes narrows nv to its value (branch-free:
                                                                    // a divergent branch here kept the warp split far into the loop)
@@ -1301,7 +1383,10 @@ k_search_lov(const SearchArgs a) {
         // (BITS: what is left of its interval is forbidden -- failed nodes, counted here) the child takes its place
         // instead of going on top of it: no pop back into an exhausted frame, no reload of it.
         const bool last_value = BITS ? avail == 0u : rem == 0u;
-        if (BITS && last_value) { n32 += rem; c32 += rem; }
+        if (BITS && last_value) {
+          if (SAMPLE) s_skipped(cur - vbase, cur - vbase + (int)rem, var, plo, phi);
+          n32 += rem; c32 += rem;
+        }
         int *nf = last_value ? sf : sf + sfw;
         if (lane == 0) {
           if (!last_value) reinterpret_cast<int2 *>(sf)[0] = make_int2(cur, (int)rem);
@@ -1583,7 +1668,7 @@ __device__ __forceinline__ uint32_t lovk_F(const LovK<K> &x, int v) {
   return __shfl_sync(FULL, f, v & 31);
 }
 
-template <bool EXPAND, int K>
+template <bool EXPAND, int K, bool SAMPLE = false>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, 3)
 k_search_lovk(const SearchArgs a) {
   const DevModel &m = a.m;
@@ -1612,6 +1697,27 @@ k_search_lovk(const SearchArgs a) {
 #pragma unroll
   for (int q = 0; q < K; q++) { amask[q] = 0; P.lo[q] = P.hi[q] = m.lov_vbase; P.F[q] = 0; }
 
+  // parity instrumentation (SAMPLE instances only)
+  auto s_hash = [&](const LovK<K> &z) {
+    unsigned h = 0;
+#pragma unroll
+    for (int q = 0; q < K; q++)
+      if (lane + 32 * q < V) h ^= mix_hash(0x9E3779B9u + (unsigned)(lane + 32 * q), (unsigned)z.lo[q], (unsigned)z.hi[q]);
+    return __reduce_xor_sync(FULL, h);
+  };
+  auto s_record = [&](int flags, int svar, int sval, const LovK<K> &z0, const LovK<K> &z1) {
+    int *r = sample_begin(a, lane, flags, svar, sval, 0);
+    if (r == nullptr) return;
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      const int v = lane + 32 * q;
+      if (v < V) {
+        reinterpret_cast<int2 *>(r + 4)[v] = make_int2(z0.lo[q], z0.hi[q]);
+        reinterpret_cast<int2 *>(r + 4 + 2 * V)[v] = make_int2(z1.lo[q], z1.hi[q]);
+      }
+    }
+  };
+
   for (;;) {
     if (level < base) {
       const int *src;
@@ -1622,7 +1728,7 @@ k_search_lovk(const SearchArgs a) {
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
       } else {
-        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry);
+        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
         if (slot < 0) break;
         src = a.pool + (size_t)slot * fw;
       }
@@ -1670,6 +1776,7 @@ k_search_lovk(const SearchArgs a) {
     const int val = step_value(flo, fhi, iter);
     iter++;
     if ((fvarF >> (val - m.lov_vbase)) & 1u) {      // already forbidden: a failed node (see k_search_lov)
+      if (SAMPLE && sample_hit(a, s_hash(P), var, val, true)) s_record(SAMPLE_FAILED | SAMPLE_COUNTED, var, val, P, P);
       nodes++; cuts++;
       continue;
     }
@@ -1685,6 +1792,13 @@ k_search_lovk(const SearchArgs a) {
     }
     const bool ok = lovk_fixpoint<K>(m, lane, x, pend, props, visits);
     nodes++;
+    bool s_hit = false;
+    unsigned s_hx = 0;
+    if (SAMPLE) {
+      s_hit = sample_hit(a, s_hash(P), var, val, !ok);
+      if (!ok && s_hit) s_record(SAMPLE_FAILED, var, val, P, x);
+      if (ok) s_hx = s_hash(x);
+    }
 
     if (!ok) {
       cuts++;
@@ -1707,6 +1821,13 @@ k_search_lovk(const SearchArgs a) {
           const int v = lane + 32 * q;
           const bool fixed = v < V && !((am[q] >> lane) & 1u) && x.lo[q] == x.hi[q];
           const unsigned mk = __ballot_sync(FULL, fixed);
+          if (SAMPLE) {
+            for (unsigned rest = mk; rest; rest &= rest - 1u) {
+              const int bit = __ffs((int)rest) - 1;
+              const int fv = __shfl_sync(FULL, x.lo[q], bit);
+              if (sample_hit(a, s_hx, bit + 32 * q, fv, false)) s_record(SAMPLE_COUNTED, bit + 32 * q, fv, x, x);
+            }
+          }
           cnt += (unsigned)__popc(mk);
           am[q] |= mk;
           fold ^= fixed ? mix_hash(0x9E3779B9u, (unsigned)v, (unsigned)x.lo[q]) : 0u;
@@ -1721,6 +1842,7 @@ k_search_lovk(const SearchArgs a) {
         nv = lovk_select<K>(m, lane, x, am, a.order, lev);
         nb = lovk_bounds<K>(x, nv);
         if (nb.x != nb.y) break;
+        if (SAMPLE && sample_hit(a, s_hx, nv, nb.x, false)) s_record(SAMPLE_COUNTED, nv, nb.x, x, x);
         nodes++;                                   // the level of a fixed variable
         hsh = mix_hash(hsh, (unsigned)nv, (unsigned)nb.x);
 #pragma unroll
@@ -1733,7 +1855,9 @@ k_search_lovk(const SearchArgs a) {
 #pragma unroll
         for (int q = 0; q < K; q++)
           if (lane + 32 * q < V && (x.lo[q] != x.hi[q] || ((x.F[q] >> (x.lo[q] - m.lov_vbase)) & 1u))) good = false;
-        if (__all_sync(FULL, good)) {
+        const bool leaf_ok = __all_sync(FULL, good);
+        if (SAMPLE && s_hit) s_record(leaf_ok ? SAMPLE_LEAF : 0, var, val, P, x);
+        if (leaf_ok) {
           bool accepted = true;
           if (m.objective == CSOLVE_OBJ_ANY) {
             int old = 0;
@@ -1756,6 +1880,7 @@ k_search_lovk(const SearchArgs a) {
           }
         }
       } else {
+        if (SAMPLE && s_hit) s_record(0, var, val, P, x);
         int *g;
         if (EXPAND) {
           int slot = 0;
@@ -1919,8 +2044,8 @@ k_propagate_batch_lovk(const DevModel m, int n_nodes, const int32_t *dom_in, con
 
 template <int K>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK)
-k_root_frames_lovk(const DevModel m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out, int32_t *n_out,
-                   unsigned char *root_failed) {
+k_root_frames_lovk(const DevModel m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out, int out_cap,
+                   int32_t *n_out, unsigned char *root_failed) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int V = m.n_vars, fw = m.frame_words;
   const int n_warps = gridDim.x * WARPS_PER_BLOCK;
@@ -1941,6 +2066,7 @@ k_root_frames_lovk(const DevModel m, int n_roots, const int32_t *root_dom, int o
     int slot = 0;
     if (lane == 0) slot = atomicAdd(n_out, 1);
     slot = __shfl_sync(FULL, slot, 0);
+    if (slot >= out_cap) continue;             // the host checks the capacity before the launch; never write past the pool
     int *g = frames_out + (size_t)slot * fw;
     if (lane == 0) {
       __stcg(reinterpret_cast<int4 *>(g), make_int4(nv, 0, (int)((unsigned)nb.y - (unsigned)nb.x), nb.x));
@@ -1976,7 +2102,14 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
     const unsigned ring = (unsigned)(a.pool_cap - a.n_initial);
     for (int i = served + (int)threadIdx.x; i - taken < 0; i += blockDim.x) a.ready[a.n_initial + (int)((unsigned)i % ring)] = 0;
     __syncthreads();
-    if (threadIdx.x == 0 && taken - served > 0) a.ctl->item_count = taken;
+    if (threadIdx.x == 0) {
+      // unserved tickets are void; both counters are rebased to the ring size so that the ticket -> slot mapping
+      // (ticket % ring) survives any number of slices without the 32-bit counters wrapping
+      const int cnt = taken - served > 0 ? taken : served;
+      const int shift = (int)((unsigned)taken / ring * ring);
+      a.ctl->item_count = cnt - shift;
+      a.ctl->item_next = taken - shift;
+    }
     __syncthreads();
   }
   // frames still in the frontier pool are work too: nothing to move while they last
@@ -2171,8 +2304,8 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
 // The warp propagates EVERY variable's watchers to fixpoint (what the reference's root sweeps do,
 // src/propagate.c:474-485) and, if the root is consistent, emits its level-0 frame tagged with r.
 __global__ void __launch_bounds__(THREADS_PER_BLOCK)
-k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out, int32_t *n_out,
-              unsigned char *root_failed) {
+k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out, int out_cap,
+              int32_t *n_out, unsigned char *root_failed) {
   extern __shared__ __align__(16) int smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int4 *wrec; const int *wptr;
@@ -2200,7 +2333,8 @@ k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order,
       if (lane == 0) slot = atomicAdd(n_out, 1);
       slot = __shfl_sync(FULL, slot, 0);
       // header word 6 = root id; the path hash starts from the root id so partitions spread the roots
-      write_child_frame(m, s, frames_out + (size_t)slot * fw, lane, nv, 0, r, mix_hash(0x1234567u, (unsigned)r, 0u), -1);
+      if (slot < out_cap)
+        write_child_frame(m, s, frames_out + (size_t)slot * fw, lane, nv, 0, r, mix_hash(0x1234567u, (unsigned)r, 0u), -1);
     }
     __syncwarp();
   }
@@ -2218,17 +2352,33 @@ size_t search_smem_bytes(const DevModel &m, bool learn) {
   return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
 }
 
+template <bool SAMPLE>
 static const void *lovk_kernel(bool expand, int K) {
   switch (K) {
-  case 2: return expand ? (const void *)k_search_lovk<true, 2> : (const void *)k_search_lovk<false, 2>;
-  case 3: return expand ? (const void *)k_search_lovk<true, 3> : (const void *)k_search_lovk<false, 3>;
-  default: return expand ? (const void *)k_search_lovk<true, 4> : (const void *)k_search_lovk<false, 4>;
+  case 2: return expand ? (const void *)k_search_lovk<true, 2, SAMPLE> : (const void *)k_search_lovk<false, 2, SAMPLE>;
+  case 3: return expand ? (const void *)k_search_lovk<true, 3, SAMPLE> : (const void *)k_search_lovk<false, 3, SAMPLE>;
+  default: return expand ? (const void *)k_search_lovk<true, 4, SAMPLE> : (const void *)k_search_lovk<false, 4, SAMPLE>;
   }
 }
 
+template <bool SAMPLE>
 static const void *lov_kernel(bool expand, bool bits) {
-  if (expand) return bits ? (const void *)k_search_lov<true, true> : (const void *)k_search_lov<true, false>;
-  return bits ? (const void *)k_search_lov<false, true> : (const void *)k_search_lov<false, false>;
+  if (expand) return bits ? (const void *)k_search_lov<true, true, SAMPLE> : (const void *)k_search_lov<true, false, SAMPLE>;
+  return bits ? (const void *)k_search_lov<false, true, SAMPLE> : (const void *)k_search_lov<false, false, SAMPLE>;
+}
+
+template <bool SAMPLE>
+static const void *general_kernel(bool expand, bool lin) {
+  if (lin) return expand ? (const void *)k_search<true, false, true, SAMPLE> : (const void *)k_search<false, false, true, SAMPLE>;
+  return expand ? (const void *)k_search<true, false, false, SAMPLE> : (const void *)k_search<false, false, false, SAMPLE>;
+}
+
+// the kernel instance a search runs on (sample: the parity-instrumented instances, never with learning)
+static const void *search_kernel(const DevModel &m, bool expand, bool learn, bool sample) {
+  if (learn) return expand ? (const void *)k_search<true, true> : (const void *)k_search<false, true>;
+  if (m.lovk) return sample ? lovk_kernel<true>(expand, m.lovk) : lovk_kernel<false>(expand, m.lovk);
+  if (m.lov) return sample ? lov_kernel<true>(expand, m.lov_bits != 0) : lov_kernel<false>(expand, m.lov_bits != 0);
+  return sample ? general_kernel<true>(expand, m.n_lin > 0) : general_kernel<false>(expand, m.n_lin > 0);
 }
 
 static cudaError_t ensure_smem(const void *fn, size_t bytes) {
@@ -2238,56 +2388,19 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 bool search_learns(const SearchArgs &a) { return a.ng.lits != nullptr; }
 
-int search_blocks_per_sm(const DevModel &m, bool expand, bool learn) {
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn, bool sample) {
   int n = 0;
   const size_t smem = search_smem_bytes(m, learn);
-  if (learn) {
-    const void *fn = expand ? (const void *)k_search<true, true> : (const void *)k_search<false, true>;
-    if (ensure_smem(fn, smem) != cudaSuccess) return 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem);
-    return n;
-  }
-  if (m.lovk) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lovk_kernel(expand, m.lovk), THREADS_PER_BLOCK, 0);
-    return n;
-  }
-  if (m.lov) {
-    const void *lf = lov_kernel(expand, m.lov_bits != 0);
-    if (ensure_smem(lf, smem) != cudaSuccess) return 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lf, THREADS_PER_BLOCK, smem);
-    return n;
-  }
-  const void *fn = m.n_lin > 0 ? (expand ? (const void *)k_search<true, false, true> : (const void *)k_search<false, false, true>)
-                               : (expand ? (const void *)k_search<true, false, false> : (const void *)k_search<false, false, false>);
+  const void *fn = search_kernel(m, expand, learn, sample);
   if (ensure_smem(fn, smem) != cudaSuccess) return 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem) != cudaSuccess) return 0;
   return n;
 }
 
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
   const bool learn = search_learns(a);
   const size_t smem = search_smem_bytes(a.m, learn);
-  if (learn) {
-    // conflict-clause learning runs on the general kernel
-    const void *fn = expand ? (const void *)k_search<true, true> : (const void *)k_search<false, true>;
-    cudaError_t e = ensure_smem(fn, smem);
-    if (e != cudaSuccess) return e;
-    void *args[] = {(void *)&a};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(THREADS_PER_BLOCK), args, smem, st);
-  }
-  if (a.m.lovk) {
-    void *args[] = {(void *)&a};
-    return cudaLaunchKernel(lovk_kernel(expand, a.m.lovk), dim3(grid), dim3(THREADS_PER_BLOCK), args, 0, st);
-  }
-  if (a.m.lov) {
-    const void *lf = lov_kernel(expand, a.m.lov_bits != 0);
-    cudaError_t e = ensure_smem(lf, smem);
-    if (e != cudaSuccess) return e;
-    void *args[] = {(void *)&a};
-    return cudaLaunchKernel(lf, dim3(grid), dim3(THREADS_PER_BLOCK), args, smem, st);
-  }
-  const void *fn = a.m.n_lin > 0 ? (expand ? (const void *)k_search<true, false, true> : (const void *)k_search<false, false, true>)
-                                 : (expand ? (const void *)k_search<true, false, false> : (const void *)k_search<false, false, false>);
+  const void *fn = search_kernel(a.m, expand, learn, a.sample_mod != 0u);
   cudaError_t e = ensure_smem(fn, smem);
   if (e != cudaSuccess) return e;
   void *args[] = {(void *)&a};
@@ -2295,12 +2408,12 @@ cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream
 }
 
 cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
-                               int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t st) {
+                               int out_cap, int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t st) {
   if (m_in.lovk) {
     switch (m_in.lovk) {
-    case 2: k_root_frames_lovk<2><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, n_out, root_failed); break;
-    case 3: k_root_frames_lovk<3><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, n_out, root_failed); break;
-    default: k_root_frames_lovk<4><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, n_out, root_failed); break;
+    case 2: k_root_frames_lovk<2><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, out_cap, n_out, root_failed); break;
+    case 3: k_root_frames_lovk<3><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, out_cap, n_out, root_failed); break;
+    default: k_root_frames_lovk<4><<<grid, THREADS_PER_BLOCK, 0, st>>>(m_in, n_roots, root_dom, order, frames_out, out_cap, n_out, root_failed); break;
     }
     return cudaGetLastError();
   }
@@ -2309,7 +2422,7 @@ cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t 
   const size_t smem = search_smem_bytes(m, false);
   cudaError_t e = ensure_smem((const void *)k_root_frames, smem);
   if (e != cudaSuccess) return e;
-  k_root_frames<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_roots, root_dom, order, frames_out, n_out, root_failed);
+  k_root_frames<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_roots, root_dom, order, frames_out, out_cap, n_out, root_failed);
   return cudaGetLastError();
 }
 

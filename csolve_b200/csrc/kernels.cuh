@@ -92,7 +92,21 @@ struct SearchArgs {
   int32_t n_initial;          // the first n_initial pool entries are the expanded root frontier (rank partition applies)
   int32_t part_rank;          // this process searches the frontier frames whose path hash % part_count == part_rank
   int32_t part_count;
+  // Parity instrumentation (csolve_solve_options.sample_mod > 0; runs the SAMPLE instances of the search kernels):
+  // every search node -- executed or counted in bulk -- whose identity hash (parent domains, variable, value) is 0
+  // modulo sample_mod is written to sample_rec as
+  //   [0] flags (SAMPLE_*)  [1] variable  [2] value  [3] incumbent the node was propagated against
+  //   [4 .. 4+2V) parent domains (state before the assignment)   [4+2V .. 4+4V) post-fixpoint domains
+  int32_t *sample_rec;        // [sample_cap][4 + 4 * n_vars]
+  int32_t *sample_n;          // records wanted so far (may exceed sample_cap: the excess was dropped)
+  int32_t sample_cap;
+  uint32_t sample_mod;
+  uint32_t sample_fkeep;      // of the hits that failed, 1 in sample_fkeep is kept (>= 1)
 };
+static const int SAMPLE_FAILED = 1;    // the node failed (PROP_ERROR); its post-fixpoint domains are meaningless
+static const int SAMPLE_COUNTED = 2;   // the node was counted by a bulk shortcut of the kernel, not executed
+static const int SAMPLE_LEAF = 4;      // the node is an accepted leaf (every variable a value, every clause true)
+CSOLVE_HOSTDEV static inline int sample_words(int n_vars) { return 4 + 4 * n_vars; }
 
 size_t search_smem_bytes(const DevModel &m, bool learn = false);
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s);
@@ -104,8 +118,8 @@ cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps
 cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t s);
-int search_blocks_per_sm(const DevModel &m, bool expand, bool learn = false);
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn = false, bool sample = false);
 cudaError_t launch_root_frames(const DevModel &m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
-                               int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t s);
+                               int out_cap, int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t s);
 
 }  // namespace csolve_dev

@@ -75,7 +75,11 @@ class _SolveOptions(C.Structure):
     _fields_ = [("order", C.c_int32), ("part_rank", C.c_int32), ("part_count", C.c_int32),
                 ("split_target", C.c_int32), ("max_solutions", C.c_int32), ("time_limit_ms", C.c_int32),
                 ("slice_ms", C.c_int32), ("create_conflicts", C.c_int32), ("reserved", C.c_int32),
-                ("prefer_failing", C.c_int32)]
+                ("prefer_failing", C.c_int32), ("sample_mod", C.c_uint32), ("sample_cap", C.c_int32),
+                ("restart_frequency", C.c_int32), ("sample_failed_keep", C.c_uint32), ("reserved2", C.c_int32 * 4)]
+
+
+SAMPLE_FAILED, SAMPLE_COUNTED, SAMPLE_LEAF = 1, 2, 4   # CSOLVE_SAMPLE_* flags of a sampled search node
 
 
 class _GpuResult(C.Structure):
@@ -121,6 +125,8 @@ def library():
     lib.csolve_gpu_init.argtypes = [C.POINTER(_GpuConfig)]
     lib.csolve_gpu_shutdown.restype = None
     lib.csolve_gpu_load.argtypes = [C.POINTER(FlatModel), C.POINTER(C.c_void_p)]
+    lib.csolve_gpu_load_device.argtypes = [C.POINTER(FlatModel), C.c_int32, C.POINTER(C.c_void_p)]
+    lib.csolve_gpu_get_samples.argtypes = [C.c_void_p, I32P, C.c_int32, I32P, I32P]
     lib.csolve_gpu_unload.argtypes = [C.c_void_p]
     lib.csolve_gpu_unload.restype = None
     lib.csolve_gpu_propagate_batch.argtypes = [C.c_void_p, C.c_int32, I32P, I32P, I32P, I32P, I32P, U8P]
@@ -207,12 +213,11 @@ class GpuProblem:
 
     def __init__(self, model, device=0):
         lib = library()
-        _check(lib.csolve_gpu_init(C.byref(_GpuConfig(device))))
         self.model = model
         flat = model.flat if isinstance(model, Model) else model
         self.n_vars = flat.n_vars
         h = C.c_void_p()
-        _check(lib.csolve_gpu_load(C.byref(flat), C.byref(h)))
+        _check(lib.csolve_gpu_load_device(C.byref(flat), int(device), C.byref(h)))
         self._h = h
 
     def propagate_batch(self, dom_in, var, val, best=None):
@@ -234,11 +239,13 @@ class GpuProblem:
         return out, failed
 
     def solve(self, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0,
-              time_limit_ms=0, slice_ms=0, prefer_failing=False, create_conflicts=False):
+              time_limit_ms=0, slice_ms=0, prefer_failing=False, create_conflicts=False, sample_mod=0, sample_cap=0,
+              restart_frequency=0, sample_failed_keep=1):
         if isinstance(order, str):
             order = ORDER_NAMES[order]
         opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
-                            1 if create_conflicts else 0, 0, 1 if prefer_failing else 0)
+                            1 if create_conflicts else 0, 0, 1 if prefer_failing else 0, int(sample_mod), int(sample_cap),
+                            int(restart_frequency), int(sample_failed_keep))
         res = _GpuResult()
         _check(library().csolve_gpu_solve(self._h, C.byref(opt), C.byref(res)))
         sols = []
@@ -247,6 +254,21 @@ class GpuProblem:
             _check(library().csolve_gpu_get_solution(self._h, i, buf))
             sols.append(list(buf))
         return SolveResult(res, sols)
+
+    def samples(self, cap=1 << 20):
+        """search nodes recorded by the last solve(sample_mod=k): dict of arrays flags [n], var [n], val [n], best [n],
+        parent [n, 2V], child [n, 2V] (+ 'seen': hits including the ones dropped when the buffer was full)"""
+        W = 4 + 4 * self.n_vars
+        n, seen = C.c_int32(), C.c_int32()
+        I32P = C.POINTER(C.c_int32)
+        _check(library().csolve_gpu_get_samples(self._h, None, 0, C.byref(n), C.byref(seen)))
+        cap = min(cap, max(seen.value, 1))
+        buf = np.zeros((cap, W), np.int32)
+        _check(library().csolve_gpu_get_samples(self._h, buf.ctypes.data_as(I32P), cap, C.byref(n), C.byref(seen)))
+        buf = buf[:n.value]
+        V = self.n_vars
+        return dict(flags=buf[:, 0].copy(), var=buf[:, 1].copy(), val=buf[:, 2].copy(), best=buf[:, 3].copy(),
+                    parent=buf[:, 4:4 + 2 * V].copy(), child=buf[:, 4 + 2 * V:].copy(), seen=seen.value)
 
     def nogoods(self, cap_lits=1 << 22, cap_ng=1 << 18):
         """nogoods learned by the last solve(create_conflicts=True): list of [(var, value), ...]"""
@@ -309,7 +331,7 @@ class GpuProblem:
         return frames.shape[0]
 
     def solve_batch(self, root_domains, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0,
-                    max_solutions=0, time_limit_ms=0, slice_ms=0):
+                    max_solutions=0, time_limit_ms=0, slice_ms=0, sample_mod=0, sample_cap=0, sample_failed_keep=1):
         """Search many roots that share this model's network. root_domains: [R, 2*V] int32.
         Returns (SolveResult, per-root solution counts [R], per-root infeasible-at-root flags [R]);
         SolveResult.assignments are (root id, values) pairs."""
@@ -320,7 +342,8 @@ class GpuProblem:
         n = roots.shape[0]
         counts = np.zeros(n, np.uint32)
         failed = np.zeros(n, np.uint8)
-        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms, 0, 0, 0)
+        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms, 0, 0, 0,
+                            int(sample_mod), int(sample_cap), 0, int(sample_failed_keep))
         res = _GpuResult()
         _check(library().csolve_gpu_solve_batch(self._h, C.byref(opt), n, roots.ctypes.data_as(I32P),
                                                 counts.ctypes.data_as(C.POINTER(C.c_uint32)),

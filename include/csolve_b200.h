@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSOLVE_B200_ABI_VERSION 2
+#define CSOLVE_B200_ABI_VERSION 3
 
 /* ---- error codes (all entry points return 0 on success) ------------------ */
 #define CSOLVE_OK                 0
@@ -119,7 +119,14 @@ int csolve_model_parse(const char *text, size_t len, const csolve_front_options 
 const csolve_flat_model *csolve_model_flat(const csolve_model *m);
 void csolve_model_free(csolve_model *m);
 
-/* ---- device ---------------------------------------------------------------*/
+/* ---- device ---------------------------------------------------------------
+ * Threading: a csolve_gpu_problem belongs to the device it was loaded on and must be used by one host thread at a
+ * time; different problems (on the same or on different devices) may be used from different threads concurrently.
+ * csolve_gpu_init() only chooses the device later csolve_gpu_load() calls use; csolve_gpu_load_device() names it.
+ * Domains handed to csolve_gpu_solve_batch (root_dom) and csolve_gpu_propagate_batch (dom_in, val) must be
+ * sub-intervals of the model's own root domains -- the model was compiled against those (constant folding of
+ * variables fixed at root, no-saturation proofs of the specialised clause forms, the 32-value window of the
+ * value-set kernels); anything else is rejected with CSOLVE_ERR_INVALID. */
 typedef struct csolve_gpu_problem csolve_gpu_problem;
 
 typedef struct csolve_gpu_config {
@@ -147,6 +154,18 @@ typedef struct csolve_solve_options {
                                 * shared by all warps and updated during the search (src/csolve.c:459-462,
                                 * src/propagate.c:33-54). The tree then depends on timing: ALL counts and optima are
                                 * unchanged, node counters are not reproducible. 0 = static parse-time priorities */
+  uint32_t sample_mod;         /* parity instrumentation, 0 = off. Every search node -- executed or counted in bulk by a
+                                * kernel shortcut -- whose identity hash (parent domains, variable, value) is 0 modulo
+                                * sample_mod is recorded: parent domains, decision, incumbent, fail flag, post-fixpoint
+                                * domains. The search then runs on instrumented instances of the same kernels (same
+                                * source, a template flag). Read the records with csolve_gpu_get_samples(); replayed
+                                * through the reference's bind + propagate_clauses (src/csolve.c:448-457) they must
+                                * come out identical. Not available together with create_conflicts. */
+  int32_t sample_cap;          /* records kept (0 = 65536); further hits are counted and dropped */
+  int32_t restart_frequency;   /* -r (src/main.c:109-113): ANY models restart after restart_frequency * luby(k) failed
+                                * nodes (src/csolve.c:76-83,264-276). 0 = never restart */
+  uint32_t sample_failed_keep; /* of the sampled nodes that failed, keep 1 in sample_failed_keep (0, 1 = all): most nodes fail */
+  int32_t reserved2[4];
 } csolve_solve_options;
 
 typedef struct csolve_gpu_result {
@@ -168,7 +187,8 @@ typedef struct csolve_gpu_result {
 
 int  csolve_gpu_init(const csolve_gpu_config *cfg);
 void csolve_gpu_shutdown(void);
-int  csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **out);
+int  csolve_gpu_load(const csolve_flat_model *m, csolve_gpu_problem **out);        /* on the device of the last csolve_gpu_init() */
+int  csolve_gpu_load_device(const csolve_flat_model *m, int32_t device, csolve_gpu_problem **out);
 void csolve_gpu_unload(csolve_gpu_problem *p);
 
 /* Parity hook: B independent node transitions (src/csolve.c:448-457):
@@ -224,6 +244,15 @@ int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_options *op
  * returns the number of nogoods n in *n_out. For inspection and tests. */
 int csolve_gpu_get_nogoods(csolve_gpu_problem *p, int32_t *lits, int32_t cap_lits, int32_t *starts, int32_t cap_ng,
                            int32_t *n_out);
+
+/* Records written by the last csolve_gpu_solve / csolve_gpu_solve_batch with sample_mod > 0. One record is
+ * 4 + 4 * n_vars int32: flags (CSOLVE_SAMPLE_*), variable, value, incumbent, parent domains (n_vars lo,hi pairs: the
+ * state before the assignment), post-fixpoint domains (n_vars pairs; meaningless when the node failed).
+ * Copies up to cap_records records to `records` (HOST); *n_out = records copied, *n_seen = hits including dropped. */
+#define CSOLVE_SAMPLE_FAILED  1   /* the node failed (PROP_ERROR) */
+#define CSOLVE_SAMPLE_COUNTED 2   /* counted by a bulk shortcut of the kernel, not executed */
+#define CSOLVE_SAMPLE_LEAF    4   /* an accepted leaf: every variable a value and every clause true */
+int csolve_gpu_get_samples(csolve_gpu_problem *p, int32_t *records, int32_t cap_records, int32_t *n_out, int32_t *n_seen);
 
 /* key of stored assignment i: MIN/MAX objective value, or the root id for batched roots */
 int csolve_gpu_get_solution_key(csolve_gpu_problem *p, int32_t i, int32_t *key);

@@ -530,7 +530,8 @@ static int select_var(const orc *o, const val_t *dom, const uint8_t *assigned, i
   return bestv;
 }
 
-typedef struct { orc *o; int order; int *static_order; uint8_t *assigned; orc_result *res; uint64_t max_calls; int32_t *solution; } tree_ctx;
+typedef struct { orc *o; int order; int *static_order; uint8_t *assigned; orc_result *res; uint64_t max_calls; int32_t *solution;
+                 uint32_t part, n_parts, counter; int split_level; } tree_ctx;
 
 static void tree_rec(tree_ctx *t, int level) {
   orc *o = t->o;
@@ -541,24 +542,28 @@ static void tree_rec(tree_ctx *t, int level) {
   val_t bounds = o->dom[var];
   t->assigned[var] = 1;
   for (uint32_t it = 0; step_check(it, bounds); it++) {
+    /* this process's share: the (node, subtree) pairs at the split level are dealt round-robin in DFS order; the
+     * levels above it are walked by every part and counted by part 0 only */
+    if (level == t->split_level && t->n_parts > 1 && t->counter++ % t->n_parts != t->part) continue;
+    const int counted = t->n_parts <= 1 || level >= t->split_level || t->part == 0;
     size_t depth = o->trail_len;
     val_t obj_saved = mkv(0, 0);
     if (o->obj_var >= 0) obj_saved = o->dom[o->obj_var];
     if (!is_value(o->dom[var])) { int32_t x = step_val(it, bounds); bind_var(o, var, mkv(x, x)); }
     objective_update_val(o);
-    t->res->calls++;
+    t->res->calls += counted;
     if (t->max_calls && t->res->calls >= t->max_calls) t->res->hit_limit = 1;
     int failed = 0;
     if (o->obj_var >= 0 && o->dom[o->obj_var].lo > o->dom[o->obj_var].hi) failed = 1;  /* device rule: empty <obj> fails */
     if (!failed) failed = check_assignment(o, var);
     if (failed) {
-      t->res->cuts++;
+      t->res->cuts += counted;
     } else if (level + 1 == V) {
       if (root_true(o) && objective_better(o)) {
         objective_update_best(o);
         if (t->solution && (o->objective != CSOLVE_OBJ_ALL || t->res->solutions == 0))
           for (int v = 0; v < V; v++) t->solution[v] = o->dom[v].lo;
-        t->res->solutions++;
+        t->res->solutions += counted;
       }
     } else {
       tree_rec(t, level + 1);
@@ -571,7 +576,11 @@ static void tree_rec(tree_ctx *t, int level) {
   t->assigned[var] = 0;
 }
 
-int orc_solve_tree(orc *o, int order, uint64_t max_calls, orc_result *res, int32_t *solution) {
+/* part / n_parts / split_level: the nodes of level split_level (with the subtrees below them) are dealt round-robin
+ * to n_parts processes, so that they cover the tree between them; ALL mode and unsatisfiable ANY models: solutions,
+ * calls and cuts of the parts add up to the whole tree's (props do not: the levels above the split are replayed). */
+int orc_solve_tree_part(orc *o, int order, uint64_t max_calls, uint32_t part, uint32_t n_parts, int split_level,
+                        orc_result *res, int32_t *solution) {
   reset(o, order, 0);
   memset(res, 0, sizeof(*res));
   int V = o->V;
@@ -584,9 +593,14 @@ int orc_solve_tree(orc *o, int order, uint64_t max_calls, orc_result *res, int32
     so[j + 1] = x;
   }
   tree_ctx t; t.o = o; t.order = order; t.static_order = so; t.assigned = calloc(V, 1);
-  t.res = res; t.max_calls = max_calls; t.solution = solution;
+  t.res = res; t.max_calls = max_calls; t.solution = solution; t.part = part; t.n_parts = n_parts;
+  t.counter = 0; t.split_level = split_level;
   if (V > 0) tree_rec(&t, 0);
   free(so); free(t.assigned);
   res->props = o->props; res->best = o->best; res->has_solution = res->solutions > 0;
   return 0;
+}
+
+int orc_solve_tree(orc *o, int order, uint64_t max_calls, orc_result *res, int32_t *solution) {
+  return orc_solve_tree_part(o, order, max_calls, 0, 1, 0, res, solution);
 }

@@ -32,7 +32,7 @@ def test_header_symbols_are_exported():
 
 
 def test_abi_version():
-    assert cb.library().csolve_abi_version() == 2
+    assert cb.library().csolve_abi_version() == 3
 
 
 def test_header_compiles_as_c():

@@ -29,7 +29,7 @@ def _newer(target, sources):
 def build_oracle():
     src = os.path.join(ROOT, "oracle", "csolve_oracle.c")
     if not _newer(ORACLE_SO, [src, os.path.join(ROOT, "include", "csolve_b200.h")]):
-        subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+        subprocess.check_call(["gcc", "-std=c99", "-O3", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
                                src, "-o", ORACLE_SO])
     return ORACLE_SO
 
@@ -74,6 +74,7 @@ def oracle_lib():
         lib.orc_eval_root.argtypes = [C.c_void_p, I32P, I32P]
         lib.orc_solve_reference.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.POINTER(OrcResult), I32P]
         lib.orc_solve_tree.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(OrcResult), I32P]
+        lib.orc_solve_tree_part.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(OrcResult), I32P]
         for f in ("orc_neg", "orc_add", "orc_mul", "orc_min", "orc_max"):
             getattr(lib, f).restype = C.c_int32
         _orc = lib
@@ -129,6 +130,13 @@ class Oracle:
         sol = np.zeros(max(self.V, 1), np.int32)
         self.lib.orc_solve_tree(self.h, order, max_calls, C.byref(r), p32(sol))
         return r, sol[:self.V].copy()
+
+    def solve_tree_part(self, order, part, n_parts, split_level=0, max_calls=0):
+        """share `part` of the tree: the nodes of level split_level, dealt round-robin in DFS order, with their subtrees"""
+        r = OrcResult()
+        sol = np.zeros(max(self.V, 1), np.int32)
+        self.lib.orc_solve_tree_part(self.h, order, max_calls, part, n_parts, split_level, C.byref(r), p32(sol))
+        return r
 
     def __del__(self):
         try:
