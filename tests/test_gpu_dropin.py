@@ -8,6 +8,7 @@ import tempfile
 
 import pytest
 
+import csolve_b200 as cb
 import util
 from csolve_b200 import instances as I
 
@@ -46,3 +47,24 @@ def test_dropin_optimisation_and_unsat():
     assert "NO SOLUTION FOUND" in a.stdout
     a = _run(GPU_CLI, "ALL; 0 <= x; x <= 3; x > 5;")
     assert "INFEASIBLE PROBLEM" in a.stdout          # printed by the reference's own front end
+
+
+def test_front_corpus_inputs_solve_like_the_reference_cli():
+    """tests/golden/front_corpus.json (the reference's fuzz seeds mutated with its fuzz dictionary, labelled by the
+    compiled reference CLI): every accepted input, searched on the device, gives the reference's result"""
+    import json
+    corpus = json.load(open(os.path.join(util.GOLDEN, "front_corpus.json")))
+    n = 0
+    for c in corpus:
+        if c["kind"] != "ok":
+            continue
+        m = cb.Model(c["text"])
+        r = cb.GpuProblem(m).solve(time_limit_ms=5000)
+        assert r.timed_out == 0
+        assert bool(r.has_solution) == (not c["no_solution"]), c["text"]
+        if m.objective == cb.OBJ_ALL:
+            assert r.solutions == c["solutions"], c["text"]
+        elif m.objective in (cb.OBJ_MIN, cb.OBJ_MAX) and r.has_solution:
+            assert r.best == c["best"], c["text"]
+        n += 1
+    assert n >= 300
