@@ -657,6 +657,11 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   for (;;) {
     if (!local_done) {
       CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
+      if (getenv("CSOLVE_DEBUG_SYNC")) {
+        const cudaError_t es = cudaStreamSynchronize(st);
+        fprintf(stderr, "[csolve] depth-first kernel: %s (solbuf %p cap %d, pool %p cap %d, stacks %p)\n", cudaGetErrorString(es), (void *)p->solbuf,
+                p->sol_cap, (void *)a.pool, a.pool_cap, (void *)a.stacks);
+      }
       CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
       CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));

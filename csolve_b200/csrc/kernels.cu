@@ -18,12 +18,20 @@
 // mask with atomicOr. No tensor cores: the work is irregular int32 compare/min/max.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "kernels.cuh"
 #include "contract.cuh"
 
 namespace csolve_dev {
 
 #define FULL 0xffffffffu
+
+// development: CHK(cond, tag, value) reports a violated bound once per lane and stops the kernel (-DCSOLVE_BOUNDS)
+#ifdef CSOLVE_BOUNDS
+#define CHK(cond, tag, v) do { if (!(cond)) { printf("[bounds] %s: %lld (block %d thread %d)\n", tag, (long long)(v), blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define CHK(cond, tag, v) do { } while (0)
+#endif
 
 // resident blocks per SM the search kernel is compiled for (bounds the registers per thread)
 // nodes between two polls of the control block (signal, time slice)
@@ -437,6 +445,7 @@ __device__ __forceinline__ void store_solution(const SearchArgs &a, const WarpSm
     for (int v = lane; v < a.m.n_vars; v += 32) dst[v] = s.d[2 * v];
     if (lane == 0) dst[a.m.n_vars] = key;
   }
+  __syncwarp();       // reconverge after the predicated stores (see k_search_lov)
 }
 
 
@@ -1104,6 +1113,9 @@ k_search_lov(const SearchArgs a) {
       const int mk = __ldcg(&g[FR_MASK]);
       const unsigned it = (unsigned)h0.y, la = (unsigned)h0.z;
       const bool left = it <= la;
+      CHK(h0.x >= 0 && h0.x < V, "lov frame_in var", h0.x);
+      CHK(h1.y >= 0 && h1.y < V, "lov frame_in level", h1.y);
+      CHK(!left || la - it < 32u, "lov frame_in rem", la - it);
       reinterpret_cast<int4 *>(sf)[0] = make_int4((left ? (int)((unsigned)h0.w + ((it + 1) >> 1)) : h0.w) - zb, left ? (int)(la - it + 1u) : 0, h0.x, h1.y);
       reinterpret_cast<int2 *>(sf)[2] = make_int2(mk, h1.w);
     }
@@ -1196,6 +1208,7 @@ k_search_lov(const SearchArgs a) {
         src = a.pool + (size_t)slot * fw;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
+      CHK(L >= 0 && L < V, "lov claimed level", L);
       frame_in(src, sst + L * sfw);
       if (!EXPAND) {
         __syncwarp();
@@ -1208,8 +1221,10 @@ k_search_lov(const SearchArgs a) {
     }
 
     if (!have) {
+      CHK(sf >= sst && sf + sfw <= sst + (EXPAND ? 1 : V) * sfw, "lov top frame", (sf - sst) / sfw);
       const int4 h0 = reinterpret_cast<const int4 *>(sf)[0];
       const int2 h1 = reinterpret_cast<const int2 *>(sf)[2];
+      CHK(h0.z >= 0 && h0.z < V && h0.w >= 0 && h0.w < V, "lov top frame var/level", h0.z * 1000 + h0.w);
       int2 dj = make_int2(vbase, vbase);       // idle lanes hold a harmless one-value domain
       if (act) dj = reinterpret_cast<const int2 *>(sf + 8)[lane];
       plo = dj.x; phi = dj.y;
@@ -1310,6 +1325,10 @@ k_search_lov(const SearchArgs a) {
             if (act) dst[lane] = lo + zb;
             if (lane == 0) dst[V] = 0;
           }
+          // Reconverge here: without it the lanes that skipped the stores ran ahead into the shuffles of the poll /
+          // donation code and paired with the wrong ones (measured on B200: garbage split points, lost nodes,
+          // illegal addresses -- only with max_solutions > 0, i.e. when this block stores anything).
+          __syncwarp();
         }
       }
     } else {
@@ -1388,6 +1407,7 @@ k_search_lov(const SearchArgs a) {
           n32 += rem; c32 += rem;
         }
         int *nf = last_value ? sf : sf + sfw;
+        CHK(nf >= sst && nf + sfw <= sst + V * sfw, "lov push frame", (nf - sst) / sfw);
         if (lane == 0) {
           if (!last_value) reinterpret_cast<int2 *>(sf)[0] = make_int2(cur, (int)rem);
           reinterpret_cast<int4 *>(nf)[0] = make_int4(nlo, (int)nrem, nv, flevel + 1);
@@ -1454,6 +1474,7 @@ k_search_lov(const SearchArgs a) {
           // this warp keeps the lower part [d_cur, d_cur + keep), the donated frame owns the rest
           const unsigned give = d_rem - keep;
           const int glo = (int)((unsigned)d_cur + keep);
+          CHK(give >= 1u && give <= 32u && keep <= 32u, "lov donate give", give);
           int *own = sst + L * sfw;
           for (;;) {
             const int slot = reserve_slot(a, lane);
@@ -1877,6 +1898,7 @@ k_search_lovk(const SearchArgs a) {
               for (int q = 0; q < K; q++) if (lane + 32 * q < V) dst[lane + 32 * q] = x.lo[q];
               if (lane == 0) dst[V] = ftag;
             }
+            __syncwarp();     // reconverge after the predicated stores (see k_search_lov)
           }
         }
       } else {

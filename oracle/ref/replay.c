@@ -148,6 +148,33 @@ int ref_replay(const int32_t *dom_in, int var, int32_t val, int32_t best,
   return failed;
 }
 
+/* The reference's own solve() (src/csolve.c:398) on the loaded model, timed without process start, parsing or
+ * printing: stdout is pointed at /dev/null for the duration (solve() prints every solution and the final stats).
+ * Returns the seconds spent inside solve(); calls / solutions receive CALLS and SOLUTIONS. The engine state is
+ * left as solve() leaves it: call ref_load() again before anything else. */
+#include <fcntl.h>
+#include <time.h>
+#include <unistd.h>
+double ref_solve_timed(uint64_t *calls, uint64_t *solutions) {
+  fflush(stdout);
+  int saved = dup(1);
+  int devnull = open("/dev/null", O_WRONLY);
+  dup2(devnull, 1);
+  close(devnull);
+  stats_init();
+  shared()->solutions = 0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  solve(standin_size, standin_env, standin_norm);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  fflush(stdout);
+  dup2(saved, 1);
+  close(saved);
+  if (calls != NULL) *calls = stat_get_calls();
+  if (solutions != NULL) *solutions = shared()->solutions;
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 /* leaf test of update_solution(): is_true(eval(root)) (src/csolve.c:226) */
 int ref_eval_root(const int32_t *dom_in) {
   size_t n = standin_size;
