@@ -32,10 +32,14 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queens", type=int, default=16, help="board size of the workload (BASELINE config 3: 14..16)")
+    ap.add_argument("--workload", default="queens", choices=["queens", "wcet", "sat200"],
+                    help="queens: N-queens ALL (BASELINE headline, config 3); wcet: examples/wcet.txt MAX (config 4, "
+                         "incumbent shared between the GPUs); sat200: random 3-SAT n=200 seed 1 ANY (config 5, UNSAT)")
+    ap.add_argument("--no-comm", action="store_true",
+                    help="N > 1: static path-hash partition of a replicated frontier instead of the shared frontier of a csolve_gpu_comm")
     ap.add_argument("--order", default="none")
     ap.add_argument("--cpu-queens", type=int, default=0,
-                    help="board size of the bounded CPU sample (default: 13-queens, ~10 s, for cpu_baseline; 12-queens, "
-                         "~2 s per step, for the steps of --impl reference)")
+                    help="board size of the bounded CPU sample of the queens workload (default: 13-queens, ~10 s per run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -43,10 +47,33 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------------
 # CPU side: the reference's own implementation (oracle/_ref, built from /root/reference where it was
 # available) or, failing that, the oracle port. Only used as the reported baseline / reference arm.
-def cpu_reference_run(n_queens):
-    """one single-threaded all-solutions run; returns (nodes, seconds, kind, solutions)"""
+def host_info():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"host_cores": os.cpu_count(), "cpu_model": model}
+
+
+def workload_text(args, n_queens=None):
     from csolve_b200 import instances as I
-    text = I.queens(n_queens)
+    if args.workload == "wcet":
+        return I.wcet()
+    if args.workload == "sat200":
+        return I.random_3sat(200, seed=1)
+    return I.queens(n_queens or args.queens)
+
+
+def cpu_reference_run(n_queens, text=None, flags=()):
+    """one single-threaded run of the reference CLI; returns (nodes, seconds, kind, solutions)"""
+    from csolve_b200 import instances as I
+    if text is None:
+        text = I.queens(n_queens)
     ref_cli = os.path.join(ROOT, "oracle", "_ref", "csolve_ref")
     if os.path.exists(ref_cli):
         import re
@@ -56,7 +83,7 @@ def cpu_reference_run(n_queens):
         t0 = time.perf_counter()
         # the reference's defaults (-c true -f true -w true -o none -r 100 -j 1), stats printing off,
         # solutions discarded by the pipe reader (it prints every solution)
-        out = subprocess.run([ref_cli, "-s", "0", f.name], capture_output=True, text=True).stdout
+        out = subprocess.run([ref_cli, "-s", "0", *flags, f.name], capture_output=True, text=True).stdout
         dt = time.perf_counter() - t0
         os.unlink(f.name)
         m = re.search(r"CALLS: (\d+).*SOLUTIONS: (\d+)", out)
@@ -72,32 +99,56 @@ def cpu_reference_run(n_queens):
     return int(r.calls), dt, "port", int(r.solutions)
 
 
+# reference CALLS of 16-queens ALL (measured once in the build container: 6 629.7 s there)
+REF_CALLS_QUEENS16 = 1048203447
+
+
+def reference_sample(args):
+    """(text, flags, description) of the bounded CPU sample of the workload: the reference needs ~1 h for 16-queens,
+    83 s for wcet and 37 s for 3-SAT n=200 seed 1, so a step of the reference arm is a smaller board / a time-boxed run
+    of the same instance (the CLI's own -t; CALLS are printed when it stops)."""
+    if args.workload == "wcet":
+        return workload_text(args), ("-t", "10"), "wcet MAX, first 10 s of the search (-t 10), single thread, default flags"
+    if args.workload == "sat200":
+        return workload_text(args), ("-t", "10", "-c", "false"), "3-SAT n=200 seed 1 ANY, first 10 s (-t 10), single thread, -c false"
+    n = args.cpu_queens or 13
+    return workload_text(args, n), (), "%d-queens all-solutions, single thread, default flags" % n
+
+
+def workload_name(args):
+    return {"queens": "queens%d-all" % args.queens, "wcet": "wcet-max", "sat200": "sat200-seed1-any"}[args.workload]
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_queens or 12
-    for _ in range(max(args.warmup, 0) and 1):   # one untimed run is enough to page the binary in
-        cpu_reference_run(min(n, 10))
+    text, flags, desc = reference_sample(args)
+    if args.warmup > 0:                      # one untimed run is enough to page the binary in
+        cpu_reference_run(8)
     nodes = 0
     secs = 0.0
     kind = "reference"
     for _ in range(args.steps):
-        c, dt, kind, sols = cpu_reference_run(n)
+        c, dt, kind, sols = cpu_reference_run(0, text, flags)
         nodes += c
         secs += dt
     value = nodes / secs
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "queens%d-all" % args.queens, "sample": "queens%d-all" % n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
-                         "sample": "%d-queens all-solutions per step (%d nodes), single thread, default flags; "
-                                   "the reference's -j fork mode does not scale (BASELINE.md)" % (n, nodes // max(args.steps, 1))},
+        "config": {"workload": workload_name(args), "sample": desc},
+        "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                              "sample": "%s; %d nodes per step; the reference's -j fork mode does not scale (BASELINE.md)"
+                                        % (desc, nodes // max(args.steps, 1))}, **host_info()),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload == "queens" and args.queens == 16:
+        # like-for-like time to solution: the reference's CALLS for 16-queens at the node rate this host just showed
+        # (its rate FALLS with the board size -- BASELINE.md: 201 k/s at N=12, 158 k/s at N=16 -- so this flatters the CPU)
+        line["config"]["time_to_solution_s_calibrated"] = REF_CALLS_QUEENS16 / value
     print(json.dumps(line), flush=True)
 
 
@@ -176,7 +227,6 @@ def run_ours(args):
     import torch.distributed as dist
     import csolve_b200 as cb
     from csolve_b200 import distributed as D
-    from csolve_b200 import instances as I
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,19 +240,46 @@ def run_ours(args):
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    comm = None
+    mode = "single GPU"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        mode = "tree-partition x%d (path hash of a replicated frontier)" % world
+        if not args.no_comm:
+            # the ranks' segments are mapped into each other once (CUDA IPC handles through one all-gather); a box
+            # that cannot do that falls back to the static partition -- on EVERY rank, so they decide together
+            ok = 1
+            try:
+                comm = D.make_comm(local)
+            except Exception as e:                      # noqa: BLE001
+                print("[bench rank %d] comm unavailable (%s): static partition" % (rank, e), file=sys.stderr, flush=True)
+                ok = 0
+            t = torch.tensor([ok], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                comm = None
+            else:
+                mode = "shared frontier x%d (claims and incumbents over NVLink peer memory)" % world
 
-    text = I.queens(args.queens)
+    text = workload_text(args)
     order = cb.host.ORDER_NAMES[args.order]
+    objective = {"queens": cb.OBJ_ALL, "wcet": cb.OBJ_MAX, "sat200": cb.OBJ_ANY}[args.workload]
+    solve_kw = dict(order=order)
+    if args.workload == "sat200":
+        solve_kw["prefer_failing"] = True
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def one_step():
-        """the call a user makes: parse + root phase, upload, search, read the result back"""
+        """the call a user makes: parse + root phase, upload, search, read the result back -- and, with several
+        ranks, the reduction that puts the whole job's result on every rank; the clock stops after it"""
         t0 = time.perf_counter()
         model = cb.Model(text)                          # host front end
         prob = cb.GpuProblem(model, device=local)       # H2D: compiled model
-        res = prob.solve(order=order, part_rank=rank, part_count=world)   # D2H: counters, incumbent, status
+        if comm is not None:
+            res = prob.solve(comm=comm, **solve_kw)
+        else:
+            res = prob.solve(part_rank=rank, part_count=world, **solve_kw)   # D2H: counters, incumbent, status
+        red = D.reduce_results(res, objective, device=dev)
         wall = time.perf_counter() - t0
         f = model.flat
         # model arrays + root frame + the 640-byte control block once per expansion level and once for the search
@@ -211,7 +288,7 @@ def run_ours(args):
                + (8 + f.n_vars * 2 + 4) * 4 + 640 * (levels + 1))
         d2h = 640 * (levels + 2) + 96                   # control block per expansion level / slice / at the end + counters
         prob.close(); model.close()
-        return res, wall, h2d, d2h
+        return res, red, wall, h2d, d2h
 
     def barrier():
         if world > 1:
@@ -229,16 +306,16 @@ def run_ours(args):
     dev_ms = wall_s = search_ms = 0.0
     my_nodes = 0
     h2d = d2h = 0
-    objective = cb.OBJ_ALL
+    best = None
     for _ in range(args.steps):
         flush.fill_(int(time.time()) & 1)               # flush L2 between timed iterations
         barrier()
-        res, wall, h2d, d2h = one_step()
-        red = D.reduce_results(res, objective, device=dev)
+        res, red, wall, h2d, d2h = one_step()
         w = torch.tensor([wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
         tot_nodes += red["nodes"]; tot_sols = red["solutions"]; tot_launch += red["kernel_launches"]
+        best = red["best"] if red["has_solution"] else None
         dev_ms += red["kernel_ms"] + red["expand_ms"]   # max over ranks, device clock (CUDA events on the library's stream)
         search_ms += res.kernel_ms
         print("[bench rank %d] nodes=%d search_ms=%.2f expand_ms=%.2f launches=%d wall_ms=%.2f" % (
@@ -248,47 +325,62 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    expected = {4: 2, 5: 10, 6: 4, 7: 40, 8: 92, 9: 352, 10: 724, 11: 2680, 12: 14200, 13: 73712, 14: 365596,
-                15: 2279184, 16: 14772512, 17: 95815104}.get(args.queens)
-    if expected is not None and tot_sols != expected:
-        raise SystemExit("bench.py: wrong solution count %d (expected %d)" % (tot_sols, expected))
+    # results identical to the reference's: solution count (OEIS A000170), optimum, SAT status
+    if args.workload == "queens":
+        expected = {4: 2, 5: 10, 6: 4, 7: 40, 8: 92, 9: 352, 10: 724, 11: 2680, 12: 14200, 13: 73712, 14: 365596,
+                    15: 2279184, 16: 14772512, 17: 95815104}.get(args.queens)
+        if expected is not None and tot_sols != expected:
+            raise SystemExit("bench.py: wrong solution count %d (expected %d)" % (tot_sols, expected))
+    elif args.workload == "wcet" and best != 1560:
+        raise SystemExit("bench.py: wrong optimum %r (expected 1560)" % (best,))
+    elif args.workload == "sat200" and tot_sols != 0:
+        raise SystemExit("bench.py: 3-SAT n=200 seed 1 is unsatisfiable, got a solution")
 
     if rank == 0:
-        V = args.queens
+        V = {"queens": args.queens, "wcet": 12, "sat200": 200}[args.workload]
         bytes_per_node = 2 * (8 * V + 16)                       # parent domains + header in, child out
         peak, peak_src = measured_peak_gbs()
         achieved = (my_nodes * bytes_per_node) / (search_ms / 1000.0) / 1e9 if search_ms > 0 else 0.0
-        kernel = "k_search_lov<false,true>" if args.queens <= 32 else "k_search<false>"
+        kernel = {"queens": "k_search_lov<false,true>" if args.queens <= 32 else "k_search<false>",
+                  "wcet": "k_search<false,false,LIN=true>", "sat200": "k_search<false,false,LIN=false>"}[args.workload]
         line = {
             "metric": METRIC, "value": tot_nodes / (dev_ms / 1000.0), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "queens%d-all" % V, "order": args.order, "solutions": tot_sols,
-                       "nodes_per_step": tot_nodes // args.steps, "parallelism": "tree-partition x%d" % world,
+            "config": {"workload": workload_name(args), "order": args.order, "solutions": tot_sols, "best": best,
+                       "nodes_per_step": tot_nodes // args.steps, "parallelism": mode,
                        "l2": "flushed between iterations (256 MiB write)",
                        "time_to_solution_s": dev_ms / 1000.0 / args.steps},
             "clocks": clocks,
             "e2e": {"value": tot_nodes / wall_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "time_to_solution_s": wall_s / args.steps,
-                    "path": "Model(text) -> GpuProblem -> solve() through libcsolve_b200.so, host buffers"},
+                    "path": "Model(text) -> GpuProblem -> solve() through libcsolve_b200.so, host buffers"
+                            + ("; the clock stops after the all-reduce of the ranks' results" if world > 1 else "")},
             "gpu_launches": tot_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(kernel, "queens%d-all" % V), "kernel": kernel,
+                         "frac": achieved / peak, "traffic": measured_traffic(kernel, workload_name(args)), "kernel": kernel,
                          "bytes_per_node": bytes_per_node, "peak_source": peak_src,
                          "note": "rank 0; algorithmic bytes = nodes x 2 x (8V+16); the DFS stacks live in shared memory during a slice, so real DRAM traffic is far below this nominal figure (DESIGN.md)"},
         }
         if not args.no_cpu_baseline and world == 1:
-            nq = args.cpu_queens or 13
-            c, dt, kind, sols = cpu_reference_run(nq)
-            line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": 1, "kind": kind,
-                                    "sample": "%d-queens all-solutions, %d nodes in %.2f s, single thread, default flags"
-                                              % (nq, c, dt)}
+            rtext, rflags, rdesc = reference_sample(args)
+            c, dt, kind, sols = cpu_reference_run(0, rtext, rflags)
+            line["cpu_baseline"] = dict({"value": c / dt, "unit": UNIT, "cores": 1, "kind": kind,
+                                         "sample": "%s: %d nodes in %.2f s" % (rdesc, c, dt)}, **host_info())
+            if args.workload == "queens" and args.queens == 16:
+                # like-for-like: the reference's 16-queens CALLS at the node rate this host just showed (which flatters
+                # the CPU: its rate falls with the board size) against the measured end-to-end time
+                cal = REF_CALLS_QUEENS16 / (c / dt)
+                line["cpu_baseline"]["time_to_solution_s_calibrated"] = cal
+                line["e2e"]["time_to_solution_speedup_calibrated"] = cal / (wall_s / args.steps)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
     sys.stdout.flush()
     os.dup2(real_stdout, 1)

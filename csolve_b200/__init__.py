@@ -8,7 +8,10 @@ library with ctypes and exposes the same entry points.
 from .host import (  # noqa: F401
     CsolveError,
     FlatModel,
+    Comm,
+    GpuGroup,
     GpuProblem,
+    device_count,
     Model,
     SolveResult,
     library,

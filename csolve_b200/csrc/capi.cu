@@ -257,6 +257,27 @@ struct csolve_gpu_problem {
   }
 };
 
+// ---- ranks that search one tree together (include/csolve_b200.h: csolve_gpu_comm) -----------------------------------
+// Segment of one rank (plain cudaMalloc, so that it can be exported with CUDA IPC):
+//   [0, 1024)      the rank's SearchCtl (rank 0's init_next hands out the shared root frontier)
+//   [1024, 1152)   CommBlock: written by the peers with system-scope atomics / small copies
+//   [4096, ...)    rank 0: the expanded root frontier of the current epoch
+static const size_t SEG_CTL = 0, SEG_COMM = 1024, SEG_FRONT = 4096;
+struct csolve_gpu_comm {
+  DeviceCtx *ctx = nullptr;
+  int rank = 0, world = 1;
+  unsigned char *seg = nullptr;
+  size_t front_bytes = 0;
+  unsigned char *peer_seg[COMM_MAX_RANKS] = {};
+  bool opened[COMM_MAX_RANKS] = {};     // mapped with cudaIpcOpenMemHandle (closed in destroy)
+  bool connected = false;
+  int epoch = 0;                        // solve counter: every rank calls csolve_gpu_solve_comm the same number of times
+  SearchCtl *ctl() const { return reinterpret_cast<SearchCtl *>(seg + SEG_CTL); }
+  CommBlock *block(int r) const { return reinterpret_cast<CommBlock *>(peer_seg[r] + SEG_COMM); }
+  SearchCtl *ctl_of(int r) const { return reinterpret_cast<SearchCtl *>(peer_seg[r] + SEG_CTL); }
+  int32_t *front_of(int r) const { return reinterpret_cast<int32_t *>(peer_seg[r] + SEG_FRONT); }
+};
+
 extern "C" const char *csolve_last_error(void) { return csolve_front::last_error(); }
 extern "C" int csolve_abi_version(void) { return CSOLVE_B200_ABI_VERSION; }
 
@@ -467,14 +488,39 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
 
 namespace {
 // n_roots == 0: the model's own root. n_roots > 0: batched roots over the shared network (ALL models).
-int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve_gpu_result *res, int n_roots,
+// host-side waits on a CommBlock in device memory (this rank's or, through the peer mapping, rank 0's): polled with
+// small synchronous copies; `ok(block)` decides. Returns false after `limit_s` seconds.
+template <class F>
+bool comm_wait(const CommBlock *dev_block, F ok, double limit_s, CommBlock *out) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spin = 0;; spin++) {
+    CommBlock b;
+    if (cudaMemcpy(&b, dev_block, sizeof(b), cudaMemcpyDefault) != cudaSuccess) return false;
+    if (ok(b)) {
+      // the fields of a block are written by separate stores: read once more so that everything that was written
+      // before the field `ok` looked at is seen as well
+      if (cudaMemcpy(&b, dev_block, sizeof(b), cudaMemcpyDefault) != cudaSuccess) return false;
+      if (out) *out = b;
+      return true;
+    }
+    if ((spin & 63u) == 63u && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) return false;
+    if (spin > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+}
+const double COMM_WAIT_S = 300.0;
+
+int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_options *opt_in, csolve_gpu_result *res, int n_roots,
                const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed) {
   if (p == nullptr || res == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
   ENTER(p);
+  if (c != nullptr && (c->ctx != p->ctx || !c->connected)) return fail(CSOLVE_ERR_INVALID, "the comm is not connected or lives on another device than the problem");
+  if (c != nullptr && n_roots > 0) return fail(CSOLVE_ERR_UNSUPPORTED, "batched roots are sharded by the caller (one slice of the roots per rank), not through a comm");
+  if (c != nullptr && c->world == 1) c = nullptr;
   csolve_solve_options opt;
   memset(&opt, 0, sizeof(opt));
   if (opt_in) opt = *opt_in;
   if (opt.part_count <= 0) opt.part_count = 1;
+  if (c != nullptr) { opt.part_rank = 0; opt.part_count = 1; }       // the comm decides (shared frontier, or rank / world as a fallback)
   if (opt.part_rank < 0 || opt.part_rank >= opt.part_count) return fail(CSOLVE_ERR_INVALID, "part_rank out of range");
   if (opt.order < CSOLVE_ORDER_NONE || opt.order > CSOLVE_ORDER_LARGEST_VALUE) return fail(CSOLVE_ERR_INVALID, "invalid ordering strategy");
   memset(res, 0, sizeof(*res));
@@ -504,6 +550,23 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
 
   DevModel m = p->dev;
   if (batch) m.lov = 0;            // batched roots run on the general kernels
+  SearchCtl *const dctl = c != nullptr ? c->ctl() : p->ctl;      // with a comm the control block lives in the rank's segment
+  // ---- comm: epoch bookkeeping. Whatever way this call ends, the other ranks must not wait for ever: rank 0
+  //      publishes "failed" if it never published a frontier, every other rank reports that it has left the epoch.
+  const int epoch = c != nullptr ? ++c->epoch : 0;
+  bool front_published = false;
+  ScopeExit comm_guard([&]() {
+    if (c == nullptr) return;
+    if (c->rank == 0) {
+      if (!front_published) {
+        const int32_t hdr[3] = {epoch, -2, 0};
+        cudaMemcpy(&c->block(0)->front_n, &hdr[1], 2 * sizeof(int32_t), cudaMemcpyDefault);
+        cudaMemcpy(&c->block(0)->front_epoch, &hdr[0], sizeof(int32_t), cudaMemcpyDefault);
+      }
+    } else {
+      cudaMemcpy(&c->block(0)->done_epoch[c->rank], &epoch, sizeof(int32_t), cudaMemcpyDefault);
+    }
+  });
   const CompiledModel &cm = p->cm;
   const int V = m.n_vars, fw = m.frame_words;
   cudaStream_t st = p->stream;
@@ -551,11 +614,11 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     CUDA_TRY(cudaStreamSynchronize(st));
     ctl.item_count = n_ok;
   }
-  CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
 
   SearchArgs a;
   memset(&a, 0, sizeof(a));
-  a.m = m; a.ctl = p->ctl; a.stacks = p->stacks; a.wstate = p->wstate; a.wcount = p->wcount;
+  a.m = m; a.ctl = dctl; a.stacks = p->stacks; a.wstate = p->wstate; a.wcount = p->wcount;
   a.solbuf = p->solbuf; a.max_solutions = p->sol_cap; a.n_warps = p->n_warps; a.order = opt.order;
   a.out_cap = p->pool_cap; a.expand_branch_max = 64;
   a.inst_solutions = d_rsol;
@@ -599,36 +662,91 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   // Breadth-first levels pay off while the frontier multiplies; once there is about one frame per two warps
   // and a level no longer doubles it (unit-propagation-heavy models, batched roots), or after 24 levels,
   // the depth-first phase with rebalancing takes over.
-  for (int lvl = 0; lvl < V && lvl < 24 && n_items > 0 && n_items < target; ++lvl) {
-    const int before = n_items;
-    // would another level overflow the pool? domains only shrink, so a frame has at most as many
-    // children as the largest root domain (and never more than expand_branch_max)
-    if ((long long)n_items * max_branch > p->pool_cap - ring_min_frames(p->n_warps)) break;
-    a.items = pin; a.items_out = pout; a.frozen_best = ctl.best;
-    ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.passed = 0;
-    CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
-    const int grid = std::min(p->grid, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    CUDA_TRY(launch_search(a, grid, true, st)); launches++;
-    CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (ctl.out_dropped > 0) return fail(CSOLVE_ERR_CAPACITY, "frontier pool overflow during expansion");
-    n_items = ctl.out_count;
-    if (getenv("CSOLVE_DEBUG")) fprintf(stderr, "[csolve] expand level %d -> %d frames (target %d, pool %d, branch %lld)\n", lvl, n_items, target, p->pool_cap, max_branch);
-    std::swap(pin, pout);
-    if (ctl.signal == SIG_STOP) { stopped = true; break; }
-    // frames with huge domains are passed through unsplit; when nothing else is left the
-    // breadth-first phase cannot make progress and the depth-first phase (which bisects) takes over
-    if (ctl.passed == n_items) break;
-    if (n_items >= p->n_warps / 2 && n_items < 2 * (long long)before) break;
+  auto expand_root = [&]() -> int {
+    for (int lvl = 0; lvl < V && lvl < 24 && n_items > 0 && n_items < target; ++lvl) {
+      const int before = n_items;
+      // would another level overflow the pool? domains only shrink, so a frame has at most as many
+      // children as the largest root domain (and never more than expand_branch_max)
+      if ((long long)n_items * max_branch > p->pool_cap - ring_min_frames(p->n_warps)) break;
+      a.items = pin; a.items_out = pout; a.frozen_best = ctl.best;
+      ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.passed = 0;
+      CUDA_TRY(cudaMemcpyAsync(dctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+      const int grid = std::min(p->grid, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+      CUDA_TRY(launch_search(a, grid, true, st)); launches++;
+      CUDA_TRY(cudaMemcpyAsync(&ctl, dctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (ctl.out_dropped > 0) return fail(CSOLVE_ERR_CAPACITY, "frontier pool overflow during expansion");
+      n_items = ctl.out_count;
+      if (getenv("CSOLVE_DEBUG")) fprintf(stderr, "[csolve] expand level %d -> %d frames (target %d, pool %d, branch %lld)\n", lvl, n_items, target, p->pool_cap, max_branch);
+      std::swap(pin, pout);
+      if (ctl.signal == SIG_STOP) { stopped = true; break; }
+      // frames with huge domains are passed through unsplit; when nothing else is left the
+      // breadth-first phase cannot make progress and the depth-first phase (which bisects) takes over
+      if (ctl.passed == n_items) break;
+      if (n_items >= p->n_warps / 2 && n_items < 2 * (long long)before) break;
+    }
+    return CSOLVE_OK;
+  };
+  // Ranks of a comm: rank 0 alone expands the root; the others take the frontier from rank 0's segment (below).
+  // part_rank / part_count: 0 / 1 with a shared frontier; the comm's rank / world when the frontier did not fit the
+  // segment and every rank expands for itself (path-hash partition, as without a comm).
+  int part_rank = opt.part_rank, part_count = opt.part_count;
+  const int32_t *front_pool = nullptr;
+  SearchCtl *front_ctl = dctl;
+  if (c == nullptr || c->rank == 0) {
+    rc = expand_root();
+    if (rc != CSOLVE_OK) return rc;
   }
   if (n_items < 0) n_items = -n_items;
+  if (c != nullptr) {
+    if (c->rank == 0) {
+      // the previous epoch's frontier is overwritten: every peer must have left that search
+      if (!comm_wait(c->block(0), [&](const CommBlock &b) {
+            for (int r = 1; r < c->world; r++) if (b.done_epoch[r] < epoch - 1) return false;
+            return true; }, COMM_WAIT_S, nullptr))
+        return fail(CSOLVE_ERR_CUDA, "comm: a peer rank did not finish the previous search");
+      const size_t bytes = (size_t)n_items * fw * sizeof(int32_t);
+      int32_t hdr[3] = {epoch, stopped ? 0 : n_items, fw};      // ANY solved by the expansion itself: nothing to share
+      if (bytes <= c->front_bytes) {
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(c->front_of(0), pin, bytes, cudaMemcpyDeviceToDevice, st));
+        front_pool = c->front_of(0);
+      } else {
+        hdr[1] = -1;                              // does not fit: every rank expands for itself
+        part_rank = 0; part_count = c->world;
+      }
+      // the frontier's claim counter must be zero before anybody sees the frontier
+      ctl.init_next = 0;
+      CUDA_TRY(cudaMemcpyAsync(&dctl->init_next, &ctl.init_next, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(&c->block(0)->front_n, &hdr[1], 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      CUDA_TRY(cudaMemcpyAsync(&c->block(0)->front_epoch, &hdr[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      front_published = true;
+    } else {
+      CommBlock b;
+      if (!comm_wait(c->block(0), [&](const CommBlock &x) { return x.front_epoch >= epoch; }, COMM_WAIT_S, &b))
+        return fail(CSOLVE_ERR_CUDA, "comm: rank 0 did not publish the root frontier");
+      if (b.front_epoch != epoch || b.front_n == -2) return fail(CSOLVE_ERR_CUDA, "comm: rank 0 failed or the ranks are out of step");
+      if (b.front_n >= 0) {
+        if (b.front_fw != fw) return fail(CSOLVE_ERR_INVALID, "comm: the ranks loaded different models");
+        n_items = b.front_n;
+        front_pool = c->front_of(0);
+        front_ctl = c->ctl_of(0);
+      } else {
+        part_rank = c->rank; part_count = c->world;
+        rc = expand_root();
+        if (rc != CSOLVE_OK) return rc;
+        if (n_items < 0) n_items = -n_items;
+      }
+    }
+  }
   CUDA_TRY(cudaEventRecord(ev1, st));
 
   // ---- partition: every rank holds the whole frontier; the search kernel skips the frames whose path
   //      hash maps to another rank (no copy, no compaction)
-  a.part_rank = opt.part_rank; a.part_count = opt.part_count;
+  a.part_rank = part_rank; a.part_count = part_count;
 
-  if (opt.part_count > 1 && opt.part_rank != 0) {
+  if (part_count > 1 && part_rank != 0) {
     // the expansion was replicated on every rank (also when it exhausted the whole tree):
     // only rank 0 reports its counters and the leaves found in it
     CUDA_TRY(cudaMemsetAsync(p->wcount, 0, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long), st));
@@ -639,13 +757,26 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   a.items = pin; a.items_out = nullptr;
   // shared pool ring of the depth-first phase: the expanded frontier occupies the first n_items slots
   a.pool = pin; a.pool_cap = p->pool_cap; a.ready = p->ready; a.n_initial = n_items;
+  a.front_pool = front_pool != nullptr ? front_pool : pin;
+  a.front_ctl = front_ctl;
+  a.total_warps = p->n_warps * (front_pool != nullptr ? c->world : 1);
+  if (c != nullptr) {
+    a.comm = c->block(c->rank); a.epoch = epoch;
+    for (int r = 0; r < c->world; r++) if (r != c->rank) a.peer_comm[a.n_peers++] = c->block(r);
+  }
   CUDA_TRY(cudaMemsetAsync(p->ready, 0, (size_t)p->pool_cap * sizeof(int32_t), st));
   if (p->pool_cap - n_items < ring_min_frames(p->n_warps)) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
   a.gprio = d_gprio;     // the breadth-first expansion above stays deterministic (identical on every rank)
   if (learn) a.ng = p->ng;
   ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0;
   ctl.signal = stopped ? SIG_STOP : SIG_RUN;
-  CUDA_TRY(cudaMemcpyAsync(p->ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+  if (c != nullptr && c->rank == 0 && front_pool != nullptr) {
+    // the peers may already be claiming from init_next (line 1 of the block): upload everything but that line
+    CUDA_TRY(cudaMemcpyAsync(dctl, &ctl, offsetof(SearchCtl, init_next), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(&dctl->item_next, &ctl.item_next, sizeof(ctl) - offsetof(SearchCtl, item_next), cudaMemcpyHostToDevice, st));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(dctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+  }
   int idle_now = p->n_warps;          // every warp starts without a stack
   int busy = 0;
   bool timed_out = false;
@@ -663,7 +794,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
                 p->sol_cap, (void *)a.pool, a.pool_cap, (void *)a.stacks);
       }
       CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
-      CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(&ctl, dctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       slices++;
       busy = ctl.busy;
@@ -683,7 +814,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
     const int all_done = p->exchange(p->exchange_user, &best, &found, local_done ? 1 : 0);
     if (m.obj_var >= 0 && (is_min ? best < ctl.best : best > ctl.best)) {
       ctl.best = best;     // another rank found a better incumbent: prune with it from the next slice on
-      CUDA_TRY(cudaMemcpyAsync(&p->ctl->best, &ctl.best, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(&dctl->best, &ctl.best, sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     if (found && m.objective == CSOLVE_OBJ_ANY && !local_done) {
       local_done = true;   // found_any() on another rank (src/csolve.c:207-209)
@@ -707,7 +838,7 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
   CUDA_TRY(launch_reduce_counters(p->wcount, p->n_warps, p->totals, st)); launches++;
   unsigned long long tot[CNT_WIDTH];
   CUDA_TRY(cudaMemcpyAsync(tot, p->totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(&ctl, p->ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&ctl, dctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (getenv("CSOLVE_DEBUG")) {
     // load-balance diagnostics of the depth-first phase
@@ -801,7 +932,206 @@ int solve_impl(csolve_gpu_problem *p, const csolve_solve_options *opt_in, csolve
 }  // namespace
 
 extern "C" int csolve_gpu_solve(csolve_gpu_problem *p, const csolve_solve_options *opt, csolve_gpu_result *res) {
-  return solve_impl(p, opt, res, 0, nullptr, nullptr, nullptr);
+  return solve_impl(p, nullptr, opt, res, 0, nullptr, nullptr, nullptr);
+}
+
+// ---- comm ------------------------------------------------------------------------------------------------------------
+extern "C" int csolve_gpu_comm_create(int32_t device, int32_t rank, int32_t world, size_t frontier_bytes, csolve_gpu_comm **out) {
+  if (out == nullptr || world < 1 || world > COMM_MAX_RANKS || rank < 0 || rank >= world) return fail(CSOLVE_ERR_INVALID, "comm: bad rank / world (at most 8 ranks)");
+  *out = nullptr;
+  DeviceCtx *C = nullptr;
+  const int rc = device_ctx(device, &C);
+  if (rc != CSOLVE_OK) return rc;
+  std::unique_ptr<csolve_gpu_comm> c(new csolve_gpu_comm);
+  c->ctx = C; c->rank = rank; c->world = world;
+  c->front_bytes = rank == 0 ? (frontier_bytes ? frontier_bytes : (size_t)256 << 20) : 0;
+  const size_t bytes = SEG_FRONT + c->front_bytes;
+  CUDA_TRY(cudaMalloc((void **)&c->seg, bytes));          // not from the block cache: the allocation is exported whole
+  CUDA_TRY(cudaMemset(c->seg, 0, SEG_FRONT));
+  const unsigned long long none = ~0ull;
+  CUDA_TRY(cudaMemcpy(&reinterpret_cast<CommBlock *>(c->seg + SEG_COMM)->rmin64, &none, sizeof(none), cudaMemcpyHostToDevice));
+  c->peer_seg[rank] = c->seg;
+  c->connected = world == 1;
+  *out = c.release();
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_comm_handle(csolve_gpu_comm *c, void *handle) {
+  if (c == nullptr || handle == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == CSOLVE_COMM_HANDLE_BYTES, "handle size");
+  CUDA_TRY(cudaSetDevice(c->ctx->device));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c->seg));
+  memcpy(handle, &h, sizeof(h));
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_comm_connect(csolve_gpu_comm *c, const void *handles) {
+  if (c == nullptr || handles == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(c->ctx->device));
+  for (int r = 0; r < c->world; r++) {
+    if (r == c->rank || c->peer_seg[r] != nullptr) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const unsigned char *)handles + (size_t)r * CSOLVE_COMM_HANDLE_BYTES, sizeof(h));
+    void *ptr = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_seg[r] = (unsigned char *)ptr;
+    c->opened[r] = true;
+  }
+  c->connected = true;
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_comm_connect_local(csolve_gpu_comm **comms, int32_t world) {
+  if (comms == nullptr || world < 1 || world > COMM_MAX_RANKS) return fail(CSOLVE_ERR_INVALID, "bad arguments");
+  for (int i = 0; i < world; i++) {
+    if (comms[i] == nullptr || comms[i]->rank != i || comms[i]->world != world) return fail(CSOLVE_ERR_INVALID, "comms must be given in rank order");
+  }
+  for (int i = 0; i < world; i++) {
+    CUDA_TRY(cudaSetDevice(comms[i]->ctx->device));
+    for (int j = 0; j < world; j++) {
+      if (i == j) continue;
+      const int di = comms[i]->ctx->device, dj = comms[j]->ctx->device;
+      if (di != dj) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, di, dj));
+        if (!can) return fail(CSOLVE_ERR_UNSUPPORTED, "no peer access between devices " + std::to_string(di) + " and " + std::to_string(dj));
+        const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else CUDA_TRY(e);
+      }
+      comms[i]->peer_seg[j] = comms[j]->seg;
+    }
+    comms[i]->connected = true;
+  }
+  return CSOLVE_OK;
+}
+
+extern "C" void csolve_gpu_comm_destroy(csolve_gpu_comm *c) {
+  if (c == nullptr) return;
+  cudaSetDevice(c->ctx->device);
+  for (int r = 0; r < c->world; r++) if (c->opened[r]) cudaIpcCloseMemHandle(c->peer_seg[r]);
+  cudaFree(c->seg);
+  delete c;
+}
+
+extern "C" int csolve_gpu_solve_comm(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_options *opt, csolve_gpu_result *res) {
+  if (c == nullptr) return fail(CSOLVE_ERR_INVALID, "null comm");
+  return solve_impl(p, c, opt, res, 0, nullptr, nullptr, nullptr);
+}
+
+// ---- group: all GPUs of this process on one tree, one host thread per device ---------------------------------------
+struct csolve_gpu_group {
+  std::vector<int> devices;
+  std::vector<csolve_gpu_comm *> comms;
+  std::vector<csolve_gpu_problem *> probs;
+  int32_t n_vars = 0, objective = 0, obj_var = -1;
+  std::vector<int32_t> sols;          // merged stored assignments: (n_vars values, key) each
+  int32_t n_stored = 0;
+};
+
+extern "C" int csolve_gpu_device_count(int32_t *n) {
+  if (n == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  int k = 0;
+  const cudaError_t e = cudaGetDeviceCount(&k);
+  if (e != cudaSuccess || k == 0) { *n = 0; return fail(CSOLVE_ERR_NO_DEVICE, "no CUDA device (the search path has no CPU fallback)"); }
+  *n = k;
+  return CSOLVE_OK;
+}
+
+extern "C" void csolve_gpu_group_destroy(csolve_gpu_group *g) {
+  if (g == nullptr) return;
+  for (auto *p : g->probs) delete p;
+  for (auto *c : g->comms) csolve_gpu_comm_destroy(c);
+  delete g;
+}
+
+extern "C" int csolve_gpu_group_create(int32_t n_devices, const int32_t *devices, size_t frontier_bytes, csolve_gpu_group **out) {
+  if (out == nullptr || n_devices < 1 || n_devices > COMM_MAX_RANKS) return fail(CSOLVE_ERR_INVALID, "group: 1..8 devices");
+  *out = nullptr;
+  std::unique_ptr<csolve_gpu_group, void (*)(csolve_gpu_group *)> g(new csolve_gpu_group, csolve_gpu_group_destroy);
+  for (int i = 0; i < n_devices; i++) g->devices.push_back(devices ? devices[i] : i);
+  for (int i = 0; i < n_devices; i++) {
+    csolve_gpu_comm *c = nullptr;
+    const int rc = csolve_gpu_comm_create(g->devices[i], i, n_devices, frontier_bytes, &c);
+    if (rc != CSOLVE_OK) return rc;
+    g->comms.push_back(c);
+  }
+  const int rc = csolve_gpu_comm_connect_local(g->comms.data(), n_devices);
+  if (rc != CSOLVE_OK) return rc;
+  *out = g.release();
+  return CSOLVE_OK;
+}
+
+namespace {
+// runs fn(i) on one host thread per device and returns the first error (with its text)
+template <class F>
+int group_parallel(csolve_gpu_group *g, F fn) {
+  const int n = (int)g->devices.size();
+  std::vector<int> rc(n, CSOLVE_OK);
+  std::vector<std::string> err(n);
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; i++) th.emplace_back([&, i]() { rc[i] = fn(i); if (rc[i] != CSOLVE_OK) err[i] = csolve_front::last_error(); });
+  rc[0] = fn(0);
+  if (rc[0] != CSOLVE_OK) err[0] = csolve_front::last_error();
+  for (auto &t : th) t.join();
+  for (int i = 0; i < n; i++) if (rc[i] != CSOLVE_OK) return fail(rc[i], "device " + std::to_string(g->devices[i]) + ": " + err[i]);
+  return CSOLVE_OK;
+}
+}  // namespace
+
+extern "C" int csolve_gpu_group_load(csolve_gpu_group *g, const csolve_flat_model *m) {
+  if (g == nullptr || m == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  for (auto *p : g->probs) delete p;
+  g->probs.assign(g->devices.size(), nullptr);
+  g->n_vars = m->n_vars; g->objective = m->objective; g->obj_var = m->obj_var;
+  return group_parallel(g, [&](int i) { return csolve_gpu_load_device(m, g->devices[i], &g->probs[i]); });
+}
+
+extern "C" int csolve_gpu_group_solve(csolve_gpu_group *g, const csolve_solve_options *opt, csolve_gpu_result *res,
+                                      csolve_gpu_result *per_device) {
+  if (g == nullptr || res == nullptr || g->probs.empty() || g->probs[0] == nullptr) return fail(CSOLVE_ERR_INVALID, "group: no model loaded");
+  const int n = (int)g->devices.size();
+  std::vector<csolve_gpu_result> r(n);
+  const int rc = group_parallel(g, [&](int i) { return solve_impl(g->probs[i], g->comms[i], opt, &r[i], 0, nullptr, nullptr, nullptr); });
+  if (rc != CSOLVE_OK) return rc;
+  // the reference's shared page (struct shared_t, src/csolve.h:259-266): counters add up, the incumbent is the best one
+  memset(res, 0, sizeof(*res));
+  const bool is_min = g->objective == CSOLVE_OBJ_MIN, is_opt = g->obj_var >= 0;
+  for (int i = 0; i < n; i++) {
+    res->solutions += r[i].solutions; res->nodes += r[i].nodes; res->cuts += r[i].cuts; res->props += r[i].props;
+    res->clause_visits += r[i].clause_visits; res->kernel_launches += r[i].kernel_launches;
+    res->conflicts += r[i].conflicts; res->conflicts_abandoned += r[i].conflicts_abandoned;
+    res->timed_out |= r[i].timed_out;
+    res->kernel_ms = std::max(res->kernel_ms, r[i].kernel_ms); res->expand_ms = std::max(res->expand_ms, r[i].expand_ms);
+    if (r[i].has_solution) {
+      if (!res->has_solution || (is_opt && (is_min ? r[i].best < res->best : r[i].best > res->best))) res->best = r[i].best;
+      res->has_solution = 1;
+    }
+    if (per_device) per_device[i] = r[i];
+  }
+  if (g->objective == CSOLVE_OBJ_ANY && res->solutions > 1) res->solutions = 1;     // two ranks may both have finished a leaf
+  // stored assignments of all devices; MIN / MAX: one chain of improvements, the optimum last
+  const int V = g->n_vars;
+  struct Ref { int dev, idx, key; };
+  std::vector<Ref> refs;
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < g->probs[i]->n_stored; k++) refs.push_back(Ref{i, k, g->probs[i]->sol_host[(size_t)k * (V + 1) + V]});
+  if (is_opt) std::stable_sort(refs.begin(), refs.end(), [&](const Ref &x, const Ref &y) { return is_min ? x.key > y.key : x.key < y.key; });
+  if (g->objective == CSOLVE_OBJ_ANY && refs.size() > 1) refs.resize(1);
+  g->sols.resize(refs.size() * (size_t)(V + 1));
+  for (size_t k = 0; k < refs.size(); k++)
+    memcpy(&g->sols[k * (V + 1)], &g->probs[refs[k].dev]->sol_host[(size_t)refs[k].idx * (V + 1)], sizeof(int32_t) * (V + 1));
+  g->n_stored = (int32_t)refs.size();
+  res->n_stored = g->n_stored;
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_group_get_solution(csolve_gpu_group *g, int32_t i, int32_t *values, int32_t *key) {
+  if (g == nullptr || values == nullptr || i < 0 || i >= g->n_stored) return fail(CSOLVE_ERR_INVALID, "solution index out of range");
+  memcpy(values, &g->sols[(size_t)i * (g->n_vars + 1)], sizeof(int32_t) * g->n_vars);
+  if (key) *key = g->sols[(size_t)i * (g->n_vars + 1) + g->n_vars];
+  return CSOLVE_OK;
 }
 
 extern "C" int csolve_gpu_set_exchange(csolve_gpu_problem *p, csolve_exchange_fn fn, void *user) {
@@ -862,7 +1192,7 @@ extern "C" int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_
                                       const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed,
                                       csolve_gpu_result *res) {
   if (n_roots <= 0 || root_dom == nullptr) return fail(CSOLVE_ERR_INVALID, "bad arguments");
-  return solve_impl(p, opt, res, n_roots, root_dom, root_solutions, root_failed);
+  return solve_impl(p, nullptr, opt, res, n_roots, root_dom, root_solutions, root_failed);
 }
 
 extern "C" int csolve_gpu_get_nogoods(csolve_gpu_problem *p, int32_t *lits, int32_t cap_lits, int32_t *starts, int32_t cap_ng,

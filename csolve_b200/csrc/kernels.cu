@@ -489,10 +489,11 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
       if (tslot < 0 && (spins & 7u) == 0u && *reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) {
         code = -1;
       } else if (!cl.drained) {
-        const int nx = *reinterpret_cast<volatile int *>(&ctl->init_next);
+        // the frontier's claim counter may live on another GPU (csolve_gpu_comm): system-scope atomic over NVLink
+        const int nx = *reinterpret_cast<volatile int *>(&a.front_ctl->init_next);
         if (nx < a.n_initial) {
-          n = min(32, max(min(a.part_count, 32), (a.n_initial - nx) / (a.n_warps * 4)));
-          it = atomicAdd(&ctl->init_next, n);
+          n = min(32, max(min(a.part_count, 32), (a.n_initial - nx) / (a.total_warps * 4)));
+          it = a.n_peers > 0 ? atomicAdd_system(&a.front_ctl->init_next, n) : atomicAdd(&a.front_ctl->init_next, n);
           if (it >= a.n_initial) n = 0;
         }
         if (n == 0) code = -3;
@@ -507,6 +508,7 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
         } else {
           bool leave = false;
           if ((spins & 3u) == 3u) {
+            if (a.n_peers > 0 && *reinterpret_cast<volatile int *>(&a.comm->stop_epoch) == a.epoch) atomicMax(&ctl->signal, SIG_STOP);
             if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) leave = true;
             else if (*reinterpret_cast<volatile int *>(&ctl->hungry) >= a.n_warps || clock64() - t0 > a.slice_cycles) {
               // every warp is waiting: nothing left anywhere -- or the time slice is over. Waiters watch the clock too:
@@ -537,7 +539,7 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
       const int idx = it + lane;
       bool mine = lane < n && idx < a.n_initial;
       if (mine && a.part_count > 1)
-        mine = (unsigned)__ldcg(&a.pool[(size_t)idx * fw + 7]) % (unsigned)a.part_count == (unsigned)a.part_rank;
+        mine = (unsigned)__ldcg(&a.front_pool[(size_t)idx * fw + 7]) % (unsigned)a.part_count == (unsigned)a.part_rank;
       const unsigned mk = __ballot_sync(FULL, mine);
       if (mk) {
         cl.base = it;
@@ -590,6 +592,42 @@ __device__ __forceinline__ bool publish_slot(const SearchArgs &a, int lane, int 
   return __shfl_sync(FULL, ok, 0) != 0;
 }
 
+// frame of a claimed slot: the first n_initial slots are the root frontier (possibly on another GPU), the rest the ring
+__device__ __forceinline__ const int *claimed_frame(const SearchArgs &a, int slot) {
+  return (slot < a.n_initial ? a.front_pool : a.pool) + (size_t)slot * a.m.frame_words;
+}
+
+// ---- ranks of a csolve_gpu_comm: incumbent and first-solution exchange over peer memory -------------------------
+// An accepted improving leaf stores its key into every peer's CommBlock (lane r serves peer r: one 64-bit
+// system-scope atomic each, 8 bytes over NVLink, no kernel drain, no host in the loop).
+__device__ __forceinline__ void comm_push_best(const SearchArgs &a, int lane, int key) {
+  if (lane < a.n_peers) {
+    if (a.m.objective == CSOLVE_OBJ_MIN) atomicMin_system(&a.peer_comm[lane]->rmin64, comm_key_min(a.epoch, key));
+    else atomicMax_system(&a.peer_comm[lane]->rmax64, comm_key_max(a.epoch, key));
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void comm_push_stop(const SearchArgs &a, int lane) {
+  if (lane < a.n_peers) atomicMax_system(&a.peer_comm[lane]->stop_epoch, a.epoch);
+  __syncwarp();
+}
+// poll of this rank's own block (local memory, the peers wrote it): fold a better incumbent into ctl->best, turn a
+// peer's "found" into SIG_STOP. Lane 0; called where the control block is polled anyway.
+__device__ __forceinline__ void comm_poll(const SearchArgs &a, int lane) {
+  if (lane == 0) {
+    if (a.m.objective == CSOLVE_OBJ_MIN) {
+      const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&a.comm->rmin64);
+      if (comm_key_is_epoch_min(k, a.epoch)) atomicMin(&a.ctl->best, comm_key_value(k));
+    } else if (a.m.objective == CSOLVE_OBJ_MAX) {
+      const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&a.comm->rmax64);
+      if (comm_key_is_epoch_max(k, a.epoch)) atomicMax(&a.ctl->best, comm_key_value(k));
+    } else if (a.m.objective == CSOLVE_OBJ_ANY) {
+      if (*reinterpret_cast<volatile int *>(&a.comm->stop_epoch) == a.epoch) atomicMax(&a.ctl->signal, SIG_STOP);
+    }
+  }
+  __syncwarp();
+}
+
 // ---- the search kernel ----------------------------------------------------------------------------
 // Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
 template <bool EXPAND, bool LEARN, bool LIN = false, bool SAMPLE = false>
@@ -636,6 +674,7 @@ k_search(const SearchArgs a) {
     if (level < base) {
       // out of work: take a frame of the frontier / shared pool
       const int *src;
+      int ring_slot = 0;
       if (EXPAND) {
         int it = 0;
         if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
@@ -649,14 +688,15 @@ k_search(const SearchArgs a) {
         waited += clock64() - w0;
         if (slot < 0) break;
         claims++;
-        src = a.pool + (size_t)slot * fw;
+        src = claimed_frame(a, slot);
+        ring_slot = slot;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       int *dst = stack + (size_t)L * fw;
       for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
       if (!EXPAND) {
         __syncwarp();
-        if (lane == 0) { __threadfence(); __stcg(&a.ready[(src - a.pool) / fw], 0); }   // slot may be reused
+        if (lane == 0) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }   // slot may be reused
       }
       level = base = L;
       have = false;
@@ -810,17 +850,20 @@ k_search(const SearchArgs a) {
           if (lane == 0) old = atomicMin(&ctl->best, key);
           old = __shfl_sync(FULL, old, 0);
           accepted = key < old;
+          if (accepted && a.n_peers > 0) comm_push_best(a, lane, key);
         } else if (m.objective == CSOLVE_OBJ_MAX) {
           key = s.d[2 * m.obj_var + 1];
           int old = 0;
           if (lane == 0) old = atomicMax(&ctl->best, key);
           old = __shfl_sync(FULL, old, 0);
           accepted = key > old;
+          if (accepted && a.n_peers > 0) comm_push_best(a, lane, key);
         } else if (m.objective == CSOLVE_OBJ_ANY) {
           int old = 0;
           if (lane == 0) old = atomicMax(&ctl->signal, SIG_STOP);
           old = __shfl_sync(FULL, old, 0);
           accepted = old != SIG_STOP;     // first finder wins (found_any(), src/csolve.c:207-209)
+          if (accepted && a.n_peers > 0) comm_push_stop(a, lane);
         }
         if (accepted) {
           sols++;
@@ -864,6 +907,7 @@ k_search(const SearchArgs a) {
     // (general-kernel nodes are long, so the control block is polled often; an L2 round trip per node would
     // dominate the short nodes of the lane-owns-variable kernel, which polls every POLL_NODES nodes)
     if (!EXPAND && ((++poll & 3u) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
+      if (a.n_peers > 0) comm_poll(a, lane);
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -1192,6 +1236,7 @@ k_search_lov(const SearchArgs a) {
     if (level < base) {
       // out of work: take a frame of the frontier / shared pool
       const int *src;
+      int ring_slot = 0;
       if (EXPAND) {
         int it = 0;
         if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
@@ -1205,14 +1250,15 @@ k_search_lov(const SearchArgs a) {
         waited += clock64() - w0;
         if (slot < 0) break;
         claims++;
-        src = a.pool + (size_t)slot * fw;
+        src = claimed_frame(a, slot);
+        ring_slot = slot;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       CHK(L >= 0 && L < V, "lov claimed level", L);
       frame_in(src, sst + L * sfw);
       if (!EXPAND) {
         __syncwarp();
-        if (lane == 0) { __threadfence(); __stcg(&a.ready[(src - a.pool) / fw], 0); }   // slot may be reused
+        if (lane == 0) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }   // slot may be reused
       }
       level = base = L;
       sf = sst + L * sfw;
@@ -1314,6 +1360,7 @@ k_search_lov(const SearchArgs a) {
           if (lane == 0) old = atomicMax(&ctl->signal, SIG_STOP);
           old = __shfl_sync(FULL, old, 0);
           accepted = old != SIG_STOP;
+          if (accepted && a.n_peers > 0) comm_push_stop(a, lane);
         }
         if (accepted) {
           sols++;
@@ -1438,6 +1485,7 @@ k_search_lov(const SearchArgs a) {
 #endif
       nodes += n32; cuts += c32; n32 = 0; c32 = 0;
       dbg_polls++;
+      if (a.n_peers > 0) comm_poll(a, lane);
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -1742,6 +1790,7 @@ k_search_lovk(const SearchArgs a) {
   for (;;) {
     if (level < base) {
       const int *src;
+      int ring_slot = 0;
       if (EXPAND) {
         int it = 0;
         if (lane == 0) it = atomicAdd(&ctl->item_next, 1);
@@ -1751,14 +1800,15 @@ k_search_lovk(const SearchArgs a) {
       } else {
         const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
         if (slot < 0) break;
-        src = a.pool + (size_t)slot * fw;
+        src = claimed_frame(a, slot);
+        ring_slot = slot;
       }
       const int L = EXPAND ? 0 : __ldcg(&src[FR_LEVEL]);
       int *dst = stack + (size_t)L * fw;
       for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
       if (!EXPAND) {
         __syncwarp();
-        if (lane == 0) { __threadfence(); __stcg(&a.ready[(src - a.pool) / fw], 0); }
+        if (lane == 0) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }
       }
       level = base = L;
       have = false;
@@ -1885,6 +1935,7 @@ k_search_lovk(const SearchArgs a) {
             if (lane == 0) old = atomicMax(&ctl->signal, SIG_STOP);
             old = __shfl_sync(FULL, old, 0);
             accepted = old != SIG_STOP;
+            if (accepted && a.n_peers > 0) comm_push_stop(a, lane);
           }
           if (accepted) {
             sols++;
@@ -1942,6 +1993,7 @@ k_search_lovk(const SearchArgs a) {
     }
 
     if (!EXPAND && (++poll & (*reinterpret_cast<volatile int *>(&s_blk_hungry) > 0 ? 1u : 7u)) == 0) {
+      if (a.n_peers > 0) comm_poll(a, lane);
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -2135,7 +2187,7 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
     __syncthreads();
   }
   // frames still in the frontier pool are work too: nothing to move while they last
-  const bool pool_left = a.ctl->item_count - a.ctl->item_next > 0 || a.ctl->init_next < a.n_initial;
+  const bool pool_left = a.ctl->item_count - a.ctl->item_next > 0 || *reinterpret_cast<volatile int *>(&a.front_ctl->init_next) < a.n_initial;
   for (int round = 0; round < 4 && !pool_left; ++round) {
     if (idle_done >= n_idle) break;
     if (threadIdx.x == 0) n_donor = 0;

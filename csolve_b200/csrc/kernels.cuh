@@ -49,6 +49,34 @@ struct SearchCtl {
   int32_t pad4[28];
 };
 
+// One process (or host thread) per GPU: what the ranks of a csolve_gpu_comm share. Every rank owns one CommBlock in
+// device memory that its peers map (NVLink peer access inside one process, CUDA IPC between processes) and write with
+// system-scope atomics; nothing in it is ever reset -- every entry carries the epoch (the comm's solve counter) it
+// belongs to, so a late store of the previous search cannot leak into the next one.
+//   rmin64 / rmax64  best incumbent pushed by a peer (MIN / MAX models): epoch-tagged key, see comm_key_min / _max
+//   stop_epoch       ANY models: a peer found a solution in this epoch (found_any(), src/csolve.c:207-209)
+//   front_*          rank 0 only: the expanded root frontier of this epoch is in rank 0's segment (front_n frames of
+//                    front_fw words; front_n < 0: not shared -- every rank expands and partitions by path hash)
+//   done_epoch[r]    rank 0 only: rank r has finished the search of this epoch (the frontier may be overwritten)
+struct CommBlock {
+  unsigned long long rmin64, rmax64;
+  int32_t stop_epoch;
+  int32_t front_epoch, front_n, front_fw;
+  int32_t done_epoch[8];
+  int32_t pad[16];
+};
+static const int COMM_MAX_RANKS = 8;
+// epoch-tagged incumbent keys: a later epoch always wins the atomic, inside an epoch the better value wins
+CSOLVE_HOSTDEV static inline unsigned long long comm_key_min(int epoch, int32_t v) {
+  return ((unsigned long long)(0xffffffffu - (uint32_t)epoch) << 32) | (uint32_t)((uint32_t)v ^ 0x80000000u);
+}
+CSOLVE_HOSTDEV static inline unsigned long long comm_key_max(int epoch, int32_t v) {
+  return ((unsigned long long)(uint32_t)epoch << 32) | (uint32_t)((uint32_t)v ^ 0x80000000u);
+}
+CSOLVE_HOSTDEV static inline int32_t comm_key_value(unsigned long long k) { return (int32_t)((uint32_t)k ^ 0x80000000u); }
+CSOLVE_HOSTDEV static inline bool comm_key_is_epoch_min(unsigned long long k, int epoch) { return (uint32_t)(k >> 32) == 0xffffffffu - (uint32_t)epoch; }
+CSOLVE_HOSTDEV static inline bool comm_key_is_epoch_max(unsigned long long k, int epoch) { return (uint32_t)(k >> 32) == (uint32_t)epoch; }
+
 struct WarpState {
   int32_t level;   // index of the top frame of the warp's stack; < base when the warp is idle
   int32_t base;    // lowest level the warp owns
@@ -92,6 +120,16 @@ struct SearchArgs {
   int32_t n_initial;          // the first n_initial pool entries are the expanded root frontier (rank partition applies)
   int32_t part_rank;          // this process searches the frontier frames whose path hash % part_count == part_rank
   int32_t part_count;
+  // Ranks of a csolve_gpu_comm (n_peers == 0: a search on its own). The expanded root frontier and its claim counter
+  // may live on another GPU: every rank claims chunks of the SAME frontier with one system-scope atomicAdd over NVLink,
+  // so the ranks run out of root frames together whatever the sizes of the sub-trees (no static partition).
+  const int32_t *front_pool;  // the root frontier: [n_initial][frame_words] (== pool without a comm)
+  SearchCtl *front_ctl;       // control block whose init_next hands the frontier out (== ctl without a comm)
+  CommBlock *comm;            // this rank's block (peers write it)
+  CommBlock *peer_comm[COMM_MAX_RANKS];   // the other ranks' blocks, peer-mapped
+  int32_t n_peers;
+  int32_t epoch;
+  int32_t total_warps;        // search warps of all ranks (size of a guided chunk)
   // Parity instrumentation (csolve_solve_options.sample_mod > 0; runs the SAMPLE instances of the search kernels):
   // every search node -- executed or counted in bulk -- whose identity hash (parent domains, variable, value) is 0
   // modulo sample_mod is written to sample_rec as

@@ -48,6 +48,31 @@ def reduce_results(res, objective, device=None, group=None):
                 kernel_ms=float(times[0].item()), expand_ms=float(times[1].item()), kernel_ms_min=float(-times[2].item()))
 
 
+def make_comm(device_index, group=None, frontier_bytes=0):
+    """One process per GPU: this rank's Comm, connected to the other ranks' (the 64-byte CUDA IPC handles of the
+    ranks' segments travel through ONE all-gather; after that the ranks talk over NVLink peer memory only).
+    Returns None for a single rank."""
+    from .host import Comm, COMM_HANDLE_BYTES
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    comm = Comm(device_index, rank, world, frontier_bytes)
+    dev = torch.device("cuda", device_index) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(comm.handle()), dtype=torch.uint8, device=dev)
+    allh = [torch.zeros(COMM_HANDLE_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    comm.connect([bytes(t.cpu().tolist()) for t in allh])
+    dist.barrier(group=group)
+    return comm
+
+
+def solve_comm(problem, comm, objective, device=None, group=None, **solve_kw):
+    """Collective search through a Comm (shared root frontier, incumbents over peer memory), then ONE reduction of
+    the ranks' counters. -> (whole-job dict, this rank's SolveResult)"""
+    res = problem.solve(comm=comm, **solve_kw)
+    return reduce_results(res, objective, device=device, group=group), res
+
+
 def make_exchange(objective, device=None, group=None):
     """The per-slice exchange between ranks: ONE all-reduce of three integers.
     MIN models reduce with MIN over [best, -found, done]; everything else with MAX over [best, found, -done]

@@ -140,6 +140,20 @@ def library():
     lib.csolve_gpu_set_rebalance.argtypes = [C.c_void_p, REBALANCE_FN, C.c_void_p]
     lib.csolve_gpu_export_frames.argtypes = [C.c_void_p, C.c_int32, I32P, I32P]
     lib.csolve_gpu_import_frames.argtypes = [C.c_void_p, I32P, C.c_int32]
+    lib.csolve_gpu_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.csolve_gpu_comm_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.csolve_gpu_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.csolve_gpu_comm_connect_local.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+    lib.csolve_gpu_comm_destroy.argtypes = [C.c_void_p]
+    lib.csolve_gpu_comm_destroy.restype = None
+    lib.csolve_gpu_solve_comm.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_SolveOptions), C.POINTER(_GpuResult)]
+    lib.csolve_gpu_device_count.argtypes = [I32P]
+    lib.csolve_gpu_group_create.argtypes = [C.c_int32, I32P, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.csolve_gpu_group_load.argtypes = [C.c_void_p, C.POINTER(FlatModel)]
+    lib.csolve_gpu_group_solve.argtypes = [C.c_void_p, C.POINTER(_SolveOptions), C.POINTER(_GpuResult), C.POINTER(_GpuResult)]
+    lib.csolve_gpu_group_get_solution.argtypes = [C.c_void_p, C.c_int32, I32P, I32P]
+    lib.csolve_gpu_group_destroy.argtypes = [C.c_void_p]
+    lib.csolve_gpu_group_destroy.restype = None
     lib.csolve_last_error.restype = C.c_char_p
     _lib = lib
     return lib
@@ -208,6 +222,103 @@ class SolveResult:
                 % (self.solutions, self.nodes, self.cuts, self.props, self.best, self.has_solution, self.kernel_ms))
 
 
+def solve_options(order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0, time_limit_ms=0,
+                  slice_ms=0, prefer_failing=False, create_conflicts=False, sample_mod=0, sample_cap=0,
+                  restart_frequency=0, sample_failed_keep=1):
+    if isinstance(order, str):
+        order = ORDER_NAMES[order]
+    return _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
+                         1 if create_conflicts else 0, 0, 1 if prefer_failing else 0, int(sample_mod), int(sample_cap),
+                         int(restart_frequency), int(sample_failed_keep))
+
+
+COMM_HANDLE_BYTES = 64
+
+
+class Comm:
+    """One rank of a csolve_gpu_comm (include/csolve_b200.h): the ranks search one tree together over NVLink peer
+    memory. One process per GPU: create, all-gather `handle()`, `connect(handles)` (distributed.make_comm does that
+    over torch.distributed)."""
+
+    def __init__(self, device, rank, world, frontier_bytes=0):
+        h = C.c_void_p()
+        _check(library().csolve_gpu_comm_create(int(device), int(rank), int(world), int(frontier_bytes), C.byref(h)))
+        self._h = h
+        self.rank, self.world = int(rank), int(world)
+
+    def handle(self):
+        buf = (C.c_ubyte * COMM_HANDLE_BYTES)()
+        _check(library().csolve_gpu_comm_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles):
+        """handles: the ranks' handle() bytes in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == self.world * COMM_HANDLE_BYTES
+        _check(library().csolve_gpu_comm_connect(self._h, blob))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            library().csolve_gpu_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_count():
+    n = C.c_int32()
+    _check(library().csolve_gpu_device_count(C.byref(n)))
+    return n.value
+
+
+class GpuGroup:
+    """Several GPUs of THIS process on one search tree (csolve_gpu_group_*: one host thread per device inside the
+    library -- what the drop-in solve() uses for `-j N`)."""
+
+    def __init__(self, n_devices, devices=None, frontier_bytes=0):
+        h = C.c_void_p()
+        dev = None
+        if devices is not None:
+            dev = (C.c_int32 * n_devices)(*devices)
+        _check(library().csolve_gpu_group_create(int(n_devices), dev, int(frontier_bytes), C.byref(h)))
+        self._h = h
+        self.n_devices = int(n_devices)
+        self.n_vars = 0
+
+    def load(self, model):
+        flat = model.flat if isinstance(model, Model) else model
+        self.n_vars = flat.n_vars
+        _check(library().csolve_gpu_group_load(self._h, C.byref(flat)))
+
+    def solve(self, **kw):
+        """-> (SolveResult of the whole job, [SolveResult per device])"""
+        opt = solve_options(**kw)
+        res = _GpuResult()
+        per = (_GpuResult * self.n_devices)()
+        _check(library().csolve_gpu_group_solve(self._h, C.byref(opt), C.byref(res), per))
+        sols = []
+        buf = (C.c_int32 * self.n_vars)()
+        for i in range(res.n_stored):
+            _check(library().csolve_gpu_group_get_solution(self._h, i, buf, None))
+            sols.append(list(buf))
+        return SolveResult(res, sols), [SolveResult(per[i], []) for i in range(self.n_devices)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            library().csolve_gpu_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class GpuProblem:
     """A model resident on one GPU."""
 
@@ -240,14 +351,16 @@ class GpuProblem:
 
     def solve(self, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0,
               time_limit_ms=0, slice_ms=0, prefer_failing=False, create_conflicts=False, sample_mod=0, sample_cap=0,
-              restart_frequency=0, sample_failed_keep=1):
-        if isinstance(order, str):
-            order = ORDER_NAMES[order]
-        opt = _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
-                            1 if create_conflicts else 0, 0, 1 if prefer_failing else 0, int(sample_mod), int(sample_cap),
-                            int(restart_frequency), int(sample_failed_keep))
+              restart_frequency=0, sample_failed_keep=1, comm=None):
+        """comm: a connected Comm -- the call is then COLLECTIVE over the comm's ranks (csolve_gpu_solve_comm): they
+        search one tree together and each gets its own share of the counters back."""
+        opt = solve_options(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
+                            prefer_failing, create_conflicts, sample_mod, sample_cap, restart_frequency, sample_failed_keep)
         res = _GpuResult()
-        _check(library().csolve_gpu_solve(self._h, C.byref(opt), C.byref(res)))
+        if comm is not None:
+            _check(library().csolve_gpu_solve_comm(self._h, comm._h, C.byref(opt), C.byref(res)))
+        else:
+            _check(library().csolve_gpu_solve(self._h, C.byref(opt), C.byref(res)))
         sols = []
         buf = (C.c_int32 * self.n_vars)()
         for i in range(res.n_stored):

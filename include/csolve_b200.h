@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSOLVE_B200_ABI_VERSION 3
+#define CSOLVE_B200_ABI_VERSION 4
 
 /* ---- error codes (all entry points return 0 on success) ------------------ */
 #define CSOLVE_OK                 0
@@ -227,6 +227,44 @@ typedef int (*csolve_rebalance_fn)(void *user, csolve_gpu_problem *p, int32_t n_
 int csolve_gpu_set_rebalance(csolve_gpu_problem *p, csolve_rebalance_fn fn, void *user);
 int csolve_gpu_export_frames(csolve_gpu_problem *p, int32_t max_frames, int32_t *frames, int32_t *n_out);
 int csolve_gpu_import_frames(csolve_gpu_problem *p, const int32_t *frames, int32_t n_frames);
+
+/* ---- several GPUs on ONE search tree ------------------------------------------------------------------
+ * The reference's parallel mode lives inside solve(): `-j N` forks workers that split a variable's interval
+ * (worker_spawn, src/csolve.c:105-152) and meet in a shared page (struct shared_t, src/csolve.h:259-266:
+ * objective_best, solutions). Here the ranks of a csolve_gpu_comm (one GPU each, at most 8) do the same over
+ * NVLink peer memory, with no host in the loop while the search runs:
+ *   - rank 0 expands the root breadth-first and leaves the frontier in its segment; EVERY rank claims chunks of that
+ *     one frontier with a system-scope atomicAdd on rank 0's counter, so all GPUs run out of root frames together
+ *     whatever the sizes of the sub-trees (no static partition);
+ *   - an improving incumbent (MIN / MAX) and "a solution exists" (ANY) are stored straight into every peer's
+ *     control block by the warp that found them (8 bytes, epoch-tagged, system-scope atomicMin / atomicMax);
+ *   - each rank returns its own counters; their sum / the best incumbent is the result (csolve_gpu_group_solve does
+ *     that for the in-process case, csolve_b200/distributed.py with one NCCL all-reduce for one process per GPU).
+ * csolve_gpu_solve_comm is COLLECTIVE: every rank calls it, the same number of times, on the same model.
+ *
+ * One process per GPU (torchrun / MPI): create, exchange the 64-byte handles (any all-gather), connect:
+ *     csolve_gpu_comm_create(device, rank, world, 0, &c); csolve_gpu_comm_handle(c, mine);
+ *     <all-gather mine -> all>;                            csolve_gpu_comm_connect(c, all);
+ * One process, several GPUs: csolve_gpu_group_* below (host threads, direct peer access) -- what the drop-in
+ * solve() uses for `-j N`. frontier_bytes: capacity of rank 0's frontier buffer (0 = 256 MiB); a frontier that does
+ * not fit falls back to "every rank expands, frames are partitioned by path hash". */
+#define CSOLVE_COMM_HANDLE_BYTES 64
+typedef struct csolve_gpu_comm csolve_gpu_comm;
+int  csolve_gpu_comm_create(int32_t device, int32_t rank, int32_t world, size_t frontier_bytes, csolve_gpu_comm **out);
+int  csolve_gpu_comm_handle(csolve_gpu_comm *c, void *handle /* CSOLVE_COMM_HANDLE_BYTES */);
+int  csolve_gpu_comm_connect(csolve_gpu_comm *c, const void *handles /* world x CSOLVE_COMM_HANDLE_BYTES, rank order */);
+int  csolve_gpu_comm_connect_local(csolve_gpu_comm **comms, int32_t world);   /* all ranks in this process */
+void csolve_gpu_comm_destroy(csolve_gpu_comm *c);
+int  csolve_gpu_solve_comm(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_options *opt, csolve_gpu_result *res);
+
+typedef struct csolve_gpu_group csolve_gpu_group;
+int  csolve_gpu_device_count(int32_t *n);
+int  csolve_gpu_group_create(int32_t n_devices, const int32_t *devices /* NULL: 0..n-1 */, size_t frontier_bytes, csolve_gpu_group **out);
+int  csolve_gpu_group_load(csolve_gpu_group *g, const csolve_flat_model *m);           /* the model on every device */
+int  csolve_gpu_group_solve(csolve_gpu_group *g, const csolve_solve_options *opt, csolve_gpu_result *res /* whole job */,
+                            csolve_gpu_result *per_device /* [n_devices] or NULL */);
+int  csolve_gpu_group_get_solution(csolve_gpu_group *g, int32_t i, int32_t *values, int32_t *key /* or NULL */);
+void csolve_gpu_group_destroy(csolve_gpu_group *g);
 
 /* Batched roots (BASELINE config 2: many instances that share one constraint network and differ only in
  * their root domains, e.g. 10 000 sudokus = the 27 all_different groups + per-instance clue domains).

@@ -34,7 +34,35 @@ cases += [("queens13 lopsided +rebal", I.queens(13), dict(split_target=1, slice_
           ("sat200 s1 lopsided", I.random_3sat(200, seed=1), dict(prefer_failing=True, split_target=1, slice_ms=2), ("has_solution", 0))]
 ok = True
 counts = {}
-for name, text, kw, (key, want) in cases:
+# ---- the comm path (csolve_gpu_comm): shared frontier + incumbents over peer memory, no Python in the loop ----------
+comm = None
+try:
+    comm = D.make_comm(local)
+except Exception as e:  # noqa: BLE001
+    if rank == 0:
+        print("comm unavailable: %s" % e, flush=True)
+    ok = False
+if comm is not None:
+    for name, text, kw, (key, want) in [c for c in cases if "rebal" not in c[0] and "lopsided" not in c[0]] * 2:
+        kw = {k: v for k, v in kw.items() if k not in ("exchange", "rebalance", "slice_ms")}
+        m = cb.Model(text)
+        p = cb.GpuProblem(m, device=local)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, mine = D.solve_comm(p, comm, m.objective, device=dev, **kw)
+        dt = time.perf_counter() - t0
+        good = out[key] == want
+        ok &= good
+        nodes_all = [None] * dist.get_world_size()
+        dist.all_gather_object(nodes_all, int(mine.nodes))
+        if rank == 0:
+            print("comm %-14s world=%d %s=%s (want %s) %s nodes=%d per-rank=%s dev=%.2f ms wall=%.1f ms" % (
+                name, dist.get_world_size(), key, out[key], want, "OK" if good else "WRONG", out["nodes"], nodes_all,
+                out["kernel_ms"] + out["expand_ms"], dt * 1e3), flush=True)
+        if "ALL" in name:
+            ref = counts.setdefault("comm " + name, (out["solutions"], out["nodes"], out["cuts"]))
+            ok &= ref == (out["solutions"], out["nodes"], out["cuts"])
+for name, text, kw, (key, want) in ([] if "--comm-only" in sys.argv else cases):
     m = cb.Model(text)
     p = cb.GpuProblem(m, device=local)
     dist.barrier(); torch.cuda.synchronize()
@@ -54,5 +82,7 @@ for name, text, kw, (key, want) in cases:
             if rank == 0:
                 print("   counters differ from the run without rebalancing: %s vs %s" % ((out["solutions"], out["nodes"], out["cuts"]), ref))
 dist.barrier()
+if comm is not None:
+    comm.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -32,7 +32,7 @@ def test_header_symbols_are_exported():
 
 
 def test_abi_version():
-    assert cb.library().csolve_abi_version() == 3
+    assert cb.library().csolve_abi_version() == 4
 
 
 def test_header_compiles_as_c():
@@ -68,6 +68,23 @@ def test_no_device_is_a_loud_error():
     with pytest.raises(cb.CsolveError) as e:
         cb.GpuProblem(m)
     assert e.value.code == -7 and "no CPU fallback" in e.value.message
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_comm_and_group_need_a_device_too():
+    """the multi-GPU entry points (csolve_gpu_comm_*, csolve_gpu_group_*) have no CPU fallback either"""
+    with pytest.raises(cb.CsolveError) as e:
+        cb.Comm(0, 0, 2)
+    assert e.value.code == -7
+    with pytest.raises(cb.CsolveError) as e:
+        cb.GpuGroup(2)
+    assert e.value.code == -7
+    with pytest.raises(cb.CsolveError) as e:
+        cb.device_count()
+    assert e.value.code == -7
+    with pytest.raises(cb.CsolveError) as e:
+        cb.Comm(0, 3, 2)                      # rank outside the world: rejected before any device call
+    assert e.value.code == -1
 
 
 def test_invalid_models_are_rejected_before_touching_the_device():

@@ -1,0 +1,75 @@
+"""Several GPUs on one search tree through the C library (csolve_gpu_group_* / csolve_gpu_comm_*): shared root
+frontier claimed over peer memory, incumbents and first solutions pushed to the peers. Results must be the
+single-GPU ones. With one GPU on the box the group has one device (the comm is then inert); the 2..8-device paths run
+whenever the box has them (scripts/multi_gpu_check.py runs the same checks under torchrun, one process per GPU)."""
+import pytest
+
+import csolve_b200 as cb
+import util
+from csolve_b200 import instances as I
+
+pytestmark = pytest.mark.gpu
+
+
+def _sizes():
+    n = cb.device_count()
+    return [k for k in (1, 2, 4, 8) if k <= n]
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_group_counts_equal_single_gpu(n_dev):
+    if n_dev not in _sizes():
+        pytest.skip("needs %d GPUs" % n_dev)
+    m = cb.Model(I.queens(12))
+    one = cb.GpuProblem(m).solve()
+    g = cb.GpuGroup(n_dev)
+    g.load(m)
+    for _ in range(3):                       # the comm's epochs: several collective searches on one group
+        r, per = g.solve()
+        assert (r.solutions, r.nodes, r.cuts) == (one.solutions, one.nodes, one.cuts) == (14200, 635714, 467802)
+        assert sum(p.nodes for p in per) == r.nodes
+        if n_dev > 1:
+            assert all(p.nodes > 0 for p in per)          # every device searched a share of the ONE frontier
+    g.close()
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_group_optimum_and_sat_status(n_dev):
+    if n_dev not in _sizes():
+        pytest.skip("needs %d GPUs" % n_dev)
+    g = cb.GpuGroup(n_dev)
+    m = cb.Model(I.wcet())
+    g.load(m)
+    r, _ = g.solve()
+    assert r.has_solution and r.best == 1560
+    assert r.assignments and r.assignments[-1][m.obj_var] == 1560       # the optimum's witness is the last of the chain
+    o = util.Oracle(m)
+    import numpy as np
+    dom = np.repeat(np.asarray(r.assignments[-1], np.int32), 2)
+    assert o.leaf_true(dom)
+    m = cb.Model(I.schedule())
+    g.load(m)
+    r, _ = g.solve()
+    assert r.has_solution and r.best == 11
+    # config 5: seed 3 is satisfiable, seed 1 is not (z3 and the reference agree)
+    for seed, sat in ((3, True), (1, False)):
+        m = cb.Model(I.random_3sat(200, seed=seed))
+        g.load(m)
+        r, _ = g.solve(prefer_failing=True)
+        assert bool(r.has_solution) == sat
+        if sat:
+            assert r.solutions == 1
+            dom = np.repeat(np.asarray(r.assignments[0], np.int32), 2)
+            assert util.Oracle(m).leaf_true(dom)
+    g.close()
+
+
+def test_group_stored_solutions():
+    n = _sizes()[-1]
+    g = cb.GpuGroup(n)
+    m = cb.Model(I.queens(8))
+    g.load(m)
+    r, _ = g.solve(max_solutions=200)
+    assert r.solutions == 92 and len(r.assignments) == 92
+    assert len({tuple(a) for a in r.assignments}) == 92
+    g.close()
