@@ -261,13 +261,16 @@ struct csolve_gpu_problem {
 // Segment of one rank (plain cudaMalloc, so that it can be exported with CUDA IPC):
 //   [0, 1024)      the rank's SearchCtl (rank 0's init_next hands out the shared root frontier)
 //   [1024, 1152)   CommBlock: written by the peers with system-scope atomics / small copies
-//   [4096, ...)    rank 0: the expanded root frontier of the current epoch
-static const size_t SEG_CTL = 0, SEG_COMM = 1024, SEG_FRONT = 4096;
+//   [4 KiB, +4 MiB)  ready flags of the rank's donation ring
+//   then ring_bytes  the donation ring itself (frames): peers serve this rank's tickets over NVLink
+//   then             rank 0: the expanded root frontier of the current epoch
+static const size_t SEG_CTL = 0, SEG_COMM = 1024, SEG_READY = 4096, SEG_READY_BYTES = (size_t)4 << 20, SEG_RING = SEG_READY + SEG_READY_BYTES;
+static const size_t SEG_RING_BYTES_DEFAULT = (size_t)96 << 20;
 struct csolve_gpu_comm {
   DeviceCtx *ctx = nullptr;
   int rank = 0, world = 1;
   unsigned char *seg = nullptr;
-  size_t front_bytes = 0;
+  size_t front_bytes = 0, ring_bytes = SEG_RING_BYTES_DEFAULT;
   unsigned char *peer_seg[COMM_MAX_RANKS] = {};
   bool opened[COMM_MAX_RANKS] = {};     // mapped with cudaIpcOpenMemHandle (closed in destroy)
   bool connected = false;
@@ -275,7 +278,10 @@ struct csolve_gpu_comm {
   SearchCtl *ctl() const { return reinterpret_cast<SearchCtl *>(seg + SEG_CTL); }
   CommBlock *block(int r) const { return reinterpret_cast<CommBlock *>(peer_seg[r] + SEG_COMM); }
   SearchCtl *ctl_of(int r) const { return reinterpret_cast<SearchCtl *>(peer_seg[r] + SEG_CTL); }
-  int32_t *front_of(int r) const { return reinterpret_cast<int32_t *>(peer_seg[r] + SEG_FRONT); }
+  int32_t *front_of(int r) const { return reinterpret_cast<int32_t *>(peer_seg[r] + SEG_RING + ring_bytes); }
+  int32_t *ring_of(int r) const { return reinterpret_cast<int32_t *>(peer_seg[r] + SEG_RING); }
+  int32_t *ready_of(int r) const { return reinterpret_cast<int32_t *>(peer_seg[r] + SEG_READY); }
+  int ring_frames(int fw) const { return (int)std::min<size_t>(ring_bytes / ((size_t)fw * sizeof(int32_t)), SEG_READY_BYTES / sizeof(int32_t)); }
 };
 
 extern "C" const char *csolve_last_error(void) { return csolve_front::last_error(); }
@@ -555,8 +561,16 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   //      publishes "failed" if it never published a frontier, every other rank reports that it has left the epoch.
   const int epoch = c != nullptr ? ++c->epoch : 0;
   bool front_published = false;
+  const SearchArgs *comm_args = nullptr;       // set once the search arguments are complete
+  int32_t *d_cstate = nullptr;                 // comm: result of k_comm_state
   ScopeExit comm_guard([&]() {
     if (c == nullptr) return;
+    // leave the epoch: this rank no longer counts as active, whatever state its search is in (errors, time limit)
+    if (comm_args != nullptr && d_cstate != nullptr) {
+      launch_comm_state(*comm_args, 0, 1, d_cstate, p->stream);
+      cudaStreamSynchronize(p->stream);
+    }
+    C->cfree(d_cstate);
     if (c->rank == 0) {
       if (!front_published) {
         const int32_t hdr[3] = {epoch, -2, 0};
@@ -714,6 +728,12 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
         hdr[1] = -1;                              // does not fit: every rank expands for itself
         part_rank = 0; part_count = c->world;
       }
+      // every rank starts the epoch active; the count lives in rank 0's block (CommBlock::active64)
+      {
+        const unsigned long long act = ((unsigned long long)(uint32_t)epoch << 32) | (unsigned)c->world;
+        CUDA_TRY(cudaMemcpyAsync(&c->block(0)->active64, &act, sizeof(act), cudaMemcpyHostToDevice, st));
+        for (int r = 0; r < c->world; r++) CUDA_TRY(cudaMemcpyAsync(&c->block(r)->busy_epoch, &epoch, sizeof(int32_t), cudaMemcpyDefault, st));
+      }
       // the frontier's claim counter must be zero before anybody sees the frontier
       ctl.init_next = 0;
       CUDA_TRY(cudaMemcpyAsync(&dctl->init_next, &ctl.init_next, sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -760,14 +780,37 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   a.front_pool = front_pool != nullptr ? front_pool : pin;
   a.front_ctl = front_ctl;
   a.total_warps = p->n_warps * (front_pool != nullptr ? c->world : 1);
+  const bool cross = c != nullptr && front_pool != nullptr;     // one frontier for all ranks: they also serve each other's tickets
   if (c != nullptr) {
-    a.comm = c->block(c->rank); a.epoch = epoch;
-    for (int r = 0; r < c->world; r++) if (r != c->rank) a.peer_comm[a.n_peers++] = c->block(r);
+    a.comm = c->block(c->rank); a.epoch = epoch; a.rank = c->rank; a.world = c->world; a.n_peers = c->world - 1;
+    for (int r = 0; r < c->world; r++) a.peer_comm[r] = c->block(r);
   }
-  CUDA_TRY(cudaMemsetAsync(p->ready, 0, (size_t)p->pool_cap * sizeof(int32_t), st));
-  if (p->pool_cap - n_items < ring_min_frames(p->n_warps)) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
+  if (cross) {
+    // the donation ring lives in the rank's segment, where the peers can reach it; slot numbers are the same on
+    // every rank (n_initial .. n_initial + ring), so the pointers are shifted by the frontier's length
+    const int ring = c->ring_frames(fw);
+    if (ring < ring_min_frames(p->n_warps))
+      return fail(CSOLVE_ERR_CAPACITY, "comm: the donation ring holds " + std::to_string(ring) + " frames of this model, " + std::to_string(ring_min_frames(p->n_warps)) + " are needed");
+    a.pool_cap = n_items + ring;
+    a.pool = c->ring_of(c->rank) - (size_t)n_items * fw;
+    a.ready = c->ready_of(c->rank) - n_items;
+    for (int r = 0; r < c->world; r++) {
+      a.peer_ctl[r] = c->ctl_of(r);
+      a.peer_pool[r] = c->ring_of(r) - (size_t)n_items * fw;
+      a.peer_ready[r] = c->ready_of(r) - n_items;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->ready_of(c->rank), 0, (size_t)ring * sizeof(int32_t), st));
+    const int32_t zeros[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // demand[8], inflight
+    CUDA_TRY(cudaMemcpyAsync(c->block(c->rank)->demand, zeros, 9 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(&c->block(c->rank)->ring_open, zeros, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cmalloc(C, &d_cstate, 4 * sizeof(int32_t)));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(p->ready, 0, (size_t)p->pool_cap * sizeof(int32_t), st));
+    if (p->pool_cap - n_items < ring_min_frames(p->n_warps)) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
+  }
   a.gprio = d_gprio;     // the breadth-first expansion above stays deterministic (identical on every rank)
   if (learn) a.ng = p->ng;
+  if (cross) comm_args = &a;
   ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0;
   ctl.signal = stopped ? SIG_STOP : SIG_RUN;
   if (c != nullptr && c->rank == 0 && front_pool != nullptr) {
@@ -803,6 +846,23 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       if (!local_done && opt.time_limit_ms > 0) {
         const auto now = std::chrono::steady_clock::now();
         if (std::chrono::duration_cast<std::chrono::milliseconds>(now - wall0).count() > opt.time_limit_ms) { timed_out = true; local_done = true; }
+      }
+      if (cross && local_done && ctl.signal != SIG_STOP && !timed_out) {
+        // This rank ran dry. It asks its peers for frames (CommBlock::demand) and waits here, its ring open to
+        // them, until one arrives -- or until no rank is active any more: the search is over everywhere.
+        for (unsigned spin = 0;; spin++) {
+          int32_t stt[4] = {0, 0, 0, 0};
+          CUDA_TRY(launch_comm_state(a, std::max(p->n_warps / (4 * (c->world - 1)), 32), 0, d_cstate, st)); launches++;   // per peer and per look: the ring holds 4 x n_warps frames
+          CUDA_TRY(cudaMemcpyAsync(stt, d_cstate, sizeof(stt), cudaMemcpyDeviceToHost, st));
+          CUDA_TRY(cudaStreamSynchronize(st));
+          if (stt[2]) break;                                   // ANY: a peer has a solution
+          if (stt[0]) { local_done = false; break; }           // frames arrived (or the shared frontier is not drained yet)
+          if (stt[1] == 0) break;                              // every rank is idle
+          if (stt[1] < 0) return fail(CSOLVE_ERR_CUDA, "comm: the ranks are out of step");
+          if (opt.time_limit_ms > 0 && std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - wall0).count() > opt.time_limit_ms) { timed_out = true; break; }
+          if (std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count() > 3600.0) return fail(CSOLVE_ERR_CUDA, "comm: waited an hour for the other ranks");
+          if (spin > 50) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
       }
     }
     if (p->exchange == nullptr) {
@@ -945,9 +1005,9 @@ extern "C" int csolve_gpu_comm_create(int32_t device, int32_t rank, int32_t worl
   std::unique_ptr<csolve_gpu_comm> c(new csolve_gpu_comm);
   c->ctx = C; c->rank = rank; c->world = world;
   c->front_bytes = rank == 0 ? (frontier_bytes ? frontier_bytes : (size_t)256 << 20) : 0;
-  const size_t bytes = SEG_FRONT + c->front_bytes;
+  const size_t bytes = SEG_RING + c->ring_bytes + c->front_bytes;
   CUDA_TRY(cudaMalloc((void **)&c->seg, bytes));          // not from the block cache: the allocation is exported whole
-  CUDA_TRY(cudaMemset(c->seg, 0, SEG_FRONT));
+  CUDA_TRY(cudaMemset(c->seg, 0, SEG_RING));
   const unsigned long long none = ~0ull;
   CUDA_TRY(cudaMemcpy(&reinterpret_cast<CommBlock *>(c->seg + SEG_COMM)->rmin64, &none, sizeof(none), cudaMemcpyHostToDevice));
   c->peer_seg[rank] = c->seg;

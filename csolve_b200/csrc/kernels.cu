@@ -553,28 +553,54 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
   return slot;
 }
 
-// should this warp donate now?  (lane 0 reads the control block; every lane gets the answer)
-__device__ __forceinline__ bool donation_wanted(const SearchArgs &a, int lane) {
-  int want = 0;
+// should this warp donate now, and into whose ring?  (lane 0 reads the control block; every lane gets the answer)
+// -1: no. a.rank: this rank's own ring (tickets taken by its waiting warps that no donor has picked up yet).
+// another rank r: rank r ran dry and asked for frames (CommBlock::demand, csolve_gpu_comm) -- one unit of its budget
+// is taken here; its tickets are served over NVLink exactly like local ones.
+__device__ __forceinline__ int donation_target(const SearchArgs &a, int lane) {
+  int tgt = -1;
   if (lane == 0) {
-    // tickets taken by waiting warps that no donor has picked up yet
-    want = *reinterpret_cast<volatile int *>(&a.ctl->item_next) - *reinterpret_cast<volatile int *>(&a.ctl->item_count) > 0;
+    if (*reinterpret_cast<volatile int *>(&a.ctl->item_next) - *reinterpret_cast<volatile int *>(&a.ctl->item_count) > 0) {
+      tgt = a.rank;
+    } else if (a.n_peers > 0) {
+      for (int r = 0; r < a.world; r++) {
+        if (r == a.rank || *reinterpret_cast<volatile int *>(&a.comm->demand[r]) <= 0) continue;
+        if (atomicSub(&a.comm->demand[r], 1) <= 0) continue;
+        // announce the visit, then make sure the ring is (still) open: its owner waits for announced visitors
+        // before it touches the ring again (k_comm_state)
+        atomicAdd_system(&a.peer_comm[r]->inflight, 1);
+        if (*reinterpret_cast<volatile int *>(&a.peer_comm[r]->ring_open) == a.epoch) { tgt = r; break; }
+        atomicSub_system(&a.peer_comm[r]->inflight, 1);
+      }
+    }
   }
-  return __shfl_sync(FULL, want, 0) != 0;
+  return __shfl_sync(FULL, tgt, 0);
+}
+// end of a visit to another rank's ring (whether or not a frame was delivered)
+__device__ __forceinline__ void donation_done(const SearchArgs &a, int lane, int tgt) {
+  if (tgt != a.rank && lane == 0) { __threadfence_system(); atomicSub_system(&a.peer_comm[tgt]->inflight, 1); }
+  __syncwarp();
 }
 
-// take the next ticket to serve (lane 0); its slot must be free: wait while the previous lap's frame is still being
-// copied out, skip tickets whose holder left
-__device__ __forceinline__ int reserve_slot(const SearchArgs &a, int lane) {
+__device__ __forceinline__ int *ring_frame(const SearchArgs &a, int tgt, int slot) {
+  return (tgt == a.rank ? a.pool : a.peer_pool[tgt]) + (size_t)slot * a.m.frame_words;
+}
+
+// take the next ticket of rank tgt's ring to serve (lane 0); its slot must be free: wait while the previous lap's
+// frame is still being copied out, skip tickets whose holder left
+__device__ __forceinline__ int reserve_slot(const SearchArgs &a, int lane, int tgt) {
   int s = 0;
   if (lane == 0) {
+    const bool local = tgt == a.rank;
+    SearchCtl *ctl = local ? a.ctl : a.peer_ctl[tgt];
+    int *ready = local ? a.ready : a.peer_ready[tgt];
     for (;;) {
-      const int t = atomicAdd(&a.ctl->item_count, 1);
+      const int t = local ? atomicAdd(&ctl->item_count, 1) : atomicAdd_system(&ctl->item_count, 1);
       s = a.n_initial + (int)((unsigned)t % (unsigned)(a.pool_cap - a.n_initial));
       int r;
-      while ((r = *reinterpret_cast<volatile int *>(&a.ready[s])) == 1) __nanosleep(100);
+      while ((r = *reinterpret_cast<volatile int *>(&ready[s])) == 1) __nanosleep(100);
       if (r == 0) break;
-      __stcg(&a.ready[s], 0);       // abandoned ticket: nobody waits here any more
+      __stcg(&ready[s], 0);       // abandoned ticket: nobody waits here any more
     }
   }
   return __shfl_sync(FULL, s, 0);
@@ -582,12 +608,20 @@ __device__ __forceinline__ int reserve_slot(const SearchArgs &a, int lane) {
 
 // make the frame written to `slot` visible to the ticket's holder (lane 0; every lane gets the answer).
 // false: the holder left while the frame was being written -- the caller donates again to another ticket.
-__device__ __forceinline__ bool publish_slot(const SearchArgs &a, int lane, int slot) {
+// Another rank's ring: that rank counts as active from here on (it may have been idle, its host polls for this).
+__device__ __forceinline__ bool publish_slot(const SearchArgs &a, int lane, int tgt, int slot) {
   int ok = 1;
   if (lane == 0) {
-    __threadfence();
-    ok = atomicCAS(&a.ready[slot], 0, 1) == 0;
-    if (!ok) __stcg(&a.ready[slot], 0);
+    if (tgt == a.rank) {
+      __threadfence();
+      ok = atomicCAS(&a.ready[slot], 0, 1) == 0;
+      if (!ok) __stcg(&a.ready[slot], 0);
+    } else {
+      if (atomicExch_system(&a.peer_comm[tgt]->busy_epoch, a.epoch) != a.epoch) atomicAdd_system(&a.peer_comm[0]->active64, 1ull);
+      __threadfence_system();
+      ok = atomicCAS_system(&a.peer_ready[tgt][slot], 0, 1) == 0;
+      if (!ok) __stcg(&a.peer_ready[tgt][slot], 0);
+    }
   }
   return __shfl_sync(FULL, ok, 0) != 0;
 }
@@ -601,14 +635,14 @@ __device__ __forceinline__ const int *claimed_frame(const SearchArgs &a, int slo
 // An accepted improving leaf stores its key into every peer's CommBlock (lane r serves peer r: one 64-bit
 // system-scope atomic each, 8 bytes over NVLink, no kernel drain, no host in the loop).
 __device__ __forceinline__ void comm_push_best(const SearchArgs &a, int lane, int key) {
-  if (lane < a.n_peers) {
+  if (lane < a.world && lane != a.rank) {
     if (a.m.objective == CSOLVE_OBJ_MIN) atomicMin_system(&a.peer_comm[lane]->rmin64, comm_key_min(a.epoch, key));
     else atomicMax_system(&a.peer_comm[lane]->rmax64, comm_key_max(a.epoch, key));
   }
   __syncwarp();
 }
 __device__ __forceinline__ void comm_push_stop(const SearchArgs &a, int lane) {
-  if (lane < a.n_peers) atomicMax_system(&a.peer_comm[lane]->stop_epoch, a.epoch);
+  if (lane < a.world && lane != a.rank) atomicMax_system(&a.peer_comm[lane]->stop_epoch, a.epoch);
   __syncwarp();
 }
 // poll of this rank's own block (local memory, the peers wrote it): fold a better incumbent into ctl->best, turn a
@@ -696,7 +730,7 @@ k_search(const SearchArgs a) {
       for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
       if (!EXPAND) {
         __syncwarp();
-        if (lane == 0) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }   // slot may be reused
+        if (lane == 0 && ring_slot >= a.n_initial) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }   // slot may be reused
       }
       level = base = L;
       have = false;
@@ -913,7 +947,8 @@ k_search(const SearchArgs a) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
       }
-      if (level >= base && donation_wanted(a, lane)) {
+      int tgt = -1;
+      if (level >= base && (tgt = donation_target(a, lane)) >= 0) {
         // shallowest frame with at least two untried values; the top frame's header is in registers
         int L = -1;
         unsigned d_iter = 0; int d_lo = 0, d_hi = 0;
@@ -936,8 +971,8 @@ k_search(const SearchArgs a) {
           const long long mid = L < level ? ua - 1 : ua + (ub - ua) / 2;
           int *own = stack + (size_t)L * fw;
           for (;;) {
-            const int slot = reserve_slot(a, lane);
-            int *g = a.pool + (size_t)slot * fw;
+            const int slot = reserve_slot(a, lane, tgt);
+            int *g = ring_frame(a, tgt, slot);
             for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
             __syncwarp();
             if (lane == 0) {
@@ -945,7 +980,7 @@ k_search(const SearchArgs a) {
               __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
               __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
             }
-            if (publish_slot(a, lane, slot)) break;
+            if (publish_slot(a, lane, tgt, slot)) break;
           }
           if (lane == 0) {
             if (L < level) { __stcg(&own[FR_ITER], 1); __stcg(&own[FR_LAST], 0); }     // exhausted: iter > last
@@ -957,6 +992,7 @@ k_search(const SearchArgs a) {
           if (L == level) { iter = 0; lo = (int)ua; hi = (int)mid; last = (unsigned)(mid - ua); }
           __syncwarp();
         }
+        donation_done(a, lane, tgt);
       }
     }
   }
@@ -1258,7 +1294,7 @@ k_search_lov(const SearchArgs a) {
       frame_in(src, sst + L * sfw);
       if (!EXPAND) {
         __syncwarp();
-        if (lane == 0) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }   // slot may be reused
+        if (lane == 0 && ring_slot >= a.n_initial) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }   // slot may be reused
       }
       level = base = L;
       sf = sst + L * sfw;
@@ -1491,7 +1527,8 @@ k_search_lov(const SearchArgs a) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
       }
-      if (level >= base && donation_wanted(a, lane)) {
+      int tgt = -1;
+      if (level >= base && (tgt = donation_target(a, lane)) >= 0) {
         // shallowest frame with at least two untried values (the top frame's cursor is in registers)
         // BITS: only values that are not forbidden yet count -- both halves get real work
         dbg_wanted++;
@@ -1525,15 +1562,15 @@ k_search_lov(const SearchArgs a) {
           CHK(give >= 1u && give <= 32u && keep <= 32u, "lov donate give", give);
           int *own = sst + L * sfw;
           for (;;) {
-            const int slot = reserve_slot(a, lane);
-            int *g = a.pool + (size_t)slot * fw;
+            const int slot = reserve_slot(a, lane, tgt);
+            int *g = ring_frame(a, tgt, slot);
             frame_out(own, g);
             __syncwarp();
             if (lane == 0) {
               __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], glo + zb); __stcg(&g[FR_HI], (int)((unsigned)glo + give - 1u) + zb);
               __stcg(&g[FR_LAST], (int)(give - 1u));
             }
-            if (publish_slot(a, lane, slot)) break;
+            if (publish_slot(a, lane, tgt, slot)) break;
           }
           if (lane == 0) { own[0] = d_cur; own[1] = (int)keep; }
           if (L == level) {
@@ -1544,6 +1581,7 @@ k_search_lov(const SearchArgs a) {
           dbg_donated++;
           __syncwarp();
         }
+        donation_done(a, lane, tgt);
       }
     }
   }
@@ -1808,7 +1846,7 @@ k_search_lovk(const SearchArgs a) {
       for (int w = lane; w < fw; w += 32) __stcg(&dst[w], __ldcg(&src[w]));
       if (!EXPAND) {
         __syncwarp();
-        if (lane == 0) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }
+        if (lane == 0 && ring_slot >= a.n_initial) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }
       }
       level = base = L;
       have = false;
@@ -1999,7 +2037,8 @@ k_search_lovk(const SearchArgs a) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
         break;
       }
-      if (level >= base && donation_wanted(a, lane)) {
+      int tgt = -1;
+      if (level >= base && (tgt = donation_target(a, lane)) >= 0) {
         int L = -1;
         unsigned d_iter = 0; int d_lo = 0, d_hi = 0;
         if (lane == 0) {
@@ -2021,15 +2060,15 @@ k_search_lovk(const SearchArgs a) {
           const long long mid = L < level ? ua - 1 : ua + (ub - ua) / 2;
           int *own = stack + (size_t)L * fw;
           for (;;) {
-            const int slot = reserve_slot(a, lane);
-            int *g = a.pool + (size_t)slot * fw;
+            const int slot = reserve_slot(a, lane, tgt);
+            int *g = ring_frame(a, tgt, slot);
             for (int w = lane; w < fw; w += 32) __stcg(&g[w], __ldcg(&own[w]));
             __syncwarp();
             if (lane == 0) {
               __stcg(&g[FR_ITER], 0); __stcg(&g[FR_LO], (int)(mid + 1)); __stcg(&g[FR_HI], (int)ub);
               __stcg(&g[FR_LAST], (int)(unsigned)(ub - mid - 1));
             }
-            if (publish_slot(a, lane, slot)) break;
+            if (publish_slot(a, lane, tgt, slot)) break;
           }
           if (lane == 0) {
             if (L < level) { __stcg(&own[FR_ITER], 1); __stcg(&own[FR_LAST], 0); }     // exhausted: iter > last
@@ -2041,6 +2080,7 @@ k_search_lovk(const SearchArgs a) {
           if (L == level) { iter = 0; flo = (int)ua; fhi = (int)mid; last = (unsigned)(mid - ua); }
           __syncwarp();
         }
+        donation_done(a, lane, tgt);
       }
     }
   }
@@ -2317,6 +2357,46 @@ k_import_frames(const SearchArgs a, const int32_t *in, int n_frames) {
   }
 }
 
+// ---- comm: a rank's state between two launches of its search kernel (one thread) ------------------------------------
+// See CommBlock. A rank that has nothing left clears its busy mark (and takes itself out of rank 0's count of active
+// ranks) -- and looks at its ring once more afterwards: a peer that reserved a ticket in it before the mark was cleared
+// is seen then, one that comes later finds the mark cleared and counts the rank in again itself (publish_slot).
+__global__ void k_comm_state(const SearchArgs a, int want_frames, int force_idle, int32_t *out) {
+  CommBlock *root = a.peer_comm[0];
+  auto has_work = [&]() {
+    return *reinterpret_cast<volatile int *>(&a.ctl->item_count) - *reinterpret_cast<volatile int *>(&a.ctl->item_next) > 0 ||
+           *reinterpret_cast<volatile int *>(&a.front_ctl->init_next) < a.n_initial;
+  };
+  auto close_ring = [&]() {
+    atomicExch_system(&a.comm->ring_open, 0);
+    __threadfence_system();
+    while (*reinterpret_cast<volatile int *>(&a.comm->inflight) > 0) __nanosleep(200);
+  };
+  bool work = false;
+  for (;;) {
+    work = !force_idle && has_work();
+    if (work || force_idle) {
+      close_ring();                          // nobody is writing into the ring after this: the look below is exact
+      work = !force_idle && has_work();
+    }
+    if (work) {
+      if (atomicExch_system(&a.comm->busy_epoch, a.epoch) != a.epoch) atomicAdd_system(&root->active64, 1ull);
+      break;
+    }
+    if (!force_idle) atomicExch_system(&a.comm->ring_open, a.epoch);
+    if (atomicExch_system(&a.comm->busy_epoch, 0) == a.epoch) atomicAdd_system(&root->active64, ~0ull);
+    __threadfence_system();
+    if (force_idle || !has_work()) break;    // a ticket reserved before the mark was cleared is seen here
+  }
+  for (int r = 0; r < a.world; r++) {
+    if (r != a.rank) *reinterpret_cast<volatile int *>(&a.peer_comm[r]->demand[a.rank]) = work ? 0 : want_frames;
+  }
+  const unsigned long long act = *reinterpret_cast<volatile unsigned long long *>(&root->active64);
+  out[0] = work ? 1 : 0;
+  out[1] = (int)(act >> 32) == a.epoch ? (int)(unsigned)act : -1;
+  out[2] = *reinterpret_cast<volatile int *>(&a.comm->stop_epoch) == a.epoch ? 1 : 0;
+}
+
 __global__ void k_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out) {
   __shared__ unsigned long long acc[CNT_WIDTH];
   if (threadIdx.x < CNT_WIDTH) acc[threadIdx.x] = 0;
@@ -2497,6 +2577,11 @@ cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t 
   cudaError_t e = ensure_smem((const void *)k_root_frames, smem);
   if (e != cudaSuccess) return e;
   k_root_frames<<<grid, THREADS_PER_BLOCK, smem, st>>>(m, n_roots, root_dom, order, frames_out, out_cap, n_out, root_failed);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_comm_state(const SearchArgs &a, int want_frames, int force_idle, int32_t *out, cudaStream_t st) {
+  k_comm_state<<<1, 1, 0, st>>>(a, want_frames, force_idle, out);
   return cudaGetLastError();
 }
 

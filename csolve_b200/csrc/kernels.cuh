@@ -58,12 +58,24 @@ struct SearchCtl {
 //   front_*          rank 0 only: the expanded root frontier of this epoch is in rank 0's segment (front_n frames of
 //                    front_fw words; front_n < 0: not shared -- every rank expands and partitions by path hash)
 //   done_epoch[r]    rank 0 only: rank r has finished the search of this epoch (the frontier may be overwritten)
+//   busy_epoch       == the current epoch while the rank has (or is being handed) work; cleared by the rank itself when
+//                    it ran dry, set again by whoever hands it a frame (k_comm_state / publish_slot)
+//   demand[r]        frames rank r asks THIS rank for (r ran dry and says so in every peer's block); a busy warp that
+//                    sees a positive entry takes one unit and serves a ticket of rank r's donation ring over NVLink
+//   ring_open/inflight  a peer serves this rank's ring only while the rank waits in its idle loop (nothing else touches
+//                    the ring then); the rank closes the ring and waits for the peers in flight before it moves on
+//   active64         rank 0 only: epoch << 32 | number of ranks whose busy_epoch is set -- 0 ends the search everywhere
 struct CommBlock {
   unsigned long long rmin64, rmax64;
   int32_t stop_epoch;
   int32_t front_epoch, front_n, front_fw;
   int32_t done_epoch[8];
-  int32_t pad[16];
+  int32_t busy_epoch;
+  int32_t ring_open;          // == epoch while the rank sits in its idle loop: only then may peers serve its ring
+  unsigned long long active64;
+  int32_t demand[8];
+  int32_t inflight;           // peers that are serving a ticket of this rank's ring right now
+  int32_t pad[3];
 };
 static const int COMM_MAX_RANKS = 8;
 // epoch-tagged incumbent keys: a later epoch always wins the atomic, inside an epoch the better value wins
@@ -126,8 +138,14 @@ struct SearchArgs {
   const int32_t *front_pool;  // the root frontier: [n_initial][frame_words] (== pool without a comm)
   SearchCtl *front_ctl;       // control block whose init_next hands the frontier out (== ctl without a comm)
   CommBlock *comm;            // this rank's block (peers write it)
-  CommBlock *peer_comm[COMM_MAX_RANKS];   // the other ranks' blocks, peer-mapped
-  int32_t n_peers;
+  CommBlock *peer_comm[COMM_MAX_RANKS];   // every rank's block, peer-mapped, indexed by rank (peer_comm[rank] == comm)
+  // every rank's donation ring (control block, frames, ready flags; same slot numbering on all ranks: the frontier
+  // and the ring size are the same everywhere): a busy warp serves the tickets of a rank that ran dry over NVLink
+  SearchCtl *peer_ctl[COMM_MAX_RANKS];
+  int32_t *peer_pool[COMM_MAX_RANKS];
+  int32_t *peer_ready[COMM_MAX_RANKS];
+  int32_t n_peers;            // world - 1 (0: no comm)
+  int32_t rank, world;
   int32_t epoch;
   int32_t total_warps;        // search warps of all ranks (size of a guided chunk)
   // Parity instrumentation (csolve_solve_options.sample_mod > 0; runs the SAMPLE instances of the search kernels):
@@ -150,6 +168,10 @@ size_t search_smem_bytes(const DevModel &m, bool learn = false);
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s);
 bool search_learns(const SearchArgs &a);
 cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t s);
+// comm: this rank's state between two kernel launches. out[0] = 1 if the rank has work (frames in its ring or in the
+// shared frontier), out[1] = number of ranks still active (-1: another epoch), out[2] = 1 if a peer found a solution
+// (ANY). want_frames > 0 and no work: ask every peer for that many frames. force_idle: leave the epoch whatever is left.
+cudaError_t launch_comm_state(const SearchArgs &a, int want_frames, int force_idle, int32_t *out, cudaStream_t s);
 cudaError_t launch_export_frames(const SearchArgs &a, int32_t *out, int max_frames, int32_t *n_out, cudaStream_t s);
 cudaError_t launch_import_frames(const SearchArgs &a, const int32_t *in, int n_frames, cudaStream_t s);
 cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out, cudaStream_t s);

@@ -28,8 +28,12 @@ def test_group_counts_equal_single_gpu(n_dev):
         r, per = g.solve()
         assert (r.solutions, r.nodes, r.cuts) == (one.solutions, one.nodes, one.cuts) == (14200, 635714, 467802)
         assert sum(p.nodes for p in per) == r.nodes
-        if n_dev > 1:
-            assert all(p.nodes > 0 for p in per)          # every device searched a share of the ONE frontier
+    # a tree large enough that every device is still searching when the others arrive (config 3)
+    m = cb.Model(I.queens(15))
+    g.load(m)
+    r, per = g.solve()
+    assert (r.solutions, r.nodes, r.cuts) == (2279184, 125900250, 96700627)
+    assert all(p.nodes > r.nodes // (4 * n_dev) for p in per)          # every device searched its share of the ONE frontier
     g.close()
 
 
