@@ -238,6 +238,8 @@ struct csolve_gpu_problem {
   int32_t *sample_rec = nullptr, *sample_n = nullptr;   // parity instrumentation (csolve_solve_options.sample_mod)
   int32_t sample_cap = 0;
   int32_t sample_seen = 0;
+  csolve_solution_fn sink = nullptr;    // every solution is handed to the host between slices (csolve_gpu_set_solution_sink)
+  void *sink_user = nullptr;
   csolve_exchange_fn exchange = nullptr;
   void *exchange_user = nullptr;
   csolve_rebalance_fn rebalance = nullptr;
@@ -426,6 +428,10 @@ namespace {
 // most n_warps frames from another rank)
 int ring_min_frames(int n_warps) { return 4 * n_warps + 1024; }
 
+// solutions a search can add to the buffer after a warp has noticed that it is nearly full: every warp runs on to
+// its next poll of the control block (at most 32 nodes, each of which may be an accepted leaf), twice over
+int sink_headroom(int n_warps) { return 64 * n_warps + 4096; }
+
 // Breadth-first expansion target. The ticket queue keeps every warp busy to the end whatever the size of the root
 // frontier (measured: 16-queens search time is the same from 16 to 256 frames per warp), so the frontier only has to
 // be long enough for an even rank partition; every further level is expansion time that all ranks replicate.
@@ -482,6 +488,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
     if (p->sample_n == nullptr) CUDA_TRY(cmalloc(C, &p->sample_n, sizeof(int32_t)));
   }
   int sol_cap = std::max(opt.max_solutions, m.obj_var >= 0 ? 4096 : (m.objective == CSOLVE_OBJ_ANY ? 1 : 0));
+  if (p->sink != nullptr && m.objective == CSOLVE_OBJ_ALL) sol_cap = std::max(sol_cap, std::max(1 << 20, 4 * sink_headroom(p->n_warps)));
   if (sol_cap > p->sol_cap) {
     C->cfree(p->solbuf); p->solbuf = nullptr;
     CUDA_TRY(cmalloc(C, &p->solbuf, (size_t)sol_cap * (m.n_vars + 1) * sizeof(int32_t)));
@@ -636,6 +643,24 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   a.solbuf = p->solbuf; a.max_solutions = p->sol_cap; a.n_warps = p->n_warps; a.order = opt.order;
   a.out_cap = p->pool_cap; a.expand_branch_max = 64;
   a.inst_solutions = d_rsol;
+  int part_rank = opt.part_rank, part_count = opt.part_count;
+  const bool sinking = p->sink != nullptr && m.objective == CSOLVE_OBJ_ALL && !batch;
+  if (sinking) a.sink_headroom = sink_headroom(p->n_warps);
+  uint64_t sunk = 0, n_sliced = 0;      // n_sliced: depth-first slices run so far (0 = still in the expansion)
+  // hands what the solution buffer holds to the sink and empties it (`ctl` was just read back from the device)
+  auto drain_solutions = [&]() -> int {
+    if (!sinking || ctl.n_stored <= 0) return CSOLVE_OK;
+    if (ctl.n_stored > p->sol_cap) return fail(CSOLVE_ERR_CAPACITY, "solution buffer overflow: " + std::to_string(ctl.n_stored) + " solutions in one slice, room for " + std::to_string(p->sol_cap));
+    p->sol_host.resize((size_t)ctl.n_stored * (V + 1));
+    CUDA_TRY(cudaMemcpyAsync(p->sol_host.data(), p->solbuf, p->sol_host.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    const int32_t zero = 0;
+    CUDA_TRY(cudaMemcpyAsync(&dctl->n_stored, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // (a replicated expansion is reported by rank 0 only, like its counters)
+    if (!(part_count > 1 && part_rank != 0 && n_sliced == 0)) { p->sink(p->sink_user, p->sol_host.data(), ctl.n_stored, V + 1); sunk += (uint64_t)ctl.n_stored; }
+    ctl.n_stored = 0;
+    return CSOLVE_OK;
+  };
   p->sample_seen = 0;
   if (opt.sample_mod != 0u) {
     a.sample_rec = p->sample_rec; a.sample_n = p->sample_n; a.sample_cap = p->sample_cap; a.sample_mod = opt.sample_mod;
@@ -690,6 +715,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       CUDA_TRY(cudaMemcpyAsync(&ctl, dctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       if (ctl.out_dropped > 0) return fail(CSOLVE_ERR_CAPACITY, "frontier pool overflow during expansion");
+      { const int rcd = drain_solutions(); if (rcd != CSOLVE_OK) return rcd; }
       n_items = ctl.out_count;
       if (getenv("CSOLVE_DEBUG")) fprintf(stderr, "[csolve] expand level %d -> %d frames (target %d, pool %d, branch %lld)\n", lvl, n_items, target, p->pool_cap, max_branch);
       std::swap(pin, pout);
@@ -704,7 +730,6 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   // Ranks of a comm: rank 0 alone expands the root; the others take the frontier from rank 0's segment (below).
   // part_rank / part_count: 0 / 1 with a shared frontier; the comm's rank / world when the frontier did not fit the
   // segment and every rank expands for itself (path-hash partition, as without a comm).
-  int part_rank = opt.part_rank, part_count = opt.part_count;
   const int32_t *front_pool = nullptr;
   SearchCtl *front_ctl = dctl;
   if (c == nullptr || c->rank == 0) {
@@ -839,7 +864,8 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       CUDA_TRY(launch_rebalance(a, p->scratch, st)); launches++;
       CUDA_TRY(cudaMemcpyAsync(&ctl, dctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
-      slices++;
+      slices++; n_sliced++;
+      { const int rcd = drain_solutions(); if (rcd != CSOLVE_OK) return rcd; }
       busy = ctl.busy;
       idle_now = p->n_warps - busy;
       if (ctl.signal == SIG_STOP || ctl.busy == 0) local_done = true;
@@ -930,6 +956,9 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       fprintf(stderr, "\n");
     }
   }
+  { const int rcd = drain_solutions(); if (rcd != CSOLVE_OK) return rcd; }
+  if (sinking && sunk != tot[CNT_SOLUTIONS])
+    return fail(CSOLVE_ERR_CAPACITY, "solutions lost between the device and the sink: " + std::to_string(sunk) + " of " + std::to_string(tot[CNT_SOLUTIONS]));
   p->n_stored = std::min(ctl.n_stored, p->sol_cap);
   p->sol_host.resize((size_t)p->n_stored * (V + 1));
   if (p->n_stored > 0) {
@@ -1088,6 +1117,9 @@ struct csolve_gpu_group {
   int32_t n_vars = 0, objective = 0, obj_var = -1;
   std::vector<int32_t> sols;          // merged stored assignments: (n_vars values, key) each
   int32_t n_stored = 0;
+  csolve_solution_fn sink = nullptr;  // the devices' sinks funnel into this one, one call at a time
+  void *sink_user = nullptr;
+  std::mutex sink_mu;
 };
 
 extern "C" int csolve_gpu_device_count(int32_t *n) {
@@ -1140,12 +1172,30 @@ int group_parallel(csolve_gpu_group *g, F fn) {
 }
 }  // namespace
 
+namespace {
+void group_sink(void *user, const int32_t *values, int32_t n, int32_t stride) {
+  csolve_gpu_group *g = static_cast<csolve_gpu_group *>(user);
+  std::lock_guard<std::mutex> lk(g->sink_mu);
+  if (g->sink) g->sink(g->sink_user, values, n, stride);
+}
+}  // namespace
+
+extern "C" int csolve_gpu_group_set_solution_sink(csolve_gpu_group *g, csolve_solution_fn fn, void *user) {
+  if (g == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  g->sink = fn;
+  g->sink_user = user;
+  for (auto *p : g->probs) if (p) { p->sink = fn ? group_sink : nullptr; p->sink_user = g; }
+  return CSOLVE_OK;
+}
+
 extern "C" int csolve_gpu_group_load(csolve_gpu_group *g, const csolve_flat_model *m) {
   if (g == nullptr || m == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
   for (auto *p : g->probs) delete p;
   g->probs.assign(g->devices.size(), nullptr);
   g->n_vars = m->n_vars; g->objective = m->objective; g->obj_var = m->obj_var;
-  return group_parallel(g, [&](int i) { return csolve_gpu_load_device(m, g->devices[i], &g->probs[i]); });
+  const int rc = group_parallel(g, [&](int i) { return csolve_gpu_load_device(m, g->devices[i], &g->probs[i]); });
+  if (rc == CSOLVE_OK && g->sink) for (auto *p : g->probs) { p->sink = group_sink; p->sink_user = g; }
+  return rc;
 }
 
 extern "C" int csolve_gpu_group_solve(csolve_gpu_group *g, const csolve_solve_options *opt, csolve_gpu_result *res,
@@ -1191,6 +1241,13 @@ extern "C" int csolve_gpu_group_get_solution(csolve_gpu_group *g, int32_t i, int
   if (g == nullptr || values == nullptr || i < 0 || i >= g->n_stored) return fail(CSOLVE_ERR_INVALID, "solution index out of range");
   memcpy(values, &g->sols[(size_t)i * (g->n_vars + 1)], sizeof(int32_t) * g->n_vars);
   if (key) *key = g->sols[(size_t)i * (g->n_vars + 1) + g->n_vars];
+  return CSOLVE_OK;
+}
+
+extern "C" int csolve_gpu_set_solution_sink(csolve_gpu_problem *p, csolve_solution_fn fn, void *user) {
+  if (p == nullptr) return fail(CSOLVE_ERR_INVALID, "null argument");
+  p->sink = fn;
+  p->sink_user = user;
   return CSOLVE_OK;
 }
 

@@ -942,6 +942,10 @@ k_search(const SearchArgs a) {
     // dominate the short nodes of the lane-owns-variable kernel, which polls every POLL_NODES nodes)
     if (!EXPAND && ((++poll & 3u) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
       if (a.n_peers > 0) comm_poll(a, lane);
+      if (a.sink_headroom > 0 && *reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions - a.sink_headroom) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);      // the solution buffer is nearly full: let the host drain it
+        break;
+      }
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -1522,6 +1526,10 @@ k_search_lov(const SearchArgs a) {
       nodes += n32; cuts += c32; n32 = 0; c32 = 0;
       dbg_polls++;
       if (a.n_peers > 0) comm_poll(a, lane);
+      if (a.sink_headroom > 0 && *reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions - a.sink_headroom) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);      // the solution buffer is nearly full: let the host drain it
+        break;
+      }
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
@@ -2032,6 +2040,10 @@ k_search_lovk(const SearchArgs a) {
 
     if (!EXPAND && (++poll & (*reinterpret_cast<volatile int *>(&s_blk_hungry) > 0 ? 1u : 7u)) == 0) {
       if (a.n_peers > 0) comm_poll(a, lane);
+      if (a.sink_headroom > 0 && *reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions - a.sink_headroom) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);      // the solution buffer is nearly full: let the host drain it
+        break;
+      }
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);

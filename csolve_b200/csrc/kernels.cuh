@@ -118,6 +118,8 @@ struct SearchArgs {
   int32_t out_cap;            // expand mode: capacity of the output pool (frames)
   int32_t *solbuf;            // [max_solutions][n_vars + 1]  (values..., objective key)
   int32_t max_solutions;
+  int32_t sink_headroom;      // > 0: the host drains the solution buffer between slices (csolve_gpu_set_solution_sink): a
+                              // slice ends as soon as fewer than this many entries are free
   int32_t n_warps;
   int32_t order;              // CSOLVE_ORDER_*
   int32_t frozen_best;        // expand mode: incumbent every node of this level is propagated against

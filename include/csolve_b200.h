@@ -258,12 +258,14 @@ void csolve_gpu_comm_destroy(csolve_gpu_comm *c);
 int  csolve_gpu_solve_comm(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_options *opt, csolve_gpu_result *res);
 
 typedef struct csolve_gpu_group csolve_gpu_group;
+typedef void (*csolve_solution_fn)(void *user, const int32_t *values, int32_t n, int32_t stride);   /* see csolve_gpu_set_solution_sink */
 int  csolve_gpu_device_count(int32_t *n);
 int  csolve_gpu_group_create(int32_t n_devices, const int32_t *devices /* NULL: 0..n-1 */, size_t frontier_bytes, csolve_gpu_group **out);
 int  csolve_gpu_group_load(csolve_gpu_group *g, const csolve_flat_model *m);           /* the model on every device */
 int  csolve_gpu_group_solve(csolve_gpu_group *g, const csolve_solve_options *opt, csolve_gpu_result *res /* whole job */,
                             csolve_gpu_result *per_device /* [n_devices] or NULL */);
 int  csolve_gpu_group_get_solution(csolve_gpu_group *g, int32_t i, int32_t *values, int32_t *key /* or NULL */);
+int  csolve_gpu_group_set_solution_sink(csolve_gpu_group *g, csolve_solution_fn fn, void *user);  /* calls are serialised */
 void csolve_gpu_group_destroy(csolve_gpu_group *g);
 
 /* Batched roots (BASELINE config 2: many instances that share one constraint network and differ only in
@@ -276,6 +278,15 @@ void csolve_gpu_group_destroy(csolve_gpu_group *g);
 int csolve_gpu_solve_batch(csolve_gpu_problem *p, const csolve_solve_options *opt, int32_t n_roots,
                            const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed,
                            csolve_gpu_result *res);
+
+/* Every solution, however many: the reference prints each accepted leaf as it finds it (src/csolve.c:228-236). With a
+ * sink installed the solution buffer (max_solutions entries, at least 2^20 then) is drained between time slices: a
+ * slice ends as soon as the buffer is nearly full, the host copies the assignments out, hands them to the sink
+ * (n assignments of n_vars values each, `stride` int32 apart; the value after an assignment is its key) and the search
+ * goes on -- nothing is dropped, nothing is kept for csolve_gpu_get_solution(). If a buffer overflows all the same
+ * (a sink that cannot keep up is not the reason: the search waits for it) the call fails with CSOLVE_ERR_CAPACITY
+ * rather than lose a solution silently. ALL models; MIN / MAX keep their chain of incumbents in the buffer as before. */
+int csolve_gpu_set_solution_sink(csolve_gpu_problem *p, csolve_solution_fn fn, void *user);
 
 /* Learned nogoods of the last csolve_gpu_solve() with create_conflicts: copies up to cap_lits literal codes
  * (var << 1 | value) into lits and the start offset of every nogood into starts[0..n] (starts[n] = total);

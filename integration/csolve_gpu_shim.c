@@ -177,6 +177,67 @@ int csolve_flatten_reference(size_t size, struct env_t *env, struct constr_t *co
 }
 
 #ifndef CSOLVE_SHIM_NO_SOLVE
+/* ---- options --------------------------------------------------------------------------------------------
+ * Everything src/main.c parsed is read back through the reference's own public getters where they exist:
+ *   -c  strategy_create_conflicts()      -f  strategy_prefer_failing()      -r  strategy_restart_frequency()
+ * -o has no getter (strategy.c keeps `_order` static); it is recovered from the behaviour of the public
+ * variable heap (strategy_var_order_init / _push / _pop, src/csolve.h:430-436) on synthetic variables: with two
+ * entries, pop returns the one pushed first unless strategy_var_cmp() strictly prefers the other.
+ * -t and -j live in statics of csolve.c; integration/csolve_accessors.c (a translation unit that includes the
+ * unmodified csolve.c and adds two getters) exposes them. Without it: CSOLVE_GPU_TIME_MAX / CSOLVE_GPU_DEVICES. */
+uint32_t csolve_shim_time_max(void) __attribute__((weak));
+uint32_t csolve_shim_workers_max(void) __attribute__((weak));
+
+static struct env_t *probe_pop(struct env_t *pair, struct constr_t *terms, int lo0, int hi0, int lo1, int hi1) {
+  memset(pair, 0, 2 * sizeof(*pair));
+  memset(terms, 0, 2 * sizeof(*terms));
+  terms[0].constr.term.val = INTERVAL(lo0, hi0);
+  terms[1].constr.term.val = INTERVAL(lo1, hi1);
+  pair[0].key = "a"; pair[0].val = &terms[0];
+  pair[1].key = "b"; pair[1].val = &terms[1];
+  strategy_var_order_init(2, pair);          /* pushes pair[0], then pair[1] */
+  struct env_t *first = strategy_var_order_pop();
+  strategy_var_order_free();
+  return first;
+}
+
+/* which of two variables the configured order prefers: 0 / 1, or -1 for a tie (priorities are equal) */
+static int probe_prefers(int lo0, int hi0, int lo1, int hi1) {
+  struct env_t pair[2];
+  struct constr_t terms[2];
+  const int ab = probe_pop(pair, terms, lo0, hi0, lo1, hi1) == &pair[0] ? 0 : 1;
+  const int ba = probe_pop(pair, terms, lo1, hi1, lo0, hi0) == &pair[0] ? 1 : 0;
+  return ab == ba ? ab : -1;
+}
+
+static int probe_order(void) {
+  /* A = [0,10] vs B = [2,5]: smallest-domain prefers B, everything else A; C = [0,3] vs D = [5,6]: largest-domain and
+   * smallest-value prefer C; E = [0,9] vs F = [1,20]: smallest-value prefers E, largest-value F. -o none ties. */
+  const int ab = probe_prefers(0, 10, 2, 5), cd = probe_prefers(0, 3, 5, 6), ef = probe_prefers(0, 9, 1, 20);
+  if (ab < 0 && cd < 0 && ef < 0) return CSOLVE_ORDER_NONE;
+  if (ab == 1) return CSOLVE_ORDER_SMALLEST_DOMAIN;
+  if (cd == 1) return CSOLVE_ORDER_LARGEST_VALUE;
+  return ef == 0 ? CSOLVE_ORDER_SMALLEST_VALUE : CSOLVE_ORDER_LARGEST_DOMAIN;
+}
+
+/* ---- printing (src/csolve.c:228-236, src/print.c:57-70) ------------------------------------------------------ */
+struct sink_state { size_t size; struct env_t *env; int quiet; uint64_t printed; };
+
+static void print_assignment(const struct sink_state *st, const int32_t *vals, int32_t best) {
+  fprintf(stdout, "#1: SOLUTION: ");
+  for (size_t v = 0; v < st->size; v++) {
+    fprintf(stdout, "%s = %d, ", st->env[v].key, vals[v]);
+  }
+  fprintf(stdout, "BEST: %d\n", best);
+}
+
+static void solution_sink(void *user, const int32_t *values, int32_t n, int32_t stride) {
+  struct sink_state *st = user;
+  st->printed += (uint64_t)n;
+  if (st->quiet) return;
+  for (int32_t i = 0; i < n; i++) print_assignment(st, values + (size_t)i * stride, 0);
+}
+
 /* The drop-in: same signature and side effects as src/csolve.c:398. */
 void solve(size_t size, struct env_t *env, struct constr_t *constr) {
   csolve_flat_model m;
@@ -184,52 +245,66 @@ void solve(size_t size, struct env_t *env, struct constr_t *constr) {
   if (rc != CSOLVE_OK) {
     print_fatal("cannot flatten model for the GPU path: %d", rc);
   }
-  csolve_gpu_config cfg = { .device = 0 };
-  if ((rc = csolve_gpu_init(&cfg)) != CSOLVE_OK) {
-    print_fatal("%s", csolve_last_error());
-  }
-  csolve_gpu_problem *p = NULL;
-  if ((rc = csolve_gpu_load(&m, &p)) != CSOLVE_OK) {
-    print_fatal("%s", csolve_last_error());
-  }
-  const char *maxsol = getenv("CSOLVE_GPU_MAX_PRINT");
+  /* the reference's heap of the real variables is not needed on this path; it is rebuilt below for the caller */
+  strategy_var_order_free();
   csolve_solve_options opt;
   memset(&opt, 0, sizeof(opt));
-  opt.order = CSOLVE_ORDER_NONE;
+  opt.order = probe_order();
   opt.part_count = 1;
-  opt.max_solutions = maxsol ? atoi(maxsol) : (1 << 20);
-  csolve_gpu_result res;
-  if ((rc = csolve_gpu_solve(p, &opt, &res)) != CSOLVE_OK) {
+  opt.create_conflicts = strategy_create_conflicts() ? 1 : 0;
+  opt.prefer_failing = strategy_prefer_failing() ? 1 : 0;
+  opt.restart_frequency = (int32_t)(strategy_restart_frequency() > 0x7fffffffu ? 0x7fffffff : strategy_restart_frequency());
+  uint32_t time_max = csolve_shim_time_max ? csolve_shim_time_max() : 0;
+  if (getenv("CSOLVE_GPU_TIME_MAX")) time_max = (uint32_t)strtoul(getenv("CSOLVE_GPU_TIME_MAX"), NULL, 10);
+  if (time_max > 0 && time_max < 2000000u) opt.time_limit_ms = (int32_t)(time_max * 1000u);   /* UINT32_MAX: no limit */
+  int32_t n_dev = csolve_shim_workers_max ? (int32_t)csolve_shim_workers_max() : 1;            /* -j N: N GPUs */
+  if (getenv("CSOLVE_GPU_DEVICES")) n_dev = atoi(getenv("CSOLVE_GPU_DEVICES"));
+  int32_t have = 0;
+  if ((rc = csolve_gpu_device_count(&have)) != CSOLVE_OK) {
     print_fatal("%s", csolve_last_error());
   }
-  /* print the stored assignments in the reference's format; for MIN/MAX the
-   * stored sequence is the chain of improving incumbents */
-  int32_t *vals = malloc(size * sizeof(int32_t));
+  if (n_dev < 1) n_dev = 1;
+  if (n_dev > have) n_dev = have;
+  if (n_dev > 8) n_dev = 8;
+
+  /* ALL: every solution is printed as the reference does, streamed out of the device between time slices.
+   * CSOLVE_GPU_COUNT_ONLY=1 keeps the count and the statistics but prints no assignment (then the kernels count the
+   * last level instead of producing it). MIN / MAX: the chain of improving incumbents; ANY: the solution. */
+  struct sink_state st = { size, env, 0, 0 };
+  const int count_only = getenv("CSOLVE_GPU_COUNT_ONLY") != NULL && atoi(getenv("CSOLVE_GPU_COUNT_ONLY")) != 0;
+  const int stream = m.objective == CSOLVE_OBJ_ALL && !count_only;
+
+  csolve_gpu_result res;
+  csolve_gpu_group *g = NULL;
+  if ((rc = csolve_gpu_group_create(n_dev, NULL, 0, &g)) != CSOLVE_OK ||
+      (rc = csolve_gpu_group_load(g, &m)) != CSOLVE_OK ||
+      (stream && (rc = csolve_gpu_group_set_solution_sink(g, solution_sink, &st)) != CSOLVE_OK) ||
+      (rc = csolve_gpu_group_solve(g, &opt, &res, NULL)) != CSOLVE_OK) {
+    print_fatal("%s", csolve_last_error());
+  }
+  int32_t *vals = malloc((size ? size : 1) * sizeof(int32_t));
   for (int32_t i = 0; i < res.n_stored; i++) {
-    csolve_gpu_get_solution(p, i, vals);
-    fprintf(stdout, "#1: SOLUTION: ");
-    for (size_t v = 0; v < size; v++) {
-      fprintf(stdout, "%s = %d, ", env[v].key, vals[v]);
-    }
-    int32_t best = 0;
-    if (m.obj_var >= 0) best = vals[m.obj_var];
-    fprintf(stdout, "BEST: %d\n", best);
+    int32_t key = 0;
+    csolve_gpu_group_get_solution(g, i, vals, &key);
+    print_assignment(&st, vals, m.obj_var >= 0 ? vals[m.obj_var] : 0);
   }
   free(vals);
   shared()->solutions = res.solutions;
   if (m.obj_var >= 0 && res.has_solution) {
     shared()->objective_best = res.best;
   }
-  fprintf(stdout, "#1: CALLS: %lu, CUTS: %lu, PROPS: %lu, SOLUTIONS: %lu\n",
+  fprintf(stdout, "#1: CALLS: %lu, CUTS: %lu, PROPS: %lu, CONFL: %lu, SOLUTIONS: %lu\n",
           (unsigned long)res.nodes, (unsigned long)res.cuts, (unsigned long)res.props,
-          (unsigned long)res.solutions);
+          (unsigned long)res.conflicts, (unsigned long)res.solutions);
   if (res.timed_out) {
+    shared()->timeout = true;
     fprintf(stdout, "TIMEOUT\n");
   }
   if (!res.has_solution) {
     fprintf(stdout, "NO SOLUTION FOUND\n");
   }
-  csolve_gpu_unload(p);
+  csolve_gpu_group_destroy(g);
   csolve_flat_model_release(&m);
+  strategy_var_order_init(size, env);      /* the caller's env_free() / later code finds the heap as it left it */
 }
 #endif
