@@ -1034,6 +1034,7 @@ extern "C" int csolve_gpu_comm_create(int32_t device, int32_t rank, int32_t worl
   std::unique_ptr<csolve_gpu_comm> c(new csolve_gpu_comm);
   c->ctx = C; c->rank = rank; c->world = world;
   c->front_bytes = rank == 0 ? (frontier_bytes ? frontier_bytes : (size_t)256 << 20) : 0;
+  if (world == 1) { c->front_bytes = 0; c->ring_bytes = 0; }      // a comm of one rank is inert: no ring, no frontier
   const size_t bytes = SEG_RING + c->ring_bytes + c->front_bytes;
   CUDA_TRY(cudaMalloc((void **)&c->seg, bytes));          // not from the block cache: the allocation is exported whole
   CUDA_TRY(cudaMemset(c->seg, 0, SEG_RING));
@@ -1193,7 +1194,16 @@ extern "C" int csolve_gpu_group_load(csolve_gpu_group *g, const csolve_flat_mode
   for (auto *p : g->probs) delete p;
   g->probs.assign(g->devices.size(), nullptr);
   g->n_vars = m->n_vars; g->objective = m->objective; g->obj_var = m->obj_var;
-  const int rc = group_parallel(g, [&](int i) { return csolve_gpu_load_device(m, g->devices[i], &g->probs[i]); });
+  // the search workspace is allocated here as well: with peer mappings in the process a cudaMalloc takes milliseconds,
+  // and a device that is still allocating when the others start searching gets nothing of a short search
+  const int rc = group_parallel(g, [&](int i) {
+    const int r = csolve_gpu_load_device(m, g->devices[i], &g->probs[i]);
+    if (r != CSOLVE_OK) return r;
+    csolve_solve_options o;
+    memset(&o, 0, sizeof(o));
+    if (g->sink) { g->probs[i]->sink = group_sink; g->probs[i]->sink_user = g; }
+    return ensure_workspace(g->probs[i], o, false, 0, false);
+  });
   if (rc == CSOLVE_OK && g->sink) for (auto *p : g->probs) { p->sink = group_sink; p->sink_user = g; }
   return rc;
 }

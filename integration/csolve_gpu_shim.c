@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 struct flat_builder {
   size_t n_nodes, cap_nodes;
@@ -238,9 +239,17 @@ static void solution_sink(void *user, const int32_t *values, int32_t n, int32_t 
   for (int32_t i = 0; i < n; i++) print_assignment(st, values + (size_t)i * stride, 0);
 }
 
+static double now_s(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
 /* The drop-in: same signature and side effects as src/csolve.c:398. */
 void solve(size_t size, struct env_t *env, struct constr_t *constr) {
   csolve_flat_model m;
+  const int timing = getenv("CSOLVE_GPU_TIMING") != NULL;        /* where a cold process spends its time (stderr) */
+  const double t_begin = now_s();
   int rc = csolve_flatten_reference(size, env, constr, &m);
   if (rc != CSOLVE_OK) {
     print_fatal("cannot flatten model for the GPU path: %d", rc);
@@ -260,9 +269,11 @@ void solve(size_t size, struct env_t *env, struct constr_t *constr) {
   int32_t n_dev = csolve_shim_workers_max ? (int32_t)csolve_shim_workers_max() : 1;            /* -j N: N GPUs */
   if (getenv("CSOLVE_GPU_DEVICES")) n_dev = atoi(getenv("CSOLVE_GPU_DEVICES"));
   int32_t have = 0;
+  const double t_flat = now_s();
   if ((rc = csolve_gpu_device_count(&have)) != CSOLVE_OK) {
     print_fatal("%s", csolve_last_error());
   }
+  const double t_count = now_s();
   if (n_dev < 1) n_dev = 1;
   if (n_dev > have) n_dev = have;
   if (n_dev > 8) n_dev = 8;
@@ -276,11 +287,18 @@ void solve(size_t size, struct env_t *env, struct constr_t *constr) {
 
   csolve_gpu_result res;
   csolve_gpu_group *g = NULL;
+  double t_create = 0, t_load = 0;
   if ((rc = csolve_gpu_group_create(n_dev, NULL, 0, &g)) != CSOLVE_OK ||
-      (rc = csolve_gpu_group_load(g, &m)) != CSOLVE_OK ||
-      (stream && (rc = csolve_gpu_group_set_solution_sink(g, solution_sink, &st)) != CSOLVE_OK) ||
+      (t_create = now_s(), rc = csolve_gpu_group_load(g, &m)) != CSOLVE_OK ||
+      (t_load = now_s(), stream && (rc = csolve_gpu_group_set_solution_sink(g, solution_sink, &st)) != CSOLVE_OK) ||
       (rc = csolve_gpu_group_solve(g, &opt, &res, NULL)) != CSOLVE_OK) {
     print_fatal("%s", csolve_last_error());
+  }
+  if (timing) {
+    fprintf(stderr, "[csolve_gpu] flatten + options %.1f ms, CUDA init (device count) %.1f ms, contexts + segments %.1f ms, "
+                    "model upload + workspace %.1f ms, search %.1f ms (device: expand %.2f + search %.2f ms)\n",
+            1e3 * (t_flat - t_begin), 1e3 * (t_count - t_flat), 1e3 * (t_create - t_count), 1e3 * (t_load - t_create),
+            1e3 * (now_s() - t_load), res.expand_ms, res.kernel_ms);
   }
   int32_t *vals = malloc((size ? size : 1) * sizeof(int32_t));
   for (int32_t i = 0; i < res.n_stored; i++) {

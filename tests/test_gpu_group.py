@@ -31,9 +31,10 @@ def test_group_counts_equal_single_gpu(n_dev):
     # a tree large enough that every device is still searching when the others arrive (config 3)
     m = cb.Model(I.queens(15))
     g.load(m)
-    r, per = g.solve()
-    assert (r.solutions, r.nodes, r.cuts) == (2279184, 125900250, 96700627)
-    assert all(p.nodes > r.nodes // (4 * n_dev) for p in per)          # every device searched its share of the ONE frontier
+    for _ in range(2):
+        r, per = g.solve()
+        assert (r.solutions, r.nodes, r.cuts) == (2279184, 125900250, 96700627)
+    assert all(p.nodes > r.nodes // (4 * n_dev) for p in per), [p.nodes for p in per]   # every device searched its share of the ONE frontier
     g.close()
 
 
