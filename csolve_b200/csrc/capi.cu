@@ -322,6 +322,7 @@ extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device
   DevModel &d = p->dev;
   d = p->cm.host;
   if (getenv("CSOLVE_NO_LOV")) { d.lov = 0; d.lovk = 0; d.frame_words = frame_words(d.n_vars, d.mask_words); }   // development switch: general kernels only
+  if (getenv("CSOLVE_NO_SAT")) d.sat = 0;
   std::vector<unsigned char> image;
   struct Part { size_t off; const void *src; size_t bytes; const void **field; };
   std::vector<Part> parts;
@@ -334,7 +335,7 @@ extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device
 #define UP(field, vec) add(p->cm.vec.data(), p->cm.vec.size() * sizeof(p->cm.vec[0]), (const void **)&d.field)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
   UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst);
-  UP(lin, lin); UP(lin_term, lin_term);
+  UP(lin, lin); UP(lin_term, lin_term); UP(sat_occ_ptr, sat_occ_ptr); UP(sat_occ, sat_occ);
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
 #undef UP
@@ -442,7 +443,8 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
   DevModel m = p->dev;
   if (batch) m.lov = 0;
   const bool sample = opt.sample_mod != 0u;
-  const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0) + (sample ? 128 : 0);
+  const bool sat = !batch && search_uses_sat(m, learn, opt.order);
+  const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0) + (sample ? 128 : 0) + (sat ? 256 : 0);
   if (p->stacks != nullptr && p->ws_lov != ws_key) {
     // the lane-owns-variable and the general kernels have different occupancies: rebuild the per-warp state
     C->release(p->stacks, p->stacks_bytes); C->cfree(p->wstate); C->cfree(p->wcount); C->cfree(p->totals); C->cfree(p->ctl); C->cfree(p->scratch);
@@ -450,7 +452,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
   }
   if (p->stacks == nullptr) {
     p->ws_lov = ws_key;
-    int per_sm = search_blocks_per_sm(m, false, learn, sample);
+    int per_sm = search_blocks_per_sm(m, false, learn, sample, sat);
     if (per_sm <= 0) return fail(CSOLVE_ERR_CUDA, "search kernel does not fit on the device (shared memory per node too large)");
     p->grid = per_sm * C->sm_count;
     p->n_warps = p->grid * WARPS_PER_BLOCK;
@@ -643,6 +645,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   a.solbuf = p->solbuf; a.max_solutions = p->sol_cap; a.n_warps = p->n_warps; a.order = opt.order;
   a.out_cap = p->pool_cap; a.expand_branch_max = 64;
   a.inst_solutions = d_rsol;
+  a.use_sat = !batch && search_uses_sat(m, learn, opt.order) ? 1 : 0;
   int part_rank = opt.part_rank, part_count = opt.part_count;
   const bool sinking = p->sink != nullptr && m.objective == CSOLVE_OBJ_ALL && !batch;
   if (sinking) a.sink_headroom = sink_headroom(p->n_warps);

@@ -312,6 +312,42 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     }
   }
 
+  // ---- "bit state" tables (pure SAT) ----
+  {
+    bool sat = V >= 1 && V <= 1024 && m.obj_var < 0 && C > 0;
+    for (int v = 0; v < V && sat; v++) if (m.var_lo[v] < 0 || m.var_hi[v] > 1) sat = false;
+    for (int c = 0; c < C && sat; c++) {
+      const ClauseRec &rec = out.clause[c];
+      if ((rec.kind & 0xff) != CK_LITS) { sat = false; break; }
+      const int32_t lit[3] = {rec.a, rec.b, rec.c};
+      // a literal over a variable that is a value at root would never be visited by an assignment event
+      for (int k = 0; k < (rec.kind >> 8); k++) if (m.var_lo[lit[k] >> 1] == m.var_hi[lit[k] >> 1]) sat = false;
+    }
+    out.sat_occ_ptr.assign(2 * (size_t)V + 1, 0);
+    out.sat_occ.clear();
+    if (sat) {
+      std::vector<std::vector<int2_t>> occ(2 * (size_t)V);
+      for (int c = 0; c < C; c++) {
+        const ClauseRec &rec = out.clause[c];
+        const int n = rec.kind >> 8;
+        const int32_t lit[3] = {rec.a, rec.b, rec.c};
+        for (int k = 0; k < n; k++) {
+          int2_t o{-1, -1};
+          int q = 0;
+          for (int j = 0; j < n; j++) if (j != k) { (q == 0 ? o.x : o.y) = lit[j]; q++; }
+          // the literal var << 1 | negated is false when var == negated: that assignment event visits the clause
+          occ[(size_t)lit[k]].push_back(o);
+        }
+      }
+      for (size_t e = 0; e < occ.size(); e++) {
+        out.sat_occ_ptr[e] = (int32_t)out.sat_occ.size();
+        out.sat_occ.insert(out.sat_occ.end(), occ[e].begin(), occ[e].end());
+      }
+      out.sat_occ_ptr[2 * (size_t)V] = (int32_t)out.sat_occ.size();
+    }
+    out.host.sat = sat ? 1 : 0;
+  }
+
   // static branching order: priority descending, index ascending (the reference's heap with
   // -o none -f true orders by env_t.prio only, src/strategy.c:79-121)
   out.order.resize(V);
@@ -344,6 +380,14 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   {
     const size_t bytes = out.wrec.size() * sizeof(WatchRec) + (size_t)(V + 1) * sizeof(int32_t);
     h.table_smem_bytes = bytes <= 40 * 1024 ? (int32_t)((bytes + 15) & ~(size_t)15) : 0;
+  }
+  h.sat_occ_ptr = out.sat_occ_ptr.data();
+  h.sat_occ = out.sat_occ.data();
+  h.n_sat_occ = (int32_t)out.sat_occ.size();
+  {
+    // occurrence records + their index + the static order (16-bit) + the root state (two bit vectors)
+    const size_t bytes = out.sat_occ.size() * sizeof(int2_t) + (2 * (size_t)V + 1) * sizeof(int32_t) + (size_t)V * 2 + 2 * (size_t)h.mask_words * 4;
+    h.sat_smem_bytes = (h.sat && bytes <= 64 * 1024) ? (int32_t)((bytes + 15) & ~(size_t)15) : 0;
   }
   h.n_lin = (int32_t)out.lin.size();
   h.lin = out.lin.data();

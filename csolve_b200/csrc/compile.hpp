@@ -17,6 +17,8 @@ struct CompiledModel {
   std::vector<uint32_t> lov_fconst;
   std::vector<int32_t> watch_ptr, watch_idx, node_l, node_r, node_first, order, prio, root_dom;
   std::vector<uint8_t> node_op;
+  std::vector<int32_t> sat_occ_ptr;
+  std::vector<int2_t> sat_occ;
   std::vector<LinClause> lin;
   std::vector<LinTerm> lin_term;
 };

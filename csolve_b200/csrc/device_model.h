@@ -55,6 +55,8 @@ static const int MAX_LIN = 32;          // linear clauses per model (a dirty bit
 // csolve_gpu_load() rejects deeper models (CSOLVE_ERR_UNSUPPORTED).
 static const int MAX_DEPTH = 48;
 
+struct int2_t { int32_t x, y; };
+
 struct DevModel {
   int32_t n_vars, n_clauses, n_nodes, n_watch;
   int32_t objective, obj_var;
@@ -84,6 +86,15 @@ struct DevModel {
   const int32_t *lov_cptr;   // [n_vars + 1]
   const int32_t *lov_cval;   // [n_lov_cval]
   const uint32_t *lov_fconst; // [n_vars] forbidden-value set of the constants (lov_bits)
+  // "bit state" form (pure SAT: every variable's root domain lies in [0,1], every clause is a disjunction of at most
+  // three literals): sat_occ_ptr[e] .. sat_occ_ptr[e + 1], e = var << 1 | value, are the clauses in which the
+  // assignment var := value falsifies a literal; each record holds the clause's OTHER literals (code = var << 1 |
+  // negated, -1 = none)
+  int32_t sat;               // 1 when the model is eligible
+  int32_t n_sat_occ;
+  int32_t sat_smem_bytes;    // bytes needed to stage the occurrence table, the order and the root state (0 = table stays in global memory)
+  const int32_t *sat_occ_ptr;   // [2 * n_vars + 1]
+  const int2_t *sat_occ;        // [n_sat_occ]
   int32_t n_lin;             // linear clauses (watch records WK_GENERIC with n == 2, arg = index into lin[])
   const LinClause *lin;      // [n_lin]
   const LinTerm *lin_term;   // terms of all linear clauses

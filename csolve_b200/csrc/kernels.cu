@@ -2203,6 +2203,501 @@ k_root_frames_lovk(const DevModel m, int n_roots, const int32_t *root_dom, int o
   }
 }
 
+// =====================================================================================================
+// "Bit state" search kernel for pure SAT models (DevModel::sat: every variable 0/1, every clause a disjunction of at
+// most three literals -- what scripts/cnf2csolve produces, BASELINE config 5).
+//
+// On such a model an interval is one of [0,0], [1,1], [0,1], and the reference's contractors are unit propagation
+// (contract_lits above; src/propagate.c:320-376). A node's whole domain vector is two bit vectors -- assigned, value --
+// that live in REGISTERS: lane w holds word w of each (V <= 1024). Nothing is copied per node:
+//   * a decision and everything it implies is appended to the warp's trail (shared memory, 16-bit literal codes) and
+//     the trail itself is the propagation queue: four pending assignments are expanded per step, eight lanes each,
+//     every lane looking at one clause in which the assignment falsified a literal (the clause's two OTHER literals
+//     come with the occurrence record: two shuffles each tell their state); unit literals found by the 32 lanes are
+//     gathered with a ballot and applied one after the other (two lanes may force the same variable, also to
+//     different values: that is the reference's empty intersection, src/propagate.c:57-66);
+//   * a failed node restores the two words from the copy taken before the decision (registers); only when a decision
+//     has no value left is the trail undone entry by entry down to the previous decision;
+//   * the DFS stack is a list of decision records (variable, trail position, level, values left): 8 bytes a level.
+// Levels, node counts and the order of decisions are exactly those of k_search (static order: a level per variable in
+// DevModel::order, levels of variables that already are a value are one never-failing node each -- counted here by
+// position, without executing them; with failure-driven priorities: highest priority among the open variables).
+// The HBM frame format is spoken at the edges only: frames claimed from the frontier / donation ring are turned into
+// bit vectors, a donated or parked decision is turned into a frame (the state before it is replayed from the trail).
+// Parked frames are a private LIFO in the warp's HBM stack: a resumed warp pops them like claimed frames.
+static const int SAT_FRAME_BITS = 0x5A7B175;      // header word 6 of a frame whose domain area holds the two bit vectors
+#ifndef SAT_DONATE_MIN
+#define SAT_DONATE_MIN 32
+#endif
+struct SatRec { unsigned short var, trail, pos; unsigned char nxt, cnt; };     // 8 bytes: one decision level
+
+__host__ __device__ __forceinline__ int sat_table_words(const DevModel &m) {
+  int o = (m.n_vars * 2 + 3) / 4;            // order16
+  o += 2 * m.mask_words;                     // root_asg, root_val
+  o = (o + 1) & ~1;
+  if (m.sat_smem_bytes > 0) {
+    o += 2 * m.n_vars + 1; o = (o + 1) & ~1;
+    o += 2 * m.n_sat_occ;
+  }
+  return (o + 3) & ~3;
+}
+__host__ __device__ __forceinline__ int sat_warp_words(const DevModel &m) {
+  return (((m.n_vars * 2 + 3) / 4 + 1) & ~1) + 3 * (m.n_vars + 1);      // trail (16-bit), decision records, entry counters
+}
+
+template <bool SAMPLE>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, 4)
+k_search_sat(const SearchArgs a) {
+  extern __shared__ __align__(16) int smem[];
+  const DevModel &m = a.m;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+  __shared__ int s_blk_hungry;
+  const int V = m.n_vars, W = m.mask_words, fw = m.frame_words;
+  const int dofs = frame_dom_offset(W);
+
+  // ---- block: tables into shared memory -------------------------------------------------------------------------
+  unsigned short *order16 = reinterpret_cast<unsigned short *>(smem);
+  int o = (V * 2 + 3) / 4;
+  unsigned *root_asg = reinterpret_cast<unsigned *>(smem + o), *root_val = root_asg + W;
+  o += 2 * W; o = (o + 1) & ~1;
+  const int *optr = m.sat_occ_ptr;
+  const int2 *occ = reinterpret_cast<const int2 *>(m.sat_occ);
+  if (threadIdx.x == 0) s_blk_hungry = 0;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    const int rem = V - (i << 5);
+    root_asg[i] = rem >= 32 ? 0u : ~((1u << rem) - 1u);     // bits beyond V count as assigned
+    root_val[i] = 0u;
+  }
+  for (int i = threadIdx.x; i < V; i += blockDim.x) order16[i] = (unsigned short)__ldg(&m.order[i]);
+  if (m.sat_smem_bytes > 0) {
+    int *sp = smem + o;
+    for (int i = threadIdx.x; i <= 2 * V; i += blockDim.x) sp[i] = __ldg(&m.sat_occ_ptr[i]);
+    o += 2 * V + 1; o = (o + 1) & ~1;
+    int2 *so = reinterpret_cast<int2 *>(smem + o);
+    for (int i = threadIdx.x; i < m.n_sat_occ; i += blockDim.x) so[i] = __ldg(reinterpret_cast<const int2 *>(m.sat_occ) + i);
+    optr = sp; occ = so;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const int lo = __ldg(&m.root_dom[2 * i]), hi = __ldg(&m.root_dom[2 * i + 1]);
+    if (lo == hi) { atomicOr(&root_asg[i >> 5], 1u << (i & 31)); if (lo == 1) atomicOr(&root_val[i >> 5], 1u << (i & 31)); }
+  }
+  __syncthreads();
+  if (gw >= a.n_warps) return;
+
+  // ---- warp --------------------------------------------------------------------------------------------------------
+  int *wbase = smem + sat_table_words(m) + wib * sat_warp_words(m);
+  unsigned short *trail = reinterpret_cast<unsigned short *>(wbase);
+  SatRec *drec = reinterpret_cast<SatRec *>(wbase + (((V * 2 + 3) / 4 + 1) & ~1));
+  unsigned *dentry = reinterpret_cast<unsigned *>(drec + (V + 1));     // node counter when a level's current value was entered
+  int *stack = a.stacks + (size_t)gw * (V + 1) * fw;
+  SearchCtl *ctl = a.ctl;
+  const bool dynamic = a.gprio != nullptr;
+
+  unsigned asg = lane < W ? root_asg[lane] : 0xffffffffu, val = lane < W ? root_val[lane] : 0u;
+  unsigned pa = asg, pv = val;             // state before the top decision (valid while `snap`)
+  unsigned ba = asg, bv = val;             // state the current frame was loaded with (trail position 0)
+  bool snap = false;
+  int depth = -1, tlen = 0;
+  int tvar = 0, ttrail = 0, tpos = 0, tnxt = 0, tcnt = 0;      // top decision record
+  unsigned n32 = 0;                        // nodes since the kernel started (32 bits are plenty inside one slice)
+  int parked = a.wstate[gw].level;         // top of the private LIFO of parked frames (-1: empty)
+  Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
+  unsigned long long nodes = 0, cuts = 0, sols = 0;
+  unsigned props = 0, visits = 0, poll = 0;
+  const long long t0 = clock64();
+  long long waited = 0, lastwork = -1;
+  unsigned claims = 0, dbg_donated = 0;
+  bool hungry = false;
+
+  // state of literal code c (var << 1 | negated): 0 open, 1 true, 2 false (two shuffles; c < 0: "false")
+  auto lit_state = [&](int c) {
+    const int v = c >= 0 ? c >> 1 : 0;
+    const unsigned aw = __shfl_sync(FULL, asg, v >> 5), vw = __shfl_sync(FULL, val, v >> 5);
+    if (c < 0) return 2;
+    if (!((aw >> (v & 31)) & 1u)) return 0;
+    return (int)((vw >> (v & 31)) & 1u) != (c & 1) ? 1 : 2;
+  };
+  // bit vectors -> lo,hi pairs of variables lane, lane + 32, ... written to dst (2 * V words)
+  auto write_domains = [&](unsigned xa, unsigned xv, int *dst, bool global) {
+    for (int k = 0; k < W; k++) {
+      const unsigned aw = __shfl_sync(FULL, xa, k), vw = __shfl_sync(FULL, xv, k);
+      const int v = (k << 5) + lane;
+      if (v < V) {
+        const int b = (int)((vw >> lane) & 1u);
+        const int2 d = ((aw >> lane) & 1u) ? make_int2(b, b) : make_int2(0, 1);
+        if (global) __stcg(reinterpret_cast<int2 *>(dst) + v, d); else reinterpret_cast<int2 *>(dst)[v] = d;
+      }
+    }
+  };
+  // state after the first `upto` trail entries of the current frame
+  auto prefix_state = [&](int upto, unsigned &xa, unsigned &xv) {
+    xa = ba; xv = bv;
+    for (int i = 0; i < upto; i++) {
+      const int l = trail[i];
+      if (lane == (l >> 6)) { xa |= 1u << ((l >> 1) & 31); if (l & 1) xv |= 1u << ((l >> 1) & 31); }
+    }
+  };
+  // a decision level with values left -> HBM frame (device_model.h): the state before the decision, its open values
+  auto frame_out = [&](int var, int trail_pos, int pos, int nxt, int cnt, int *g) {
+    unsigned xa, xv;
+    prefix_state(trail_pos, xa, xv);
+    if (lane == 0) {
+      __stcg(reinterpret_cast<int4 *>(g), make_int4(var, 0, cnt - 1, nxt));
+      __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nxt + cnt - 1, pos, 0, 0));
+    }
+    for (int w = lane; w < W; w += 32) __stcg(&g[FR_MASK + w], 0);
+    write_domains(xa, xv, g + dofs, true);
+    __syncwarp();
+  };
+  // the same for a frame that only travels through a donation ring to another warp of this kernel: the two bit vectors
+  // instead of 2 * V domain words (header word 6 says so) -- 56 bytes instead of 1.6 KB for 200 variables
+  auto frame_out_bits = [&](int var, int trail_pos, int pos, int nxt, int cnt, int *g) {
+    unsigned xa, xv;
+    prefix_state(trail_pos, xa, xv);
+    if (lane == 0) {
+      __stcg(reinterpret_cast<int4 *>(g), make_int4(var, 0, cnt - 1, nxt));
+      __stcg(reinterpret_cast<int4 *>(g) + 1, make_int4(nxt + cnt - 1, pos, SAT_FRAME_BITS, 0));
+    }
+    if (lane < W) { __stcg(&g[dofs + lane], (int)xa); __stcg(&g[dofs + W + lane], (int)xv); }
+    __syncwarp();
+  };
+  // identity hash of a state (SAMPLE): same function of the domains as the other kernels'
+  auto state_hash = [&](unsigned xa, unsigned xv) {
+    unsigned h = 0;
+    for (int k = 0; k < W; k++) {
+      const unsigned aw = __shfl_sync(FULL, xa, k), vw = __shfl_sync(FULL, xv, k);
+      const int v = (k << 5) + lane;
+      if (v < V) {
+        const int b = (int)((vw >> lane) & 1u);
+        const bool as = (aw >> lane) & 1u;
+        h ^= mix_hash(0x9E3779B9u + (unsigned)v, (unsigned)(as ? b : 0), (unsigned)(as ? b : 1));
+      }
+    }
+    return __reduce_xor_sync(FULL, h);
+  };
+  auto s_record = [&](int flags, int svar, int sval, unsigned xa0, unsigned xv0, unsigned xa1, unsigned xv1) {
+    int *r = sample_begin(a, lane, flags, svar, sval, 0);
+    if (r == nullptr) return;
+    write_domains(xa0, xv0, r + 4, false);
+    write_domains(xa1, xv1, r + 4 + 2 * V, false);
+    __syncwarp();
+  };
+
+  for (;;) {
+    // ---- poll: stop / slice end / somebody waiting for work ---------------------------------------------------------
+    // (every 16 nodes; every 4 while a warp of this block waits for work: an L2 round trip per node would halve the node rate)
+    if ((++poll & 3u) == 0 && ((poll & 15u) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
+      if (a.n_peers > 0) comm_poll(a, lane);
+      if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
+      if (clock64() - t0 > a.slice_cycles) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);
+        break;
+      }
+      int tgt = -1;
+      if (depth >= 0 && (tgt = donation_target(a, lane)) >= 0) {
+        // Shallowest decision level with a value left: given away whole (a 0/1 level has at most one value besides
+        // the one being searched). Only if this warp has already spent SAT_DONATE_MIN nodes below that level's current
+        // value: sibling sub-trees are of similar size, and handing over one that is finished in a handful of nodes
+        // costs both warps more than it saves (measured on the unsatisfiable seed 1: 61 M hand-offs of 7 nodes each,
+        // three quarters of all warp time spent waiting).
+        int L = -1, dv = 0, dt = 0, dp = 0, dn = 0, dc = 0;
+        for (int q = 0; q < depth && L < 0; q++) {
+          const SatRec r = drec[q];
+          if (r.cnt >= 1) {
+            if (n32 - dentry[q] >= (unsigned)SAT_DONATE_MIN) { L = q; dv = r.var; dt = r.trail; dp = r.pos; dn = r.nxt; dc = r.cnt; }
+            break;
+          }
+        }
+        if (L >= 0) {
+          for (;;) {
+            const int slot = reserve_slot(a, lane, tgt);
+            frame_out_bits(dv, dt, dp, dn, dc, ring_frame(a, tgt, slot));
+            if (publish_slot(a, lane, tgt, slot)) break;
+          }
+          if (lane == 0) drec[L].cnt = 0;
+          dbg_donated++;
+          __syncwarp();
+        }
+        donation_done(a, lane, tgt);
+      }
+    }
+
+    // ---- no decision level: take a frame (parked ones first) --------------------------------------------------------
+    if (depth < 0) {
+      const int *src;
+      int ring_slot = -1;
+      if (parked >= 0) {
+        src = stack + (size_t)parked * fw;
+        parked--;
+      } else {
+        const long long w0 = clock64();
+        lastwork = w0 - t0;
+        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
+        waited += clock64() - w0;
+        if (slot < 0) break;
+        claims++;
+        src = claimed_frame(a, slot);
+        ring_slot = slot;
+      }
+      const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(src));
+      const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(src) + 1);
+      if (h1.z == SAT_FRAME_BITS) {
+        if (lane < W) { asg = (unsigned)__ldcg(&src[dofs + lane]); val = (unsigned)__ldcg(&src[dofs + W + lane]); }
+      } else {
+        for (int k = 0; k < W; k++) {
+          const int v = (k << 5) + lane;
+          int2 d = make_int2(0, 0);
+          if (v < V) d = __ldcg(reinterpret_cast<const int2 *>(src + dofs) + v);
+          const unsigned xa = __ballot_sync(FULL, d.x == d.y), xv = __ballot_sync(FULL, d.x == d.y && d.x == 1);
+          if (lane == k) { asg = xa; val = xv; }
+        }
+      }
+      if (lane >= W) { asg = 0xffffffffu; val = 0u; }
+      // The level's variable is taken as open whatever the frame's domains say: k_rebalance writes the interval a
+      // half owns into them, and re-propagating a variable that already was a value changes nothing (the state is a
+      // fixpoint that contains it).
+      if (lane == (h0.x >> 5)) { asg &= ~(1u << (h0.x & 31)); val &= ~(1u << (h0.x & 31)); }
+      if (ring_slot >= a.n_initial) {
+        __syncwarp();
+        if (lane == 0) { __threadfence(); __stcg(&a.ready[ring_slot], 0); }
+      }
+      __syncwarp();
+      ba = asg; bv = val; pa = asg; pv = val; snap = true;
+      tlen = 0; depth = 0;
+      const unsigned it = (unsigned)h0.y, la = (unsigned)h0.z;
+      tvar = h0.x; ttrail = 0; tpos = h1.y;
+      tnxt = step_value(h0.w, h1.x, it);
+      tcnt = it <= la ? (int)(la - it + 1u) : 0;
+      continue;
+    }
+
+    // ---- top level has no value left: back to the level below ----------------------------------------------------
+    if (tcnt == 0) {
+      depth--;
+      if (depth >= 0) {
+        const SatRec r = drec[depth];
+        tvar = r.var; ttrail = r.trail; tpos = r.pos; tnxt = r.nxt; tcnt = r.cnt;
+      }
+      snap = false;
+      continue;
+    }
+    if (!snap) {
+      // undo the trail down to the state before this level's decision
+      for (int i = tlen - 1; i >= ttrail; i--) {
+        const int l = trail[i];
+        if (lane == (l >> 6)) { asg &= ~(1u << ((l >> 1) & 31)); val &= ~(1u << ((l >> 1) & 31)); }
+      }
+      tlen = ttrail;
+      pa = asg; pv = val; snap = true;
+    }
+
+    // ---- one search node: tvar := b, unit propagation to fixpoint (src/csolve.c:444-457) ---------------------------
+    const int b = tnxt;
+    tnxt = b + 1; tcnt--;
+    nodes++; n32++;
+    bool ok = true;
+    int fail_var = -1;
+    {
+      const unsigned aw = __shfl_sync(FULL, asg, tvar >> 5);
+      const unsigned bit = 1u << (tvar & 31);
+      if (aw & bit) {
+        // the level of a variable that already is a value (a frame of the expanded frontier): nothing to propagate
+        const unsigned vw = __shfl_sync(FULL, val, tvar >> 5);
+        ok = (int)((vw >> (tvar & 31)) & 1u) == b;
+      } else {
+        if (lane == (tvar >> 5)) { asg |= bit; if (b) val |= bit; }
+        if (lane == 0) trail[tlen] = (unsigned short)((tvar << 1) | b);
+        tlen++;
+        __syncwarp();
+        int qh = tlen - 1;
+        while (ok && qh < tlen) {
+          const int li = qh + (lane >> 3);
+          const int ev = li < tlen ? (int)trail[li] : -1;       // assignment event var << 1 | value
+          int i = 0, e = 0;
+          if (ev >= 0) { i = optr[ev] + (lane & 7); e = optr[ev + 1]; }
+          qh = min(qh + 4, tlen);
+          while (__any_sync(FULL, i < e)) {
+            const bool act = i < e;
+            int2 r = make_int2(-1, -1);
+            if (act) r = occ[i];
+            i += 8;
+            const int s0 = lit_state(r.x), s1 = lit_state(r.y);
+            int unit = -1;
+            bool conf = false;
+            if (act && s0 != 1 && s1 != 1) {
+              if (s0 == 2 && s1 == 2) conf = true;
+              else if (s0 == 0 && s1 == 2) unit = r.x;
+              else if (s0 == 2 && s1 == 0) unit = r.y;
+            }
+            visits += act ? 1u : 0u;
+            const unsigned cm = __ballot_sync(FULL, conf);
+            if (cm) { ok = false; fail_var = __shfl_sync(FULL, ev, __ffs((int)cm) - 1) >> 1; break; }
+            unsigned um = __ballot_sync(FULL, unit >= 0);
+            while (um) {
+              const int src = __ffs((int)um) - 1;
+              um &= um - 1u;
+              const int u = __shfl_sync(FULL, unit, src);
+              const int v = u >> 1, want = (u & 1) ^ 1;
+              const unsigned aw2 = __shfl_sync(FULL, asg, v >> 5), vw2 = __shfl_sync(FULL, val, v >> 5);
+              const unsigned bit2 = 1u << (v & 31);
+              if (aw2 & bit2) {
+                if ((int)((vw2 >> (v & 31)) & 1u) != want) { ok = false; fail_var = v; break; }      // forced to 0 and to 1
+                continue;
+              }
+              if (lane == (v >> 5)) { asg |= bit2; if (want) val |= bit2; }
+              if (lane == 0) trail[tlen] = (unsigned short)((v << 1) | want);
+              tlen++;
+              props++;
+            }
+            if (!ok) break;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (dynamic && lane == 0) {
+      // prio-- on success, prio++ on failure, and ++ for the variable whose clauses failed (src/csolve.c:459-462, src/propagate.c:44-54)
+      atomicAdd(&a.gprio[tvar], ok ? -1 : 1);
+      if (!ok && fail_var >= 0) atomicAdd(&a.gprio[fail_var], 1);
+    }
+    unsigned s_hp = 0;
+    bool s_hit = false;
+    if (SAMPLE) {
+      s_hp = state_hash(pa, pv);
+      s_hit = sample_hit(a, s_hp, tvar, b, !ok);
+    }
+    if (!ok) {
+      if (SAMPLE && s_hit) s_record(SAMPLE_FAILED, tvar, b, pa, pv, asg, val);
+      cuts++;
+      asg = pa; val = pv; tlen = ttrail;
+      continue;
+    }
+
+    // ---- the next level ------------------------------------------------------------------------------------------------
+    int nv = -1, npos = V;
+    if (!dynamic) {
+      // first position after tpos whose variable is still open; the positions passed are levels of variables that
+      // are a value: one never-failing node each
+      for (int p0 = tpos + 1; p0 < V; p0 += 32) {
+        const int p = p0 + lane;
+        const int v = p < V ? (int)order16[p] : 0;
+        const unsigned aw = __shfl_sync(FULL, asg, v >> 5);
+        const unsigned open = __ballot_sync(FULL, p < V && !((aw >> (v & 31)) & 1u));
+        if (open) { npos = p0 + __ffs((int)open) - 1; break; }
+      }
+      if (npos < V) nv = order16[npos];
+      const int passed = npos - tpos - 1;
+      if (SAMPLE) {
+        // the node just executed, then the levels counted in bulk; the last level of a complete assignment is the leaf
+        const bool leaf_here = npos >= V && passed == 0;
+        if (s_hit) s_record(leaf_here ? SAMPLE_LEAF : 0, tvar, b, pa, pv, asg, val);
+        if (passed > 0) {
+          const unsigned hs = state_hash(asg, val);
+          for (int p = tpos + 1; p < npos; p++) {
+            const int v = order16[p];
+            const int fv = (int)((__shfl_sync(FULL, val, v >> 5) >> (v & 31)) & 1u);
+            if (sample_hit(a, hs, v, fv, false)) s_record(SAMPLE_COUNTED | ((npos >= V && p == V - 1) ? SAMPLE_LEAF : 0), v, fv, asg, val, asg, val);
+          }
+        }
+      }
+      nodes += (unsigned)passed;
+    } else {
+      // highest failure-driven priority among the open variables, ties: lower index (the levels of the variables this
+      // node made a value are counted here: one node each)
+      unsigned long long bestk = ~0ull;
+      for (int k = 0; k < W; k++) {
+        const unsigned aw = __shfl_sync(FULL, asg, k);
+        const int v = (k << 5) + lane;
+        if (v < V && !((aw >> lane) & 1u)) {
+          const unsigned key = ~((unsigned)__ldcg(&a.gprio[v]) ^ 0x80000000u);
+          const unsigned long long kk = ((unsigned long long)key << 32) | (unsigned)v;
+          if (kk < bestk) bestk = kk;
+        }
+      }
+#pragma unroll
+      for (int q = 16; q > 0; q >>= 1) {
+        const unsigned long long ok2 = __shfl_xor_sync(FULL, bestk, q);
+        if (ok2 < bestk) bestk = ok2;
+      }
+      if (bestk != ~0ull) { nv = (int)(unsigned)bestk; npos = 0; }
+      if (SAMPLE && s_hit) s_record(nv < 0 ? SAMPLE_LEAF : 0, tvar, b, pa, pv, asg, val);
+      nodes += (unsigned)(tlen - ttrail > 0 ? tlen - ttrail - 1 : 0);
+    }
+
+    if (nv < 0) {
+      // every variable is a value and no clause failed: an accepted leaf (src/csolve.c:222-244)
+      bool accepted = true;
+      if (m.objective == CSOLVE_OBJ_ANY) {
+        int old = 0;
+        if (lane == 0) old = atomicMax(&ctl->signal, SIG_STOP);
+        old = __shfl_sync(FULL, old, 0);
+        accepted = old != SIG_STOP;
+        if (accepted && a.n_peers > 0) comm_push_stop(a, lane);
+      }
+      if (accepted) {
+        sols++;
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&ctl->n_stored, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot < a.max_solutions) {
+          int *dst = a.solbuf + (size_t)slot * (V + 1);
+          for (int k = 0; k < W; k++) {
+            const unsigned vw = __shfl_sync(FULL, val, k);
+            const int v = (k << 5) + lane;
+            if (v < V) dst[v] = (int)((vw >> lane) & 1u);
+          }
+          if (lane == 0) dst[V] = 0;
+        }
+        __syncwarp();
+      }
+      asg = pa; val = pv; tlen = ttrail;          // the leaf's level is done: on with the next value of this one
+      continue;
+    }
+    // push
+    if (lane == 0) {
+      SatRec r; r.var = (unsigned short)tvar; r.trail = (unsigned short)ttrail; r.pos = (unsigned short)tpos;
+      r.nxt = (unsigned char)tnxt; r.cnt = (unsigned char)tcnt;
+      drec[depth] = r;
+      dentry[depth] = n32;
+    }
+    depth++;
+    tvar = nv; ttrail = tlen; tpos = npos; tnxt = 0; tcnt = 2;
+    pa = asg; pv = val; snap = true;
+    __syncwarp();
+  }
+
+  // ---- park: every level with values left becomes a frame of the private LIFO (shallowest first) -----------------
+  if (depth >= 0) {
+    if (lane == 0) {
+      SatRec r; r.var = (unsigned short)tvar; r.trail = (unsigned short)ttrail; r.pos = (unsigned short)tpos;
+      r.nxt = (unsigned char)tnxt; r.cnt = (unsigned char)tcnt;
+      drec[depth] = r;
+    }
+    __syncwarp();
+    for (int q = 0; q <= depth; q++) {
+      const SatRec r = drec[q];
+      if (r.cnt == 0) continue;
+      parked++;
+      frame_out(r.var, r.trail, r.pos, r.nxt, r.cnt, stack + (size_t)parked * fw);
+    }
+  }
+#pragma unroll
+  for (int q = 16; q > 0; q >>= 1) visits += __shfl_xor_sync(FULL, visits, q);
+  if (lane == 0) {
+    a.wstate[gw].level = parked;
+    a.wstate[gw].base = 0;
+    a.wstate[gw].claim_base = cl.base; a.wstate[gw].claim_mask = cl.mask;
+    unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
+    c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;
+    c[CNT_VISITS] += visits; c[CNT_SOLUTIONS] += sols;
+    c[CNT_WAIT] += (unsigned long long)waited; c[CNT_CLAIMS] += claims; c[CNT_DONATED] += dbg_donated;
+    c[CNT_LASTWORK] = (unsigned long long)(lastwork >= 0 ? lastwork : clock64() - t0);
+  }
+}
+
 // ---- rebalance -----------------------------------------------------------------------------------
 // One block. Idle warps (level < base) are paired with busy warps that own a frame with at
 // least two untried values; the donor keeps the lower half of the untried interval, the idle
@@ -2507,7 +3002,13 @@ k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order,
 }
 
 // ---- host-side launch wrappers -----------------------------------------------------------------------
-size_t search_smem_bytes(const DevModel &m, bool learn) {
+// does the depth-first phase of this search run on the bit-state kernel?
+bool search_uses_sat(const DevModel &m, bool learn, int order) {
+  return m.sat && !learn && order == CSOLVE_ORDER_NONE && !m.lov && !m.lovk;
+}
+
+size_t search_smem_bytes(const DevModel &m, bool learn, bool sat) {
+  if (sat) return (size_t)(sat_table_words(m) + WARPS_PER_BLOCK * sat_warp_words(m)) * sizeof(int);
   if (learn) {
     const int wwords = (warp_smem_words(m, true) + 3) & ~3;
     return (size_t)m.table_smem_bytes + (size_t)wwords * sizeof(int) * WARPS_PER_BLOCK;
@@ -2540,7 +3041,8 @@ static const void *general_kernel(bool expand, bool lin) {
 }
 
 // the kernel instance a search runs on (sample: the parity-instrumented instances, never with learning)
-static const void *search_kernel(const DevModel &m, bool expand, bool learn, bool sample) {
+static const void *search_kernel(const DevModel &m, bool expand, bool learn, bool sample, bool sat = false) {
+  if (sat && !expand) return sample ? (const void *)k_search_sat<true> : (const void *)k_search_sat<false>;
   if (learn) return expand ? (const void *)k_search<true, true> : (const void *)k_search<false, true>;
   if (m.lovk) return sample ? lovk_kernel<true>(expand, m.lovk) : lovk_kernel<false>(expand, m.lovk);
   if (m.lov) return sample ? lov_kernel<true>(expand, m.lov_bits != 0) : lov_kernel<false>(expand, m.lov_bits != 0);
@@ -2554,10 +3056,10 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 bool search_learns(const SearchArgs &a) { return a.ng.lits != nullptr; }
 
-int search_blocks_per_sm(const DevModel &m, bool expand, bool learn, bool sample) {
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn, bool sample, bool sat) {
   int n = 0;
-  const size_t smem = search_smem_bytes(m, learn);
-  const void *fn = search_kernel(m, expand, learn, sample);
+  const size_t smem = search_smem_bytes(m, learn, sat && !expand);
+  const void *fn = search_kernel(m, expand, learn, sample, sat);
   if (ensure_smem(fn, smem) != cudaSuccess) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem) != cudaSuccess) return 0;
   return n;
@@ -2565,8 +3067,9 @@ int search_blocks_per_sm(const DevModel &m, bool expand, bool learn, bool sample
 
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
   const bool learn = search_learns(a);
-  const size_t smem = search_smem_bytes(a.m, learn);
-  const void *fn = search_kernel(a.m, expand, learn, a.sample_mod != 0u);
+  const bool sat = a.use_sat != 0 && !expand;
+  const size_t smem = search_smem_bytes(a.m, learn, sat);
+  const void *fn = search_kernel(a.m, expand, learn, a.sample_mod != 0u, sat);
   cudaError_t e = ensure_smem(fn, smem);
   if (e != cudaSuccess) return e;
   void *args[] = {(void *)&a};

@@ -118,6 +118,7 @@ struct SearchArgs {
   int32_t out_cap;            // expand mode: capacity of the output pool (frames)
   int32_t *solbuf;            // [max_solutions][n_vars + 1]  (values..., objective key)
   int32_t max_solutions;
+  int32_t use_sat;            // the depth-first phase runs on k_search_sat (pure SAT model, static or failure-driven order)
   int32_t sink_headroom;      // > 0: the host drains the solution buffer between slices (csolve_gpu_set_solution_sink): a
                               // slice ends as soon as fewer than this many entries are free
   int32_t n_warps;
@@ -166,7 +167,8 @@ static const int SAMPLE_COUNTED = 2;   // the node was counted by a bulk shortcu
 static const int SAMPLE_LEAF = 4;      // the node is an accepted leaf (every variable a value, every clause true)
 CSOLVE_HOSTDEV static inline int sample_words(int n_vars) { return 4 + 4 * n_vars; }
 
-size_t search_smem_bytes(const DevModel &m, bool learn = false);
+size_t search_smem_bytes(const DevModel &m, bool learn = false, bool sat = false);
+bool search_uses_sat(const DevModel &m, bool learn, int order);
 cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s);
 bool search_learns(const SearchArgs &a);
 cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t s);
@@ -180,7 +182,7 @@ cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps
 cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t s);
-int search_blocks_per_sm(const DevModel &m, bool expand, bool learn = false, bool sample = false);
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn = false, bool sample = false, bool sat = false);
 cudaError_t launch_root_frames(const DevModel &m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
                                int out_cap, int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t s);
 

@@ -48,6 +48,8 @@ if "wcet" in args:
 if "sat" in args:
     for seed in (1, 2, 3):
         run("sat200 seed %d" % seed, I.random_3sat(200, seed=seed), prefer_failing=True)
+if "satstatic" in args:
+    run("sat200 seed 1 static", I.random_3sat(200, seed=1), reps=1)
 if "sudoku" in args:
     grids = I.sudoku_batch(10000, base=50)
     m = cb.Model(I.sudoku("." * 81))
