@@ -266,7 +266,9 @@ def run_ours(args):
     objective = {"queens": cb.OBJ_ALL, "wcet": cb.OBJ_MAX, "sat200": cb.OBJ_ANY}[args.workload]
     solve_kw = dict(order=order)
     if args.workload == "sat200":
-        solve_kw["prefer_failing"] = True
+        solve_kw["prefer_failing"] = True          # the reference's defaults: -f true ...
+        if world == 1:
+            solve_kw["restart_frequency"] = 100    # ... -r 100 (Luby restarts; single-GPU searches only)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def one_step():

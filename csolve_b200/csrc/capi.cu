@@ -245,6 +245,7 @@ struct csolve_gpu_problem {
   csolve_rebalance_fn rebalance = nullptr;
   void *rebalance_user = nullptr;
   const SearchArgs *parked = nullptr;   // search arguments while the rebalance callback runs (export / import are valid)
+  bool order_dirty = false;             // a restart rewrote the device copy of the static order (restored by the next solve)
 
   ~csolve_gpu_problem() {
     DeviceCtx *C = ctx;
@@ -594,6 +595,10 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   const int V = m.n_vars, fw = m.frame_words;
   cudaStream_t st = p->stream;
   const auto wall0 = std::chrono::steady_clock::now();
+  if (p->order_dirty) {
+    CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t *>(m.order), cm.order.data(), (size_t)m.n_vars * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    p->order_dirty = false;
+  }
 
   // ---- initial state ----------------------------------------------------------------------------
   SearchCtl ctl;
@@ -605,10 +610,10 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
 
   int32_t *d_roots = nullptr; unsigned char *d_rfail = nullptr; unsigned int *d_rsol = nullptr; int32_t *d_nout = nullptr;
   ScopeExit batch_guard([&]() { C->cfree(d_roots); C->cfree(d_rfail); C->cfree(d_rsol); C->cfree(d_nout); });
-  if (!batch) {
-    // root frame
+  // the root frame (root_var < 0: the configured order's first variable)
+  auto upload_root_frame = [&](int root_var) -> int {
     std::vector<int32_t> root(fw, 0);
-    const int rv = select_root_var(cm, opt.order);
+    const int rv = root_var >= 0 ? root_var : select_root_var(cm, opt.order);
     root[FR_VAR] = rv; root[FR_ITER] = 0;
     root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
     root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
@@ -616,7 +621,13 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
     if (m.lovk) memcpy(&root[frame_dom_offset(m.mask_words) + 2 * V], cm.lov_fconst.data(), sizeof(int32_t) * V);   // value sets
     CUDA_TRY(cudaMemcpyAsync(p->pool_a, root.data(), fw * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));            // `root` goes out of scope
     ctl.item_count = 1;
+    return CSOLVE_OK;
+  };
+  if (!batch) {
+    rc = upload_root_frame(-1);
+    if (rc != CSOLVE_OK) return rc;
   } else {
     // root phase on the device: propagate every root to fixpoint, emit one tagged frame per consistent root
     const size_t rb = (size_t)n_roots * 2 * V * sizeof(int32_t);
@@ -848,6 +859,16 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   } else {
     CUDA_TRY(cudaMemcpyAsync(dctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
   }
+  // ---- restarts (src/csolve.c:76-83, 264-276): Knuth's rendering of the Luby sequence, one unit = restart_frequency
+  //      failed nodes per search warp; see csolve_solve_options.restart_frequency
+  const bool restarting = opt.restart_frequency > 0 && m.objective == CSOLVE_OBJ_ANY && d_gprio != nullptr && c == nullptr && !batch && !learn;
+  unsigned long long luby_counter = 1, luby_threshold = 1;
+  uint64_t n_restarts = 0;
+  auto fail_limit_now = [&]() {
+    const double lim = (double)luby_threshold * (double)opt.restart_frequency * (double)p->n_warps;
+    return (int32_t)std::min(lim, 2.0e9);
+  };
+  if (restarting) a.fail_limit = fail_limit_now();
   int idle_now = p->n_warps;          // every warp starts without a stack
   int busy = 0;
   bool timed_out = false;
@@ -872,6 +893,36 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       busy = ctl.busy;
       idle_now = p->n_warps - busy;
       if (ctl.signal == SIG_STOP || ctl.busy == 0) local_done = true;
+      if (restarting && !local_done && ctl.fails > a.fail_limit) {
+        // RESTART (src/csolve.c:380-385): every open frame is dropped, the root is expanded again -- its top levels now
+        // in the order of the failure-driven priorities the search has learned (they survive, src/csolve.c:459-462)
+        if ((luby_counter & (~luby_counter + 1)) == luby_threshold) { luby_counter++; luby_threshold = 1; } else { luby_threshold <<= 1; }
+        n_restarts++;
+        std::vector<int32_t> gp(V), ord(V);
+        CUDA_TRY(cudaMemcpyAsync(gp.data(), d_gprio, (size_t)V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int v = 0; v < V; v++) ord[v] = v;
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return gp[x] > gp[y]; });
+        CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t *>(m.order), ord.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        p->order_dirty = true;
+        rc = upload_root_frame(ord[0]);
+        if (rc != CSOLVE_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(p->wstate, ws.data(), ws.size() * sizeof(WarpState), cudaMemcpyHostToDevice, st));
+        pin = p->pool_a; pout = p->pool_b; n_items = 1;
+        a.gprio = nullptr; a.fail_limit = 0;
+        ctl.signal = SIG_RUN;
+        rc = expand_root();
+        if (rc != CSOLVE_OK) return rc;
+        a.items = pin; a.items_out = nullptr;
+        a.pool = pin; a.front_pool = pin; a.n_initial = n_items; a.gprio = d_gprio;
+        a.fail_limit = fail_limit_now();
+        CUDA_TRY(cudaMemsetAsync(p->ready, 0, (size_t)p->pool_cap * sizeof(int32_t), st));
+        if (p->pool_cap - n_items < ring_min_frames(p->n_warps)) return fail(CSOLVE_ERR_CAPACITY, "no room for donated frames behind the root frontier");
+        ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0; ctl.fails = 0;
+        if (ctl.signal == SIG_STOP || n_items == 0) local_done = true;      // the expansion itself found a solution / emptied the tree
+        CUDA_TRY(cudaMemcpyAsync(dctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+      }
       if (!local_done && opt.time_limit_ms > 0) {
         const auto now = std::chrono::steady_clock::now();
         if (std::chrono::duration_cast<std::chrono::milliseconds>(now - wall0).count() > opt.time_limit_ms) { timed_out = true; local_done = true; }
@@ -1011,6 +1062,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   res->kernel_ms = ms_search;
   res->expand_ms = ms_expand;
   res->kernel_launches = launches;
+  res->restarts = n_restarts;
   if (learn) {
     int32_t cnt[8];
     CUDA_TRY(cudaMemcpy(cnt, p->ng.counters, sizeof(cnt), cudaMemcpyDeviceToHost));

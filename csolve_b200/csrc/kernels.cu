@@ -626,6 +626,21 @@ __device__ __forceinline__ bool publish_slot(const SearchArgs &a, int lane, int 
   return __shfl_sync(FULL, ok, 0) != 0;
 }
 
+// restarts (src/csolve.c:264-276): the warps report their failed nodes at every poll; the slice ends for everybody when
+// the device-wide count passes the limit (the host restarts the search from the root, src/csolve.c:380-385).
+// `reported`: this warp's failed nodes already added to the count. Returns true when the limit is reached.
+__device__ __forceinline__ bool restart_due(const SearchArgs &a, int lane, unsigned long long cuts, unsigned long long &reported) {
+  int due = 0;
+  if (lane == 0) {
+    const int delta = (int)(cuts - reported);
+    const int before = delta > 0 ? atomicAdd(&a.ctl->fails, delta) : *reinterpret_cast<volatile int *>(&a.ctl->fails);
+    due = before + delta > a.fail_limit;
+    if (due) atomicMax(&a.ctl->signal, SIG_SLICE_END);
+  }
+  reported = cuts;
+  return __shfl_sync(FULL, due, 0) != 0;
+}
+
 // frame of a claimed slot: the first n_initial slots are the root frontier (possibly on another GPU), the rest the ring
 __device__ __forceinline__ const int *claimed_frame(const SearchArgs &a, int slot) {
   return (slot < a.n_initial ? a.front_pool : a.pool) + (size_t)slot * a.m.frame_words;
@@ -689,7 +704,7 @@ k_search(const SearchArgs a) {
 
   int level = a.wstate[gw].level, base = a.wstate[gw].base;
   Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
-  unsigned long long nodes = 0, cuts = 0, sols = 0, refresh = 0;
+  unsigned long long nodes = 0, cuts = 0, sols = 0, refresh = 0, cuts_reported = 0;
   unsigned props = 0, visits = 0;
   const long long t0 = clock64();
   long long waited = 0, lastwork = -1;     // load-balance diagnostics (CSOLVE_DEBUG)
@@ -942,6 +957,7 @@ k_search(const SearchArgs a) {
     // dominate the short nodes of the lane-owns-variable kernel, which polls every POLL_NODES nodes)
     if (!EXPAND && ((++poll & 3u) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
       if (a.n_peers > 0) comm_poll(a, lane);
+      if (a.fail_limit > 0 && restart_due(a, lane, cuts, cuts_reported)) break;
       if (a.sink_headroom > 0 && *reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions - a.sink_headroom) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);      // the solution buffer is nearly full: let the host drain it
         break;
@@ -2305,7 +2321,7 @@ k_search_sat(const SearchArgs a) {
   unsigned n32 = 0;                        // nodes since the kernel started (32 bits are plenty inside one slice)
   int parked = a.wstate[gw].level;         // top of the private LIFO of parked frames (-1: empty)
   Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
-  unsigned long long nodes = 0, cuts = 0, sols = 0;
+  unsigned long long nodes = 0, cuts = 0, sols = 0, cuts_reported = 0;
   unsigned props = 0, visits = 0, poll = 0;
   const long long t0 = clock64();
   long long waited = 0, lastwork = -1;
@@ -2391,6 +2407,7 @@ k_search_sat(const SearchArgs a) {
     // (every 16 nodes; every 4 while a warp of this block waits for work: an L2 round trip per node would halve the node rate)
     if ((++poll & 3u) == 0 && ((poll & 15u) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
       if (a.n_peers > 0) comm_poll(a, lane);
+      if (a.fail_limit > 0 && restart_due(a, lane, cuts, cuts_reported)) break;
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);

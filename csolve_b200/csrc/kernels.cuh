@@ -46,7 +46,8 @@ struct SearchCtl {
   int32_t out_count;    // expand mode: frames appended to the output frontier
   int32_t out_dropped;  // expand mode: children that did not fit (capacity error)
   int32_t passed;       // expand mode: frames passed through unsplit (domain too large to enumerate)
-  int32_t pad4[28];
+  int32_t fails;        // failed nodes reported by the warps since the last restart (only counted when restarts are on)
+  int32_t pad4[27];
 };
 
 // One process (or host thread) per GPU: what the ranks of a csolve_gpu_comm share. Every rank owns one CommBlock in
@@ -118,6 +119,8 @@ struct SearchArgs {
   int32_t out_cap;            // expand mode: capacity of the output pool (frames)
   int32_t *solbuf;            // [max_solutions][n_vars + 1]  (values..., objective key)
   int32_t max_solutions;
+  int32_t fail_limit;         // > 0: restarts are on (ANY models, src/csolve.c:264-276): the slice ends when the warps have
+                              // reported more failed nodes than this
   int32_t use_sat;            // the depth-first phase runs on k_search_sat (pure SAT model, static or failure-driven order)
   int32_t sink_headroom;      // > 0: the host drains the solution buffer between slices (csolve_gpu_set_solution_sink): a
                               // slice ends as soon as fewer than this many entries are free

@@ -87,7 +87,7 @@ class _GpuResult(C.Structure):
                 ("clause_visits", C.c_uint64), ("best", C.c_int32), ("has_solution", C.c_int32),
                 ("timed_out", C.c_int32), ("n_stored", C.c_int32), ("kernel_ms", C.c_double),
                 ("expand_ms", C.c_double), ("kernel_launches", C.c_uint64), ("conflicts", C.c_uint64),
-                ("conflicts_abandoned", C.c_uint64)]
+                ("conflicts_abandoned", C.c_uint64), ("restarts", C.c_uint64)]
 
 
 # int (*csolve_exchange_fn)(void *user, int32_t *best, int32_t *found, int32_t local_done)

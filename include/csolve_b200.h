@@ -163,7 +163,14 @@ typedef struct csolve_solve_options {
                                 * come out identical. Not available together with create_conflicts. */
   int32_t sample_cap;          /* records kept (0 = 65536); further hits are counted and dropped */
   int32_t restart_frequency;   /* -r (src/main.c:109-113): ANY models restart after restart_frequency * luby(k) failed
-                                * nodes (src/csolve.c:76-83,264-276). 0 = never restart */
+                                * nodes (src/csolve.c:76-83,264-276; Knuth's Luby sequence). On the device one "failed
+                                * node" of the schedule is one per search warp: the whole search goes back to the root
+                                * when the warps together have failed restart_frequency * luby(k) * n_warps times, and
+                                * the root is expanded again in the order of the failure-driven priorities learned so
+                                * far (prefer_failing must be on: without it a restart would rebuild the same tree;
+                                * priorities -- and learned nogoods -- survive a restart as in the reference). Counters
+                                * include the repeated work, like the reference's CALLS. Single-GPU searches only.
+                                * 0 = never restart */
   uint32_t sample_failed_keep; /* of the sampled nodes that failed, keep 1 in sample_failed_keep (0, 1 = all): most nodes fail */
   int32_t reserved2[4];
 } csolve_solve_options;
@@ -183,6 +190,7 @@ typedef struct csolve_gpu_result {
   uint64_t kernel_launches;    /* kernels launched by this call */
   uint64_t conflicts;          /* nogoods learned = CONFL (src/conflict.c:361) */
   uint64_t conflicts_abandoned;/* analyses given up (non-0/1 value involved, too long, pool full) */
+  uint64_t restarts;           /* RESTARTS (src/csolve.c:272) */
 } csolve_gpu_result;
 
 int  csolve_gpu_init(const csolve_gpu_config *cfg);

@@ -82,6 +82,49 @@ def test_config5_random_3sat_n200(seed, sat):
             assert any((val["x%d" % abs(l)] == 1) == (l > 0) for l in cl), cl
 
 
+# status of seeds 1..11 (z3 for 1-3; the compiled reference CLI for all of them, profiles/r2_sat_seeds.md)
+SAT200_STATUS = {1: False, 2: True, 3: True, 4: True, 5: False, 6: True, 7: True, 8: True, 9: False, 10: True, 11: False}
+
+
+@pytest.mark.parametrize("seed", sorted(SAT200_STATUS))
+def test_config5_with_luby_restarts(seed):
+    """-r 100 (the reference's default, src/main.c:109-113): the search goes back to the root on the Luby schedule and
+    expands it again in the order of the failure-driven priorities learned so far (src/csolve.c:76-83,264-276,380-385).
+    Restarts change the tree, never the answer: SAT / UNSAT as without them, every model checked on the CNF."""
+    cnf = I.random_3sat_cnf(200, seed=seed)
+    m = cb.Model(I.cnf_to_csolve(200, cnf))
+    p = cb.GpuProblem(m)
+    restarts = 0
+    for rf in (100, 5):
+        r = p.solve(prefer_failing=True, restart_frequency=rf, time_limit_ms=120000)
+        assert r.timed_out == 0 and bool(r.has_solution) == SAT200_STATUS[seed], (seed, rf)
+        restarts += r.restarts
+        if r.has_solution:
+            val = dict(zip(m.var_names, r.assignments[0]))
+            for cl in cnf:
+                assert any((val["x%d" % abs(l)] == 1) == (l > 0) for l in cl), cl
+    if not SAT200_STATUS[seed]:
+        assert restarts > 0                      # an unsatisfiable instance outlasts the first thresholds
+
+
+def test_restarts_leave_all_mode_and_later_searches_alone():
+    """restarts are for ANY models only (is_restartable(), src/csolve.c:212-215): ALL-mode counts are the tree's; and
+    the static order a restart rewrote on the device is the model's own again for the next search"""
+    m = cb.Model(I.random_3sat(20, seed=1, objective="ALL"))
+    p = cb.GpuProblem(m)
+    a = p.solve(prefer_failing=True)
+    b = p.solve(prefer_failing=True, restart_frequency=1)
+    assert b.solutions == a.solutions > 0 and b.restarts == 0
+    m = cb.Model(I.random_3sat(100, seed=4))
+    p = cb.GpuProblem(m)
+    before = p.solve()                                   # static order: a deterministic tree when unsatisfiable
+    r = p.solve(prefer_failing=True, restart_frequency=1)
+    after = p.solve()
+    assert bool(r.has_solution) == bool(before.has_solution)
+    if not before.has_solution:
+        assert (after.nodes, after.cuts) == (before.nodes, before.cuts)
+
+
 def test_config4_optima_with_and_without_learning():
     """config 4: schedule (MIN, optimum 11) and wcet (MAX, optimum 1560, confirmed with z3 in BASELINE.md)"""
     for text, best in ((I.schedule(), 11), (I.wcet(), 1560)):
