@@ -336,7 +336,7 @@ extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device
 #define UP(field, vec) add(p->cm.vec.data(), p->cm.vec.size() * sizeof(p->cm.vec[0]), (const void **)&d.field)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
   UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst);
-  UP(lin, lin); UP(lin_term, lin_term); UP(sat_occ_ptr, sat_occ_ptr); UP(sat_occ, sat_occ);
+  UP(lin, lin); UP(lin_term, lin_term); UP(linrel, linrel); UP(sat_occ_ptr, sat_occ_ptr); UP(sat_occ, sat_occ);
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
 #undef UP

@@ -71,6 +71,18 @@ bool collect_terms(const csolve_flat_model &m, int n, std::vector<LinTerm> &term
   return false;
 }
 
+// A sum of variables and constants with unit coefficients below n (ADD / NEG directly above a leaf): terms as
+// variable | LR_NEG, constants folded into konst. sign: -1 when the whole sum counts negative (the right operand).
+bool collect_unit_terms(const csolve_flat_model &m, int n, int sign, std::vector<int32_t> &terms, int64_t &konst) {
+  const int op = m.node_op[n];
+  if (op == CSOLVE_OP_ADD) return collect_unit_terms(m, m.node_l[n], sign, terms, konst) && collect_unit_terms(m, m.node_r[n], sign, terms, konst);
+  int t = n, s = sign;
+  if (op == CSOLVE_OP_NEG) { t = m.node_l[n]; s = -s; }
+  if (m.node_op[t] == CSOLVE_OP_VAR) { terms.push_back(m.node_l[t] | (s < 0 ? LR_NEG : 0)); return true; }
+  if (m.node_op[t] == CSOLVE_OP_CONST && m.node_l[t] == m.node_r[t]) { konst += s * (int64_t)m.node_l[t]; return true; }
+  return false;
+}
+
 // every value involved stays far away from the +-infinity sentinels of src/arith.c
 const int64_t SAFE = (int64_t)1 << 29;
 bool small(int64_t v) { return v > -SAFE && v < SAFE; }
@@ -208,6 +220,39 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   }
   std::vector<int> lin_of_clause(C, -1);
   for (size_t i = 0; i < out.lin.size(); i++) lin_of_clause[out.lin[i].clause] = (int)i;
+  // Small linear relations: EQ(l, r), LT(l, r), NOT(LT(l, r)) over sums of at most four DISTINCT variables with unit
+  // coefficients. What the nested propagate_eq / propagate_lt / propagate_add / propagate_neg calls do to such a tree
+  // (src/propagate.c:90-246) has the fixpoint of plain bounds reasoning on the flat relation (same argument as for the
+  // linear clause above; checked against the oracle by scripts/diff_fuzz.py and against the reference's node
+  // transitions on schedule / wcet). Nothing may be able to saturate.
+  out.linrel.clear();
+  std::vector<int> linrel_of_clause(C, -1);
+  for (int c = 0; c < C; c++) {
+    if (out.clause[c].kind != CK_GENERIC || lin_of_clause[c] >= 0 || V > LR_VAR) continue;
+    int root = m.clause_first[c + 1] - 1, rel = -1;
+    if (m.node_op[root] == CSOLVE_OP_EQ) rel = LR_EQ;
+    else if (m.node_op[root] == CSOLVE_OP_LT) rel = LR_LT;
+    else if (m.node_op[root] == CSOLVE_OP_NOT && m.node_op[m.node_l[root]] == CSOLVE_OP_LT) { rel = LR_GE; root = m.node_l[root]; }
+    if (rel < 0) continue;
+    std::vector<int32_t> terms;
+    int64_t konst = 0;
+    if (!collect_unit_terms(m, m.node_l[root], +1, terms, konst) || !collect_unit_terms(m, m.node_r[root], -1, terms, konst)) continue;
+    if (terms.empty() || terms.size() > 4) continue;
+    bool good = small(konst);
+    int64_t span = std::llabs(konst);
+    for (size_t i = 0; i < terms.size() && good; i++) {
+      const int v = terms[i] & LR_VAR;
+      for (size_t j = 0; j < i; j++) if ((terms[j] & LR_VAR) == v) good = false;
+      const int64_t bound = std::max(std::llabs((int64_t)m.var_lo[v]), std::llabs((int64_t)m.var_hi[v]));
+      span += 2 * bound + 2;
+      if (!small(bound) || !small(span)) good = false;
+    }
+    if (!good) continue;
+    LinRel r{rel, (int32_t)terms.size(), (int32_t)konst, c, {-1, -1, -1, -1}};
+    for (size_t i = 0; i < terms.size(); i++) r.v[i] = terms[i];
+    linrel_of_clause[c] = (int)out.linrel.size();
+    out.linrel.push_back(r);
+  }
   if (max_depth > MAX_DEPTH) { err = "clause expression too deep for the device interpreter"; return CSOLVE_ERR_UNSUPPORTED; }
 
   // ---- watch records: per variable, the NOT(EQ) clauses grouped by partner, then the generic ones ----
@@ -259,7 +304,8 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     for (int c : generic) {
       WatchRec r; r.c[0] = r.c[1] = r.c[2] = 0;
       r.w0 = lin_of_clause[c] >= 0 ? (WK_GENERIC << 30) | (2u << 28) | (uint32_t)lin_of_clause[c]
-                                   : (WK_GENERIC << 30) | (1u << 28) | (uint32_t)c;
+             : linrel_of_clause[c] >= 0 ? (WK_GENERIC << 30) | (3u << 28) | (uint32_t)linrel_of_clause[c]
+                                        : (WK_GENERIC << 30) | (1u << 28) | (uint32_t)c;
       out.wrec.push_back(r);
     }
   }
@@ -389,6 +435,8 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     const size_t bytes = out.sat_occ.size() * sizeof(int2_t) + (2 * (size_t)V + 1) * sizeof(int32_t) + (size_t)V * 2 + 2 * (size_t)h.mask_words * 4;
     h.sat_smem_bytes = (h.sat && bytes <= 64 * 1024) ? (int32_t)((bytes + 15) & ~(size_t)15) : 0;
   }
+  h.n_linrel = (int32_t)out.linrel.size();
+  h.linrel = out.linrel.data();
   h.n_lin = (int32_t)out.lin.size();
   h.lin = out.lin.data();
   h.lin_term = out.lin_term.data();

@@ -19,6 +19,7 @@ struct CompiledModel {
   std::vector<uint8_t> node_op;
   std::vector<int32_t> sat_occ_ptr;
   std::vector<int2_t> sat_occ;
+  std::vector<LinRel> linrel;
   std::vector<LinClause> lin;
   std::vector<LinTerm> lin_term;
 };

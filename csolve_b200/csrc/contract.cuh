@@ -539,6 +539,53 @@ CSOLVE_HD bool lin_lane_apply(Cx &cx, const LinClause &L, const LinLane &t, int 
   return ok;
 }
 
+// ---- small linear relation  SUM(s_k * x_k) + konst  REL  0  (s_k = +-1, at most four variables), one lane ----------
+// The flat form of what propagate_eq / propagate_lt (true and false branch) / propagate_add / propagate_neg do to
+// EQ(l, r), LT(l, r), NOT(LT(l, r)) over sums with unit coefficients (src/propagate.c:90-246; derivation in DESIGN.md):
+// with A / B the lower / upper bound of D = SUM(s_k * x_k) + konst,
+//   D == 0 :  s_k x_k  in  [hi_k - B, lo_k - A]      (lo_k / hi_k: bounds of s_k x_k; the others sum to [A - lo_k, B - hi_k])
+//   D <  0 :  only the upper side:  s_k x_k <= lo_k - A - 1
+//   D >= 0 :  only the lower side:  s_k x_k >= hi_k - B
+// Snapshot semantics (every term against the bounds the call started with): a single call may narrow less than the
+// reference's, which re-evaluates after narrowing the right operand; the fixpoint is the same.
+template <class Cx>
+CSOLVE_HD bool contract_linrel(Cx &cx, const LinRel &R) {
+  int32_t lo[4], hi[4];
+  int32_t A = R.konst, B = R.konst;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; k++) {
+    lo[k] = 0; hi[k] = 0;
+    if (k < R.n) {
+      const Dom X = cx.dom(R.v[k] & LR_VAR);
+      const bool neg = (R.v[k] & LR_NEG) != 0;
+      lo[k] = neg ? -X.hi : X.lo;
+      hi[k] = neg ? -X.lo : X.hi;
+    }
+    A += lo[k]; B += hi[k];
+  }
+  bool ok = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; k++) {
+    if (k < R.n) {
+      // bounds asked of s_k x_k
+      int32_t tl = DMIN, th = DMAX;
+      if (R.rel == LR_EQ) { tl = hi[k] - B; th = lo[k] - A; }
+      else if (R.rel == LR_LT) { th = lo[k] - A - 1; }
+      else { tl = hi[k] - B; }
+      const bool neg = (R.v[k] & LR_NEG) != 0;
+      // ... of x_k itself (an open side stays open)
+      const int32_t xl = neg ? (th == DMAX ? DMIN : -th) : tl;
+      const int32_t xh = neg ? (tl == DMIN ? DMAX : -tl) : th;
+      if (!contract_var(cx, R.v[k] & LR_VAR, xl, xh)) ok = false;
+    }
+  }
+  return ok;
+}
+
 // ---- specialised contractors ----------------------------------------------------------
 // NOT(EQ(x + c, y)): the false branch of propagate_eq (src/propagate.c:104-134) reached
 // through propagate_not (src/propagate.c:289-301) and propagate_add (src/propagate.c:222-246);
@@ -639,6 +686,16 @@ CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const 
   const uint32_t kind = wrec_kind(rec.w0);
   const int n = wrec_n(rec.w0);
   if (kind == WK_GENERIC && n == 2) return contract_tree(cx, m, m.clause[m.lin[wrec_arg(rec.w0)].clause].b);
+  if (kind == WK_GENERIC && n == 3) {
+#if defined(__CUDA_ARCH__)
+    const int4 q0 = __ldg(reinterpret_cast<const int4 *>(&m.linrel[wrec_arg(rec.w0)]));
+    const int4 q1 = __ldg(reinterpret_cast<const int4 *>(&m.linrel[wrec_arg(rec.w0)]) + 1);
+    LinRel R; R.rel = q0.x; R.n = q0.y; R.konst = q0.z; R.clause = q0.w; R.v[0] = q1.x; R.v[1] = q1.y; R.v[2] = q1.z; R.v[3] = q1.w;
+    return contract_linrel(cx, R);
+#else
+    return contract_linrel(cx, m.linrel[wrec_arg(rec.w0)]);
+#endif
+  }
   if (kind == WK_NE_VV) {
     const int y = wrec_arg(rec.w0);
     const Dom Y = cx.dom(y);

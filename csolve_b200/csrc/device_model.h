@@ -30,6 +30,7 @@ struct ClauseRec { int32_t kind, a, b, c; };
 //   w0 = kind << 30 | n << 28 | arg        (n = number of offsets/constants used, 1..3)
 //   WK_GENERIC : n == 1: arg = clause index; the whole clause is contracted by the interpreter
 //                n == 2: arg = index of a linear clause (LinClause below), contracted by the whole warp
+//                n == 3: arg = index of a small linear relation (LinRel below), contracted by this lane, no interpreter
 //   WK_NE_VV   : arg = partner variable p; for k < n:  self + w[1 + k] != p
 //                (all NOT(EQ) clauses between the two variables, oriented from `self`, duplicates
 //                 merged: contracting the same clause twice cannot change the fixpoint)
@@ -48,6 +49,13 @@ CSOLVE_HOSTDEV static inline int wrec_arg(uint32_t w0) { return (int)(w0 & 0x0ff
 // term is the bare variable, k == 1).
 struct LinClause { int32_t obj, n_terms, first, konst, clause, pad0, pad1, pad2; };
 struct LinTerm { int32_t var, k; };
+// Linear relation between at most four variables with unit coefficients:  SUM(+-x_k) + konst  REL  0, where
+// REL is == (EQ(l, r)), < (LT(l, r)) or >= (NOT(LT(l, r))) and the terms of r count negative. One lane contracts it in
+// straight-line code (contract_linrel): a watch record WK_GENERIC with n == 3, arg = index into linrel[].
+// v[k]: variable | LR_NEG (the term counts negative); unused slots are -1.
+struct LinRel { int32_t rel, n, konst, clause; int32_t v[4]; };
+static const int32_t LR_EQ = 0, LR_LT = 1, LR_GE = 2;
+static const int32_t LR_NEG = 1 << 30, LR_VAR = (1 << 28) - 1;
 static const int32_t LIN_NEG = 1 << 30, LIN_MUL = 1 << 29, LIN_VAR = (1 << 28) - 1;
 static const int MAX_LIN = 32;          // linear clauses per model (a dirty bit each), terms per clause (a lane each)
 
@@ -95,6 +103,8 @@ struct DevModel {
   int32_t sat_smem_bytes;    // bytes needed to stage the occurrence table, the order and the root state (0 = table stays in global memory)
   const int32_t *sat_occ_ptr;   // [2 * n_vars + 1]
   const int2_t *sat_occ;        // [n_sat_occ]
+  int32_t n_linrel;          // small linear relations (watch records WK_GENERIC with n == 3)
+  const LinRel *linrel;      // [n_linrel]
   int32_t n_lin;             // linear clauses (watch records WK_GENERIC with n == 2, arg = index into lin[])
   const LinClause *lin;      // [n_lin]
   const LinTerm *lin_term;   // terms of all linear clauses

@@ -271,7 +271,8 @@ struct Analysis {
       const int n = wrec_n((uint32_t)q.x);
       visit(q.y >> 1); if (n > 1) visit(q.z >> 1); if (n > 2) visit(q.w >> 1);
     } else {
-      const int ci = wrec_n((uint32_t)q.x) == 2 ? m.lin[wrec_arg((uint32_t)q.x)].clause : wrec_arg((uint32_t)q.x);
+      const int wn = wrec_n((uint32_t)q.x);
+      const int ci = wn == 2 ? m.lin[wrec_arg((uint32_t)q.x)].clause : (wn == 3 ? m.linrel[wrec_arg((uint32_t)q.x)].clause : wrec_arg((uint32_t)q.x));
       const ClauseRec c = m.clause[ci];
       for (int j = c.a; j <= c.b && ok; j++) if (m.node_op[j] == CSOLVE_OP_VAR) visit(m.node_l[j]);
     }

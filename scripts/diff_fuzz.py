@@ -7,13 +7,13 @@ import csolve_b200 as cb, util, gen_random
 os.environ["NC"]="8"
 hc=util.harness_lib()
 seed0=int(sys.argv[1]); n=int(sys.argv[2])
-models=checked=mism=lin=lov=0
+models=checked=mism=lin=lov=rel=0
 for s in range(seed0, seed0+n):
     text=gen_random.gen_instance(s)
     try: m=cb.Model(text)
     except cb.CsolveError: continue
     if hc.hc_load(C.byref(m.flat),1)!=0: continue
-    models+=1; lin+= hc.hc_n_linear()>0
+    models+=1; lin+= hc.hc_n_linear()>0; rel+= hc.hc_n_linrel()>0
     orc=util.Oracle(m); V=m.n_vars; rng=random.Random(s)
     for _w in range(12):
         dom=m.root_domains.copy()
@@ -44,4 +44,4 @@ for s in range(seed0, seed0+n):
                         if mism<=3: print("MISMATCH (lov) seed",s,"var",v,"val",val,"\n",text,dom.tolist(),"\noracle",eo.tolist(),"\nlov",lf,out2.tolist())
             if ef: break
             dom=eo
-print("seeds %d..%d: models %d (with linear clause %d), node transitions %d, mismatches %d, of those also through the lane-owns-variable form %d"%(seed0,seed0+n,models,lin,checked,mism,lov))
+print("seeds %d..%d: models %d (with linear clause %d, with small linear relations %d), node transitions %d, mismatches %d, of those also through the lane-owns-variable form %d"%(seed0,seed0+n,models,lin,rel,checked,mism,lov))

@@ -53,6 +53,7 @@ extern "C" int hc_load(const csolve_flat_model *m, int specialise) {
 }
 extern "C" const char *hc_error() { return g_err.c_str(); }
 extern "C" int hc_n_linear() { return g_cm.host.n_lin; }
+extern "C" int hc_n_linrel() { return g_cm.host.n_linrel; }
 extern "C" int hc_n_specialised() {
   int n = 0;
   for (auto &c : g_cm.clause) n += c.kind != CK_GENERIC;
