@@ -324,6 +324,7 @@ extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device
   d = p->cm.host;
   if (getenv("CSOLVE_NO_LOV")) { d.lov = 0; d.lovk = 0; d.frame_words = frame_words(d.n_vars, d.mask_words); }   // development switch: general kernels only
   if (getenv("CSOLVE_NO_SAT")) d.sat = 0;
+  if (getenv("CSOLVE_NO_DENSE")) d.dense = 0;
   std::vector<unsigned char> image;
   struct Part { size_t off; const void *src; size_t bytes; const void **field; };
   std::vector<Part> parts;
@@ -336,7 +337,7 @@ extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device
 #define UP(field, vec) add(p->cm.vec.data(), p->cm.vec.size() * sizeof(p->cm.vec[0]), (const void **)&d.field)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
   UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst);
-  UP(lin, lin); UP(lin_term, lin_term); UP(linrel, linrel); UP(sat_occ_ptr, sat_occ_ptr); UP(sat_occ, sat_occ);
+  UP(lin, lin); UP(lin_term, lin_term); UP(linrel, linrel); UP(dense_form, dense_form); UP(sat_occ_ptr, sat_occ_ptr); UP(sat_occ, sat_occ);
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);
 #undef UP
@@ -998,7 +999,8 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
                     "(min %.3f, max %.3f), most nodes on one warp %.0f (avg %.0f), %d frames donated\n", dbg_ms, (unsigned long long)slices, p->n_warps,
             wait / p->n_warps / khz, claims / p->n_warps, lw / p->n_warps / khz, lw_min / khz, lw_max / khz, nmax,
             (double)tot[CNT_NODES] / p->n_warps, ctl.item_count);
-    fprintf(stderr, "[csolve]   polls %llu, donation wanted %llu, donated %llu\n", tot[CNT_POLLS], tot[CNT_WANTED], tot[CNT_DONATED]);
+    fprintf(stderr, "[csolve]   polls %llu, donation wanted %llu, donated %llu; nodes %llu, frame refreshes %llu, props %llu, clause visits %llu\n", tot[CNT_POLLS], tot[CNT_WANTED], tot[CNT_DONATED],
+            tot[CNT_NODES], tot[CNT_REFRESH], tot[CNT_PROPS], tot[CNT_VISITS]);
     {
       std::vector<double> lws, wts;
       for (int w = 0; w < p->n_warps; w++) { lws.push_back((double)wc[(size_t)w * CNT_WIDTH + CNT_LASTWORK] / khz); wts.push_back((double)wc[(size_t)w * CNT_WIDTH + CNT_WAIT] / khz); }

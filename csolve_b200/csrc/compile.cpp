@@ -255,6 +255,14 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   }
   if (max_depth > MAX_DEPTH) { err = "clause expression too deep for the device interpreter"; return CSOLVE_ERR_UNSUPPORTED; }
 
+  // dense propagation: few clauses, one lane each (device_model.h)
+  out.dense_form.assign(C, int2_t{DF_CLAUSE, 0});
+  for (int c = 0; c < C; c++) {
+    if (lin_of_clause[c] >= 0) out.dense_form[c] = int2_t{DF_LIN, lin_of_clause[c]};
+    else if (linrel_of_clause[c] >= 0) out.dense_form[c] = int2_t{DF_LINREL, linrel_of_clause[c]};
+  }
+  out.host.dense = (C >= 1 && C <= 32) ? 1 : 0;
+
   // ---- watch records: per variable, the NOT(EQ) clauses grouped by partner, then the generic ones ----
   out.wrec.clear();
   out.wrec_ptr.assign(V + 1, 0);
@@ -424,7 +432,12 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   h.wrec_ptr = out.wrec_ptr.data();
   h.n_wrec = (int32_t)out.wrec.size();
   {
-    const size_t bytes = out.wrec.size() * sizeof(WatchRec) + (size_t)(V + 1) * sizeof(int32_t);
+    // watch records, their index, and (16-byte aligned behind them) the small tables a contraction reads: linear
+    // relations, linear clauses and their terms -- out of global memory each of them costs an L2 round trip per visit
+    size_t bytes = out.wrec.size() * sizeof(WatchRec) + (size_t)(V + 1) * sizeof(int32_t);
+    bytes = (bytes + 15) & ~(size_t)15;
+    bytes += out.linrel.size() * sizeof(LinRel) + out.lin.size() * sizeof(LinClause) + out.lin_term.size() * sizeof(LinTerm);
+    if (h.dense) bytes += out.dense_form.size() * sizeof(int2_t);
     h.table_smem_bytes = bytes <= 40 * 1024 ? (int32_t)((bytes + 15) & ~(size_t)15) : 0;
   }
   h.sat_occ_ptr = out.sat_occ_ptr.data();
@@ -437,6 +450,8 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   }
   h.n_linrel = (int32_t)out.linrel.size();
   h.linrel = out.linrel.data();
+  h.dense_form = out.dense_form.data();
+  h.n_lin_term = (int32_t)out.lin_term.size();
   h.n_lin = (int32_t)out.lin.size();
   h.lin = out.lin.data();
   h.lin_term = out.lin_term.data();

@@ -20,6 +20,7 @@ struct CompiledModel {
   std::vector<int32_t> sat_occ_ptr;
   std::vector<int2_t> sat_occ;
   std::vector<LinRel> linrel;
+  std::vector<int2_t> dense_form;
   std::vector<LinClause> lin;
   std::vector<LinTerm> lin_term;
 };

@@ -133,14 +133,16 @@ CSOLVE_HD bool contract_var(Cx &cx, int v, int32_t lo, int32_t hi) {
 // src/propagate.c:249-271; out: 0 nothing, 1 interval in [*lo,*hi], -1 error
 CSOLVE_HD int mul_target(Dom v, Dom cv, int32_t *lo, int32_t *hi) {
   if (v.lo != DMIN && v.hi != DMIN && is_single(cv)) {
-    int32_t k = cv.lo;
+    // 32-bit division: the numerators are never INT32_MIN here, so k == -1 cannot overflow (a 64-bit division is a
+    // hundred instructions on the device; this function runs for every term of a linear clause in every round)
+    const int32_t k = cv.lo;
     if (((v.lo > 0 || v.hi < 0) && k == 0) ||
-        (is_single(v) && k != 0 && ((long long)v.lo % (long long)k) != 0)) {
+        (is_single(v) && k != 0 && (v.lo % k) != 0)) {
       return -1;
     }
     if (k != 0) {
-      int32_t a = (int32_t)((long long)v.lo / (long long)k);
-      int32_t b = (int32_t)((long long)v.hi / (long long)k);
+      const int32_t a = v.lo / k;
+      const int32_t b = v.hi / k;
       *lo = imin(a, b);
       *hi = imax(a, b);
       return 1;
@@ -508,7 +510,11 @@ template <class Cx>
 CSOLVE_HD LinLane lin_lane_load(Cx &cx, const DevModel &m, const LinClause &L, int lane) {
   LinLane t; t.var = -1; t.k = 0; t.flags = 0; t.X = mk(0, 0); t.tlo = 0; t.thi = 0;
   if (lane < L.n_terms) {
+#if defined(__CUDA_ARCH__)
+    const LinTerm q = cx.lin_term[L.first + lane];        // the kernels' contexts carry the (shared-memory) tables
+#else
     const LinTerm q = m.lin_term[L.first + lane];
+#endif
     t.var = q.var & LIN_VAR; t.flags = q.var & (LIN_NEG | LIN_MUL); t.k = q.k;
     t.X = cx.dom(t.var);
     const long long a = (long long)t.k * t.X.lo, b = (long long)t.k * t.X.hi;
@@ -685,11 +691,15 @@ template <class Cx>
 CSOLVE_HD bool contract_watch(Cx &cx, const DevModel &m, int self, Dom X, const WatchRec &rec) {
   const uint32_t kind = wrec_kind(rec.w0);
   const int n = wrec_n(rec.w0);
+#if defined(__CUDA_ARCH__)
+  if (kind == WK_GENERIC && n == 2) return contract_tree(cx, m, m.clause[cx.lin[wrec_arg(rec.w0)].clause].b);
+#else
   if (kind == WK_GENERIC && n == 2) return contract_tree(cx, m, m.clause[m.lin[wrec_arg(rec.w0)].clause].b);
+#endif
   if (kind == WK_GENERIC && n == 3) {
 #if defined(__CUDA_ARCH__)
-    const int4 q0 = __ldg(reinterpret_cast<const int4 *>(&m.linrel[wrec_arg(rec.w0)]));
-    const int4 q1 = __ldg(reinterpret_cast<const int4 *>(&m.linrel[wrec_arg(rec.w0)]) + 1);
+    const int4 q0 = reinterpret_cast<const int4 *>(&cx.linrel[wrec_arg(rec.w0)])[0];
+    const int4 q1 = reinterpret_cast<const int4 *>(&cx.linrel[wrec_arg(rec.w0)])[1];
     LinRel R; R.rel = q0.x; R.n = q0.y; R.konst = q0.z; R.clause = q0.w; R.v[0] = q1.x; R.v[1] = q1.y; R.v[2] = q1.z; R.v[3] = q1.w;
     return contract_linrel(cx, R);
 #else

@@ -55,6 +55,7 @@ struct LinTerm { int32_t var, k; };
 // v[k]: variable | LR_NEG (the term counts negative); unused slots are -1.
 struct LinRel { int32_t rel, n, konst, clause; int32_t v[4]; };
 static const int32_t LR_EQ = 0, LR_LT = 1, LR_GE = 2;
+static const int32_t DF_CLAUSE = 0, DF_LINREL = 1, DF_LIN = 2;
 static const int32_t LR_NEG = 1 << 30, LR_VAR = (1 << 28) - 1;
 static const int32_t LIN_NEG = 1 << 30, LIN_MUL = 1 << 29, LIN_VAR = (1 << 28) - 1;
 static const int MAX_LIN = 32;          // linear clauses per model (a dirty bit each), terms per clause (a lane each)
@@ -105,6 +106,12 @@ struct DevModel {
   const int2_t *sat_occ;        // [n_sat_occ]
   int32_t n_linrel;          // small linear relations (watch records WK_GENERIC with n == 3)
   const LinRel *linrel;      // [n_linrel]
+  // "dense" propagation (at most 32 clauses): a fixpoint round contracts EVERY clause, lane c clause c, instead of
+  // walking worklists -- dense_form[c] = {form, arg}: DF_CLAUSE (ClauseRec c), DF_LINREL (linrel[arg]), DF_LIN (lin[arg],
+  // contracted by the whole warp after the lanes' clauses)
+  int32_t dense;
+  const int2_t *dense_form;  // [n_clauses]
+  int32_t n_lin_term;        // terms of all linear clauses
   int32_t n_lin;             // linear clauses (watch records WK_GENERIC with n == 2, arg = index into lin[])
   const LinClause *lin;      // [n_lin]
   const LinTerm *lin_term;   // terms of all linear clauses

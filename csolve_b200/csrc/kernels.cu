@@ -49,6 +49,9 @@ struct WarpCx {
   int *d;            // shared: 2 * n_vars words
   unsigned *nxt;     // shared: mask of variables narrowed in this round
   unsigned props;    // per-lane PROPS partial
+  const LinRel *linrel = nullptr;       // small tables (shared memory when they were staged, else the model's global arrays)
+  const LinClause *lin = nullptr;
+  const LinTerm *lin_term = nullptr;
   int *rlo = nullptr, *rhi = nullptr;   // learning: which record last raised lo / lowered hi of a variable in this node
   int cur = -1;                         // ... code of the record being contracted (>= 0 watch record, <= -2 nogood -2 - id)
   __device__ __forceinline__ Dom dom(int v) const {
@@ -69,8 +72,8 @@ struct WarpCx {
 
 // one linear clause contracted by the whole warp (contract.cuh: lin_lane_load / lin_lane_apply)
 __device__ __forceinline__ bool warp_contract_linear(WarpCx &cx, const DevModel &m, int c, int lane) {
-  const int4 q0 = __ldg(reinterpret_cast<const int4 *>(&m.lin[c]));
-  const int4 q1 = __ldg(reinterpret_cast<const int4 *>(&m.lin[c]) + 1);
+  const int4 q0 = reinterpret_cast<const int4 *>(&cx.lin[c])[0];
+  const int4 q1 = reinterpret_cast<const int4 *>(&cx.lin[c])[1];
   LinClause L; L.obj = q0.x; L.n_terms = q0.y; L.first = q0.z; L.konst = q0.w; L.clause = q1.x; L.pad0 = L.pad1 = L.pad2 = 0;
   const Dom O = cx.dom(L.obj);
   const LinLane t = lin_lane_load(cx, m, L, lane);
@@ -79,7 +82,10 @@ __device__ __forceinline__ bool warp_contract_linear(WarpCx &cx, const DevModel 
 }
 
 // per-warp shared memory carve-up
+struct LinTables { const LinRel *linrel; const LinClause *lin; const LinTerm *lin_term; const int2 *dense_form; };
+
 struct WarpSmem {
+  LinTables lt;    // small tables of the block (set after stage_table)
   int *d;          // 2V: the node being propagated
   int *p;          // 2V: domains of the top frame (state before this level's assignment)
   unsigned *cur;   // mask_words: variables whose watchers run in this round
@@ -125,7 +131,46 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
                                               const NogoodPool *ng = nullptr, FailInfo *fi = nullptr) {
   WarpCx cx;
   cx.d = s.d; cx.props = 0;
+  cx.linrel = s.lt.linrel; cx.lin = s.lt.lin; cx.lin_term = s.lt.lin_term;
   if (LEARN) { cx.rlo = s.rlo; cx.rhi = s.rhi; }
+  if (!LEARN && m.dense) {
+    // Few clauses (at most 32): every round contracts ALL of them, lane c clause c, then the linear clauses with the
+    // whole warp -- no worklists, no per-variable record walks. Same contractors, same greatest fixpoint;
+    // a wcet fixpoint went from ~80 clause visits of ~100 warp instructions each to a handful of rounds of ~150.
+    cx.nxt = s.nxt;
+    for (;;) {
+      bool bad = false;
+      if (lane < m.n_clauses) {
+        const int2 f = s.lt.dense_form[lane];
+        if (f.x == DF_LINREL) {
+          const int4 q0 = reinterpret_cast<const int4 *>(&cx.linrel[f.y])[0];
+          const int4 q1 = reinterpret_cast<const int4 *>(&cx.linrel[f.y])[1];
+          LinRel R; R.rel = q0.x; R.n = q0.y; R.konst = q0.z; R.clause = q0.w; R.v[0] = q1.x; R.v[1] = q1.y; R.v[2] = q1.z; R.v[3] = q1.w;
+          bad = !contract_linrel(cx, R);
+        } else if (f.x == DF_CLAUSE) {
+          const int4 q = __ldg(reinterpret_cast<const int4 *>(&m.clause[lane]));
+          ClauseRec rec; rec.kind = q.x; rec.a = q.y; rec.b = q.z; rec.c = q.w;
+          bad = !contract_clause(cx, m, rec);
+        }
+        visits++;
+      }
+      __syncwarp();
+      for (int c = 0; LIN && c < m.n_lin; c++) {
+        if (!warp_contract_linear(cx, m, c, lane)) bad = true;
+        visits++;
+      }
+      __syncwarp();
+      // bounds published by different lanes may have crossed
+      for (int v = lane; v < m.n_vars; v += 32) { const Dom X = cx.dom(v); if (X.lo > X.hi) bad = true; }
+      if (__any_sync(FULL, bad)) { props += cx.props; return false; }
+      unsigned ch = 0;
+      for (int w = lane; w < m.mask_words; w += 32) { ch |= s.nxt[w]; s.nxt[w] = 0; }
+      __syncwarp();
+      if (!__any_sync(FULL, ch != 0u)) break;
+    }
+    props += cx.props;
+    return true;
+  }
   bool failed = false;
   int fail_var = -1, fail_rec = -1, empty_var = -1;
   for (;;) {
@@ -189,7 +234,7 @@ __device__ __forceinline__ bool warp_fixpoint(const DevModel &m, WarpSmem &s, co
         while (dirty) {
           const int c = __ffs((int)dirty) - 1;
           dirty &= dirty - 1;
-          if (!warp_contract_linear(cx, m, c, lane)) { failed = true; fail_var = m.lin[c].obj; }
+          if (!warp_contract_linear(cx, m, c, lane)) { failed = true; fail_var = cx.lin[c].obj; }
           visits++;
         }
       }
@@ -314,14 +359,27 @@ __device__ __noinline__ void learn_nogood(const DevModel &m, const WarpSmem &s, 
   }
 }
 
-// stage the watch-record table into shared memory (whole block); returns the pointers to use
-__device__ __forceinline__ void stage_table(const DevModel &m, int *smem, const int4 *&wrec, const int *&wptr) {
+// stage the watch-record table and the small linear tables into shared memory (whole block); returns the pointers to use
+__device__ __forceinline__ void stage_table(const DevModel &m, int *smem, const int4 *&wrec, const int *&wptr, LinTables &lt) {
+  lt.linrel = m.linrel; lt.lin = m.lin; lt.lin_term = m.lin_term; lt.dense_form = reinterpret_cast<const int2 *>(m.dense_form);
   if (m.table_smem_bytes > 0) {
     int4 *dst = reinterpret_cast<int4 *>(smem);
     const int4 *src = reinterpret_cast<const int4 *>(m.wrec);
     for (int i = threadIdx.x; i < m.n_wrec; i += blockDim.x) dst[i] = __ldg(&src[i]);
     int *pdst = smem + 4 * m.n_wrec;
     for (int i = threadIdx.x; i <= m.n_vars; i += blockDim.x) pdst[i] = __ldg(&m.wrec_ptr[i]);
+    int *t = smem + ((4 * m.n_wrec + m.n_vars + 1 + 3) & ~3);
+    const int n0 = 8 * m.n_linrel, n1 = 8 * m.n_lin, n2 = 2 * m.n_lin_term;
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) t[i] = __ldg(reinterpret_cast<const int *>(m.linrel) + i);
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) t[n0 + i] = __ldg(reinterpret_cast<const int *>(m.lin) + i);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) t[n0 + n1 + i] = __ldg(reinterpret_cast<const int *>(m.lin_term) + i);
+    if (m.dense) {
+      for (int i = threadIdx.x; i < 2 * m.n_clauses; i += blockDim.x) t[n0 + n1 + n2 + i] = __ldg(reinterpret_cast<const int *>(m.dense_form) + i);
+      lt.dense_form = reinterpret_cast<const int2 *>(t + n0 + n1 + n2);
+    }
+    lt.linrel = reinterpret_cast<const LinRel *>(t);
+    lt.lin = reinterpret_cast<const LinClause *>(t + n0);
+    lt.lin_term = reinterpret_cast<const LinTerm *>(t + n0 + n1);
     __syncthreads();
     wrec = dst; wptr = pdst;
   } else {
@@ -332,6 +390,7 @@ __device__ __forceinline__ void stage_table(const DevModel &m, int *smem, const 
 // leaf test: every clause evaluates to true (src/csolve.c:226, src/eval.c:221-245)
 __device__ bool warp_all_true(const DevModel &m, WarpSmem &s, int lane) {
   WarpCx cx; cx.d = s.d; cx.nxt = s.nxt; cx.props = 0;
+  cx.linrel = s.lt.linrel; cx.lin = s.lt.lin; cx.lin_term = s.lt.lin_term;
   bool ok = true;
   for (int c = lane; c < m.n_clauses; c += 32) {
     const int4 q = __ldg(reinterpret_cast<const int4 *>(&m.clause[c]));
@@ -692,11 +751,13 @@ k_search(const SearchArgs a) {
   __shared__ int s_blk_hungry;       // warps of this block waiting for a frame: their neighbours poll for donations faster
   if (threadIdx.x == 0) s_blk_hungry = 0;
   __syncthreads();
-  stage_table(m, smem, wrec, wptr);
+  LinTables ltab;
+  stage_table(m, smem, wrec, wptr, ltab);
   if (gw >= a.n_warps) return;
   // per-warp regions are padded to 16 bytes so the int2 staging copies stay aligned
   const int wwords = (warp_smem_words(m, LEARN) + 3) & ~3;
   WarpSmem s = carve(m, smem + (m.table_smem_bytes >> 2) + wib * wwords);
+  s.lt = ltab;
 
   const int V = m.n_vars, fw = m.frame_words;
   const bool optimise = m.obj_var >= 0;
@@ -2942,9 +3003,11 @@ k_propagate_batch(const DevModel m, int n_nodes, const int32_t *dom_in, const in
   extern __shared__ __align__(16) int smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int4 *wrec; const int *wptr;
-  stage_table(m, smem, wrec, wptr);
+  LinTables ltab;
+  stage_table(m, smem, wrec, wptr, ltab);
   const int wwords = (warp_smem_words(m) + 3) & ~3;
   WarpSmem s = carve(m, smem + (m.table_smem_bytes >> 2) + wib * wwords);
+  s.lt = ltab;
   const int V = m.n_vars;
   const int n_warps = gridDim.x * WARPS_PER_BLOCK;
   for (int b = blockIdx.x * WARPS_PER_BLOCK + wib; b < n_nodes; b += n_warps) {
@@ -2988,9 +3051,11 @@ k_root_frames(const DevModel m, int n_roots, const int32_t *root_dom, int order,
   extern __shared__ __align__(16) int smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int4 *wrec; const int *wptr;
-  stage_table(m, smem, wrec, wptr);
+  LinTables ltab;
+  stage_table(m, smem, wrec, wptr, ltab);
   const int wwords = (warp_smem_words(m) + 3) & ~3;
   WarpSmem s = carve(m, smem + (m.table_smem_bytes >> 2) + wib * wwords);
+  s.lt = ltab;
   const int V = m.n_vars, fw = m.frame_words;
   const int n_warps = gridDim.x * WARPS_PER_BLOCK;
   for (int r = blockIdx.x * WARPS_PER_BLOCK + wib; r < n_roots; r += n_warps) {
