@@ -267,6 +267,7 @@ struct csolve_gpu_problem {
 //   [4 KiB, +4 MiB)  ready flags of the rank's donation ring
 //   then ring_bytes  the donation ring itself (frames): peers serve this rank's tickets over NVLink
 //   then             rank 0: the expanded root frontier of the current epoch
+static const size_t SEG_COPY = 2048;     // [2048, 2176): where k_comm_wait_front leaves its copy of rank 0's block
 static const size_t SEG_CTL = 0, SEG_COMM = 1024, SEG_READY = 4096, SEG_READY_BYTES = (size_t)4 << 20, SEG_RING = SEG_READY + SEG_READY_BYTES;
 static const size_t SEG_RING_BYTES_DEFAULT = (size_t)96 << 20;
 struct csolve_gpu_comm {
@@ -278,6 +279,22 @@ struct csolve_gpu_comm {
   bool opened[COMM_MAX_RANKS] = {};     // mapped with cudaIpcOpenMemHandle (closed in destroy)
   bool connected = false;
   int epoch = 0;                        // solve counter: every rank calls csolve_gpu_solve_comm the same number of times
+  // Host-side looks at / small writes into the blocks go through a stream of this rank's own and pinned memory.
+  // cudaMemcpy (the synchronous call) on a peer's memory was measured to wait for the peer's running kernel.
+  cudaStream_t aux = nullptr;
+  CommBlock *hblk = nullptr;            // pinned: [0] block read, [1] staging of a write
+  CommBlock *copy_block() const { return reinterpret_cast<CommBlock *>(seg + SEG_COPY); }
+  bool read_block(const CommBlock *dev_block, CommBlock *out) {
+    if (cudaMemcpyAsync(&hblk[0], dev_block, sizeof(CommBlock), cudaMemcpyDefault, aux) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(aux) != cudaSuccess) return false;
+    *out = hblk[0];
+    return true;
+  }
+  bool write_words(void *dev_dst, const void *src, size_t bytes) {
+    memcpy(&hblk[1], src, bytes);
+    if (cudaMemcpyAsync(dev_dst, &hblk[1], bytes, cudaMemcpyDefault, aux) != cudaSuccess) return false;
+    return cudaStreamSynchronize(aux) == cudaSuccess;
+  }
   SearchCtl *ctl() const { return reinterpret_cast<SearchCtl *>(seg + SEG_CTL); }
   CommBlock *block(int r) const { return reinterpret_cast<CommBlock *>(peer_seg[r] + SEG_COMM); }
   SearchCtl *ctl_of(int r) const { return reinterpret_cast<SearchCtl *>(peer_seg[r] + SEG_CTL); }
@@ -505,18 +522,19 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
 
 namespace {
 // n_roots == 0: the model's own root. n_roots > 0: batched roots over the shared network (ALL models).
-// host-side waits on a CommBlock in device memory (this rank's or, through the peer mapping, rank 0's): polled with
-// small synchronous copies; `ok(block)` decides. Returns false after `limit_s` seconds.
+// host-side wait on a CommBlock in THIS rank's device memory: polled with small copies on the comm's own stream;
+// `ok(block)` decides. Returns false after `limit_s` seconds. (Waits on a peer's block run on the device:
+// k_comm_wait_front.)
 template <class F>
-bool comm_wait(const CommBlock *dev_block, F ok, double limit_s, CommBlock *out) {
+bool comm_wait(csolve_gpu_comm *c, const CommBlock *dev_block, F ok, double limit_s, CommBlock *out) {
   const auto t0 = std::chrono::steady_clock::now();
   for (unsigned spin = 0;; spin++) {
     CommBlock b;
-    if (cudaMemcpy(&b, dev_block, sizeof(b), cudaMemcpyDefault) != cudaSuccess) return false;
+    if (!c->read_block(dev_block, &b)) return false;
     if (ok(b)) {
       // the fields of a block are written by separate stores: read once more so that everything that was written
       // before the field `ok` looked at is seen as well
-      if (cudaMemcpy(&b, dev_block, sizeof(b), cudaMemcpyDefault) != cudaSuccess) return false;
+      if (!c->read_block(dev_block, &b)) return false;
       if (out) *out = b;
       return true;
     }
@@ -524,7 +542,18 @@ bool comm_wait(const CommBlock *dev_block, F ok, double limit_s, CommBlock *out)
     if (spin > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));
   }
 }
-const double COMM_WAIT_S = 300.0;
+const double COMM_WAIT_S = 120.0;
+
+// CSOLVE_DEBUG_COMM: host-side timeline of a rank (microseconds since the first call in this process)
+double comm_now_us() {
+  static const auto t0 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
+#define COMM_TRACE(c, what)                                                                              \
+  do {                                                                                                   \
+    if ((c) != nullptr && g_comm_trace) fprintf(stderr, "[csolve comm] rank %d %10.1f us  %s\n", (c)->rank, comm_now_us(), what); \
+  } while (0)
+const bool g_comm_trace = getenv("CSOLVE_DEBUG_COMM") != nullptr;
 
 int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_options *opt_in, csolve_gpu_result *res, int n_roots,
                const int32_t *root_dom, uint32_t *root_solutions, uint8_t *root_failed) {
@@ -533,6 +562,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   if (c != nullptr && (c->ctx != p->ctx || !c->connected)) return fail(CSOLVE_ERR_INVALID, "the comm is not connected or lives on another device than the problem");
   if (c != nullptr && n_roots > 0) return fail(CSOLVE_ERR_UNSUPPORTED, "batched roots are sharded by the caller (one slice of the roots per rank), not through a comm");
   if (c != nullptr && c->world == 1) c = nullptr;
+  COMM_TRACE(c, "enter");
   csolve_solve_options opt;
   memset(&opt, 0, sizeof(opt));
   if (opt_in) opt = *opt_in;
@@ -585,11 +615,11 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     if (c->rank == 0) {
       if (!front_published) {
         const int32_t hdr[3] = {epoch, -2, 0};
-        cudaMemcpy(&c->block(0)->front_n, &hdr[1], 2 * sizeof(int32_t), cudaMemcpyDefault);
-        cudaMemcpy(&c->block(0)->front_epoch, &hdr[0], sizeof(int32_t), cudaMemcpyDefault);
+        c->write_words(&c->block(0)->front_n, &hdr[1], 2 * sizeof(int32_t));
+        c->write_words(&c->block(0)->front_epoch, &hdr[0], sizeof(int32_t));
       }
     } else {
-      cudaMemcpy(&c->block(0)->done_epoch[c->rank], &epoch, sizeof(int32_t), cudaMemcpyDefault);
+      c->write_words(&c->block(0)->done_epoch[c->rank], &epoch, sizeof(int32_t));
     }
   });
   const CompiledModel &cm = p->cm;
@@ -747,15 +777,17 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   // segment and every rank expands for itself (path-hash partition, as without a comm).
   const int32_t *front_pool = nullptr;
   SearchCtl *front_ctl = dctl;
+  COMM_TRACE(c, "set up");
   if (c == nullptr || c->rank == 0) {
     rc = expand_root();
     if (rc != CSOLVE_OK) return rc;
   }
+  COMM_TRACE(c, "expanded");
   if (n_items < 0) n_items = -n_items;
   if (c != nullptr) {
     if (c->rank == 0) {
       // the previous epoch's frontier is overwritten: every peer must have left that search
-      if (!comm_wait(c->block(0), [&](const CommBlock &b) {
+      if (!comm_wait(c, c->block(0), [&](const CommBlock &b) {
             for (int r = 1; r < c->world; r++) if (b.done_epoch[r] < epoch - 1) return false;
             return true; }, COMM_WAIT_S, nullptr))
         return fail(CSOLVE_ERR_CUDA, "comm: a peer rank did not finish the previous search");
@@ -783,9 +815,12 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       CUDA_TRY(cudaStreamSynchronize(st));
       front_published = true;
     } else {
-      CommBlock b;
-      if (!comm_wait(c->block(0), [&](const CommBlock &x) { return x.front_epoch >= epoch; }, COMM_WAIT_S, &b))
-        return fail(CSOLVE_ERR_CUDA, "comm: rank 0 did not publish the root frontier");
+      // wait on the device (one thread polls rank 0's block over NVLink), then ONE copy of what it saw
+      CUDA_TRY(launch_comm_wait_front(c->block(0), epoch, COMM_WAIT_S, c->copy_block(), st));
+      CUDA_TRY(cudaMemcpyAsync(&c->hblk[0], c->copy_block(), sizeof(CommBlock), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      const CommBlock b = c->hblk[0];
+      if (b.front_epoch < epoch) return fail(CSOLVE_ERR_CUDA, "comm: rank 0 did not publish the root frontier");
       if (b.front_epoch != epoch || b.front_n == -2) return fail(CSOLVE_ERR_CUDA, "comm: rank 0 failed or the ranks are out of step");
       if (b.front_n >= 0) {
         if (b.front_fw != fw) return fail(CSOLVE_ERR_INVALID, "comm: the ranks loaded different models");
@@ -800,6 +835,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       }
     }
   }
+  COMM_TRACE(c, "frontier published / seen");
   CUDA_TRY(cudaEventRecord(ev1, st));
 
   // ---- partition: every rank holds the whole frontier; the search kernel skips the frames whose path
@@ -821,6 +857,19 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   a.front_ctl = front_ctl;
   a.total_warps = p->n_warps * (front_pool != nullptr ? c->world : 1);
   const bool cross = c != nullptr && front_pool != nullptr;     // one frontier for all ranks: they also serve each other's tickets
+  a.front_stride = 1;
+  if (cross && m.objective == CSOLVE_OBJ_ALL && n_items > 64) {
+    // Frames that are neighbours in the frontier are siblings and cousins: their sub-trees are of similar size (the
+    // first rows of N-queens: the corner columns leave the largest ones). Handed out in frontier order, the rank whose
+    // warps start first -- rank 0, it has no hop to make -- takes the whole expensive end (measured on 8 GPUs: 143 M
+    // of 836 M nodes on rank 0, 75-110 M on the others, which then lived on donations). The claims walk the frontier
+    // with a stride near n / golden ratio instead; every rank computes the same one. ANY / MIN / MAX keep the
+    // frontier's own order: there the first frames are the ones the value order prefers.
+    int s = (int)((double)n_items * 0.6180339887) | 1;
+    auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
+    while (gcd(s, n_items) != 1) s += 2;
+    a.front_stride = s % n_items;
+  }
   if (c != nullptr) {
     a.comm = c->block(c->rank); a.epoch = epoch; a.rank = c->rank; a.world = c->world; a.n_peers = c->world - 1;
     for (int r = 0; r < c->world; r++) a.peer_comm[r] = c->block(r);
@@ -880,6 +929,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   const bool is_min = m.objective == CSOLVE_OBJ_MIN;
   for (;;) {
     if (!local_done) {
+      COMM_TRACE(c, "launch search slice");
       CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
       if (getenv("CSOLVE_DEBUG_SYNC")) {
         const cudaError_t es = cudaStreamSynchronize(st);
@@ -890,6 +940,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       CUDA_TRY(cudaMemcpyAsync(&ctl, dctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       slices++; n_sliced++;
+      COMM_TRACE(c, "slice back");
       { const int rcd = drain_solutions(); if (rcd != CSOLVE_OK) return rcd; }
       busy = ctl.busy;
       idle_now = p->n_warps - busy;
@@ -973,6 +1024,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
       if (got > 0) local_done = false;
     }
   }
+  COMM_TRACE(c, "search over");
   CUDA_TRY(cudaEventRecord(ev2, st));
 
   // ---- results ---------------------------------------------------------------------------------------------
@@ -1035,7 +1087,9 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     p->sol_host.swap(sorted);
   }
 
-  if (m.obj_var >= 0 && tot[CNT_SOLUTIONS] > 0 &&
+  // (ranks of a comm / of an exchange: the incumbent may be a peer's, whose buffer then holds the witness -- the caller
+  //  that merges the ranks' results checks it, csolve_gpu_group_solve / csolve_b200.distributed)
+  if (m.obj_var >= 0 && tot[CNT_SOLUTIONS] > 0 && c == nullptr && p->exchange == nullptr &&
       (p->n_stored == 0 || p->sol_host[(size_t)(p->n_stored - 1) * (V + 1) + V] != ctl.best)) {
     return fail(CSOLVE_ERR_CAPACITY, "the witness of the optimum was overwritten in the solution ring (more than " +
                                          std::to_string(p->sol_cap) + " concurrent incumbents); raise max_solutions");
@@ -1097,6 +1151,8 @@ extern "C" int csolve_gpu_comm_create(int32_t device, int32_t rank, int32_t worl
   CUDA_TRY(cudaMemset(c->seg, 0, SEG_RING));
   const unsigned long long none = ~0ull;
   CUDA_TRY(cudaMemcpy(&reinterpret_cast<CommBlock *>(c->seg + SEG_COMM)->rmin64, &none, sizeof(none), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+  CUDA_TRY(cudaHostAlloc((void **)&c->hblk, 2 * sizeof(CommBlock), cudaHostAllocDefault));
   c->peer_seg[rank] = c->seg;
   c->connected = world == 1;
   *out = c.release();
@@ -1159,6 +1215,8 @@ extern "C" void csolve_gpu_comm_destroy(csolve_gpu_comm *c) {
   cudaSetDevice(c->ctx->device);
   for (int r = 0; r < c->world; r++) if (c->opened[r]) cudaIpcCloseMemHandle(c->peer_seg[r]);
   cudaFree(c->seg);
+  if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->hblk) cudaFreeHost(c->hblk);
   delete c;
 }
 
@@ -1301,6 +1359,8 @@ extern "C" int csolve_gpu_group_solve(csolve_gpu_group *g, const csolve_solve_op
     memcpy(&g->sols[k * (V + 1)], &g->probs[refs[k].dev]->sol_host[(size_t)refs[k].idx * (V + 1)], sizeof(int32_t) * (V + 1));
   g->n_stored = (int32_t)refs.size();
   res->n_stored = g->n_stored;
+  if (is_opt && res->has_solution && (refs.empty() || refs.back().key != res->best))
+    return fail(CSOLVE_ERR_CAPACITY, "the witness of the optimum was overwritten in a device's solution ring; raise max_solutions");
   return CSOLVE_OK;
 }
 

@@ -530,6 +530,11 @@ struct Claim {
   bool drained;                // the root frontier has been handed out completely
 };
 
+// claim number -> frame of the root frontier (SearchArgs::front_stride)
+__device__ __forceinline__ int front_index(const SearchArgs &a, int claim) {
+  return a.front_stride > 1 ? (int)((unsigned long long)(unsigned)claim * (unsigned)a.front_stride % (unsigned)a.n_initial) : claim;
+}
+
 __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &hungry, Claim &cl, int *blk_hungry, long long t0) {
   if (cl.mask) {
     const int b = __ffs((int)cl.mask) - 1;
@@ -599,7 +604,7 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
       const int idx = it + lane;
       bool mine = lane < n && idx < a.n_initial;
       if (mine && a.part_count > 1)
-        mine = (unsigned)__ldcg(&a.front_pool[(size_t)idx * fw + 7]) % (unsigned)a.part_count == (unsigned)a.part_rank;
+        mine = (unsigned)__ldcg(&a.front_pool[(size_t)front_index(a, idx) * fw + 7]) % (unsigned)a.part_count == (unsigned)a.part_rank;
       const unsigned mk = __ballot_sync(FULL, mine);
       if (mk) {
         cl.base = it;
@@ -703,7 +708,7 @@ __device__ __forceinline__ bool restart_due(const SearchArgs &a, int lane, unsig
 
 // frame of a claimed slot: the first n_initial slots are the root frontier (possibly on another GPU), the rest the ring
 __device__ __forceinline__ const int *claimed_frame(const SearchArgs &a, int slot) {
-  return (slot < a.n_initial ? a.front_pool : a.pool) + (size_t)slot * a.m.frame_words;
+  return slot < a.n_initial ? a.front_pool + (size_t)front_index(a, slot) * a.m.frame_words : a.pool + (size_t)slot * a.m.frame_words;
 }
 
 // ---- ranks of a csolve_gpu_comm: incumbent and first-solution exchange over peer memory -------------------------
@@ -2983,6 +2988,25 @@ __global__ void k_comm_state(const SearchArgs a, int want_frames, int force_idle
   out[2] = *reinterpret_cast<volatile int *>(&a.comm->stop_epoch) == a.epoch ? 1 : 0;
 }
 
+// comm: a rank waits ON THE DEVICE for rank 0's frontier of this epoch (one thread, polling rank 0's block over NVLink
+// about once a microsecond). The host then needs one copy of the block instead of a polling loop of copies: small
+// synchronous copies out of a peer's memory were measured to serialise with whatever that peer's streams are doing --
+// a rank polling that way saw the frontier only after rank 0 had finished the whole search.
+__global__ void k_comm_wait_front(const CommBlock *root, int epoch, unsigned long long timeout_ns, CommBlock *copy) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*reinterpret_cast<volatile const int *>(&root->front_epoch) - epoch < 0) {
+    __nanosleep(500);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) break;
+  }
+  __threadfence_system();
+  // everything rank 0 wrote before front_epoch (front_n, front_fw) is visible now: hand the host a consistent copy
+  const volatile int *src = reinterpret_cast<const volatile int *>(root);
+  int *dst = reinterpret_cast<int *>(copy);
+  for (int i = 0; i < (int)(sizeof(CommBlock) / sizeof(int)); i++) dst[i] = src[i];
+}
+
 __global__ void k_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out) {
   __shared__ unsigned long long acc[CNT_WIDTH];
   if (threadIdx.x < CNT_WIDTH) acc[threadIdx.x] = 0;
@@ -3180,6 +3204,11 @@ cudaError_t launch_root_frames(const DevModel &m_in, int n_roots, const int32_t 
 
 cudaError_t launch_comm_state(const SearchArgs &a, int want_frames, int force_idle, int32_t *out, cudaStream_t st) {
   k_comm_state<<<1, 1, 0, st>>>(a, want_frames, force_idle, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_comm_wait_front(const CommBlock *root, int epoch, double timeout_s, CommBlock *copy, cudaStream_t st) {
+  k_comm_wait_front<<<1, 1, 0, st>>>(root, epoch, (unsigned long long)(timeout_s * 1e9), copy);
   return cudaGetLastError();
 }
 

@@ -154,6 +154,9 @@ struct SearchArgs {
   int32_t rank, world;
   int32_t epoch;
   int32_t total_warps;        // search warps of all ranks (size of a guided chunk)
+  int32_t front_stride;       // > 1: claim number i of the root frontier is frame (i * front_stride) % n_initial -- a bijection
+                              // (the stride is coprime to n_initial) that scatters neighbouring frames, whose sub-trees are
+                              // of similar size, over the ranks and over time (ALL models on a shared frontier)
   // Parity instrumentation (csolve_solve_options.sample_mod > 0; runs the SAMPLE instances of the search kernels):
   // every search node -- executed or counted in bulk -- whose identity hash (parent domains, variable, value) is 0
   // modulo sample_mod is written to sample_rec as
@@ -179,6 +182,9 @@ cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t
 // shared frontier), out[1] = number of ranks still active (-1: another epoch), out[2] = 1 if a peer found a solution
 // (ANY). want_frames > 0 and no work: ask every peer for that many frames. force_idle: leave the epoch whatever is left.
 cudaError_t launch_comm_state(const SearchArgs &a, int want_frames, int force_idle, int32_t *out, cudaStream_t s);
+// comm: wait on the device until rank 0's block carries front_epoch >= epoch (or timeout_s passed), then copy the block
+// to `copy` (device memory of this rank)
+cudaError_t launch_comm_wait_front(const CommBlock *root, int epoch, double timeout_s, CommBlock *copy, cudaStream_t s);
 cudaError_t launch_export_frames(const SearchArgs &a, int32_t *out, int max_frames, int32_t *n_out, cudaStream_t s);
 cudaError_t launch_import_frames(const SearchArgs &a, const int32_t *in, int n_frames, cudaStream_t s);
 cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out, cudaStream_t s);

@@ -15,37 +15,48 @@ import torch.distributed as dist
 from .host import OBJ_ANY, OBJ_MAX, OBJ_MIN
 
 
-def reduce_results(res, objective, device=None, group=None):
-    """res: SolveResult-like of this rank -> dict with the whole-job totals (same on every rank)."""
+def reduce_results(res, objective, device=None, group=None, witness=None):
+    """res: SolveResult-like of this rank -> dict with the whole-job totals (same on every rank).
+    ONE collective: every rank contributes one row of twelve integers (all-gather), the reduction itself is done
+    locally -- sums, flags, the incumbent and the times need three different operators, and each extra collective is
+    tens of microseconds on a search that takes a few milliseconds.
+    witness: None, or whether this rank holds the assignment that attains ITS `res.best`; the result then says
+    whether any rank holds the witness of the whole job's optimum (`has_witness`)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return dict(solutions=int(res.solutions), nodes=int(res.nodes), cuts=int(res.cuts), props=int(res.props),
                     clause_visits=int(res.clause_visits), best=int(res.best), has_solution=int(res.has_solution),
                     timed_out=int(res.timed_out), kernel_ms=float(res.kernel_ms), expand_ms=float(res.expand_ms),
-                    kernel_launches=int(res.kernel_launches), kernel_ms_min=float(res.kernel_ms))
+                    kernel_launches=int(res.kernel_launches), kernel_ms_min=float(res.kernel_ms),
+                    has_witness=int(bool(witness)) if witness is not None else None)
     dev = device if device is not None else torch.device("cpu")
-    sums = torch.tensor([res.solutions, res.nodes, res.cuts, res.props, res.clause_visits, res.kernel_launches],
-                        dtype=torch.int64, device=dev)
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    flags = torch.tensor([res.has_solution, res.timed_out], dtype=torch.int64, device=dev)
-    dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    world = dist.get_world_size(group)
+    row = torch.tensor([res.solutions, res.nodes, res.cuts, res.props, res.clause_visits, res.kernel_launches,
+                        res.has_solution, res.timed_out, res.best, int(round(res.kernel_ms * 1e6)),
+                        int(round(res.expand_ms * 1e6)), 1 if witness else 0], dtype=torch.int64, device=dev)
+    rows = torch.empty(world * row.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(rows, row, group=group)
+    rows = rows.view(world, row.numel()).cpu().tolist()
+    s = [sum(r[k] for r in rows) for k in range(6)]
+    has_solution = max(r[6] for r in rows)
+    timed_out = max(r[7] for r in rows)
     # a rank without a solution must not win the incumbent reduction
-    neutral = 2**31 - 1 if objective == OBJ_MIN else -2**31
-    mine = int(res.best) if res.has_solution else neutral
-    best = torch.tensor([mine], dtype=torch.int64, device=dev)
-    if objective == OBJ_MIN:
-        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
-    elif objective == OBJ_MAX:
-        dist.all_reduce(best, op=dist.ReduceOp.MAX, group=group)
-    times = torch.tensor([res.kernel_ms, res.expand_ms, -res.kernel_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(times, op=dist.ReduceOp.MAX, group=group)
-    s = sums.tolist()
+    cands = [r[8] for r in rows if r[6]]
+    if objective == OBJ_MIN and cands:
+        best = min(cands)
+    elif objective == OBJ_MAX and cands:
+        best = max(cands)
+    else:
+        best = int(res.best)
     solutions = s[0]
     if objective == OBJ_ANY:
         solutions = min(solutions, 1)   # found_any(): one solution is reported (src/csolve.c:207-209)
+    has_witness = None
+    if witness is not None:
+        has_witness = int(any(r[11] and r[6] and r[8] == best for r in rows))
     return dict(solutions=solutions, nodes=s[1], cuts=s[2], props=s[3], clause_visits=s[4], kernel_launches=s[5],
-                best=int(best.item()) if objective in (OBJ_MIN, OBJ_MAX) and flags[0].item() else int(res.best),
-                has_solution=int(flags[0].item()), timed_out=int(flags[1].item()),
-                kernel_ms=float(times[0].item()), expand_ms=float(times[1].item()), kernel_ms_min=float(-times[2].item()))
+                best=best, has_solution=int(has_solution), timed_out=int(timed_out),
+                kernel_ms=max(r[9] for r in rows) * 1e-6, expand_ms=max(r[10] for r in rows) * 1e-6,
+                kernel_ms_min=min(r[9] for r in rows) * 1e-6, has_witness=has_witness)
 
 
 def make_comm(device_index, group=None, frontier_bytes=0):
@@ -70,7 +81,15 @@ def solve_comm(problem, comm, objective, device=None, group=None, **solve_kw):
     """Collective search through a Comm (shared root frontier, incumbents over peer memory), then ONE reduction of
     the ranks' counters. -> (whole-job dict, this rank's SolveResult)"""
     res = problem.solve(comm=comm, **solve_kw)
-    return reduce_results(res, objective, device=device, group=group), res
+    witness = None
+    obj_var = getattr(getattr(problem, "model", None), "obj_var", -1)
+    if objective in (OBJ_MIN, OBJ_MAX) and obj_var is not None and obj_var >= 0:
+        # the incumbent a rank reports may be a peer's (pushed over NVLink); whoever found it stored the assignment
+        witness = bool(res.has_solution and res.assignments and res.assignments[-1][obj_var] == res.best)
+    out = reduce_results(res, objective, device=device, group=group, witness=witness)
+    if witness is not None and out["has_solution"] and not out["has_witness"]:
+        raise RuntimeError("the witness of the optimum was overwritten in a rank's solution ring; raise max_solutions")
+    return out, res
 
 
 def make_exchange(objective, device=None, group=None):
