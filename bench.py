@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu-queens", type=int, default=0,
                     help="board size of the bounded CPU sample of the queens workload (default: 13-queens, ~10 s per run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-target", type=int, default=0, help="frames of the expanded root frontier (0: the library's default)")
     return ap.parse_args()
 
 
@@ -265,6 +266,8 @@ def run_ours(args):
     order = cb.host.ORDER_NAMES[args.order]
     objective = {"queens": cb.OBJ_ALL, "wcet": cb.OBJ_MAX, "sat200": cb.OBJ_ANY}[args.workload]
     solve_kw = dict(order=order)
+    if args.split_target > 0:
+        solve_kw["split_target"] = args.split_target
     if args.workload == "sat200":
         solve_kw["prefer_failing"] = True          # the reference's defaults: -f true ...
         if world == 1:

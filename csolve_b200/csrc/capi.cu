@@ -772,82 +772,115 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     }
     return CSOLVE_OK;
   };
-  // Ranks of a comm: rank 0 alone expands the root; the others take the frontier from rank 0's segment (below).
-  // part_rank / part_count: 0 / 1 with a shared frontier; the comm's rank / world when the frontier did not fit the
-  // segment and every rank expands for itself (path-hash partition, as without a comm).
+  // Ranks of a comm.
+  // ANY / MIN / MAX: rank 0 alone expands the root; the others take the frontier from rank 0's segment and every rank
+  //   claims frames of that ONE frontier in its own order (part_rank / part_count = 0 / 1) -- the value order's
+  //   preferred sub-trees are searched first, by everybody.
+  // ALL (and whenever the frontier does not fit the segment): every rank expands for itself and keeps the frames whose
+  //   path hash maps to it (part_rank / part_count = rank / world): the frontier, its claim counter and all frame reads
+  //   are local. Measured on 8 x B200, 16-queens: with the shared frontier the seven remote ranks claimed 75-110 M
+  //   nodes' worth of frames against rank 0's 143 M (10.0 ms); finer frontiers balanced it but rank 0's longer
+  //   expansion, during which the others wait, ate the gain (7.9 ms); replicated expansion + hash partition: 7.2 ms.
+  // Either way the ranks serve each other's donation rings over NVLink, so the partition only has to be roughly even.
   const int32_t *front_pool = nullptr;
   SearchCtl *front_ctl = dctl;
   COMM_TRACE(c, "set up");
-  if (c == nullptr || c->rank == 0) {
-    rc = expand_root();
-    if (rc != CSOLVE_OK) return rc;
-  }
-  COMM_TRACE(c, "expanded");
-  if (n_items < 0) n_items = -n_items;
-  if (c != nullptr) {
-    if (c->rank == 0) {
-      // the previous epoch's frontier is overwritten: every peer must have left that search
-      if (!comm_wait(c, c->block(0), [&](const CommBlock &b) {
-            for (int r = 1; r < c->world; r++) if (b.done_epoch[r] < epoch - 1) return false;
-            return true; }, COMM_WAIT_S, nullptr))
-        return fail(CSOLVE_ERR_CUDA, "comm: a peer rank did not finish the previous search");
-      const size_t bytes = (size_t)n_items * fw * sizeof(int32_t);
-      int32_t hdr[3] = {epoch, stopped ? 0 : n_items, fw};      // ANY solved by the expansion itself: nothing to share
-      if (bytes <= c->front_bytes) {
-        if (bytes) CUDA_TRY(cudaMemcpyAsync(c->front_of(0), pin, bytes, cudaMemcpyDeviceToDevice, st));
-        front_pool = c->front_of(0);
-      } else {
-        hdr[1] = -1;                              // does not fit: every rank expands for itself
-        part_rank = 0; part_count = c->world;
-      }
-      // every rank starts the epoch active; the count lives in rank 0's block (CommBlock::active64)
-      {
-        const unsigned long long act = ((unsigned long long)(uint32_t)epoch << 32) | (unsigned)c->world;
-        CUDA_TRY(cudaMemcpyAsync(&c->block(0)->active64, &act, sizeof(act), cudaMemcpyHostToDevice, st));
-        for (int r = 0; r < c->world; r++) CUDA_TRY(cudaMemcpyAsync(&c->block(r)->busy_epoch, &epoch, sizeof(int32_t), cudaMemcpyDefault, st));
-      }
+  const bool own_front = c != nullptr && m.objective == CSOLVE_OBJ_ALL && getenv("CSOLVE_COMM_SHARED_FRONT") == nullptr;
+  // rank 0 opens the epoch: every rank starts it active (the count lives in rank 0's block, CommBlock::active64), then
+  // the header the peers wait for. front_n >= 0: that many frames are in rank 0's segment; -1: every rank expands.
+  auto publish_epoch = [&](int front_n) -> int {
+    // the previous epoch's frontier / counters are overwritten: every peer must have left that search
+    if (!comm_wait(c, c->block(0), [&](const CommBlock &b) {
+          for (int r = 1; r < c->world; r++) if (b.done_epoch[r] < epoch - 1) return false;
+          return true; }, COMM_WAIT_S, nullptr))
+      return fail(CSOLVE_ERR_CUDA, "comm: a peer rank did not finish the previous search");
+    const int32_t hdr[3] = {epoch, front_n, fw};
+    const unsigned long long act = ((unsigned long long)(uint32_t)epoch << 32) | (unsigned)c->world;
+    CUDA_TRY(cudaMemcpyAsync(&c->block(0)->active64, &act, sizeof(act), cudaMemcpyHostToDevice, st));
+    for (int r = 0; r < c->world; r++) CUDA_TRY(cudaMemcpyAsync(&c->block(r)->busy_epoch, &epoch, sizeof(int32_t), cudaMemcpyDefault, st));
+    if (front_n >= 0) {
       // the frontier's claim counter must be zero before anybody sees the frontier
       ctl.init_next = 0;
       CUDA_TRY(cudaMemcpyAsync(&dctl->init_next, &ctl.init_next, sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(&c->block(0)->front_n, &hdr[1], 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      CUDA_TRY(cudaMemcpyAsync(&c->block(0)->front_epoch, &hdr[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      front_published = true;
+    }
+    CUDA_TRY(cudaMemcpyAsync(&c->block(0)->front_n, &hdr[1], 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpyAsync(&c->block(0)->front_epoch, &hdr[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    front_published = true;
+    return CSOLVE_OK;
+  };
+  // the other ranks wait for it on the device (one thread polls rank 0's block over NVLink), then ONE copy of what it saw
+  auto await_epoch = [&](CommBlock *b) -> int {
+    CUDA_TRY(launch_comm_wait_front(c->block(0), epoch, COMM_WAIT_S, c->copy_block(), st));
+    CUDA_TRY(cudaMemcpyAsync(&c->hblk[0], c->copy_block(), sizeof(CommBlock), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *b = c->hblk[0];
+    if (b->front_epoch < epoch) return fail(CSOLVE_ERR_CUDA, "comm: rank 0 did not open the search");
+    if (b->front_epoch != epoch || b->front_n == -2) return fail(CSOLVE_ERR_CUDA, "comm: rank 0 failed or the ranks are out of step");
+    return CSOLVE_OK;
+  };
+  if (c == nullptr) {
+    rc = expand_root();
+    if (rc != CSOLVE_OK) return rc;
+    if (n_items < 0) n_items = -n_items;
+  } else if (own_front) {
+    part_rank = c->rank; part_count = c->world;
+    if (c->rank == 0) { rc = publish_epoch(-1); if (rc != CSOLVE_OK) return rc; }     // the peers are not kept waiting for rank 0's expansion
+    rc = expand_root();
+    if (rc != CSOLVE_OK) return rc;
+    if (n_items < 0) n_items = -n_items;
+    COMM_TRACE(c, "expanded");
+    if (c->rank != 0) {
+      CommBlock b;
+      rc = await_epoch(&b);
+      if (rc != CSOLVE_OK) return rc;
+      if (b.front_n != -1) return fail(CSOLVE_ERR_INVALID, "comm: the ranks loaded different models");
+    }
+  } else if (c->rank == 0) {
+    rc = expand_root();
+    if (rc != CSOLVE_OK) return rc;
+    if (n_items < 0) n_items = -n_items;
+    COMM_TRACE(c, "expanded");
+    const size_t bytes = (size_t)n_items * fw * sizeof(int32_t);
+    int front_n = stopped ? 0 : n_items;           // ANY solved by the expansion itself: nothing to share
+    if (bytes <= c->front_bytes) {
+      if (bytes) CUDA_TRY(cudaMemcpyAsync(c->front_of(0), pin, bytes, cudaMemcpyDeviceToDevice, st));
+      front_pool = c->front_of(0);
     } else {
-      // wait on the device (one thread polls rank 0's block over NVLink), then ONE copy of what it saw
-      CUDA_TRY(launch_comm_wait_front(c->block(0), epoch, COMM_WAIT_S, c->copy_block(), st));
-      CUDA_TRY(cudaMemcpyAsync(&c->hblk[0], c->copy_block(), sizeof(CommBlock), cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      const CommBlock b = c->hblk[0];
-      if (b.front_epoch < epoch) return fail(CSOLVE_ERR_CUDA, "comm: rank 0 did not publish the root frontier");
-      if (b.front_epoch != epoch || b.front_n == -2) return fail(CSOLVE_ERR_CUDA, "comm: rank 0 failed or the ranks are out of step");
-      if (b.front_n >= 0) {
-        if (b.front_fw != fw) return fail(CSOLVE_ERR_INVALID, "comm: the ranks loaded different models");
-        n_items = b.front_n;
-        front_pool = c->front_of(0);
-        front_ctl = c->ctl_of(0);
-      } else {
-        part_rank = c->rank; part_count = c->world;
-        rc = expand_root();
-        if (rc != CSOLVE_OK) return rc;
-        if (n_items < 0) n_items = -n_items;
-      }
+      front_n = -1;                                // does not fit: every rank expands for itself
+      part_rank = 0; part_count = c->world;
+    }
+    rc = publish_epoch(front_n);
+    if (rc != CSOLVE_OK) return rc;
+  } else {
+    CommBlock b;
+    rc = await_epoch(&b);
+    if (rc != CSOLVE_OK) return rc;
+    if (b.front_n >= 0) {
+      if (b.front_fw != fw) return fail(CSOLVE_ERR_INVALID, "comm: the ranks loaded different models");
+      n_items = b.front_n;
+      front_pool = c->front_of(0);
+      front_ctl = c->ctl_of(0);
+    } else {
+      part_rank = c->rank; part_count = c->world;
+      rc = expand_root();
+      if (rc != CSOLVE_OK) return rc;
+      if (n_items < 0) n_items = -n_items;
     }
   }
-  COMM_TRACE(c, "frontier published / seen");
-  CUDA_TRY(cudaEventRecord(ev1, st));
-
   // ---- partition: every rank holds the whole frontier; the search kernel skips the frames whose path
   //      hash maps to another rank (no copy, no compaction)
   a.part_rank = part_rank; a.part_count = part_count;
 
-  if (part_count > 1 && part_rank != 0) {
+  if (part_count > 1 && part_rank != 0 && front_pool == nullptr) {
     // the expansion was replicated on every rank (also when it exhausted the whole tree):
     // only rank 0 reports its counters and the leaves found in it
     CUDA_TRY(cudaMemsetAsync(p->wcount, 0, (size_t)p->n_warps * CNT_WIDTH * sizeof(unsigned long long), st));
     if (m.objective == CSOLVE_OBJ_ALL) ctl.n_stored = 0;
   }
+  COMM_TRACE(c, "frontier published / seen");
+  CUDA_TRY(cudaEventRecord(ev1, st));
 
   // ---- time-sliced persistent search -----------------------------------------------------------------------
   a.items = pin; a.items_out = nullptr;
@@ -856,24 +889,12 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   a.front_pool = front_pool != nullptr ? front_pool : pin;
   a.front_ctl = front_ctl;
   a.total_warps = p->n_warps * (front_pool != nullptr ? c->world : 1);
-  const bool cross = c != nullptr && front_pool != nullptr;     // one frontier for all ranks: they also serve each other's tickets
-  a.front_stride = 1;
-  if (cross && m.objective == CSOLVE_OBJ_ALL && n_items > 64) {
-    // Frames that are neighbours in the frontier are siblings and cousins: their sub-trees are of similar size (the
-    // first rows of N-queens: the corner columns leave the largest ones). Handed out in frontier order, the rank whose
-    // warps start first -- rank 0, it has no hop to make -- takes the whole expensive end (measured on 8 GPUs: 143 M
-    // of 836 M nodes on rank 0, 75-110 M on the others, which then lived on donations). The claims walk the frontier
-    // with a stride near n / golden ratio instead; every rank computes the same one. ANY / MIN / MAX keep the
-    // frontier's own order: there the first frames are the ones the value order prefers.
-    int s = (int)((double)n_items * 0.6180339887) | 1;
-    auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
-    while (gcd(s, n_items) != 1) s += 2;
-    a.front_stride = s % n_items;
-  }
+  const bool cross = c != nullptr;     // the ranks serve each other's donation rings, whichever way the frontier was dealt
   if (c != nullptr) {
     a.comm = c->block(c->rank); a.epoch = epoch; a.rank = c->rank; a.world = c->world; a.n_peers = c->world - 1;
     for (int r = 0; r < c->world; r++) a.peer_comm[r] = c->block(r);
   }
+  a.peer_demand = cross && getenv("CSOLVE_COMM_NO_DEMAND") == nullptr ? 1 : 0;
   if (cross) {
     // the donation ring lives in the rank's segment, where the peers can reach it; slot numbers are the same on
     // every rank (n_initial .. n_initial + ring), so the pointers are shifted by the frontier's length
@@ -930,6 +951,8 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   for (;;) {
     if (!local_done) {
       COMM_TRACE(c, "launch search slice");
+      // the peers may serve this rank's tickets while its kernel runs (k_rebalance closes the ring again)
+      if (cross) CUDA_TRY(cudaMemcpyAsync(&c->block(c->rank)->ring_open, &epoch, sizeof(int32_t), cudaMemcpyHostToDevice, st));
       CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
       if (getenv("CSOLVE_DEBUG_SYNC")) {
         const cudaError_t es = cudaStreamSynchronize(st);

@@ -530,11 +530,10 @@ struct Claim {
   bool drained;                // the root frontier has been handed out completely
 };
 
-// claim number -> frame of the root frontier (SearchArgs::front_stride)
-__device__ __forceinline__ int front_index(const SearchArgs &a, int claim) {
-  return a.front_stride > 1 ? (int)((unsigned long long)(unsigned)claim * (unsigned)a.front_stride % (unsigned)a.n_initial) : claim;
-}
-
+// DEMAND: the waiting loop carries the request to the peer ranks (see there). Compiled out of the lane-owns-variable
+// kernel: its trees are dealt evenly by the path hash, and the mere presence of that code in the waiting path moved
+// the compiler's choices in the node loop (16-queens: 16.22 -> 15.88 G nodes/s on one GPU, A/B on the same box).
+template <bool DEMAND>
 __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &hungry, Claim &cl, int *blk_hungry, long long t0) {
   if (cl.mask) {
     const int b = __ffs((int)cl.mask) - 1;
@@ -574,8 +573,17 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
           bool leave = false;
           if ((spins & 3u) == 3u) {
             if (a.n_peers > 0 && *reinterpret_cast<volatile int *>(&a.comm->stop_epoch) == a.epoch) atomicMax(&ctl->signal, SIG_STOP);
+            const int n_hungry = *reinterpret_cast<volatile int *>(&ctl->hungry);
+            // Ranks of a comm: when this GPU is running out of donors (three quarters of its warps are waiting) a peer
+            // is asked to serve some of its tickets over NVLink -- while this kernel keeps running. (Asking earlier,
+            // whenever an eighth of the warps held unserved tickets, cost 16-queens on 8 GPUs 17 %: in the second half
+            // of such a search every rank is short of frames now and then, and a hand-off over NVLink stalls the donor
+            // for several round trips.) The request is a LEVEL in the peer's block (stale requests do not pile up),
+            // the peers take turns, and a busy warp over there serves a ticket like a local donor (donation_target).
+            if (DEMAND && a.peer_demand && n_hungry * 4 >= a.n_warps * 3 && (spins & 31u) == 3u)
+              atomicMax_system(&a.peer_comm[(a.rank + 1 + (int)((unsigned)(tslot + (int)(spins >> 5)) % (unsigned)a.n_peers)) % a.world]->demand[a.rank], n_hungry / a.n_peers + 1);
             if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) leave = true;
-            else if (*reinterpret_cast<volatile int *>(&ctl->hungry) >= a.n_warps || clock64() - t0 > a.slice_cycles) {
+            else if (n_hungry >= a.n_warps || clock64() - t0 > a.slice_cycles) {
               // every warp is waiting: nothing left anywhere -- or the time slice is over. Waiters watch the clock too:
               // if fewer blocks are resident than the launch assumed (another context on the device, a profiler),
               // `hungry` can never reach n_warps and the resident warps would wait for ever.
@@ -604,7 +612,7 @@ __device__ __forceinline__ int claim_frame(const SearchArgs &a, int lane, bool &
       const int idx = it + lane;
       bool mine = lane < n && idx < a.n_initial;
       if (mine && a.part_count > 1)
-        mine = (unsigned)__ldcg(&a.front_pool[(size_t)front_index(a, idx) * fw + 7]) % (unsigned)a.part_count == (unsigned)a.part_rank;
+        mine = (unsigned)__ldcg(&a.front_pool[(size_t)idx * fw + 7]) % (unsigned)a.part_count == (unsigned)a.part_rank;
       const unsigned mk = __ballot_sync(FULL, mine);
       if (mk) {
         cl.base = it;
@@ -708,7 +716,7 @@ __device__ __forceinline__ bool restart_due(const SearchArgs &a, int lane, unsig
 
 // frame of a claimed slot: the first n_initial slots are the root frontier (possibly on another GPU), the rest the ring
 __device__ __forceinline__ const int *claimed_frame(const SearchArgs &a, int slot) {
-  return slot < a.n_initial ? a.front_pool + (size_t)front_index(a, slot) * a.m.frame_words : a.pool + (size_t)slot * a.m.frame_words;
+  return (slot < a.n_initial ? a.front_pool : a.pool) + (size_t)slot * a.m.frame_words;
 }
 
 // ---- ranks of a csolve_gpu_comm: incumbent and first-solution exchange over peer memory -------------------------
@@ -800,7 +808,7 @@ k_search(const SearchArgs a) {
       } else {
         const long long w0 = clock64();
         lastwork = w0 - t0;
-        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
+        const int slot = claim_frame<true>(a, lane, hungry, cl, &s_blk_hungry, t0);
         waited += clock64() - w0;
         if (slot < 0) break;
         claims++;
@@ -1369,7 +1377,7 @@ k_search_lov(const SearchArgs a) {
       } else {
         const long long w0 = clock64();
         lastwork = w0 - t0;
-        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
+        const int slot = claim_frame<false>(a, lane, hungry, cl, &s_blk_hungry, t0);
         waited += clock64() - w0;
         if (slot < 0) break;
         claims++;
@@ -1927,7 +1935,7 @@ k_search_lovk(const SearchArgs a) {
         if (it >= ctl->item_count) break;
         src = a.items + (size_t)it * fw;
       } else {
-        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
+        const int slot = claim_frame<true>(a, lane, hungry, cl, &s_blk_hungry, t0);
         if (slot < 0) break;
         src = claimed_frame(a, slot);
         ring_slot = slot;
@@ -2519,7 +2527,7 @@ k_search_sat(const SearchArgs a) {
       } else {
         const long long w0 = clock64();
         lastwork = w0 - t0;
-        const int slot = claim_frame(a, lane, hungry, cl, &s_blk_hungry, t0);
+        const int slot = claim_frame<true>(a, lane, hungry, cl, &s_blk_hungry, t0);
         waited += clock64() - w0;
         if (slot < 0) break;
         claims++;
@@ -2794,7 +2802,17 @@ k_rebalance(const SearchArgs a, int32_t *scratch) {
   int *idle_list = scratch + 4;
   int *donor_list = idle_list + nw;
   __shared__ int n_idle, n_donor, idle_done, busy, moved;
-  if (threadIdx.x == 0) { n_idle = 0; n_donor = 0; idle_done = 0; busy = 0; moved = 0; }
+  if (threadIdx.x == 0) {
+    n_idle = 0; n_donor = 0; idle_done = 0; busy = 0; moved = 0;
+    if (a.n_peers > 0 && a.peer_ready[a.rank] != nullptr) {
+      // ranks of a comm: the peers serve this rank's ring while its search kernel runs; the ring is closed (and the
+      // visitors already inside waited for) before its counters are looked at and rebased below
+      atomicExch_system(&a.comm->ring_open, 0);
+      __threadfence_system();
+      while (*reinterpret_cast<volatile int *>(&a.comm->inflight) > 0) __nanosleep(200);
+      __threadfence_system();
+    }
+  }
   __syncthreads();
   for (int w = threadIdx.x; w < nw; w += blockDim.x) {
     if (a.wstate[w].level >= a.wstate[w].base || a.wstate[w].claim_mask != 0u) atomicAdd(&busy, 1);   // claimed root-frontier frames are work too

@@ -154,9 +154,7 @@ struct SearchArgs {
   int32_t rank, world;
   int32_t epoch;
   int32_t total_warps;        // search warps of all ranks (size of a guided chunk)
-  int32_t front_stride;       // > 1: claim number i of the root frontier is frame (i * front_stride) % n_initial -- a bijection
-                              // (the stride is coprime to n_initial) that scatters neighbouring frames, whose sub-trees are
-                              // of similar size, over the ranks and over time (ALL models on a shared frontier)
+  int32_t peer_demand;        // ranks of a comm: a starving rank asks its peers for frames while its kernel runs (claim_frame)
   // Parity instrumentation (csolve_solve_options.sample_mod > 0; runs the SAMPLE instances of the search kernels):
   // every search node -- executed or counted in bulk -- whose identity hash (parent domains, variable, value) is 0
   // modulo sample_mod is written to sample_rec as
