@@ -212,14 +212,16 @@ def measured_peak_gbs():
 
 def measured_traffic(kernel, workload):
     """real DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum), None when there is no capture"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f)
-        if t.get("kernel") == kernel and t.get("workload") == workload:
-            return float(t["dram_bytes_per_launch"])
-    except Exception:
-        pass
+    (profiles/r2_traffic.json, r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum), None when there is no capture"""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            for e in (t if isinstance(t, list) else [t]):
+                if e.get("kernel") == kernel and e.get("workload") == workload:
+                    return float(e["dram_bytes_per_launch"])
+        except Exception:
+            pass
     return None
 
 
@@ -260,7 +262,12 @@ def run_ours(args):
             if int(t.item()) == 0:
                 comm = None
             else:
-                mode = "shared frontier x%d (claims and incumbents over NVLink peer memory)" % world
+                if args.workload == "queens":
+                    mode = ("csolve_gpu_comm x%d: ALL model, every rank expands the root and searches the frames of its "
+                            "path-hash share (no data-path exchange; results summed)" % world)
+                else:
+                    mode = ("csolve_gpu_comm x%d: shared root frontier, incumbents / first solution and donated frames "
+                            "over NVLink peer memory" % world)
 
     text = workload_text(args)
     order = cb.host.ORDER_NAMES[args.order]
@@ -347,7 +354,7 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         achieved = (my_nodes * bytes_per_node) / (search_ms / 1000.0) / 1e9 if search_ms > 0 else 0.0
         kernel = {"queens": "k_search_lov<false,true>" if args.queens <= 32 else "k_search<false>",
-                  "wcet": "k_search<false,false,LIN=true>", "sat200": "k_search<false,false,LIN=false>"}[args.workload]
+                  "wcet": "k_search<false,false,LIN=true>", "sat200": "k_search_sat<false>"}[args.workload]
         line = {
             "metric": METRIC, "value": tot_nodes / (dev_ms / 1000.0), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,

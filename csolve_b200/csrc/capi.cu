@@ -775,13 +775,17 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   // Ranks of a comm.
   // ANY / MIN / MAX: rank 0 alone expands the root; the others take the frontier from rank 0's segment and every rank
   //   claims frames of that ONE frontier in its own order (part_rank / part_count = 0 / 1) -- the value order's
-  //   preferred sub-trees are searched first, by everybody.
-  // ALL (and whenever the frontier does not fit the segment): every rank expands for itself and keeps the frames whose
-  //   path hash maps to it (part_rank / part_count = rank / world): the frontier, its claim counter and all frame reads
-  //   are local. Measured on 8 x B200, 16-queens: with the shared frontier the seven remote ranks claimed 75-110 M
-  //   nodes' worth of frames against rank 0's 143 M (10.0 ms); finer frontiers balanced it but rank 0's longer
-  //   expansion, during which the others wait, ate the gain (7.9 ms); replicated expansion + hash partition: 7.2 ms.
-  // Either way the ranks serve each other's donation rings over NVLink, so the partition only has to be roughly even.
+  //   preferred sub-trees are searched first, by everybody; incumbents and "found" travel over peer memory, and the
+  //   ranks serve each other's donation rings over NVLink (3-SAT n=200 seed 1 on 8 x B200: 7.4 ms, 14.1 ms on one).
+  // ALL: every rank expands for itself, keeps the frames whose path hash maps to it (part_rank / part_count = rank /
+  //   world) and searches them on its own -- no data-path exchange at all, the results are summed by the caller.
+  //   Measured on 8 x B200, 16-queens (one GPU: 51.7 ms):
+  //     shared frontier, remote claims                      10.0 ms  (rank 0 143 M nodes, the others 75-110 M + donations)
+  //     shared frontier of 4 x / 16 x as many frames          7.9 / 8.5 ms  (balanced, but rank 0's expansion is serial)
+  //     own frontiers + rings served across ranks             7.75 ms (hand-offs over NVLink in the end game stall the donors)
+  //     own frontiers, nothing shared                         7.14 ms
+  //   The path hash deals sub-trees to within 2 %, which no exchange on a 7 ms search can beat.
+  // The same partition is used when a shared frontier does not fit rank 0's segment.
   const int32_t *front_pool = nullptr;
   SearchCtl *front_ctl = dctl;
   COMM_TRACE(c, "set up");
@@ -825,18 +829,13 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     if (rc != CSOLVE_OK) return rc;
     if (n_items < 0) n_items = -n_items;
   } else if (own_front) {
+    // nothing is shared in this search: no frontier, no ring, no incumbent -- the ranks do not even have to meet
     part_rank = c->rank; part_count = c->world;
-    if (c->rank == 0) { rc = publish_epoch(-1); if (rc != CSOLVE_OK) return rc; }     // the peers are not kept waiting for rank 0's expansion
+    front_published = true;
     rc = expand_root();
     if (rc != CSOLVE_OK) return rc;
     if (n_items < 0) n_items = -n_items;
     COMM_TRACE(c, "expanded");
-    if (c->rank != 0) {
-      CommBlock b;
-      rc = await_epoch(&b);
-      if (rc != CSOLVE_OK) return rc;
-      if (b.front_n != -1) return fail(CSOLVE_ERR_INVALID, "comm: the ranks loaded different models");
-    }
   } else if (c->rank == 0) {
     rc = expand_root();
     if (rc != CSOLVE_OK) return rc;
@@ -889,12 +888,22 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
   a.front_pool = front_pool != nullptr ? front_pool : pin;
   a.front_ctl = front_ctl;
   a.total_warps = p->n_warps * (front_pool != nullptr ? c->world : 1);
-  const bool cross = c != nullptr;     // the ranks serve each other's donation rings, whichever way the frontier was dealt
-  if (c != nullptr) {
+  const bool cross = c != nullptr && !own_front;     // the ranks serve each other's donation rings
+  if (c != nullptr && !own_front) {
     a.comm = c->block(c->rank); a.epoch = epoch; a.rank = c->rank; a.world = c->world; a.n_peers = c->world - 1;
     for (int r = 0; r < c->world; r++) a.peer_comm[r] = c->block(r);
   }
-  a.peer_demand = cross && getenv("CSOLVE_COMM_NO_DEMAND") == nullptr ? 1 : 0;
+  // Branch-and-bound: a rank that ran dry does not ask its peers for frames during the first COMM_BNB_GRACE_MS of a
+  // search. Sub-trees handed to another GPU are searched against an incumbent that arrives late, and on a tree as
+  // narrow as wcet's (330 k nodes, 6 ms on one GPU) that is all the extra GPUs ever do: 2 GPUs searched 2.4 x the
+  // nodes in 10 ms. A search that lasts longer than the grace period is worth sharing.
+  const double COMM_BNB_GRACE_MS = 20.0;
+  auto demand_allowed = [&]() {
+    if (!cross || getenv("CSOLVE_COMM_NO_DEMAND") != nullptr) return false;
+    if (m.obj_var < 0) return true;
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count() >= COMM_BNB_GRACE_MS;
+  };
+  a.peer_demand = demand_allowed() ? 1 : 0;
   if (cross) {
     // the donation ring lives in the rank's segment, where the peers can reach it; slot numbers are the same on
     // every rank (n_initial .. n_initial + ring), so the pointers are shifted by the frontier's length
@@ -952,7 +961,10 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     if (!local_done) {
       COMM_TRACE(c, "launch search slice");
       // the peers may serve this rank's tickets while its kernel runs (k_rebalance closes the ring again)
-      if (cross) CUDA_TRY(cudaMemcpyAsync(&c->block(c->rank)->ring_open, &epoch, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      if (cross) {
+        CUDA_TRY(cudaMemcpyAsync(&c->block(c->rank)->ring_open, &epoch, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        a.peer_demand = demand_allowed() ? 1 : 0;
+      }
       CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
       if (getenv("CSOLVE_DEBUG_SYNC")) {
         const cudaError_t es = cudaStreamSynchronize(st);
@@ -1007,7 +1019,8 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
         // them, until one arrives -- or until no rank is active any more: the search is over everywhere.
         for (unsigned spin = 0;; spin++) {
           int32_t stt[4] = {0, 0, 0, 0};
-          CUDA_TRY(launch_comm_state(a, std::max(p->n_warps / (4 * (c->world - 1)), 32), 0, d_cstate, st)); launches++;   // per peer and per look: the ring holds 4 x n_warps frames
+          // per peer and per look: the ring holds 4 x n_warps frames
+          CUDA_TRY(launch_comm_state(a, demand_allowed() ? std::max(p->n_warps / (4 * (c->world - 1)), 32) : 0, 0, d_cstate, st)); launches++;
           CUDA_TRY(cudaMemcpyAsync(stt, d_cstate, sizeof(stt), cudaMemcpyDeviceToHost, st));
           CUDA_TRY(cudaStreamSynchronize(st));
           if (stt[2]) break;                                   // ANY: a peer has a solution

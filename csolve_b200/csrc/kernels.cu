@@ -3025,17 +3025,22 @@ __global__ void k_comm_wait_front(const CommBlock *root, int epoch, unsigned lon
   for (int i = 0; i < (int)(sizeof(CommBlock) / sizeof(int)); i++) dst[i] = src[i];
 }
 
-__global__ void k_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out) {
+// sums the per-warp counters: thread t of a block always adds the same counter (the stride is a multiple of CNT_WIDTH),
+// consecutive threads read consecutive words. `out` is zeroed by the caller. (One block of 256 threads walking the
+// rows one after the other took 55-60 us for 4 736 warps -- of a search that takes 7 ms on eight GPUs.)
+static const int REDUCE_THREADS = 85 * CNT_WIDTH;      // 1020
+__global__ void __launch_bounds__(1024)
+k_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out) {
   __shared__ unsigned long long acc[CNT_WIDTH];
   if (threadIdx.x < CNT_WIDTH) acc[threadIdx.x] = 0;
   __syncthreads();
-  unsigned long long loc[CNT_WIDTH];
-  for (int k = 0; k < CNT_WIDTH; k++) loc[k] = 0;
-  for (int w = threadIdx.x; w < n_warps; w += blockDim.x)
-    for (int k = 0; k < CNT_WIDTH; k++) loc[k] += wcount[(size_t)w * CNT_WIDTH + k];
-  for (int k = 0; k < CNT_WIDTH; k++) atomicAdd(&acc[k], loc[k]);
+  const size_t total = (size_t)n_warps * CNT_WIDTH;
+  unsigned long long sum = 0;
+  if (threadIdx.x < REDUCE_THREADS)
+    for (size_t i = (size_t)blockIdx.x * REDUCE_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * REDUCE_THREADS) sum += wcount[i];
+  if (sum) atomicAdd(&acc[threadIdx.x % CNT_WIDTH], sum);
   __syncthreads();
-  if (threadIdx.x < CNT_WIDTH) out[threadIdx.x] = acc[threadIdx.x];
+  if (threadIdx.x < CNT_WIDTH && acc[threadIdx.x]) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
 }
 
 // ---- parity hook: independent node transitions ------------------------------------------------------
@@ -3246,7 +3251,10 @@ cudaError_t launch_import_frames(const SearchArgs &a, const int32_t *in, int n_f
 }
 
 cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps, unsigned long long *out, cudaStream_t st) {
-  k_reduce_counters<<<1, 256, 0, st>>>(wcount, n_warps, out);
+  cudaError_t e = cudaMemsetAsync(out, 0, CNT_WIDTH * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  const int grid = (int)std::min<size_t>(32, ((size_t)n_warps * CNT_WIDTH + REDUCE_THREADS - 1) / REDUCE_THREADS);
+  k_reduce_counters<<<std::max(grid, 1), 1024, 0, st>>>(wcount, n_warps, out);
   return cudaGetLastError();
 }
 
