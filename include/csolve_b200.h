@@ -241,9 +241,13 @@ int csolve_gpu_import_frames(csolve_gpu_problem *p, const int32_t *frames, int32
  * (worker_spawn, src/csolve.c:105-152) and meet in a shared page (struct shared_t, src/csolve.h:259-266:
  * objective_best, solutions). Here the ranks of a csolve_gpu_comm (one GPU each, at most 8) do the same over
  * NVLink peer memory, with no host in the loop while the search runs:
- *   - rank 0 expands the root breadth-first and leaves the frontier in its segment; EVERY rank claims chunks of that
- *     one frontier with a system-scope atomicAdd on rank 0's counter, so all GPUs run out of root frames together
- *     whatever the sizes of the sub-trees (no static partition);
+ *   - ANY / MIN / MAX models: rank 0 expands the root breadth-first and leaves the frontier in its segment; EVERY rank
+ *     claims frames of that one frontier with a system-scope atomicAdd on rank 0's counter (the sub-trees the value
+ *     order prefers are searched first, by everybody); a rank that is running out of work has its donation ring served
+ *     by the busy warps of its peers over NVLink, exactly like the tickets of its own waiting warps;
+ *   - ALL models: every rank expands the root for itself and searches the frames whose path hash maps to it; nothing is
+ *     exchanged while the search runs (measured on 8 x B200: every form of sharing cost more than the 2 % the hash
+ *     partition is off by, profiles/r2_scaling.md);
  *   - an improving incumbent (MIN / MAX) and "a solution exists" (ANY) are stored straight into every peer's
  *     control block by the warp that found them (8 bytes, epoch-tagged, system-scope atomicMin / atomicMax);
  *   - each rank returns its own counters; their sum / the best incumbent is the result (csolve_gpu_group_solve does
@@ -255,7 +259,7 @@ int csolve_gpu_import_frames(csolve_gpu_problem *p, const int32_t *frames, int32
  *     <all-gather mine -> all>;                            csolve_gpu_comm_connect(c, all);
  * One process, several GPUs: csolve_gpu_group_* below (host threads, direct peer access) -- what the drop-in
  * solve() uses for `-j N`. frontier_bytes: capacity of rank 0's frontier buffer (0 = 256 MiB); a frontier that does
- * not fit falls back to "every rank expands, frames are partitioned by path hash". */
+ * not fit falls back to "every rank expands, frames are partitioned by path hash" (what ALL models always do). */
 #define CSOLVE_COMM_HANDLE_BYTES 64
 typedef struct csolve_gpu_comm csolve_gpu_comm;
 int  csolve_gpu_comm_create(int32_t device, int32_t rank, int32_t world, size_t frontier_bytes, csolve_gpu_comm **out);
