@@ -341,6 +341,7 @@ extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device
   d = p->cm.host;
   if (getenv("CSOLVE_NO_LOV")) { d.lov = 0; d.lovk = 0; d.frame_words = frame_words(d.n_vars, d.mask_words); }   // development switch: general kernels only
   if (getenv("CSOLVE_NO_SAT")) d.sat = 0;
+  if (getenv("CSOLVE_NO_ADJ")) d.lov_adj_only = 0;
   if (getenv("CSOLVE_NO_DENSE")) d.dense = 0;
   std::vector<unsigned char> image;
   struct Part { size_t off; const void *src; size_t bytes; const void **field; };
@@ -353,7 +354,7 @@ extern "C" int csolve_gpu_load_device(const csolve_flat_model *m, int32_t device
   };
 #define UP(field, vec) add(p->cm.vec.data(), p->cm.vec.size() * sizeof(p->cm.vec[0]), (const void **)&d.field)
   UP(clause, clause); UP(watch_ptr, watch_ptr); UP(watch_idx, watch_idx); UP(wrec, wrec); UP(wrec_ptr, wrec_ptr);
-  UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst);
+  UP(lov_pair, lov_pair); UP(lov_cptr, lov_cptr); UP(lov_cval, lov_cval); UP(lov_fconst, lov_fconst); UP(lov_adj, lov_adj);
   UP(lin, lin); UP(lin_term, lin_term); UP(linrel, linrel); UP(dense_form, dense_form); UP(sat_occ_ptr, sat_occ_ptr); UP(sat_occ, sat_occ);
   UP(node_op, node_op); UP(node_l, node_l); UP(node_r, node_r); UP(node_first, node_first);
   UP(order, order); UP(prio, prio); UP(root_dom, root_dom);

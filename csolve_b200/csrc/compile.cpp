@@ -356,6 +356,17 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
     // constants outside the window can never sit on a bound: they are simply not representable (and not needed)
     out.host.lov_bits = (bits && K == 1) ? 1 : 0;
     out.host.lov_vbase = vmin;
+    // all-different style networks: offset 0 only -> adjacency bit matrix (device_model.h: lov_adj)
+    out.lov_adj.assign((size_t)V * K, 0u);
+    bool adj_only = bits && K >= 2;
+    for (int v = 0; v < V && adj_only; v++)
+      for (int j = 0; j < stride; j++) {
+        const unsigned long long e = out.lov_pair[(size_t)v * stride + j];
+        if (e == 0ull) continue;
+        if (e != (1ull << 32)) { adj_only = false; break; }
+        out.lov_adj[(size_t)v * K + (j >> 5)] |= 1u << (j & 31);
+      }
+    out.host.lov_adj_only = adj_only ? 1 : 0;
     out.lov_fconst.assign(V, 0u);
     if (bits) {
       for (int v = 0; v < V; v++)
@@ -428,6 +439,7 @@ int compile_model(const csolve_flat_model &m, CompiledModel &out, std::string &e
   h.lov_pair = out.lov_pair.data(); h.lov_cptr = out.lov_cptr.data(); h.lov_cval = out.lov_cval.data();
   h.n_lov_cval = (int32_t)out.lov_cval.size();
   h.lov_fconst = out.lov_fconst.data();
+  h.lov_adj = out.lov_adj.data();
   h.lov_smem_bytes = (int32_t)((((size_t)V * 32 * 2 + (V + 1) + out.lov_cval.size() + V) * 4 + 15) & ~(size_t)15);   // K == 1 only
   h.wrec_ptr = out.wrec_ptr.data();
   h.n_wrec = (int32_t)out.wrec.size();

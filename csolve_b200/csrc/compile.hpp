@@ -14,7 +14,7 @@ struct CompiledModel {
   std::vector<int32_t> wrec_ptr;
   std::vector<unsigned long long> lov_pair;
   std::vector<int32_t> lov_cptr, lov_cval;
-  std::vector<uint32_t> lov_fconst;
+  std::vector<uint32_t> lov_fconst, lov_adj;
   std::vector<int32_t> watch_ptr, watch_idx, node_l, node_r, node_first, order, prio, root_dom;
   std::vector<uint8_t> node_op;
   std::vector<int32_t> sat_occ_ptr;

@@ -95,6 +95,11 @@ struct DevModel {
   const int32_t *lov_cptr;   // [n_vars + 1]
   const int32_t *lov_cval;   // [n_lov_cval]
   const uint32_t *lov_fconst; // [n_vars] forbidden-value set of the constants (lov_bits)
+  // K-per-lane form of an all-different style network (every pair clause is x_i != x_j, offset 0: sudoku): the pair
+  // table is an adjacency bit matrix, lov_adj[i * K + q] bit l = variable l + 32 q shares a clause with variable i
+  // (972 bytes for sudoku instead of 62 KB of 64-bit offset sets). lov_adj_only: 1 when the model qualifies.
+  const uint32_t *lov_adj;    // [n_vars * K]
+  int32_t lov_adj_only;
   // "bit state" form (pure SAT: every variable's root domain lies in [0,1], every clause is a disjunction of at most
   // three literals): sat_occ_ptr[e] .. sat_occ_ptr[e + 1], e = var << 1 | value, are the clauses in which the
   // assignment var := value falsifies a literal; each record holds the clause's OTHER literals (code = var << 1 |

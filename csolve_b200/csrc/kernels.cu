@@ -1774,9 +1774,18 @@ __device__ __forceinline__ bool lovk_fixpoint(const DevModel &m, int lane, LovK<
         pq &= pq - 1;
         const int i = q * 32 + bit;
         const int w = __shfl_sync(FULL, x.lo[q], bit);
+        if (m.lov_adj_only) {
+          // all-different style network: one broadcast word per 32 variables says who shares a clause with variable i,
+          // and the only value they lose is w itself
+          const uint32_t wbit = 1u << (w - vbase);
 #pragma unroll
-        for (int q2 = 0; q2 < K; q2++)     // v >= V: zero entries of the table
-          x.F[q2] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + lane + 32 * q2]), w, vbase);
+          for (int q2 = 0; q2 < K; q2++)
+            x.F[q2] |= ((__ldg(&m.lov_adj[i * K + q2]) >> lane) & 1u) ? wbit : 0u;
+        } else {
+#pragma unroll
+          for (int q2 = 0; q2 < K; q2++)     // v >= V: zero entries of the table
+            x.F[q2] |= lov_forbid(__ldg(&m.lov_pair[(size_t)i * (32 * K) + lane + 32 * q2]), w, vbase);
+        }
         visits += (unsigned)V;
       }
     }

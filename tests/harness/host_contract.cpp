@@ -54,6 +54,7 @@ extern "C" int hc_load(const csolve_flat_model *m, int specialise) {
 extern "C" const char *hc_error() { return g_err.c_str(); }
 extern "C" int hc_n_linear() { return g_cm.host.n_lin; }
 extern "C" int hc_n_linrel() { return g_cm.host.n_linrel; }
+extern "C" int hc_lov_adj_only() { return g_cm.host.lov_adj_only; }
 extern "C" int hc_n_specialised() {
   int n = 0;
   for (auto &c : g_cm.clause) n += c.kind != CK_GENERIC;
@@ -116,11 +117,17 @@ extern "C" int hc_node_lov(const int32_t *dom_in, int var, int32_t val, int32_t 
   if (m.lov_bits || m.lovk) {
     // forbidden-value-set form (lov_forbid / lov_trim), lanes emulated one after the other
     const int vb = m.lov_vbase;
+    // the K-per-lane kernel reads an all-different style network through its adjacency bit matrix (lovk_fixpoint)
+    const int K = (V + 31) / 32;
+    auto forbid = [&](int i, int j, int32_t w) -> uint32_t {
+      if (m.lovk && m.lov_adj_only) return ((m.lov_adj[(size_t)i * K + (j >> 5)] >> (j & 31)) & 1u) ? 1u << (w - vb) : 0u;
+      return lov_forbid(m.lov_pair[(size_t)i * stride + j], w, vb);
+    };
     uint32_t F[128];
     for (int j = 0; j < V; j++) {
       F[j] = m.lov_fconst[j];
       for (int i = 0; i < V; i++)
-        if (dom_in[2 * i] == dom_in[2 * i + 1]) F[j] |= lov_forbid(m.lov_pair[(size_t)i * stride + j], dom_in[2 * i], vb);
+        if (dom_in[2 * i] == dom_in[2 * i + 1]) F[j] |= forbid(i, j, dom_in[2 * i]);
     }
     std::vector<int> pend(1, var);
     std::vector<uint8_t> in_pend(V, 0);
@@ -128,7 +135,7 @@ extern "C" int hc_node_lov(const int32_t *dom_in, int var, int32_t val, int32_t 
       const int i = pend[qi];
       const int32_t w = lo[i];
       for (int j = 0; j < V; j++) {
-        F[j] |= lov_forbid(m.lov_pair[(size_t)i * stride + j], w, vb);
+        F[j] |= forbid(i, j, w);
         const bool was = lo[j] == hi[j];
         if (!lov_trim(F[j], vb, lo[j], hi[j])) { failed = true; }
         else if (!was && lo[j] == hi[j] && !in_pend[j]) { in_pend[j] = 1; pend.push_back(j); }

@@ -69,6 +69,9 @@ def test_lane_owns_variable_form_on_host(name):
     m = cb.Model(INST[name])
     hc = util.harness_lib()
     assert hc.hc_load(m.flat, 1) == 0, hc.hc_error()
+    # sudoku is an all-different style network (every pair clause has offset 0): the K-per-lane kernel reads it through
+    # the adjacency bit matrix; the diagonals of N-queens carry offsets, so they keep the 64-bit offset sets
+    assert hc.hc_lov_adj_only() == (1 if name.startswith("sudoku") else 0)
 
     def node(dom, var, val, best):
         dom = np.ascontiguousarray(dom, np.int32)
