@@ -194,3 +194,62 @@ def test_rebalance_moves_frames_to_the_rank_that_ran_dry():
     assert len(ids1) > 40                                   # the idle rank took a real share
     assert outs[0][1]["solutions"] == 200 and outs[0][1] == outs[1][1]
     assert outs[0][1]["kernel_ms"] < 20                     # 200 frames at 10 per slice on one rank would be 20 slices
+
+
+# ---- solve_comm: the optimum's witness when the incumbent a rank reports is a peer's -------------------------------
+def _witness_worker(rank, world, port, lost, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import csolve_b200 as cb
+    from csolve_b200 import distributed as D
+
+    class _Model:
+        obj_var = 2
+
+    class CommFake:
+        """stands in for GpuProblem.solve(comm=...): both ranks end with the incumbent 7 (pushed over peer memory), only
+        rank 1 found it and holds the assignment -- unless `lost`, where its ring was overwritten"""
+        model = _Model()
+
+        def solve(self, comm=None, **kw):
+            r = _Res()
+            r.solutions = 3 if rank == 0 else 2
+            r.nodes, r.cuts, r.props, r.clause_visits, r.kernel_launches = 100 + rank, 50, 10, 20, 4
+            r.best, r.has_solution, r.timed_out = 7, 1, 0
+            r.kernel_ms, r.expand_ms = 5.0 + rank, 0.25
+            chain = [[1, 2, 12], [2, 1, 9]] if rank == 0 else [[4, 4, 8], [3, 0, 7]]
+            r.assignments = chain[:1] if (lost and rank == 1) else chain
+            return r
+
+    try:
+        out, mine = D.solve_comm(CommFake(), object(), cb.OBJ_MIN)
+        q.put((rank, out, None))
+    except RuntimeError as e:
+        q.put((rank, None, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lost", [False, True])
+def test_solve_comm_checks_the_witness_of_the_optimum(lost):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_witness_worker, args=(r, 2, port, lost, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=120) for _ in procs], key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if lost:
+        assert all(o[1] is None and "witness" in o[2] for o in outs)      # loud on every rank, never a silent optimum without proof
+    else:
+        a = outs[0][1]
+        assert a == outs[1][1]
+        assert (a["best"], a["has_solution"], a["has_witness"]) == (7, 1, 1)
+        assert (a["solutions"], a["nodes"], a["kernel_launches"]) == (5, 201, 8)
+        assert abs(a["kernel_ms"] - 6.0) < 1e-6 and abs(a["kernel_ms_min"] - 5.0) < 1e-6 and abs(a["expand_ms"] - 0.25) < 1e-6
