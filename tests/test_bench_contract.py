@@ -41,3 +41,14 @@ def test_product_arm_needs_a_gpu():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
     assert out.stdout.strip() == ""               # nothing that could be taken for a result
+
+
+def test_roofline_traffic_comes_from_the_committed_captures():
+    """`roofline.traffic` of the three workloads is read from profiles/r?_traffic.json (ncu --set full captures),
+    keyed by the kernel the workload runs and the workload's name"""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.measured_traffic("k_search_lov<false,true>", "queens16-all") == 7714048.0
+    assert bench.measured_traffic("k_search_sat<false>", "sat200-seed1-any") > 1e6
+    assert bench.measured_traffic("k_search<false,false,LIN=true>", "wcet-max") > 1e8
+    assert bench.measured_traffic("k_search_lov<false,true>", "queens15-all") is None     # no capture of that workload
