@@ -1883,8 +1883,11 @@ __device__ __forceinline__ uint32_t lovk_F(const LovK<K> &x, int v) {
   return __shfl_sync(FULL, f, v & 31);
 }
 
+#ifndef CSOLVE_LOVK_MIN_BLOCKS
+#define CSOLVE_LOVK_MIN_BLOCKS 3
+#endif
 template <bool EXPAND, int K, bool SAMPLE = false>
-__global__ void __launch_bounds__(THREADS_PER_BLOCK, 3)
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_LOVK_MIN_BLOCKS)
 k_search_lovk(const SearchArgs a) {
   const DevModel &m = a.m;
   const int lane = threadIdx.x & 31;
