@@ -61,10 +61,12 @@ struct SearchCtl {
 //   done_epoch[r]    rank 0 only: rank r has finished the search of this epoch (the frontier may be overwritten)
 //   busy_epoch       == the current epoch while the rank has (or is being handed) work; cleared by the rank itself when
 //                    it ran dry, set again by whoever hands it a frame (k_comm_state / publish_slot)
-//   demand[r]        frames rank r asks THIS rank for (r ran dry and says so in every peer's block); a busy warp that
+//   demand[r]        frames rank r asks THIS rank for (r is running dry: raised from its waiting loop, claim_frame, or by
+//                    its host loop, k_comm_state); a busy warp that
 //                    sees a positive entry takes one unit and serves a ticket of rank r's donation ring over NVLink
-//   ring_open/inflight  a peer serves this rank's ring only while the rank waits in its idle loop (nothing else touches
-//                    the ring then); the rank closes the ring and waits for the peers in flight before it moves on
+//   ring_open/inflight  a peer serves this rank's ring while ring_open == epoch: while the rank's search kernel runs and
+//                    while the rank waits in its idle loop; the rank closes the ring and waits for the peers in flight
+//                    before its counters are rebased (k_rebalance) or judged (k_comm_state)
 //   active64         rank 0 only: epoch << 32 | number of ranks whose busy_epoch is set -- 0 ends the search everywhere
 struct CommBlock {
   unsigned long long rmin64, rmax64;
@@ -138,9 +140,9 @@ struct SearchArgs {
   int32_t n_initial;          // the first n_initial pool entries are the expanded root frontier (rank partition applies)
   int32_t part_rank;          // this process searches the frontier frames whose path hash % part_count == part_rank
   int32_t part_count;
-  // Ranks of a csolve_gpu_comm (n_peers == 0: a search on its own). The expanded root frontier and its claim counter
-  // may live on another GPU: every rank claims chunks of the SAME frontier with one system-scope atomicAdd over NVLink,
-  // so the ranks run out of root frames together whatever the sizes of the sub-trees (no static partition).
+  // Ranks of a csolve_gpu_comm (n_peers == 0: a search on its own). ANY / MIN / MAX models: the expanded root frontier
+  // and its claim counter live on rank 0's GPU and every rank claims frames of that ONE frontier with a system-scope
+  // atomicAdd over NVLink. (ALL models are dealt by path hash and searched without a comm, capi.cu.)
   const int32_t *front_pool;  // the root frontier: [n_initial][frame_words] (== pool without a comm)
   SearchCtl *front_ctl;       // control block whose init_next hands the frontier out (== ctl without a comm)
   CommBlock *comm;            // this rank's block (peers write it)
