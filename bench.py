@@ -169,7 +169,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -307,13 +307,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler starts with the warm-up steps (the same work as the timed ones): nvidia-smi needs a few hundred
+    # milliseconds to deliver its first row, and 10 timed steps on 8 GPUs are over in less than that
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         one_step()
         flush.fill_(1)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     tot_nodes = tot_sols = tot_launch = 0
     dev_ms = wall_s = search_ms = 0.0
     my_nodes = 0
