@@ -458,13 +458,13 @@ int sink_headroom(int n_warps) { return 64 * n_warps + 4096; }
 // be long enough for an even rank partition; every further level is expansion time that all ranks replicate.
 const int DEFAULT_FRAMES_PER_WARP = 16;
 
-int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots, bool learn) {
+int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, bool batch, int n_roots, bool learn, bool backjump) {
   DeviceCtx *C = p->ctx;
   DevModel m = p->dev;
   if (batch) m.lov = 0;
   const bool sample = opt.sample_mod != 0u;
   const bool sat = !batch && search_uses_sat(m, learn, opt.order);
-  const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0) + (sample ? 128 : 0) + (sat ? 256 : 0);
+  const int ws_key = m.lov * 16 + m.lovk + (learn ? 64 : 0) + (sample ? 128 : 0) + (sat ? 256 : 0) + (backjump ? 512 : 0);
   if (p->stacks != nullptr && p->ws_lov != ws_key) {
     // the lane-owns-variable and the general kernels have different occupancies: rebuild the per-warp state
     C->release(p->stacks, p->stacks_bytes); C->cfree(p->wstate); C->cfree(p->wcount); C->cfree(p->totals); C->cfree(p->ctl); C->cfree(p->scratch);
@@ -472,7 +472,7 @@ int ensure_workspace(csolve_gpu_problem *p, const csolve_solve_options &opt, boo
   }
   if (p->stacks == nullptr) {
     p->ws_lov = ws_key;
-    int per_sm = search_blocks_per_sm(m, false, learn, sample, sat);
+    int per_sm = search_blocks_per_sm(m, false, learn, sample, sat, backjump);
     if (per_sm <= 0) return fail(CSOLVE_ERR_CUDA, "search kernel does not fit on the device (shared memory per node too large)");
     p->grid = per_sm * C->sm_count;
     p->n_warps = p->grid * WARPS_PER_BLOCK;
@@ -581,7 +581,9 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     const int rc0 = check_domains(p, n_roots, root_dom, "root");
     if (rc0 != CSOLVE_OK) return rc0;
   }
-  int rc = ensure_workspace(p, opt, batch, n_roots, learn);
+  // back-jumping (src/csolve.c:350-364) re-decides frames: never for ALL models, whose counts must stay the tree's
+  const bool backjump = learn && opt.backjump != 0 && p->dev.objective != CSOLVE_OBJ_ALL;
+  int rc = ensure_workspace(p, opt, batch, n_roots, learn, backjump);
   if (rc != CSOLVE_OK) return rc;
   if (learn) {
     NogoodPool &g = p->ng;
@@ -966,7 +968,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
         CUDA_TRY(cudaMemcpyAsync(&c->block(c->rank)->ring_open, &epoch, sizeof(int32_t), cudaMemcpyHostToDevice, st));
         a.peer_demand = demand_allowed() ? 1 : 0;
       }
-      CUDA_TRY(launch_search(a, p->grid, false, st)); launches++;
+      CUDA_TRY(launch_search(a, p->grid, false, st, backjump)); launches++;
       if (getenv("CSOLVE_DEBUG_SYNC")) {
         const cudaError_t es = cudaStreamSynchronize(st);
         fprintf(stderr, "[csolve] depth-first kernel: %s (solbuf %p cap %d, pool %p cap %d, stacks %p)\n", cudaGetErrorString(es), (void *)p->solbuf,
@@ -1161,6 +1163,7 @@ int solve_impl(csolve_gpu_problem *p, csolve_gpu_comm *c, const csolve_solve_opt
     CUDA_TRY(cudaMemcpy(cnt, p->ng.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
     res->conflicts = std::min(cnt[0], p->ng.cap_ng);
     res->conflicts_abandoned = (uint64_t)cnt[3] + (uint64_t)cnt[4];
+    res->backjumps = (uint64_t)cnt[5];
   }
   (void)slices;
   return CSOLVE_OK;
@@ -1354,7 +1357,7 @@ extern "C" int csolve_gpu_group_load(csolve_gpu_group *g, const csolve_flat_mode
     csolve_solve_options o;
     memset(&o, 0, sizeof(o));
     if (g->sink) { g->probs[i]->sink = group_sink; g->probs[i]->sink_user = g; }
-    return ensure_workspace(g->probs[i], o, false, 0, false);
+    return ensure_workspace(g->probs[i], o, false, 0, false, false);
   });
   if (rc == CSOLVE_OK && g->sink) for (auto *p : g->probs) { p->sink = group_sink; p->sink_user = g; }
   return rc;
@@ -1373,7 +1376,7 @@ extern "C" int csolve_gpu_group_solve(csolve_gpu_group *g, const csolve_solve_op
   for (int i = 0; i < n; i++) {
     res->solutions += r[i].solutions; res->nodes += r[i].nodes; res->cuts += r[i].cuts; res->props += r[i].props;
     res->clause_visits += r[i].clause_visits; res->kernel_launches += r[i].kernel_launches;
-    res->conflicts += r[i].conflicts; res->conflicts_abandoned += r[i].conflicts_abandoned;
+    res->conflicts += r[i].conflicts; res->conflicts_abandoned += r[i].conflicts_abandoned; res->backjumps += r[i].backjumps;
     res->timed_out |= r[i].timed_out;
     res->kernel_ms = std::max(res->kernel_ms, r[i].kernel_ms); res->expand_ms = std::max(res->expand_ms, r[i].expand_ms);
     if (r[i].has_solution) {

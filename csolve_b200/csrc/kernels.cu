@@ -324,8 +324,9 @@ struct Analysis {
   }
 };
 
-__device__ __noinline__ void learn_nogood(const DevModel &m, const WarpSmem &s, const int4 *wrec, const int *wptr,
-                                          const NogoodPool &ng, int decision_var, FailInfo fi) {
+// Returns the number of literals of the nogood that was stored (they stay in s.nlits), 0 when none was.
+__device__ __noinline__ int learn_nogood(const DevModel &m, const WarpSmem &s, const int4 *wrec, const int *wptr,
+                                         const NogoodPool &ng, int decision_var, FailInfo fi) {
   atomicAdd(&ng.counters[2], 1);
   for (int w = 0; w < m.mask_words; w++) s.seen[w] = 0;
   Analysis an{m, s, wrec, wptr, ng, decision_var, 0, 0, true};
@@ -342,12 +343,12 @@ __device__ __noinline__ void learn_nogood(const DevModel &m, const WarpSmem &s, 
     an.ok = false;
   }
   while (an.ok && an.n_work > 0) an.expand(s.work[--an.n_work]);
-  if (!an.ok || an.n_lits == 0) { atomicAdd(&ng.counters[3], 1); return; }
+  if (!an.ok || an.n_lits == 0) { atomicAdd(&ng.counters[3], 1); return 0; }
   const int n = an.n_lits;
   const int st = atomicAdd(&ng.counters[1], n);
-  if (st + n > ng.cap_lits) { atomicAdd(&ng.counters[4], 1); return; }
+  if (st + n > ng.cap_lits) { atomicAdd(&ng.counters[4], 1); return 0; }
   const int id = atomicAdd(&ng.counters[0], 1);
-  if (id >= ng.cap_ng) { atomicAdd(&ng.counters[4], 1); return; }
+  if (id >= ng.cap_ng) { atomicAdd(&ng.counters[4], 1); return 0; }
   for (int k = 0; k < n; k++) ng.lits[st + k] = s.nlits[k];
   ng.start[id] = st; ng.len[id] = n;
   __threadfence();
@@ -357,6 +358,7 @@ __device__ __noinline__ void learn_nogood(const DevModel &m, const WarpSmem &s, 
     const int slot = atomicAdd(&ng.watch_n[v], 1);
     if (slot < ng.cap_w) __stcg(&ng.watch[(size_t)v * ng.cap_w + slot], id);
   }
+  return n;
 }
 
 // stage the watch-record table and the small linear tables into shared memory (whole block); returns the pointers to use
@@ -752,6 +754,10 @@ __device__ __forceinline__ void comm_poll(const SearchArgs &a, int lane) {
 
 // ---- the search kernel ----------------------------------------------------------------------------
 // Frame header words (device_model.h): var, iter, last, lo | hi, level, best_seen, hash
+// CSOLVE_BJ (kernels_bj.cu compiles this file a second time with it, up to the end of this kernel: CSOLVE_BJ_UNIT):
+// the LEARN instance of the depth-first phase back-jumps after a conflict, see the block that follows learn_nogood in
+// the node loop. A property of the compilation unit, not a template parameter: the instances of this unit keep their
+// names and their code.
 template <bool EXPAND, bool LEARN, bool LIN = false, bool SAMPLE = false>
 __global__ void __launch_bounds__(THREADS_PER_BLOCK, CSOLVE_MIN_BLOCKS)
 k_search(const SearchArgs a) {
@@ -938,10 +944,17 @@ k_search(const SearchArgs a) {
     FailInfo fi; fi.rec = -1; fi.var = -1;
     if (ok) ok = warp_fixpoint<LEARN, LIN>(m, s, wrec, wptr, lane, props, visits, a.gprio, &a.ng, &fi);
     nodes++;
+#ifdef CSOLVE_BJ
+    int n_ng = 0;      // lane 0: literals of the nogood this node contributed (in s.nlits)
+#endif
     if (LEARN && !ok) {
       // conflict_create (src/conflict.c:327-362): record why this node failed
       __syncwarp();
+#ifdef CSOLVE_BJ
+      if (lane == 0) n_ng = learn_nogood(m, s, wrec, wptr, a.ng, var, fi);
+#else
       if (lane == 0) learn_nogood(m, s, wrec, wptr, a.ng, var, fi);
+#endif
       __syncwarp();
     }
     // prio-- on success, prio++ on failure (src/csolve.c:459-462)
@@ -958,6 +971,91 @@ k_search(const SearchArgs a) {
 
     if (!ok) {
       cuts++;
+#ifdef CSOLVE_BJ
+      if (LEARN && !EXPAND && m.objective != CSOLVE_OBJ_ALL) {
+        // ---- back-jump (conflict_backtrack, src/csolve.c:350-364; conflict_update, src/conflict.c:311-324) -----------
+        // The reference unwinds to 1 + the second-highest level of the nogood's variables, propagates the new nogood
+        // there and goes on with a FRESH step at that level (the steps above it are deactivated, the next iteration
+        // of solve() picks a variable again). With copy-on-branch frames: frame q of the stack holds the domains before
+        // level q's assignment, so "the level variable y became a value at" is the first frame that has y as a value
+        // (found by bisection over the frames of this warp's path, lane 0), T = the deepest such frame over the
+        // nogood's literals other than the decision; the frames above T are dropped, frame T's domains are
+        // propagated again with the nogood's variables on the worklist (the nogood now removes the decision's value
+        // there, propagate_confl) and frame T is decided again from scratch. T is kept above the warp's base frame
+        // (that frame may own only a part of its variable's values). Dropping and re-deciding frames loses nothing
+        // -- the fresh frame T enumerates a whole domain under the same decisions, and what frame T had given away
+        // (donation, k_rebalance) is searched by whoever took it -- so the result does not depend on T; what the
+        // nogood buys is that the failure is not met again. Every jump stores a nogood, the pool is
+        // finite, and with a full pool learn_nogood returns 0: the search is chronological from then on and ends.
+        // ALL models never jump (a re-decided frame would count solutions twice: the reference's -c true over-counts).
+        int T = level;
+        if (lane == 0 && n_ng > 0 && level > base + 1) {
+          int t = base + 1;
+          const int doff = frame_dom_offset(m.mask_words);
+          for (int k = 0; k < n_ng && t < level; k++) {
+            const int y = s.nlits[k] >> 1;
+            if (y == var) continue;
+            int2 dy = __ldcg(reinterpret_cast<const int2 *>(stack + (size_t)t * fw + doff) + y);
+            if (dy.x == dy.y) continue;                       // already a value in frame t
+            int qa = t, qb = level;                           // not a value in frame qa, a value in frame qb (s.p)
+            while (qb - qa > 1) {
+              const int qm = (qa + qb) >> 1;
+              dy = __ldcg(reinterpret_cast<const int2 *>(stack + (size_t)qm * fw + doff) + y);
+              if (dy.x == dy.y) qb = qm; else qa = qm;
+            }
+            t = qb;
+          }
+          T = t;
+        }
+        T = __shfl_sync(FULL, T, 0);
+        if (T < level) {
+          level = T;
+          int *ft = stack + (size_t)T * fw;
+          const int4 g1 = __ldcg(reinterpret_cast<const int4 *>(ft) + 1);
+          flevel = g1.y; fhash = (unsigned)g1.w;
+          // The value of frame T that was being searched (frame T + 1 has T's variable at it). k_rebalance, k_export_frames
+          // and the incumbent refresh narrow a frame's own variable to the values the frame still owns, which no longer
+          // include that one -- and what is left of its sub-tree is in the frames being dropped.
+          const int tvar = __ldcg(&ft[FR_VAR]);
+          const int tval = __ldcg(&stack[(size_t)(T + 1) * fw + frame_dom_offset(m.mask_words) + 2 * tvar]);
+          load_domains(m, ft, s.d, lane);
+          for (int w = lane; w < m.mask_words; w += 32) { s.amask[w] = (unsigned)__ldcg(&ft[FR_MASK + w]); s.cur[w] = 0; s.nxt[w] = 0; }
+          for (int v = lane; v < V; v += 32) { s.rlo[v] = -1; s.rhi[v] = -1; }
+          __syncwarp();
+          bool ok2 = true;
+          if (lane == 0) {
+            if (tval < s.d[2 * tvar]) s.d[2 * tvar] = tval;             // the re-decided frame covers that value again
+            if (tval > s.d[2 * tvar + 1]) s.d[2 * tvar + 1] = tval;
+            for (int k = 0; k < n_ng; k++) { const int y = s.nlits[k] >> 1; s.cur[y >> 5] |= 1u << (y & 31); }
+            if (optimise) {
+              Dom o; o.lo = s.d[2 * m.obj_var]; o.hi = s.d[2 * m.obj_var + 1];
+              o = objective_tighten(m.objective, o, best);
+              s.d[2 * m.obj_var] = o.lo; s.d[2 * m.obj_var + 1] = o.hi;
+              s.cur[m.obj_var >> 5] |= 1u << (m.obj_var & 31);
+              ok2 = o.lo <= o.hi;
+            }
+            atomicAdd(&a.ng.counters[5], 1);
+          }
+          ok2 = __shfl_sync(FULL, ok2, 0);
+          __syncwarp();
+          if (ok2) ok2 = warp_fixpoint<LEARN, LIN>(m, s, wrec, wptr, lane, props, visits, nullptr, &a.ng, nullptr);
+          if (!ok2) {
+            // nothing is left below frame T - 1's current value: it goes on with its next one (T - 1 >= base)
+            level = T - 1;
+            have = false;
+            continue;
+          }
+          const int nv = warp_select_var(m, s, lane, a.order, flevel, -1, a.gprio);
+          fbest = optimise ? best : g1.z;
+          write_child_frame(m, s, ft, lane, nv, flevel, fbest, fhash, -1);
+          for (int v = lane; v < V; v += 32) reinterpret_cast<int2 *>(s.p)[v] = reinterpret_cast<const int2 *>(s.d)[v];
+          __syncwarp();
+          lo = s.p[2 * nv]; hi = s.p[2 * nv + 1];
+          var = nv; iter = 0; last = (unsigned)hi - (unsigned)lo;
+          have = true;
+        }
+      }
+#endif
     } else if (flevel + 1 == V) {
       // all variables assigned: leaf (src/csolve.c:416-424, 222-244)
       const bool leaf_ok = warp_all_true(m, s, lane);
@@ -1112,6 +1210,16 @@ k_search(const SearchArgs a) {
     c[CNT_LASTWORK] = (unsigned long long)(lastwork >= 0 ? lastwork : clock64() - t0);
   }
 }
+
+#ifdef CSOLVE_BJ_UNIT
+// kernels_bj.cu compiles this file up to here, in a namespace of its own, for the one back-jumping instance of
+// k_search: the instances of this unit keep the code they were measured and parity-tested with (an instantiation more
+// in the same unit moves the inliner's choices in the others).
+}  // namespace csolve_dev (renamed by kernels_bj.cu)
+extern "C" const void *csolve_bj_search_kernel(void) {
+  return (const void *)csolve_dev::k_search<false, true, false, false>;
+}
+#else
 
 // =====================================================================================================
 // "Lane owns variable" search kernel for pure NOT(EQ) networks with at most 32 variables (N-queens).
@@ -3183,8 +3291,11 @@ static const void *general_kernel(bool expand, bool lin) {
 }
 
 // the kernel instance a search runs on (sample: the parity-instrumented instances, never with learning)
-static const void *search_kernel(const DevModel &m, bool expand, bool learn, bool sample, bool sat = false) {
+static const void *search_kernel(const DevModel &m, bool expand, bool learn, bool sample, bool sat = false, bool backjump = false) {
   if (sat && !expand) return sample ? (const void *)k_search_sat<true> : (const void *)k_search_sat<false>;
+#ifndef CSOLVE_BJ_UNIT
+  if (learn && backjump && !expand) return csolve_bj_search_kernel();    // kernels_bj.cu
+#endif
   if (learn) return expand ? (const void *)k_search<true, true> : (const void *)k_search<false, true>;
   if (m.lovk) return sample ? lovk_kernel<true>(expand, m.lovk) : lovk_kernel<false>(expand, m.lovk);
   if (m.lov) return sample ? lov_kernel<true>(expand, m.lov_bits != 0) : lov_kernel<false>(expand, m.lov_bits != 0);
@@ -3198,20 +3309,20 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 bool search_learns(const SearchArgs &a) { return a.ng.lits != nullptr; }
 
-int search_blocks_per_sm(const DevModel &m, bool expand, bool learn, bool sample, bool sat) {
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn, bool sample, bool sat, bool backjump) {
   int n = 0;
   const size_t smem = search_smem_bytes(m, learn, sat && !expand);
-  const void *fn = search_kernel(m, expand, learn, sample, sat);
+  const void *fn = search_kernel(m, expand, learn, sample, sat, backjump);
   if (ensure_smem(fn, smem) != cudaSuccess) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, THREADS_PER_BLOCK, smem) != cudaSuccess) return 0;
   return n;
 }
 
-cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st) {
+cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t st, bool backjump) {
   const bool learn = search_learns(a);
   const bool sat = a.use_sat != 0 && !expand;
   const size_t smem = search_smem_bytes(a.m, learn, sat);
-  const void *fn = search_kernel(a.m, expand, learn, a.sample_mod != 0u, sat);
+  const void *fn = search_kernel(a.m, expand, learn, a.sample_mod != 0u, sat, learn && backjump);
   cudaError_t e = ensure_smem(fn, smem);
   if (e != cudaSuccess) return e;
   void *args[] = {(void *)&a};
@@ -3295,3 +3406,4 @@ cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t
 }
 
 }  // namespace csolve_dev
+#endif  // CSOLVE_BJ_UNIT

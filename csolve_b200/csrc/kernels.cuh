@@ -103,7 +103,7 @@ struct WarpState {
 //   nogood k = lits[start[k] .. start[k] + len[k]), literal code = var << 1 | value (value in {0,1})
 //   watch[v * cap_w + i] = nogoods that mention variable v (-1 = slot reserved, not written yet)
 //   counters: [0] nogoods, [1] literals, [2] conflicts analysed, [3] analyses abandoned (a non-0/1 value was involved,
-//   src/conflict.c:173-179, or the nogood was too long), [4] pool full
+//   src/conflict.c:173-179, or the nogood was too long), [4] pool full, [5] back-jumps taken
 struct NogoodPool {
   int32_t *lits, *start, *len, *watch, *watch_n, *counters;
   int32_t cap_ng, cap_lits, cap_w;
@@ -175,7 +175,7 @@ CSOLVE_HOSTDEV static inline int sample_words(int n_vars) { return 4 + 4 * n_var
 
 size_t search_smem_bytes(const DevModel &m, bool learn = false, bool sat = false);
 bool search_uses_sat(const DevModel &m, bool learn, int order);
-cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s);
+cudaError_t launch_search(const SearchArgs &a, int grid, bool expand, cudaStream_t s, bool backjump = false);
 bool search_learns(const SearchArgs &a);
 cudaError_t launch_rebalance(const SearchArgs &a, int32_t *scratch, cudaStream_t s);
 // comm: this rank's state between two kernel launches. out[0] = 1 if the rank has work (frames in its ring or in the
@@ -191,8 +191,11 @@ cudaError_t launch_reduce_counters(const unsigned long long *wcount, int n_warps
 cudaError_t launch_propagate_batch(const DevModel &m, int n_nodes, const int32_t *dom_in, const int32_t *var,
                                    const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed,
                                    int grid, cudaStream_t s);
-int search_blocks_per_sm(const DevModel &m, bool expand, bool learn = false, bool sample = false, bool sat = false);
+int search_blocks_per_sm(const DevModel &m, bool expand, bool learn = false, bool sample = false, bool sat = false, bool backjump = false);
 cudaError_t launch_root_frames(const DevModel &m, int n_roots, const int32_t *root_dom, int order, int32_t *frames_out,
                                int out_cap, int32_t *n_out, unsigned char *root_failed, int grid, cudaStream_t s);
 
 }  // namespace csolve_dev
+
+// the back-jumping instance of the general search kernel (csolve_solve_options.backjump), compiled in a unit of its own
+extern "C" const void *csolve_bj_search_kernel(void);

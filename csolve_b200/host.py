@@ -74,7 +74,7 @@ class _GpuConfig(C.Structure):
 class _SolveOptions(C.Structure):
     _fields_ = [("order", C.c_int32), ("part_rank", C.c_int32), ("part_count", C.c_int32),
                 ("split_target", C.c_int32), ("max_solutions", C.c_int32), ("time_limit_ms", C.c_int32),
-                ("slice_ms", C.c_int32), ("create_conflicts", C.c_int32), ("reserved", C.c_int32),
+                ("slice_ms", C.c_int32), ("create_conflicts", C.c_int32), ("backjump", C.c_int32),
                 ("prefer_failing", C.c_int32), ("sample_mod", C.c_uint32), ("sample_cap", C.c_int32),
                 ("restart_frequency", C.c_int32), ("sample_failed_keep", C.c_uint32), ("reserved2", C.c_int32 * 4)]
 
@@ -87,7 +87,7 @@ class _GpuResult(C.Structure):
                 ("clause_visits", C.c_uint64), ("best", C.c_int32), ("has_solution", C.c_int32),
                 ("timed_out", C.c_int32), ("n_stored", C.c_int32), ("kernel_ms", C.c_double),
                 ("expand_ms", C.c_double), ("kernel_launches", C.c_uint64), ("conflicts", C.c_uint64),
-                ("conflicts_abandoned", C.c_uint64), ("restarts", C.c_uint64)]
+                ("conflicts_abandoned", C.c_uint64), ("restarts", C.c_uint64), ("backjumps", C.c_uint64)]
 
 
 # int (*csolve_exchange_fn)(void *user, int32_t *best, int32_t *found, int32_t local_done)
@@ -224,11 +224,11 @@ class SolveResult:
 
 def solve_options(order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0, time_limit_ms=0,
                   slice_ms=0, prefer_failing=False, create_conflicts=False, sample_mod=0, sample_cap=0,
-                  restart_frequency=0, sample_failed_keep=1):
+                  restart_frequency=0, sample_failed_keep=1, backjump=False):
     if isinstance(order, str):
         order = ORDER_NAMES[order]
     return _SolveOptions(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
-                         1 if create_conflicts else 0, 0, 1 if prefer_failing else 0, int(sample_mod), int(sample_cap),
+                         1 if create_conflicts else 0, 1 if backjump else 0, 1 if prefer_failing else 0, int(sample_mod), int(sample_cap),
                          int(restart_frequency), int(sample_failed_keep))
 
 
@@ -351,11 +351,12 @@ class GpuProblem:
 
     def solve(self, order=ORDER_NONE, part_rank=0, part_count=1, split_target=0, max_solutions=0,
               time_limit_ms=0, slice_ms=0, prefer_failing=False, create_conflicts=False, sample_mod=0, sample_cap=0,
-              restart_frequency=0, sample_failed_keep=1, comm=None):
+              restart_frequency=0, sample_failed_keep=1, comm=None, backjump=False):
         """comm: a connected Comm -- the call is then COLLECTIVE over the comm's ranks (csolve_gpu_solve_comm): they
         search one tree together and each gets its own share of the counters back."""
         opt = solve_options(order, part_rank, part_count, split_target, max_solutions, time_limit_ms, slice_ms,
-                            prefer_failing, create_conflicts, sample_mod, sample_cap, restart_frequency, sample_failed_keep)
+                            prefer_failing, create_conflicts, sample_mod, sample_cap, restart_frequency, sample_failed_keep,
+                            backjump)
         res = _GpuResult()
         if comm is not None:
             _check(library().csolve_gpu_solve_comm(self._h, comm._h, C.byref(opt), C.byref(res)))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSOLVE_B200_ABI_VERSION 4
+#define CSOLVE_B200_ABI_VERSION 5
 
 /* ---- error codes (all entry points return 0 on success) ------------------ */
 #define CSOLVE_OK                 0
@@ -148,8 +148,14 @@ typedef struct csolve_solve_options {
                                 * device clause pool that is propagated on later nodes. Only 0/1-valued facts can be
                                 * recorded, so it matters for SAT-like models; models that run on the specialised
                                 * NOT(EQ) kernels never produce a nogood (neither does the reference) and ignore it.
-                                * No back-jump, no restarts: results are identical with and without. 0 = off */
-  int32_t reserved;
+                                * Results are identical with and without. 0 = off */
+  int32_t backjump;            /* with create_conflicts, ANY / MIN / MAX models: after a conflict the search unwinds to
+                                * 1 + the second-highest level of the nogood's variables, propagates the nogood there and
+                                * decides that level again (conflict_backtrack, src/csolve.c:350-364; conflict_update,
+                                * src/conflict.c:311-324) instead of popping one level. Per search warp, within the frames
+                                * the warp owns. Status, optimum and the validity of the returned assignment do not depend
+                                * on it; node counters do. Ignored for ALL models (re-deciding a level would count
+                                * solutions twice -- the reference's -c true over-counts them). 0 = chronological */
   int32_t prefer_failing;      /* -f (src/main.c:63-67): break ordering ties by a failure-driven priority that is
                                 * shared by all warps and updated during the search (src/csolve.c:459-462,
                                 * src/propagate.c:33-54). The tree then depends on timing: ALL counts and optima are
@@ -191,6 +197,7 @@ typedef struct csolve_gpu_result {
   uint64_t conflicts;          /* nogoods learned = CONFL (src/conflict.c:361) */
   uint64_t conflicts_abandoned;/* analyses given up (non-0/1 value involved, too long, pool full) */
   uint64_t restarts;           /* RESTARTS (src/csolve.c:272) */
+  uint64_t backjumps;          /* conflicts after which the search dropped more than one level (options.backjump) */
 } csolve_gpu_result;
 
 int  csolve_gpu_init(const csolve_gpu_config *cfg);

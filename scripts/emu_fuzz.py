@@ -1,0 +1,109 @@
+"""Differential fuzz of the search kernel SOURCE on the CPU: csolve_b200/csrc/kernels.cu (k_search) runs under the SIMT
+emulator of tests/harness/simt_emu.h and is compared with the oracle -- ALL: (solutions, nodes, cuts) of the tree;
+ANY: status and a model that satisfies the CNF; MIN / MAX: the optimum. With --backjump the back-jumping build
+(csrc/kernels_bj.cu) is used for the learning runs.   python scripts/emu_fuzz.py [--seeds N] [--seed0 S] [--backjump]"""
+import argparse
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import csolve_b200 as cb
+import gen_random
+import util
+from csolve_b200 import instances as I
+
+
+def sat_case(rng, backjump):
+    n = rng.randint(10, 70)
+    ratio = rng.choice([3.0, 3.8, 4.26, 4.26, 4.8])
+    cnf = I.random_3sat_cnf(n, ratio, rng.randint(1, 10**6))
+    obj = rng.choice(["ANY", "ANY", "ALL", "MIN"])
+    if obj == "ALL" and n > 34:
+        obj = "ANY"
+    if obj == "MIN":
+        n = min(n, 26)
+        cnf = [cl for cl in cnf if all(abs(l) <= n for l in cl)] or [[1, 2, 3]]
+        text = I.cnf_to_csolve(n, cnf, "MIN " + " + ".join("x%d" % i for i in range(1, n + 1)))
+    else:
+        text = I.cnf_to_csolve(n, cnf, obj)
+    m = cb.Model(text)
+    o, _ = util.Oracle(m).solve_tree(0)
+    learn = rng.random() < 0.7
+    kw = dict(order=0 if obj == "ALL" else rng.randint(0, 4), learn=learn, backjump=learn and backjump,
+              prefer_failing=obj != "ALL" and rng.random() < 0.4, n_blocks=rng.choice([1, 1, 2, 3]), max_solutions=16)
+    if obj == "ALL":
+        o, _ = util.Oracle(m).solve_tree(kw["order"])
+    r, sols = util.emu_search(m, **kw)
+    if obj == "ALL":
+        ok = (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
+    elif obj == "ANY":
+        ok = r.has_solution == (1 if o.solutions > 0 else 0)
+        if ok and r.has_solution:
+            val = dict(zip(m.var_names, sols[0]))
+            ok = all(any((val["x%d" % abs(l)] == 1) == (l > 0) for l in cl) for cl in cnf)
+    else:
+        ok = r.has_solution == o.has_solution and (not o.has_solution or r.best == o.best)
+        if ok and r.has_solution:
+            val = dict(zip(m.var_names, sols[0]))
+            xs = [val["x%d" % i] for i in range(1, n + 1)]
+            ok = sum(xs) == r.best and all(any((val["x%d" % abs(l)] == 1) == (l > 0) for l in cl) for cl in cnf)
+    return ok, "sat n=%d %s %s" % (n, obj, kw), r
+
+
+def generic_case(rng, backjump):
+    text = gen_random.gen_instance(rng.randint(0, 10**7))
+    try:
+        m = cb.Model(text)
+    except cb.CsolveError:
+        return True, "rejected", None
+    hc = util.harness_lib()
+    if hc.hc_load(m.flat, 1) != 0:
+        return True, "unsupported", None
+    obj = text.split(";")[0].split()[0]
+    order = rng.randint(0, 4)
+    o, _ = util.Oracle(m).solve_tree(order)
+    if o.hit_limit:
+        return True, "too large", None
+    learn = rng.random() < 0.3
+    kw = dict(order=order, learn=learn, backjump=learn and backjump, n_blocks=rng.choice([1, 2]), max_solutions=16)
+    r, sols = util.emu_search(m, **kw)
+    if obj == "ALL":
+        ok = (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
+    elif obj == "ANY":
+        ok = r.has_solution == (1 if o.solutions > 0 else 0)
+    else:
+        ok = r.has_solution == o.has_solution and (not o.has_solution or r.best == o.best)
+    return ok, "generic %s %s\n%s" % (obj, kw, text), r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=200)
+    ap.add_argument("--seed0", type=int, default=0)
+    ap.add_argument("--backjump", action="store_true")
+    ap.add_argument("--kind", default="both")
+    a = ap.parse_args()
+    t0 = time.time()
+    bad = 0
+    tot = {"nodes": 0, "conflicts": 0, "backjumps": 0, "cases": 0}
+    for s in range(a.seed0, a.seed0 + a.seeds):
+        rng = random.Random(s)
+        fn = sat_case if (a.kind == "sat" or (a.kind == "both" and s % 2 == 0)) else generic_case
+        ok, what, r = fn(rng, a.backjump)
+        if r is not None:
+            tot["cases"] += 1; tot["nodes"] += r.nodes; tot["conflicts"] += r.conflicts; tot["backjumps"] += r.backjumps
+        if not ok:
+            bad += 1
+            print("MISMATCH seed %d: %s -> %s" % (s, what, (r.solutions, r.nodes, r.cuts, r.best, r.has_solution)), flush=True)
+    print("emu_fuzz: %d seeds, %d searches, %d nodes, %d nogoods, %d back-jumps, %d mismatches, %.0f s"
+          % (a.seeds, tot["cases"], tot["nodes"], tot["conflicts"], tot["backjumps"], bad, time.time() - t0), flush=True)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,169 @@
+// emu_search.cpp -- TEST-ONLY: the product's search kernels (csolve_b200/csrc/kernels.cu: k_search, k_search_lov,
+// k_search_lovk, k_search_sat, k_rebalance) run on the CPU under the SIMT emulator of simt_emu.h, driven the way capi.cu
+// drives the depth-first phase of a search whose root was not expanded (split_target = 1): one root frame in the pool,
+// the donation ring behind it, time slices with k_rebalance between them until no warp owns work.
+// Built by tests/util.py build_emu() from the kernel source itself (kernels_emu.inc = kernels.cu with its __shared__
+// declarations rewritten and the launch wrappers cut off); -DCSOLVE_BJ builds k_search<false, true> as kernels_bj.cu does.
+// Not part of the library, never a fallback.
+#define EMU_DEFINE_MACHINE 1
+#include "simt_emu.h"
+extern "C" const void *csolve_bj_search_kernel(void) { return nullptr; }     // kernels_bj.cu's instance: here -DCSOLVE_BJ
+#include "kernels_emu.inc"
+#include <climits>
+#include <string>
+#include "compile.hpp"
+
+using namespace csolve_dev;
+
+namespace {
+
+int root_var(const CompiledModel &cm, int order) {      // select_root_var of capi.cu
+  const DevModel &m = cm.host;
+  if (order == CSOLVE_ORDER_NONE) return cm.order[0];
+  unsigned long long bestk = ~0ull;
+  int bestv = 0;
+  for (int v = 0; v < m.n_vars; v++) {
+    const int lo = cm.root_dom[2 * v], hi = cm.root_dom[2 * v + 1];
+    unsigned primary;
+    switch (order) {
+    case CSOLVE_ORDER_SMALLEST_DOMAIN: primary = (unsigned)hi - (unsigned)lo; break;
+    case CSOLVE_ORDER_LARGEST_DOMAIN:  primary = ~((unsigned)hi - (unsigned)lo); break;
+    case CSOLVE_ORDER_SMALLEST_VALUE:  primary = (unsigned)lo ^ 0x80000000u; break;
+    default:                           primary = ~((unsigned)hi ^ 0x80000000u); break;
+    }
+    const unsigned secondary = ~((unsigned)cm.prio[v] ^ 0x80000000u);
+    const unsigned long long k = ((unsigned long long)primary << 32) | secondary;
+    if (k < bestk) { bestk = k; bestv = v; }
+  }
+  return bestv;
+}
+
+struct Launch { SearchArgs a; void (*fn)(const SearchArgs); int32_t *scratch; };
+
+void run_kernel(void *arg) {
+  const Launch *l = static_cast<const Launch *>(arg);
+  l->fn(l->a);
+}
+void run_rebalance(void *arg) {
+  const Launch *l = static_cast<const Launch *>(arg);
+  k_rebalance(l->a, l->scratch);
+}
+
+std::string g_err;
+
+}  // namespace
+
+struct emu_result {
+  uint64_t solutions, nodes, cuts, props;
+  int32_t best, has_solution, n_stored, conflicts, conflicts_abandoned, backjumps, claims, slices;
+  uint64_t switches, collectives, site_mismatches;
+};
+
+extern "C" const char *emu_error() { return g_err.c_str(); }
+extern "C" int emu_backjump_build() {
+#ifdef CSOLVE_BJ
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+// one whole search; solutions: [max_solutions][n_vars + 1] (values..., objective key) or NULL
+// general: 1 = the general kernel whatever the model (what capi.cu does for batched roots), 0 = the kernel the product
+// picks (lane-owns-variable / K-per-lane / bit-state / general). slice_clock: length of a time slice in emulator clock
+// units (every clock64() call adds 64), 0 = the whole search in one slice.
+extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
+                          int max_solutions, int general, long long slice_clock, emu_result *res, int32_t *solutions) {
+  CompiledModel cm;
+  int rc = compile_model(*fm, cm, g_err);
+  if (rc != 0) return rc;
+  DevModel m = cm.host;
+  if (general || learn) { m.lov = 0; m.lovk = 0; }
+  if (prefer_failing && m.lov) prefer_failing = 0;       // capi.cu: the lane-owns-variable kernel has no dynamic priorities
+  const int V = m.n_vars, fw = m.frame_words;
+  const int n_warps = n_blocks * WARPS_PER_BLOCK;
+  memset(res, 0, sizeof(*res));
+
+  SearchCtl ctl;
+  memset(&ctl, 0, sizeof(ctl));
+  ctl.best = m.objective == CSOLVE_OBJ_MIN ? INT32_MAX : (m.objective == CSOLVE_OBJ_MAX ? INT32_MIN : 0);
+  ctl.signal = SIG_RUN;
+  const int ring = 4 * n_warps + 1024;   // ring_min_frames of capi.cu
+  const int n_initial = 1, pool_cap = n_initial + ring;
+  std::vector<int32_t> pool((size_t)pool_cap * fw, 0), ready(pool_cap, 0), stacks((size_t)n_warps * (V + 1) * fw, 0);
+  std::vector<WarpState> ws(n_warps, WarpState{-1, 0, 0, 0u});
+  std::vector<unsigned long long> wcount((size_t)n_warps * CNT_WIDTH, 0);
+  const int sol_cap = max_solutions > 0 ? max_solutions : (m.obj_var >= 0 ? 16 : 1);
+  std::vector<int32_t> solbuf((size_t)sol_cap * (V + 1), 0);
+  const int rv = root_var(cm, order);
+  int32_t *root = pool.data();
+  root[FR_VAR] = rv; root[FR_ITER] = 0;
+  root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
+  root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
+  root[FR_LEVEL] = 0; root[FR_BEST] = ctl.best; root[7] = 0x1234567;
+  memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
+  if (m.lovk) memcpy(&root[frame_dom_offset(m.mask_words) + 2 * V], cm.lov_fconst.data(), sizeof(int32_t) * V);   // value sets
+
+  std::vector<int32_t> gprio(cm.prio.begin(), cm.prio.end());
+  NogoodPool ng;
+  memset(&ng, 0, sizeof(ng));
+  std::vector<int32_t> ng_lits, ng_start, ng_len, ng_watch, ng_watch_n, ng_counters(8, 0);
+  if (learn) {
+    ng.cap_ng = 1 << 14; ng.cap_lits = 1 << 18; ng.cap_w = 1024;
+    ng_lits.assign(ng.cap_lits, 0); ng_start.assign(ng.cap_ng, 0); ng_len.assign(ng.cap_ng, 0);
+    ng_watch.assign((size_t)V * ng.cap_w, -1); ng_watch_n.assign(V, 0);
+    ng.lits = ng_lits.data(); ng.start = ng_start.data(); ng.len = ng_len.data();
+    ng.watch = ng_watch.data(); ng.watch_n = ng_watch_n.data(); ng.counters = ng_counters.data();
+  }
+
+  Launch l;
+  SearchArgs &a = l.a;
+  memset(&a, 0, sizeof(a));
+  a.m = m; a.ctl = &ctl; a.stacks = stacks.data(); a.wstate = ws.data(); a.wcount = wcount.data();
+  a.solbuf = solbuf.data(); a.max_solutions = sol_cap; a.n_warps = n_warps; a.order = order;
+  a.out_cap = pool_cap; a.expand_branch_max = 64;
+  a.part_rank = 0; a.part_count = 1;
+  a.slice_cycles = slice_clock > 0 ? slice_clock : LLONG_MAX / 2;
+  a.items = pool.data(); a.pool = pool.data(); a.pool_cap = pool_cap; a.ready = ready.data(); a.n_initial = n_initial;
+  a.front_pool = pool.data(); a.front_ctl = &ctl; a.total_warps = n_warps;
+  a.gprio = prefer_failing ? gprio.data() : nullptr;
+  if (learn) a.ng = ng;
+  const bool sat = !general && search_uses_sat(m, learn != 0, order);
+  a.use_sat = sat ? 1 : 0;
+  l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, learn != 0, false, sat, false)));
+  std::vector<int32_t> scratch(4 + 3 * n_warps, 0);
+  l.scratch = scratch.data();
+  const size_t smem = search_smem_bytes(m, learn != 0, sat);
+  for (;;) {
+    emu::launch(n_blocks, THREADS_PER_BLOCK, smem, run_kernel, &l);
+    res->switches += emu::M.switches; res->collectives += emu::M.collectives; res->site_mismatches += emu::M.site_mismatches;
+    emu::launch(1, 1024, 0, run_rebalance, &l);
+    res->switches += emu::M.switches; res->collectives += emu::M.collectives; res->site_mismatches += emu::M.site_mismatches;
+    res->slices++;
+    if (ctl.signal == SIG_STOP || ctl.busy == 0) break;
+    if (res->slices > 1000000) { g_err = "the search does not end"; return -101; }
+  }
+  for (int w = 0; w < n_warps; w++) {
+    const unsigned long long *c = &wcount[(size_t)w * CNT_WIDTH];
+    res->nodes += c[CNT_NODES]; res->cuts += c[CNT_CUTS]; res->props += c[CNT_PROPS]; res->solutions += c[CNT_SOLUTIONS];
+    res->claims += (int32_t)c[CNT_CLAIMS];
+    if ((ws[w].level >= ws[w].base || ws[w].claim_mask != 0u) && ctl.signal != SIG_STOP) {
+      g_err = "a warp left the kernel with open frames: warp " + std::to_string(w) + " level " + std::to_string(ws[w].level) + " base " + std::to_string(ws[w].base) +
+              ", signal " + std::to_string(ctl.signal) + " hungry " + std::to_string(ctl.hungry) + " tickets " + std::to_string(ctl.item_next) + "/" + std::to_string(ctl.item_count);
+      return -100;
+    }   // ANY: the first solution stops everybody
+  }
+  res->best = ctl.best;
+  res->has_solution = res->solutions > 0;
+  res->n_stored = ctl.n_stored;
+  if (learn) { res->conflicts = ng_counters[0]; res->conflicts_abandoned = ng_counters[3] + ng_counters[4]; res->backjumps = ng_counters[5]; }
+  if (solutions != nullptr) {
+    // MIN / MAX: the buffer is a ring, the most recent entry is the optimum's witness
+    const int n = ctl.n_stored;
+    for (int k = 0; k < sol_cap && k < n; k++) {
+      const int slot = m.obj_var >= 0 ? (n - 1 - k) % sol_cap : k;
+      memcpy(solutions + (size_t)k * (V + 1), &solbuf[(size_t)slot * (V + 1)], sizeof(int32_t) * (V + 1));
+    }
+  }
+  return 0;
+}

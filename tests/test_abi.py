@@ -32,7 +32,7 @@ def test_header_symbols_are_exported():
 
 
 def test_abi_version():
-    assert cb.library().csolve_abi_version() == 4
+    assert cb.library().csolve_abi_version() == 5
 
 
 def test_header_compiles_as_c():
@@ -99,3 +99,33 @@ def test_invalid_models_are_rejected_before_touching_the_device():
     bad.n_clauses = d.n_clauses - 1
     assert hc.hc_load(bad, 1) == -1
     assert hc.hc_load(d, 1) == 0
+
+
+def test_ctypes_mirrors_have_the_header_layout(tmp_path):
+    """every field of the option / result structs sits where the C header puts it (a C program prints offsetof)"""
+    structs = {"csolve_solve_options": cb.host._SolveOptions, "csolve_gpu_result": cb.host._GpuResult,
+               "csolve_flat_model": cb.FlatModel}
+    lines = []
+    for cname, ct in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include "csolve_b200.h"\nint main(void) {\n%s\nreturn 0; }\n' % "\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
+
+
+def test_backjump_kernel_is_in_the_library():
+    """csolve_solve_options.backjump runs the depth-first phase on an instance of k_search compiled in its own unit
+    (csrc/kernels_bj.cu); the instances of kernels.cu are the ones every other test and the bench run"""
+    out = subprocess.run(["cuobjdump", "-res-usage", cb.library_path()], capture_output=True, text=True).stdout
+    names = re.findall(r"Function (\w+):", out)
+    bj = [n for n in names if "csolve_dev_bj" in n]
+    assert len(bj) == 1 and "k_searchILb0ELb1ELb0ELb0E" in bj[0], bj
+    assert any("csolve_dev8k_searchILb0ELb1ELb0ELb0E" in n for n in names)

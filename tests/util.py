@@ -4,6 +4,7 @@ import ctypes as C
 import hashlib
 import json
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -42,6 +43,63 @@ def build_harness():
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
                                "-I", csrc, srcs[0], srcs[1], "-o", HARNESS_SO])
     return HARNESS_SO
+
+
+EMU_DIR = os.path.join(ROOT, "build", "emu")
+
+
+def emu_kernel_source(text):
+    """kernels.cu rewritten for the emulator: shared-memory declarations become per-block storage of the emulator, the
+    launch wrappers (<<< >>>, cudaFuncSetAttribute) are cut off; everything else is the product's text."""
+    text, n1 = re.subn(r"extern __shared__ __align__\(16\) int smem\[\];", "int *smem = emu_dynamic_smem();", text)
+    assert n1 >= 1
+
+    def static_shared(mt):
+        indent, ty, decls = mt.group(1), mt.group(2), mt.group(3)
+        out = []
+        for k, d in enumerate(x.strip() for x in decls.split(",")):
+            arr = re.match(r"(\w+)\[(.+)\]$", d)
+            if arr:
+                out.append("%s (&%s)[%s] = *reinterpret_cast<%s (*)[%s]>(emu_static_shared(__LINE__ * 16 + %d, sizeof(%s) * (%s)));"
+                           % (ty, arr.group(1), arr.group(2), ty, arr.group(2), k, ty, arr.group(2)))
+            else:
+                out.append("%s &%s = *reinterpret_cast<%s *>(emu_static_shared(__LINE__ * 16 + %d, sizeof(%s)));" % (ty, d, ty, k, ty))
+        return indent + " ".join(out)
+
+    text, n2 = re.subn(r"(?m)^(\s*)__shared__ ((?:unsigned long long|unsigned int|unsigned|int)) ([^;]+);", static_shared, text)
+    assert n2 >= 1 and "__shared__" not in re.sub(r"//.*", "", text), "a __shared__ declaration the emulator does not know"
+    text = text.replace("__noinline__", "EMU_NOINLINE")
+    # control words every lane of a warp reads for itself to steer a branch with collectives in it: a converged warp
+    # issues such a load once on the device; under the emulator the lanes run one after the other between two
+    # collectives (lane 0 may already have changed the word), so the read is made explicitly uniform
+    text = text.replace("*reinterpret_cast<volatile int *>(&s_blk_hungry)", "EMU_UNIFORM(*reinterpret_cast<volatile int *>(&s_blk_hungry))")
+    text = re.sub(r'asm volatile\("mov\.u64 %0, %%globaltimer;" : "=l"\((\w+)\)\);', r"\1 = (unsigned long long)clock64();", text)
+    assert "asm" not in re.sub(r"//.*", "", text)
+    cut = text.index("static cudaError_t ensure_smem(")
+    return text[:cut] + "\n}  // namespace csolve_dev\n#endif  // CSOLVE_BJ_UNIT (emulator: the launch wrappers are cut off)\n"
+
+
+def build_emu(backjump=False):
+    """The product's general search kernel compiled for the CPU under the SIMT emulator (tests/harness/simt_emu.h):
+    kernels.cu itself, with its dynamic / static __shared__ declarations rewritten to the emulator's per-block storage."""
+    csrc = os.path.join(ROOT, "csolve_b200", "csrc")
+    os.makedirs(EMU_DIR, exist_ok=True)
+    so = os.path.join(EMU_DIR, "libemu_search%s.so" % ("_bj" if backjump else ""))
+    srcs = [os.path.join(ROOT, "tests", "harness", "emu_search.cpp"), os.path.join(ROOT, "tests", "harness", "simt_emu.h"),
+            os.path.join(csrc, "kernels.cu"), os.path.join(csrc, "kernels.cuh"), os.path.join(csrc, "contract.cuh"),
+            os.path.join(csrc, "device_model.h"), os.path.join(csrc, "compile.cpp"), os.path.join(csrc, "compile.hpp")]
+    if _newer(so, srcs):
+        return so
+    text = emu_kernel_source(open(os.path.join(csrc, "kernels.cu")).read())
+    inc = os.path.join(EMU_DIR, "kernels_emu.inc")
+    if not os.path.exists(inc) or open(inc).read() != text:
+        open(inc, "w").write(text)
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fno-omit-frame-pointer", "-w",
+                           "-I", os.path.join(ROOT, "include"), "-I", csrc, "-I", EMU_DIR, "-I", cuda_inc,
+                           "-I", os.path.join(ROOT, "tests", "harness")] + (["-DCSOLVE_BJ=1"] if backjump else []) +
+                          [srcs[0], os.path.join(csrc, "compile.cpp"), "-o", so])
+    return so
 
 
 def ensure_built():
@@ -223,3 +281,43 @@ def flat_digest(flat):
 def load_vectors():
     with open(os.path.join(GOLDEN, "ref_unit_vectors.json")) as f:
         return json.load(f)
+
+
+class EmuResult(C.Structure):
+    _fields_ = [("solutions", C.c_uint64), ("nodes", C.c_uint64), ("cuts", C.c_uint64), ("props", C.c_uint64),
+                ("best", C.c_int32), ("has_solution", C.c_int32), ("n_stored", C.c_int32), ("conflicts", C.c_int32),
+                ("conflicts_abandoned", C.c_int32), ("backjumps", C.c_int32), ("claims", C.c_int32), ("slices", C.c_int32),
+                ("switches", C.c_uint64), ("collectives", C.c_uint64), ("site_mismatches", C.c_uint64)]
+
+
+_emu = {}
+
+
+def emu_lib(backjump=False):
+    """the general search kernel under the SIMT emulator (build_emu); backjump: the back-jumping build"""
+    if backjump not in _emu:
+        import csolve_b200 as cb
+        lib = C.CDLL(build_emu(backjump))
+        lib.emu_search.argtypes = [C.POINTER(cb.FlatModel), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                   C.POINTER(EmuResult), I32P]
+        lib.emu_error.restype = C.c_char_p
+        assert lib.emu_backjump_build() == (1 if backjump else 0)
+        _emu[backjump] = lib
+    return _emu[backjump]
+
+
+def emu_search(model, order=0, learn=False, backjump=False, prefer_failing=False, n_blocks=1, max_solutions=0, general=True,
+               slice_clock=0):
+    """-> (EmuResult, [assignments]) of one whole search of `model` (csolve_b200.Model) on the emulated kernels.
+    general=False: the kernel the product picks for the model (lane-owns-variable, K-per-lane, bit-state, general);
+    slice_clock > 0: time slices of that many emulator clock units with k_rebalance between them."""
+    lib = emu_lib(backjump)
+    res = EmuResult()
+    cap = max_solutions if max_solutions > 0 else 16
+    buf = np.zeros((cap, model.n_vars + 1), np.int32)
+    rc = lib.emu_search(C.byref(model.flat), order, 1 if (learn or backjump) else 0, 1 if prefer_failing else 0, n_blocks,
+                        max_solutions, 1 if general else 0, int(slice_clock), C.byref(res), buf.ctypes.data_as(I32P))
+    if rc != 0:
+        raise RuntimeError("emu_search: %d %s" % (rc, lib.emu_error().decode()))
+    n = min(res.n_stored, cap)
+    return res, [buf[k, :model.n_vars].tolist() for k in range(n)]
