@@ -2514,7 +2514,11 @@ k_search_sat(const SearchArgs a) {
   int depth = -1, tlen = 0;
   int tvar = 0, ttrail = 0, tpos = 0, tnxt = 0, tcnt = 0;      // top decision record
   unsigned n32 = 0;                        // nodes since the kernel started (32 bits are plenty inside one slice)
-  int parked = a.wstate[gw].level;         // top of the private LIFO of parked frames (-1: empty)
+  // private LIFO of parked frames: stack[pbase .. parked] (empty: parked < pbase). k_rebalance hands an idle warp ONE frame,
+  // at the index it had in the donor's stack (level = base = that index): what lies below `base` in this warp's stack is
+  // left over from earlier slices and must not be searched again (found by the CPU emulation of this kernel: ALL-mode
+  // counts of a time-sliced search came out too high)
+  int parked = a.wstate[gw].level, pbase = a.wstate[gw].base;
   Claim cl; cl.base = a.wstate[gw].claim_base; cl.mask = a.wstate[gw].claim_mask; cl.drained = false;
   unsigned long long nodes = 0, cuts = 0, sols = 0, cuts_reported = 0;
   unsigned props = 0, visits = 0, poll = 0;
@@ -2641,7 +2645,7 @@ k_search_sat(const SearchArgs a) {
     if (depth < 0) {
       const int *src;
       int ring_slot = -1;
-      if (parked >= 0) {
+      if (parked >= pbase) {
         src = stack + (size_t)parked * fw;
         parked--;
       } else {
@@ -2882,6 +2886,7 @@ k_search_sat(const SearchArgs a) {
   }
 
   // ---- park: every level with values left becomes a frame of the private LIFO (shallowest first) -----------------
+  if (parked < pbase) { parked = -1; pbase = 0; }      // empty: start again at the bottom of the stack
   if (depth >= 0) {
     if (lane == 0) {
       SatRec r; r.var = (unsigned short)tvar; r.trail = (unsigned short)ttrail; r.pos = (unsigned short)tpos;
@@ -2900,7 +2905,7 @@ k_search_sat(const SearchArgs a) {
   for (int q = 16; q > 0; q >>= 1) visits += __shfl_xor_sync(FULL, visits, q);
   if (lane == 0) {
     a.wstate[gw].level = parked;
-    a.wstate[gw].base = 0;
+    a.wstate[gw].base = pbase;
     a.wstate[gw].claim_base = cl.base; a.wstate[gw].claim_mask = cl.mask;
     unsigned long long *c = a.wcount + (size_t)gw * CNT_WIDTH;
     c[CNT_NODES] += nodes; c[CNT_CUTS] += cuts; c[CNT_PROPS] += props;

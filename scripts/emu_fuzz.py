@@ -35,12 +35,14 @@ def sat_case(rng, backjump):
     o, _ = util.Oracle(m).solve_tree(0)
     learn = rng.random() < 0.7
     kw = dict(order=0 if obj == "ALL" else rng.randint(0, 4), learn=learn, backjump=learn and backjump,
-              prefer_failing=obj != "ALL" and rng.random() < 0.4, n_blocks=rng.choice([1, 1, 2, 3]), max_solutions=16)
+              prefer_failing=obj != "ALL" and rng.random() < 0.4, n_blocks=rng.choice([1, 1, 2, 3]), max_solutions=16,
+              general=rng.random() < 0.5, slice_clock=rng.choice([0, 0, 2000, 10000, 50000]))
     if obj == "ALL":
         o, _ = util.Oracle(m).solve_tree(kw["order"])
     r, sols = util.emu_search(m, **kw)
     if obj == "ALL":
-        ok = (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
+        # learned nogoods cut nodes the plain tree expands: with learning only the solution count is the tree's
+        ok = r.solutions == o.solutions if learn else (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
     elif obj == "ANY":
         ok = r.has_solution == (1 if o.solutions > 0 else 0)
         if ok and r.has_solution:
@@ -52,7 +54,32 @@ def sat_case(rng, backjump):
             val = dict(zip(m.var_names, sols[0]))
             xs = [val["x%d" % i] for i in range(1, n + 1)]
             ok = sum(xs) == r.best and all(any((val["x%d" % abs(l)] == 1) == (l > 0) for l in cl) for cl in cnf)
-    return ok, "sat n=%d %s %s" % (n, obj, kw), r
+    return ok, "sat n=%d %s %s expected %s" % (n, obj, kw, (o.solutions, o.calls, o.cuts, o.best)), r
+
+
+def queens_case(rng, backjump):
+    """N-queens / sudoku: the lane-owns-variable and K-per-lane kernels"""
+    if rng.random() < 0.6:
+        n = rng.randint(4, 9)
+        text = I.queens(n, rng.choice(["ALL", "ALL", "ANY"]))
+    else:
+        text = I.sudoku(I.sudoku_puzzle(random.Random(rng.randint(0, 10**6)), rng.randint(24, 32)), rng.choice(["ALL", "ANY"]))
+    m = cb.Model(text)
+    order = rng.randint(0, 4)
+    o, _ = util.Oracle(m).solve_tree(order)
+    kw = dict(order=order, n_blocks=rng.choice([1, 2, 3]), general=rng.random() < 0.25, slice_clock=rng.choice([0, 0, 2000, 10000, 50000]))
+    r, sols = util.emu_search(m, **kw)
+    if text.startswith("ALL"):
+        ok = (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
+    else:
+        ok = r.has_solution == (1 if o.solutions > 0 else 0)
+        if ok and r.has_solution:
+            # the assignment satisfies the model: as the only root domain it leaves exactly one solution
+            orc = util.Oracle(m)
+            dom = [x for v in sols[0] for x in (v, v)]
+            import numpy as np
+            ok = bool(orc.leaf_true(np.array(dom, np.int32)))
+    return ok, "queens/sudoku %s %s" % (text.split(";")[0], kw), r
 
 
 def generic_case(rng, backjump):
@@ -70,15 +97,16 @@ def generic_case(rng, backjump):
     if o.hit_limit:
         return True, "too large", None
     learn = rng.random() < 0.3
-    kw = dict(order=order, learn=learn, backjump=learn and backjump, n_blocks=rng.choice([1, 2]), max_solutions=16)
+    kw = dict(order=order, learn=learn, backjump=learn and backjump, n_blocks=rng.choice([1, 2]), max_solutions=16,
+              general=rng.random() < 0.5, slice_clock=rng.choice([0, 0, 2000, 10000, 50000]))
     r, sols = util.emu_search(m, **kw)
     if obj == "ALL":
-        ok = (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
+        ok = r.solutions == o.solutions if learn else (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
     elif obj == "ANY":
         ok = r.has_solution == (1 if o.solutions > 0 else 0)
     else:
         ok = r.has_solution == o.has_solution and (not o.has_solution or r.best == o.best)
-    return ok, "generic %s %s\n%s" % (obj, kw, text), r
+    return ok, "generic %s %s expected %s\n%s" % (obj, kw, (o.solutions, o.calls, o.cuts, o.best), text), r
 
 
 def main():
@@ -93,7 +121,7 @@ def main():
     tot = {"nodes": 0, "conflicts": 0, "backjumps": 0, "cases": 0}
     for s in range(a.seed0, a.seed0 + a.seeds):
         rng = random.Random(s)
-        fn = sat_case if (a.kind == "sat" or (a.kind == "both" and s % 2 == 0)) else generic_case
+        fn = {"sat": sat_case, "generic": generic_case, "queens": queens_case}.get(a.kind) or (sat_case, generic_case, queens_case)[s % 3]
         ok, what, r = fn(rng, a.backjump)
         if r is not None:
             tot["cases"] += 1; tot["nodes"] += r.nodes; tot["conflicts"] += r.conflicts; tot["backjumps"] += r.backjumps

@@ -9,6 +9,7 @@
 #include "simt_emu.h"
 extern "C" const void *csolve_bj_search_kernel(void) { return nullptr; }     // kernels_bj.cu's instance: here -DCSOLVE_BJ
 #include "kernels_emu.inc"
+#include <algorithm>
 #include <climits>
 #include <string>
 #include "compile.hpp"
@@ -158,12 +159,17 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   res->n_stored = ctl.n_stored;
   if (learn) { res->conflicts = ng_counters[0]; res->conflicts_abandoned = ng_counters[3] + ng_counters[4]; res->backjumps = ng_counters[5]; }
   if (solutions != nullptr) {
-    // MIN / MAX: the buffer is a ring, the most recent entry is the optimum's witness
-    const int n = ctl.n_stored;
-    for (int k = 0; k < sol_cap && k < n; k++) {
-      const int slot = m.obj_var >= 0 ? (n - 1 - k) % sol_cap : k;
-      memcpy(solutions + (size_t)k * (V + 1), &solbuf[(size_t)slot * (V + 1)], sizeof(int32_t) * (V + 1));
-    }
+    // MIN / MAX: the buffer is a ring of improving incumbents (slots are drawn after the incumbent is updated, so the
+    // order of two warps' entries may be swapped): best key first, as capi.cu sorts them
+    const int n = ctl.n_stored < sol_cap ? ctl.n_stored : sol_cap;
+    std::vector<int> idx(n);
+    for (int k = 0; k < n; k++) idx[k] = k;
+    if (m.obj_var >= 0)
+      std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+        const int kx = solbuf[(size_t)x * (V + 1) + V], ky = solbuf[(size_t)y * (V + 1) + V];
+        return m.objective == CSOLVE_OBJ_MIN ? kx < ky : kx > ky;
+      });
+    for (int k = 0; k < n; k++) memcpy(solutions + (size_t)k * (V + 1), &solbuf[(size_t)idx[k] * (V + 1)], sizeof(int32_t) * (V + 1));
   }
   return 0;
 }

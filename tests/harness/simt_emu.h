@@ -62,6 +62,7 @@ struct Warp {
   const char *op = nullptr;
   long long clock_val = 0;
   unsigned clock_gen = 0;
+  int blocked = 0;          // lanes waiting at a collective or a block barrier
 };
 
 struct Block {
@@ -178,7 +179,7 @@ inline const uint64_t *warp_exchange(uint64_t v, long site, const char *op) {
     // device a converged warp issues such a load once for all lanes)
     if ((M.collectives & 63u) == 0) yield_outer();
   }
-  else while (w.gen == g) yield_inner();
+  else { w.blocked++; while (w.gen == g) yield_inner(); w.blocked--; }
   return w.val[g & 1];
 }
 
@@ -257,7 +258,7 @@ inline void __syncthreads() {
   emu::Block &b = emu::M.blocks[emu::M.cur->block];
   const unsigned g = b.gen;
   if (++b.arrived == b.threads) { b.arrived = 0; b.gen = g + 1; }
-  else while (b.gen == g) emu::yield_outer();
+  else { emu::Warp &w = emu::M.warps[emu::M.cur->warp]; w.blocked++; while (b.gen == g) emu::yield_outer(); w.blocked--; }
 }
 
 // ---- memory, atomics, clocks -----------------------------------------------------------------------------------
@@ -269,7 +270,13 @@ inline void __stcg(int2 *p, int2 v) { *p = v; }
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline void __threadfence_block() {}
-inline void __nanosleep(unsigned) { emu::yield_outer(); }
+// a waiting lane gives the other warps a turn -- once the other lanes of its own warp have caught up with it (they
+// wait at the collective that follows the wait loop): what they read on the way must not be newer than what this lane read
+inline void __nanosleep(unsigned) {
+  emu::Warp &w = emu::M.warps[emu::M.cur->warp];
+  for (int tries = 0; tries < 64 && w.blocked < w.alive - 1; tries++) emu::yield_inner();
+  emu::yield_outer();
+}
 // the clock is read once per warp between two collectives (a converged warp reads one SM clock value on the device)
 inline long long clock64() {
   emu::Warp &w = emu::M.warps[emu::M.cur->warp];

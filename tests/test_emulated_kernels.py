@@ -1,0 +1,153 @@
+"""The search kernels' SOURCE (csolve_b200/csrc/kernels.cu) on the CPU: tests/harness/simt_emu.h runs every CUDA thread as
+a fiber with real warp collectives, tests/harness/emu_search.cpp drives the depth-first phase the way capi.cu does (root
+frame, donation ring, time slices with k_rebalance between them). Checked against the oracle: ALL counters are the
+tree's, optima and statuses are the oracle's, assignments satisfy the model. Test infrastructure only: the product has no
+CPU path (tests/test_abi.py), and what runs here is the kernels' logic, not their memory ordering (simt_emu.h)."""
+import platform
+import random
+
+import numpy as np
+import pytest
+
+import csolve_b200 as cb
+import util
+from csolve_b200 import instances as I
+
+pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emulator's fiber switch is x86-64 assembly")
+
+
+def tree(m, order=0):
+    o, _ = util.Oracle(m).solve_tree(order)
+    return (o.solutions, o.calls, o.cuts)
+
+
+def counters(r):
+    return (r.solutions, r.nodes, r.cuts)
+
+
+def satisfies(cnf, names, assignment):
+    val = {k: v for k, v in zip(names, assignment) if k.startswith("x")}
+    return set(val.values()) <= {0, 1} and all(any((val["x%d" % abs(l)] == 1) == (l > 0) for l in cl) for cl in cnf)
+
+
+@pytest.mark.parametrize("n", [4, 6, 8, 9])
+def test_headline_kernel_counts_the_oracle_tree(n):
+    """k_search_lov<false, true> (N-queens, the headline configuration): solutions, nodes and cuts of the whole tree, in
+    every variable order, with work shared between 16 warps, with and without time slices"""
+    m = cb.Model(I.queens(n))
+    for order in range(5):
+        want = tree(m, order)
+        for blocks, slice_clock in ((1, 0), (2, 0), (2, 20000)):
+            r, _ = util.emu_search(m, order=order, n_blocks=blocks, general=False, slice_clock=slice_clock)
+            assert counters(r) == want, (n, order, blocks, slice_clock)
+            if slice_clock and n >= 8:
+                assert r.slices > 1
+    assert want[0] == {4: 2, 6: 4, 8: 92, 9: 352}[n]
+
+
+def test_general_kernel_on_the_same_trees():
+    """k_search<false> on N-queens (what batched roots run on) and on a 3-SAT model in ALL mode"""
+    for text in (I.queens(6), I.queens(8), I.random_3sat(30, 3.6, 21, "ALL")):
+        m = cb.Model(text)
+        for order in (0, 1, 4):
+            want = tree(m, order)
+            for blocks, slice_clock in ((1, 0), (2, 3000)):
+                r, _ = util.emu_search(m, order=order, n_blocks=blocks, general=True, slice_clock=slice_clock)
+                assert counters(r) == want, (text[:20], order, blocks, slice_clock)
+
+
+def test_sudoku_kernel():
+    """k_search_lovk: one puzzle per search here (the batched root phase is device-side host logic)"""
+    rng = random.Random(5)
+    for _ in range(3):
+        g = I.sudoku_puzzle(rng, 26)
+        m = cb.Model(I.sudoku(g, "ALL"))
+        want = tree(m)
+        for blocks, slice_clock in ((1, 0), (2, 2000)):
+            r, _ = util.emu_search(m, n_blocks=blocks, general=False, slice_clock=slice_clock)
+            assert counters(r) == want and r.solutions == 1
+
+
+def test_bit_state_sat_kernel_with_time_slices():
+    """k_search_sat: the tree's counters in ALL mode -- also when the search is cut into time slices and k_rebalance hands
+    parked frames to idle warps (this test found that a warp which received one frame went on to search what was left
+    below it in its own stack from earlier slices: counts too high; fixed in the kernel)"""
+    cnf = I.random_3sat_cnf(30, 3.6, 21)
+    m = cb.Model(I.cnf_to_csolve(30, cnf, "ALL"))
+    want = tree(m)
+    assert want == (1152, 9413, 156)
+    for blocks in (1, 2):
+        for slice_clock in (0, 30000, 10000, 3000):
+            r, _ = util.emu_search(m, n_blocks=blocks, general=False, slice_clock=slice_clock)
+            assert counters(r) == want, (blocks, slice_clock, counters(r))
+    for n, ratio, seed in ((40, 4.26, 1), (50, 4.6, 4), (60, 4.26, 3)):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        m = cb.Model(I.cnf_to_csolve(n, cnf))
+        sat = tree(m)[0] > 0
+        for blocks, slice_clock, pf in ((1, 0, False), (2, 5000, False), (2, 0, True)):
+            r, sols = util.emu_search(m, n_blocks=blocks, general=False, slice_clock=slice_clock, prefer_failing=pf)
+            assert r.has_solution == (1 if sat else 0)
+            assert not sat or satisfies(cnf, m.var_names, sols[0])
+
+
+def test_branch_and_bound_models():
+    """MIN / MAX: schedule (optimum 11), a generated weighted model; linear clauses contracted by the whole warp"""
+    r, sols = util.emu_search(cb.Model(I.schedule()), n_blocks=1, max_solutions=16)
+    assert r.best == 11 and r.has_solution
+    r, _ = util.emu_search(cb.Model(I.schedule()), n_blocks=2, max_solutions=16, slice_clock=2000)
+    assert r.best == 11
+    for n, ratio, seed in ((16, 3.0, 11), (20, 3.2, 12), (24, 3.5, 13)):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        m = cb.Model(I.cnf_to_csolve(n, cnf, "MIN " + " + ".join("x%d" % i for i in range(1, n + 1))))
+        o, _ = util.Oracle(m).solve_tree(0)
+        for blocks, slice_clock in ((1, 0), (2, 3000)):
+            r, sols = util.emu_search(m, n_blocks=blocks, max_solutions=16, slice_clock=slice_clock)
+            assert r.best == o.best
+            w = dict(zip(m.var_names, sols[0]))
+            assert sum(v for k, v in w.items() if k.startswith("x")) == r.best and satisfies(cnf, m.var_names, sols[0])
+
+
+def test_conflict_learning_and_backjump():
+    """-c on the device with and without back-jumping (csolve_solve_options.backjump, the kernels_bj.cu instance): same
+    status, valid models, same optima; the search does jump; ALL models never do and keep their solution count"""
+    jumps = 0
+    for n, ratio, seed in ((20, 4.26, 1), (30, 4.26, 2), (40, 4.26, 1), (40, 4.26, 2), (50, 4.6, 4), (60, 4.26, 3), (70, 4.26, 9)):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        m = cb.Model(I.cnf_to_csolve(n, cnf))
+        sat = tree(m)[0] > 0
+        for bj in (False, True):
+            for blocks, slice_clock, pf in ((1, 0, False), (2, 0, True), (3, 5000, False)):
+                r, sols = util.emu_search(m, learn=True, backjump=bj, prefer_failing=pf, n_blocks=blocks, slice_clock=slice_clock)
+                assert r.has_solution == (1 if sat else 0), (n, seed, bj, blocks)
+                assert not sat or satisfies(cnf, m.var_names, sols[0])
+                assert r.conflicts > 0 and (bj or r.backjumps == 0)
+                jumps += r.backjumps
+    assert jumps > 100
+    for n, ratio, seed in ((16, 3.0, 11), (20, 3.2, 12), (24, 3.5, 13)):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        m = cb.Model(I.cnf_to_csolve(n, cnf, "MIN " + " + ".join("x%d" % i for i in range(1, n + 1))))
+        o, _ = util.Oracle(m).solve_tree(0)
+        for blocks, slice_clock in ((1, 0), (2, 2000)):
+            r, sols = util.emu_search(m, learn=True, backjump=True, n_blocks=blocks, max_solutions=16, slice_clock=slice_clock)
+            assert r.best == o.best and satisfies(cnf, m.var_names, sols[0])
+    m = cb.Model(I.random_3sat(30, 3.6, 21, "ALL"))
+    r, _ = util.emu_search(m, learn=True, backjump=True, n_blocks=2)
+    assert r.solutions == 1152 and r.backjumps == 0 and r.conflicts > 0
+
+
+def test_generated_models_through_the_emulated_kernels():
+    """the differential fuzzer of scripts/emu_fuzz.py, a bounded run: SAT-shaped, N-queens / sudoku and generated models
+    (every operator of the grammar) through the kernel the product picks or the general one, random warps / slices"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("emu_fuzz", os.path.join(util.ROOT, "scripts", "emu_fuzz.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    n = 0
+    for seed in range(150):
+        rng = random.Random(seed)
+        fn = (fz.sat_case, fz.generic_case, fz.queens_case)[seed % 3]
+        ok, what, r = fn(rng, seed % 2 == 0)
+        assert ok, (seed, what)
+        n += r is not None
+    assert n >= 100

@@ -73,6 +73,12 @@ def emu_kernel_source(text):
     # issues such a load once on the device; under the emulator the lanes run one after the other between two
     # collectives (lane 0 may already have changed the word), so the read is made explicitly uniform
     text = text.replace("*reinterpret_cast<volatile int *>(&s_blk_hungry)", "EMU_UNIFORM(*reinterpret_cast<volatile int *>(&s_blk_hungry))")
+    n0 = text.count("if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;")
+    text = text.replace("if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;",
+                        "if (EMU_UNIFORM(*reinterpret_cast<volatile int *>(&ctl->signal)) != SIG_RUN) break;")
+    n1 = text.count("*reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions")
+    text = text.replace("*reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions", "EMU_UNIFORM(*reinterpret_cast<volatile int *>(&ctl->n_stored)) > a.max_solutions")
+    assert n0 == 4 and n1 == 3, (n0, n1)       # the poll sections of the four search kernels
     text = re.sub(r'asm volatile\("mov\.u64 %0, %%globaltimer;" : "=l"\((\w+)\)\);', r"\1 = (unsigned long long)clock64();", text)
     assert "asm" not in re.sub(r"//.*", "", text)
     cut = text.index("static cudaError_t ensure_smem(")
@@ -87,7 +93,8 @@ def build_emu(backjump=False):
     so = os.path.join(EMU_DIR, "libemu_search%s.so" % ("_bj" if backjump else ""))
     srcs = [os.path.join(ROOT, "tests", "harness", "emu_search.cpp"), os.path.join(ROOT, "tests", "harness", "simt_emu.h"),
             os.path.join(csrc, "kernels.cu"), os.path.join(csrc, "kernels.cuh"), os.path.join(csrc, "contract.cuh"),
-            os.path.join(csrc, "device_model.h"), os.path.join(csrc, "compile.cpp"), os.path.join(csrc, "compile.hpp")]
+            os.path.join(csrc, "device_model.h"), os.path.join(csrc, "compile.cpp"), os.path.join(csrc, "compile.hpp"),
+            os.path.abspath(__file__)]
     if _newer(so, srcs):
         return so
     text = emu_kernel_source(open(os.path.join(csrc, "kernels.cu")).read())
