@@ -261,6 +261,9 @@ void solve(size_t size, struct env_t *env, struct constr_t *constr) {
   opt.order = probe_order();
   opt.part_count = 1;
   opt.create_conflicts = strategy_create_conflicts() ? 1 : 0;
+  /* the reference back-jumps whenever it learns (src/csolve.c:350-364, 463-466); on the device that is an option of its
+   * own (csolve_solve_options.backjump), opted into here with CSOLVE_GPU_BACKJUMP=1 until it has been measured */
+  opt.backjump = opt.create_conflicts && getenv("CSOLVE_GPU_BACKJUMP") != NULL && atoi(getenv("CSOLVE_GPU_BACKJUMP")) != 0;
   opt.prefer_failing = strategy_prefer_failing() ? 1 : 0;
   opt.restart_frequency = (int32_t)(strategy_restart_frequency() > 0x7fffffffu ? 0x7fffffff : strategy_restart_frequency());
   uint32_t time_max = csolve_shim_time_max ? csolve_shim_time_max() : 0;
