@@ -2607,6 +2607,10 @@ k_search_sat(const SearchArgs a) {
     if ((++poll & 3u) == 0 && ((poll & 15u) == 0 || *reinterpret_cast<volatile int *>(&s_blk_hungry) > 0)) {
       if (a.n_peers > 0) comm_poll(a, lane);
       if (a.fail_limit > 0 && restart_due(a, lane, cuts, cuts_reported)) break;
+      if (a.sink_headroom > 0 && *reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions - a.sink_headroom) {
+        if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);      // the solution buffer is nearly full: let the host drain it
+        break;
+      }
       if (*reinterpret_cast<volatile int *>(&ctl->signal) != SIG_RUN) break;
       if (clock64() - t0 > a.slice_cycles) {
         if (lane == 0) atomicMax(&ctl->signal, SIG_SLICE_END);

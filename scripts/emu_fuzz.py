@@ -18,6 +18,19 @@ import util
 from csolve_b200 import instances as I
 
 
+def sink_check(m, o, kw, rng):
+    """ALL models now and then through a bounded solution buffer that is drained between slices (the solution sink of the
+    drop-in): every solution exactly once, each of them a leaf the oracle accepts"""
+    import numpy as np
+    kw = dict(kw, sink_headroom=rng.choice([40, 100, 300]), sink_rows=int(o.solutions) + 8)
+    r, sols = util.emu_search(m, **kw)
+    uniq = {tuple(s) for s in sols}
+    orc = util.Oracle(m)
+    ok = len(sols) == o.solutions == len(uniq) == r.solutions
+    ok = ok and all(orc.leaf_true(np.array([x for v in s for x in (v, v)], np.int32)) for s in list(uniq)[:64])
+    return ok, kw, r
+
+
 def sat_case(rng, backjump):
     n = rng.randint(10, 70)
     ratio = rng.choice([3.0, 3.8, 4.26, 4.26, 4.8])
@@ -39,6 +52,9 @@ def sat_case(rng, backjump):
               general=rng.random() < 0.5, slice_clock=rng.choice([0, 0, 2000, 10000, 50000]))
     if obj == "ALL":
         o, _ = util.Oracle(m).solve_tree(kw["order"])
+    if obj == "ALL" and not learn and o.solutions < 20000 and rng.random() < 0.5:
+        ok, kw, r = sink_check(m, o, kw, rng)
+        return ok, "sat n=%d ALL sink %s expected %s" % (n, kw, o.solutions), r
     r, sols = util.emu_search(m, **kw)
     if obj == "ALL":
         # learned nogoods cut nodes the plain tree expands: with learning only the solution count is the tree's
@@ -68,6 +84,9 @@ def queens_case(rng, backjump):
     order = rng.randint(0, 4)
     o, _ = util.Oracle(m).solve_tree(order)
     kw = dict(order=order, n_blocks=rng.choice([1, 2, 3]), general=rng.random() < 0.25, slice_clock=rng.choice([0, 0, 2000, 10000, 50000]))
+    if text.startswith("ALL") and rng.random() < 0.4:
+        ok, kw, r = sink_check(m, o, kw, rng)
+        return ok, "queens/sudoku ALL sink %s expected %s" % (kw, o.solutions), r
     r, sols = util.emu_search(m, **kw)
     if text.startswith("ALL"):
         ok = (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)

@@ -73,8 +73,11 @@ extern "C" int emu_backjump_build() {
 // general: 1 = the general kernel whatever the model (what capi.cu does for batched roots), 0 = the kernel the product
 // picks (lane-owns-variable / K-per-lane / bit-state / general). slice_clock: length of a time slice in emulator clock
 // units (every clock64() call adds 64), 0 = the whole search in one slice.
+// sink_headroom > 0 (ALL models): the solution buffer holds 4 x sink_headroom assignments and is drained between slices
+// into `solutions` (room for sink_rows assignments), as capi.cu does for csolve_gpu_set_solution_sink.
 extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
-                          int max_solutions, int general, long long slice_clock, emu_result *res, int32_t *solutions) {
+                          int max_solutions, int general, long long slice_clock, int sink_headroom, int sink_rows,
+                          emu_result *res, int32_t *solutions) {
   CompiledModel cm;
   int rc = compile_model(*fm, cm, g_err);
   if (rc != 0) return rc;
@@ -94,7 +97,9 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   std::vector<int32_t> pool((size_t)pool_cap * fw, 0), ready(pool_cap, 0), stacks((size_t)n_warps * (V + 1) * fw, 0);
   std::vector<WarpState> ws(n_warps, WarpState{-1, 0, 0, 0u});
   std::vector<unsigned long long> wcount((size_t)n_warps * CNT_WIDTH, 0);
-  const int sol_cap = max_solutions > 0 ? max_solutions : (m.obj_var >= 0 ? 16 : 1);
+  const bool sinking = sink_headroom > 0 && m.objective == CSOLVE_OBJ_ALL;
+  const int sol_cap = sinking ? 4 * sink_headroom : max_solutions > 0 ? max_solutions : (m.obj_var >= 0 ? 16 : 1);
+  long long sunk = 0;
   std::vector<int32_t> solbuf((size_t)sol_cap * (V + 1), 0);
   const int rv = root_var(cm, order);
   int32_t *root = pool.data();
@@ -125,6 +130,7 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   a.out_cap = pool_cap; a.expand_branch_max = 64;
   a.part_rank = 0; a.part_count = 1;
   a.slice_cycles = slice_clock > 0 ? slice_clock : LLONG_MAX / 2;
+  if (sinking) a.sink_headroom = sink_headroom;
   a.items = pool.data(); a.pool = pool.data(); a.pool_cap = pool_cap; a.ready = ready.data(); a.n_initial = n_initial;
   a.front_pool = pool.data(); a.front_ctl = &ctl; a.total_warps = n_warps;
   a.gprio = prefer_failing ? gprio.data() : nullptr;
@@ -141,6 +147,13 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
     emu::launch(1, 1024, 0, run_rebalance, &l);
     res->switches += emu::M.switches; res->collectives += emu::M.collectives; res->site_mismatches += emu::M.site_mismatches;
     res->slices++;
+    if (sinking && ctl.n_stored > 0) {
+      if (ctl.n_stored > sol_cap) { g_err = "solution buffer overflow: " + std::to_string(ctl.n_stored) + " in one slice, room for " + std::to_string(sol_cap); return -102; }
+      if (sunk + ctl.n_stored > sink_rows) { g_err = "more solutions than the caller expects"; return -103; }
+      memcpy(solutions + (size_t)sunk * (V + 1), solbuf.data(), sizeof(int32_t) * (size_t)ctl.n_stored * (V + 1));
+      sunk += ctl.n_stored;
+      ctl.n_stored = 0;
+    }
     if (ctl.signal == SIG_STOP || ctl.busy == 0) break;
     if (res->slices > 1000000) { g_err = "the search does not end"; return -101; }
   }
@@ -158,7 +171,8 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   res->has_solution = res->solutions > 0;
   res->n_stored = ctl.n_stored;
   if (learn) { res->conflicts = ng_counters[0]; res->conflicts_abandoned = ng_counters[3] + ng_counters[4]; res->backjumps = ng_counters[5]; }
-  if (solutions != nullptr) {
+  if (sinking) res->n_stored = (int32_t)sunk;
+  if (solutions != nullptr && !sinking) {
     // MIN / MAX: the buffer is a ring of improving incumbents (slots are drawn after the incumbent is updated, so the
     // order of two warps' entries may be swapped): best key first, as capi.cu sorts them
     const int n = ctl.n_stored < sol_cap ? ctl.n_stored : sol_cap;

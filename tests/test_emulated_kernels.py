@@ -90,6 +90,24 @@ def test_bit_state_sat_kernel_with_time_slices():
             assert not sat or satisfies(cnf, m.var_names, sols[0])
 
 
+def test_every_solution_through_a_bounded_buffer():
+    """the solution sink of the drop-in (csolve_gpu_set_solution_sink): the kernels end a slice when the solution buffer
+    is nearly full, the host drains it -- every solution arrives exactly once, on all four search kernels (the bit-state
+    SAT kernel did not look at the buffer at all: a loud overflow error on the device; found here, fixed in the kernel)"""
+    for text in (I.queens(8), I.queens(9), I.random_3sat(30, 3.6, 21, "ALL"), I.sudoku(I.sudoku_puzzle(random.Random(7), 24), "ALL")):
+        m = cb.Model(text)
+        orc = util.Oracle(m)
+        o, _ = orc.solve_tree(0)
+        for general in (False, True):
+            for blocks, slice_clock, headroom in ((1, 0, 40), (2, 5000, 80), (3, 20000, 120)):
+                r, sols = util.emu_search(m, n_blocks=blocks, general=general, slice_clock=slice_clock, sink_headroom=headroom,
+                                          sink_rows=int(o.solutions) + 8)
+                uniq = {tuple(s) for s in sols}
+                assert len(sols) == len(uniq) == o.solutions == r.solutions, (text[:12], general, blocks, slice_clock)
+                for s1 in list(uniq)[:50]:
+                    assert orc.leaf_true(np.array([x for v in s1 for x in (v, v)], np.int32))
+
+
 def test_branch_and_bound_models():
     """MIN / MAX: schedule (optimum 11), a generated weighted model; linear clauses contracted by the whole warp"""
     r, sols = util.emu_search(cb.Model(I.schedule()), n_blocks=1, max_solutions=16)

@@ -78,7 +78,7 @@ def emu_kernel_source(text):
                         "if (EMU_UNIFORM(*reinterpret_cast<volatile int *>(&ctl->signal)) != SIG_RUN) break;")
     n1 = text.count("*reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions")
     text = text.replace("*reinterpret_cast<volatile int *>(&ctl->n_stored) > a.max_solutions", "EMU_UNIFORM(*reinterpret_cast<volatile int *>(&ctl->n_stored)) > a.max_solutions")
-    assert n0 == 4 and n1 == 3, (n0, n1)       # the poll sections of the four search kernels
+    assert n0 == 4 and n1 == 4, (n0, n1)       # the poll sections of the four search kernels
     text = re.sub(r'asm volatile\("mov\.u64 %0, %%globaltimer;" : "=l"\((\w+)\)\);', r"\1 = (unsigned long long)clock64();", text)
     assert "asm" not in re.sub(r"//.*", "", text)
     cut = text.index("static cudaError_t ensure_smem(")
@@ -306,7 +306,7 @@ def emu_lib(backjump=False):
         import csolve_b200 as cb
         lib = C.CDLL(build_emu(backjump))
         lib.emu_search.argtypes = [C.POINTER(cb.FlatModel), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
-                                   C.POINTER(EmuResult), I32P]
+                                   C.c_int, C.c_int, C.POINTER(EmuResult), I32P]
         lib.emu_error.restype = C.c_char_p
         assert lib.emu_backjump_build() == (1 if backjump else 0)
         _emu[backjump] = lib
@@ -314,16 +314,19 @@ def emu_lib(backjump=False):
 
 
 def emu_search(model, order=0, learn=False, backjump=False, prefer_failing=False, n_blocks=1, max_solutions=0, general=True,
-               slice_clock=0):
+               slice_clock=0, sink_headroom=0, sink_rows=0):
     """-> (EmuResult, [assignments]) of one whole search of `model` (csolve_b200.Model) on the emulated kernels.
     general=False: the kernel the product picks for the model (lane-owns-variable, K-per-lane, bit-state, general);
-    slice_clock > 0: time slices of that many emulator clock units with k_rebalance between them."""
+    slice_clock > 0: time slices of that many emulator clock units with k_rebalance between them;
+    sink_headroom > 0 (ALL models): a bounded solution buffer drained between slices, every solution returned (at most
+    sink_rows)."""
     lib = emu_lib(backjump)
     res = EmuResult()
-    cap = max_solutions if max_solutions > 0 else 16
+    cap = sink_rows if sink_headroom > 0 else (max_solutions if max_solutions > 0 else 16)
     buf = np.zeros((cap, model.n_vars + 1), np.int32)
     rc = lib.emu_search(C.byref(model.flat), order, 1 if (learn or backjump) else 0, 1 if prefer_failing else 0, n_blocks,
-                        max_solutions, 1 if general else 0, int(slice_clock), C.byref(res), buf.ctypes.data_as(I32P))
+                        max_solutions, 1 if general else 0, int(slice_clock), int(sink_headroom), int(sink_rows), C.byref(res),
+                        buf.ctypes.data_as(I32P))
     if rc != 0:
         raise RuntimeError("emu_search: %d %s" % (rc, lib.emu_error().decode()))
     n = min(res.n_stored, cap)
