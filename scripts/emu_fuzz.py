@@ -18,6 +18,21 @@ import util
 from csolve_b200 import instances as I
 
 
+def ranks_search(m, kw, rng):
+    """the search as `world` ranks run it in ALL mode: everybody expands the root, the frames are dealt by path hash, the
+    counters add up (the expansion is reported by rank 0)"""
+    world = rng.choice([1, 1, 2, 3])
+    kw = dict(kw, split_target=rng.choice([1, 1, 8, 64, 500]))
+    tot = None
+    for rank in range(world):
+        r, sols = util.emu_search(m, part_rank=rank, part_count=world, **kw)
+        if tot is None:
+            tot = r
+        else:
+            tot.solutions += r.solutions; tot.nodes += r.nodes; tot.cuts += r.cuts
+    return tot, sols, dict(kw, world=world)
+
+
 def sink_check(m, o, kw, rng):
     """ALL models now and then through a bounded solution buffer that is drained between slices (the solution sink of the
     drop-in): every solution exactly once, each of them a leaf the oracle accepts"""
@@ -55,7 +70,10 @@ def sat_case(rng, backjump):
     if obj == "ALL" and not learn and o.solutions < 20000 and rng.random() < 0.5:
         ok, kw, r = sink_check(m, o, kw, rng)
         return ok, "sat n=%d ALL sink %s expected %s" % (n, kw, o.solutions), r
-    r, sols = util.emu_search(m, **kw)
+    if obj == "ALL" and not learn:
+        r, sols, kw = ranks_search(m, kw, rng)
+    else:
+        r, sols = util.emu_search(m, split_target=rng.choice([1, 1, 8, 64]), **kw)
     if obj == "ALL":
         # learned nogoods cut nodes the plain tree expands: with learning only the solution count is the tree's
         ok = r.solutions == o.solutions if learn else (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
@@ -87,7 +105,10 @@ def queens_case(rng, backjump):
     if text.startswith("ALL") and rng.random() < 0.4:
         ok, kw, r = sink_check(m, o, kw, rng)
         return ok, "queens/sudoku ALL sink %s expected %s" % (kw, o.solutions), r
-    r, sols = util.emu_search(m, **kw)
+    if text.startswith("ALL"):
+        r, sols, kw = ranks_search(m, kw, rng)
+    else:
+        r, sols = util.emu_search(m, split_target=rng.choice([1, 1, 8, 64]), **kw)
     if text.startswith("ALL"):
         ok = (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
     else:
@@ -118,7 +139,10 @@ def generic_case(rng, backjump):
     learn = rng.random() < 0.3
     kw = dict(order=order, learn=learn, backjump=learn and backjump, n_blocks=rng.choice([1, 2]), max_solutions=16,
               general=rng.random() < 0.5, slice_clock=rng.choice([0, 0, 2000, 10000, 50000]))
-    r, sols = util.emu_search(m, **kw)
+    if obj == "ALL" and not learn:
+        r, sols, kw = ranks_search(m, kw, rng)
+    else:
+        r, sols = util.emu_search(m, split_target=rng.choice([1, 1, 8, 64]), **kw)
     if obj == "ALL":
         ok = r.solutions == o.solutions if learn else (r.solutions, r.nodes, r.cuts) == (o.solutions, o.calls, o.cuts)
     elif obj == "ANY":

@@ -57,6 +57,7 @@ std::string g_err;
 struct emu_result {
   uint64_t solutions, nodes, cuts, props;
   int32_t best, has_solution, n_stored, conflicts, conflicts_abandoned, backjumps, claims, slices;
+  int32_t expand_levels, frontier;
   uint64_t switches, collectives, site_mismatches;
 };
 
@@ -73,11 +74,14 @@ extern "C" int emu_backjump_build() {
 // general: 1 = the general kernel whatever the model (what capi.cu does for batched roots), 0 = the kernel the product
 // picks (lane-owns-variable / K-per-lane / bit-state / general). slice_clock: length of a time slice in emulator clock
 // units (every clock64() call adds 64), 0 = the whole search in one slice.
+// split_target > 1: the root is expanded breadth-first first (k_search<true>, level by level as capi.cu's expand_root)
+// until at least that many frames exist; part_rank / part_count: this call searches the frames whose path hash maps to
+// part_rank (the ALL-mode partition between GPUs; the replicated expansion is reported by rank 0 only).
 // sink_headroom > 0 (ALL models): the solution buffer holds 4 x sink_headroom assignments and is drained between slices
 // into `solutions` (room for sink_rows assignments), as capi.cu does for csolve_gpu_set_solution_sink.
 extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
                           int max_solutions, int general, long long slice_clock, int sink_headroom, int sink_rows,
-                          emu_result *res, int32_t *solutions) {
+                          int split_target, int part_rank, int part_count, emu_result *res, int32_t *solutions) {
   CompiledModel cm;
   int rc = compile_model(*fm, cm, g_err);
   if (rc != 0) return rc;
@@ -93,8 +97,9 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   ctl.best = m.objective == CSOLVE_OBJ_MIN ? INT32_MAX : (m.objective == CSOLVE_OBJ_MAX ? INT32_MIN : 0);
   ctl.signal = SIG_RUN;
   const int ring = 4 * n_warps + 1024;   // ring_min_frames of capi.cu
-  const int n_initial = 1, pool_cap = n_initial + ring;
-  std::vector<int32_t> pool((size_t)pool_cap * fw, 0), ready(pool_cap, 0), stacks((size_t)n_warps * (V + 1) * fw, 0);
+  const int target = split_target > 1 ? split_target : 1;
+  const int pool_cap = std::max(4 * target, 1024) + ring;
+  std::vector<int32_t> pool((size_t)pool_cap * fw, 0), pool_b((size_t)pool_cap * fw, 0), ready(pool_cap, 0), stacks((size_t)n_warps * (V + 1) * fw, 0);
   std::vector<WarpState> ws(n_warps, WarpState{-1, 0, 0, 0u});
   std::vector<unsigned long long> wcount((size_t)n_warps * CNT_WIDTH, 0);
   const bool sinking = sink_headroom > 0 && m.objective == CSOLVE_OBJ_ALL;
@@ -131,17 +136,59 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   a.part_rank = 0; a.part_count = 1;
   a.slice_cycles = slice_clock > 0 ? slice_clock : LLONG_MAX / 2;
   if (sinking) a.sink_headroom = sink_headroom;
-  a.items = pool.data(); a.pool = pool.data(); a.pool_cap = pool_cap; a.ready = ready.data(); a.n_initial = n_initial;
-  a.front_pool = pool.data(); a.front_ctl = &ctl; a.total_warps = n_warps;
+  std::vector<int32_t> scratch(4 + 3 * n_warps, 0);
+  l.scratch = scratch.data();
+
+  // ---- batched frontier expansion (capi.cu: expand_root) ----------------------------------------------------------
+  int32_t *pin = pool.data(), *pout = pool_b.data();
+  int n_items = 1;
+  bool stopped = false;
+  {
+    long long max_branch = 1;
+    for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
+    max_branch = std::min<long long>(max_branch, a.expand_branch_max);
+    l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, true, false, false, false, false)));
+    const size_t smem_x = search_smem_bytes(m, false, false);
+    for (int lvl = 0; lvl < V && lvl < 24 && n_items > 0 && n_items < target; ++lvl) {
+      const int before = n_items;
+      if ((long long)n_items * max_branch > pool_cap - ring) break;
+      a.items = pin; a.items_out = pout; a.frozen_best = ctl.best;
+      ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.passed = 0;
+      const int grid = std::min(n_blocks, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+      emu::launch(grid, THREADS_PER_BLOCK, smem_x, run_kernel, &l);
+      res->collectives += emu::M.collectives;
+      if (ctl.out_dropped > 0) { g_err = "frontier pool overflow during expansion"; return -104; }
+      if (sinking && ctl.n_stored > 0) {
+        if (sunk + ctl.n_stored > sink_rows) { g_err = "more solutions than the caller expects"; return -103; }
+        if (!(part_count > 1 && part_rank != 0)) { memcpy(solutions + (size_t)sunk * (V + 1), solbuf.data(), sizeof(int32_t) * (size_t)ctl.n_stored * (V + 1)); sunk += ctl.n_stored; }
+        ctl.n_stored = 0;
+      }
+      n_items = ctl.out_count;
+      std::swap(pin, pout);
+      res->expand_levels++;
+      if (ctl.signal == SIG_STOP) { stopped = true; break; }
+      if (ctl.passed == n_items) break;
+      if (n_items >= n_warps / 2 && n_items < 2 * (long long)before) break;
+    }
+  }
+  a.part_rank = part_rank; a.part_count = part_count > 0 ? part_count : 1;
+  if (a.part_count > 1 && part_rank != 0) {
+    std::fill(wcount.begin(), wcount.end(), 0ull);       // the replicated expansion is reported by rank 0 only
+    if (m.objective == CSOLVE_OBJ_ALL) ctl.n_stored = 0;
+  }
+  res->frontier = n_items;
+  a.items = pin; a.items_out = nullptr;
+  a.pool = pin; a.pool_cap = pool_cap; a.ready = ready.data(); a.n_initial = n_items;
+  a.front_pool = pin; a.front_ctl = &ctl; a.total_warps = n_warps;
   a.gprio = prefer_failing ? gprio.data() : nullptr;
   if (learn) a.ng = ng;
+  ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0;
+  ctl.signal = stopped ? SIG_STOP : SIG_RUN;
   const bool sat = !general && search_uses_sat(m, learn != 0, order);
   a.use_sat = sat ? 1 : 0;
   l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, learn != 0, false, sat, false)));
-  std::vector<int32_t> scratch(4 + 3 * n_warps, 0);
-  l.scratch = scratch.data();
   const size_t smem = search_smem_bytes(m, learn != 0, sat);
-  for (;;) {
+  for (; !stopped && n_items > 0;) {
     emu::launch(n_blocks, THREADS_PER_BLOCK, smem, run_kernel, &l);
     res->switches += emu::M.switches; res->collectives += emu::M.collectives; res->site_mismatches += emu::M.site_mismatches;
     emu::launch(1, 1024, 0, run_rebalance, &l);

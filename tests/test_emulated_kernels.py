@@ -56,6 +56,22 @@ def test_general_kernel_on_the_same_trees():
                 assert counters(r) == want, (text[:20], order, blocks, slice_clock)
 
 
+def test_expansion_and_the_partition_between_ranks():
+    """k_search<true> / k_search_lov<true> expand the root breadth-first; in ALL mode every rank does, keeps the frames
+    whose path hash maps to it, and the ranks' counters add up to the tree (the multi-GPU mode of the headline bench)"""
+    for text in (I.queens(8), I.queens(9), I.random_3sat(30, 3.6, 21, "ALL")):
+        m = cb.Model(text)
+        want = tree(m)
+        for general in (False, True):
+            for split, world in ((8, 1), (64, 1), (64, 2), (200, 3), (100000, 1)):
+                tot = [0, 0, 0]
+                for rank in range(world):
+                    r, _ = util.emu_search(m, n_blocks=2, general=general, split_target=split, part_rank=rank, part_count=world, slice_clock=20000)
+                    tot[0] += r.solutions; tot[1] += r.nodes; tot[2] += r.cuts
+                    assert r.expand_levels >= 1 and r.frontier >= min(split, 8)
+                assert tuple(tot) == want, (text[:12], general, split, world)
+
+
 def test_sudoku_kernel():
     """k_search_lovk: one puzzle per search here (the batched root phase is device-side host logic)"""
     rng = random.Random(5)

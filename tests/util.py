@@ -294,6 +294,7 @@ class EmuResult(C.Structure):
     _fields_ = [("solutions", C.c_uint64), ("nodes", C.c_uint64), ("cuts", C.c_uint64), ("props", C.c_uint64),
                 ("best", C.c_int32), ("has_solution", C.c_int32), ("n_stored", C.c_int32), ("conflicts", C.c_int32),
                 ("conflicts_abandoned", C.c_int32), ("backjumps", C.c_int32), ("claims", C.c_int32), ("slices", C.c_int32),
+                ("expand_levels", C.c_int32), ("frontier", C.c_int32),
                 ("switches", C.c_uint64), ("collectives", C.c_uint64), ("site_mismatches", C.c_uint64)]
 
 
@@ -306,7 +307,7 @@ def emu_lib(backjump=False):
         import csolve_b200 as cb
         lib = C.CDLL(build_emu(backjump))
         lib.emu_search.argtypes = [C.POINTER(cb.FlatModel), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
-                                   C.c_int, C.c_int, C.POINTER(EmuResult), I32P]
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(EmuResult), I32P]
         lib.emu_error.restype = C.c_char_p
         assert lib.emu_backjump_build() == (1 if backjump else 0)
         _emu[backjump] = lib
@@ -314,18 +315,20 @@ def emu_lib(backjump=False):
 
 
 def emu_search(model, order=0, learn=False, backjump=False, prefer_failing=False, n_blocks=1, max_solutions=0, general=True,
-               slice_clock=0, sink_headroom=0, sink_rows=0):
+               slice_clock=0, sink_headroom=0, sink_rows=0, split_target=1, part_rank=0, part_count=1):
     """-> (EmuResult, [assignments]) of one whole search of `model` (csolve_b200.Model) on the emulated kernels.
     general=False: the kernel the product picks for the model (lane-owns-variable, K-per-lane, bit-state, general);
     slice_clock > 0: time slices of that many emulator clock units with k_rebalance between them;
     sink_headroom > 0 (ALL models): a bounded solution buffer drained between slices, every solution returned (at most
-    sink_rows)."""
+    sink_rows); split_target > 1: breadth-first expansion of the root first (k_search<true>); part_rank / part_count: the
+    share of the expanded frontier whose path hash maps to this rank (the ALL-mode partition between GPUs)."""
     lib = emu_lib(backjump)
     res = EmuResult()
     cap = sink_rows if sink_headroom > 0 else (max_solutions if max_solutions > 0 else 16)
     buf = np.zeros((cap, model.n_vars + 1), np.int32)
     rc = lib.emu_search(C.byref(model.flat), order, 1 if (learn or backjump) else 0, 1 if prefer_failing else 0, n_blocks,
-                        max_solutions, 1 if general else 0, int(slice_clock), int(sink_headroom), int(sink_rows), C.byref(res),
+                        max_solutions, 1 if general else 0, int(slice_clock), int(sink_headroom), int(sink_rows), int(split_target), int(part_rank),
+                        int(part_count), C.byref(res),
                         buf.ctypes.data_as(I32P))
     if rc != 0:
         raise RuntimeError("emu_search: %d %s" % (rc, lib.emu_error().decode()))
