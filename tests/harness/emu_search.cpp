@@ -51,6 +51,7 @@ void run_rebalance(void *arg) {
 }
 
 std::string g_err;
+std::vector<int32_t> g_ng_flat;      // nogoods of the last learning search: len, literals (var << 1 | value), len, ...
 
 }  // namespace
 
@@ -62,6 +63,12 @@ struct emu_result {
 };
 
 extern "C" const char *emu_error() { return g_err.c_str(); }
+// nogoods learned by the last search, flattened (length, literals, length, ...); returns the number of words
+extern "C" int emu_nogoods(int32_t *out, int cap) {
+  const int n = (int)g_ng_flat.size();
+  if (out != nullptr) memcpy(out, g_ng_flat.data(), sizeof(int32_t) * (size_t)std::min(n, cap));
+  return n;
+}
 extern "C" int emu_backjump_build() {
 #ifdef CSOLVE_BJ
   return 1;
@@ -217,6 +224,14 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   res->best = ctl.best;
   res->has_solution = res->solutions > 0;
   res->n_stored = ctl.n_stored;
+  g_ng_flat.clear();
+  if (learn) {
+    const int n_ng = std::min(ng_counters[0], ng.cap_ng);
+    for (int k = 0; k < n_ng; k++) {
+      g_ng_flat.push_back(ng_len[k]);
+      for (int j = 0; j < ng_len[k]; j++) g_ng_flat.push_back(ng_lits[ng_start[k] + j]);
+    }
+  }
   if (learn) { res->conflicts = ng_counters[0]; res->conflicts_abandoned = ng_counters[3] + ng_counters[4]; res->backjumps = ng_counters[5]; }
   if (sinking) res->n_stored = (int32_t)sunk;
   if (solutions != nullptr && !sinking) {

@@ -169,6 +169,34 @@ def test_conflict_learning_and_backjump():
     assert r.solutions == 1152 and r.backjumps == 0 and r.conflicts > 0
 
 
+def test_learned_nogoods_are_implied_by_the_model():
+    """conflict_create on the device (learn_nogood, src/conflict.c:327-362): every nogood the emulated search learns -- with
+    or without back-jumping, 0/1 literals only (src/conflict.c:173-179) -- leaves the model without a solution when its
+    literals are added as constraints"""
+    checked = 0
+    for n, ratio, seed, obj in ((20, 4.0, 3, "ANY"), (24, 3.8, 5, "ALL"), (30, 4.26, 2, "ANY"), (22, 3.5, 8, "MIN")):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        head = obj if obj != "MIN" else "MIN " + " + ".join("x%d" % i for i in range(1, n + 1))
+        text = I.cnf_to_csolve(n, cnf, head)
+        m = cb.Model(text)
+        names = m.var_names
+        for bj in (False, True):
+            r, _ = util.emu_search(m, learn=True, backjump=bj, n_blocks=2, max_solutions=16)
+            ngs = util.emu_nogoods(bj)
+            assert len(ngs) == r.conflicts > 0
+            for ng in ngs[:: max(1, len(ngs) // 12)]:
+                assert all(val in (0, 1) for _, val in ng) and len({v for v, _ in ng}) == len(ng)
+                assert all(names[v].startswith("x") for v, _ in ng)
+                extra = "".join("%s = %d;\n" % (names[v], val) for v, val in ng)
+                try:
+                    o, _ = util.Oracle(cb.Model(I.cnf_to_csolve(n, cnf, "ALL") + extra)).solve_tree(0)
+                    assert o.solutions == 0, (n, seed, bj, ng)
+                except cb.CsolveError as e:
+                    assert e.code == -3                      # already infeasible at root
+                checked += 1
+    assert checked >= 40
+
+
 def test_generated_models_through_the_emulated_kernels():
     """the differential fuzzer of scripts/emu_fuzz.py, a bounded run: SAT-shaped, N-queens / sudoku and generated models
     (every operator of the grammar) through the kernel the product picks or the general one, random warps / slices"""

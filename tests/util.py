@@ -334,3 +334,18 @@ def emu_search(model, order=0, learn=False, backjump=False, prefer_failing=False
         raise RuntimeError("emu_search: %d %s" % (rc, lib.emu_error().decode()))
     n = min(res.n_stored, cap)
     return res, [buf[k, :model.n_vars].tolist() for k in range(n)]
+
+
+def emu_nogoods(backjump=False):
+    """nogoods learned by the last emu_search(learn=True) of that build: [[(var, value), ...], ...]"""
+    lib = emu_lib(backjump)
+    lib.emu_nogoods.argtypes = [I32P, C.c_int]
+    n = lib.emu_nogoods(None, 0)
+    buf = np.zeros(max(n, 1), np.int32)
+    lib.emu_nogoods(buf.ctypes.data_as(I32P), n)
+    out, i = [], 0
+    while i < n:
+        k = int(buf[i])
+        out.append([(int(l) >> 1, int(l) & 1) for l in buf[i + 1:i + 1 + k]])
+        i += 1 + k
+    return out
