@@ -45,6 +45,16 @@ void run_kernel(void *arg) {
   const Launch *l = static_cast<const Launch *>(arg);
   l->fn(l->a);
 }
+struct BatchLaunch { DevModel m; int n_roots; const int32_t *root_dom; int order; int32_t *frames; int cap; int32_t *n_out; unsigned char *failed; };
+void run_root_frames(void *arg) {
+  const BatchLaunch *b = static_cast<const BatchLaunch *>(arg);
+  switch (b->m.lovk) {
+  case 0: k_root_frames(b->m, b->n_roots, b->root_dom, b->order, b->frames, b->cap, b->n_out, b->failed); break;
+  case 2: k_root_frames_lovk<2>(b->m, b->n_roots, b->root_dom, b->order, b->frames, b->cap, b->n_out, b->failed); break;
+  case 3: k_root_frames_lovk<3>(b->m, b->n_roots, b->root_dom, b->order, b->frames, b->cap, b->n_out, b->failed); break;
+  default: k_root_frames_lovk<4>(b->m, b->n_roots, b->root_dom, b->order, b->frames, b->cap, b->n_out, b->failed); break;
+  }
+}
 void run_rebalance(void *arg) {
   const Launch *l = static_cast<const Launch *>(arg);
   k_rebalance(l->a, l->scratch);
@@ -86,13 +96,19 @@ extern "C" int emu_backjump_build() {
 // part_rank (the ALL-mode partition between GPUs; the replicated expansion is reported by rank 0 only).
 // sink_headroom > 0 (ALL models): the solution buffer holds 4 x sink_headroom assignments and is drained between slices
 // into `solutions` (room for sink_rows assignments), as capi.cu does for csolve_gpu_set_solution_sink.
-extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
-                          int max_solutions, int general, long long slice_clock, int sink_headroom, int sink_rows,
-                          int split_target, int part_rank, int part_count, emu_result *res, int32_t *solutions) {
+// n_roots > 0: batched roots (csolve_gpu_solve_batch): the root phase runs on the device (k_root_frames / _lovk: every
+// root propagated to fixpoint, one tagged frame per consistent root), per-root solution counts and failed flags come back.
+static int search_core(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
+                       int max_solutions, int general, long long slice_clock, int sink_headroom, int sink_rows,
+                       int split_target, int part_rank, int part_count, int n_roots, const int32_t *root_dom,
+                       uint32_t *root_solutions, uint8_t *root_failed, emu_result *res, int32_t *solutions) {
   CompiledModel cm;
   int rc = compile_model(*fm, cm, g_err);
   if (rc != 0) return rc;
   DevModel m = cm.host;
+  const bool batch = n_roots > 0;
+  if (batch && m.objective != CSOLVE_OBJ_ALL) { g_err = "batched roots need an ALL model"; return -105; }
+  if (batch) m.lov = 0;                  // capi.cu: batched roots run on the general kernels (or the K-per-lane one)
   if (general || learn) { m.lov = 0; m.lovk = 0; }
   if (prefer_failing && m.lov) prefer_failing = 0;       // capi.cu: the lane-owns-variable kernel has no dynamic priorities
   const int V = m.n_vars, fw = m.frame_words;
@@ -105,7 +121,7 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   ctl.signal = SIG_RUN;
   const int ring = 4 * n_warps + 1024;   // ring_min_frames of capi.cu
   const int target = split_target > 1 ? split_target : 1;
-  const int pool_cap = std::max(4 * target, 1024) + ring;
+  const int pool_cap = std::max(std::max(4 * target, 1024), 2 * n_roots) + ring;
   std::vector<int32_t> pool((size_t)pool_cap * fw, 0), pool_b((size_t)pool_cap * fw, 0), ready(pool_cap, 0), stacks((size_t)n_warps * (V + 1) * fw, 0);
   std::vector<WarpState> ws(n_warps, WarpState{-1, 0, 0, 0u});
   std::vector<unsigned long long> wcount((size_t)n_warps * CNT_WIDTH, 0);
@@ -150,7 +166,20 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
   int32_t *pin = pool.data(), *pout = pool_b.data();
   int n_items = 1;
   bool stopped = false;
-  {
+  std::vector<unsigned int> rsol(std::max(n_roots, 1), 0u);
+  if (batch) {
+    // root phase on the device (capi.cu: launch_root_frames)
+    static BatchLaunch bl;
+    std::vector<unsigned char> rfail(n_roots, 0);
+    int32_t n_out = 0;
+    bl = BatchLaunch{m, n_roots, root_dom, order, pool.data(), pool_cap, &n_out, rfail.data()};
+    const int grid = std::min(n_blocks, (n_roots + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    emu::launch(grid, THREADS_PER_BLOCK, m.lovk ? 0 : search_smem_bytes(m, false), run_root_frames, &bl);
+    memcpy(root_failed, rfail.data(), n_roots);
+    n_items = n_out;
+    a.inst_solutions = rsol.data();
+  }
+  if (!(batch && n_items >= n_warps / 2)) {
     long long max_branch = 1;
     for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
     max_branch = std::min<long long>(max_branch, a.expand_branch_max);
@@ -221,6 +250,7 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
       return -100;
     }   // ANY: the first solution stops everybody
   }
+  if (batch) for (int r = 0; r < n_roots; r++) root_solutions[r] = rsol[r];
   res->best = ctl.best;
   res->has_solution = res->solutions > 0;
   res->n_stored = ctl.n_stored;
@@ -248,4 +278,19 @@ extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int
     for (int k = 0; k < n; k++) memcpy(solutions + (size_t)k * (V + 1), &solbuf[(size_t)idx[k] * (V + 1)], sizeof(int32_t) * (V + 1));
   }
   return 0;
+}
+
+extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
+                          int max_solutions, int general, long long slice_clock, int sink_headroom, int sink_rows,
+                          int split_target, int part_rank, int part_count, emu_result *res, int32_t *solutions) {
+  return search_core(fm, order, learn, prefer_failing, n_blocks, max_solutions, general, slice_clock, sink_headroom, sink_rows,
+                     split_target, part_rank, part_count, 0, nullptr, nullptr, nullptr, res, solutions);
+}
+
+// csolve_gpu_solve_batch: root_dom [n_roots][2 * n_vars]; root_solutions [n_roots], root_failed [n_roots] come back
+extern "C" int emu_search_batch(const csolve_flat_model *fm, int order, int n_blocks, int general, long long slice_clock,
+                                int split_target, int n_roots, const int32_t *root_dom, uint32_t *root_solutions,
+                                uint8_t *root_failed, emu_result *res) {
+  return search_core(fm, order, 0, 0, n_blocks, 0, general, slice_clock, 0, 0, split_target, 0, 1, n_roots, root_dom,
+                     root_solutions, root_failed, res, nullptr);
 }

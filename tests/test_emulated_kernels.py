@@ -84,6 +84,33 @@ def test_sudoku_kernel():
             assert counters(r) == want and r.solutions == 1
 
 
+def test_batched_sudoku_roots():
+    """csolve_gpu_solve_batch: the root phase on the device (k_root_frames_lovk / k_root_frames: every root propagated to
+    fixpoint, one tagged frame per consistent root), then one search over all roots with per-root solution counters --
+    against the oracle's per-instance trees (tests/golden/tree_counts.json, the fixture of the device test)"""
+    import json
+    import os
+    t = json.load(open(os.path.join(util.GOLDEN, "tree_counts.json")))["sudoku_batch200_seed20261018/smallest-domain"]
+    grids = I.sudoku_batch(200, seed=20261018)[:24]
+    want = t["per_root"][:24]
+    m = cb.Model(I.sudoku("." * 81))
+    roots = I.sudoku_roots(m.var_names, grids)
+    for general in (False, True):
+        for blocks, slice_clock in ((1, 0), (2, 3000)):
+            r, counts, failed = util.emu_search_batch(m, roots, order=1, n_blocks=blocks, general=general, slice_clock=slice_clock)
+            assert not failed.any() and counts.tolist() == [w[0] for w in want]
+            assert counters(r) == tuple(sum(w[k] for w in want) for k in range(3))
+    r1, c1, _ = util.emu_search_batch(m, roots[5:6], order=1)
+    assert counters(r1) == tuple(want[5])
+    # a root whose clues contradict each other fails in the root phase and contributes nothing
+    bad = np.array(roots[:3], np.int32).copy()
+    a, b = m.var_names.index(I._cell(0, 0)), m.var_names.index(I._cell(0, 1))
+    bad[1, 2 * a:2 * a + 2] = 5
+    bad[1, 2 * b:2 * b + 2] = 5
+    r, counts, failed = util.emu_search_batch(m, bad, order=1)
+    assert failed.tolist() == [0, 1, 0] and counts.tolist() == [want[0][0], 0, want[2][0]]
+
+
 def test_bit_state_sat_kernel_with_time_slices():
     """k_search_sat: the tree's counters in ALL mode -- also when the search is cut into time slices and k_rebalance hands
     parked frames to idle warps (this test found that a warp which received one frame went on to search what was left

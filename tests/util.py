@@ -349,3 +349,21 @@ def emu_nogoods(backjump=False):
         out.append([(int(l) >> 1, int(l) & 1) for l in buf[i + 1:i + 1 + k]])
         i += 1 + k
     return out
+
+
+def emu_search_batch(model, root_domains, order=0, n_blocks=1, general=False, slice_clock=0, split_target=1):
+    """csolve_gpu_solve_batch on the emulated kernels: -> (EmuResult, per-root solution counts, per-root failed flags)"""
+    lib = emu_lib(False)
+    U32P, U8P = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    lib.emu_search_batch.argtypes = [C.POINTER(type(model.flat)), C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, I32P,
+                                     U32P, U8P, C.POINTER(EmuResult)]
+    roots = np.ascontiguousarray(root_domains, np.int32).reshape(-1, 2 * model.n_vars)
+    n = roots.shape[0]
+    counts = np.zeros(n, np.uint32)
+    failed = np.zeros(n, np.uint8)
+    res = EmuResult()
+    rc = lib.emu_search_batch(C.byref(model.flat), order, n_blocks, 1 if general else 0, int(slice_clock), int(split_target), n,
+                              roots.ctypes.data_as(I32P), counts.ctypes.data_as(U32P), failed.ctypes.data_as(U8P), C.byref(res))
+    if rc != 0:
+        raise RuntimeError("emu_search_batch: %d %s" % (rc, lib.emu_error().decode()))
+    return res, counts, failed
