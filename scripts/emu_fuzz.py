@@ -70,6 +70,8 @@ def sat_case(rng, backjump):
     if obj == "ALL" and not learn and o.solutions < 20000 and rng.random() < 0.5:
         ok, kw, r = sink_check(m, o, kw, rng)
         return ok, "sat n=%d ALL sink %s expected %s" % (n, kw, o.solutions), r
+    if obj == "ANY" and kw["prefer_failing"] and not learn and rng.random() < 0.6:
+        kw["restart_frequency"] = rng.choice([1, 2, 5, 20])         # Luby restarts (-r), ANY models without learning
     if obj == "ALL" and not learn:
         r, sols, kw = ranks_search(m, kw, rng)
     else:

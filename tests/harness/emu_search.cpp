@@ -68,7 +68,7 @@ std::vector<int32_t> g_ng_flat;      // nogoods of the last learning search: len
 struct emu_result {
   uint64_t solutions, nodes, cuts, props;
   int32_t best, has_solution, n_stored, conflicts, conflicts_abandoned, backjumps, claims, slices;
-  int32_t expand_levels, frontier;
+  int32_t expand_levels, frontier, restarts, pad;
   uint64_t switches, collectives, site_mismatches;
 };
 
@@ -100,7 +100,7 @@ extern "C" int emu_backjump_build() {
 // root propagated to fixpoint, one tagged frame per consistent root), per-root solution counts and failed flags come back.
 static int search_core(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
                        int max_solutions, int general, long long slice_clock, int sink_headroom, int sink_rows,
-                       int split_target, int part_rank, int part_count, int n_roots, const int32_t *root_dom,
+                       int split_target, int part_rank, int part_count, int restart_frequency, int n_roots, const int32_t *root_dom,
                        uint32_t *root_solutions, uint8_t *root_failed, emu_result *res, int32_t *solutions) {
   CompiledModel cm;
   int rc = compile_model(*fm, cm, g_err);
@@ -129,14 +129,17 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
   const int sol_cap = sinking ? 4 * sink_headroom : max_solutions > 0 ? max_solutions : (m.obj_var >= 0 ? 16 : 1);
   long long sunk = 0;
   std::vector<int32_t> solbuf((size_t)sol_cap * (V + 1), 0);
-  const int rv = root_var(cm, order);
+  auto upload_root_frame = [&](int rv) {
   int32_t *root = pool.data();
+  std::fill(root, root + fw, 0);
   root[FR_VAR] = rv; root[FR_ITER] = 0;
   root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
   root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
   root[FR_LEVEL] = 0; root[FR_BEST] = ctl.best; root[7] = 0x1234567;
   memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
   if (m.lovk) memcpy(&root[frame_dom_offset(m.mask_words) + 2 * V], cm.lov_fconst.data(), sizeof(int32_t) * V);   // value sets
+  };
+  upload_root_frame(root_var(cm, order));
 
   std::vector<int32_t> gprio(cm.prio.begin(), cm.prio.end());
   NogoodPool ng;
@@ -179,7 +182,8 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
     n_items = n_out;
     a.inst_solutions = rsol.data();
   }
-  if (!(batch && n_items >= n_warps / 2)) {
+  int rc_expand = 0;
+  auto expand_root = [&]() {
     long long max_branch = 1;
     for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
     max_branch = std::min<long long>(max_branch, a.expand_branch_max);
@@ -193,9 +197,9 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
       const int grid = std::min(n_blocks, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
       emu::launch(grid, THREADS_PER_BLOCK, smem_x, run_kernel, &l);
       res->collectives += emu::M.collectives;
-      if (ctl.out_dropped > 0) { g_err = "frontier pool overflow during expansion"; return -104; }
+      if (ctl.out_dropped > 0) { g_err = "frontier pool overflow during expansion"; rc_expand = -104; return; }
       if (sinking && ctl.n_stored > 0) {
-        if (sunk + ctl.n_stored > sink_rows) { g_err = "more solutions than the caller expects"; return -103; }
+        if (sunk + ctl.n_stored > sink_rows) { g_err = "more solutions than the caller expects"; rc_expand = -103; return; }
         if (!(part_count > 1 && part_rank != 0)) { memcpy(solutions + (size_t)sunk * (V + 1), solbuf.data(), sizeof(int32_t) * (size_t)ctl.n_stored * (V + 1)); sunk += ctl.n_stored; }
         ctl.n_stored = 0;
       }
@@ -206,7 +210,9 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
       if (ctl.passed == n_items) break;
       if (n_items >= n_warps / 2 && n_items < 2 * (long long)before) break;
     }
-  }
+  };
+  if (!(batch && n_items >= n_warps / 2)) expand_root();
+  if (rc_expand != 0) return rc_expand;
   a.part_rank = part_rank; a.part_count = part_count > 0 ? part_count : 1;
   if (a.part_count > 1 && part_rank != 0) {
     std::fill(wcount.begin(), wcount.end(), 0ull);       // the replicated expansion is reported by rank 0 only
@@ -224,6 +230,12 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
   a.use_sat = sat ? 1 : 0;
   l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, learn != 0, false, sat, false)));
   const size_t smem = search_smem_bytes(m, learn != 0, sat);
+  void (*const fn_dfs)(const SearchArgs) = l.fn;
+  // restarts (capi.cu; src/csolve.c:76-83, 264-276): Luby thresholds in units of restart_frequency failed nodes per warp
+  const bool restarting = restart_frequency > 0 && m.objective == CSOLVE_OBJ_ANY && a.gprio != nullptr && !batch && !learn;
+  unsigned long long luby_counter = 1, luby_threshold = 1;
+  auto fail_limit_now = [&]() { return (int32_t)std::min((double)luby_threshold * (double)restart_frequency * (double)n_warps, 2.0e9); };
+  if (restarting) a.fail_limit = fail_limit_now();
   for (; !stopped && n_items > 0;) {
     emu::launch(n_blocks, THREADS_PER_BLOCK, smem, run_kernel, &l);
     res->switches += emu::M.switches; res->collectives += emu::M.collectives; res->site_mismatches += emu::M.site_mismatches;
@@ -239,6 +251,29 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
     }
     if (ctl.signal == SIG_STOP || ctl.busy == 0) break;
     if (res->slices > 1000000) { g_err = "the search does not end"; return -101; }
+    if (restarting && ctl.fails > a.fail_limit) {
+      // RESTART: every open frame is dropped, the root is expanded again in the order of the priorities learned so far
+      if ((luby_counter & (~luby_counter + 1)) == luby_threshold) { luby_counter++; luby_threshold = 1; } else { luby_threshold <<= 1; }
+      res->restarts++;
+      std::vector<int32_t> ord(V);
+      for (int v = 0; v < V; v++) ord[v] = v;
+      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return gprio[x] > gprio[y]; });
+      std::copy(ord.begin(), ord.end(), cm.order.begin());       // DevModel::order points into cm.order
+      upload_root_frame(ord[0]);
+      std::fill(ws.begin(), ws.end(), WarpState{-1, 0, 0, 0u});
+      pin = pool.data(); pout = pool_b.data(); n_items = 1;
+      a.gprio = nullptr; a.fail_limit = 0;
+      ctl.signal = SIG_RUN;
+      expand_root();
+      if (rc_expand != 0) return rc_expand;
+      a.items = pin; a.items_out = nullptr;
+      a.pool = pin; a.front_pool = pin; a.n_initial = n_items; a.gprio = gprio.data();
+      a.fail_limit = fail_limit_now();
+      std::fill(ready.begin(), ready.end(), 0);
+      ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0; ctl.fails = 0;
+      l.fn = fn_dfs;
+      if (stopped || n_items == 0) break;
+    }
   }
   for (int w = 0; w < n_warps; w++) {
     const unsigned long long *c = &wcount[(size_t)w * CNT_WIDTH];
@@ -282,15 +317,15 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
 
 extern "C" int emu_search(const csolve_flat_model *fm, int order, int learn, int prefer_failing, int n_blocks,
                           int max_solutions, int general, long long slice_clock, int sink_headroom, int sink_rows,
-                          int split_target, int part_rank, int part_count, emu_result *res, int32_t *solutions) {
+                          int split_target, int part_rank, int part_count, int restart_frequency, emu_result *res, int32_t *solutions) {
   return search_core(fm, order, learn, prefer_failing, n_blocks, max_solutions, general, slice_clock, sink_headroom, sink_rows,
-                     split_target, part_rank, part_count, 0, nullptr, nullptr, nullptr, res, solutions);
+                     split_target, part_rank, part_count, restart_frequency, 0, nullptr, nullptr, nullptr, res, solutions);
 }
 
 // csolve_gpu_solve_batch: root_dom [n_roots][2 * n_vars]; root_solutions [n_roots], root_failed [n_roots] come back
 extern "C" int emu_search_batch(const csolve_flat_model *fm, int order, int n_blocks, int general, long long slice_clock,
                                 int split_target, int n_roots, const int32_t *root_dom, uint32_t *root_solutions,
                                 uint8_t *root_failed, emu_result *res) {
-  return search_core(fm, order, 0, 0, n_blocks, 0, general, slice_clock, 0, 0, split_target, 0, 1, n_roots, root_dom,
+  return search_core(fm, order, 0, 0, n_blocks, 0, general, slice_clock, 0, 0, split_target, 0, 1, 0, n_roots, root_dom,
                      root_solutions, root_failed, res, nullptr);
 }

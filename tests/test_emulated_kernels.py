@@ -151,6 +151,24 @@ def test_every_solution_through_a_bounded_buffer():
                     assert orc.leaf_true(np.array([x for v in s1 for x in (v, v)], np.int32))
 
 
+def test_luby_restarts():
+    """-r on ANY models (src/csolve.c:76-83, 264-276): the warps report their failed nodes, the slice ends at the Luby
+    threshold, the host drops every frame and expands the root again in the order of the priorities learned so far
+    (the harness mirrors capi.cu's loop) -- same status, valid models, on the bit-state kernel and the general one"""
+    restarts = 0
+    for n, ratio, seed in ((40, 4.26, 1), (50, 4.6, 4), (60, 4.26, 3), (80, 4.26, 5)):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        m = cb.Model(I.cnf_to_csolve(n, cnf))
+        sat = tree(m)[0] > 0
+        for general in (False, True):
+            for blocks, rf, split in ((1, 1, 1), (2, 2, 16), (2, 5, 64)):
+                r, sols = util.emu_search(m, n_blocks=blocks, general=general, prefer_failing=True, restart_frequency=rf, split_target=split)
+                assert r.has_solution == (1 if sat else 0), (n, general, blocks, rf)
+                assert not sat or satisfies(cnf, m.var_names, sols[0])
+                restarts += r.restarts
+    assert restarts > 50
+
+
 def test_branch_and_bound_models():
     """MIN / MAX: schedule (optimum 11), a generated weighted model; linear clauses contracted by the whole warp"""
     r, sols = util.emu_search(cb.Model(I.schedule()), n_blocks=1, max_solutions=16)

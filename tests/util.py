@@ -294,7 +294,7 @@ class EmuResult(C.Structure):
     _fields_ = [("solutions", C.c_uint64), ("nodes", C.c_uint64), ("cuts", C.c_uint64), ("props", C.c_uint64),
                 ("best", C.c_int32), ("has_solution", C.c_int32), ("n_stored", C.c_int32), ("conflicts", C.c_int32),
                 ("conflicts_abandoned", C.c_int32), ("backjumps", C.c_int32), ("claims", C.c_int32), ("slices", C.c_int32),
-                ("expand_levels", C.c_int32), ("frontier", C.c_int32),
+                ("expand_levels", C.c_int32), ("frontier", C.c_int32), ("restarts", C.c_int32), ("pad", C.c_int32),
                 ("switches", C.c_uint64), ("collectives", C.c_uint64), ("site_mismatches", C.c_uint64)]
 
 
@@ -307,7 +307,7 @@ def emu_lib(backjump=False):
         import csolve_b200 as cb
         lib = C.CDLL(build_emu(backjump))
         lib.emu_search.argtypes = [C.POINTER(cb.FlatModel), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
-                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(EmuResult), I32P]
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(EmuResult), I32P]
         lib.emu_error.restype = C.c_char_p
         assert lib.emu_backjump_build() == (1 if backjump else 0)
         _emu[backjump] = lib
@@ -315,7 +315,7 @@ def emu_lib(backjump=False):
 
 
 def emu_search(model, order=0, learn=False, backjump=False, prefer_failing=False, n_blocks=1, max_solutions=0, general=True,
-               slice_clock=0, sink_headroom=0, sink_rows=0, split_target=1, part_rank=0, part_count=1):
+               slice_clock=0, sink_headroom=0, sink_rows=0, split_target=1, part_rank=0, part_count=1, restart_frequency=0):
     """-> (EmuResult, [assignments]) of one whole search of `model` (csolve_b200.Model) on the emulated kernels.
     general=False: the kernel the product picks for the model (lane-owns-variable, K-per-lane, bit-state, general);
     slice_clock > 0: time slices of that many emulator clock units with k_rebalance between them;
@@ -328,7 +328,7 @@ def emu_search(model, order=0, learn=False, backjump=False, prefer_failing=False
     buf = np.zeros((cap, model.n_vars + 1), np.int32)
     rc = lib.emu_search(C.byref(model.flat), order, 1 if (learn or backjump) else 0, 1 if prefer_failing else 0, n_blocks,
                         max_solutions, 1 if general else 0, int(slice_clock), int(sink_headroom), int(sink_rows), int(split_target), int(part_rank),
-                        int(part_count), C.byref(res),
+                        int(part_count), int(restart_frequency), C.byref(res),
                         buf.ctypes.data_as(I32P))
     if rc != 0:
         raise RuntimeError("emu_search: %d %s" % (rc, lib.emu_error().decode()))
