@@ -967,6 +967,7 @@ k_search(const SearchArgs a) {
         int *r = sample_begin(a, lane, ok ? 0 : SAMPLE_FAILED, var, val, best);
         if (r != nullptr) for (int w = lane; w < 2 * V; w += 32) { r[4 + w] = s.p[w]; r[4 + 2 * V + w] = s.d[w]; }
       }
+      __syncwarp();      // every lane has copied its words of s.p / s.d before the push below overwrites s.p
     }
 
     if (!ok) {

@@ -61,6 +61,9 @@ void run_rebalance(void *arg) {
 }
 
 std::string g_err;
+std::vector<int32_t> g_samples;      // records of the last search with sample_mod > 0 (sample_words(V) words each)
+int g_sample_seen = 0;
+unsigned g_sample_mod = 0, g_sample_fkeep = 1;
 std::vector<int32_t> g_ng_flat;      // nogoods of the last learning search: len, literals (var << 1 | value), len, ...
 
 }  // namespace
@@ -73,6 +76,14 @@ struct emu_result {
 };
 
 extern "C" const char *emu_error() { return g_err.c_str(); }
+// parity instrumentation (csolve_solve_options.sample_mod): the next searches run on the SAMPLE instances of the kernels
+extern "C" void emu_set_sampling(unsigned mod, unsigned failed_keep) { g_sample_mod = mod; g_sample_fkeep = failed_keep; }
+// records of the last sampled search: returns the number kept, *seen = hits including the ones that did not fit
+extern "C" int emu_samples(int32_t *out, int cap_words, int *seen) {
+  if (seen != nullptr) *seen = g_sample_seen;
+  if (out != nullptr) memcpy(out, g_samples.data(), sizeof(int32_t) * std::min((size_t)cap_words, g_samples.size()));
+  return (int)g_samples.size();
+}
 // nogoods learned by the last search, flattened (length, literals, length, ...); returns the number of words
 extern "C" int emu_nogoods(int32_t *out, int cap) {
   const int n = (int)g_ng_flat.size();
@@ -164,6 +175,15 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
   if (sinking) a.sink_headroom = sink_headroom;
   std::vector<int32_t> scratch(4 + 3 * n_warps, 0);
   l.scratch = scratch.data();
+  const bool sample = g_sample_mod != 0u && !learn;
+  const int sample_cap = 1 << 16;
+  int32_t sample_n = 0;
+  g_samples.clear(); g_sample_seen = 0;
+  if (sample) {
+    g_samples.assign((size_t)sample_cap * sample_words(V), 0);
+    a.sample_rec = g_samples.data(); a.sample_n = &sample_n; a.sample_cap = sample_cap; a.sample_mod = g_sample_mod;
+    a.sample_fkeep = g_sample_fkeep > 0 ? g_sample_fkeep : 1;
+  }
 
   // ---- batched frontier expansion (capi.cu: expand_root) ----------------------------------------------------------
   int32_t *pin = pool.data(), *pout = pool_b.data();
@@ -187,7 +207,7 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
     long long max_branch = 1;
     for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
     max_branch = std::min<long long>(max_branch, a.expand_branch_max);
-    l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, true, false, false, false, false)));
+    l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, true, false, sample, false, false)));
     const size_t smem_x = search_smem_bytes(m, false, false);
     for (int lvl = 0; lvl < V && lvl < 24 && n_items > 0 && n_items < target; ++lvl) {
       const int before = n_items;
@@ -228,7 +248,7 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
   ctl.signal = stopped ? SIG_STOP : SIG_RUN;
   const bool sat = !general && search_uses_sat(m, learn != 0, order);
   a.use_sat = sat ? 1 : 0;
-  l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, learn != 0, false, sat, false)));
+  l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, learn != 0, sample, sat, false)));
   const size_t smem = search_smem_bytes(m, learn != 0, sat);
   void (*const fn_dfs)(const SearchArgs) = l.fn;
   // restarts (capi.cu; src/csolve.c:76-83, 264-276): Luby thresholds in units of restart_frequency failed nodes per warp
@@ -286,6 +306,7 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
     }   // ANY: the first solution stops everybody
   }
   if (batch) for (int r = 0; r < n_roots; r++) root_solutions[r] = rsol[r];
+  if (sample) { g_sample_seen = sample_n; g_samples.resize((size_t)std::min(sample_n, sample_cap) * sample_words(V)); }
   res->best = ctl.best;
   res->has_solution = res->solutions > 0;
   res->n_stored = ctl.n_stored;

@@ -151,6 +151,31 @@ def test_every_solution_through_a_bounded_buffer():
                     assert orc.leaf_true(np.array([x for v in s1 for x in (v, v)], np.int32))
 
 
+def test_search_sampled_nodes_replay_through_the_oracle():
+    """the parity instrumentation (csolve_solve_options.sample_mod, the SAMPLE instances of the kernels): every recorded
+    node -- executed, or counted in bulk by a kernel shortcut -- has the oracle's fail flag and post-fixpoint domains;
+    all four search kernels, expansion included. (Here the general kernel's record copy turned out to lack a warp sync
+    before the push overwrites the parent domains: harmless on a converged warp, wrong words under the emulator's lane
+    order; the sync is in the kernel now.)"""
+    import search_samples as S
+    cases = (("q8", I.queens(8), {}), ("q9", I.queens(9), dict(order=1)), ("sat30", I.random_3sat(30, 3.6, 21, "ALL"), {}),
+             ("sat60", I.random_3sat(60, 4.26, 3), {}), ("schedule", I.schedule(), dict(max_solutions=16)),
+             ("sudoku", I.sudoku(I.sudoku_puzzle(random.Random(5), 26)), dict(order=1)))
+    counted = 0
+    for name, text, kw in cases:
+        m = cb.Model(text)
+        for general in (False, True):
+            for split in (1, 64):
+                r, smp = util.emu_sampled_search(m, 3, 2, n_blocks=2, general=general, split_target=split, slice_clock=20000, **kw)
+                n, nonfailed, bad = S.check_against_oracle(m, smp)
+                assert n > 10 and not bad, (name, general, split, bad[:1])
+                assert smp["seen"] == n
+                counted += int(((smp["flags"] & S.COUNTED) != 0).sum())
+                if m.objective == cb.OBJ_ALL:
+                    assert counters(r) == tree(m, kw.get("order", 0))
+    assert counted > 1000          # the bulk shortcuts of the specialised kernels were exercised
+
+
 def test_luby_restarts():
     """-r on ANY models (src/csolve.c:76-83, 264-276): the warps report their failed nodes, the slice ends at the Luby
     threshold, the host drops every frame and expands the root again in the order of the priorities learned so far

@@ -367,3 +367,24 @@ def emu_search_batch(model, root_domains, order=0, n_blocks=1, general=False, sl
     if rc != 0:
         raise RuntimeError("emu_search_batch: %d %s" % (rc, lib.emu_error().decode()))
     return res, counts, failed
+
+
+def emu_sampled_search(model, sample_mod, failed_keep=1, **kw):
+    """emu_search on the SAMPLE instances of the kernels: -> (EmuResult, records as GpuProblem.samples() returns them)"""
+    lib = emu_lib(False)
+    lib.emu_set_sampling.argtypes = [C.c_uint, C.c_uint]
+    lib.emu_samples.argtypes = [I32P, C.c_int, C.POINTER(C.c_int)]
+    lib.emu_set_sampling(int(sample_mod), int(failed_keep))
+    try:
+        r, _ = emu_search(model, **kw)
+    finally:
+        lib.emu_set_sampling(0, 1)
+    seen = C.c_int()
+    n_words = lib.emu_samples(None, 0, C.byref(seen))
+    V = model.n_vars
+    W = 4 + 4 * V
+    buf = np.zeros(max(n_words, 1), np.int32)
+    lib.emu_samples(buf.ctypes.data_as(I32P), n_words, C.byref(seen))
+    buf = buf[:n_words].reshape(-1, W)
+    return r, dict(flags=buf[:, 0].copy(), var=buf[:, 1].copy(), val=buf[:, 2].copy(), best=buf[:, 3].copy(),
+                   parent=buf[:, 4:4 + 2 * V].copy(), child=buf[:, 4 + 2 * V:].copy(), seen=seen.value)
