@@ -96,11 +96,16 @@ inline void switch_to(Fiber *to) {
   emu_switch(&from->sp, to->sp);
 }
 
+// Lane schedule: between two collectives the lanes of a warp run one after the other, in ascending lane order (step 1),
+// descending (step 31) or any odd stride. Results must not depend on it: a kernel whose answer changes with the stride has
+// lanes communicating through memory without a warp sync in between (a race the hardware's lockstep usually hides).
+extern int lane_step;
+
 // next live lane of the current warp (cyclic, may be the caller itself)
 inline Fiber *next_lane(const Fiber *f) {
   Warp &w = M.warps[f->warp];
   for (int k = 1; k <= 32; k++) {
-    Fiber *c = &M.fibers[w.first + ((f->lane + k) & 31)];
+    Fiber *c = &M.fibers[w.first + ((f->lane + k * lane_step) & 31)];
     if (!c->done) return c;
   }
   return nullptr;
@@ -371,7 +376,7 @@ inline void launch(int grid, int block, size_t smem_bytes, void (*entry)(void *)
 }  // namespace emu
 
 #ifdef EMU_DEFINE_MACHINE
-namespace emu { Machine M; }
+namespace emu { Machine M; int lane_step = 1; }
 asm(R"(
 .text
 .globl emu_switch

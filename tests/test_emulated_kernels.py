@@ -176,6 +176,31 @@ def test_search_sampled_nodes_replay_through_the_oracle():
     assert counted > 1000          # the bulk shortcuts of the specialised kernels were exercised
 
 
+def test_results_do_not_depend_on_the_lane_schedule():
+    """race detection: between two collectives the emulator runs a warp's lanes one after the other; whatever the order
+    (ascending, descending, stride 13) counters, optima, recorded nodes and learned-search statuses stay the same -- a lane
+    that read what another lane wrote without a warp sync in between would show here"""
+    import search_samples as S
+    try:
+        for step in (31, 13):
+            util.emu_set_lane_step(step)
+            for text, kw in ((I.queens(8), {}), (I.random_3sat(30, 3.6, 21, "ALL"), {}), (I.sudoku(I.sudoku_puzzle(random.Random(5), 26)), dict(order=1))):
+                m = cb.Model(text)
+                want = tree(m, kw.get("order", 0))
+                for general in (False, True):
+                    r, smp = util.emu_sampled_search(m, 3, 2, n_blocks=2, general=general, split_target=16, slice_clock=20000, **kw)
+                    assert counters(r) == want and not S.check_against_oracle(m, smp)[2], (step, text[:10], general)
+            cnf = I.random_3sat_cnf(50, 4.6, 4)
+            m = cb.Model(I.cnf_to_csolve(50, cnf))
+            for bj in (False, True):
+                r, sols = util.emu_search(m, learn=True, backjump=bj, n_blocks=2, slice_clock=5000)
+                assert r.has_solution == 1 and satisfies(cnf, m.var_names, sols[0])
+            r, _ = util.emu_search(cb.Model(I.schedule()), n_blocks=2, max_solutions=16, slice_clock=2000)
+            assert r.best == 11
+    finally:
+        util.emu_set_lane_step(1)
+
+
 def test_luby_restarts():
     """-r on ANY models (src/csolve.c:76-83, 264-276): the warps report their failed nodes, the slice ends at the Luby
     threshold, the host drops every frame and expands the root again in the order of the priorities learned so far

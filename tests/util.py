@@ -310,6 +310,7 @@ def emu_lib(backjump=False):
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(EmuResult), I32P]
         lib.emu_error.restype = C.c_char_p
         assert lib.emu_backjump_build() == (1 if backjump else 0)
+        lib.emu_set_lane_step(int(os.environ.get("EMU_LANE_STEP", "1")))     # the emulator's lane schedule (simt_emu.h)
         _emu[backjump] = lib
     return _emu[backjump]
 
@@ -388,3 +389,9 @@ def emu_sampled_search(model, sample_mod, failed_keep=1, **kw):
     buf = buf[:n_words].reshape(-1, W)
     return r, dict(flags=buf[:, 0].copy(), var=buf[:, 1].copy(), val=buf[:, 2].copy(), best=buf[:, 3].copy(),
                    parent=buf[:, 4:4 + 2 * V].copy(), child=buf[:, 4 + 2 * V:].copy(), seen=seen.value)
+
+
+def emu_set_lane_step(step):
+    """lane schedule of the emulator (both builds): odd stride, 1 = ascending lanes, 31 = descending (simt_emu.h)"""
+    for bj in (False, True):
+        emu_lib(bj).emu_set_lane_step(int(step))
