@@ -78,6 +78,8 @@ struct emu_result {
 extern "C" const char *emu_error() { return g_err.c_str(); }
 // lane schedule of the emulator (simt_emu.h): an odd stride, 1 = ascending lanes, 31 = descending
 extern "C" void emu_set_lane_step(int step) { emu::lane_step = (step & 31) | 1; }
+// warp schedule: collectives a warp completes before the other warps get their turn (default 64)
+extern "C" void emu_set_warp_quantum(int q) { emu::warp_quantum = q > 0 ? (unsigned)q : 64u; }
 // parity instrumentation (csolve_solve_options.sample_mod): the next searches run on the SAMPLE instances of the kernels
 extern "C" void emu_set_sampling(unsigned mod, unsigned failed_keep) { g_sample_mod = mod; g_sample_fkeep = failed_keep; }
 // records of the last sampled search: returns the number kept, *seen = hits including the ones that did not fit

@@ -100,6 +100,8 @@ inline void switch_to(Fiber *to) {
 // descending (step 31) or any odd stride. Results must not depend on it: a kernel whose answer changes with the stride has
 // lanes communicating through memory without a warp sync in between (a race the hardware's lockstep usually hides).
 extern int lane_step;
+// Warp schedule: a running warp gives the others a turn after every warp_quantum-th collective (and whenever it waits).
+extern unsigned warp_quantum;
 
 // next live lane of the current warp (cyclic, may be the caller itself)
 inline Fiber *next_lane(const Fiber *f) {
@@ -182,7 +184,7 @@ inline const uint64_t *warp_exchange(uint64_t v, long site, const char *op) {
     // the other warps get their turn HERE, where this warp is converged: between two collectives its lanes run one
     // after the other without anybody else in between, so that they all read the same values from memory (on the
     // device a converged warp issues such a load once for all lanes)
-    if ((M.collectives & 63u) == 0) yield_outer();
+    if (M.collectives % warp_quantum == 0) yield_outer();
   }
   else { w.blocked++; while (w.gen == g) yield_inner(); w.blocked--; }
   return w.val[g & 1];
@@ -376,7 +378,7 @@ inline void launch(int grid, int block, size_t smem_bytes, void (*entry)(void *)
 }  // namespace emu
 
 #ifdef EMU_DEFINE_MACHINE
-namespace emu { Machine M; int lane_step = 1; }
+namespace emu { Machine M; int lane_step = 1; unsigned warp_quantum = 64; }
 asm(R"(
 .text
 .globl emu_switch

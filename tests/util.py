@@ -311,6 +311,7 @@ def emu_lib(backjump=False):
         lib.emu_error.restype = C.c_char_p
         assert lib.emu_backjump_build() == (1 if backjump else 0)
         lib.emu_set_lane_step(int(os.environ.get("EMU_LANE_STEP", "1")))     # the emulator's lane schedule (simt_emu.h)
+        lib.emu_set_warp_quantum(int(os.environ.get("EMU_WARP_QUANTUM", "64")))   # ... and its warp schedule
         _emu[backjump] = lib
     return _emu[backjump]
 
