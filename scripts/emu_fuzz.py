@@ -37,7 +37,8 @@ def sink_check(m, o, kw, rng):
     """ALL models now and then through a bounded solution buffer that is drained between slices (the solution sink of the
     drop-in): every solution exactly once, each of them a leaf the oracle accepts"""
     import numpy as np
-    kw = dict(kw, sink_headroom=rng.choice([40, 100, 300]), sink_rows=int(o.solutions) + 8)
+    # the head room capi.cu reserves (sink_headroom()): every warp may add a solution per node until its next poll
+    kw = dict(kw, sink_headroom=64 * 8 * kw["n_blocks"] + rng.choice([8, 64, 256]), sink_rows=int(o.solutions) + 8)
     r, sols = util.emu_search(m, **kw)
     uniq = {tuple(s) for s in sols}
     orc = util.Oracle(m)

@@ -142,7 +142,7 @@ def test_every_solution_through_a_bounded_buffer():
         orc = util.Oracle(m)
         o, _ = orc.solve_tree(0)
         for general in (False, True):
-            for blocks, slice_clock, headroom in ((1, 0, 40), (2, 5000, 80), (3, 20000, 120)):
+            for blocks, slice_clock, headroom in ((1, 0, 40), (2, 5000, 80), (3, 20000, 120)):      # (tight: the schedule is fine-grained)
                 r, sols = util.emu_search(m, n_blocks=blocks, general=general, slice_clock=slice_clock, sink_headroom=headroom,
                                           sink_rows=int(o.solutions) + 8)
                 uniq = {tuple(s) for s in sols}
