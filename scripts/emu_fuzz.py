@@ -125,6 +125,35 @@ def queens_case(rng, backjump):
     return ok, "queens/sudoku %s %s" % (text.split(";")[0], kw), r
 
 
+def comm_case(rng, backjump):
+    """ANY / MIN models on 2-3 emulated GPUs of a csolve_gpu_comm (util.emu_search_comm)"""
+    n = rng.randint(10, 60)
+    cnf = I.random_3sat_cnf(n, rng.choice([3.0, 3.8, 4.26, 4.8]), rng.randint(1, 10**6))
+    obj = rng.choice(["ANY", "MIN"])
+    if obj == "MIN":
+        n = min(n, 24)
+        cnf = [cl for cl in cnf if all(abs(l) <= n for l in cl)] or [[1, 2, 3]]
+        text = I.cnf_to_csolve(n, cnf, "MIN " + " + ".join("x%d" % i for i in range(1, n + 1)))
+    else:
+        text = I.cnf_to_csolve(n, cnf, obj)
+    m = cb.Model(text)
+    o, _ = util.Oracle(m).solve_tree(0)
+    kw = dict(world=rng.choice([2, 2, 3, 4]), order=rng.randint(0, 4), prefer_failing=rng.random() < 0.3, n_blocks=rng.choice([1, 1, 2]),
+              split_target=rng.choice([1, 8, 32, 128]), slice_clock=rng.choice([0, 2000, 10000, 50000]), general=rng.random() < 0.5)
+    world = kw.pop("world")
+    r, w = util.emu_search_comm(m, world, **kw)
+    if obj == "ANY":
+        ok = r.has_solution == (1 if o.solutions > 0 else 0) and (w is not None) == bool(r.has_solution)
+    else:
+        ok = r.has_solution == o.has_solution and (not o.has_solution or (r.best == o.best and w is not None))
+    if ok and w is not None:
+        val = dict(zip(m.var_names, w))
+        ok = all(any((val["x%d" % abs(l)] == 1) == (l > 0) for l in cl) for cl in cnf)
+        if obj == "MIN":
+            ok = ok and sum(val["x%d" % i] for i in range(1, n + 1)) == r.best
+    return ok, "comm world=%d n=%d %s %s expected %s" % (world, n, obj, kw, (o.solutions, o.best)), r
+
+
 def generic_case(rng, backjump):
     text = gen_random.gen_instance(rng.randint(0, 10**7))
     try:
@@ -167,7 +196,8 @@ def main():
     tot = {"nodes": 0, "conflicts": 0, "backjumps": 0, "cases": 0}
     for s in range(a.seed0, a.seed0 + a.seeds):
         rng = random.Random(s)
-        fn = {"sat": sat_case, "generic": generic_case, "queens": queens_case}.get(a.kind) or (sat_case, generic_case, queens_case)[s % 3]
+        fn = ({"sat": sat_case, "generic": generic_case, "queens": queens_case, "comm": comm_case}.get(a.kind)
+              or (sat_case, generic_case, queens_case, sat_case, comm_case)[s % 5])
         ok, what, r = fn(rng, a.backjump)
         if r is not None:
             tot["cases"] += 1; tot["nodes"] += r.nodes; tot["conflicts"] += r.conflicts; tot["backjumps"] += r.backjumps

@@ -354,3 +354,179 @@ extern "C" int emu_search_batch(const csolve_flat_model *fm, int order, int n_bl
   return search_core(fm, order, 0, 0, n_blocks, 0, general, slice_clock, 0, 0, split_target, 0, 1, 0, n_roots, root_dom,
                      root_solutions, root_failed, res, nullptr);
 }
+
+// ---- several GPUs on one tree (csolve_gpu_comm; ANY / MIN / MAX models) ----------------------------------------------
+// `world` emulated ranks, n_blocks blocks each, run side by side in ONE emulated launch: rank 0 has expanded the root,
+// every rank claims frames of that one frontier (front_ctl->init_next), incumbents / "found" travel through the ranks'
+// CommBlocks (comm_push_best / comm_push_stop / comm_poll), a rank that is running dry asks its peers from its waiting
+// loop (CommBlock::demand) and their busy warps serve its donation ring (donation_target, reserve_slot, publish_slot).
+// Between slices every rank runs k_rebalance (which closes its ring). The host's idle loop (k_comm_state) is not
+// mirrored: a rank without any work stays idle, the others finish the tree.
+namespace {
+struct CommLaunch { std::vector<SearchArgs> a; void (*fn)(const SearchArgs); int n_blocks; int32_t *scratch; int rank_for_rebalance; };
+void run_comm_kernel(void *arg) {
+  const CommLaunch *c = static_cast<const CommLaunch *>(arg);
+  c->fn(c->a[emu::M.cur->block / c->n_blocks]);
+}
+void run_comm_rebalance(void *arg) {
+  const CommLaunch *c = static_cast<const CommLaunch *>(arg);
+  k_rebalance(c->a[c->rank_for_rebalance], c->scratch);
+}
+}  // namespace
+
+extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefer_failing, int n_blocks, int world,
+                               int split_target, long long slice_clock, int general, emu_result *res, int32_t *solution) {
+  CompiledModel cm;
+  int rc = compile_model(*fm, cm, g_err);
+  if (rc != 0) return rc;
+  DevModel m = cm.host;
+  if (general) { m.lov = 0; m.lovk = 0; }
+  if (m.objective == CSOLVE_OBJ_ALL) { g_err = "ALL models are dealt by path hash (emu_search with part_count)"; return -110; }
+  if (world < 1 || world > COMM_MAX_RANKS) { g_err = "bad world"; return -111; }
+  if (prefer_failing && m.lov) prefer_failing = 0;
+  const int V = m.n_vars, fw = m.frame_words, n_warps = n_blocks * WARPS_PER_BLOCK, epoch = 1;
+  memset(res, 0, sizeof(*res));
+  const int ring = 4 * n_warps + 1024;
+  const int target = split_target > 1 ? split_target : 1;
+  const int front_cap = std::max(4 * target, 1024) + ring;
+  std::vector<int32_t> pool_a((size_t)front_cap * fw, 0), pool_b((size_t)front_cap * fw, 0);
+  const int sol_cap = 64;
+
+  struct Rank {
+    SearchCtl ctl; CommBlock blk;
+    std::vector<int32_t> stacks, ring_frames, ready, solbuf;
+    std::vector<WarpState> ws; std::vector<unsigned long long> wcount;
+  };
+  std::vector<Rank> R(world);
+  std::vector<int32_t> gprio(cm.prio.begin(), cm.prio.end());      // per GPU in the product; one here (a heuristic)
+  for (auto &r : R) {
+    memset(&r.ctl, 0, sizeof(r.ctl)); memset(&r.blk, 0, sizeof(r.blk));
+    r.ctl.best = m.objective == CSOLVE_OBJ_MIN ? INT32_MAX : (m.objective == CSOLVE_OBJ_MAX ? INT32_MIN : 0);
+    r.blk.rmin64 = ~0ull; r.blk.rmax64 = 0ull;
+    r.stacks.assign((size_t)n_warps * (V + 1) * fw, 0); r.ring_frames.assign((size_t)ring * fw, 0); r.ready.assign(ring, 0);
+    r.solbuf.assign((size_t)sol_cap * (V + 1), 0);
+    r.ws.assign(n_warps, WarpState{-1, 0, 0, 0u}); r.wcount.assign((size_t)n_warps * CNT_WIDTH, 0);
+  }
+  // rank 0 expands the root (the same loop as search_core's, without batch / sink)
+  int32_t *pin = pool_a.data(), *pout = pool_b.data();
+  {
+    const int rv = root_var(cm, order);
+    int32_t *root = pin;
+    root[FR_VAR] = rv; root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
+    root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
+    root[FR_BEST] = R[0].ctl.best; root[7] = 0x1234567;
+    memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
+    if (m.lovk) memcpy(&root[frame_dom_offset(m.mask_words) + 2 * V], cm.lov_fconst.data(), sizeof(int32_t) * V);
+  }
+  Launch l;
+  memset(&l.a, 0, sizeof(l.a));
+  SearchArgs &a0 = l.a;
+  a0.m = m; a0.ctl = &R[0].ctl; a0.stacks = R[0].stacks.data(); a0.wstate = R[0].ws.data(); a0.wcount = R[0].wcount.data();
+  a0.solbuf = R[0].solbuf.data(); a0.max_solutions = sol_cap; a0.n_warps = n_warps; a0.order = order;
+  a0.out_cap = front_cap; a0.expand_branch_max = 64; a0.part_count = 1; a0.slice_cycles = LLONG_MAX / 2;
+  int n_items = 1;
+  bool stopped = false;
+  {
+    long long max_branch = 1;
+    for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
+    max_branch = std::min<long long>(max_branch, a0.expand_branch_max);
+    l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, true, false, false, false, false)));
+    const size_t smem_x = search_smem_bytes(m, false, false);
+    SearchCtl &ctl = R[0].ctl;
+    for (int lvl = 0; lvl < V && lvl < 24 && n_items > 0 && n_items < target; ++lvl) {
+      const int before = n_items;
+      if ((long long)n_items * max_branch > front_cap - ring) break;
+      a0.items = pin; a0.items_out = pout; a0.frozen_best = ctl.best;
+      ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.passed = 0;
+      emu::launch(std::min(n_blocks, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), THREADS_PER_BLOCK, smem_x, run_kernel, &l);
+      if (ctl.out_dropped > 0) { g_err = "frontier pool overflow during expansion"; return -104; }
+      n_items = ctl.out_count;
+      std::swap(pin, pout);
+      if (ctl.signal == SIG_STOP) { stopped = true; break; }
+      if (ctl.passed == n_items) break;
+      if (n_items >= n_warps / 2 && n_items < 2 * (long long)before) break;
+    }
+  }
+  res->frontier = n_items;
+  // every rank: the shared frontier is rank 0's, the donation ring its own, slot numbers the same everywhere
+  CommLaunch c;
+  c.a.assign(world, a0);
+  c.n_blocks = n_blocks;
+  const bool sat = !general && search_uses_sat(m, false, order);
+  c.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, false, false, sat, false)));
+  std::vector<int32_t> scratch(4 + 3 * n_warps, 0);
+  c.scratch = scratch.data();
+  const int best0 = R[0].ctl.best;
+  for (int r = 0; r < world; r++) {
+    SearchArgs &a = c.a[r];
+    a.ctl = &R[r].ctl; a.stacks = R[r].stacks.data(); a.wstate = R[r].ws.data(); a.wcount = R[r].wcount.data();
+    a.solbuf = R[r].solbuf.data();
+    a.items = pin; a.items_out = nullptr;
+    a.pool_cap = n_items + ring; a.n_initial = n_items;
+    a.pool = R[r].ring_frames.data() - (size_t)n_items * fw;
+    a.ready = R[r].ready.data() - n_items;
+    a.front_pool = pin; a.front_ctl = &R[0].ctl;
+    a.total_warps = n_warps * world;
+    a.comm = &R[r].blk; a.epoch = epoch; a.rank = r; a.world = world; a.n_peers = world - 1;
+    for (int q = 0; q < world; q++) {
+      a.peer_comm[q] = &R[q].blk; a.peer_ctl[q] = &R[q].ctl;
+      a.peer_pool[q] = R[q].ring_frames.data() - (size_t)n_items * fw;
+      a.peer_ready[q] = R[q].ready.data() - n_items;
+    }
+    a.peer_demand = world > 1 ? 1 : 0;
+    a.use_sat = sat ? 1 : 0;
+    a.gprio = prefer_failing ? gprio.data() : nullptr;
+    a.slice_cycles = slice_clock > 0 ? slice_clock : LLONG_MAX / 2;
+    const int keep_stored = r == 0 ? R[0].ctl.n_stored : 0;
+    SearchCtl &ctl = R[r].ctl;
+    if (r != 0) memset(&ctl, 0, sizeof(ctl));
+    ctl.best = best0; ctl.n_stored = keep_stored;
+    ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0;
+    ctl.signal = stopped ? SIG_STOP : SIG_RUN;
+    R[r].blk.busy_epoch = epoch;
+  }
+  const size_t smem = search_smem_bytes(m, false, sat);
+  emu::block_group = n_blocks;
+  for (; !stopped && n_items > 0;) {
+    for (int r = 0; r < world; r++) R[r].blk.ring_open = epoch;
+    emu::launch(n_blocks * world, THREADS_PER_BLOCK, smem, run_comm_kernel, &c);
+    res->switches += emu::M.switches; res->collectives += emu::M.collectives;
+    emu::block_group = 0;
+    bool any_busy = false, any_stop = false;
+    for (int r = 0; r < world; r++) {
+      c.rank_for_rebalance = r;
+      emu::launch(1, 1024, 0, run_comm_rebalance, &c);
+      any_busy |= R[r].ctl.busy != 0;
+      any_stop |= R[r].ctl.signal == SIG_STOP;
+    }
+    emu::block_group = n_blocks;
+    res->slices++;
+    if (any_stop || !any_busy) break;
+    if (res->slices > 100000) { emu::block_group = 0; g_err = "the search does not end"; return -101; }
+  }
+  emu::block_group = 0;
+  // reduce (capi.cu: the ranks' results are added up, the incumbent is the best one, its witness comes from its rank)
+  res->best = best0;
+  int best_rank = -1;
+  for (int r = 0; r < world; r++) {
+    for (int w = 0; w < n_warps; w++) {
+      const unsigned long long *cn = &R[r].wcount[(size_t)w * CNT_WIDTH];
+      res->nodes += cn[CNT_NODES]; res->cuts += cn[CNT_CUTS]; res->solutions += cn[CNT_SOLUTIONS]; res->claims += (int32_t)cn[CNT_CLAIMS];
+      if ((R[r].ws[w].level >= R[r].ws[w].base || R[r].ws[w].claim_mask != 0u) && m.objective != CSOLVE_OBJ_ANY) {
+        g_err = "rank " + std::to_string(r) + " warp " + std::to_string(w) + " left with open frames"; return -100;
+      }
+    }
+    const int b = R[r].ctl.best;
+    if (m.objective == CSOLVE_OBJ_MIN ? b < res->best : (m.objective == CSOLVE_OBJ_MAX ? b > res->best : false)) res->best = b;
+  }
+  res->has_solution = res->solutions > 0;
+  // witness: the stored assignment whose key is the optimum (MIN / MAX), the first stored one (ANY)
+  for (int r = 0; r < world && best_rank < 0; r++) {
+    const int n = std::min(R[r].ctl.n_stored, sol_cap);
+    for (int k = 0; k < n; k++) {
+      const int32_t *row = &R[r].solbuf[(size_t)k * (V + 1)];
+      if (m.objective == CSOLVE_OBJ_ANY || row[V] == res->best) { memcpy(solution, row, sizeof(int32_t) * (V + 1)); best_rank = r; res->n_stored = 1; break; }
+    }
+  }
+  return 0;
+}

@@ -102,6 +102,9 @@ inline void switch_to(Fiber *to) {
 extern int lane_step;
 // Warp schedule: a running warp gives the others a turn after every warp_quantum-th collective (and whenever it waits).
 extern unsigned warp_quantum;
+// block_group > 0: the grid is several kernels running side by side (one per emulated GPU), block_group blocks each;
+// blockIdx counts inside the group, emu::M.cur->block / block_group tells the entry function which kernel it is
+extern int block_group;
 
 // next live lane of the current warp (cyclic, may be the caller itself)
 inline Fiber *next_lane(const Fiber *f) {
@@ -354,7 +357,8 @@ inline void launch(int grid, int block, size_t smem_bytes, void (*entry)(void *)
   }
   for (int i = 0; i < n; i++) {
     Fiber &f = M.fibers[i];
-    f.block = i / block; f.tid = uint3{(unsigned)(i % block), 0, 0}; f.bid = uint3{(unsigned)f.block, 0, 0};
+    f.block = i / block; f.tid = uint3{(unsigned)(i % block), 0, 0};
+    f.bid = uint3{(unsigned)(block_group > 0 ? f.block % block_group : f.block), 0, 0};
     f.warp = i / 32; f.lane = i % 32;
     f.stack = stacks + STACK * i;
     // initial frame for emu_switch: six callee-saved registers, then the return address; the entry point finds the
@@ -378,7 +382,7 @@ inline void launch(int grid, int block, size_t smem_bytes, void (*entry)(void *)
 }  // namespace emu
 
 #ifdef EMU_DEFINE_MACHINE
-namespace emu { Machine M; int lane_step = 1; unsigned warp_quantum = 64; }
+namespace emu { Machine M; int lane_step = 1; unsigned warp_quantum = 64; int block_group = 0; }
 asm(R"(
 .text
 .globl emu_switch

@@ -201,6 +201,42 @@ def test_results_do_not_depend_on_the_lane_schedule():
         util.emu_set_lane_step(1)
 
 
+def test_several_gpus_on_one_tree():
+    """csolve_gpu_comm for ANY / MIN / MAX models, 2 and 3 emulated ranks side by side in one launch: one root frontier on
+    rank 0 claimed by everybody (system-scope atomics on front_ctl), incumbents and "found" through the CommBlocks
+    (comm_push_best / comm_push_stop / comm_poll), a rank running dry asks its peers from its waiting loop and their busy
+    warps serve its donation ring; k_rebalance between the slices. Optimum and witness, status and model are the
+    oracle's; an unsatisfiable instance in static order is the same tree whatever the number of ranks."""
+    for n, ratio, seed in ((20, 3.2, 12), (24, 3.5, 13), (26, 3.6, 14)):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        m = cb.Model(I.cnf_to_csolve(n, cnf, "MIN " + " + ".join("x%d" % i for i in range(1, n + 1))))
+        o, _ = util.Oracle(m).solve_tree(0)
+        for world in (1, 2, 3):
+            r, w = util.emu_search_comm(m, world, split_target=16, slice_clock=5000)
+            assert r.best == o.best and w is not None and satisfies(cnf, m.var_names, w)
+            assert sum(v for k, v in zip(m.var_names, w) if k.startswith("x")) == r.best
+    for world in (2, 3):
+        r, _ = util.emu_search_comm(cb.Model(I.schedule()), world, split_target=16, slice_clock=20000)
+        assert r.best == 11
+    nodes = set()
+    cnf = I.random_3sat_cnf(60, 4.7, 11)
+    m = cb.Model(I.cnf_to_csolve(60, cnf))
+    assert tree(m)[0] == 0
+    for world in (1, 2, 3):
+        for general in (False, True):
+            r, w = util.emu_search_comm(m, world, split_target=32, slice_clock=10000, general=general)
+            assert r.has_solution == 0 and w is None
+            nodes.add((r.nodes, r.cuts))
+    assert len(nodes) == 1 and nodes.pop() == tree(m)[1:]
+    for n, ratio, seed in ((50, 4.6, 4), (60, 4.26, 3)):
+        cnf = I.random_3sat_cnf(n, ratio, seed)
+        m = cb.Model(I.cnf_to_csolve(n, cnf))
+        for world in (2, 3):
+            for general, pf in ((False, False), (True, True)):
+                r, w = util.emu_search_comm(m, world, split_target=32, slice_clock=10000, general=general, prefer_failing=pf)
+                assert r.has_solution == 1 and satisfies(cnf, m.var_names, w)
+
+
 def test_luby_restarts():
     """-r on ANY models (src/csolve.c:76-83, 264-276): the warps report their failed nodes, the slice ends at the Luby
     threshold, the host drops every frame and expands the root again in the order of the priorities learned so far
