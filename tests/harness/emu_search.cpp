@@ -530,3 +530,38 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
   }
   return 0;
 }
+
+// ---- csolve_gpu_propagate_batch: n independent node transitions (the parity hook) ------------------------------------
+namespace {
+struct PropLaunch { DevModel m; int n; const int32_t *dom_in, *var, *val, *best; int32_t *dom_out; uint8_t *failed; };
+void run_propagate_batch(void *arg) {
+  const PropLaunch *q = static_cast<const PropLaunch *>(arg);
+  if (q->m.lovk) {
+    switch (q->m.lovk) {
+    case 2: k_propagate_batch_lovk<2>(q->m, q->n, q->dom_in, q->var, q->val, q->dom_out, q->failed); break;
+    case 3: k_propagate_batch_lovk<3>(q->m, q->n, q->dom_in, q->var, q->val, q->dom_out, q->failed); break;
+    default: k_propagate_batch_lovk<4>(q->m, q->n, q->dom_in, q->var, q->val, q->dom_out, q->failed); break;
+    }
+  } else if (q->m.lov) {
+    k_propagate_batch_lov(q->m, q->n, q->dom_in, q->var, q->val, q->dom_out, q->failed);
+  } else {
+    k_propagate_batch(q->m, q->n, q->dom_in, q->var, q->val, q->best, q->dom_out, q->failed);
+  }
+}
+}  // namespace
+
+// general: 1 = the general kernel whatever the model; best may be NULL (zeros, as capi.cu passes)
+extern "C" int emu_propagate_batch(const csolve_flat_model *fm, int general, int n_blocks, int n, const int32_t *dom_in,
+                                   const int32_t *var, const int32_t *val, const int32_t *best, int32_t *dom_out, uint8_t *failed) {
+  CompiledModel cm;
+  int rc = compile_model(*fm, cm, g_err);
+  if (rc != 0) return rc;
+  DevModel m = cm.host;
+  if (general) { m.lov = 0; m.lovk = 0; }
+  std::vector<int32_t> zero_best;
+  if (best == nullptr) { zero_best.assign(n, 0); best = zero_best.data(); }
+  PropLaunch q{m, n, dom_in, var, val, best, dom_out, failed};
+  const int grid = std::max(1, std::min((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, n_blocks));
+  emu::launch(grid, THREADS_PER_BLOCK, m.lovk ? 0 : search_smem_bytes(m, false), run_propagate_batch, &q);
+  return 0;
+}

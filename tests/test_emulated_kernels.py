@@ -237,6 +237,31 @@ def test_several_gpus_on_one_tree():
                 assert r.has_solution == 1 and satisfies(cnf, m.var_names, w)
 
 
+def test_reference_node_transitions_through_the_emulated_kernels():
+    """csolve_gpu_propagate_batch (k_propagate_batch / _lov / _lovk): the 25 k node transitions replayed through the COMPILED
+    REFERENCE (tests/golden/replay_*.npz, the fixtures of the device test) -- bit-exact fail flags and post-fixpoint
+    domains, on the kernel the product picks and on the general one"""
+    import glob
+    import os
+    from make_instances import instance_table
+    inst = instance_table()
+    n = 0
+    for path in sorted(glob.glob(os.path.join(util.GOLDEN, "replay_*.npz"))):
+        name = os.path.basename(path)[7:-4]
+        if name == "random":
+            continue
+        z = np.load(path)
+        g = {k: z[k] for k in z.files}
+        m = cb.Model(inst[name])
+        for general in (False, True):
+            out, failed = util.emu_propagate_batch(m, g["dom_in"], g["var"], g["val"], g["best"], general=general)
+            assert np.array_equal(failed.astype(bool), g["failed"].astype(bool)), (name, general)
+            ok = ~g["failed"].astype(bool)
+            assert np.array_equal(out[ok], g["dom_out"][ok]), (name, general)
+        n += len(g["var"])
+    assert n > 20000
+
+
 def test_luby_restarts():
     """-r on ANY models (src/csolve.c:76-83, 264-276): the warps report their failed nodes, the slice ends at the Luby
     threshold, the host drops every frame and expands the root again in the order of the priorities learned so far

@@ -412,3 +412,23 @@ def emu_search_comm(model, world, order=0, prefer_failing=False, n_blocks=1, spl
     if rc != 0:
         raise RuntimeError("emu_search_comm: %d %s" % (rc, lib.emu_error().decode()))
     return res, (buf[:model.n_vars].tolist() if res.n_stored else None)
+
+
+def emu_propagate_batch(model, dom_in, var, val, best=None, general=False, n_blocks=4):
+    """csolve_gpu_propagate_batch on the emulated kernels (k_propagate_batch / _lov / _lovk): -> (dom_out [n, 2V], failed [n])"""
+    lib = emu_lib(False)
+    U8P = C.POINTER(C.c_uint8)
+    lib.emu_propagate_batch.argtypes = [C.POINTER(type(model.flat)), C.c_int, C.c_int, C.c_int, I32P, I32P, I32P, I32P, I32P, U8P]
+    dom_in = np.ascontiguousarray(dom_in, np.int32).reshape(-1, 2 * model.n_vars)
+    n = dom_in.shape[0]
+    var = np.ascontiguousarray(var, np.int32)
+    val = np.ascontiguousarray(val, np.int32)
+    bestp = None if best is None else np.ascontiguousarray(best, np.int32)
+    out = np.zeros_like(dom_in)
+    failed = np.zeros(n, np.uint8)
+    rc = lib.emu_propagate_batch(C.byref(model.flat), 1 if general else 0, n_blocks, n, dom_in.ctypes.data_as(I32P), var.ctypes.data_as(I32P),
+                                 val.ctypes.data_as(I32P), None if bestp is None else bestp.ctypes.data_as(I32P),
+                                 out.ctypes.data_as(I32P), failed.ctypes.data_as(U8P))
+    if rc != 0:
+        raise RuntimeError("emu_propagate_batch: %d %s" % (rc, lib.emu_error().decode()))
+    return out, failed
