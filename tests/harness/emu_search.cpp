@@ -55,6 +55,11 @@ void run_root_frames(void *arg) {
   default: k_root_frames_lovk<4>(b->m, b->n_roots, b->root_dom, b->order, b->frames, b->cap, b->n_out, b->failed); break;
   }
 }
+struct ReduceLaunch { const unsigned long long *wcount; int n_warps; unsigned long long *out; };
+void run_reduce(void *arg) {
+  const ReduceLaunch *r = static_cast<const ReduceLaunch *>(arg);
+  k_reduce_counters(r->wcount, r->n_warps, r->out);
+}
 void run_rebalance(void *arg) {
   const Launch *l = static_cast<const Launch *>(arg);
   k_rebalance(l->a, l->scratch);
@@ -308,6 +313,17 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
               ", signal " + std::to_string(ctl.signal) + " hungry " + std::to_string(ctl.hungry) + " tickets " + std::to_string(ctl.item_next) + "/" + std::to_string(ctl.item_count);
       return -100;
     }   // ANY: the first solution stops everybody
+  }
+  {
+    // the device's own reduction of the per-warp counters (k_reduce_counters, what capi.cu reads) against the sums above
+    static ReduceLaunch rl;
+    std::vector<unsigned long long> totals(CNT_WIDTH, 0);
+    rl = ReduceLaunch{wcount.data(), n_warps, totals.data()};
+    const int grid = (int)std::min<size_t>(32, ((size_t)n_warps * CNT_WIDTH + REDUCE_THREADS - 1) / REDUCE_THREADS);
+    emu::launch(std::max(grid, 1), 1024, 0, run_reduce, &rl);
+    if (totals[CNT_NODES] != res->nodes || totals[CNT_CUTS] != res->cuts || totals[CNT_SOLUTIONS] != res->solutions || totals[CNT_PROPS] != res->props) {
+      g_err = "k_reduce_counters disagrees with the per-warp counters"; return -120;
+    }
   }
   if (batch) for (int r = 0; r < n_roots; r++) root_solutions[r] = rsol[r];
   if (sample) { g_sample_seen = sample_n; g_samples.resize((size_t)std::min(sample_n, sample_cap) * sample_words(V)); }
