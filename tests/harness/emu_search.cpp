@@ -69,6 +69,7 @@ std::string g_err;
 std::vector<int32_t> g_samples;      // records of the last search with sample_mod > 0 (sample_words(V) words each)
 int g_sample_seen = 0;
 unsigned g_sample_mod = 0, g_sample_fkeep = 1;
+int32_t g_fill = 0;                  // what the workspace holds before a search (cudaMalloc'ed memory is not zeroed either)
 std::vector<int32_t> g_ng_flat;      // nogoods of the last learning search: len, literals (var << 1 | value), len, ...
 
 }  // namespace
@@ -82,6 +83,8 @@ struct emu_result {
 
 extern "C" const char *emu_error() { return g_err.c_str(); }
 // lane schedule of the emulator (simt_emu.h): an odd stride, 1 = ascending lanes, 31 = descending
+// the pattern stacks / pools / solution buffers are filled with before a search (default 0)
+extern "C" void emu_set_workspace_fill(int32_t v) { g_fill = v; }
 extern "C" void emu_set_lane_step(int step) { emu::lane_step = (step & 31) | 1; }
 // warp schedule: collectives a warp completes before the other warps get their turn (default 64)
 extern "C" void emu_set_warp_quantum(int q) { emu::warp_quantum = q > 0 ? (unsigned)q : 64u; }
@@ -142,13 +145,15 @@ static int search_core(const csolve_flat_model *fm, int order, int learn, int pr
   const int ring = 4 * n_warps + 1024;   // ring_min_frames of capi.cu
   const int target = split_target > 1 ? split_target : 1;
   const int pool_cap = std::max(std::max(4 * target, 1024), 2 * n_roots) + ring;
-  std::vector<int32_t> pool((size_t)pool_cap * fw, 0), pool_b((size_t)pool_cap * fw, 0), ready(pool_cap, 0), stacks((size_t)n_warps * (V + 1) * fw, 0);
+  // stacks, pools and the solution buffer start with whatever the workspace held (g_fill); capi.cu clears only the ready
+  // flags, the per-warp state and the counters
+  std::vector<int32_t> pool((size_t)pool_cap * fw, g_fill), pool_b((size_t)pool_cap * fw, g_fill), ready(pool_cap, 0), stacks((size_t)n_warps * (V + 1) * fw, g_fill);
   std::vector<WarpState> ws(n_warps, WarpState{-1, 0, 0, 0u});
   std::vector<unsigned long long> wcount((size_t)n_warps * CNT_WIDTH, 0);
   const bool sinking = sink_headroom > 0 && m.objective == CSOLVE_OBJ_ALL;
   const int sol_cap = sinking ? 4 * sink_headroom : max_solutions > 0 ? max_solutions : (m.obj_var >= 0 ? 16 : 1);
   long long sunk = 0;
-  std::vector<int32_t> solbuf((size_t)sol_cap * (V + 1), 0);
+  std::vector<int32_t> solbuf((size_t)sol_cap * (V + 1), g_fill);
   auto upload_root_frame = [&](int rv) {
   int32_t *root = pool.data();
   std::fill(root, root + fw, 0);
@@ -405,7 +410,7 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
   const int ring = 4 * n_warps + 1024;
   const int target = split_target > 1 ? split_target : 1;
   const int front_cap = std::max(4 * target, 1024) + ring;
-  std::vector<int32_t> pool_a((size_t)front_cap * fw, 0), pool_b((size_t)front_cap * fw, 0);
+  std::vector<int32_t> pool_a((size_t)front_cap * fw, g_fill), pool_b((size_t)front_cap * fw, g_fill);
   const int sol_cap = 64;
 
   struct Rank {
@@ -419,8 +424,8 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
     memset(&r.ctl, 0, sizeof(r.ctl)); memset(&r.blk, 0, sizeof(r.blk));
     r.ctl.best = m.objective == CSOLVE_OBJ_MIN ? INT32_MAX : (m.objective == CSOLVE_OBJ_MAX ? INT32_MIN : 0);
     r.blk.rmin64 = ~0ull; r.blk.rmax64 = 0ull;
-    r.stacks.assign((size_t)n_warps * (V + 1) * fw, 0); r.ring_frames.assign((size_t)ring * fw, 0); r.ready.assign(ring, 0);
-    r.solbuf.assign((size_t)sol_cap * (V + 1), 0);
+    r.stacks.assign((size_t)n_warps * (V + 1) * fw, g_fill); r.ring_frames.assign((size_t)ring * fw, g_fill); r.ready.assign(ring, 0);
+    r.solbuf.assign((size_t)sol_cap * (V + 1), g_fill);
     r.ws.assign(n_warps, WarpState{-1, 0, 0, 0u}); r.wcount.assign((size_t)n_warps * CNT_WIDTH, 0);
   }
   // rank 0 expands the root (the same loop as search_core's, without batch / sink)
@@ -428,6 +433,7 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
   {
     const int rv = root_var(cm, order);
     int32_t *root = pin;
+    std::fill(root, root + fw, 0);
     root[FR_VAR] = rv; root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
     root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]);
     root[FR_BEST] = R[0].ctl.best; root[7] = 0x1234567;

@@ -312,6 +312,8 @@ def emu_lib(backjump=False):
         assert lib.emu_backjump_build() == (1 if backjump else 0)
         lib.emu_set_lane_step(int(os.environ.get("EMU_LANE_STEP", "1")))     # the emulator's lane schedule (simt_emu.h)
         lib.emu_set_warp_quantum(int(os.environ.get("EMU_WARP_QUANTUM", "64")))   # ... and its warp schedule
+        lib.emu_set_workspace_fill.argtypes = [C.c_int32]
+        lib.emu_set_workspace_fill(int(os.environ.get("EMU_WORKSPACE_FILL", "0"), 0))  # what stacks / pools hold before a search
         _emu[backjump] = lib
     return _emu[backjump]
 
