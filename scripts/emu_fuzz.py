@@ -23,6 +23,11 @@ def ranks_search(m, kw, rng):
     counters add up (the expansion is reported by rank 0)"""
     world = rng.choice([1, 1, 2, 3])
     kw = dict(kw, split_target=rng.choice([1, 1, 8, 64, 500]))
+    if world > 1 and rng.random() < 0.4 and not kw.get("sink_headroom"):
+        # ... with frames shipped from the busiest rank to ranks that ran dry at the slice boundaries
+        r, moved = util.emu_search_exchange(m, world, order=kw["order"], n_blocks=kw["n_blocks"], split_target=max(kw["split_target"], 2),
+                                            slice_clock=kw["slice_clock"] or 5000, general=kw["general"])
+        return r, [], dict(kw, world=world, exchange=moved)
     tot = None
     for rank in range(world):
         r, sols = util.emu_search(m, part_rank=rank, part_count=world, **kw)

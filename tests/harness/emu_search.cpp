@@ -587,3 +587,139 @@ extern "C" int emu_propagate_batch(const csolve_flat_model *fm, int general, int
   emu::launch(grid, THREADS_PER_BLOCK, m.lovk ? 0 : search_smem_bytes(m, false), run_propagate_batch, &q);
   return 0;
 }
+
+// ---- frames shipped between ranks at the slice boundaries (csolve_gpu_set_rebalance + csolve_gpu_export_frames /
+//      csolve_gpu_import_frames: the per-slice rank hooks of round 1) ----------------------------------------------
+// `world` ranks search their path-hash shares of an ALL model's tree slice by slice; after every round a rank that ran
+// dry receives frames that k_export_frames split off the parked stacks of the busiest rank, k_import_frames puts them
+// into its donation ring as tickets served ahead of their holders (csolve_b200/distributed.py: make_rebalance).
+namespace {
+struct XferLaunch { const SearchArgs *a; int32_t *buf; int max_frames; int32_t *n_out; int n_frames; };
+void run_export(void *arg) { const XferLaunch *x = static_cast<const XferLaunch *>(arg); k_export_frames(*x->a, x->buf, x->max_frames, x->n_out); }
+void run_import(void *arg) { const XferLaunch *x = static_cast<const XferLaunch *>(arg); k_import_frames(*x->a, x->buf, x->n_frames); }
+}  // namespace
+
+extern "C" int emu_search_exchange(const csolve_flat_model *fm, int order, int n_blocks, int world, int split_target,
+                                   long long slice_clock, int general, emu_result *res, int32_t *frames_moved) {
+  CompiledModel cm;
+  int rc = compile_model(*fm, cm, g_err);
+  if (rc != 0) return rc;
+  DevModel m = cm.host;
+  if (general) { m.lov = 0; m.lovk = 0; }
+  if (m.objective != CSOLVE_OBJ_ALL) { g_err = "ALL models only"; return -110; }
+  const int V = m.n_vars, fw = m.frame_words, n_warps = n_blocks * WARPS_PER_BLOCK;
+  memset(res, 0, sizeof(*res));
+  *frames_moved = 0;
+  const int ring = 4 * n_warps + 1024;
+  const int target = split_target > 1 ? split_target : 1;
+  const int pool_cap = std::max(4 * target, 1024) + ring;
+  struct Rank {
+    SearchCtl ctl;
+    std::vector<int32_t> stacks, pool, ready, solbuf, scratch;
+    std::vector<WarpState> ws; std::vector<unsigned long long> wcount;
+    SearchArgs a;
+  };
+  std::vector<Rank> R(world);
+  std::vector<int32_t> pool_b((size_t)pool_cap * fw, g_fill);
+  for (auto &r : R) {
+    memset(&r.ctl, 0, sizeof(r.ctl));
+    r.stacks.assign((size_t)n_warps * (V + 1) * fw, g_fill); r.pool.assign((size_t)pool_cap * fw, g_fill); r.ready.assign(pool_cap, 0);
+    r.solbuf.assign(V + 1, 0); r.scratch.assign(4 + 3 * n_warps, 0);
+    r.ws.assign(n_warps, WarpState{-1, 0, 0, 0u}); r.wcount.assign((size_t)n_warps * CNT_WIDTH, 0);
+  }
+  // rank 0 expands the root; every rank holds a copy of the frontier (the expansion is replicated in the product)
+  Launch l;
+  SearchArgs &a0 = l.a;
+  memset(&a0, 0, sizeof(a0));
+  int32_t *pin = R[0].pool.data(), *pout = pool_b.data();
+  {
+    const int rv = root_var(cm, order);
+    int32_t *root = pin;
+    std::fill(root, root + fw, 0);
+    root[FR_VAR] = rv; root[FR_LO] = cm.root_dom[2 * rv]; root[FR_HI] = cm.root_dom[2 * rv + 1];
+    root[FR_LAST] = (int32_t)((uint32_t)root[FR_HI] - (uint32_t)root[FR_LO]); root[7] = 0x1234567;
+    memcpy(&root[frame_dom_offset(m.mask_words)], cm.root_dom.data(), sizeof(int32_t) * 2 * V);
+    if (m.lovk) memcpy(&root[frame_dom_offset(m.mask_words) + 2 * V], cm.lov_fconst.data(), sizeof(int32_t) * V);
+  }
+  a0.m = m; a0.ctl = &R[0].ctl; a0.stacks = R[0].stacks.data(); a0.wstate = R[0].ws.data(); a0.wcount = R[0].wcount.data();
+  a0.solbuf = R[0].solbuf.data(); a0.max_solutions = 1; a0.n_warps = n_warps; a0.order = order;
+  a0.out_cap = pool_cap; a0.expand_branch_max = 64; a0.part_count = 1; a0.slice_cycles = LLONG_MAX / 2;
+  int n_items = 1;
+  {
+    long long max_branch = 1;
+    for (int v = 0; v < V; v++) max_branch = std::max<long long>(max_branch, (long long)cm.root_dom[2 * v + 1] - cm.root_dom[2 * v] + 1);
+    max_branch = std::min<long long>(max_branch, a0.expand_branch_max);
+    l.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, true, false, false, false, false)));
+    const size_t smem_x = search_smem_bytes(m, false, false);
+    SearchCtl &ctl = R[0].ctl;
+    for (int lvl = 0; lvl < V && lvl < 24 && n_items > 0 && n_items < target; ++lvl) {
+      const int before = n_items;
+      if ((long long)n_items * max_branch > pool_cap - ring) break;
+      a0.items = pin; a0.items_out = pout;
+      ctl.item_next = 0; ctl.item_count = n_items; ctl.out_count = 0; ctl.passed = 0;
+      emu::launch(std::min(n_blocks, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), THREADS_PER_BLOCK, smem_x, run_kernel, &l);
+      if (ctl.out_dropped > 0) { g_err = "frontier pool overflow during expansion"; return -104; }
+      n_items = ctl.out_count;
+      std::swap(pin, pout);
+      if (ctl.passed == n_items) break;
+      if (n_items >= n_warps / 2 && n_items < 2 * (long long)before) break;
+    }
+  }
+  if (pin != R[0].pool.data()) std::copy(pin, pin + (size_t)n_items * fw, R[0].pool.data());
+  const bool sat = !general && search_uses_sat(m, false, order);
+  void (*const fn_dfs)(const SearchArgs) = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, false, false, sat, false)));
+  for (int r = 0; r < world; r++) {
+    if (r != 0) std::copy(R[0].pool.begin(), R[0].pool.begin() + (size_t)n_items * fw, R[r].pool.begin());
+    SearchArgs &a = R[r].a;
+    a = a0;
+    a.ctl = &R[r].ctl; a.stacks = R[r].stacks.data(); a.wstate = R[r].ws.data(); a.wcount = R[r].wcount.data(); a.solbuf = R[r].solbuf.data();
+    a.items = R[r].pool.data(); a.items_out = nullptr; a.pool = R[r].pool.data(); a.pool_cap = pool_cap; a.ready = R[r].ready.data();
+    a.n_initial = n_items; a.front_pool = R[r].pool.data(); a.front_ctl = &R[r].ctl; a.total_warps = n_warps;
+    a.part_rank = r; a.part_count = world; a.use_sat = sat ? 1 : 0;
+    a.slice_cycles = slice_clock > 0 ? slice_clock : LLONG_MAX / 2;
+    SearchCtl &ctl = R[r].ctl;
+    const int keep = r == 0 ? 1 : 0;
+    if (!keep) { memset(&ctl, 0, sizeof(ctl)); }
+    ctl.item_next = 0; ctl.item_count = 0; ctl.init_next = 0; ctl.busy = 0; ctl.hungry = 0; ctl.signal = SIG_RUN;
+  }
+  const size_t smem = search_smem_bytes(m, false, sat);
+  std::vector<int> busy(world, 1);
+  std::vector<int32_t> xbuf;
+  for (int round = 0; n_items > 0; round++) {
+    for (int r = 0; r < world; r++) {
+      if (!busy[r]) continue;
+      l.a = R[r].a; l.fn = fn_dfs; l.scratch = R[r].scratch.data();
+      emu::launch(n_blocks, THREADS_PER_BLOCK, smem, run_kernel, &l);
+      emu::launch(1, 1024, 0, run_rebalance, &l);
+      busy[r] = R[r].ctl.busy;
+      res->slices++;
+    }
+    int donor = -1;
+    for (int r = 0; r < world; r++) if (busy[r] > 0 && (donor < 0 || busy[r] > busy[donor])) donor = r;
+    if (donor < 0) break;
+    // ranks that ran dry get frames of the busiest rank (at most a quarter of their warps each)
+    for (int r = 0; r < world; r++) {
+      if (busy[r] != 0 || r == donor) continue;
+      const int want = std::max(1, n_warps / 4);
+      xbuf.assign((size_t)want * fw, 0);
+      int32_t n_out = 0;
+      XferLaunch x{&R[donor].a, xbuf.data(), want, &n_out, 0};
+      emu::launch(1, 1024, 0, run_export, &x);
+      if (n_out <= 0) continue;
+      x.a = &R[r].a; x.n_frames = n_out;
+      emu::launch(1, 1024, 0, run_import, &x);
+      *frames_moved += n_out;
+      busy[r] = 1;
+    }
+    if (round > 100000) { g_err = "the search does not end"; return -101; }
+  }
+  for (int r = 0; r < world; r++)
+    for (int w = 0; w < n_warps; w++) {
+      const unsigned long long *cn = &R[r].wcount[(size_t)w * CNT_WIDTH];
+      res->nodes += cn[CNT_NODES]; res->cuts += cn[CNT_CUTS]; res->solutions += cn[CNT_SOLUTIONS]; res->claims += (int32_t)cn[CNT_CLAIMS];
+      if (R[r].ws[w].level >= R[r].ws[w].base || R[r].ws[w].claim_mask != 0u) { g_err = "a warp left with open frames"; return -100; }
+    }
+  res->has_solution = res->solutions > 0;
+  res->frontier = n_items;
+  return 0;
+}

@@ -262,6 +262,22 @@ def test_reference_node_transitions_through_the_emulated_kernels():
     assert n > 20000
 
 
+def test_frames_shipped_between_ranks_at_the_slice_boundaries():
+    """csolve_gpu_set_rebalance + csolve_gpu_export_frames / _import_frames: ranks search their path-hash shares slice by
+    slice, a rank that ran dry gets frames k_export_frames split off the busiest rank's parked stacks, k_import_frames
+    puts them into its ring as served tickets -- nothing lost, nothing searched twice: the counters are the tree's"""
+    moved = 0
+    for text in (I.queens(8), I.queens(9), I.random_3sat(30, 3.6, 21, "ALL")):
+        m = cb.Model(text)
+        want = tree(m)
+        for general in (False, True):
+            for world, split, slice_clock in ((2, 8, 3000), (3, 64, 5000), (4, 16, 2000)):
+                r, n = util.emu_search_exchange(m, world, split_target=split, slice_clock=slice_clock, general=general)
+                assert counters(r) == want, (text[:12], general, world)
+                moved += n
+    assert moved > 50
+
+
 def test_luby_restarts():
     """-r on ANY models (src/csolve.c:76-83, 264-276): the warps report their failed nodes, the slice ends at the Luby
     threshold, the host drops every frame and expands the root again in the order of the priorities learned so far

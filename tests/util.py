@@ -434,3 +434,18 @@ def emu_propagate_batch(model, dom_in, var, val, best=None, general=False, n_blo
     if rc != 0:
         raise RuntimeError("emu_propagate_batch: %d %s" % (rc, lib.emu_error().decode()))
     return out, failed
+
+
+def emu_search_exchange(model, world, order=0, n_blocks=1, split_target=64, slice_clock=5000, general=True):
+    """ALL model searched by `world` emulated ranks (path-hash shares) with frames shipped from the busiest rank to ranks
+    that ran dry at the slice boundaries (k_export_frames / k_import_frames) -> (EmuResult of the whole job, frames moved)"""
+    lib = emu_lib(False)
+    lib.emu_search_exchange.argtypes = [C.POINTER(type(model.flat)), C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int,
+                                        C.POINTER(EmuResult), I32P]
+    res = EmuResult()
+    moved = C.c_int32(0)
+    rc = lib.emu_search_exchange(C.byref(model.flat), order, n_blocks, world, int(split_target), int(slice_clock), 1 if general else 0,
+                                 C.byref(res), C.byref(moved))
+    if rc != 0:
+        raise RuntimeError("emu_search_exchange: %d %s" % (rc, lib.emu_error().decode()))
+    return res, moved.value
