@@ -381,13 +381,23 @@ extern "C" int emu_search_batch(const csolve_flat_model *fm, int order, int n_bl
 // every rank claims frames of that one frontier (front_ctl->init_next), incumbents / "found" travel through the ranks'
 // CommBlocks (comm_push_best / comm_push_stop / comm_poll), a rank that is running dry asks its peers from its waiting
 // loop (CommBlock::demand) and their busy warps serve its donation ring (donation_target, reserve_slot, publish_slot).
-// Between slices every rank runs k_rebalance (which closes its ring). The host's idle loop (k_comm_state) is not
-// mirrored: a rank without any work stays idle, the others finish the tree.
+// Between slices every rank that searched runs k_rebalance (which closes its ring); a rank that ran dry does what the
+// host's idle loop does (capi.cu): k_comm_state clears its busy mark in rank 0's count of active ranks, leaves its ring
+// open and raises its demand with the peers -- whose warps serve it during the next launch -- until frames have arrived
+// (it joins the next launch) or no rank is active any more (the search is over everywhere).
 namespace {
-struct CommLaunch { std::vector<SearchArgs> a; void (*fn)(const SearchArgs); int n_blocks; int32_t *scratch; int rank_for_rebalance; };
+struct CommLaunch {
+  std::vector<SearchArgs> a; void (*fn)(const SearchArgs); int n_blocks; int32_t *scratch; int rank_for_rebalance;
+  std::vector<int> active;          // the ranks whose search kernels run side by side in this launch
+  int want_frames; int32_t *state_out;
+};
 void run_comm_kernel(void *arg) {
   const CommLaunch *c = static_cast<const CommLaunch *>(arg);
-  c->fn(c->a[emu::M.cur->block / c->n_blocks]);
+  c->fn(c->a[c->active[emu::M.cur->block / c->n_blocks]]);
+}
+void run_comm_state(void *arg) {
+  const CommLaunch *c = static_cast<const CommLaunch *>(arg);
+  k_comm_state(c->a[c->rank_for_rebalance], c->want_frames, 0, c->state_out);
 }
 void run_comm_rebalance(void *arg) {
   const CommLaunch *c = static_cast<const CommLaunch *>(arg);
@@ -508,25 +518,49 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
     R[r].blk.busy_epoch = epoch;
   }
   const size_t smem = search_smem_bytes(m, false, sat);
-  emu::block_group = n_blocks;
+  R[0].blk.active64 = ((unsigned long long)(unsigned)epoch << 32) | (unsigned)world;      // capi.cu: publish_epoch
+  std::vector<int> has_work(world, 1);
+  int32_t state[4] = {0, 0, 0, 0};
+  c.state_out = state;
+  c.want_frames = world > 1 ? std::max(n_warps / (4 * (world - 1)), 32) : 0;
   for (; !stopped && n_items > 0;) {
-    for (int r = 0; r < world; r++) R[r].blk.ring_open = epoch;
-    emu::launch(n_blocks * world, THREADS_PER_BLOCK, smem, run_comm_kernel, &c);
+    c.active.clear();
+    for (int r = 0; r < world; r++) if (has_work[r]) { c.active.push_back(r); R[r].blk.ring_open = epoch; }
+    if (c.active.empty()) break;
+    emu::block_group = n_blocks;
+    emu::launch(n_blocks * (int)c.active.size(), THREADS_PER_BLOCK, smem, run_comm_kernel, &c);
     res->switches += emu::M.switches; res->collectives += emu::M.collectives;
     emu::block_group = 0;
-    bool any_busy = false, any_stop = false;
-    for (int r = 0; r < world; r++) {
+    bool any_stop = false;
+    for (int r : c.active) {
       c.rank_for_rebalance = r;
       emu::launch(1, 1024, 0, run_comm_rebalance, &c);
-      any_busy |= R[r].ctl.busy != 0;
+      has_work[r] = R[r].ctl.busy != 0;
       any_stop |= R[r].ctl.signal == SIG_STOP;
     }
-    emu::block_group = n_blocks;
     res->slices++;
-    if (any_stop || !any_busy) break;
-    if (res->slices > 100000) { emu::block_group = 0; g_err = "the search does not end"; return -101; }
+    if (any_stop) break;
+    // the ranks without work: the host's idle loop, one look each
+    int active_ranks = -1;
+    bool peer_found = false;
+    for (int r = 0; r < world && world > 1; r++) {
+      if (has_work[r]) continue;
+      c.rank_for_rebalance = r;
+      emu::launch(1, 1, 0, run_comm_state, &c);
+      if (state[2]) peer_found = true;
+      if (state[0]) has_work[r] = 1;
+      active_ranks = state[1];
+      if (state[1] < 0) { g_err = "comm: the ranks are out of step"; return -112; }
+    }
+    if (peer_found) break;
+    bool any = false;
+    for (int r = 0; r < world; r++) any |= has_work[r] != 0;
+    if (!any) {
+      if (world > 1 && active_ranks != 0) { g_err = "every rank is idle but rank 0 counts " + std::to_string(active_ranks) + " active ranks"; return -113; }
+      break;
+    }
+    if (res->slices > 100000) { g_err = "the search does not end"; return -101; }
   }
-  emu::block_group = 0;
   // reduce (capi.cu: the ranks' results are added up, the incumbent is the best one, its witness comes from its rank)
   res->best = best0;
   int best_rank = -1;

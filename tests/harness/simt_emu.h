@@ -343,8 +343,10 @@ namespace emu {
 inline void launch(int grid, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
   const size_t STACK = 512 * 1024;
   const int n = grid * block;
+  if (block % 32 != 0 && grid != 1) { fprintf(stderr, "[emu] a block that is not a multiple of 32 threads needs grid 1\n"); abort(); }
+  const int n_slots = (n + 31) / 32 * 32;          // lanes that do not exist are fibers that are done from the start
   M = Machine();
-  M.fibers.resize(n); M.warps.resize(n / 32); M.blocks.resize(grid);
+  M.fibers.resize(n_slots); M.warps.resize(n_slots / 32); M.blocks.resize(grid);
   M.block_dim = dim3(block, 1, 1); M.grid_dim = dim3(grid, 1, 1);
   M.entry = entry; M.entry_arg = arg; M.live = n;
   char *stacks = (char *)mmap(nullptr, STACK * n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
@@ -370,6 +372,7 @@ inline void launch(int grid, int block, size_t smem_bytes, void (*entry)(void *)
     f.sp = sp;
   }
   for (size_t w = 0; w < M.warps.size(); w++) M.warps[w].first = (int)w * 32;
+  for (int i = n; i < n_slots; i++) { M.fibers[i].done = true; M.fibers[i].warp = i / 32; M.fibers[i].lane = i % 32; M.warps[i / 32].alive--; }
   Fiber boot;
   M.cur = &M.fibers[0];
   M.switches++;
