@@ -146,6 +146,9 @@ def comm_case(rng, backjump):
     kw = dict(world=rng.choice([2, 2, 3, 4]), order=rng.randint(0, 4), prefer_failing=rng.random() < 0.3, n_blocks=rng.choice([1, 1, 2]),
               split_target=rng.choice([1, 8, 32, 128]), slice_clock=rng.choice([0, 2000, 10000, 50000]), general=rng.random() < 0.5)
     world = kw.pop("world")
+    if rng.random() < 0.4:
+        kw["learn"] = True                      # -c under -j N: every rank learns into a pool of its own
+        kw["backjump"] = backjump
     r, w = util.emu_search_comm(m, world, **kw)
     if obj == "ANY":
         ok = r.has_solution == (1 if o.solutions > 0 else 0) and (w is not None) == bool(r.has_solution)

@@ -405,13 +405,14 @@ void run_comm_rebalance(void *arg) {
 }
 }  // namespace
 
+// learn: every rank learns into a nogood pool of its own (-c under -j N; with -DCSOLVE_BJ the ranks back-jump)
 extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefer_failing, int n_blocks, int world,
-                               int split_target, long long slice_clock, int general, emu_result *res, int32_t *solution) {
+                               int split_target, long long slice_clock, int general, int learn, emu_result *res, int32_t *solution) {
   CompiledModel cm;
   int rc = compile_model(*fm, cm, g_err);
   if (rc != 0) return rc;
   DevModel m = cm.host;
-  if (general) { m.lov = 0; m.lovk = 0; }
+  if (general || learn) { m.lov = 0; m.lovk = 0; }
   if (m.objective == CSOLVE_OBJ_ALL) { g_err = "ALL models are dealt by path hash (emu_search with part_count)"; return -110; }
   if (world < 1 || world > COMM_MAX_RANKS) { g_err = "bad world"; return -111; }
   if (prefer_failing && m.lov) prefer_failing = 0;
@@ -427,6 +428,8 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
     SearchCtl ctl; CommBlock blk;
     std::vector<int32_t> stacks, ring_frames, ready, solbuf;
     std::vector<WarpState> ws; std::vector<unsigned long long> wcount;
+    std::vector<int32_t> ng_lits, ng_start, ng_len, ng_watch, ng_watch_n, ng_counters;
+    NogoodPool ng;
   };
   std::vector<Rank> R(world);
   std::vector<int32_t> gprio(cm.prio.begin(), cm.prio.end());      // per GPU in the product; one here (a heuristic)
@@ -437,6 +440,14 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
     r.stacks.assign((size_t)n_warps * (V + 1) * fw, g_fill); r.ring_frames.assign((size_t)ring * fw, g_fill); r.ready.assign(ring, 0);
     r.solbuf.assign((size_t)sol_cap * (V + 1), g_fill);
     r.ws.assign(n_warps, WarpState{-1, 0, 0, 0u}); r.wcount.assign((size_t)n_warps * CNT_WIDTH, 0);
+    memset(&r.ng, 0, sizeof(r.ng));
+    if (learn) {
+      r.ng.cap_ng = 1 << 13; r.ng.cap_lits = 1 << 17; r.ng.cap_w = 512;
+      r.ng_lits.assign(r.ng.cap_lits, 0); r.ng_start.assign(r.ng.cap_ng, 0); r.ng_len.assign(r.ng.cap_ng, 0);
+      r.ng_watch.assign((size_t)V * r.ng.cap_w, -1); r.ng_watch_n.assign(V, 0); r.ng_counters.assign(8, 0);
+      r.ng.lits = r.ng_lits.data(); r.ng.start = r.ng_start.data(); r.ng.len = r.ng_len.data();
+      r.ng.watch = r.ng_watch.data(); r.ng.watch_n = r.ng_watch_n.data(); r.ng.counters = r.ng_counters.data();
+    }
   }
   // rank 0 expands the root (the same loop as search_core's, without batch / sink)
   int32_t *pin = pool_a.data(), *pout = pool_b.data();
@@ -484,8 +495,8 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
   CommLaunch c;
   c.a.assign(world, a0);
   c.n_blocks = n_blocks;
-  const bool sat = !general && search_uses_sat(m, false, order);
-  c.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, false, false, sat, false)));
+  const bool sat = !general && search_uses_sat(m, learn != 0, order);
+  c.fn = reinterpret_cast<void (*)(const SearchArgs)>(const_cast<void *>(search_kernel(m, false, learn != 0, false, sat, false)));
   std::vector<int32_t> scratch(4 + 3 * n_warps, 0);
   c.scratch = scratch.data();
   const int best0 = R[0].ctl.best;
@@ -508,6 +519,7 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
     a.peer_demand = world > 1 ? 1 : 0;
     a.use_sat = sat ? 1 : 0;
     a.gprio = prefer_failing ? gprio.data() : nullptr;
+    if (learn) a.ng = R[r].ng;
     a.slice_cycles = slice_clock > 0 ? slice_clock : LLONG_MAX / 2;
     const int keep_stored = r == 0 ? R[0].ctl.n_stored : 0;
     SearchCtl &ctl = R[r].ctl;
@@ -517,7 +529,7 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
     ctl.signal = stopped ? SIG_STOP : SIG_RUN;
     R[r].blk.busy_epoch = epoch;
   }
-  const size_t smem = search_smem_bytes(m, false, sat);
+  const size_t smem = search_smem_bytes(m, learn != 0, sat);
   R[0].blk.active64 = ((unsigned long long)(unsigned)epoch << 32) | (unsigned)world;      // capi.cu: publish_epoch
   std::vector<int> has_work(world, 1);
   int32_t state[4] = {0, 0, 0, 0};
@@ -572,6 +584,7 @@ extern "C" int emu_search_comm(const csolve_flat_model *fm, int order, int prefe
         g_err = "rank " + std::to_string(r) + " warp " + std::to_string(w) + " left with open frames"; return -100;
       }
     }
+    if (learn) { res->conflicts += R[r].ng_counters[0]; res->conflicts_abandoned += R[r].ng_counters[3] + R[r].ng_counters[4]; res->backjumps += R[r].ng_counters[5]; }
     const int b = R[r].ctl.best;
     if (m.objective == CSOLVE_OBJ_MIN ? b < res->best : (m.objective == CSOLVE_OBJ_MAX ? b > res->best : false)) res->best = b;
   }

@@ -228,6 +228,7 @@ def test_several_gpus_on_one_tree():
             assert r.has_solution == 0 and w is None
             nodes.add((r.nodes, r.cuts))
     assert len(nodes) == 1 and nodes.pop() == tree(m)[1:]
+    jumps = 0
     for n, ratio, seed in ((50, 4.6, 4), (60, 4.26, 3)):
         cnf = I.random_3sat_cnf(n, ratio, seed)
         m = cb.Model(I.cnf_to_csolve(n, cnf))
@@ -235,6 +236,12 @@ def test_several_gpus_on_one_tree():
             for general, pf in ((False, False), (True, True)):
                 r, w = util.emu_search_comm(m, world, split_target=32, slice_clock=10000, general=general, prefer_failing=pf)
                 assert r.has_solution == 1 and satisfies(cnf, m.var_names, w)
+            # -c under -j N: every rank learns into a pool of its own, with and without back-jumping
+            for bj in (False, True):
+                r, w = util.emu_search_comm(m, world, split_target=8, slice_clock=10000, learn=True, backjump=bj)
+                assert r.has_solution == 1 and satisfies(cnf, m.var_names, w) and r.conflicts > 0
+                jumps += r.backjumps
+    assert jumps > 0
 
 
 def test_reference_node_transitions_through_the_emulated_kernels():

@@ -400,17 +400,18 @@ def emu_set_lane_step(step):
         emu_lib(bj).emu_set_lane_step(int(step))
 
 
-def emu_search_comm(model, world, order=0, prefer_failing=False, n_blocks=1, split_target=64, slice_clock=0, general=True):
+def emu_search_comm(model, world, order=0, prefer_failing=False, n_blocks=1, split_target=64, slice_clock=0, general=True,
+                    learn=False, backjump=False):
     """ANY / MIN / MAX model searched by `world` emulated GPUs of a csolve_gpu_comm (shared root frontier on rank 0, claims
     with system-scope atomics, incumbents / "found" through the CommBlocks, a rank running dry served by its peers' warps)
     -> (EmuResult of the whole job, witness or None)"""
-    lib = emu_lib(False)
-    lib.emu_search_comm.argtypes = [C.POINTER(type(model.flat)), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int,
+    lib = emu_lib(backjump)
+    lib.emu_search_comm.argtypes = [C.POINTER(type(model.flat)), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                     C.POINTER(EmuResult), I32P]
     res = EmuResult()
     buf = np.zeros(model.n_vars + 1, np.int32)
     rc = lib.emu_search_comm(C.byref(model.flat), order, 1 if prefer_failing else 0, n_blocks, world, int(split_target),
-                             int(slice_clock), 1 if general else 0, C.byref(res), buf.ctypes.data_as(I32P))
+                             int(slice_clock), 1 if general else 0, 1 if (learn or backjump) else 0, C.byref(res), buf.ctypes.data_as(I32P))
     if rc != 0:
         raise RuntimeError("emu_search_comm: %d %s" % (rc, lib.emu_error().decode()))
     return res, (buf[:model.n_vars].tolist() if res.n_stored else None)
