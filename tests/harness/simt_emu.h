@@ -4,7 +4,7 @@
 // Every CUDA thread of a launch is a fiber with a stack of its own; a fiber runs until it reaches a warp collective
 // (__shfl_sync, __ballot_sync, __syncwarp, ...), a block barrier or a wait (__nanosleep), where the next lane of the
 // warp / the next warp is resumed. Collectives complete when all 32 lanes of the warp have arrived (the kernels only
-// ever use the full mask) and check that every lane arrived from the same call site.
+// ever use the full mask) and check that every lane arrived from the same source line.
 // What this does NOT model: the memory system (every store is visible at once), real concurrency between warps, and
 // lanes running ahead of a missing __syncwarp -- a kernel that passes here has its logic checked, not its fences.
 // Not part of the library, never a fallback: the product has no CPU path (tests/test_abi.py).
@@ -15,7 +15,6 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
-#include <dlfcn.h>
 #include <list>
 #include <utility>
 #include <vector>
@@ -373,11 +372,9 @@ inline void launch(int grid, int block, size_t smem_bytes, void (*entry)(void *)
   }
   for (size_t w = 0; w < M.warps.size(); w++) M.warps[w].first = (int)w * 32;
   for (int i = n; i < n_slots; i++) { M.fibers[i].done = true; M.fibers[i].warp = i / 32; M.fibers[i].lane = i % 32; M.warps[i / 32].alive--; }
-  Fiber boot;
   M.cur = &M.fibers[0];
   M.switches++;
   emu_switch(&M.main_sp, M.fibers[0].sp);
-  (void)boot;
   if (M.live != 0) { fprintf(stderr, "[emu] %d threads never finished\n", M.live); abort(); }
   munmap(stacks, STACK * n);
 }
