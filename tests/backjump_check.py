@@ -12,7 +12,7 @@ import csolve_b200 as cb
 import util
 from csolve_b200 import instances as I
 
-LIMIT_MS = 30000
+LIMIT_MS = 10000
 
 
 def check_model(m, cnf, assignment):

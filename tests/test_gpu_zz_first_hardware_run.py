@@ -30,7 +30,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="first hardware run of the back-jumping kernel instance (see the module docstring)")
 def test_backjump_keeps_status_optimum_and_all_counts():
-    proc = subprocess.run([sys.executable, os.path.join(HERE, "backjump_check.py")], capture_output=True, text=True, timeout=900)
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "backjump_check.py")], capture_output=True, text=True, timeout=420)
     lines = [json.loads(l) for l in proc.stdout.splitlines() if l.startswith("{")]
     sys.stdout.write(proc.stdout[-4000:])
     sys.stderr.write(proc.stderr[-4000:])
